@@ -1,0 +1,171 @@
+/*
+ * mapdit.h — C ABI of libmapdit.so: the B200 (sm_100a) kernels behind the MaP-DiT hot path.
+ *
+ * The reference (ericbill21/map-dit) is pure Python/PyTorch and has no FFI of its own; its
+ * boundary is the Python API (src/models.py:50-56 DIT_MODELS, src/dit.py:70-118 DiT.forward /
+ * forward_with_cfg, diffusion/respace.py + diffusion/gaussian_diffusion.py training_losses /
+ * p_sample_loop).  The Python package mapdit_b200 mirrors that API and calls the entry points
+ * below through ctypes with raw device pointers.  Each entry point names the reference code it
+ * replaces.  Conventions:
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - row-major tensors; `ld*` are leading dimensions in ELEMENTS;
+ *   - `stream` is a cudaStream_t passed as void*; nothing here synchronises or allocates;
+ *   - return 0 on success, negative on error (text via mapdit_last_error()).
+ *   - dtype codes: MAPDIT_F32 = 0, MAPDIT_BF16 = 1.
+ */
+#ifndef MAPDIT_H_
+#define MAPDIT_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MAPDIT_F32 0
+#define MAPDIT_BF16 1
+
+#define MAPDIT_OK 0
+#define MAPDIT_ERR_ARG (-1)
+#define MAPDIT_ERR_CUDA (-2)
+#define MAPDIT_ERR_UNSUPPORTED (-3)
+
+const char* mapdit_last_error(void);
+int mapdit_abi_version(void);
+/* number of kernels launched by this library since load (bench.py's gpu_launches) */
+int64_t mapdit_launch_count(void);
+
+/* ---- K1: weight normalisation --------------------------------------------------------------
+ * Replaces normalize()/chunk_normalize() + the forced in-place normalisation
+ * (src/utils.py:19-34, src/basic/mp_linear.py:37-46,67-75, src/basic/mp_embedding.py:16-22).
+ * For each row r of w[rows, cols]:
+ *   force != 0 : w[r] <- w[r]*sqrt(cols)/(||w[r]||+eps)   (written back in place, train mode)
+ *   eff = w[r]/(||w[r]||+eps) (= normalize(w)/sqrt(cols)), computed from the (forced) row and
+ *   written to any of eff_f32 [rows, cols], eff_bf16 [rows, cols], eff_bf16_t [cols, rows]
+ *   (transposed copy for dgrad).  inv_norm [rows] (optional) receives 1/(||w||+eps) of the
+ *   row that eff was computed from (needed by the backward).                                  */
+int mapdit_weight_norm_fwd(float* w, int rows, int cols, float eps, int force, float* eff_f32,
+                           void* eff_bf16, void* eff_bf16_t, float* inv_norm, void* stream);
+/* Backward of eff = v/(||v||+eps) per row: given G = dL/d eff [rows, cols]
+ * and the (forced) weights v, grad_v = (G - v (v·G)/(r (r+eps)))/(r+eps); accumulate==0 overwrites. */
+int mapdit_weight_norm_bwd(const float* v, const float* g_eff, float* grad_v, int rows, int cols,
+                           float eps, int accumulate, void* stream);
+
+/* ---- fp32 GEMM (mode a: CUDA-core FFMA, strided) --------------------------------------------
+ * C[m,n] (+)= sum_k A(m,k) * B(n,k), A element (m,k) at a[m*sam + k*sak], B element (n,k) at
+ * b[n*sbn + k*sbk]; C row-major with leading dimension ldc.  Replaces F.linear
+ * (src/basic/mp_linear.py:46,75) and its autograd transposes in the fp32 parity mode.         */
+int mapdit_gemm_f32(const float* a, int64_t sam, int64_t sak, const float* b, int64_t sbn, int64_t sbk,
+                    float* c, int64_t ldc, int m, int n, int k, int accumulate, void* stream);
+
+/* ---- K2/K3: bf16 tcgen05 GEMM with fused epilogues ------------------------------------------
+ * D = A[M,K] · B[N,K]^T, bf16 operands (K-major, row-major with lda/ldb), fp32 accumulation in
+ * TMEM, TMA-fed, persistent.  Epilogues fuse the reference's elementwise neighbours:          */
+#define MAPDIT_EPI_STORE 0      /* out = acc                                   (F.linear)                         */
+#define MAPDIT_EPI_QKNORM 1     /* q,k heads L2-normalised in registers        (src/layers/attention.py:43-45)    */
+#define MAPDIT_EPI_MPSILU 2     /* out = silu(acc)/0.596 (+ optional pre-act)  (src/basic/mp_silu.py:7)           */
+#define MAPDIT_EPI_RESID_MOD 3  /* x' = mp_sum(x, gate*acc, .3); h = modulate(x', shift, scale, g)
+                                   (src/blocks/dit_block.py:35-36, src/utils.py:11-16)                            */
+#define MAPDIT_EPI_RESID 4      /* x' = mp_sum(x, gate*acc, .3) only                                              */
+
+typedef struct mapdit_gemm_args {
+  const void* a;   /* bf16 [M, K] */
+  const void* b;   /* bf16 [N, K] */
+  void* out;       /* bf16 or f32 [M, N] (EPI_RESID*: the new residual stream x') */
+  void* out2;      /* EPI_MPSILU: optional bf16 pre-activation [M,N]; EPI_RESID_MOD: h [M,N] bf16 */
+  const void* resid;  /* EPI_RESID*: bf16 x [M, N] (may alias out) */
+  const float* gate;  /* EPI_RESID*: per-sample fp32 [n_samples, ldmod] column slice start */
+  const float* shift; /* EPI_RESID_MOD */
+  const float* scale; /* EPI_RESID_MOD */
+  const float* gain;  /* EPI_RESID_MOD: device scalar g (blocks.i.gain_*) */
+  int64_t lda, ldb, ldo, ldmod;
+  int m, n, k;
+  int tokens;      /* rows per sample (sample index = row / tokens) */
+  int head_dim;    /* EPI_QKNORM */
+  int qk_cols;     /* EPI_QKNORM: columns [0, qk_cols) are q|k heads, the rest (v) is stored as is */
+  int epilogue;
+  int out_dtype;   /* MAPDIT_BF16 or MAPDIT_F32 (EPI_STORE only) */
+  float eps;
+} mapdit_gemm_args;
+
+int mapdit_gemm_bf16(const mapdit_gemm_args* args, void* stream);
+int mapdit_sizeof_gemm_args(void); /* lets a binding check its struct mirror */
+
+/* ---- K3 standalone elementwise ops (fp32 mode and fallbacks); dtype = activation dtype ------ */
+/* h = modulate(x, shift, scale, g) = lerp(x*scale, shift, g)/sqrt((1-g)^2+g^2)  (src/utils.py:11-16) */
+int mapdit_modulate_fwd(const void* x, void* h, const float* shift, const float* scale, const float* gain,
+                        int64_t ldmod, int m, int d, int tokens, int dtype, void* stream);
+/* xout = mp_sum(x, gate*y, 0.3) (src/blocks/dit_block.py:35-36) */
+int mapdit_resid_fwd(const void* x, const void* y, void* xout, const float* gate, int64_t ldmod, int m, int d,
+                     int tokens, int dtype, void* stream);
+/* y = silu(x)/0.596 (src/basic/mp_silu.py:7); in/out dtypes independent */
+int mapdit_mp_silu_fwd(const void* x, void* y, int64_t n, int in_dtype, int out_dtype, void* stream);
+/* in-place L2 normalisation of the q and k heads of qkv[M, 3D] (src/layers/attention.py:43-45) */
+int mapdit_qk_normalize(void* qkv, int m, int d, int head_dim, float eps, int dtype, void* stream);
+/* dtype casts */
+int mapdit_cast(const void* src, void* dst, int64_t n, int src_dtype, int dst_dtype, void* stream);
+
+/* ---- K4: cosine attention --------------------------------------------------------------------
+ * o[M, D] = merge_heads(softmax(q^ k^T / sqrt(hd)) v) for qkv[M, 3D] whose q,k heads are already
+ * normalised (src/layers/attention.py:37-49).  f32: CUDA-core flash kernel (mode a);
+ * bf16: tcgen05/TMEM kernel.                                                                   */
+int mapdit_cos_attn_fwd(const void* qkv, void* o, int n_samples, int tokens, int heads, int head_dim,
+                        int dtype, void* stream);
+
+/* ---- embedders / final layer ------------------------------------------------------------------ */
+/* x0 = mp_sum(patchify(x)|1 · Wx^T, pos, .5) (src/dit.py:81-84); optional h = modulate(x0,...).   */
+int mapdit_patch_embed(const float* x, const float* wx_eff, const float* pos, void* x0, void* h,
+                       const float* shift, const float* scale, const float* gain, int64_t ldmod,
+                       int n_samples, int channels, int input_size, int patch, int d, int dtype, void* stream);
+/* e[n, j] = sqrt(2) cos(fl(fl(t*scale_j)+shift_j)) (src/blocks/timestep_embedder.py:18-21) */
+int mapdit_fourier(const int64_t* t, const float* scale, const float* shift, float* e, int n, int channels, void* stream);
+/* out[n,:] = normalize(table[idx[n],:]) (src/basic/mp_embedding.py:21-24); drop: idx -> null_idx where mask */
+int mapdit_embed_rows(const int64_t* idx, const uint8_t* drop_mask, int64_t null_idx, const float* table,
+                      float* out, int n, int d, float eps, void* stream);
+/* c = mp_sum(a, b, 0.5) (src/dit.py:88) and cs = silu(c)/0.596 in f32 and/or bf16 (nullable) */
+int mapdit_cond_combine(const float* a, const float* b, float* c, float* cs_f32, void* cs_bf16, int64_t n, void* stream);
+/* s[n] = sigmoid((c[n,:]·W_eff^T)·ref/sqrt(adim)) (src/blocks/final_layer.py:12-22) */
+int mapdit_mp_scale(const float* c, const float* w_eff, const float* ref, float* s, int n, int d, int adim, void* stream);
+/* out[N, 2C, H, W] = cat(unpatchify(mean*s_mu), unpatchify(sigma*s_sigma)) from lin[M, 2 p^2 C]
+ * (src/blocks/final_layer.py:57-59, src/dit.py:95-100) */
+int mapdit_final_unpatchify(const void* lin, const float* s_mu, const float* s_sigma, float* out, int n_samples,
+                            int channels, int input_size, int patch, int dtype, void* stream);
+/* classifier-free guidance combine (src/dit.py:113-118), in place on out[2n, 2C, H, W] */
+int mapdit_cfg_combine(float* out, int n_half, int channels, int hw, float cfg_scale, void* stream);
+
+/* ---- diffusion coefficient table (fp32 [8, steps], built on the host from the float64 tables of
+ * diffusion/gaussian_diffusion.py:166-201 and cast to fp32 exactly where the reference casts,
+ * :870): rows 0 sqrt_alphas_cumprod, 1 sqrt_one_minus_alphas_cumprod, 2 sqrt_recip_alphas_cumprod,
+ * 3 sqrt_recipm1_alphas_cumprod, 4 posterior_mean_coef1, 5 posterior_mean_coef2,
+ * 6 posterior_log_variance_clipped, 7 log(betas).                                              */
+#define MAPDIT_DIFF_ROWS 8
+
+/* ---- K5: fused diffusion step (diffusion/gaussian_diffusion.py:285-293,320-323,334-339,410-416)
+ * t: int64 [N] respaced step index per sample.  sample may alias x.  pred_xstart nullable.     */
+int mapdit_diffusion_step(const float* model_out, const float* x, const float* noise, const int64_t* t,
+                          const float* tables, int steps, float* sample, float* pred_xstart, int n_samples,
+                          int channels, int hw, int clip_denoised, void* stream);
+/* ---- K6: fused q_sample + loss (diffusion/gaussian_diffusion.py:215-230,682-713,747-783;
+ * diffusion/diffusion_utils.py:10-36,62-88).                                                    */
+int mapdit_q_sample(const float* x0, const float* noise, const int64_t* t, const float* tables, int steps,
+                    float* x_t, int n_samples, int chw, void* stream);
+/* loss[n] = mse[n] + vb[n] (outputs nullable).  grad_out (nullable) [N, 2C, H, W]: eps channels receive
+ * gs_eps[n] * d mse[n]/d eps, variance channels gs_var[n] * d vb[n]/d v (gs_* nullable = 1).       */
+int mapdit_loss_fwd_bwd(const float* model_out, const float* x0, const float* x_t, const float* noise,
+                        const int64_t* t, const float* tables, int steps, float* loss, float* mse, float* vb,
+                        float* grad_out, const float* gs_eps, const float* gs_var, int n_samples, int channels,
+                        int hw, void* stream);
+/* p_mean_variance as separate tensors (diffusion/gaussian_diffusion.py:254-332) */
+int mapdit_p_mean_variance(const float* model_out, const float* x, const int64_t* t, const float* tables, int steps,
+                           float* mean, float* variance, float* log_variance, float* pred_xstart, int n_samples,
+                           int channels, int hw, int clip_denoised, void* stream);
+/* posterior mean c1*x0 + c2*x_t (:238-241) and sample = mean + [t!=0] exp(.5 logvar) noise (:410-416) */
+int mapdit_posterior_mean(const float* x0, const float* x, const int64_t* t, const float* tables, int steps,
+                          float* mean, int n_samples, int chw, void* stream);
+int mapdit_noise_add(const float* mean, const float* log_variance, const float* noise, const int64_t* t,
+                     float* sample, int n_samples, int chw, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAPDIT_H_ */

@@ -1,0 +1,80 @@
+"""ctypes binding of libmapdit.so (C ABI declared in include/mapdit.h).
+
+There is no CPU fallback: importing the ops without the built library raises.  Build it with
+``python -m mapdit_b200.build`` (or ``__graft_entry__.build()``).
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmapdit.so")
+
+F32, BF16 = 0, 1
+EPI_STORE, EPI_QKNORM, EPI_MPSILU, EPI_RESID_MOD, EPI_RESID = 0, 1, 2, 3, 4
+
+_p, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
+
+
+class GemmArgs(C.Structure):
+    """mirror of mapdit_gemm_args (include/mapdit.h)"""
+    _fields_ = [("a", _p), ("b", _p), ("out", _p), ("out2", _p), ("resid", _p), ("gate", _p), ("shift", _p),
+                ("scale", _p), ("gain", _p), ("lda", _i64), ("ldb", _i64), ("ldo", _i64), ("ldmod", _i64),
+                ("m", _i), ("n", _i), ("k", _i), ("tokens", _i), ("head_dim", _i), ("qk_cols", _i),
+                ("epilogue", _i), ("out_dtype", _i), ("eps", _f)]
+
+
+SIGNATURES = {
+    "mapdit_weight_norm_fwd": [_p, _i, _i, _f, _i, _p, _p, _p, _p, _p],
+    "mapdit_weight_norm_bwd": [_p, _p, _p, _i, _i, _f, _i, _p],
+    "mapdit_gemm_f32": [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i, _i, _i, _i, _p],
+    "mapdit_gemm_bf16": [C.POINTER(GemmArgs), _p],
+    "mapdit_modulate_fwd": [_p, _p, _p, _p, _p, _i64, _i, _i, _i, _i, _p],
+    "mapdit_resid_fwd": [_p, _p, _p, _p, _i64, _i, _i, _i, _i, _p],
+    "mapdit_mp_silu_fwd": [_p, _p, _i64, _i, _i, _p],
+    "mapdit_qk_normalize": [_p, _i, _i, _i, _f, _i, _p],
+    "mapdit_cast": [_p, _p, _i64, _i, _i, _p],
+    "mapdit_cos_attn_fwd": [_p, _p, _i, _i, _i, _i, _i, _p],
+    "mapdit_patch_embed": [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _i, _i, _i, _i, _p],
+    "mapdit_fourier": [_p, _p, _p, _p, _i, _i, _p],
+    "mapdit_embed_rows": [_p, _p, _i64, _p, _p, _i, _i, _f, _p],
+    "mapdit_cond_combine": [_p, _p, _p, _p, _p, _i64, _p],
+    "mapdit_mp_scale": [_p, _p, _p, _p, _i, _i, _i, _p],
+    "mapdit_final_unpatchify": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
+    "mapdit_cfg_combine": [_p, _i, _i, _i, _f, _p],
+    "mapdit_diffusion_step": [_p, _p, _p, _p, _p, _i, _p, _p, _i, _i, _i, _i, _p],
+    "mapdit_q_sample": [_p, _p, _p, _p, _i, _p, _i, _i, _p],
+    "mapdit_loss_fwd_bwd": [_p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
+    "mapdit_p_mean_variance": [_p, _p, _p, _p, _i, _p, _p, _p, _p, _i, _i, _i, _i, _p],
+    "mapdit_posterior_mean": [_p, _p, _p, _p, _i, _p, _i, _i, _p],
+    "mapdit_noise_add": [_p, _p, _p, _p, _p, _i, _i, _p],
+}
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"mapdit_b200: {LIB_PATH} is missing — the CUDA kernels are the only implementation "
+                "(no CPU fallback). Build with `python -m mapdit_b200.build`.")
+        L = C.CDLL(LIB_PATH)
+        for name, args in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.argtypes = args
+            fn.restype = _i
+        L.mapdit_last_error.restype = C.c_char_p
+        L.mapdit_abi_version.restype = _i
+        L.mapdit_launch_count.restype = _i64
+        _lib = L
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        raise RuntimeError(f"libmapdit {what} failed ({rc}): {lib().mapdit_last_error().decode()}")
+
+
+def launch_count() -> int:
+    return int(lib().mapdit_launch_count())

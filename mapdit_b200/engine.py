@@ -1,0 +1,216 @@
+"""Kernel schedule of one DiT forward (and, in train mode, the matching backward).
+
+HBM layout: token-major activations [M = N*T, features] in the activation dtype (bf16 on the
+tcgen05 path, fp32 in parity mode); per-sample conditioning [N, *] always fp32; effective
+(normalised) weights cached per parameter version, the modulation weights of all blocks plus the
+final layer concatenated so one GEMM produces every shift/scale/gate of the step.
+
+Reference order of operations: src/dit.py:70-105 -> src/blocks/dit_block.py:32-37 ->
+src/layers/attention.py:27-51, src/layers/mlp.py:18-25 -> src/blocks/final_layer.py:53-59.
+"""
+import torch
+
+from . import _lib, ops
+
+
+class _Weights:
+    """effective weights W_row/(||W_row||+eps) (src/basic/mp_linear.py:42-46) in the layouts the kernels read."""
+    pass
+
+
+class Engine:
+    def __init__(self, model):
+        self.m = model
+        self._w = {}       # mode -> _Weights
+        self._w_sig = {}   # mode -> signature of parameter versions
+        self._ws = {}      # (N, mode, device) -> workspace dict
+        self._dirty = True
+
+    # ------------------------------------------------------------------ parameters
+    def _linear_params(self):
+        m = self.m
+        ps = [m.x_embedder.weight, m.t_embedder.mlp.net[0].weight, m.t_embedder.mlp.net[2].weight,
+              m.y_embedder.embedding.weight]
+        for b in m.blocks:
+            ps += [b.attn.qkv_proj.weight, b.attn.out_proj.weight, b.mlp.net[0].weight, b.mlp.net[2].weight,
+                   b.modulation[1].weight]
+        f = m.final_layer
+        ps += [f.linear.weight, f.modulation[1].weight, f.mean_scale.linear.weight, f.sigma_scale.linear.weight]
+        return ps
+
+    def _signature(self):
+        ps = self._linear_params()
+        return (sum(p._version for p in ps), tuple(p.data_ptr() for p in ps[:3]), ps[0].device)
+
+    def invalidate(self):
+        self._dirty = True
+
+    def weights(self, mode, train):
+        """(Re)build the effective weights.  Train mode always re-normalises, writing the forced
+        normalisation back into the parameters first (src/basic/mp_linear.py:37-40)."""
+        sig = self._signature()
+        if not train and not self._dirty and self._w_sig.get(mode) == sig and mode in self._w:
+            return self._w[mode]
+        m = self.m
+        dev = m.x_embedder.weight.device
+        D, L = m.hidden_size, m.depth
+        wdt = torch.bfloat16 if mode == "bf16" else torch.float32
+        W = self._w.get(mode)
+        if W is None or W.device != dev:
+            W = _Weights()
+            W.device = dev
+            f32 = dict(device=dev, dtype=torch.float32)
+            wd = dict(device=dev, dtype=wdt)
+            W.wx = torch.empty_like(m.x_embedder.weight, **f32)
+            W.wt1 = torch.empty(D, 256, **f32)
+            W.wt2 = torch.empty(D, D, **f32)
+            W.wmu = torch.empty(8, D, **f32)
+            W.wsg = torch.empty(8, D, **f32)
+            W.modw = 6 * D
+            W.mod_total = L * 6 * D + 2 * D
+            W.wmod = torch.empty(W.mod_total, D, **wd)
+            Hm = m.blocks[0].mlp.hidden_dim
+            W.wqkv = [torch.empty(3 * D, D, **wd) for _ in range(L)]
+            W.wo = [torch.empty(D, D, **wd) for _ in range(L)]
+            W.w1 = [torch.empty(Hm, D, **wd) for _ in range(L)]
+            W.w2 = [torch.empty(D, Hm, **wd) for _ in range(L)]
+            W.wfl = torch.empty_like(m.final_layer.linear.weight, **wd)
+            self._w[mode] = W
+        force = bool(train)
+
+        def norm(p, out):
+            kw = {"eff_bf16": out} if out.dtype == torch.bfloat16 else {"eff_f32": out}
+            ops.weight_norm_fwd(p.data, force=force, **kw)
+
+        norm(m.x_embedder.weight, W.wx)
+        norm(m.t_embedder.mlp.net[0].weight, W.wt1)
+        norm(m.t_embedder.mlp.net[2].weight, W.wt2)
+        if force:  # the embedding table is normalised in place too (src/basic/mp_embedding.py:16-19)
+            ops.weight_norm_fwd(m.y_embedder.embedding.weight.data, force=True)
+        for i, b in enumerate(m.blocks):
+            norm(b.attn.qkv_proj.weight, W.wqkv[i])
+            norm(b.attn.out_proj.weight, W.wo[i])
+            norm(b.mlp.net[0].weight, W.w1[i])
+            norm(b.mlp.net[2].weight, W.w2[i])
+            norm(b.modulation[1].weight, W.wmod[i * W.modw:(i + 1) * W.modw])
+        f = m.final_layer
+        norm(f.modulation[1].weight, W.wmod[L * W.modw:])
+        norm(f.linear.weight, W.wfl)
+        norm(f.mean_scale.linear.weight, W.wmu)
+        norm(f.sigma_scale.linear.weight, W.wsg)
+        self._w_sig[mode] = self._signature()
+        self._dirty = bool(train)  # forced WN rewrote the parameters without bumping versions
+        return W
+
+    # ------------------------------------------------------------------ workspaces
+    def workspace(self, N, mode, dev):
+        key = (N, mode, str(dev))
+        ws = self._ws.get(key)
+        if ws is not None:
+            return ws
+        m = self.m
+        D, T = m.hidden_size, (m.input_size // m.patch_size) ** 2
+        M = N * T
+        Hm = m.blocks[0].mlp.hidden_dim
+        adt = torch.bfloat16 if mode == "bf16" else torch.float32
+        a = dict(device=dev, dtype=adt)
+        f = dict(device=dev, dtype=torch.float32)
+        ppc2 = m.final_layer.linear.weight.shape[0]
+        ws = dict(
+            x=torch.empty(M, D, **a), h=torch.empty(M, D, **a), qkv=torch.empty(M, 3 * D, **a), o=torch.empty(M, D, **a),
+            u=torch.empty(M, Hm, **a), lin=torch.empty(M, ppc2, **a),
+            e=torch.empty(N, 256, **f), t1=torch.empty(N, D, **f), t1s=torch.empty(N, D, **f), temb=torch.empty(N, D, **f),
+            yemb=torch.empty(N, D, **f), c=torch.empty(N, D, **f), cs=torch.empty(N, D, **f),
+            cs16=torch.empty(N, D, device=dev, dtype=torch.bfloat16),
+            mods=torch.empty(N, m.depth * 6 * D + 2 * D, **f), smu=torch.empty(N, **f), ssg=torch.empty(N, **f),
+        )
+        if mode == "fp32":
+            ws["tmp"] = torch.empty(M, D, **a)
+        self._ws[key] = ws
+        return ws
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, x, t, y, train=False, drop_mask=None):
+        m = self.m
+        if not x.is_cuda:
+            raise RuntimeError("mapdit_b200.DiT runs on CUDA only (hand-written sm_100a kernels, no CPU fallback)")
+        mode = m.compute_dtype
+        if torch.is_grad_enabled() and any(p.requires_grad for p in m.parameters()) and train:
+            from .autograd import dit_forward_autograd
+            return dit_forward_autograd(self, x, t, y, drop_mask)
+        return self._forward_impl(x, t, y, train, drop_mask, mode, save=None)
+
+    def _forward_impl(self, x, t, y, train, drop_mask, mode, save):
+        m = self.m
+        N = x.shape[0]
+        dev = x.device
+        D, L, T = m.hidden_size, m.depth, (m.input_size // m.patch_size) ** 2
+        H, hd = m.num_heads, m.hidden_size // m.num_heads
+        x = x.contiguous().float()
+        t = t.contiguous().to(torch.int64)
+        y = y.contiguous().to(torch.int64)
+        W = self.weights(mode, train)
+        ws = self.workspace(N, mode, dev)
+        ld = ws["mods"].shape[1]
+        bf = mode == "bf16"
+
+        # ---- conditioning (fp32; src/dit.py:86-88, timestep_embedder.py:18-43, label_embedder.py:29-34)
+        ops.fourier(t, m.t_embedder.embedding.scale, m.t_embedder.embedding.shift, ws["e"])
+        ops.gemm_f32(ws["e"], W.wt1, out=ws["t1"])
+        ops.mp_silu(ws["t1"], ws["t1s"])
+        ops.gemm_f32(ws["t1s"], W.wt2, out=ws["temb"])
+        mask = None
+        if train and m.y_embedder.dropout_prob > 0:
+            if drop_mask is None:
+                drop_mask = torch.rand(N, device=dev) < m.y_embedder.dropout_prob
+            mask = drop_mask.to(torch.uint8).contiguous()
+        ops.embed_rows(y, mask, m.num_classes, m.y_embedder.embedding.weight.data, ws["yemb"])
+        ops.cond_combine(ws["temb"], ws["yemb"], ws["c"], ws["cs"], ws["cs16"])
+        if bf:
+            ops.gemm_bf16(ws["cs16"], W.wmod, ws["mods"])
+        else:
+            ops.gemm_f32(ws["cs"], W.wmod, out=ws["mods"])
+        f = m.final_layer
+        ops.mp_scale(ws["c"], W.wmu, f.mean_scale.reference.data, ws["smu"])
+        ops.mp_scale(ws["c"], W.wsg, f.sigma_scale.reference.data, ws["ssg"])
+
+        mods = ws["mods"]
+
+        def mod(i, j):  # column slice j of block i's modulation output
+            return mods[:, i * 6 * D + j * D:]
+
+        blk = m.blocks
+        # ---- patch embed + first modulate (src/dit.py:81-84)
+        ops.patch_embed(x, W.wx, m.pos_embed, ws["x"], ws["h"], mod(0, 0), mod(0, 1), blk[0].gain_msa.data, ld, m.patch_size)
+        X, Hb = ws["x"], ws["h"]
+        for i in range(L):
+            nxt_shift, nxt_scale, nxt_gain = ((mod(i + 1, 0), mod(i + 1, 1), blk[i + 1].gain_msa.data) if i + 1 < L else
+                                              (mods[:, L * 6 * D:], mods[:, L * 6 * D + D:], f.gain_mod.data))
+            if bf:
+                ops.gemm_bf16(Hb, W.wqkv[i], ws["qkv"], epilogue=_lib.EPI_QKNORM, tokens=T, head_dim=hd, qk_cols=2 * D)
+                ops.cos_attn(ws["qkv"], ws["o"], N, T, H, hd)
+                ops.gemm_bf16(ws["o"], W.wo[i], X, epilogue=_lib.EPI_RESID_MOD, out2=Hb, resid=X, gate=mod(i, 2),
+                              shift=mod(i, 3), scale=mod(i, 4), gain=blk[i].gain_mlp.data, ldmod=ld, tokens=T)
+                ops.gemm_bf16(Hb, W.w1[i], ws["u"], epilogue=_lib.EPI_MPSILU)
+                ops.gemm_bf16(ws["u"], W.w2[i], X, epilogue=_lib.EPI_RESID_MOD, out2=Hb, resid=X, gate=mod(i, 5),
+                              shift=nxt_shift, scale=nxt_scale, gain=nxt_gain, ldmod=ld, tokens=T)
+            else:
+                ops.gemm_f32(Hb, W.wqkv[i], out=ws["qkv"])
+                ops.qk_normalize(ws["qkv"], D, hd)
+                ops.cos_attn(ws["qkv"], ws["o"], N, T, H, hd)
+                ops.gemm_f32(ws["o"], W.wo[i], out=ws["tmp"])
+                ops.resid(X, ws["tmp"], X, mod(i, 2), ld, T)
+                ops.modulate(X, Hb, mod(i, 3), mod(i, 4), blk[i].gain_mlp.data, ld, T)
+                ops.gemm_f32(Hb, W.w1[i], out=ws["u"])
+                ops.mp_silu(ws["u"], ws["u"])
+                ops.gemm_f32(ws["u"], W.w2[i], out=ws["tmp"])
+                ops.resid(X, ws["tmp"], X, mod(i, 5), ld, T)
+                ops.modulate(X, Hb, nxt_shift, nxt_scale, nxt_gain, ld, T)
+        # ---- final layer (src/blocks/final_layer.py:53-59, src/dit.py:95-100)
+        if bf:
+            ops.gemm_bf16(Hb, W.wfl, ws["lin"])
+        else:
+            ops.gemm_f32(Hb, W.wfl, out=ws["lin"])
+        out = torch.empty(N, 2 * m.in_channels, m.input_size, m.input_size, device=dev, dtype=torch.float32)
+        ops.final_unpatchify(ws["lin"], ws["smu"], ws["ssg"], out, m.patch_size)
+        return out

@@ -1,0 +1,186 @@
+"""Torch-tensor wrappers over the C ABI (device pointers + current CUDA stream).
+
+Each wrapper validates device/dtype/contiguity and then calls the kernel; none of them has a
+PyTorch fallback.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import BF16, F32, GemmArgs, check, lib
+
+EPS = 1e-4  # src/utils.py:19 normalize eps
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError(f"unsupported dtype {t.dtype}")
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    assert t.is_cuda, "mapdit_b200 ops need CUDA tensors (there is no CPU path)"
+    return C.c_void_p(t.data_ptr())
+
+
+def weight_norm_fwd(w, force=False, eff_f32=None, eff_bf16=None, eff_bf16_t=None, inv_norm=None):
+    assert w.dtype == torch.float32 and w.is_contiguous() and w.dim() == 2
+    rows, cols = w.shape
+    for e in (eff_f32, eff_bf16, eff_bf16_t):
+        assert e is None or (e.is_contiguous() and e.numel() == w.numel())
+    check(lib().mapdit_weight_norm_fwd(_ptr(w), rows, cols, EPS, int(force), _ptr(eff_f32), _ptr(eff_bf16),
+                                       _ptr(eff_bf16_t), _ptr(inv_norm), _stream()), "weight_norm_fwd")
+
+
+def weight_norm_bwd(v, g_eff, grad_v, accumulate=False):
+    rows, cols = v.shape
+    assert v.is_contiguous() and g_eff.is_contiguous() and grad_v.is_contiguous()
+    check(lib().mapdit_weight_norm_bwd(_ptr(v), _ptr(g_eff), _ptr(grad_v), rows, cols, EPS, int(accumulate), _stream()),
+          "weight_norm_bwd")
+
+
+def gemm_f32(a, b, out=None, trans_a=False, trans_b=False, accumulate=False):
+    """out[m,n] (+)= sum_k A(m,k) B(n,k).  a is [m,k] (or [k,m] with trans_a), b is [n,k] (or [k,n] with
+    trans_b); 2-D fp32 with arbitrary strides."""
+    assert a.dtype == torch.float32 and b.dtype == torch.float32 and a.dim() == 2 and b.dim() == 2
+    if trans_a:
+        a = a.t()
+    if trans_b:
+        b = b.t()
+    m, k = a.shape
+    n, k2 = b.shape
+    assert k == k2, (a.shape, b.shape)
+    if out is None:
+        out = torch.empty(m, n, device=a.device, dtype=torch.float32)
+    assert out.stride(1) == 1
+    check(lib().mapdit_gemm_f32(_ptr(a), a.stride(0), a.stride(1), _ptr(b), b.stride(0), b.stride(1), _ptr(out),
+                                out.stride(0), m, n, k, int(accumulate), _stream()), "gemm_f32")
+    return out
+
+
+def gemm_bf16(a, b, out, epilogue=_lib.EPI_STORE, out2=None, resid=None, gate=None, shift=None, scale=None, gain=None,
+              ldmod=0, tokens=1, head_dim=0, qk_cols=0):
+    """out = epilogue(a[M,K] @ b[N,K]^T) on the tcgen05 path (bf16 operands, fp32 accumulate)."""
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
+    assert a.stride(1) == 1 and b.stride(1) == 1 and out.stride(1) == 1
+    m, k = a.shape
+    n, k2 = b.shape
+    assert k == k2 and out.shape[0] == m and out.shape[1] == n
+    args = GemmArgs(a=a.data_ptr(), b=b.data_ptr(), out=out.data_ptr(),
+                    out2=out2.data_ptr() if out2 is not None else None,
+                    resid=resid.data_ptr() if resid is not None else None,
+                    gate=gate.data_ptr() if gate is not None else None,
+                    shift=shift.data_ptr() if shift is not None else None,
+                    scale=scale.data_ptr() if scale is not None else None,
+                    gain=gain.data_ptr() if gain is not None else None,
+                    lda=a.stride(0), ldb=b.stride(0), ldo=out.stride(0), ldmod=ldmod, m=m, n=n, k=k, tokens=tokens,
+                    head_dim=head_dim, qk_cols=qk_cols, epilogue=epilogue, out_dtype=_dt(out), eps=EPS)
+    check(lib().mapdit_gemm_bf16(C.byref(args), _stream()), "gemm_bf16")
+    return out
+
+
+def modulate(x, h, shift, scale, gain, ldmod, tokens):
+    m, d = x.shape
+    check(lib().mapdit_modulate_fwd(_ptr(x), _ptr(h), _ptr(shift), _ptr(scale), _ptr(gain), ldmod, m, d, tokens, _dt(x),
+                                    _stream()), "modulate_fwd")
+
+
+def resid(x, y, xout, gate, ldmod, tokens):
+    m, d = x.shape
+    check(lib().mapdit_resid_fwd(_ptr(x), _ptr(y), _ptr(xout), _ptr(gate), ldmod, m, d, tokens, _dt(x), _stream()), "resid_fwd")
+
+
+def mp_silu(x, y):
+    check(lib().mapdit_mp_silu_fwd(_ptr(x), _ptr(y), x.numel(), _dt(x), _dt(y), _stream()), "mp_silu_fwd")
+
+
+def qk_normalize(qkv, d, head_dim):
+    check(lib().mapdit_qk_normalize(_ptr(qkv), qkv.shape[0], d, head_dim, EPS, _dt(qkv), _stream()), "qk_normalize")
+
+
+def cast(src, dst):
+    check(lib().mapdit_cast(_ptr(src), _ptr(dst), src.numel(), _dt(src), _dt(dst), _stream()), "cast")
+
+
+def cos_attn(qkv, o, n_samples, tokens, heads, head_dim):
+    check(lib().mapdit_cos_attn_fwd(_ptr(qkv), _ptr(o), n_samples, tokens, heads, head_dim, _dt(qkv), _stream()), "cos_attn_fwd")
+
+
+def patch_embed(x, wx_eff, pos, x0, h, shift, scale, gain, ldmod, patch):
+    n, c, s, _ = x.shape
+    d = wx_eff.shape[0]
+    check(lib().mapdit_patch_embed(_ptr(x), _ptr(wx_eff), _ptr(pos), _ptr(x0), _ptr(h), _ptr(shift), _ptr(scale), _ptr(gain),
+                                   ldmod, n, c, s, patch, d, _dt(x0), _stream()), "patch_embed")
+
+
+def fourier(t, scale, shift, e):
+    check(lib().mapdit_fourier(_ptr(t), _ptr(scale), _ptr(shift), _ptr(e), t.shape[0], scale.shape[0], _stream()), "fourier")
+
+
+def embed_rows(idx, drop_mask, null_idx, table, out):
+    check(lib().mapdit_embed_rows(_ptr(idx), _ptr(drop_mask), null_idx, _ptr(table), _ptr(out), idx.shape[0], table.shape[1],
+                                  EPS, _stream()), "embed_rows")
+
+
+def cond_combine(a, b, c, cs_f32, cs_bf16):
+    check(lib().mapdit_cond_combine(_ptr(a), _ptr(b), _ptr(c), _ptr(cs_f32), _ptr(cs_bf16), a.numel(), _stream()), "cond_combine")
+
+
+def mp_scale(c, w_eff, ref, s):
+    check(lib().mapdit_mp_scale(_ptr(c), _ptr(w_eff), _ptr(ref), _ptr(s), c.shape[0], c.shape[1], ref.shape[0], _stream()), "mp_scale")
+
+
+def final_unpatchify(lin, s_mu, s_sigma, out, patch):
+    n, c2, s, _ = out.shape
+    check(lib().mapdit_final_unpatchify(_ptr(lin), _ptr(s_mu), _ptr(s_sigma), _ptr(out), n, c2 // 2, s, patch, _dt(lin), _stream()),
+          "final_unpatchify")
+
+
+def cfg_combine(out, in_channels, cfg_scale):
+    n2, c2, h, w = out.shape
+    assert c2 == 2 * in_channels and out.is_contiguous()
+    check(lib().mapdit_cfg_combine(_ptr(out), n2 // 2, in_channels, h * w, float(cfg_scale), _stream()), "cfg_combine")
+
+
+def diffusion_step(model_out, x, noise, t, tables, sample, pred_xstart, clip_denoised):
+    n, c, h, w = x.shape
+    check(lib().mapdit_diffusion_step(_ptr(model_out), _ptr(x), _ptr(noise), _ptr(t), _ptr(tables), tables.shape[1], _ptr(sample),
+                                      _ptr(pred_xstart), n, c, h * w, int(clip_denoised), _stream()), "diffusion_step")
+
+
+def q_sample(x0, noise, t, tables, x_t):
+    n = x0.shape[0]
+    check(lib().mapdit_q_sample(_ptr(x0), _ptr(noise), _ptr(t), _ptr(tables), tables.shape[1], _ptr(x_t), n, x0[0].numel(), _stream()),
+          "q_sample")
+
+
+def loss_fwd_bwd(model_out, x0, x_t, noise, t, tables, loss, mse, vb, grad_out, gs_eps, gs_var):
+    n, c, h, w = x0.shape
+    check(lib().mapdit_loss_fwd_bwd(_ptr(model_out), _ptr(x0), _ptr(x_t), _ptr(noise), _ptr(t), _ptr(tables), tables.shape[1],
+                                    _ptr(loss), _ptr(mse), _ptr(vb), _ptr(grad_out), _ptr(gs_eps), _ptr(gs_var), n, c, h * w,
+                                    _stream()), "loss_fwd_bwd")
+
+
+def p_mean_variance(model_out, x, t, tables, mean, var, logvar, x0, clip_denoised):
+    n, c, h, w = x.shape
+    check(lib().mapdit_p_mean_variance(_ptr(model_out), _ptr(x), _ptr(t), _ptr(tables), tables.shape[1], _ptr(mean), _ptr(var),
+                                       _ptr(logvar), _ptr(x0), n, c, h * w, int(clip_denoised), _stream()), "p_mean_variance")
+
+
+def posterior_mean(x0, x, t, tables, mean):
+    check(lib().mapdit_posterior_mean(_ptr(x0), _ptr(x), _ptr(t), _ptr(tables), tables.shape[1], _ptr(mean), x.shape[0],
+                                      x[0].numel(), _stream()), "posterior_mean")
+
+
+def noise_add(mean, logvar, noise, t, sample):
+    check(lib().mapdit_noise_add(_ptr(mean), _ptr(logvar), _ptr(noise), _ptr(t), _ptr(sample), mean.shape[0], mean[0].numel(),
+                                 _stream()), "noise_add")

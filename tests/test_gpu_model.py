@@ -1,0 +1,137 @@
+"""Whole-path parity on the B200: DiT forward / forward_with_cfg / sampling loop through the C ABI against
+(1) the committed outputs of the unmodified reference (tests/golden) and (2) the CPU oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, rel_l2
+from oracle import mapdit_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-5   # north_star mode (a)
+BF16_FWD_TOL = 3e-2  # north_star mode (b): bf16 operands, fp32 accumulate; SURVEY.md §A.9 measured 1.2e-2 by emulation
+
+
+def load(tag):
+    return np.load(os.path.join(GOLDEN, tag + ".npz"))
+
+
+def build(name, seed, dtype, **kw):
+    import mapdit_b200 as M
+    cfg = O.config_for(name)
+    sd = O.init_state_dict(cfg, seed=seed)
+    m = M.DIT_MODELS[name](in_channels=4, input_size=32, num_classes=1000, compute_dtype=dtype, **kw)
+    m.load_state_dict(sd, strict=True)
+    return m.cuda().eval(), cfg, sd
+
+
+@pytest.mark.parametrize("tag", ["eval_xs8", "eval_s4", "eval_xs2"])
+@pytest.mark.parametrize("dtype,tol", [("fp32", FP32_TOL), ("bf16", BF16_FWD_TOL)])
+def test_forward_vs_reference_golden(tag, dtype, tol):
+    g = load(tag)
+    m, cfg, sd = build(str(g["name"]), int(g["seed"]), dtype)
+    with torch.no_grad():
+        out = m(torch.from_numpy(g["x"]).cuda(), torch.from_numpy(g["t"]).cuda(), torch.from_numpy(g["y"]).cuda())
+    err = rel_l2(out.cpu(), g["out"])
+    print(f"{tag} {dtype}: rel-L2 vs reference = {err:.3e}")
+    assert err < tol
+
+
+@pytest.mark.parametrize("dtype,tol", [("fp32", FP32_TOL), ("bf16", BF16_FWD_TOL)])
+def test_forward_with_cfg_vs_reference_golden(dtype, tol):
+    g = load("cfg_xs4")
+    m, cfg, sd = build(str(g["name"]), int(g["seed"]), dtype)
+    with torch.no_grad():
+        out = m.forward_with_cfg(torch.from_numpy(g["x"]).cuda(), torch.from_numpy(g["t"]).cuda(), torch.from_numpy(g["y"]).cuda(),
+                                 float(g["cfg_scale"]))
+    assert rel_l2(out.cpu(), g["out"]) < tol
+
+
+@pytest.mark.parametrize("tag", ["loop_xs8", "loop_xs4_cfg"])
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_sampling_loop_vs_reference_golden(tag, dtype):
+    """free-running with clip_denoised=True; teacher-forced on the finite prefix with clip_denoised=False
+    (the reference itself overflows on random weights)."""
+    import mapdit_b200 as M
+    from mapdit_b200.diffusion import gaussian_diffusion as gd
+    g = load(tag)
+    m, cfg, sd = build(str(g["name"]), int(g["seed"]), dtype)
+    steps = int(g["steps"])
+    d = M.create_diffusion(str(steps))
+    z = torch.from_numpy(g["z"]).cuda()
+    y = torch.from_numpy(g["y"]).cuda()
+    noises = [torch.from_numpy(n).cuda() for n in g["noises"]]
+    if bool(g["use_cfg"]):
+        fn, kw = m.forward_with_cfg, dict(y=y, cfg_scale=1.5)
+    else:
+        fn, kw = m.forward, dict(y=y)
+    it = iter(noises)
+    real = gd._randn_like
+    gd._randn_like = lambda x: next(it)
+    try:
+        outs = [o["sample"].cpu() for o in d.p_sample_loop_progressive(fn, z.shape, z, clip_denoised=True, model_kwargs=kw, device="cuda")]
+    finally:
+        gd._randn_like = real
+    ref = g["samples_clip1"]
+    errs = [rel_l2(o, ref[k]) for k, o in enumerate(outs)]
+    print(f"{tag} {dtype}: free-running per-step rel-L2 = {[f'{e:.2e}' for e in errs]}")
+    # per-step tolerance; bf16 error compounds over steps and is reported, bounded loosely
+    assert max(errs) < (2e-5 if dtype == "fp32" else 5e-2)
+    # the non-progressive entry point returns the last sample
+    it = iter(noises)
+    gd._randn_like = lambda x: next(it)
+    try:
+        last = d.p_sample_loop(fn, z.shape, z, clip_denoised=True, model_kwargs=kw, device="cuda")
+    finally:
+        gd._randn_like = real
+    assert rel_l2(last.cpu(), outs[-1]) < 1e-6
+    # teacher-forced single steps, clip_denoised=False
+    ref0 = g["samples_clip0"]
+    xs = [g["z"]] + [r for r in ref0[:-1]]
+    checked = 0
+    for k in range(steps):
+        if not (np.isfinite(xs[k]).all() and np.isfinite(ref0[k]).all()):
+            break
+        i = steps - 1 - k
+        t = torch.full((z.shape[0],), i, device="cuda", dtype=torch.long)
+        gd._randn_like = lambda x, k=k: noises[k]
+        try:
+            with torch.no_grad():
+                out = d.p_sample(fn, torch.from_numpy(xs[k]).cuda(), t, clip_denoised=False, model_kwargs=kw)
+        finally:
+            gd._randn_like = real
+        e = rel_l2(out["sample"].cpu(), ref0[k])
+        print(f"{tag} {dtype}: teacher-forced step {k} clip=False rel-L2 = {e:.2e}")
+        assert e < (1e-5 if dtype == "fp32" else 5e-2)
+        checked += 1
+    assert checked >= 1
+
+
+def test_c1_config_vs_oracle_fp32():
+    """BASELINE config 1: DiT-S/4, batch 8, fp32 forward, checked against the CPU oracle run here."""
+    m, cfg, sd = build("DiT-S/4", 11, "fp32")
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(8, 4, 32, 32, generator=g)
+    t = torch.randint(0, 1000, (8,), generator=g)
+    y = torch.randint(0, 1000, (8,), generator=g)
+    with torch.no_grad():
+        ref = O.dit_forward(sd, cfg, x, t, y)
+        out = m(x.cuda(), t.cuda(), y.cuda())
+    assert rel_l2(out.cpu(), ref) < FP32_TOL
+
+
+def test_weight_cache_follows_parameter_updates():
+    m, cfg, sd = build("DiT-XS/8", 3, "fp32")
+    g = torch.Generator().manual_seed(6)
+    x, t, y = torch.randn(2, 4, 32, 32, generator=g).cuda(), torch.tensor([3, 900]).cuda(), torch.tensor([1, 2]).cuda()
+    with torch.no_grad():
+        a = m(x, t, y).clone()
+        m.blocks[0].mlp.net[0].weight.mul_(-1.0)  # in-place update bumps the version counter
+        b = m(x, t, y).clone()
+        sd2 = {k: v.clone() for k, v in m.state_dict().items()}
+        ref = O.dit_forward({k: v.cpu() for k, v in sd2.items()}, cfg, x.cpu(), t.cpu(), y.cpu())
+    assert rel_l2(a, b) > 1e-3
+    assert rel_l2(b.cpu(), ref) < FP32_TOL

@@ -1,0 +1,100 @@
+"""CPU-only checks of the host side: API surface, state-dict contract, respacing tables, the C ABI
+library loading and exporting every declared symbol, and the loud failure without a GPU."""
+import copy
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, ROOT
+from oracle import mapdit_oracle as O
+
+
+def test_registry_names_and_alias():
+    import mapdit_b200 as M
+    assert set(M.DIT_MODELS) == {f"DiT-{s}/{p}" for s in ("XS", "S", "B", "L", "XL") for p in (2, 4, 8)}
+    assert M.DiT_models is M.DIT_MODELS
+
+
+@pytest.mark.parametrize("name", ["DiT-S/4", "DiT-XS/2", "DiT-B/2"])
+def test_state_dict_contract_matches_reference(name):
+    import mapdit_b200 as M
+    m = M.DIT_MODELS[name](in_channels=4, input_size=32, num_classes=1000)
+    cfg = O.config_for(name)
+    want = O.param_shapes(cfg)
+    got = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert got == want
+    # named_parameters order equals the reference's registration order (pinned by the golden grad_names)
+    g = np.load(os.path.join(GOLDEN, "train_xs8.npz"))
+    if name == "DiT-XS/2":
+        assert [k for k, _ in m.named_parameters()] == [str(s) for s in g["grad_names"]]
+    m.load_state_dict(O.init_state_dict(cfg, seed=0), strict=True)
+    m2 = copy.deepcopy(m)  # src/ema.py:121 deep-copies the model
+    assert all(torch.equal(a, b) for a, b in zip(m.state_dict().values(), m2.state_dict().values()))
+    assert m.get_parameter("blocks.0.attn.qkv_proj.weight").shape == (3 * cfg.hidden_size, cfg.hidden_size)
+    assert torch.allclose(m.pos_embed, O.pos_embed_table(cfg.hidden_size, 32 // cfg.patch_size))
+
+
+def test_unbuilt_variants_fail_loudly():
+    import mapdit_b200 as M
+    with pytest.raises(NotImplementedError):
+        M.DIT_MODELS["DiT-XS/8"](in_channels=4, input_size=32, num_classes=10, use_mp_silu=False)
+    with pytest.raises(NotImplementedError):
+        M.DIT_MODELS["DiT-XS/8"](in_channels=4, input_size=32, num_classes=10, modulation="rotation")
+    with pytest.raises(TypeError):
+        M.DIT_MODELS["DiT-XS/8"](in_channels=4, input_size=32, num_classes=10, bogus=True)
+
+
+def test_cpu_tensors_are_rejected_not_emulated():
+    import mapdit_b200 as M
+    m = M.DIT_MODELS["DiT-XS/8"](in_channels=4, input_size=32, num_classes=10).eval()
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        m(torch.zeros(1, 4, 32, 32), torch.zeros(1, dtype=torch.long), torch.zeros(1, dtype=torch.long))
+
+
+def test_diffusion_tables_match_reference_golden():
+    import mapdit_b200 as M
+    g = np.load(os.path.join(GOLDEN, "diffusion.npz"))
+    for rs in ["", "50", "250", "10", "ddim25"]:
+        d = M.create_diffusion(rs)
+        key = rs or "full"
+        assert d.timestep_map == [int(v) for v in g[f"{key}::timestep_map"]]
+        assert d.num_timesteps == len(d.timestep_map)
+        np.testing.assert_allclose(d.betas, g[f"{key}::betas"], rtol=1e-13)
+        for k in ["sqrt_alphas_cumprod", "sqrt_one_minus_alphas_cumprod", "sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod",
+                  "posterior_variance", "posterior_log_variance_clipped", "posterior_mean_coef1", "posterior_mean_coef2"]:
+            np.testing.assert_allclose(getattr(d, k), g[f"{key}::{k}"], rtol=1e-12, err_msg=f"{key}::{k}")
+    with pytest.raises(ValueError):
+        M.create_diffusion("2000")
+
+
+def test_space_timesteps_sections():
+    from mapdit_b200.diffusion import space_timesteps
+    assert sorted(space_timesteps(300, [10, 15, 20]))[:3] == sorted(O.space_timesteps(300, [10, 15, 20]))[:3]
+    assert space_timesteps(300, "10,15,20") == set(O.space_timesteps(300, "10,15,20"))
+    assert space_timesteps(1000, "ddim50") == set(range(0, 1000, 20))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from mapdit_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "mapdit.h")).read()
+    declared = set(re.findall(r"\b(mapdit_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"mapdit_gemm_args"}
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    missing = [s for s in sorted(declared) if not hasattr(L, s)]
+    assert not missing, missing
+    assert set(_lib.SIGNATURES) <= declared
+    assert _lib.lib().mapdit_abi_version() == 1
+    assert ctypes.sizeof(_lib.GemmArgs) == L.mapdit_sizeof_gemm_args()
+
+
+def test_off_path_entry_points_say_so():
+    import mapdit_b200 as M
+    d = M.create_diffusion("ddim25")
+    with pytest.raises(NotImplementedError):
+        d.ddim_sample_loop(None, (1, 4, 32, 32))
+    with pytest.raises(NotImplementedError):
+        M.create_diffusion("", predict_xstart=True).training_losses(None, torch.zeros(1, 4, 8, 8), torch.zeros(1).long())
