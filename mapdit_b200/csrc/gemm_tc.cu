@@ -1,5 +1,397 @@
-#include "common.cuh"
-extern "C" int mapdit_gemm_bf16(const mapdit_gemm_args*, void*) {
-  mapdit_set_error("gemm_bf16: not built");
-  return MAPDIT_ERR_UNSUPPORTED;
+// K2/K3: persistent, warp-specialised bf16 GEMM on the 5th-gen tensor cores with fused epilogues.
+//
+//   D[M,N] = A[M,K] · B[N,K]^T      A,B bf16 K-major in HBM, fp32 accumulation in TMEM
+//
+// One CTA per SM walks a static tile schedule (n fastest so the CTAs of one wave share the A panel in
+// L2).  Warp 0 lane 0: TMA producer (cp.async.bulk.tensor, SWIZZLE_128B, STAGES-deep mbarrier ring);
+// warp 1 lane 0: tcgen05.mma issuer (UMMA 128 x BN x 16, accumulators double-buffered in TMEM so the
+// epilogue of tile i overlaps the main loop of tile i+1); warp 2: TMEM allocator; warps 4-7:
+// epilogue (tcgen05.ld 32x32b -> registers -> fused elementwise math -> 16-byte global stores).
+//
+// Fused epilogues (reference code they replace):
+//   QKNORM     q,k heads L2-normalised in registers        src/layers/attention.py:43-45
+//   MPSILU     silu(acc)/0.596                              src/basic/mp_silu.py:7
+//   RESID_MOD  x' = mp_sum(x, gate*acc, 0.3); h = modulate(x', shift, scale, g)
+//                                                           src/blocks/dit_block.py:35-36, src/utils.py:11-16
+#include "tc_common.cuh"
+
+extern "C" int mapdit_qk_normalize(void* qkv, int m, int d, int head_dim, float eps, int dtype, void* stream);
+
+namespace {
+using namespace tc;
+
+constexpr int BM = 128, BK = 64, UK = 16;
+constexpr int NUM_THREADS = 256;
+constexpr int SMEM_LIMIT = 227 * 1024;
+
+template <int BN>
+struct Cfg {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int MAX_STAGES = (SMEM_LIMIT - 2048) / STAGE_BYTES;
+  static constexpr int STAGES = MAX_STAGES > 8 ? 8 : MAX_STAGES;
+  static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct EpiParams {
+  void* out;
+  void* out2;
+  const void* resid;
+  const float* gate;
+  const float* shift;
+  const float* scale;
+  const float* gain;
+  long long ldo, ldmod;
+  int M, N, tokens, qk_cols, epilogue, out_f32;
+  float eps;
+};
+
+__device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)) * (1.0f / MP_SILU_DIV); }
+
+// store up to 32 consecutive columns of one row (nvalid multiple of 8)
+__device__ __forceinline__ void store_row32(void* base, long long off, const float (&f)[32], int nvalid, bool as_f32) {
+  if (as_f32) {
+    float* p = reinterpret_cast<float*>(base) + off;
+#pragma unroll
+    for (int g = 0; g < 8; ++g)
+      if (g * 4 < nvalid) *reinterpret_cast<float4*>(p + g * 4) = make_float4(f[g * 4], f[g * 4 + 1], f[g * 4 + 2], f[g * 4 + 3]);
+  } else {
+    bf16* p = reinterpret_cast<bf16*>(base) + off;
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      if (g * 8 < nvalid) {
+        uint4 u;
+        u.x = pack_bf16(f[g * 8 + 0], f[g * 8 + 1]);
+        u.y = pack_bf16(f[g * 8 + 2], f[g * 8 + 3]);
+        u.z = pack_bf16(f[g * 8 + 4], f[g * 8 + 5]);
+        u.w = pack_bf16(f[g * 8 + 6], f[g * 8 + 7]);
+        *reinterpret_cast<uint4*>(p + g * 8) = u;
+      }
+  }
+}
+
+__device__ __forceinline__ void load_row32_bf16(const void* base, long long off, float (&f)[32], int nvalid) {
+  const bf16* p = reinterpret_cast<const bf16*>(base) + off;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    uint4 u = make_uint4(0, 0, 0, 0);
+    if (g * 8 < nvalid) u = *reinterpret_cast<const uint4*>(p + g * 8);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float2 t = __bfloat1622float2(h[j]);
+      f[g * 8 + 2 * j] = t.x;
+      f[g * 8 + 2 * j + 1] = t.y;
+    }
+  }
+}
+
+__device__ __forceinline__ void load_row32_f32(const float* p, float (&f)[32], int nvalid) {
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (g * 4 < nvalid) u = *reinterpret_cast<const float4*>(p + g * 4);
+    f[g * 4] = u.x;
+    f[g * 4 + 1] = u.y;
+    f[g * 4 + 2] = u.z;
+    f[g * 4 + 3] = u.w;
+  }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const EpiParams ep,
+               int num_m_blocks, int num_n_blocks, int num_k_blocks) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* empty = full + C::STAGES;
+  uint64_t* tfull = empty + C::STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = num_m_blocks * num_n_blocks;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tma_a);
+    prefetch_tmap(&tma_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<C::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------------------------ TMA producer
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m_blk = tile / num_n_blocks, n_blk = tile - m_blk * num_n_blocks;
+      for (int kb = 0; kb < num_k_blocks; ++kb) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * C::STAGE_BYTES;
+        mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
+        tma_load_2d(sa, &tma_a, &full[stage], kb * BK, m_blk * BM);
+        tma_load_2d(sa + C::A_BYTES, &tma_b, &full[stage], kb * BK, n_blk * BN);
+        if (++stage == C::STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0, acc = 0, acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < num_k_blocks; ++kb) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + stage * C::STAGE_BYTES);
+        const uint32_t b_addr = a_addr + C::A_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / UK; ++k) {
+          const uint64_t adesc = make_smem_desc(a_addr + k * UK * 2, 16, 1024);
+          const uint64_t bdesc = make_smem_desc(b_addr + k * UK * 2, 16, 1024);
+          umma_ss(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty[stage]);  // frees the smem slot when these MMAs retire
+        if (++stage == C::STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      umma_commit(&tfull[acc]);  // accumulator complete -> epilogue
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------ epilogue (TMEM lane quarter = warp % 4)
+    const int q = warp - 4;
+    uint32_t acc = 0, acc_phase = 0;
+    float gsc = 0.f, inv_den = 1.f;
+    if (ep.epilogue == MAPDIT_EPI_RESID_MOD) {
+      gsc = *ep.gain;
+      inv_den = 1.0f / mod_den(gsc);
+    }
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m_blk = tile / num_n_blocks, n_blk = tile - m_blk * num_n_blocks;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const int row = m_blk * BM + q * 32 + lane;
+      const bool row_ok = row < ep.M;
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+      const long long sample = row_ok ? row / ep.tokens : 0;
+
+      if (ep.epilogue == MAPDIT_EPI_QKNORM) {
+        // 64 columns (= one head) at a time
+        if constexpr (BN % 64 == 0) {
+          for (int c = 0; c < BN; c += 64) {
+            uint32_t r0[32], r1[32];
+            tmem_ld32(t_row + c, r0);
+            tmem_ld32(t_row + c + 32, r1);
+            tmem_ld_wait();
+            const int col = n_blk * BN + c;
+            float f0[32], f1[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              f0[j] = __uint_as_float(r0[j]);
+              f1[j] = __uint_as_float(r1[j]);
+            }
+            if (col < ep.qk_cols) {
+              float ss = 0.f;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) ss = fmaf(f0[j], f0[j], fmaf(f1[j], f1[j], ss));
+              const float sc = 8.0f / (sqrtf(ss) + ep.eps);  // sqrt(head_dim = 64)
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                f0[j] *= sc;
+                f1[j] *= sc;
+              }
+            }
+            if (row_ok && col < ep.N) {
+              store_row32(ep.out, (long long)row * ep.ldo + col, f0, min(32, ep.N - col), false);
+              if (col + 32 < ep.N) store_row32(ep.out, (long long)row * ep.ldo + col + 32, f1, min(32, ep.N - col - 32), false);
+            }
+          }
+        }
+      } else {
+        for (int c = 0; c < BN; c += 32) {
+          uint32_t r[32];
+          tmem_ld32(t_row + c, r);
+          tmem_ld_wait();
+          const int col = n_blk * BN + c;
+          const int nvalid = min(32, ep.N - col);
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(r[j]);
+          if (!row_ok || nvalid <= 0) continue;
+          const long long off = (long long)row * ep.ldo + col;
+          if (ep.epilogue == MAPDIT_EPI_STORE) {
+            store_row32(ep.out, off, f, nvalid, ep.out_f32 != 0);
+          } else if (ep.epilogue == MAPDIT_EPI_MPSILU) {
+            if (ep.out2) store_row32(ep.out2, off, f, nvalid, false);  // pre-activation for the backward
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = silu_fast(f[j]);
+            store_row32(ep.out, off, f, nvalid, false);
+          } else {  // RESID / RESID_MOD
+            float xo[32], gt[32];
+            load_row32_bf16(ep.resid, off, xo, nvalid);
+            load_row32_f32(ep.gate + sample * ep.ldmod + col, gt, nvalid);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = fmaf(MP_RES_T, gt[j] * f[j] - xo[j], xo[j]) * (1.0f / MP_RES_DEN);
+            store_row32(ep.out, off, f, nvalid, false);
+            if (ep.epilogue == MAPDIT_EPI_RESID_MOD) {
+              float sh[32];
+              load_row32_f32(ep.shift + sample * ep.ldmod + col, sh, nvalid);
+              load_row32_f32(ep.scale + sample * ep.ldmod + col, gt, nvalid);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = lerp_t(f[j] * gt[j], sh[j], gsc) * inv_den;
+              store_row32(ep.out2, off, f, nvalid, false);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<C::TMEM_COLS>(tmem_base);
+}
+
+template <int BN>
+int launch(const mapdit_gemm_args* g, const EpiParams& ep, cudaStream_t stream, int num_sms) {
+  using C = Cfg<BN>;
+  CUtensorMap ta, tb;
+  const uint64_t dims_a[2] = {(uint64_t)g->k, (uint64_t)g->m}, dims_b[2] = {(uint64_t)g->k, (uint64_t)g->n};
+  const uint64_t str_a[1] = {(uint64_t)g->lda * 2}, str_b[1] = {(uint64_t)g->ldb * 2};
+  const uint32_t box_a[2] = {BK, BM}, box_b[2] = {BK, BN};
+  CUresult r1 = mapdit_encode_tmap(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g->a, dims_a, str_a, box_a, CU_TENSOR_MAP_SWIZZLE_128B);
+  CUresult r2 = mapdit_encode_tmap(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g->b, dims_b, str_b, box_b, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) {
+    mapdit_set_error("gemm_bf16: cuTensorMapEncodeTiled failed (%d, %d)", (int)r1, (int)r2);
+    return MAPDIT_ERR_CUDA;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      mapdit_set_error("gemm_bf16: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return MAPDIT_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  const int mb = (g->m + BM - 1) / BM, nb = (g->n + BN - 1) / BN, kb = (g->k + BK - 1) / BK;
+  const int tiles = mb * nb;
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  gemm_tc_kernel<BN><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, ep, mb, nb, kb);
+  return MAPDIT_OK;
+}
+
+int num_sms_cached() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+}  // namespace
+
+CUresult mapdit_encode_tmap(CUtensorMap* map, CUtensorMapDataType dt, uint32_t rank, const void* base, const uint64_t* dims,
+                            const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || !p)
+      return CUDA_ERROR_NOT_FOUND;
+    fn = (EncodeFn)p;
+  }
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  return fn(map, dt, rank, const_cast<void*>(base), (const cuuint64_t*)dims, (const cuuint64_t*)strides_bytes,
+            (const cuuint32_t*)box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+}
+
+extern "C" int mapdit_gemm_bf16(const mapdit_gemm_args* g, void* stream) {
+  MAPDIT_REQUIRE(g && g->a && g->b && g->out && g->m > 0 && g->n > 0 && g->k > 0, "gemm_bf16: bad args");
+  MAPDIT_REQUIRE(g->k % 8 == 0 && g->lda % 8 == 0 && g->ldb % 8 == 0 && g->n % 8 == 0 && g->ldo % 8 == 0,
+                 "gemm_bf16: k, n and leading dimensions must be multiples of 8 (16-byte TMA / vector alignment)");
+  MAPDIT_REQUIRE(((uintptr_t)g->a & 15) == 0 && ((uintptr_t)g->b & 15) == 0 && ((uintptr_t)g->out & 15) == 0,
+                 "gemm_bf16: pointers must be 16-byte aligned");
+  int epi = g->epilogue;
+  bool post_qknorm = false;
+  if (epi == MAPDIT_EPI_QKNORM && (g->head_dim != 64 || g->n % 64 != 0)) {
+    epi = MAPDIT_EPI_STORE;  // head_dim 72 (DiT-XL): plain store, then the row-wise normalise kernel
+    post_qknorm = true;
+  }
+  if (epi == MAPDIT_EPI_RESID || epi == MAPDIT_EPI_RESID_MOD) {
+    MAPDIT_REQUIRE(g->resid && g->gate && g->tokens > 0 && g->ldmod % 4 == 0, "gemm_bf16: residual epilogue needs resid/gate/tokens");
+    if (epi == MAPDIT_EPI_RESID_MOD) MAPDIT_REQUIRE(g->out2 && g->shift && g->scale && g->gain, "gemm_bf16: modulate epilogue needs out2/shift/scale/gain");
+  }
+  MAPDIT_REQUIRE(epi == MAPDIT_EPI_STORE || g->out_dtype == MAPDIT_BF16, "gemm_bf16: fused epilogues write bf16");
+  EpiParams ep;
+  ep.out = g->out; ep.out2 = g->out2; ep.resid = g->resid; ep.gate = g->gate; ep.shift = g->shift; ep.scale = g->scale;
+  ep.gain = g->gain; ep.ldo = g->ldo; ep.ldmod = g->ldmod; ep.M = g->m; ep.N = g->n; ep.tokens = g->tokens > 0 ? g->tokens : 1;
+  ep.qk_cols = g->qk_cols; ep.epilogue = epi; ep.out_f32 = (g->out_dtype == MAPDIT_F32); ep.eps = g->eps;
+
+  const int sms = num_sms_cached();
+  const int mb = (g->m + BM - 1) / BM;
+  const bool need64 = (epi == MAPDIT_EPI_QKNORM);
+  // largest BN that divides N and still yields >= 2 waves of tiles; otherwise the smallest legal one
+  const int cand[5] = {256, 192, 128, 64, 32};
+  int bn = 0;
+  for (int i = 0; i < 5; ++i) {
+    int c = cand[i];
+    if (g->n % c != 0 || (need64 && c % 64 != 0)) continue;
+    bn = c;
+    if ((long long)mb * (g->n / c) >= 2LL * sms) break;
+  }
+  if (bn == 0) bn = need64 ? 64 : 32;  // N tail handled by column masking
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc;
+  switch (bn) {
+    case 256: rc = launch<256>(g, ep, s, sms); break;
+    case 192: rc = launch<192>(g, ep, s, sms); break;
+    case 128: rc = launch<128>(g, ep, s, sms); break;
+    case 64: rc = launch<64>(g, ep, s, sms); break;
+    default: rc = launch<32>(g, ep, s, sms); break;
+  }
+  if (rc != MAPDIT_OK) return rc;
+  MAPDIT_LAUNCH_CHECK("gemm_bf16");
+  if (post_qknorm) return mapdit_qk_normalize(g->out, g->m, g->qk_cols / 2, g->head_dim, g->eps, MAPDIT_BF16, stream);
+  return MAPDIT_OK;
 }

@@ -1,0 +1,98 @@
+"""tcgen05 kernels (bf16 GEMM with fused epilogues, cosine attention) against fp32/fp64 PyTorch math on the
+same bf16-rounded operands.  Tolerances are the bf16 output rounding (2^-9 relative) unless stated."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_l2
+from oracle import mapdit_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).cuda()
+
+
+SHAPES = [(128, 32, 64), (256, 256, 64), (128, 64, 128), (512, 1152, 384), (200, 96, 384), (4096, 2304, 768), (8192, 768, 3072),
+          (1000, 1536, 384), (256, 4608, 768), (384, 384, 1536)]
+
+
+@pytest.mark.parametrize("m,n,k", SHAPES)
+def test_gemm_bf16_store(m, n, k):
+    from mapdit_b200 import ops
+    a, b = rnd(m, k, seed=1).bfloat16(), rnd(n, k, seed=2, scale=k ** -0.5).bfloat16()
+    ref = a.double() @ b.double().t()
+    out32 = torch.full((m, n), float("nan"), device="cuda")
+    ops.gemm_bf16(a, b, out32)
+    assert rel_l2(out32, ref) < 1e-5, "fp32-out GEMM must only differ by accumulation order"
+    out16 = torch.empty(m, n, device="cuda", dtype=torch.bfloat16)
+    ops.gemm_bf16(a, b, out16)
+    assert rel_l2(out16.float(), ref) < 3e-3
+    # strided A (column slice of a wider buffer), as the engine uses for q|k|v style views
+    wide = torch.zeros(m, k + 64, device="cuda", dtype=torch.bfloat16)
+    wide[:, 64:] = a
+    ops.gemm_bf16(wide[:, 64:], b, out32)
+    assert rel_l2(out32, ref) < 1e-5
+
+
+@pytest.mark.parametrize("N,T,D", [(2, 64, 384), (3, 256, 256), (1, 256, 768), (33, 64, 384)])
+def test_gemm_bf16_fused_epilogues(N, T, D):
+    from mapdit_b200 import _lib, ops
+    M, hd = N * T, 64
+    h = rnd(M, D, seed=3).bfloat16()
+    wqkv = rnd(3 * D, D, seed=4, scale=D ** -0.5).bfloat16()
+    acc = h.float() @ wqkv.float().t()
+    # QKNORM
+    qkv = torch.empty(M, 3 * D, device="cuda", dtype=torch.bfloat16)
+    ops.gemm_bf16(h, wqkv, qkv, epilogue=_lib.EPI_QKNORM, tokens=T, head_dim=hd, qk_cols=2 * D)
+    ref = acc.clone()
+    qk = ref[:, :2 * D].reshape(M, 2 * D // hd, hd)
+    ref[:, :2 * D] = (qk * math.sqrt(hd) / (qk.norm(dim=-1, keepdim=True) + 1e-4)).reshape(M, 2 * D)
+    assert rel_l2(qkv.float(), ref) < 3e-3
+    # MPSILU (+ pre-activation copy)
+    w1 = rnd(4 * D, D, seed=5, scale=D ** -0.5).bfloat16()
+    z = h.float() @ w1.float().t()
+    u = torch.empty(M, 4 * D, device="cuda", dtype=torch.bfloat16)
+    pre = torch.empty_like(u)
+    ops.gemm_bf16(h, w1, u, epilogue=_lib.EPI_MPSILU, out2=pre)
+    assert rel_l2(u.float(), F.silu(z) / 0.596) < 3e-3
+    assert rel_l2(pre.float(), z) < 3e-3
+    # RESID_MOD, in place on x
+    x = rnd(M, D, seed=6).bfloat16()
+    mods = rnd(N, 6 * D, seed=7)
+    gain = torch.tensor(0.31, device="cuda")
+    wo = rnd(D, D, seed=8, scale=D ** -0.5).bfloat16()
+    y = h.float() @ wo.float().t()
+    n_of_row = torch.arange(M, device="cuda") // T
+    gate, shift, scale = mods[:, 2 * D:3 * D][n_of_row], mods[:, 3 * D:4 * D][n_of_row], mods[:, 4 * D:5 * D][n_of_row]
+    xn = (x.float() + 0.3 * (gate * y - x.float())) / math.sqrt(0.7 ** 2 + 0.3 ** 2)
+    g = float(gain)
+    hn = ((xn * scale) + g * (shift - xn * scale)) / math.sqrt((1 - g) ** 2 + g ** 2)
+    xio = x.clone()
+    hout = torch.empty_like(x)
+    ops.gemm_bf16(h, wo, xio, epilogue=_lib.EPI_RESID_MOD, out2=hout, resid=xio, gate=mods[:, 2 * D:], shift=mods[:, 3 * D:],
+                  scale=mods[:, 4 * D:], gain=gain, ldmod=mods.shape[1], tokens=T)
+    assert rel_l2(xio.float(), xn) < 3e-3
+    assert rel_l2(hout.float(), hn) < 3e-3
+    xio = x.clone()
+    ops.gemm_bf16(h, wo, xio, epilogue=_lib.EPI_RESID, resid=xio, gate=mods[:, 2 * D:], ldmod=mods.shape[1], tokens=T)
+    assert rel_l2(xio.float(), xn) < 3e-3
+
+
+@pytest.mark.parametrize("N,T,H", [(2, 256, 6), (3, 64, 4), (1, 1024, 2), (5, 256, 12), (2, 128, 4)])
+def test_cos_attn_bf16(N, T, H):
+    from mapdit_b200 import ops
+    hd, D = 64, H * 64
+    qkv = rnd(N * T, 3 * D, seed=9)
+    ops.qk_normalize(qkv, D, hd)
+    qkv16 = qkv.bfloat16()
+    q, k, v = qkv16.float().view(N, T, 3, H, hd).permute(2, 0, 3, 1, 4)
+    ref = F.scaled_dot_product_attention(q.double(), k.double(), v.double(), scale=1 / math.sqrt(hd)).transpose(1, 2).reshape(N * T, D)
+    o = torch.empty(N * T, D, device="cuda", dtype=torch.bfloat16)
+    ops.cos_attn(qkv16, o, N, T, H, hd)
+    # P is rounded to bf16 before the PV product on the tensor-core path
+    assert rel_l2(o.float(), ref) < 6e-3
