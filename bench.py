@@ -1,0 +1,414 @@
+#!/usr/bin/env python
+"""Benchmark of the MaP-DiT hot path on B200 (contract: task prompt; metric: BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload sample|train|forward] [--impl ours|reference]
+
+One JSON line on stdout (rank 0).  A "step" is one pass of the hot path over one batch of synthetic
+latents: `sample` = one 50-step respaced p_sample_loop over the batch (model.forward, no CFG),
+`train` = training_losses + backward + Adam, `forward` = one eval forward.  Workload at every N is
+DiT-B/2 (BASELINE.json configs[2]; the configuration the metric is quoted on), batch 256 per GPU
+(weak scaling, batch-sharded, no data-path collective except the final gather of samples).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MODEL = "DiT-B/2"
+SAMPLING_STEPS = 50
+
+
+def flops_per_image(cfg):
+    """algorithmic FLOPs (2*MAC) of one forward, split for the train multiplier."""
+    T, L, D, p, C = cfg.tokens, cfg.depth, cfg.hidden_size, cfg.patch_size, cfg.in_channels
+    lin = T * L * 24 * D * D
+    attn = T * L * 4 * T * D
+    emb = T * (2 * (p * p * C + 1) * D + 2 * D * 2 * p * p * C)
+    cond = L * 12 * D * D + 4 * D * D + 2 * (256 * D + D * D) + 32 * D
+    return dict(fwd=lin + attn + emb + cond, train=3 * (lin + emb + cond) + 3.5 * attn)
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return dict(tf_burst=p["bf16_tflops"], tf_sustained=p["bf16_tflops_sustained"], hbm=p["hbm_gbs"], src="measured")
+    except Exception:
+        return dict(tf_burst=1590.0, tf_sustained=1400.0, hbm=6650.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(self.rows)}
+
+
+# --------------------------------------------------------------------------------------------- reference arm (CPU)
+def run_reference(args):
+    """The reference's own implementation of the path cannot travel to the GPU box (it is a Python repo mounted
+    read-only in the build container), so this arm times its pinned CPU restatement (oracle/, kind 'port') on all
+    host cores, on a bounded sample of the same workload."""
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import mapdit_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = O.config_for(MODEL)
+    sd = O.init_state_dict(cfg, seed=0)
+    B = 8
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(B, 4, 32, 32, generator=g)
+    y = torch.randint(0, 1000, (B,), generator=g)
+    times = []
+    if args.workload == "train":
+        p = O.make_params(sd)
+        T = O.make_tables("")
+        opt = torch.optim.Adam([v for v in p.values() if v.requires_grad], lr=1e-2, betas=(0.9, 0.99))
+        t = torch.randint(0, 1000, (B,), generator=g)
+        noise = torch.randn(B, 4, 32, 32, generator=g)
+        sample = f"{MODEL} training step (loss+backward+Adam) at batch {B} on the CPU oracle"
+
+        def step():
+            opt.zero_grad()
+            O.train_step_grads(p, cfg, T, x, t, y, noise)
+            opt.step()
+        per_step_images = B
+    else:
+        T = O.make_tables(str(SAMPLING_STEPS))
+        tm = torch.tensor(T.timestep_map)
+        nsub = 2 if args.workload == "sample" else 1
+        sample = (f"{MODEL} {nsub} of {SAMPLING_STEPS} sampling steps at batch {B} on the CPU oracle, scaled to {SAMPLING_STEPS} steps"
+                  if args.workload == "sample" else f"{MODEL} eval forward at batch {B} on the CPU oracle")
+
+        def step():
+            img = x
+            with torch.no_grad():
+                for k in range(nsub):
+                    i = T.num_timesteps - 1 - k
+                    tt = torch.full((B,), i, dtype=torch.long)
+                    out = O.dit_forward(sd, cfg, img, tm[tt], y)
+                    if args.workload == "sample":
+                        img = O.p_sample_step(T, out, img, tt, torch.randn_like(img))["sample"]
+        per_step_images = B * nsub / SAMPLING_STEPS if args.workload == "sample" else B
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        step()
+        if i >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    ms = 1e3 * sum(times) / len(times)
+    value = per_step_images / (ms / 1e3)
+    unit = "img/s"
+    line = {"impl": "reference", "metric": metric_name(args.workload), "value": value, "unit": unit, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args.workload), "model": MODEL, "batch_per_step": B},
+            "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def metric_name(w):
+    return {"sample": "dit_b2_map_sample50_img_per_s", "train": "dit_b2_map_train_img_per_s", "forward": "dit_b2_map_forward_img_per_s"}[w]
+
+
+def workload_name(w):
+    return {"sample": f"{MODEL} MaP, {SAMPLING_STEPS}-step respaced p_sample_loop, 32x32x4 latents, batch 256/GPU, no CFG",
+            "train": f"{MODEL} MaP training step (training_losses + backward + Adam), 32x32x4 latents, batch 256/GPU",
+            "forward": f"{MODEL} MaP eval forward, 32x32x4 latents, batch 256/GPU"}[w]
+
+
+# --------------------------------------------------------------------------------------------- our arm (B200)
+def cpu_baseline(workload, seconds_budget=20.0):
+    import torch
+    from oracle import mapdit_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = O.config_for(MODEL)
+    sd = O.init_state_dict(cfg, seed=0)
+    B = 8
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(B, 4, 32, 32, generator=g)
+    y = torch.randint(0, 1000, (B,), generator=g)
+    t = torch.randint(0, 1000, (B,), generator=g)
+    if workload == "train":
+        p = O.make_params(sd)
+        T = O.make_tables("")
+        opt = torch.optim.Adam([v for v in p.values() if v.requires_grad], lr=1e-2, betas=(0.9, 0.99))
+        noise = torch.randn(B, 4, 32, 32, generator=g)
+
+        def step():
+            opt.zero_grad()
+            O.train_step_grads(p, cfg, T, x, t, y, noise)
+            opt.step()
+        scale, what = B, f"{MODEL} training step at batch {B}"
+    else:
+        def step():
+            with torch.no_grad():
+                O.dit_forward(sd, cfg, x, t, y)
+        scale = B / SAMPLING_STEPS if workload == "sample" else B
+        what = f"{MODEL} eval forward at batch {B}" + (f", x{SAMPLING_STEPS} steps per image" if workload == "sample" else "")
+    step()
+    n, t0 = 0, time.perf_counter()
+    while True:
+        step()
+        n += 1
+        el = time.perf_counter() - t0
+        if el > seconds_budget or n >= 10:
+            break
+    return {"value": scale * n / el, "unit": "img/s", "cores": cores, "kind": "port",
+            "sample": f"{what}, {n} iterations in {el:.1f} s on the pinned CPU oracle (oracle/mapdit_oracle.py)"}
+
+
+def time_kernel(fn, iters=10, warm=3):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(iters + 1)]
+    ev[0].record()
+    for i in range(iters):
+        fn()
+        ev[i + 1].record()
+    torch.cuda.synchronize()
+    return sum(ev[i].elapsed_time(ev[i + 1]) for i in range(iters)) / iters  # ms
+
+
+def kernel_roofline(cfg, B, pk):
+    """Isolated timing (CUDA events on the launching stream) of the dominant kernel: the fc1 block GEMM
+    (gemm_tc_kernel<256>, fused mp_silu epilogue), plus the other block GEMMs and attention for the table."""
+    import torch
+    from mapdit_b200 import _lib, ops
+    D, T, H = cfg.hidden_size, cfg.tokens, cfg.num_heads
+    M = B * T
+    dev = "cuda"
+    mk = lambda *s: (torch.randn(*s, device=dev) * 0.05).bfloat16()
+    h, u4 = mk(M, D), mk(M, 4 * D)
+    wqkv, wo, w1, w2 = mk(3 * D, D), mk(D, D), mk(4 * D, D), mk(D, 4 * D)
+    qkv, o, x = mk(M, 3 * D), mk(M, D), mk(M, D)
+    mods = torch.randn(B, 6 * D, device=dev)
+    gain = torch.tensor(0.3, device=dev)
+    res = {}
+    cases = {
+        "qkv_gemm_qknorm": (lambda: ops.gemm_bf16(h, wqkv, qkv, epilogue=_lib.EPI_QKNORM, tokens=T, head_dim=D // H, qk_cols=2 * D), 2 * M * D * 3 * D),
+        "attn": (lambda: ops.cos_attn(qkv, o, B, T, H, D // H), 4 * M * T * D),
+        "out_gemm_resid_mod": (lambda: ops.gemm_bf16(o, wo, x, epilogue=_lib.EPI_RESID_MOD, out2=h, resid=x, gate=mods, shift=mods[:, D:], scale=mods[:, 2 * D:], gain=gain, ldmod=6 * D, tokens=T), 2 * M * D * D),
+        "fc1_gemm_mpsilu": (lambda: ops.gemm_bf16(h, w1, u4, epilogue=_lib.EPI_MPSILU), 2 * M * D * 4 * D),
+        "fc2_gemm_resid_mod": (lambda: ops.gemm_bf16(u4, w2, x, epilogue=_lib.EPI_RESID_MOD, out2=h, resid=x, gate=mods, shift=mods[:, D:], scale=mods[:, 2 * D:], gain=gain, ldmod=6 * D, tokens=T), 2 * M * 4 * D * D),
+    }
+    for k, (fn, fl) in cases.items():
+        ms = time_kernel(fn)
+        res[k] = {"ms": round(ms, 4), "tflops": round(fl / ms / 1e9, 1)}
+    dom = res["fc1_gemm_mpsilu"]
+    roof = {"bound": "tensor", "kernel": "gemm_tc_kernel<256> (fc1, fused mp_silu epilogue), M=%d N=%d K=%d" % (M, 4 * D, D),
+            "achieved": dom["tflops"], "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": round(dom["tflops"] / pk["tf_burst"], 4),
+            "peak_source": f"MEASURED_PEAKS.json bf16 burst ({pk['src']})", "traffic": None, "per_kernel": res}
+    return roof
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import mapdit_b200 as M
+    from mapdit_b200 import _lib
+    from oracle import mapdit_oracle as O  # weights only (deterministic init) + cpu_baseline leg
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    cfg = O.config_for(MODEL)
+    B = args.batch
+    model = M.DIT_MODELS[MODEL](in_channels=4, input_size=32, num_classes=1000, compute_dtype=args.dtype)
+    model.load_state_dict(O.init_state_dict(cfg, seed=0))
+    model = model.to(dev)
+    fl = flops_per_image(cfg)
+    pk = peaks()
+    g = torch.Generator().manual_seed(1 + rank)
+    # host-side (pinned) inputs for the e2e leg, device-resident copies for the kernel-only leg
+    z_host = torch.randn(B, 4, 32, 32, generator=g).pin_memory()
+    y_host = torch.randint(0, 1000, (B,), generator=g).pin_memory()
+    t_host = torch.randint(0, 1000, (B,), generator=g).pin_memory()
+    z_dev, y_dev, t_dev = z_host.to(dev), y_host.to(dev), t_host.to(dev)
+    out_host = torch.empty(B, 4, 32, 32).pin_memory()
+    diffusion = M.create_diffusion(str(SAMPLING_STEPS) if args.workload == "sample" else "")
+
+    if args.workload == "sample":
+        model.eval()
+        gather = [torch.empty(B, 4, 32, 32, device=dev) for _ in range(world)] if world > 1 else None
+
+        def step_dev():
+            s = diffusion.p_sample_loop(model.forward, z_dev.shape, z_dev, clip_denoised=False, model_kwargs=dict(y=y_dev), device=dev)
+            if world > 1:
+                dist.all_gather(gather, s)
+            return s
+
+        def step_e2e():
+            z = z_host.to(dev, non_blocking=True)
+            y = y_host.to(dev, non_blocking=True)
+            s = diffusion.p_sample_loop(model.forward, z.shape, z, clip_denoised=False, model_kwargs=dict(y=y), device=dev)
+            if world > 1:
+                dist.all_gather(gather, s)
+            out_host.copy_(s, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        images_per_step = B
+        flops_step = fl["fwd"] * B * SAMPLING_STEPS
+        h2d, d2h = z_host.numel() * 4 + y_host.numel() * 8, out_host.numel() * 4
+    elif args.workload == "forward":
+        model.eval()
+
+        def step_dev():
+            with torch.no_grad():
+                return model(z_dev, t_dev, y_dev)
+
+        out8 = torch.empty(B, 8, 32, 32).pin_memory()
+
+        def step_e2e():
+            with torch.no_grad():
+                o = model(z_host.to(dev, non_blocking=True), t_host.to(dev, non_blocking=True), y_host.to(dev, non_blocking=True))
+            out8.copy_(o, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        images_per_step = B
+        flops_step = fl["fwd"] * B
+        h2d, d2h = z_host.numel() * 4 + 2 * B * 8, out8.numel() * 4
+    else:
+        from mapdit_b200.train import TrainStep
+        model.train()
+        ts = TrainStep(model, diffusion, lr=1e-2, betas=(0.9, 0.99), world_size=world)
+        noise_dev = torch.randn(B, 4, 32, 32, device=dev)
+        noise_host = noise_dev.cpu().pin_memory()
+
+        def step_dev():
+            return ts.step(z_dev, t_dev, y_dev, noise_dev)
+
+        def step_e2e():
+            loss = ts.step(z_host.to(dev, non_blocking=True), t_host.to(dev, non_blocking=True), y_host.to(dev, non_blocking=True),
+                           noise_host.to(dev, non_blocking=True))
+            return float(loss)  # D2H read of the loss, like train.py:99
+        images_per_step = B
+        flops_step = fl["train"] * B
+        h2d, d2h = (z_host.numel() + noise_host.numel()) * 4 + 2 * B * 8, 4
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, sampler=None):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        if sampler:
+            sampler.start()
+        n0 = _lib.total_launches()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = _lib.total_launches() - n0
+        clk = sampler.stop() if sampler else None
+        if world > 1:
+            tt = torch.tensor([ms], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt)
+        return ms, launches, clk
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms, launches, clk = timed(step_dev, args.steps, max(args.warmup, 3), sampler)
+    ms_e2e, _, _ = timed(step_e2e, args.steps, 1)
+    value = images_per_step * world * args.steps / (ms / 1e3)
+    e2e_value = images_per_step * world * args.steps / (ms_e2e / 1e3)
+    if rank == 0:
+        roof = kernel_roofline(cfg, B, pk) if not args.no_roofline else None
+        if roof is not None:
+            step_tf = flops_step * args.steps / (ms / 1e3) / 1e12
+            roof["step_tflops_per_gpu"] = round(step_tf, 1)
+            roof["step_frac_of_sustained"] = round(step_tf / pk["tf_sustained"], 4)
+        cpu = cpu_baseline(args.workload) if not args.no_cpu_baseline else None
+        line = {"metric": metric_name(args.workload), "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+                "config": {"workload": workload_name(args.workload), "model": MODEL, "batch_per_gpu": B, "global_batch": B * world,
+                           "parallelism": f"dp{world}" if world > 1 else "single",
+                           "l2": "per-step working set (activations ~100 MB per [M,D] tensor, 2.4 GB per block) exceeds the 126 MB L2; no flush needed",
+                           "weights": "random init (numpy PCG64 seed 0), reference init distributions", "clip_denoised": False},
+                "e2e": {"value": e2e_value, "unit": "img/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": launches, "clocks": clk, "roofline": roof, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("MAPDIT_BENCH_WORKLOAD", "sample"), choices=["sample", "train", "forward"])
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world == 1:
+        # convenience: re-launch under torchrun
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+               "--master-port", "29541", os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

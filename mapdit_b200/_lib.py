@@ -78,3 +78,17 @@ def check(rc, what=""):
 
 def launch_count() -> int:
     return int(lib().mapdit_launch_count())
+
+
+# kernels launched through CUDA-graph replays never pass through the C entry points again, so the
+# Python side adds (kernels captured in the graph) x (replays) to the library's own counter.
+_replayed = 0
+
+
+def note_graph_replay(kernels_in_graph: int):
+    global _replayed
+    _replayed += int(kernels_in_graph)
+
+
+def total_launches() -> int:
+    return launch_count() + _replayed

@@ -292,10 +292,14 @@ class GaussianDiffusion:
                     body()  # warm-up: builds weight caches / workspaces outside capture
                 th.cuda.current_stream(dev).wait_stream(side)
                 g = th.cuda.CUDAGraph()
+                from .. import _lib
+                n_before = _lib.launch_count()
                 with th.cuda.graph(g):
                     body()
                 st["graph"] = g
+                st["kernels"] = _lib.launch_count() - n_before
                 self._graphs[key] = st
+            from .. import _lib
             dit.engine.weights(dit.compute_dtype, train=False)  # refresh cached effective weights if parameters changed
             st["y"].copy_(y)
             st["img"].copy_(img)
@@ -304,6 +308,7 @@ class GaussianDiffusion:
                 st["tm"].fill_(self._timestep_for_model(i))
                 st["noise"].copy_(_randn_like(st["img"]))
                 st["graph"].replay()
+                _lib.note_graph_replay(st["kernels"])
                 if want_xstart:
                     yield {"sample": st["img"].clone(), "pred_xstart": st["x0"].clone()}
             if not want_xstart:
