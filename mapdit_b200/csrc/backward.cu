@@ -1,0 +1,387 @@
+// Backward kernels of the block's elementwise ops (SURVEY.md §A.3 closed forms, verified against autograd):
+// mp residual, modulate (with the detached denominator of src/utils.py:16), mp_silu, q/k normalisation,
+// the final-layer scale/unpatchify, and the conditioning path.  Per-sample reductions over the T tokens
+// (dshift/dscale/dgate) are done by "column strip" threads: one thread owns one (sample, channel) and
+// walks its T rows, so loads are coalesced across channels and the sums are deterministic.
+#include "common.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// x_out = mp_sum(x, gate*y, 0.3):   R <- 0.7/den * R (in place) ; dy = 0.3/den * gate * R_in ; dgate = sum_t 0.3/den * y * R_in
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128) resid_bwd_kernel(T* __restrict__ R, const T* __restrict__ y, T* __restrict__ dy,
+                                                        const float* __restrict__ gate, float* __restrict__ dgate, int64_t ldmod,
+                                                        int d, int tokens) {
+  const int n = blockIdx.y;
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= d) return;
+  const float g = gate[n * ldmod + col];
+  const float ca = (1.0f - MP_RES_T) / MP_RES_DEN, cb = MP_RES_T / MP_RES_DEN;
+  float acc = 0.f;
+  size_t off = ((size_t)n * tokens) * d + col;
+  for (int t = 0; t < tokens; ++t, off += d) {
+    float r = ld_act(R + off);
+    float yv = ld_act(y + off);
+    st_act(dy + off, cb * g * r);
+    acc = fmaf(cb * yv, r, acc);
+    st_act(R + off, ca * r);
+  }
+  dgate[n * ldmod + col] = acc;
+}
+
+extern "C" int mapdit_resid_bwd(void* R, const void* y, void* dy, const float* gate, float* dgate, int64_t ldmod, int n_samples,
+                                int d, int tokens, int dtype, void* stream) {
+  MAPDIT_REQUIRE(R && y && dy && gate && dgate && n_samples > 0 && d > 0 && tokens > 0, "resid_bwd: bad args");
+  dim3 grid((d + 127) / 128, n_samples);
+  if (dtype == MAPDIT_F32)
+    resid_bwd_kernel<float><<<grid, 128, 0, (cudaStream_t)stream>>>((float*)R, (const float*)y, (float*)dy, gate, dgate, ldmod, d, tokens);
+  else
+    resid_bwd_kernel<bf16><<<grid, 128, 0, (cudaStream_t)stream>>>((bf16*)R, (const bf16*)y, (bf16*)dy, gate, dgate, ldmod, d, tokens);
+  MAPDIT_LAUNCH_CHECK("resid_bwd");
+  return MAPDIT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// h = lerp(x*scale, shift, g)/den(g), den detached:
+//   R += dh*(1-g)/den*scale ; dscale = sum_t dh*(1-g)/den*x ; dshift = sum_t dh*g/den ; dg = sum dh*(shift - x*scale)/den
+// dg partials: one float per CTA (deterministic two-stage reduction, finished by mapdit_sum_partials).
+// R may be null (first block: the input has no gradient); accumulate==0 overwrites R.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128) modulate_bwd_kernel(const T* __restrict__ dh, const T* __restrict__ x, T* __restrict__ R,
+                                                           const float* __restrict__ shift, const float* __restrict__ scale,
+                                                           const float* __restrict__ gain, float* __restrict__ dshift,
+                                                           float* __restrict__ dscale, float* __restrict__ dg_partial, int64_t ldmod,
+                                                           int d, int tokens, int accumulate) {
+  __shared__ float red[32];
+  const int n = blockIdx.y;
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  const float g = *gain;
+  const float den = mod_den(g);
+  const float ca = (1.0f - g) / den, cb = g / den, cd = 1.0f / den;
+  float a_sc = 0.f, a_sh = 0.f, a_g = 0.f;
+  if (col < d) {
+    const float sc = scale[n * ldmod + col], sh = shift[n * ldmod + col];
+    size_t off = ((size_t)n * tokens) * d + col;
+    for (int t = 0; t < tokens; ++t, off += d) {
+      float gh = ld_act(dh + off);
+      float xv = ld_act(x + off);
+      if (R) {
+        float add = ca * sc * gh;
+        st_act(R + off, accumulate ? ld_act(R + off) + add : add);
+      }
+      a_sc = fmaf(ca * xv, gh, a_sc);
+      a_sh += gh;
+      a_g = fmaf(gh, sh - xv * sc, a_g);
+    }
+    dscale[n * ldmod + col] = a_sc;
+    dshift[n * ldmod + col] = cb * a_sh;
+  }
+  float tot = block_sum(a_g * cd, red);
+  if (threadIdx.x == 0) dg_partial[blockIdx.y * gridDim.x + blockIdx.x] = tot;
+}
+
+extern "C" int mapdit_modulate_bwd(const void* dh, const void* x, void* R, const float* shift, const float* scale, const float* gain,
+                                   float* dshift, float* dscale, float* dg_partial, int64_t ldmod, int n_samples, int d, int tokens,
+                                   int accumulate, int dtype, void* stream) {
+  MAPDIT_REQUIRE(dh && x && shift && scale && gain && dshift && dscale && dg_partial && n_samples > 0, "modulate_bwd: bad args");
+  dim3 grid((d + 127) / 128, n_samples);
+  if (dtype == MAPDIT_F32)
+    modulate_bwd_kernel<float><<<grid, 128, 0, (cudaStream_t)stream>>>((const float*)dh, (const float*)x, (float*)R, shift, scale, gain, dshift, dscale, dg_partial, ldmod, d, tokens, accumulate);
+  else
+    modulate_bwd_kernel<bf16><<<grid, 128, 0, (cudaStream_t)stream>>>((const bf16*)dh, (const bf16*)x, (bf16*)R, shift, scale, gain, dshift, dscale, dg_partial, ldmod, d, tokens, accumulate);
+  MAPDIT_LAUNCH_CHECK("modulate_bwd");
+  return MAPDIT_OK;
+}
+extern "C" int mapdit_modulate_bwd_partials(int n_samples, int d) { return ((d + 127) / 128) * n_samples; }
+
+// out[0] (+)= sum(partials[0..n))   -- single CTA, fixed order
+__global__ void __launch_bounds__(256) sum_partials_kernel(const float* __restrict__ p, int n, float* __restrict__ out, int accumulate) {
+  __shared__ float red[32];
+  float a = 0.f;
+  for (int i = threadIdx.x; i < n; i += 256) a += p[i];
+  a = block_sum(a, red);
+  if (threadIdx.x == 0) *out = accumulate ? *out + a : a;
+}
+extern "C" int mapdit_sum_partials(const float* partials, int n, float* out, int accumulate, void* stream) {
+  MAPDIT_REQUIRE(partials && out && n > 0, "sum_partials: bad args");
+  sum_partials_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(partials, n, out, accumulate);
+  MAPDIT_LAUNCH_CHECK("sum_partials");
+  return MAPDIT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// u = silu(z)/0.596 :  dz = du * sigma(z) (1 + z (1 - sigma(z))) / 0.596
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void mp_silu_bwd_kernel(const T* __restrict__ du, const T* __restrict__ z, T* __restrict__ dz, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float zv = ld_act(z + i);
+    float s = 1.0f / (1.0f + expf(-zv));
+    st_act(dz + i, ld_act(du + i) * (s * (1.0f + zv * (1.0f - s))) / MP_SILU_DIV);
+  }
+}
+extern "C" int mapdit_mp_silu_bwd(const void* du, const void* z, void* dz, int64_t n, int dtype, void* stream) {
+  MAPDIT_REQUIRE(du && z && dz && n > 0, "mp_silu_bwd: bad args");
+  int64_t b = (n + 255) / 256;
+  int grid = (int)(b < 148 * 16 ? b : 148 * 16);
+  if (dtype == MAPDIT_F32) mp_silu_bwd_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)du, (const float*)z, (float*)dz, n);
+  else mp_silu_bwd_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)du, (const bf16*)z, (bf16*)dz, n);
+  MAPDIT_LAUNCH_CHECK("mp_silu_bwd");
+  return MAPDIT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// y = g v/(r+eps), g = sqrt(hd):  dv = (g/(r+eps)) (G - y (y.G) (r+eps)/(g^2 r)),  with sc = g/(r+eps) saved by the forward.
+// In place on the q|k thirds of dqkv[M, 3D]; one warp per (row, head).
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void qk_norm_bwd_kernel(T* __restrict__ dqkv, const T* __restrict__ qkv, const float* __restrict__ sc, int64_t total,
+                                   int heads2, int d, int hd, float eps) {
+  int lane = threadIdx.x & 31;
+  int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (wid >= total) return;
+  int64_t row = wid / heads2;
+  int hh = (int)(wid - row * heads2);
+  const size_t off = (size_t)row * 3 * d + (size_t)hh * hd;
+  float yv[4], gv[4], dot = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    int c = lane + 32 * j;
+    yv[j] = (c < hd) ? ld_act(qkv + off + c) : 0.f;
+    gv[j] = (c < hd) ? ld_act(dqkv + off + c) : 0.f;
+    dot = fmaf(yv[j], gv[j], dot);
+  }
+  dot = warp_sum(dot);
+  const float s = sc[wid];
+  const float gsq = (float)hd;
+  const float rpe = sqrtf(gsq) / s;  // r + eps
+  const float r = fmaxf(rpe - eps, 1e-30f);
+  const float coef = dot * rpe / (gsq * r);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    int c = lane + 32 * j;
+    if (c < hd) st_act(dqkv + off + c, s * (gv[j] - yv[j] * coef));
+  }
+}
+extern "C" int mapdit_qk_norm_bwd(void* dqkv, const void* qkv, const float* sc, int m, int d, int head_dim, float eps, int dtype,
+                                  void* stream) {
+  MAPDIT_REQUIRE(dqkv && qkv && sc && m > 0 && d % head_dim == 0 && head_dim <= 128, "qk_norm_bwd: bad args");
+  int heads2 = 2 * (d / head_dim);
+  int64_t total = (int64_t)m * heads2;
+  unsigned blocks = (unsigned)((total * 32 + 255) / 256);
+  if (dtype == MAPDIT_F32) qk_norm_bwd_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>((float*)dqkv, (const float*)qkv, sc, total, heads2, d, head_dim, eps);
+  else qk_norm_bwd_kernel<bf16><<<blocks, 256, 0, (cudaStream_t)stream>>>((bf16*)dqkv, (const bf16*)qkv, sc, total, heads2, d, head_dim, eps);
+  MAPDIT_LAUNCH_CHECK("qk_norm_bwd");
+  return MAPDIT_OK;
+}
+
+// forward companion: normalise q|k in place and record sc = sqrt(hd)/(||v||+eps) per (row, head)
+template <typename T>
+__global__ void qk_normalize_save_kernel(T* __restrict__ qkv, float* __restrict__ sc, int64_t total, int heads2, int d, int hd, float eps) {
+  int lane = threadIdx.x & 31;
+  int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (wid >= total) return;
+  int64_t row = wid / heads2;
+  int hh = (int)(wid - row * heads2);
+  T* p = qkv + (size_t)row * 3 * d + (size_t)hh * hd;
+  float v[4], ss = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    int c = lane + 32 * j;
+    v[j] = (c < hd) ? ld_act(p + c) : 0.f;
+    ss = fmaf(v[j], v[j], ss);
+  }
+  float nrm = sqrtf(warp_sum(ss));
+  float sq = sqrtf((float)hd), den = nrm + eps;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    int c = lane + 32 * j;
+    if (c < hd) st_act(p + c, (v[j] * sq) / den);
+  }
+  if (lane == 0) sc[wid] = sq / den;
+}
+extern "C" int mapdit_qk_normalize_save(void* qkv, float* sc, int m, int d, int head_dim, float eps, int dtype, void* stream) {
+  MAPDIT_REQUIRE(qkv && sc && m > 0 && d % head_dim == 0 && head_dim <= 128, "qk_normalize_save: bad args");
+  int heads2 = 2 * (d / head_dim);
+  int64_t total = (int64_t)m * heads2;
+  unsigned blocks = (unsigned)((total * 32 + 255) / 256);
+  if (dtype == MAPDIT_F32) qk_normalize_save_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>((float*)qkv, sc, total, heads2, d, head_dim, eps);
+  else qk_normalize_save_kernel<bf16><<<blocks, 256, 0, (cudaStream_t)stream>>>((bf16*)qkv, sc, total, heads2, d, head_dim, eps);
+  MAPDIT_LAUNCH_CHECK("qk_normalize_save");
+  return MAPDIT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// final layer: out[n, part*C+c, y, x] = lin[tok, j] * s_part[n]
+//   dlin[tok, j] = dout * s_part[n] ;  ds_part[n] = sum dout * lin      (one CTA per sample)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) final_bwd_kernel(const float* __restrict__ dout, const T* __restrict__ lin,
+                                                        const float* __restrict__ s_mu, const float* __restrict__ s_sg,
+                                                        T* __restrict__ dlin, float* __restrict__ ds_mu, float* __restrict__ ds_sg, int C,
+                                                        int S, int p) {
+  __shared__ float red[32];
+  const int n = blockIdx.x;
+  const int g = S / p, ppc = p * p * C, per = 2 * C * S * S;
+  float a_mu = 0.f, a_sg = 0.f;
+  const float smu = s_mu[n], ssg = s_sg[n];
+  for (int i = threadIdx.x; i < per; i += blockDim.x) {
+    int xx = i % S, r = i / S;
+    int yy = r % S;
+    int ch = r / S;
+    int part = ch / C, c = ch - part * C;
+    int hh = yy / p, p1 = yy - hh * p, ww = xx / p, p2 = xx - ww * p;
+    size_t li = ((size_t)n * (g * g) + hh * g + ww) * (2 * ppc) + part * ppc + (p1 * p + p2) * C + c;
+    float go = dout[(size_t)n * per + i];
+    float lv = ld_act(lin + li);
+    st_act(dlin + li, go * (part ? ssg : smu));
+    if (part) a_sg = fmaf(go, lv, a_sg);
+    else a_mu = fmaf(go, lv, a_mu);
+  }
+  a_mu = block_sum(a_mu, red);
+  a_sg = block_sum(a_sg, red);
+  if (threadIdx.x == 0) {
+    ds_mu[n] = a_mu;
+    ds_sg[n] = a_sg;
+  }
+}
+extern "C" int mapdit_final_bwd(const float* dout, const void* lin, const float* s_mu, const float* s_sigma, void* dlin, float* ds_mu,
+                                float* ds_sigma, int n_samples, int channels, int input_size, int patch, int dtype, void* stream) {
+  MAPDIT_REQUIRE(dout && lin && s_mu && s_sigma && dlin && ds_mu && ds_sigma && n_samples > 0, "final_bwd: bad args");
+  if (dtype == MAPDIT_F32)
+    final_bwd_kernel<float><<<n_samples, 256, 0, (cudaStream_t)stream>>>(dout, (const float*)lin, s_mu, s_sigma, (float*)dlin, ds_mu, ds_sigma, channels, input_size, patch);
+  else
+    final_bwd_kernel<bf16><<<n_samples, 256, 0, (cudaStream_t)stream>>>(dout, (const bf16*)lin, s_mu, s_sigma, (bf16*)dlin, ds_mu, ds_sigma, channels, input_size, patch);
+  MAPDIT_LAUNCH_CHECK("final_bwd");
+  return MAPDIT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// MPScale: s = sigmoid(a), a = sum_j l[n,j] ref[j] / sqrt(A), l = c W_eff^T  (src/blocks/final_layer.py:20-22)
+//   da = ds s (1-s);  dl[n,j] = da ref[j]/sqrt(A);  dref[j] = sum_n da l[n,j]/sqrt(A)   (single CTA)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) mp_scale_bwd_kernel(const float* __restrict__ ds, const float* __restrict__ s,
+                                                           const float* __restrict__ l, const float* __restrict__ ref,
+                                                           float* __restrict__ dl, float* __restrict__ dref, int n, int adim, int accumulate) {
+  __shared__ float red[32];
+  const float isq = rsqrtf((float)adim);
+  for (int j = 0; j < adim; ++j) {
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      float da = ds[i] * s[i] * (1.0f - s[i]);
+      dl[(size_t)i * adim + j] = da * ref[j] * isq;
+      acc = fmaf(da * isq, l[(size_t)i * adim + j], acc);
+    }
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) dref[j] = accumulate ? dref[j] + acc : acc;
+  }
+}
+extern "C" int mapdit_mp_scale_bwd(const float* ds, const float* s, const float* l, const float* ref, float* dl, float* dref, int n,
+                                   int adim, int accumulate, void* stream) {
+  MAPDIT_REQUIRE(ds && s && l && ref && dl && dref && n > 0 && adim > 0, "mp_scale_bwd: bad args");
+  mp_scale_bwd_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(ds, s, l, ref, dl, dref, n, adim, accumulate);
+  MAPDIT_LAUNCH_CHECK("mp_scale_bwd");
+  return MAPDIT_OK;
+}
+// forward companion: s[n] = sigmoid(sum_j l[n,j] ref[j]/sqrt(A)) from the precomputed l = c W_eff^T
+__global__ void mp_scale_from_lin_kernel(const float* __restrict__ l, const float* __restrict__ ref, float* __restrict__ s, int n, int adim) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float a = 0.f;
+  for (int j = 0; j < adim; ++j) a = fmaf(l[(size_t)i * adim + j], ref[j], a);
+  a /= sqrtf((float)adim);
+  s[i] = 1.0f / (1.0f + expf(-a));
+}
+extern "C" int mapdit_mp_scale_from_lin(const float* l, const float* ref, float* s, int n, int adim, void* stream) {
+  MAPDIT_REQUIRE(l && ref && s && n > 0, "mp_scale_from_lin: bad args");
+  mp_scale_from_lin_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(l, ref, s, n, adim);
+  MAPDIT_LAUNCH_CHECK("mp_scale_from_lin");
+  return MAPDIT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// conditioning path
+// ------------------------------------------------------------------------------------------------
+// c = (a+b) * 0.5 / sqrt(.5), cs = silu(c)/0.596 :  dc_total = dc + dcs * silu'(c)/0.596 ; da = db = dc_total * 0.5/sqrt(.5)
+__global__ void cond_combine_bwd_kernel(const float* __restrict__ c, const float* __restrict__ dc, const float* __restrict__ dcs,
+                                        float* __restrict__ dab, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float cv = c[i];
+  float s = 1.0f / (1.0f + expf(-cv));
+  float tot = (dc ? dc[i] : 0.f) + dcs[i] * (s * (1.0f + cv * (1.0f - s))) / MP_SILU_DIV;
+  dab[i] = tot * (0.5f / MP_HALF_DEN);
+}
+extern "C" int mapdit_cond_combine_bwd(const float* c, const float* dc, const float* dcs, float* dab, int64_t n, void* stream) {
+  MAPDIT_REQUIRE(c && dcs && dab && n > 0, "cond_combine_bwd: bad args");
+  cond_combine_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(c, dc, dcs, dab, n);
+  MAPDIT_LAUNCH_CHECK("cond_combine_bwd");
+  return MAPDIT_OK;
+}
+
+// label embedding: out[n] = normalize(E[id]) -> dE[id] += sqrt(d)/(r+eps) (G - v (v.G)/(r (r+eps)))  (rows may repeat: atomics)
+__global__ void __launch_bounds__(256) embed_rows_bwd_kernel(const int64_t* __restrict__ idx, const uint8_t* __restrict__ drop,
+                                                             int64_t null_idx, const float* __restrict__ table,
+                                                             const float* __restrict__ g, float* __restrict__ dtable, int d, float eps) {
+  __shared__ float red[32];
+  int n = blockIdx.x;
+  int64_t id = idx[n];
+  if (drop && drop[n]) id = null_idx;
+  const float* row = table + id * d;
+  float ss = 0.f, dot = 0.f;
+  for (int i = threadIdx.x; i < d; i += blockDim.x) {
+    ss = fmaf(row[i], row[i], ss);
+    dot = fmaf(row[i], g[(size_t)n * d + i], dot);
+  }
+  float r = sqrtf(block_sum(ss, red));
+  dot = block_sum(dot, red);
+  float k = sqrtf((float)d) / (r + eps);
+  float coef = dot / (fmaxf(r, 1e-30f) * (r + eps));
+  for (int i = threadIdx.x; i < d; i += blockDim.x) atomicAdd(dtable + id * d + i, k * (g[(size_t)n * d + i] - row[i] * coef));
+}
+extern "C" int mapdit_embed_rows_bwd(const int64_t* idx, const uint8_t* drop_mask, int64_t null_idx, const float* table,
+                                     const float* g, float* dtable, int n, int d, float eps, void* stream) {
+  MAPDIT_REQUIRE(idx && table && g && dtable && n > 0 && d > 0, "embed_rows_bwd: bad args");
+  embed_rows_bwd_kernel<<<n, 256, 0, (cudaStream_t)stream>>>(idx, drop_mask, null_idx, table, g, dtable, d, eps);
+  MAPDIT_LAUNCH_CHECK("embed_rows_bwd");
+  return MAPDIT_OK;
+}
+
+// patchify(x)|1 as an explicit [M, K+1] fp32 matrix (A operand of the x_embedder weight gradient)
+__global__ void patchify_kernel(const float* __restrict__ x, float* __restrict__ P, int64_t total, int C, int S, int p) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int g = S / p, K = p * p * C, K1 = K + 1;
+  int f = (int)(i % K1);
+  int64_t tok = i / K1;
+  float v = 1.0f;
+  if (f < K) {
+    int64_t n = tok / (g * g);
+    int tt = (int)(tok - n * (g * g));
+    int hh = tt / g, ww = tt - hh * g;
+    int c = f % C, pp = f / C, p1 = pp / p, p2 = pp - p1 * p;
+    v = x[((n * C + c) * S + (hh * p + p1)) * (int64_t)S + (ww * p + p2)];
+  }
+  P[i] = v;
+}
+extern "C" int mapdit_patchify(const float* x, float* P, int n_samples, int channels, int input_size, int patch, void* stream) {
+  MAPDIT_REQUIRE(x && P && n_samples > 0, "patchify: bad args");
+  int g = input_size / patch;
+  int64_t total = (int64_t)n_samples * g * g * (patch * patch * channels + 1);
+  patchify_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, P, total, channels, input_size, patch);
+  MAPDIT_LAUNCH_CHECK("patchify");
+  return MAPDIT_OK;
+}
+
+// generic: y = a*x (+ y)  fp32, used for tiny conditioning-path scalings
+__global__ void axpby_kernel(const float* __restrict__ x, float* __restrict__ y, float a, int accumulate, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = accumulate ? fmaf(a, x[i], y[i]) : a * x[i];
+}
+extern "C" int mapdit_axpby(const float* x, float* y, float a, int accumulate, int64_t n, void* stream) {
+  MAPDIT_REQUIRE(x && y && n > 0, "axpby: bad args");
+  axpby_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, y, a, accumulate, n);
+  MAPDIT_LAUNCH_CHECK("axpby");
+  return MAPDIT_OK;
+}
