@@ -41,11 +41,11 @@ int64_t mapdit_launch_count(void);
  * For each row r of w[rows, cols]:
  *   force != 0 : w[r] <- w[r]*sqrt(cols)/(||w[r]||+eps)   (written back in place, train mode)
  *   eff = w[r]/(||w[r]||+eps) (= normalize(w)/sqrt(cols)), computed from the (forced) row and
- *   written to any of eff_f32 [rows, cols], eff_bf16 [rows, cols], eff_bf16_t [cols, rows]
+ *   written to any of eff_f32 [rows, cols], eff_bf16 [rows, cols], eff_bf16_t [cols, ld_t >= rows]
  *   (transposed copy for dgrad).  inv_norm [rows] (optional) receives 1/(||w||+eps) of the
  *   row that eff was computed from (needed by the backward).                                  */
 int mapdit_weight_norm_fwd(float* w, int rows, int cols, float eps, int force, float* eff_f32,
-                           void* eff_bf16, void* eff_bf16_t, float* inv_norm, void* stream);
+                           void* eff_bf16, void* eff_bf16_t, int64_t ld_t /* 0 = rows */, float* inv_norm, void* stream);
 /* Backward of eff = v/(||v||+eps) per row: given G = dL/d eff [rows, cols]
  * and the (forced) weights v, grad_v = (G - v (v·G)/(r (r+eps)))/(r+eps); accumulate==0 overwrites. */
 int mapdit_weight_norm_bwd(const float* v, const float* g_eff, float* grad_v, int rows, int cols,
@@ -78,6 +78,8 @@ typedef struct mapdit_gemm_args {
   const float* shift; /* EPI_RESID_MOD */
   const float* scale; /* EPI_RESID_MOD */
   const float* gain;  /* EPI_RESID_MOD: device scalar g (blocks.i.gain_*) */
+  void* aux;          /* optional, for the backward: EPI_RESID*: bf16 [M,N] raw branch output (acc);
+                         EPI_QKNORM: fp32 [M, qk_cols/head_dim] per-head scale sqrt(hd)/(||v||+eps) */
   int64_t lda, ldb, ldo, ldmod;
   int m, n, k;
   int tokens;      /* rows per sample (sample index = row / tokens) */
@@ -90,6 +92,14 @@ typedef struct mapdit_gemm_args {
 
 int mapdit_gemm_bf16(const mapdit_gemm_args* args, void* stream);
 int mapdit_sizeof_gemm_args(void); /* lets a binding check its struct mirror */
+/* weight gradient C[N_out, K_in] (fp32) = dY[M, N_out]^T · X[M, K_in] on tcgen05, operands read MN-major in place
+ * (autograd of F.linear, src/basic/mp_linear.py:46,75); split-K with fp32 vector reductions when N_out*K_in is small */
+int mapdit_gemm_bf16_tn(const void* dy, int64_t ldy, const void* x, int64_t ldx, float* c, int64_t ldc, int m_tokens,
+                        int n_out, int k_in, void* stream);
+/* fused Adam step over one flat fp32 parameter span (torch.optim.Adam semantics, train.py:57,96):
+ * m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2; p -= lr * (m/bc1) / (sqrt(v/bc2) + eps) */
+int mapdit_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                     float bias_corr1, float bias_corr2, float grad_scale, void* stream);
 
 /* ---- K3 standalone elementwise ops (fp32 mode and fallbacks); dtype = activation dtype ------ */
 /* h = modulate(x, shift, scale, g) = lerp(x*scale, shift, g)/sqrt((1-g)^2+g^2)  (src/utils.py:11-16) */
@@ -109,8 +119,11 @@ int mapdit_cast(const void* src, void* dst, int64_t n, int src_dtype, int dst_dt
  * o[M, D] = merge_heads(softmax(q^ k^T / sqrt(hd)) v) for qkv[M, 3D] whose q,k heads are already
  * normalised (src/layers/attention.py:37-49).  f32: CUDA-core flash kernel (mode a);
  * bf16: tcgen05/TMEM kernel.                                                                   */
-int mapdit_cos_attn_fwd(const void* qkv, void* o, int n_samples, int tokens, int heads, int head_dim,
-                        int dtype, void* stream);
+int mapdit_cos_attn_fwd(const void* qkv, void* o, float* lse /* nullable: [M, H] log-sum-exp for the backward */,
+                        int n_samples, int tokens, int heads, int head_dim, int dtype, void* stream);
+/* dqkv[M, 3D] <- d/d(q^, k^, v) from dout[M, D]; delta: [M, H] fp32 scratch (src/layers/attention.py:47 autograd) */
+int mapdit_cos_attn_bwd(const void* qkv, const void* o, const void* dout, const float* lse, void* dqkv, float* delta,
+                        int n_samples, int tokens, int heads, int head_dim, int dtype, void* stream);
 
 /* ---- embedders / final layer ------------------------------------------------------------------ */
 /* x0 = mp_sum(patchify(x)|1 · Wx^T, pos, .5) (src/dit.py:81-84); optional h = modulate(x0,...).   */
@@ -164,6 +177,33 @@ int mapdit_posterior_mean(const float* x0, const float* x, const int64_t* t, con
                           float* mean, int n_samples, int chw, void* stream);
 int mapdit_noise_add(const float* mean, const float* log_variance, const float* noise, const int64_t* t,
                      float* sample, int n_samples, int chw, void* stream);
+
+/* ---- backward of the elementwise ops (closed forms: SURVEY.md §A.3) ------------------------------ */
+/* mp residual: R <- 0.7/den R (in place); dy = 0.3/den gate R; dgate[n, :] = sum_t 0.3/den y R */
+int mapdit_resid_bwd(void* R, const void* y, void* dy, const float* gate, float* dgate, int64_t ldmod, int n_samples,
+                     int d, int tokens, int dtype, void* stream);
+/* modulate: R (+)= dh (1-g)/den scale; dscale, dshift per sample; dg partial sums (one float per CTA,
+ * mapdit_modulate_bwd_partials() of them, finished by mapdit_sum_partials) */
+int mapdit_modulate_bwd(const void* dh, const void* x, void* R, const float* shift, const float* scale, const float* gain,
+                        float* dshift, float* dscale, float* dg_partial, int64_t ldmod, int n_samples, int d, int tokens,
+                        int accumulate, int dtype, void* stream);
+int mapdit_modulate_bwd_partials(int n_samples, int d);
+int mapdit_sum_partials(const float* partials, int n, float* out, int accumulate, void* stream);
+int mapdit_mp_silu_bwd(const void* du, const void* z, void* dz, int64_t n, int dtype, void* stream);
+/* q/k normalisation: forward variant that records sc = sqrt(hd)/(||v||+eps) [M, 2H], and its backward (in place on dqkv) */
+int mapdit_qk_normalize_save(void* qkv, float* sc, int m, int d, int head_dim, float eps, int dtype, void* stream);
+int mapdit_qk_norm_bwd(void* dqkv, const void* qkv, const float* sc, int m, int d, int head_dim, float eps, int dtype,
+                       void* stream);
+int mapdit_final_bwd(const float* dout, const void* lin, const float* s_mu, const float* s_sigma, void* dlin, float* ds_mu,
+                     float* ds_sigma, int n_samples, int channels, int input_size, int patch, int dtype, void* stream);
+int mapdit_mp_scale_from_lin(const float* l, const float* ref, float* s, int n, int adim, void* stream);
+int mapdit_mp_scale_bwd(const float* ds, const float* s, const float* l, const float* ref, float* dl, float* dref, int n,
+                        int adim, int accumulate, void* stream);
+int mapdit_cond_combine_bwd(const float* c, const float* dc, const float* dcs, float* dab, int64_t n, void* stream);
+int mapdit_embed_rows_bwd(const int64_t* idx, const uint8_t* drop_mask, int64_t null_idx, const float* table,
+                          const float* g, float* dtable, int n, int d, float eps, void* stream);
+int mapdit_patchify(const float* x, float* P, int n_samples, int channels, int input_size, int patch, void* stream);
+int mapdit_axpby(const float* x, float* y, float a, int accumulate, int64_t n, void* stream);
 
 #ifdef __cplusplus
 }

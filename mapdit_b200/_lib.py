@@ -18,22 +18,38 @@ _p, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 class GemmArgs(C.Structure):
     """mirror of mapdit_gemm_args (include/mapdit.h)"""
     _fields_ = [("a", _p), ("b", _p), ("out", _p), ("out2", _p), ("resid", _p), ("gate", _p), ("shift", _p),
-                ("scale", _p), ("gain", _p), ("lda", _i64), ("ldb", _i64), ("ldo", _i64), ("ldmod", _i64),
+                ("scale", _p), ("gain", _p), ("aux", _p), ("lda", _i64), ("ldb", _i64), ("ldo", _i64), ("ldmod", _i64),
                 ("m", _i), ("n", _i), ("k", _i), ("tokens", _i), ("head_dim", _i), ("qk_cols", _i),
                 ("epilogue", _i), ("out_dtype", _i), ("eps", _f)]
 
 
 SIGNATURES = {
-    "mapdit_weight_norm_fwd": [_p, _i, _i, _f, _i, _p, _p, _p, _p, _p],
+    "mapdit_weight_norm_fwd": [_p, _i, _i, _f, _i, _p, _p, _p, _i64, _p, _p],
     "mapdit_weight_norm_bwd": [_p, _p, _p, _i, _i, _f, _i, _p],
     "mapdit_gemm_f32": [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i, _i, _i, _i, _p],
     "mapdit_gemm_bf16": [C.POINTER(GemmArgs), _p],
+    "mapdit_gemm_bf16_tn": [_p, _i64, _p, _i64, _p, _i64, _i, _i, _i, _p],
+    "mapdit_adam_step": [_p, _p, _p, _p, _i64, _f, _f, _f, _f, _f, _f, _f, _p],
     "mapdit_modulate_fwd": [_p, _p, _p, _p, _p, _i64, _i, _i, _i, _i, _p],
     "mapdit_resid_fwd": [_p, _p, _p, _p, _i64, _i, _i, _i, _i, _p],
     "mapdit_mp_silu_fwd": [_p, _p, _i64, _i, _i, _p],
     "mapdit_qk_normalize": [_p, _i, _i, _i, _f, _i, _p],
     "mapdit_cast": [_p, _p, _i64, _i, _i, _p],
-    "mapdit_cos_attn_fwd": [_p, _p, _i, _i, _i, _i, _i, _p],
+    "mapdit_cos_attn_fwd": [_p, _p, _p, _i, _i, _i, _i, _i, _p],
+    "mapdit_cos_attn_bwd": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
+    "mapdit_resid_bwd": [_p, _p, _p, _p, _p, _i64, _i, _i, _i, _i, _p],
+    "mapdit_modulate_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _i, _i, _i, _p],
+    "mapdit_sum_partials": [_p, _i, _p, _i, _p],
+    "mapdit_mp_silu_bwd": [_p, _p, _p, _i64, _i, _p],
+    "mapdit_qk_normalize_save": [_p, _p, _i, _i, _i, _f, _i, _p],
+    "mapdit_qk_norm_bwd": [_p, _p, _p, _i, _i, _i, _f, _i, _p],
+    "mapdit_final_bwd": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
+    "mapdit_mp_scale_from_lin": [_p, _p, _p, _i, _i, _p],
+    "mapdit_mp_scale_bwd": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
+    "mapdit_cond_combine_bwd": [_p, _p, _p, _p, _i64, _p],
+    "mapdit_embed_rows_bwd": [_p, _p, _i64, _p, _p, _p, _i, _i, _f, _p],
+    "mapdit_patchify": [_p, _p, _i, _i, _i, _i, _p],
+    "mapdit_axpby": [_p, _p, _f, _i, _i64, _p],
     "mapdit_patch_embed": [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _i, _i, _i, _i, _p],
     "mapdit_fourier": [_p, _p, _p, _p, _i, _i, _p],
     "mapdit_embed_rows": [_p, _p, _i64, _p, _p, _i, _i, _f, _p],
@@ -67,6 +83,8 @@ def lib():
         L.mapdit_last_error.restype = C.c_char_p
         L.mapdit_abi_version.restype = _i
         L.mapdit_launch_count.restype = _i64
+        L.mapdit_modulate_bwd_partials.argtypes = [_i, _i]
+        L.mapdit_modulate_bwd_partials.restype = _i
         _lib = L
     return _lib
 

@@ -1,0 +1,327 @@
+"""Training-mode forward/backward of the whole DiT as one autograd node.
+
+The reference builds its graph from ~4k ATen ops per forward; here the forward saves
+exactly the activations the hand-written backward needs and the backward is a fixed kernel schedule
+using the closed forms of SURVEY.md §A.3 (weight-norm tangent projection, detached modulate
+denominator, mp residual, mp_silu, q/k normalisation, cosine attention).
+
+Gradient flow per block (reverse of src/blocks/dit_block.py:32-37), R = dL/dx residual stream:
+  resid_bwd -> fc2 wgrad/dgrad -> mp_silu_bwd -> fc1 wgrad/dgrad -> modulate_bwd (+= R)
+  resid_bwd -> out-proj wgrad/dgrad -> attention bwd -> qk_norm_bwd -> qkv wgrad/dgrad -> modulate_bwd (+= R)
+"""
+import torch
+
+from . import _lib, ops
+
+
+class _DiTFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, engine, x, t, y, drop_mask, *params):
+        out, saved = engine.trainer.forward(x, t, y, drop_mask)
+        ctx.engine = engine
+        ctx.saved = saved
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        grads = ctx.engine.trainer.backward(ctx.saved, dout.contiguous().float())
+        ctx.saved = None
+        return (None, None, None, None, None, *grads)
+
+
+def dit_forward_autograd(engine, x, t, y, drop_mask):
+    params = list(engine.m.parameters())
+    return _DiTFunction.apply(engine, x, t, y, drop_mask, *params)
+
+
+class Trainer:
+    """Owns the training workspaces (saved activations, gradient scratch) of one Engine."""
+
+    def __init__(self, engine):
+        self.e = engine
+        self.m = engine.m
+        self._bufs = {}
+        self.grad_buffers = None  # optional {id(param): preallocated grad tensor} (TrainStep's flat buffer)
+        self.grad_hook = None  # optional callable(list_of_(param, grad)) fired as soon as a block's grads are final
+
+    # ------------------------------------------------------------------ buffers
+    def buffers(self, N, mode, dev):
+        key = (N, mode, str(dev))
+        B = self._bufs.get(key)
+        if B is not None:
+            return B
+        m = self.m
+        D, L, H = m.hidden_size, m.depth, m.num_heads
+        T = (m.input_size // m.patch_size) ** 2
+        M = N * T
+        Hm = m.blocks[0].mlp.hidden_dim
+        adt = torch.bfloat16 if mode == "bf16" else torch.float32
+        a = dict(device=dev, dtype=adt)
+        f = dict(device=dev, dtype=torch.float32)
+        ppc2 = m.final_layer.linear.weight.shape[0]
+        K1 = m.x_embedder.weight.shape[1]
+        W = L * 6 * D + 2 * D
+        B = dict(
+            e=torch.empty(N, 256, **f), t1=torch.empty(N, D, **f), t1s=torch.empty(N, D, **f), temb=torch.empty(N, D, **f),
+            yemb=torch.empty(N, D, **f), c=torch.empty(N, D, **f), cs=torch.empty(N, D, **f),
+            cs16=torch.empty(N, D, device=dev, dtype=torch.bfloat16), mods=torch.empty(N, W, **f),
+            lmu=torch.empty(N, 8, **f), lsg=torch.empty(N, 8, **f), smu=torch.empty(N, **f), ssg=torch.empty(N, **f),
+            xin=[torch.empty(M, D, **a) for _ in range(L + 1)], h1=[torch.empty(M, D, **a) for _ in range(L + 1)],
+            qkv=[torch.empty(M, 3 * D, **a) for _ in range(L)], sc=[torch.empty(M, 2 * H, **f) for _ in range(L)],
+            lse=[torch.empty(M, H, **f) for _ in range(L)], o=[torch.empty(M, D, **a) for _ in range(L)],
+            a=[torch.empty(M, D, **a) for _ in range(L)], xmid=[torch.empty(M, D, **a) for _ in range(L)],
+            h2=[torch.empty(M, D, **a) for _ in range(L)], z=[torch.empty(M, Hm, **a) for _ in range(L)],
+            u=[torch.empty(M, Hm, **a) for _ in range(L)], b=[torch.empty(M, D, **a) for _ in range(L)],
+            lin=torch.empty(M, ppc2, **a),
+            # backward scratch
+            R=torch.empty(M, D, **a), dY=torch.empty(M, D, **a), dh=torch.empty(M, D, **a), dqkv=torch.empty(M, 3 * D, **a),
+            dU=torch.empty(M, Hm, **a), dlin=torch.empty(M, ppc2, **a), dmods=torch.empty(N, W, **f),
+            delta=torch.empty(M, H, **f), dgp=torch.empty(ops.modulate_bwd_partials(N, D), **f),
+            dsmu=torch.empty(N, **f), dssg=torch.empty(N, **f), dlmu=torch.empty(N, 8, **f), dlsg=torch.empty(N, 8, **f),
+            dc=torch.empty(N, D, **f), dcs=torch.empty(N, D, **f), dab=torch.empty(N, D, **f), dt1s=torch.empty(N, D, **f),
+            P=torch.empty(M, K1, **f), R32=torch.empty(M, D, **f) if mode == "bf16" else None,
+            dmods16=torch.empty(N, W, device=dev, dtype=torch.bfloat16) if mode == "bf16" else None,
+            dWs=torch.empty(max(Hm * D, W * D), **f),  # scratch for d(effective weight), largest weight
+        )
+        self._bufs[key] = B
+        return B
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, x, t, y, drop_mask):
+        e, m = self.e, self.m
+        mode = m.compute_dtype
+        bf = mode == "bf16"
+        N, dev = x.shape[0], x.device
+        D, L, H = m.hidden_size, m.depth, m.num_heads
+        hd = D // H
+        T = (m.input_size // m.patch_size) ** 2
+        x = x.contiguous().float()
+        t = t.contiguous().to(torch.int64)
+        y = y.contiguous().to(torch.int64)
+        W = e.weights(mode, train=True)
+        B = self.buffers(N, mode, dev)
+        ld = B["mods"].shape[1]
+        f = m.final_layer
+        blk = m.blocks
+
+        ops.fourier(t, m.t_embedder.embedding.scale, m.t_embedder.embedding.shift, B["e"])
+        ops.gemm_f32(B["e"], W.wt1, out=B["t1"])
+        ops.mp_silu(B["t1"], B["t1s"])
+        ops.gemm_f32(B["t1s"], W.wt2, out=B["temb"])
+        mask = None
+        if m.y_embedder.dropout_prob > 0:
+            if drop_mask is None:
+                drop_mask = torch.rand(N, device=dev) < m.y_embedder.dropout_prob
+            mask = drop_mask.to(torch.uint8).contiguous()
+        ops.embed_rows(y, mask, m.num_classes, m.y_embedder.embedding.weight.data, B["yemb"])
+        ops.cond_combine(B["temb"], B["yemb"], B["c"], B["cs"], B["cs16"])
+        if bf:
+            ops.gemm_bf16(B["cs16"], W.wmod, B["mods"])
+        else:
+            ops.gemm_f32(B["cs"], W.wmod, out=B["mods"])
+        ops.gemm_f32(B["c"], W.wmu, out=B["lmu"])
+        ops.gemm_f32(B["c"], W.wsg, out=B["lsg"])
+        ops.mp_scale_from_lin(B["lmu"], f.mean_scale.reference.data, B["smu"])
+        ops.mp_scale_from_lin(B["lsg"], f.sigma_scale.reference.data, B["ssg"])
+        mods = B["mods"]
+
+        def mod(i, j):
+            return mods[:, i * 6 * D + j * D:]
+
+        ops.patch_embed(x, W.wx, m.pos_embed, B["xin"][0], B["h1"][0], mod(0, 0), mod(0, 1), blk[0].gain_msa.data, ld, m.patch_size)
+        for i in range(L):
+            xin, h1, qkv, o, a, xmid, h2, z, u, b = (B[k][i] for k in ("xin", "h1", "qkv", "o", "a", "xmid", "h2", "z", "u", "b"))
+            xnext, hnext = B["xin"][i + 1], B["h1"][i + 1]
+            if i + 1 < L:
+                nsh, nsc, ngn = mod(i + 1, 0), mod(i + 1, 1), blk[i + 1].gain_msa.data
+            else:
+                nsh, nsc, ngn = mods[:, L * 6 * D:], mods[:, L * 6 * D + D:], f.gain_mod.data
+            if bf:
+                ops.gemm_bf16(h1, W.wqkv[i], qkv, epilogue=_lib.EPI_QKNORM, tokens=T, head_dim=hd, qk_cols=2 * D,
+                              aux=B["sc"][i] if hd == 64 else None)
+                if hd != 64:
+                    raise NotImplementedError("bf16 training needs head_dim 64 (DiT-XL uses 72): use compute_dtype='fp32'")
+                ops.cos_attn(qkv, o, N, T, H, hd, lse=B["lse"][i])
+                ops.gemm_bf16(o, W.wo[i], xmid, epilogue=_lib.EPI_RESID_MOD, out2=h2, resid=xin, gate=mod(i, 2), shift=mod(i, 3),
+                              scale=mod(i, 4), gain=blk[i].gain_mlp.data, ldmod=ld, tokens=T, aux=a)
+                ops.gemm_bf16(h2, W.w1[i], u, epilogue=_lib.EPI_MPSILU, out2=z)
+                ops.gemm_bf16(u, W.w2[i], xnext, epilogue=_lib.EPI_RESID_MOD, out2=hnext, resid=xmid, gate=mod(i, 5), shift=nsh,
+                              scale=nsc, gain=ngn, ldmod=ld, tokens=T, aux=b)
+            else:
+                ops.gemm_f32(h1, W.wqkv[i], out=qkv)
+                ops.qk_normalize_save(qkv, B["sc"][i], D, hd)
+                ops.cos_attn(qkv, o, N, T, H, hd, lse=B["lse"][i])
+                ops.gemm_f32(o, W.wo[i], out=a)
+                ops.resid(xin, a, xmid, mod(i, 2), ld, T)
+                ops.modulate(xmid, h2, mod(i, 3), mod(i, 4), blk[i].gain_mlp.data, ld, T)
+                ops.gemm_f32(h2, W.w1[i], out=z)
+                ops.mp_silu(z, u)
+                ops.gemm_f32(u, W.w2[i], out=b)
+                ops.resid(xmid, b, xnext, mod(i, 5), ld, T)
+                ops.modulate(xnext, hnext, nsh, nsc, ngn, ld, T)
+        hF = B["h1"][L]
+        if bf:
+            ops.gemm_bf16(hF, W.wfl, B["lin"])
+        else:
+            ops.gemm_f32(hF, W.wfl, out=B["lin"])
+        out = torch.empty(N, 2 * m.in_channels, m.input_size, m.input_size, device=dev, dtype=torch.float32)
+        ops.final_unpatchify(B["lin"], B["smu"], B["ssg"], out, m.patch_size)
+        saved = dict(N=N, mode=mode, dev=dev, x=x, t=t, y=y, mask=mask)
+        return out, saved
+
+    # ------------------------------------------------------------------ backward helpers
+    def _dgrad(self, dy, w_eff, w_eff_t, out, bf):
+        """out[M, K_in] = dy[M, N_out] @ W_eff[N_out, K_in]"""
+        if bf:
+            ops.gemm_bf16(dy, w_eff_t, out)
+        else:
+            ops.gemm_f32(dy, w_eff, out=out, trans_b=True)
+
+    def _wgrad(self, dy, xin, param, bf, B, grads, rows=None):
+        """param.grad = weight_norm_bwd(forced param, dy^T @ xin)"""
+        n_out, k_in = param.shape
+        dW = B["dWs"][: n_out * k_in].view(n_out, k_in)
+        if bf:
+            ops.gemm_bf16_tn(dy, xin, dW)
+        else:
+            ops.gemm_f32(dy, xin, out=dW, trans_a=True, trans_b=True)
+        g = self._gbuf(param)
+        ops.weight_norm_bwd(param.data, dW, g)
+        grads[id(param)] = g
+
+    def _gbuf(self, p):
+        """gradient destination of parameter p: a view of the caller's flat gradient buffer, or a fresh tensor"""
+        if self.grad_buffers is not None:
+            return self.grad_buffers[id(p)]
+        return torch.empty_like(p.data)
+
+    def _scalar_from_partials(self, B, n, p):
+        g = self._gbuf(p)
+        ops.sum_partials(B["dgp"], n, g)
+        return g
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, saved, dout):
+        e, m = self.e, self.m
+        N, mode, dev = saved["N"], saved["mode"], saved["dev"]
+        bf = mode == "bf16"
+        D, L, H = m.hidden_size, m.depth, m.num_heads
+        hd = D // H
+        T = (m.input_size // m.patch_size) ** 2
+        W = e._w[mode]
+        B = self.buffers(N, mode, dev)
+        ld = B["mods"].shape[1]
+        f = m.final_layer
+        blk = m.blocks
+        mods, dmods = B["mods"], B["dmods"]
+        npart = ops.modulate_bwd_partials(N, D)
+        grads = {}
+
+        def mod(buf, i, j):
+            return buf[:, i * 6 * D + j * D:]
+
+        R, dY, dh, dqkv, dU = B["R"], B["dY"], B["dh"], B["dqkv"], B["dU"]
+        # ---- final layer (src/blocks/final_layer.py:53-59)
+        ops.final_bwd(dout, B["lin"], B["smu"], B["ssg"], B["dlin"], B["dsmu"], B["dssg"], m.patch_size)
+        gref_mu, gref_sg = self._gbuf(f.mean_scale.reference), self._gbuf(f.sigma_scale.reference)
+        ops.mp_scale_bwd(B["dsmu"], B["smu"], B["lmu"], f.mean_scale.reference.data, B["dlmu"], gref_mu)
+        ops.mp_scale_bwd(B["dssg"], B["ssg"], B["lsg"], f.sigma_scale.reference.data, B["dlsg"], gref_sg)
+        grads[id(f.mean_scale.reference)] = gref_mu
+        grads[id(f.sigma_scale.reference)] = gref_sg
+        ops.gemm_f32(B["dlmu"], W.wmu, out=B["dc"], trans_b=True)                      # dc = dl_mu @ W_mu
+        ops.gemm_f32(B["dlsg"], W.wsg, out=B["dc"], trans_b=True, accumulate=True)
+        for dl, p in ((B["dlmu"], f.mean_scale.linear.weight), (B["dlsg"], f.sigma_scale.linear.weight)):
+            dW = B["dWs"][: 8 * D].view(8, D)
+            ops.gemm_f32(dl, B["c"], out=dW, trans_a=True, trans_b=True)
+            g = self._gbuf(p)
+            ops.weight_norm_bwd(p.data, dW, g)
+            grads[id(p)] = g
+        hF, xF = B["h1"][L], B["xin"][L]
+        self._wgrad(B["dlin"], hF, f.linear.weight, bf, B, grads)
+        self._dgrad(B["dlin"], W.wfl, getattr(W, "wfl_t", None), dh, bf)
+        ops.modulate_bwd(dh, xF, R, mods[:, L * 6 * D:], mods[:, L * 6 * D + D:], f.gain_mod.data, dmods[:, L * 6 * D:],
+                         dmods[:, L * 6 * D + D:], B["dgp"], ld, N, T, False)
+        grads[id(f.gain_mod)] = self._scalar_from_partials(B, npart, f.gain_mod)
+        # ---- blocks, last to first
+        for i in range(L - 1, -1, -1):
+            xin, h1, qkv, o, a, xmid, h2, z, u, b = (B[k][i] for k in ("xin", "h1", "qkv", "o", "a", "xmid", "h2", "z", "u", "b"))
+            wt = (lambda name: getattr(W, name)[i]) if bf else (lambda name: None)
+            # MLP branch
+            ops.resid_bwd(R, b, dY, mod(mods, i, 5), mod(dmods, i, 5), ld, N, T)
+            self._wgrad(dY, u, blk[i].mlp.net[2].weight, bf, B, grads)
+            self._dgrad(dY, W.w2[i], wt("w2_t"), dU, bf)
+            ops.mp_silu_bwd(dU, z, dU)
+            self._wgrad(dU, h2, blk[i].mlp.net[0].weight, bf, B, grads)
+            self._dgrad(dU, W.w1[i], wt("w1_t"), dh, bf)
+            ops.modulate_bwd(dh, xmid, R, mod(mods, i, 3), mod(mods, i, 4), blk[i].gain_mlp.data, mod(dmods, i, 3), mod(dmods, i, 4),
+                             B["dgp"], ld, N, T, True)
+            grads[id(blk[i].gain_mlp)] = self._scalar_from_partials(B, npart, blk[i].gain_mlp)
+            # attention branch
+            ops.resid_bwd(R, a, dY, mod(mods, i, 2), mod(dmods, i, 2), ld, N, T)
+            self._wgrad(dY, o, blk[i].attn.out_proj.weight, bf, B, grads)
+            self._dgrad(dY, W.wo[i], wt("wo_t"), dh, bf)
+            ops.cos_attn_bwd(qkv, o, dh, B["lse"][i], dqkv, B["delta"], N, T, H, hd)
+            ops.qk_norm_bwd(dqkv, qkv, B["sc"][i], D, hd)
+            self._wgrad(dqkv, h1, blk[i].attn.qkv_proj.weight, bf, B, grads)
+            self._dgrad(dqkv, W.wqkv[i], wt("wqkv_t"), dh, bf)
+            ops.modulate_bwd(dh, xin, R, mod(mods, i, 0), mod(mods, i, 1), blk[i].gain_msa.data, mod(dmods, i, 0), mod(dmods, i, 1),
+                             B["dgp"], ld, N, T, True)
+            grads[id(blk[i].gain_msa)] = self._scalar_from_partials(B, npart, blk[i].gain_msa)
+            if self.grad_hook is not None:
+                self.grad_hook([(p, grads[id(p)]) for p in blk[i].parameters() if id(p) in grads])
+        # ---- patch embed (src/dit.py:81-84): x0 = (lin + pos)/2/sqrt(.5) -> d lin = R * 0.5/sqrt(.5)
+        ops.patchify(saved["x"], B["P"], m.patch_size)
+        R32 = R
+        if bf:
+            ops.cast(R, B["R32"])
+            R32 = B["R32"]
+        K1 = m.x_embedder.weight.shape[1]
+        dWx = B["dWs"][: D * K1].view(D, K1)
+        ops.gemm_f32(R32, B["P"], out=dWx, trans_a=True, trans_b=True)
+        ops.axpby(dWx, dWx, 0.5 / 0.7071067811865476, False)
+        g = self._gbuf(m.x_embedder.weight)
+        ops.weight_norm_bwd(m.x_embedder.weight.data, dWx, g)
+        grads[id(m.x_embedder.weight)] = g
+        # ---- modulation GEMM of all blocks + final (one wgrad / dgrad over the concatenated weight)
+        Wtot = dmods.shape[1]
+        dWm = B["dWs"][: Wtot * D].view(Wtot, D)
+        if bf:
+            ops.cast(dmods, B["dmods16"])
+            ops.gemm_bf16(B["dmods16"], W.wmod_t, B["dcs"])
+            ops.gemm_bf16_tn(B["dmods16"], B["cs16"], dWm)
+        else:
+            ops.gemm_f32(dmods, W.wmod, out=B["dcs"], trans_b=True)
+            ops.gemm_f32(dmods, B["cs"], out=dWm, trans_a=True, trans_b=True)
+        for i in range(L):
+            p = blk[i].modulation[1].weight
+            g = self._gbuf(p)
+            ops.weight_norm_bwd(p.data, dWm[i * 6 * D:(i + 1) * 6 * D], g)
+            grads[id(p)] = g
+        p = f.modulation[1].weight
+        g = self._gbuf(p)
+        ops.weight_norm_bwd(p.data, dWm[L * 6 * D:], g)
+        grads[id(p)] = g
+        # ---- conditioning path (src/dit.py:86-88)
+        ops.cond_combine_bwd(B["c"], B["dc"], B["dcs"], B["dab"])
+        table = m.y_embedder.embedding.weight
+        gt = self._gbuf(table)
+        gt.zero_()
+        ops.embed_rows_bwd(saved["y"], saved["mask"], m.num_classes, table.data, B["dab"], gt)
+        grads[id(table)] = gt
+        p2, p1 = m.t_embedder.mlp.net[2].weight, m.t_embedder.mlp.net[0].weight
+        dW = B["dWs"][: D * D].view(D, D)
+        ops.gemm_f32(B["dab"], B["t1s"], out=dW, trans_a=True, trans_b=True)
+        g = self._gbuf(p2)
+        ops.weight_norm_bwd(p2.data, dW, g)
+        grads[id(p2)] = g
+        ops.gemm_f32(B["dab"], W.wt2, out=B["dt1s"], trans_b=True)
+        ops.mp_silu_bwd(B["dt1s"], B["t1"], B["dt1s"])
+        dW = B["dWs"][: D * 256].view(D, 256)
+        ops.gemm_f32(B["dt1s"], B["e"], out=dW, trans_a=True, trans_b=True)
+        g = self._gbuf(p1)
+        ops.weight_norm_bwd(p1.data, dW, g)
+        grads[id(p1)] = g
+        if self.grad_hook is not None:
+            done = {id(q) for b_ in blk for q in b_.parameters() if q is not b_.modulation[1].weight}
+            self.grad_hook([(q, grads[id(q)]) for q in m.parameters() if id(q) not in done])
+        return [grads[id(p)] for p in m.parameters()]

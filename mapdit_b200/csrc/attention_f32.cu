@@ -10,8 +10,8 @@ namespace {
 constexpr int KB = 32;  // keys per smem block
 
 template <typename T, int HD>
-__global__ void __launch_bounds__(128) attn_simt_kernel(const T* __restrict__ qkv, T* __restrict__ o, int tokens, int heads,
-                                                        float scale) {
+__global__ void __launch_bounds__(128) attn_simt_kernel(const T* __restrict__ qkv, T* __restrict__ o, float* __restrict__ lse,
+                                                        int tokens, int heads, float scale) {
   __shared__ __align__(16) float Ks[KB][HD];
   __shared__ __align__(16) float Vs[KB][HD];
   const int n = blockIdx.z, h = blockIdx.y;
@@ -81,26 +81,27 @@ __global__ void __launch_bounds__(128) attn_simt_kernel(const T* __restrict__ qk
     T* orow = o + ((size_t)n * tokens + qi) * D + h * HD;
 #pragma unroll
     for (int d = 0; d < HD; ++d) st_act(orow + d, acc[d] * inv);
+    if (lse) lse[((size_t)n * tokens + qi) * heads + h] = mrun + logf(lrun);
   }
 }
 
 template <typename T>
-int launch(const void* qkv, void* o, int n, int tokens, int heads, int hd, cudaStream_t s) {
+int launch(const void* qkv, void* o, float* lse, int n, int tokens, int heads, int hd, cudaStream_t s) {
   dim3 grid((tokens + 127) / 128, heads, n);
   float scale = 1.0f / sqrtf((float)hd);
   switch (hd) {
-    case 64: attn_simt_kernel<T, 64><<<grid, 128, 0, s>>>((const T*)qkv, (T*)o, tokens, heads, scale); break;
-    case 72: attn_simt_kernel<T, 72><<<grid, 128, 0, s>>>((const T*)qkv, (T*)o, tokens, heads, scale); break;
-    case 32: attn_simt_kernel<T, 32><<<grid, 128, 0, s>>>((const T*)qkv, (T*)o, tokens, heads, scale); break;
+    case 64: attn_simt_kernel<T, 64><<<grid, 128, 0, s>>>((const T*)qkv, (T*)o, lse, tokens, heads, scale); break;
+    case 72: attn_simt_kernel<T, 72><<<grid, 128, 0, s>>>((const T*)qkv, (T*)o, lse, tokens, heads, scale); break;
+    case 32: attn_simt_kernel<T, 32><<<grid, 128, 0, s>>>((const T*)qkv, (T*)o, lse, tokens, heads, scale); break;
     default: mapdit_set_error("cos_attn_fwd: unsupported head_dim %d", hd); return MAPDIT_ERR_UNSUPPORTED;
   }
   return MAPDIT_OK;
 }
 }  // namespace
 
-int mapdit_attn_simt_fwd(const void* qkv, void* o, int n, int tokens, int heads, int hd, int dtype, void* stream) {
-  int rc = (dtype == MAPDIT_F32) ? launch<float>(qkv, o, n, tokens, heads, hd, (cudaStream_t)stream)
-                                 : launch<bf16>(qkv, o, n, tokens, heads, hd, (cudaStream_t)stream);
+int mapdit_attn_simt_fwd(const void* qkv, void* o, float* lse, int n, int tokens, int heads, int hd, int dtype, void* stream) {
+  int rc = (dtype == MAPDIT_F32) ? launch<float>(qkv, o, lse, n, tokens, heads, hd, (cudaStream_t)stream)
+                                 : launch<bf16>(qkv, o, lse, n, tokens, heads, hd, (cudaStream_t)stream);
   if (rc != MAPDIT_OK) return rc;
   MAPDIT_LAUNCH_CHECK("attn_simt_fwd");
   return MAPDIT_OK;

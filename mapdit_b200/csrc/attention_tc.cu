@@ -31,8 +31,8 @@ __device__ __forceinline__ float ex2(float x) {
 }
 
 __global__ void __launch_bounds__(NTHREADS, 2)
-attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, bf16* __restrict__ o, int tokens,
-               int heads) {
+attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, bf16* __restrict__ o,
+               float* __restrict__ lse, int tokens, int heads) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -178,6 +178,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     tmem_ld_wait();
     if (q0 + r < tokens) {
       const float inv = 1.0f / rowsum;
+      if (lse) lse[(size_t)(row_base + q0 + r) * heads + h] = 8.0f + logf(rowsum);
       bf16* dst = o + (size_t)(row_base + q0 + r) * D + h * HD;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -207,7 +208,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
 
 bool mapdit_attn_tc_supported(int tokens, int hd) { return hd == HD && tokens % KB == 0 && tokens >= KB; }
 
-int mapdit_attn_tc_fwd(const void* qkv, void* o, int n, int tokens, int heads, int hd, void* stream) {
+int mapdit_attn_tc_fwd(const void* qkv, void* o, float* lse, int n, int tokens, int heads, int hd, void* stream) {
   const int D = heads * hd;
   CUtensorMap tq, tkv;
   const uint64_t dims[2] = {(uint64_t)3 * D, (uint64_t)n * tokens};
@@ -229,7 +230,7 @@ int mapdit_attn_tc_fwd(const void* qkv, void* o, int n, int tokens, int heads, i
     attr_set = true;
   }
   dim3 grid((tokens + QT - 1) / QT, heads, n);
-  attn_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tq, tkv, (bf16*)o, tokens, heads);
+  attn_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tq, tkv, (bf16*)o, lse, tokens, heads);
   MAPDIT_LAUNCH_CHECK("attn_tc_fwd");
   return MAPDIT_OK;
 }

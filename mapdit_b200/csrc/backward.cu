@@ -114,7 +114,7 @@ extern "C" int mapdit_sum_partials(const float* partials, int n, float* out, int
 // u = silu(z)/0.596 :  dz = du * sigma(z) (1 + z (1 - sigma(z))) / 0.596
 // ------------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void mp_silu_bwd_kernel(const T* __restrict__ du, const T* __restrict__ z, T* __restrict__ dz, int64_t n) {
+__global__ void mp_silu_bwd_kernel(const T* du, const T* __restrict__ z, T* dz, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float zv = ld_act(z + i);
     float s = 1.0f / (1.0f + expf(-zv));
@@ -375,7 +375,7 @@ extern "C" int mapdit_patchify(const float* x, float* P, int n_samples, int chan
 }
 
 // generic: y = a*x (+ y)  fp32, used for tiny conditioning-path scalings
-__global__ void axpby_kernel(const float* __restrict__ x, float* __restrict__ y, float a, int accumulate, int64_t n) {
+__global__ void axpby_kernel(const float* x, float* y, float a, int accumulate, int64_t n) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) y[i] = accumulate ? fmaf(a, x[i], y[i]) : a * x[i];
 }

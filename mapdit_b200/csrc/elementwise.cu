@@ -33,7 +33,7 @@ extern "C" int64_t mapdit_launch_count(void) { return (int64_t)g_launches.load()
 __global__ void __launch_bounds__(256) weight_norm_fwd_kernel(float* __restrict__ w, int cols, float eps, int force,
                                                               float* __restrict__ eff_f32, bf16* __restrict__ eff_bf16,
                                                               bf16* __restrict__ eff_bf16_t, float* __restrict__ inv_norm,
-                                                              int rows) {
+                                                              int rows, int64_t ld_t) {
   __shared__ float red[32];
   const int r = blockIdx.x;
   float* row = w + (size_t)r * cols;
@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(256) weight_norm_fwd_kernel(float* __restrict_
       float e = v * inv;
       if (eff_f32) eff_f32[(size_t)r * cols + i] = e;
       if (eff_bf16) eff_bf16[(size_t)r * cols + i] = __float2bfloat16_rn(e);
-      if (eff_bf16_t) eff_bf16_t[(size_t)i * rows + r] = __float2bfloat16_rn(e);
+      if (eff_bf16_t) eff_bf16_t[(size_t)i * ld_t + r] = __float2bfloat16_rn(e);
     }
   } else {
     inv = 1.0f / (nrm + eps);
@@ -69,17 +69,17 @@ __global__ void __launch_bounds__(256) weight_norm_fwd_kernel(float* __restrict_
       float e = row[i] * inv;
       if (eff_f32) eff_f32[(size_t)r * cols + i] = e;
       if (eff_bf16) eff_bf16[(size_t)r * cols + i] = __float2bfloat16_rn(e);
-      if (eff_bf16_t) eff_bf16_t[(size_t)i * rows + r] = __float2bfloat16_rn(e);
+      if (eff_bf16_t) eff_bf16_t[(size_t)i * ld_t + r] = __float2bfloat16_rn(e);
     }
   }
   if (inv_norm && threadIdx.x == 0) inv_norm[r] = inv;
 }
 
 extern "C" int mapdit_weight_norm_fwd(float* w, int rows, int cols, float eps, int force, float* eff_f32, void* eff_bf16,
-                                      void* eff_bf16_t, float* inv_norm, void* stream) {
+                                      void* eff_bf16_t, int64_t ld_t, float* inv_norm, void* stream) {
   MAPDIT_REQUIRE(w && rows > 0 && cols > 0, "weight_norm_fwd: bad args");
   weight_norm_fwd_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(w, cols, eps, force, eff_f32, (bf16*)eff_bf16,
-                                                                  (bf16*)eff_bf16_t, inv_norm, rows);
+                                                                  (bf16*)eff_bf16_t, inv_norm, rows, ld_t > 0 ? ld_t : rows);
   MAPDIT_LAUNCH_CHECK("weight_norm_fwd");
   return MAPDIT_OK;
 }

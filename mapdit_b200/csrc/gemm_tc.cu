@@ -43,6 +43,7 @@ struct EpiParams {
   const float* shift;
   const float* scale;
   const float* gain;
+  void* aux;
   long long ldo, ldmod;
   int M, N, tokens, qk_cols, epilogue, out_f32;
   float eps;
@@ -224,6 +225,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 #pragma unroll
               for (int j = 0; j < 32; ++j) ss = fmaf(f0[j], f0[j], fmaf(f1[j], f1[j], ss));
               const float sc = 8.0f / (sqrtf(ss) + ep.eps);  // sqrt(head_dim = 64)
+              if (ep.aux && row_ok) reinterpret_cast<float*>(ep.aux)[(long long)row * (ep.qk_cols >> 6) + (col >> 6)] = sc;
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
                 f0[j] *= sc;
@@ -258,6 +260,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           } else {  // RESID / RESID_MOD
             float xo[32], gt[32];
             load_row32_bf16(ep.resid, off, xo, nvalid);
+            if (ep.aux) store_row32(ep.aux, off, f, nvalid, false);  // raw branch output, needed for d(gate)
             load_row32_f32(ep.gate + sample * ep.ldmod + col, gt, nvalid);
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = fmaf(MP_RES_T, gt[j] * f[j] - xo[j], xo[j]) * (1.0f / MP_RES_DEN);
@@ -365,7 +368,7 @@ extern "C" int mapdit_gemm_bf16(const mapdit_gemm_args* g, void* stream) {
   MAPDIT_REQUIRE(epi == MAPDIT_EPI_STORE || g->out_dtype == MAPDIT_BF16, "gemm_bf16: fused epilogues write bf16");
   EpiParams ep;
   ep.out = g->out; ep.out2 = g->out2; ep.resid = g->resid; ep.gate = g->gate; ep.shift = g->shift; ep.scale = g->scale;
-  ep.gain = g->gain; ep.ldo = g->ldo; ep.ldmod = g->ldmod; ep.M = g->m; ep.N = g->n; ep.tokens = g->tokens > 0 ? g->tokens : 1;
+  ep.gain = g->gain; ep.aux = g->aux; ep.ldo = g->ldo; ep.ldmod = g->ldmod; ep.M = g->m; ep.N = g->n; ep.tokens = g->tokens > 0 ? g->tokens : 1;
   ep.qk_cols = g->qk_cols; ep.epilogue = epi; ep.out_f32 = (g->out_dtype == MAPDIT_F32); ep.eps = g->eps;
 
   const int sms = num_sms_cached();

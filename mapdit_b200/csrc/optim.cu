@@ -1,0 +1,46 @@
+// Fused Adam over a flat fp32 span ("next" row N1: train.py:57,96 -> torch.optim.Adam(lr, betas=(0.9, 0.99))).
+// 16 B/param of state traffic + 4 B grad read: HBM-bound, 128-bit vectorised.
+#include "common.cuh"
+
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                   float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps, float bc1,
+                                                   float bc2, float gs) {
+  const int64_t i4 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i4 >= n) return;
+  const float step = lr / bc1;
+  const float inv_sqrt_bc2 = rsqrtf(bc2);
+  if (i4 + 4 <= n && ((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0)) {
+    float4 pv = *reinterpret_cast<float4*>(p + i4), gv = *reinterpret_cast<const float4*>(g + i4);
+    float4 mv = *reinterpret_cast<float4*>(m + i4), vv = *reinterpret_cast<float4*>(v + i4);
+    float* pp = &pv.x; float* gg = &gv.x; float* mm = &mv.x; float* vq = &vv.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float gr = gg[j] * gs;
+      mm[j] = b1 * mm[j] + (1.0f - b1) * gr;
+      vq[j] = b2 * vq[j] + (1.0f - b2) * gr * gr;
+      pp[j] -= step * mm[j] / (sqrtf(vq[j]) * inv_sqrt_bc2 + eps);
+    }
+    *reinterpret_cast<float4*>(p + i4) = pv;
+    *reinterpret_cast<float4*>(m + i4) = mv;
+    *reinterpret_cast<float4*>(v + i4) = vv;
+  } else {
+    for (int64_t i = i4; i < n && i < i4 + 4; ++i) {
+      float gr = g[i] * gs;
+      float mi = b1 * m[i] + (1.0f - b1) * gr;
+      float vi = b2 * v[i] + (1.0f - b2) * gr * gr;
+      m[i] = mi;
+      v[i] = vi;
+      p[i] -= step * mi / (sqrtf(vi) * inv_sqrt_bc2 + eps);
+    }
+  }
+}
+
+extern "C" int mapdit_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                                float bias_corr1, float bias_corr2, float grad_scale, void* stream) {
+  MAPDIT_REQUIRE(p && g && m && v && n > 0, "adam_step: bad args");
+  int64_t threads = (n + 3) / 4;
+  adam_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, bias_corr1,
+                                                                                    bias_corr2, grad_scale);
+  MAPDIT_LAUNCH_CHECK("adam_step");
+  return MAPDIT_OK;
+}

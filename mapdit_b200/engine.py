@@ -45,6 +45,13 @@ class Engine:
     def invalidate(self):
         self._dirty = True
 
+    @property
+    def trainer(self):
+        if getattr(self, "_trainer", None) is None:
+            from .autograd import Trainer
+            self._trainer = Trainer(self)
+        return self._trainer
+
     def weights(self, mode, train):
         """(Re)build the effective weights.  Train mode always re-normalises, writing the forced
         normalisation back into the parameters first (src/basic/mp_linear.py:37-40)."""
@@ -77,9 +84,22 @@ class Engine:
             W.wfl = torch.empty_like(m.final_layer.linear.weight, **wd)
             self._w[mode] = W
         force = bool(train)
+        want_t = bool(train) and mode == "bf16"  # transposed bf16 copies feed the dgrad GEMMs
+        if want_t and not hasattr(W, "wqkv_t"):
+            wd = dict(device=dev, dtype=wdt)
+            Hm = m.blocks[0].mlp.hidden_dim
+            W.wqkv_t = [torch.empty(D, 3 * D, **wd) for _ in range(L)]
+            W.wo_t = [torch.empty(D, D, **wd) for _ in range(L)]
+            W.w1_t = [torch.empty(D, Hm, **wd) for _ in range(L)]
+            W.w2_t = [torch.empty(Hm, D, **wd) for _ in range(L)]
+            W.wfl_t = torch.empty(D, m.final_layer.linear.weight.shape[0], **wd)
+            W.wmod_t = torch.empty(D, W.mod_total, **wd)
 
-        def norm(p, out):
+        def norm(p, out, out_t=None, ld_t=0):
             kw = {"eff_bf16": out} if out.dtype == torch.bfloat16 else {"eff_f32": out}
+            if want_t and out_t is not None:
+                kw["eff_bf16_t"] = out_t
+                kw["ld_t"] = ld_t
             ops.weight_norm_fwd(p.data, force=force, **kw)
 
         norm(m.x_embedder.weight, W.wx)
@@ -87,15 +107,16 @@ class Engine:
         norm(m.t_embedder.mlp.net[2].weight, W.wt2)
         if force:  # the embedding table is normalised in place too (src/basic/mp_embedding.py:16-19)
             ops.weight_norm_fwd(m.y_embedder.embedding.weight.data, force=True)
+        tget = (lambda name, i: getattr(W, name)[i]) if want_t else (lambda name, i: None)
         for i, b in enumerate(m.blocks):
-            norm(b.attn.qkv_proj.weight, W.wqkv[i])
-            norm(b.attn.out_proj.weight, W.wo[i])
-            norm(b.mlp.net[0].weight, W.w1[i])
-            norm(b.mlp.net[2].weight, W.w2[i])
-            norm(b.modulation[1].weight, W.wmod[i * W.modw:(i + 1) * W.modw])
+            norm(b.attn.qkv_proj.weight, W.wqkv[i], tget("wqkv_t", i))
+            norm(b.attn.out_proj.weight, W.wo[i], tget("wo_t", i))
+            norm(b.mlp.net[0].weight, W.w1[i], tget("w1_t", i))
+            norm(b.mlp.net[2].weight, W.w2[i], tget("w2_t", i))
+            norm(b.modulation[1].weight, W.wmod[i * W.modw:(i + 1) * W.modw], W.wmod_t[:, i * W.modw:] if want_t else None, W.mod_total)
         f = m.final_layer
-        norm(f.modulation[1].weight, W.wmod[L * W.modw:])
-        norm(f.linear.weight, W.wfl)
+        norm(f.modulation[1].weight, W.wmod[L * W.modw:], W.wmod_t[:, L * W.modw:] if want_t else None, W.mod_total)
+        norm(f.linear.weight, W.wfl, W.wfl_t if want_t else None)
         norm(f.mean_scale.linear.weight, W.wmu)
         norm(f.sigma_scale.linear.weight, W.wsg)
         self._w_sig[mode] = self._signature()

@@ -32,13 +32,13 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr())
 
 
-def weight_norm_fwd(w, force=False, eff_f32=None, eff_bf16=None, eff_bf16_t=None, inv_norm=None):
+def weight_norm_fwd(w, force=False, eff_f32=None, eff_bf16=None, eff_bf16_t=None, inv_norm=None, ld_t=0):
     assert w.dtype == torch.float32 and w.is_contiguous() and w.dim() == 2
     rows, cols = w.shape
-    for e in (eff_f32, eff_bf16, eff_bf16_t):
+    for e in (eff_f32, eff_bf16):
         assert e is None or (e.is_contiguous() and e.numel() == w.numel())
     check(lib().mapdit_weight_norm_fwd(_ptr(w), rows, cols, EPS, int(force), _ptr(eff_f32), _ptr(eff_bf16),
-                                       _ptr(eff_bf16_t), _ptr(inv_norm), _stream()), "weight_norm_fwd")
+                                       _ptr(eff_bf16_t), ld_t, _ptr(inv_norm), _stream()), "weight_norm_fwd")
 
 
 def weight_norm_bwd(v, g_eff, grad_v, accumulate=False):
@@ -68,7 +68,7 @@ def gemm_f32(a, b, out=None, trans_a=False, trans_b=False, accumulate=False):
 
 
 def gemm_bf16(a, b, out, epilogue=_lib.EPI_STORE, out2=None, resid=None, gate=None, shift=None, scale=None, gain=None,
-              ldmod=0, tokens=1, head_dim=0, qk_cols=0):
+              ldmod=0, tokens=1, head_dim=0, qk_cols=0, aux=None):
     """out = epilogue(a[M,K] @ b[N,K]^T) on the tcgen05 path (bf16 operands, fp32 accumulate)."""
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
     assert a.stride(1) == 1 and b.stride(1) == 1 and out.stride(1) == 1
@@ -82,10 +82,31 @@ def gemm_bf16(a, b, out, epilogue=_lib.EPI_STORE, out2=None, resid=None, gate=No
                     shift=shift.data_ptr() if shift is not None else None,
                     scale=scale.data_ptr() if scale is not None else None,
                     gain=gain.data_ptr() if gain is not None else None,
+                    aux=aux.data_ptr() if aux is not None else None,
                     lda=a.stride(0), ldb=b.stride(0), ldo=out.stride(0), ldmod=ldmod, m=m, n=n, k=k, tokens=tokens,
                     head_dim=head_dim, qk_cols=qk_cols, epilogue=epilogue, out_dtype=_dt(out), eps=EPS)
     check(lib().mapdit_gemm_bf16(C.byref(args), _stream()), "gemm_bf16")
     return out
+
+
+def gemm_bf16_tn(dy, x, out):
+    """out[N_out, K_in] (fp32) = dy[M, N_out]^T @ x[M, K_in] on the tcgen05 path (weight gradient)."""
+    assert dy.dtype == torch.bfloat16 and x.dtype == torch.bfloat16 and out.dtype == torch.float32
+    assert dy.stride(1) == 1 and x.stride(1) == 1 and out.stride(1) == 1 and dy.shape[0] == x.shape[0]
+    m, n_out = dy.shape
+    k_in = x.shape[1]
+    assert out.shape == (n_out, k_in)
+    check(lib().mapdit_gemm_bf16_tn(_ptr(dy), dy.stride(0), _ptr(x), x.stride(0), _ptr(out), out.stride(0), m, n_out, k_in, _stream()),
+          "gemm_bf16_tn")
+    return out
+
+
+def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0):
+    """in-place Adam on flat fp32 tensors; `step` is the 1-based step count (bias corrections as torch.optim.Adam)."""
+    n = p.numel()
+    assert p.is_contiguous() and g.is_contiguous() and m.is_contiguous() and v.is_contiguous()
+    check(lib().mapdit_adam_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), n, float(lr), float(beta1), float(beta2), float(eps),
+                                 1.0 - beta1 ** step, 1.0 - beta2 ** step, float(grad_scale), _stream()), "adam_step")
 
 
 def modulate(x, h, shift, scale, gain, ldmod, tokens):
@@ -111,8 +132,79 @@ def cast(src, dst):
     check(lib().mapdit_cast(_ptr(src), _ptr(dst), src.numel(), _dt(src), _dt(dst), _stream()), "cast")
 
 
-def cos_attn(qkv, o, n_samples, tokens, heads, head_dim):
-    check(lib().mapdit_cos_attn_fwd(_ptr(qkv), _ptr(o), n_samples, tokens, heads, head_dim, _dt(qkv), _stream()), "cos_attn_fwd")
+def cos_attn(qkv, o, n_samples, tokens, heads, head_dim, lse=None):
+    check(lib().mapdit_cos_attn_fwd(_ptr(qkv), _ptr(o), _ptr(lse), n_samples, tokens, heads, head_dim, _dt(qkv), _stream()),
+          "cos_attn_fwd")
+
+
+def cos_attn_bwd(qkv, o, dout, lse, dqkv, delta, n_samples, tokens, heads, head_dim):
+    check(lib().mapdit_cos_attn_bwd(_ptr(qkv), _ptr(o), _ptr(dout), _ptr(lse), _ptr(dqkv), _ptr(delta), n_samples, tokens, heads,
+                                    head_dim, _dt(qkv), _stream()), "cos_attn_bwd")
+
+
+def resid_bwd(R, y, dy, gate, dgate, ldmod, n_samples, tokens):
+    d = R.shape[1]
+    check(lib().mapdit_resid_bwd(_ptr(R), _ptr(y), _ptr(dy), _ptr(gate), _ptr(dgate), ldmod, n_samples, d, tokens, _dt(R), _stream()),
+          "resid_bwd")
+
+
+def modulate_bwd_partials(n_samples, d):
+    return lib().mapdit_modulate_bwd_partials(n_samples, d)
+
+
+def modulate_bwd(dh, x, R, shift, scale, gain, dshift, dscale, dg_partial, ldmod, n_samples, tokens, accumulate):
+    d = dh.shape[1]
+    check(lib().mapdit_modulate_bwd(_ptr(dh), _ptr(x), _ptr(R), _ptr(shift), _ptr(scale), _ptr(gain), _ptr(dshift), _ptr(dscale),
+                                    _ptr(dg_partial), ldmod, n_samples, d, tokens, int(accumulate), _dt(dh), _stream()), "modulate_bwd")
+
+
+def sum_partials(partials, n, out, accumulate=False):
+    check(lib().mapdit_sum_partials(_ptr(partials), n, _ptr(out), int(accumulate), _stream()), "sum_partials")
+
+
+def mp_silu_bwd(du, z, dz):
+    check(lib().mapdit_mp_silu_bwd(_ptr(du), _ptr(z), _ptr(dz), du.numel(), _dt(du), _stream()), "mp_silu_bwd")
+
+
+def qk_normalize_save(qkv, sc, d, head_dim):
+    check(lib().mapdit_qk_normalize_save(_ptr(qkv), _ptr(sc), qkv.shape[0], d, head_dim, EPS, _dt(qkv), _stream()), "qk_normalize_save")
+
+
+def qk_norm_bwd(dqkv, qkv, sc, d, head_dim):
+    check(lib().mapdit_qk_norm_bwd(_ptr(dqkv), _ptr(qkv), _ptr(sc), qkv.shape[0], d, head_dim, EPS, _dt(qkv), _stream()), "qk_norm_bwd")
+
+
+def final_bwd(dout, lin, s_mu, s_sigma, dlin, ds_mu, ds_sigma, patch):
+    n, c2, s, _ = dout.shape
+    check(lib().mapdit_final_bwd(_ptr(dout), _ptr(lin), _ptr(s_mu), _ptr(s_sigma), _ptr(dlin), _ptr(ds_mu), _ptr(ds_sigma), n,
+                                 c2 // 2, s, patch, _dt(lin), _stream()), "final_bwd")
+
+
+def mp_scale_from_lin(l, ref, s):
+    check(lib().mapdit_mp_scale_from_lin(_ptr(l), _ptr(ref), _ptr(s), l.shape[0], l.shape[1], _stream()), "mp_scale_from_lin")
+
+
+def mp_scale_bwd(ds, s, l, ref, dl, dref, accumulate=False):
+    check(lib().mapdit_mp_scale_bwd(_ptr(ds), _ptr(s), _ptr(l), _ptr(ref), _ptr(dl), _ptr(dref), l.shape[0], l.shape[1],
+                                    int(accumulate), _stream()), "mp_scale_bwd")
+
+
+def cond_combine_bwd(c, dc, dcs, dab):
+    check(lib().mapdit_cond_combine_bwd(_ptr(c), _ptr(dc), _ptr(dcs), _ptr(dab), c.numel(), _stream()), "cond_combine_bwd")
+
+
+def embed_rows_bwd(idx, drop_mask, null_idx, table, g, dtable):
+    check(lib().mapdit_embed_rows_bwd(_ptr(idx), _ptr(drop_mask), null_idx, _ptr(table), _ptr(g), _ptr(dtable), idx.shape[0],
+                                      table.shape[1], EPS, _stream()), "embed_rows_bwd")
+
+
+def patchify(x, P, patch):
+    n, c, s, _ = x.shape
+    check(lib().mapdit_patchify(_ptr(x), _ptr(P), n, c, s, patch, _stream()), "patchify")
+
+
+def axpby(x, y, a, accumulate=False):
+    check(lib().mapdit_axpby(_ptr(x), _ptr(y), float(a), int(accumulate), x.numel(), _stream()), "axpby")
 
 
 def patch_embed(x, wx_eff, pos, x0, h, shift, scale, gain, ldmod, patch):

@@ -1,0 +1,103 @@
+"""Fused training step: the inner loop of the reference's train.py:86-96
+(training_losses -> loss.mean() -> backward -> Adam(lr, betas=(0.9, 0.99))) as one fixed kernel schedule.
+
+Parameters, gradients and Adam moments live in flat fp32 buffers (parameters are re-pointed into the flat
+buffer, so `model.parameters()` / `state_dict()` keep working): the optimiser is ONE kernel launch over the
+span and data-parallel training needs no per-tensor bookkeeping.  Gradient layout follows the order in which
+the backward finishes them (last block first), so each block's gradient slice is all-reduced over NCCL
+(async, overlapping the rest of the backward) the moment it is final; ranks hold identical replicas.
+"""
+import torch
+import torch.distributed as dist
+
+from . import ops
+
+
+class TrainStep:
+    def __init__(self, model, diffusion, lr=1e-2, betas=(0.9, 0.99), eps=1e-8, world_size=1):
+        self.model, self.diffusion = model, diffusion
+        self.lr, self.betas, self.eps = lr, betas, eps
+        self.world = world_size
+        self.step_count = 0
+        m = model
+        dev = next(m.parameters()).device
+        # flat layout: blocks in reverse (minus their modulation weights), then all modulation weights, then the rest
+        groups = []
+        for b in reversed(list(m.blocks)):
+            groups.append([p for p in b.parameters() if p is not b.modulation[1].weight])
+        groups.append([b.modulation[1].weight for b in m.blocks])
+        seen = {id(p) for g in groups for p in g}
+        groups.append([p for p in m.parameters() if id(p) not in seen])
+        order = [p for g in groups for p in g]
+        total = sum(p.numel() for p in order)
+        self.flat_p = torch.empty(total, device=dev, dtype=torch.float32)
+        self.flat_g = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.flat_m = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.flat_v = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.grad_views, self.slices = {}, []
+        off = 0
+        for g in groups:
+            start = off
+            for p in g:
+                n = p.numel()
+                self.flat_p[off:off + n].copy_(p.data.reshape(-1))
+                p.data = self.flat_p[off:off + n].view(p.shape)
+                self.grad_views[id(p)] = self.flat_g[off:off + n].view(p.shape)
+                off += n
+            self.slices.append((start, off))
+        self._group_of = {}
+        for gi, g in enumerate(groups):
+            for p in g:
+                self._group_of[id(p)] = gi
+        model.engine.invalidate()
+        self._works = []
+
+    # gradient hook from the backward: everything in `pairs` is final -> start its all-reduce
+    def _on_grads(self, pairs):
+        if self.world <= 1:
+            return
+        for gi in sorted({self._group_of[id(p)] for p, _ in pairs}):
+            if gi in self._reduced:
+                continue
+            # the modulation group (second to last) and the rest are only complete at the very end
+            if gi >= len(self.slices) - 2 and not self._final:
+                continue
+            s, e = self.slices[gi]
+            self._works.append(dist.all_reduce(self.flat_g[s:e], async_op=True))
+            self._reduced.add(gi)
+
+    def step(self, x, t, y, noise=None, drop_mask=None):
+        """one optimisation step on the local batch; returns the mean loss (device scalar)"""
+        m, d = self.model, self.diffusion
+        assert m.training, "TrainStep needs model.train() (forced weight normalisation + label dropout)"
+        tr = m.engine.trainer
+        tr.grad_buffers = self.grad_views
+        tr.grad_hook = self._on_grads
+        self._reduced, self._final, self._works = set(), False, []
+        x0 = x.contiguous().float()
+        tl = t.contiguous().long()
+        if noise is None:
+            noise = torch.randn_like(x0)
+        noise = noise.contiguous().float()
+        N = x0.shape[0]
+        tab = d.device_tables(x0.device)
+        x_t = torch.empty_like(x0)
+        ops.q_sample(x0, noise, tl, tab, x_t)
+        t_model = d._map_tensor(tl.device, tl.dtype)[tl] if hasattr(d, "_map_tensor") else tl
+        with torch.no_grad():
+            out, saved = tr.forward(x_t, t_model, y, drop_mask)
+            loss = torch.empty(N, device=x0.device)
+            dout = torch.empty_like(out)
+            gs = torch.full((N,), 1.0 / N, device=x0.device)
+            ops.loss_fwd_bwd(out, x0, x_t, noise, tl, tab, loss, None, None, dout, gs, gs)
+            tr.backward(saved, dout)
+            self._final = True
+            self._on_grads([(p, None) for p in m.parameters()])
+            for w in self._works:
+                w.wait()
+            self.step_count += 1
+            ops.adam_step(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.lr, self.betas[0], self.betas[1], self.eps,
+                          self.step_count, grad_scale=1.0 / self.world)
+        tr.grad_buffers = None
+        tr.grad_hook = None
+        return loss.mean()

@@ -1,0 +1,155 @@
+"""Training path on the B200: gradients of one reference training step (train.py:86-95) through the
+hand-written backward, against (1) the committed outputs of the unmodified reference and (2) the CPU oracle's
+autograd; the fused TrainStep (loss + backward + Adam) against torch.optim.Adam on the oracle."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import GOLDEN, rel_l2
+from oracle import mapdit_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).cuda()
+
+
+@pytest.mark.parametrize("m,n,k", [(256, 128, 64), (1000, 384, 384), (4096, 2304, 768), (8192, 32, 768), (512, 768, 3072), (256, 4608, 768)])
+def test_gemm_bf16_tn(m, n, k):
+    """wgrad GEMM: out[n, k] = dy[m, n]^T x[m, k] with both operands read MN-major in place"""
+    from mapdit_b200 import ops
+    dy, x = rnd(m, n, seed=1).bfloat16(), rnd(m, k, seed=2, scale=m ** -0.5).bfloat16()
+    out = torch.full((n, k), float("nan"), device="cuda")
+    ops.gemm_bf16_tn(dy, x, out)
+    ref = dy.double().t() @ x.double()
+    assert rel_l2(out, ref) < 1e-5
+
+
+@pytest.mark.parametrize("N,T,H,hd,dtype", [(2, 64, 3, 64, torch.float32), (1, 256, 2, 64, torch.float32), (1, 80, 2, 72, torch.float32),
+                                             (2, 128, 2, 64, torch.bfloat16)])
+def test_attention_backward(N, T, H, hd, dtype):
+    from mapdit_b200 import ops
+    D = H * hd
+    qkv = rnd(N * T, 3 * D, seed=3)
+    sc = torch.empty(N * T, 2 * H, device="cuda")
+    ops.qk_normalize_save(qkv, sc, D, hd)
+    qkv = qkv.to(dtype)
+    dout = rnd(N * T, D, seed=4).to(dtype)
+    o = torch.empty(N * T, D, device="cuda", dtype=dtype)
+    lse = torch.empty(N * T, H, device="cuda")
+    ops.cos_attn(qkv, o, N, T, H, hd, lse=lse)
+    dqkv = torch.empty_like(qkv)
+    delta = torch.empty(N * T, H, device="cuda")
+    ops.cos_attn_bwd(qkv, o, dout, lse, dqkv, delta, N, T, H, hd)
+    ref_in = qkv.double().requires_grad_(True)
+    q, k, v = ref_in.view(N, T, 3, H, hd).permute(2, 0, 3, 1, 4)
+    ro = F.scaled_dot_product_attention(q, k, v, scale=1 / math.sqrt(hd)).transpose(1, 2).reshape(N * T, D)
+    (ro * dout.double()).sum().backward()
+    tol = 2e-5 if dtype == torch.float32 else 2e-2
+    assert rel_l2(dqkv.float(), ref_in.grad) < tol
+    # q/k normalisation backward (in place on the q|k thirds)
+    raw = rnd(N * T, 3 * D, seed=3).double().requires_grad_(True)
+    r3 = raw.view(N * T, 3, H, hd)
+    qn = r3[:, :2] * math.sqrt(hd) / (r3[:, :2].norm(dim=-1, keepdim=True) + 1e-4)
+    full = torch.cat([qn, r3[:, 2:]], 1).reshape(N * T, 3 * D)
+    gin = rnd(N * T, 3 * D, seed=5)
+    (full * gin.double()).sum().backward()
+    g2 = gin.clone()
+    q32 = rnd(N * T, 3 * D, seed=3)
+    ops.qk_normalize_save(q32, sc, D, hd)
+    ops.qk_norm_bwd(g2, q32, sc, D, hd)
+    assert rel_l2(g2, raw.grad) < 2e-5
+
+
+def _run_train(name, seed, dtype, x, t, y, noise, drop):
+    import mapdit_b200 as M
+    cfg = O.config_for(name)
+    sd = O.init_state_dict(cfg, seed=seed)
+    m = M.DIT_MODELS[name](in_channels=4, input_size=32, num_classes=1000, compute_dtype=dtype)
+    m.load_state_dict(sd)
+    m = m.cuda().train()
+    d = M.create_diffusion("")
+    terms = d.training_losses(lambda xt, tt, **kw: m(xt, tt, kw["y"], drop_mask=drop.cuda()), x.cuda(), t.cuda(), dict(y=y.cuda()),
+                              noise=noise.cuda())
+    terms["loss"].mean().backward()
+    return m, terms, cfg, sd
+
+
+@pytest.mark.parametrize("tag", ["train_xs8", "train_xs4"])
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_training_step_gradients(tag, dtype):
+    g = np.load(os.path.join(GOLDEN, tag + ".npz"))
+    x, t, y, noise, drop = (torch.from_numpy(g[k]) for k in ("x", "t", "y", "noise", "drop"))
+    m, terms, cfg, sd = _run_train(str(g["name"]), int(g["seed"]), dtype, x, t, y, noise, drop)
+    ltol = 2e-5 if dtype == "fp32" else 3e-2
+    for k in ("loss", "mse", "vb"):
+        e = rel_l2(terms[k].detach().cpu(), g[k])
+        print(f"{tag} {dtype} {k}: rel-L2 vs reference {e:.2e}")
+        assert e < ltol, k
+    # full gradients from the oracle's autograd on the same inputs (the golden file pins the oracle's)
+    p = O.make_params(sd)
+    _, ograds = O.train_step_grads(p, cfg, O.make_tables(""), x, t, y, noise, drop_mask=drop)
+    names = [str(s) for s in g["grad_names"]]
+    stats = g["grad_stats"]
+    worst = 0.0
+    for i, (k, prm) in enumerate(m.named_parameters()):
+        assert k == names[i]
+        assert prm.grad is not None, k
+        e = rel_l2(prm.grad.cpu(), ograds[k])
+        worst = max(worst, e)
+        tol = 2e-4 if dtype == "fp32" else 8e-2
+        assert e < tol, (k, e)
+        # against the reference's own numbers
+        gn = prm.grad.double().norm().item()
+        assert abs(gn - stats[i, 0]) <= (1e-3 if dtype == "fp32" else 8e-2) * max(stats[i, 0], 1e-12), k
+        # forced weight normalisation wrote the normalised weights back (src/basic/mp_linear.py:38-40)
+        assert abs(prm.detach().double().norm().item() - stats[i, 3]) <= 1e-5 * stats[i, 3] + 1e-12, k
+    print(f"{tag} {dtype}: worst per-parameter grad rel-L2 vs oracle = {worst:.2e}")
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_fused_train_step_matches_adam(dtype):
+    """TrainStep (q_sample + forward + loss + backward + fused Adam) for 2 steps vs torch.optim.Adam on the oracle"""
+    import mapdit_b200 as M
+    from mapdit_b200.train import TrainStep
+    name = "DiT-XS/8"
+    cfg = O.config_for(name)
+    sd = O.init_state_dict(cfg, seed=21)
+    m = M.DIT_MODELS[name](in_channels=4, input_size=32, num_classes=1000, compute_dtype=dtype)
+    m.load_state_dict(sd)
+    m = m.cuda().train()
+    d = M.create_diffusion("")
+    ts = TrainStep(m, d, lr=1e-2, betas=(0.9, 0.99))
+    p = O.make_params(sd)
+    opt = torch.optim.Adam([v for v in p.values() if v.requires_grad], lr=1e-2, betas=(0.9, 0.99))
+    T = O.make_tables("")
+    gen = torch.Generator().manual_seed(4)
+    for step in range(2):
+        x = torch.randn(4, 4, 32, 32, generator=gen)
+        t = torch.randint(0, 1000, (4,), generator=gen)
+        y = torch.randint(0, 1000, (4,), generator=gen)
+        noise = torch.randn(4, 4, 32, 32, generator=gen)
+        drop = torch.tensor([False, True, False, False])
+        loss = ts.step(x.cuda(), t.cuda(), y.cuda(), noise.cuda(), drop_mask=drop.cuda())
+        opt.zero_grad()
+        terms, _ = O.train_step_grads(p, cfg, T, x, t, y, noise, drop_mask=drop)
+        opt.step()
+        e = abs(float(loss) - float(terms["loss"].mean())) / abs(float(terms["loss"].mean()))
+        print(f"step {step} {dtype}: loss {float(loss):.5f} vs oracle {float(terms['loss'].mean()):.5f}")
+        assert e < (1e-4 if dtype == "fp32" else 3e-2)
+    # Adam's first steps move every weight by ~lr regardless of gradient scale, so compare the UPDATE direction
+    worst = 0.0
+    for k, prm in m.named_parameters():
+        upd = prm.detach().cpu() - sd[k]
+        ref = p[k].detach() - sd[k]
+        e = rel_l2(upd, ref)
+        worst = max(worst, e)
+    print(f"{dtype}: worst parameter-update rel-L2 after 2 steps = {worst:.2e}")
+    assert worst < (5e-3 if dtype == "fp32" else 0.5)
+    assert m.state_dict().keys() == sd.keys()
