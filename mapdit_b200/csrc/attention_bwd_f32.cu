@@ -142,8 +142,8 @@ void launch(const void* qkv, const void* o, const void* dout, const float* lse, 
 }  // namespace
 
 // dqkv[M, 3D] <- gradients w.r.t. the (normalised) q, k and v; delta is an [M, H] fp32 scratch.
-extern "C" int mapdit_cos_attn_bwd(const void* qkv, const void* o, const void* dout, const float* lse, void* dqkv, float* delta,
-                                   int n_samples, int tokens, int heads, int head_dim, int dtype, void* stream) {
+int mapdit_attn_bwd_simt(const void* qkv, const void* o, const void* dout, const float* lse, void* dqkv, float* delta,
+                         int n_samples, int tokens, int heads, int head_dim, int dtype, void* stream) {
   MAPDIT_REQUIRE(qkv && o && dout && lse && dqkv && delta && n_samples > 0 && tokens > 0, "cos_attn_bwd: bad args");
   cudaStream_t s = (cudaStream_t)stream;
   if (head_dim == 64) {
