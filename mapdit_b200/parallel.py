@@ -1,0 +1,62 @@
+"""Data-parallel plumbing (one process per GPU, torch.distributed over NCCL/NVLink; gloo in CPU tests).
+
+The hot path shards by sample only: training needs one gradient all-reduce per step, sampling
+needs no traffic until the final gather.  Nothing here touches kernels; it is device-agnostic so the N>1 logic
+is testable with world_size-2 gloo on CPU.
+"""
+import torch
+import torch.distributed as dist
+
+
+def world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_range(global_batch: int, rank: int, world_size: int):
+    """contiguous [lo, hi) slice of the global batch owned by `rank` (remainder spread over the first ranks)"""
+    base, rem = divmod(global_batch, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def gather_samples(local: torch.Tensor, group=None) -> torch.Tensor:
+    """final all-gather of batch-sharded sampling results, rank-major (the only collective of the sampling path)"""
+    _, w = world()
+    if w == 1:
+        return local
+    outs = [torch.empty_like(local) for _ in range(w)]
+    dist.all_gather(outs, local.contiguous(), group=group)
+    return torch.cat(outs, dim=0)
+
+
+class GradReducer:
+    """Bucketed, overlapped gradient all-reduce over a flat buffer.
+
+    `slices[i] = (lo, hi)` are contiguous regions of `flat`, ordered as the backward finishes them.  `ready(i)`
+    launches the async all-reduce (SUM) of bucket i; `finish()` launches whatever is left and waits for all of
+    them, after which `flat` holds the sum over ranks (the optimiser applies the 1/world factor)."""
+
+    def __init__(self, flat: torch.Tensor, slices, group=None):
+        self.flat, self.slices, self.group = flat, list(slices), group
+        self._works, self._done = [], set()
+
+    def start_step(self):
+        self._works, self._done = [], set()
+
+    def ready(self, i: int):
+        _, w = world()
+        if w == 1 or i in self._done:
+            return
+        lo, hi = self.slices[i]
+        if hi > lo:
+            self._works.append(dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        self._done.add(i)
+
+    def finish(self):
+        for i in range(len(self.slices)):
+            self.ready(i)
+        for wk in self._works:
+            wk.wait()
+        self._works = []

@@ -8,9 +8,9 @@ the backward finishes them (last block first), so each block's gradient slice is
 (async, overlapping the rest of the backward) the moment it is final; ranks hold identical replicas.
 """
 import torch
-import torch.distributed as dist
 
 from . import ops
+from .parallel import GradReducer
 
 
 class TrainStep:
@@ -50,21 +50,14 @@ class TrainStep:
             for p in g:
                 self._group_of[id(p)] = gi
         model.engine.invalidate()
-        self._works = []
+        self.reducer = GradReducer(self.flat_g, self.slices)
 
-    # gradient hook from the backward: everything in `pairs` is final -> start its all-reduce
+    # gradient hook from the backward: every parameter in `pairs` has its final gradient -> reduce finished buckets.
+    # The last two buckets (all modulation weights; embedders/final layer) only complete at the very end.
     def _on_grads(self, pairs):
-        if self.world <= 1:
-            return
         for gi in sorted({self._group_of[id(p)] for p, _ in pairs}):
-            if gi in self._reduced:
-                continue
-            # the modulation group (second to last) and the rest are only complete at the very end
-            if gi >= len(self.slices) - 2 and not self._final:
-                continue
-            s, e = self.slices[gi]
-            self._works.append(dist.all_reduce(self.flat_g[s:e], async_op=True))
-            self._reduced.add(gi)
+            if gi < len(self.slices) - 2:
+                self.reducer.ready(gi)
 
     def step(self, x, t, y, noise=None, drop_mask=None):
         """one optimisation step on the local batch; returns the mean loss (device scalar)"""
@@ -73,7 +66,7 @@ class TrainStep:
         tr = m.engine.trainer
         tr.grad_buffers = self.grad_views
         tr.grad_hook = self._on_grads
-        self._reduced, self._final, self._works = set(), False, []
+        self.reducer.start_step()
         x0 = x.contiguous().float()
         tl = t.contiguous().long()
         if noise is None:
@@ -91,10 +84,7 @@ class TrainStep:
             gs = torch.full((N,), 1.0 / N, device=x0.device)
             ops.loss_fwd_bwd(out, x0, x_t, noise, tl, tab, loss, None, None, dout, gs, gs)
             tr.backward(saved, dout)
-            self._final = True
-            self._on_grads([(p, None) for p in m.parameters()])
-            for w in self._works:
-                w.wait()
+            self.reducer.finish()
             self.step_count += 1
             ops.adam_step(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.lr, self.betas[0], self.betas[1], self.eps,
                           self.step_count, grad_scale=1.0 / self.world)
