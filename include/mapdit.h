@@ -67,6 +67,7 @@ int mapdit_gemm_f32(const float* a, int64_t sam, int64_t sak, const float* b, in
 #define MAPDIT_EPI_RESID_MOD 3  /* x' = mp_sum(x, gate*acc, .3); h = modulate(x', shift, scale, g)
                                    (src/blocks/dit_block.py:35-36, src/utils.py:11-16)                            */
 #define MAPDIT_EPI_RESID 4      /* x' = mp_sum(x, gate*acc, .3) only                                              */
+#define MAPDIT_EPI_SILU_BWD 5   /* out = acc * d/dz[silu(z)/0.596], z = `resid` (dgrad of fc2 fused with MPSiLU's backward) */
 
 typedef struct mapdit_gemm_args {
   const void* a;   /* bf16 [M, K] */
@@ -204,6 +205,9 @@ int mapdit_embed_rows_bwd(const int64_t* idx, const uint8_t* drop_mask, int64_t 
                           const float* g, float* dtable, int n, int d, float eps, void* stream);
 int mapdit_patchify(const float* x, float* P, int n_samples, int channels, int input_size, int patch, void* stream);
 int mapdit_axpby(const float* x, float* y, float a, int accumulate, int64_t n, void* stream);
+/* x_embedder weight gradient dW[D, p*p*C+1] = scale * R[M, D]^T · (patchify(x)|1), patches gathered on the fly (src/dit.py:81-84) */
+int mapdit_patch_embed_wgrad(const void* R, const float* x, float* dW, int n_samples, int channels, int input_size,
+                             int patch, int d, float scale, int dtype, void* stream);
 
 #ifdef __cplusplus
 }

@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmapdit.so")
 
 F32, BF16 = 0, 1
-EPI_STORE, EPI_QKNORM, EPI_MPSILU, EPI_RESID_MOD, EPI_RESID = 0, 1, 2, 3, 4
+EPI_STORE, EPI_QKNORM, EPI_MPSILU, EPI_RESID_MOD, EPI_RESID, EPI_SILU_BWD = 0, 1, 2, 3, 4, 5
 
 _p, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 
@@ -50,6 +50,7 @@ SIGNATURES = {
     "mapdit_embed_rows_bwd": [_p, _p, _i64, _p, _p, _p, _i, _i, _f, _p],
     "mapdit_patchify": [_p, _p, _i, _i, _i, _i, _p],
     "mapdit_axpby": [_p, _p, _f, _i, _i64, _p],
+    "mapdit_patch_embed_wgrad": [_p, _p, _p, _i, _i, _i, _i, _i, _f, _i, _p],
     "mapdit_patch_embed": [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _i, _i, _i, _i, _p],
     "mapdit_fourier": [_p, _p, _p, _p, _i, _i, _p],
     "mapdit_embed_rows": [_p, _p, _i64, _p, _p, _i, _i, _f, _p],

@@ -249,8 +249,11 @@ class Trainer:
             # MLP branch
             ops.resid_bwd(R, b, dY, mod(mods, i, 5), mod(dmods, i, 5), ld, N, T)
             self._wgrad(dY, u, blk[i].mlp.net[2].weight, bf, B, grads)
-            self._dgrad(dY, W.w2[i], wt("w2_t"), dU, bf)
-            ops.mp_silu_bwd(dU, z, dU)
+            if bf:  # dgrad of fc2 with MPSiLU's backward fused into the epilogue
+                ops.gemm_bf16(dY, W.w2_t[i], dU, epilogue=_lib.EPI_SILU_BWD, resid=z)
+            else:
+                self._dgrad(dY, W.w2[i], None, dU, bf)
+                ops.mp_silu_bwd(dU, z, dU)
             self._wgrad(dU, h2, blk[i].mlp.net[0].weight, bf, B, grads)
             self._dgrad(dU, W.w1[i], wt("w1_t"), dh, bf)
             ops.modulate_bwd(dh, xmid, R, mod(mods, i, 3), mod(mods, i, 4), blk[i].gain_mlp.data, mod(dmods, i, 3), mod(dmods, i, 4),
@@ -270,15 +273,9 @@ class Trainer:
             if self.grad_hook is not None:
                 self.grad_hook([(p, grads[id(p)]) for p in blk[i].parameters() if id(p) in grads])
         # ---- patch embed (src/dit.py:81-84): x0 = (lin + pos)/2/sqrt(.5) -> d lin = R * 0.5/sqrt(.5)
-        ops.patchify(saved["x"], B["P"], m.patch_size)
-        R32 = R
-        if bf:
-            ops.cast(R, B["R32"])
-            R32 = B["R32"]
         K1 = m.x_embedder.weight.shape[1]
         dWx = B["dWs"][: D * K1].view(D, K1)
-        ops.gemm_f32(R32, B["P"], out=dWx, trans_a=True, trans_b=True)
-        ops.axpby(dWx, dWx, 0.5 / 0.7071067811865476, False)
+        ops.patch_embed_wgrad(R, saved["x"], dWx, m.patch_size, 0.5 / 0.7071067811865476)
         g = self._gbuf(m.x_embedder.weight)
         ops.weight_norm_bwd(m.x_embedder.weight.data, dWx, g)
         grads[id(m.x_embedder.weight)] = g

@@ -8,35 +8,59 @@
 // ------------------------------------------------------------------------------------------------
 // x_out = mp_sum(x, gate*y, 0.3):   R <- 0.7/den * R (in place) ; dy = 0.3/den * gate * R_in ; dgate = sum_t 0.3/den * y * R_in
 // ------------------------------------------------------------------------------------------------
+// CTA = (sample, 256-column chunk); 8 warps stride over the T rows, each lane owns 8 consecutive columns (16-byte
+// accesses); per-column sums are combined across the warps in shared memory in a fixed order (deterministic).
 template <typename T>
-__global__ void __launch_bounds__(128) resid_bwd_kernel(T* __restrict__ R, const T* __restrict__ y, T* __restrict__ dy,
+__global__ void __launch_bounds__(256) resid_bwd_kernel(T* __restrict__ R, const T* __restrict__ y, T* __restrict__ dy,
                                                         const float* __restrict__ gate, float* __restrict__ dgate, int64_t ldmod,
                                                         int d, int tokens) {
-  const int n = blockIdx.y;
-  const int col = blockIdx.x * blockDim.x + threadIdx.x;
-  if (col >= d) return;
-  const float g = gate[n * ldmod + col];
+  __shared__ float red[8][256];
+  const int n = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int col = blockIdx.x * 256 + lane * 8;
+  const bool ok = col < d;
   const float ca = (1.0f - MP_RES_T) / MP_RES_DEN, cb = MP_RES_T / MP_RES_DEN;
-  float acc = 0.f;
-  size_t off = ((size_t)n * tokens) * d + col;
-  for (int t = 0; t < tokens; ++t, off += d) {
-    float r = ld_act(R + off);
-    float yv = ld_act(y + off);
-    st_act(dy + off, cb * g * r);
-    acc = fmaf(cb * yv, r, acc);
-    st_act(R + off, ca * r);
+  float g[8], acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    g[j] = ok ? cb * gate[n * ldmod + col + j] : 0.f;
+    acc[j] = 0.f;
   }
-  dgate[n * ldmod + col] = acc;
+  if (ok) {
+    for (int t = warp; t < tokens; t += 8) {
+      const size_t off = ((size_t)n * tokens + t) * d + col;
+      float r[8], yv[8], o1[8], o2[8];
+      load8(R + off, r);
+      load8(y + off, yv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        o1[j] = g[j] * r[j];
+        acc[j] = fmaf(cb * yv[j], r[j], acc[j]);
+        o2[j] = ca * r[j];
+      }
+      store8(dy + off, o1);
+      store8(R + off, o2);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[warp][lane * 8 + j] = acc[j];
+  __syncthreads();
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c < d) {
+    float sacc = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) sacc += red[w][threadIdx.x];
+    dgate[n * ldmod + c] = sacc;
+  }
 }
 
 extern "C" int mapdit_resid_bwd(void* R, const void* y, void* dy, const float* gate, float* dgate, int64_t ldmod, int n_samples,
                                 int d, int tokens, int dtype, void* stream) {
-  MAPDIT_REQUIRE(R && y && dy && gate && dgate && n_samples > 0 && d > 0 && tokens > 0, "resid_bwd: bad args");
-  dim3 grid((d + 127) / 128, n_samples);
+  MAPDIT_REQUIRE(R && y && dy && gate && dgate && n_samples > 0 && d > 0 && tokens > 0 && d % 8 == 0, "resid_bwd: bad args");
+  dim3 grid((d + 255) / 256, n_samples);
   if (dtype == MAPDIT_F32)
-    resid_bwd_kernel<float><<<grid, 128, 0, (cudaStream_t)stream>>>((float*)R, (const float*)y, (float*)dy, gate, dgate, ldmod, d, tokens);
+    resid_bwd_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((float*)R, (const float*)y, (float*)dy, gate, dgate, ldmod, d, tokens);
   else
-    resid_bwd_kernel<bf16><<<grid, 128, 0, (cudaStream_t)stream>>>((bf16*)R, (const bf16*)y, (bf16*)dy, gate, dgate, ldmod, d, tokens);
+    resid_bwd_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((bf16*)R, (const bf16*)y, (bf16*)dy, gate, dgate, ldmod, d, tokens);
   MAPDIT_LAUNCH_CHECK("resid_bwd");
   return MAPDIT_OK;
 }
@@ -48,52 +72,81 @@ extern "C" int mapdit_resid_bwd(void* R, const void* y, void* dy, const float* g
 // R may be null (first block: the input has no gradient); accumulate==0 overwrites R.
 // ------------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(128) modulate_bwd_kernel(const T* __restrict__ dh, const T* __restrict__ x, T* __restrict__ R,
+__global__ void __launch_bounds__(256) modulate_bwd_kernel(const T* __restrict__ dh, const T* __restrict__ x, T* R,
                                                            const float* __restrict__ shift, const float* __restrict__ scale,
                                                            const float* __restrict__ gain, float* __restrict__ dshift,
                                                            float* __restrict__ dscale, float* __restrict__ dg_partial, int64_t ldmod,
                                                            int d, int tokens, int accumulate) {
+  __shared__ float red_sc[8][256];
+  __shared__ float red_sh[8][256];
   __shared__ float red[32];
-  const int n = blockIdx.y;
-  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int col = blockIdx.x * 256 + lane * 8;
+  const bool ok = col < d;
   const float g = *gain;
   const float den = mod_den(g);
   const float ca = (1.0f - g) / den, cb = g / den, cd = 1.0f / den;
-  float a_sc = 0.f, a_sh = 0.f, a_g = 0.f;
-  if (col < d) {
-    const float sc = scale[n * ldmod + col], sh = shift[n * ldmod + col];
-    size_t off = ((size_t)n * tokens) * d + col;
-    for (int t = 0; t < tokens; ++t, off += d) {
-      float gh = ld_act(dh + off);
-      float xv = ld_act(x + off);
-      if (R) {
-        float add = ca * sc * gh;
-        st_act(R + off, accumulate ? ld_act(R + off) + add : add);
-      }
-      a_sc = fmaf(ca * xv, gh, a_sc);
-      a_sh += gh;
-      a_g = fmaf(gh, sh - xv * sc, a_g);
-    }
-    dscale[n * ldmod + col] = a_sc;
-    dshift[n * ldmod + col] = cb * a_sh;
+  float sc[8], sh[8], a_sc[8], a_sh[8], a_g = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = ok ? scale[n * ldmod + col + j] : 0.f;
+    sh[j] = ok ? shift[n * ldmod + col + j] : 0.f;
+    a_sc[j] = 0.f;
+    a_sh[j] = 0.f;
   }
-  float tot = block_sum(a_g * cd, red);
+  if (ok) {
+    for (int t = warp; t < tokens; t += 8) {
+      const size_t off = ((size_t)n * tokens + t) * d + col;
+      float gh[8], xv[8], r[8];
+      load8(dh + off, gh);
+      load8(x + off, xv);
+      if (R) {
+        if (accumulate) load8(R + off, r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = (accumulate ? r[j] : 0.f) + ca * sc[j] * gh[j];
+        store8(R + off, r);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        a_sc[j] = fmaf(ca * xv[j], gh[j], a_sc[j]);
+        a_sh[j] += gh[j];
+        a_g = fmaf(gh[j], sh[j] - xv[j] * sc[j], a_g);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    red_sc[warp][lane * 8 + j] = a_sc[j];
+    red_sh[warp][lane * 8 + j] = a_sh[j];
+  }
+  float tot = block_sum(a_g * cd, red);  // contains the __syncthreads that publishes red_sc / red_sh
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c < d) {
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      s1 += red_sc[w][threadIdx.x];
+      s2 += red_sh[w][threadIdx.x];
+    }
+    dscale[n * ldmod + c] = s1;
+    dshift[n * ldmod + c] = cb * s2;
+  }
   if (threadIdx.x == 0) dg_partial[blockIdx.y * gridDim.x + blockIdx.x] = tot;
 }
 
 extern "C" int mapdit_modulate_bwd(const void* dh, const void* x, void* R, const float* shift, const float* scale, const float* gain,
                                    float* dshift, float* dscale, float* dg_partial, int64_t ldmod, int n_samples, int d, int tokens,
                                    int accumulate, int dtype, void* stream) {
-  MAPDIT_REQUIRE(dh && x && shift && scale && gain && dshift && dscale && dg_partial && n_samples > 0, "modulate_bwd: bad args");
-  dim3 grid((d + 127) / 128, n_samples);
+  MAPDIT_REQUIRE(dh && x && shift && scale && gain && dshift && dscale && dg_partial && n_samples > 0 && d % 8 == 0, "modulate_bwd: bad args");
+  dim3 grid((d + 255) / 256, n_samples);
   if (dtype == MAPDIT_F32)
-    modulate_bwd_kernel<float><<<grid, 128, 0, (cudaStream_t)stream>>>((const float*)dh, (const float*)x, (float*)R, shift, scale, gain, dshift, dscale, dg_partial, ldmod, d, tokens, accumulate);
+    modulate_bwd_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)dh, (const float*)x, (float*)R, shift, scale, gain, dshift, dscale, dg_partial, ldmod, d, tokens, accumulate);
   else
-    modulate_bwd_kernel<bf16><<<grid, 128, 0, (cudaStream_t)stream>>>((const bf16*)dh, (const bf16*)x, (bf16*)R, shift, scale, gain, dshift, dscale, dg_partial, ldmod, d, tokens, accumulate);
+    modulate_bwd_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)dh, (const bf16*)x, (bf16*)R, shift, scale, gain, dshift, dscale, dg_partial, ldmod, d, tokens, accumulate);
   MAPDIT_LAUNCH_CHECK("modulate_bwd");
   return MAPDIT_OK;
 }
-extern "C" int mapdit_modulate_bwd_partials(int n_samples, int d) { return ((d + 127) / 128) * n_samples; }
+extern "C" int mapdit_modulate_bwd_partials(int n_samples, int d) { return ((d + 255) / 256) * n_samples; }
 
 // out[0] (+)= sum(partials[0..n))   -- single CTA, fixed order
 __global__ void __launch_bounds__(256) sum_partials_kernel(const float* __restrict__ p, int n, float* __restrict__ out, int accumulate) {
@@ -164,11 +217,46 @@ __global__ void qk_norm_bwd_kernel(T* __restrict__ dqkv, const T* __restrict__ q
     if (c < hd) st_act(dqkv + off + c, s * (gv[j] - yv[j] * coef));
   }
 }
+// head_dim 64: 8 lanes x 8 elements per head, four heads per warp, 16-byte accesses
+template <typename T>
+__global__ void qk_norm_bwd_vec64_kernel(T* dqkv, const T* __restrict__ qkv, const float* __restrict__ sc, int64_t total, int heads2,
+                                         int d, float eps) {
+  const int sub = threadIdx.x & 7;
+  int64_t hid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  const bool ok = hid < total;
+  if (!ok) hid = total - 1;
+  int64_t row = hid / heads2;
+  int hh = (int)(hid - row * heads2);
+  const size_t off = (size_t)row * 3 * d + (size_t)hh * 64 + sub * 8;
+  float yv[8], gv[8], dot = 0.f;
+  load8(qkv + off, yv);
+  load8(dqkv + off, gv);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) dot = fmaf(yv[j], gv[j], dot);
+  dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+  dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+  dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+  const float s = sc[hid];
+  const float rpe = 8.0f / s;
+  const float r = fmaxf(rpe - eps, 1e-30f);
+  const float coef = dot * rpe / (64.0f * r);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) gv[j] = s * (gv[j] - yv[j] * coef);
+  if (ok) store8(dqkv + off, gv);
+}
+
 extern "C" int mapdit_qk_norm_bwd(void* dqkv, const void* qkv, const float* sc, int m, int d, int head_dim, float eps, int dtype,
                                   void* stream) {
   MAPDIT_REQUIRE(dqkv && qkv && sc && m > 0 && d % head_dim == 0 && head_dim <= 128, "qk_norm_bwd: bad args");
   int heads2 = 2 * (d / head_dim);
   int64_t total = (int64_t)m * heads2;
+  if (head_dim == 64) {
+    unsigned vb = (unsigned)((total * 8 + 255) / 256);
+    if (dtype == MAPDIT_F32) qk_norm_bwd_vec64_kernel<float><<<vb, 256, 0, (cudaStream_t)stream>>>((float*)dqkv, (const float*)qkv, sc, total, heads2, d, eps);
+    else qk_norm_bwd_vec64_kernel<bf16><<<vb, 256, 0, (cudaStream_t)stream>>>((bf16*)dqkv, (const bf16*)qkv, sc, total, heads2, d, eps);
+    MAPDIT_LAUNCH_CHECK("qk_norm_bwd");
+    return MAPDIT_OK;
+  }
   unsigned blocks = (unsigned)((total * 32 + 255) / 256);
   if (dtype == MAPDIT_F32) qk_norm_bwd_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>((float*)dqkv, (const float*)qkv, sc, total, heads2, d, head_dim, eps);
   else qk_norm_bwd_kernel<bf16><<<blocks, 256, 0, (cudaStream_t)stream>>>((bf16*)dqkv, (const bf16*)qkv, sc, total, heads2, d, head_dim, eps);
@@ -371,6 +459,75 @@ extern "C" int mapdit_patchify(const float* x, float* P, int n_samples, int chan
   int64_t total = (int64_t)n_samples * g * g * (patch * patch * channels + 1);
   patchify_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, P, total, channels, input_size, patch);
   MAPDIT_LAUNCH_CHECK("patchify");
+  return MAPDIT_OK;
+}
+
+// x_embedder weight gradient: dW[dch, k] = scale * sum_tok R[tok, dch] * P[tok, k]  (K+1 <= 32 columns per pass).
+// CTA = 256 tokens x 256 channels: patches staged in smem, each thread owns one channel and keeps K+1 accumulators,
+// partial sums over the token chunks are combined with fp32 atomics into a zeroed dW.
+template <typename T>
+__global__ void __launch_bounds__(256) patch_embed_wgrad_kernel(const T* __restrict__ R, const float* __restrict__ x,
+                                                                float* __restrict__ dW, int64_t m_total, int C, int S, int p, int d,
+                                                                int k0, float scale) {
+  __shared__ float sp[64][33];
+  const int g = S / p, T_ = g * g, K = p * p * C, K1 = K + 1;
+  const int kn = min(32, K1 - k0);
+  const int col = blockIdx.y * 256 + threadIdx.x;
+  float acc[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+  const int64_t tok_begin = (int64_t)blockIdx.x * 256;
+  for (int64_t t0 = tok_begin; t0 < min(m_total, tok_begin + 256); t0 += 64) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64 * 32; i += 256) {
+      int tl = i >> 5, kk = i & 31;
+      int64_t tok = t0 + tl;
+      float v = 0.f;
+      if (tok < m_total && kk < kn) {
+        int f = k0 + kk;
+        if (f == K) v = 1.0f;
+        else {
+          int64_t n = tok / T_;
+          int tt = (int)(tok - n * T_);
+          int hh = tt / g, ww = tt - hh * g;
+          int c = f % C, pp = f / C, p1 = pp / p, p2 = pp - p1 * p;
+          v = x[((n * C + c) * S + (hh * p + p1)) * (int64_t)S + (ww * p + p2)];
+        }
+      }
+      sp[tl][kk] = v;
+    }
+    __syncthreads();
+    if (col < d) {
+      for (int tl = 0; tl < 64; ++tl) {
+        int64_t tok = t0 + tl;
+        if (tok >= m_total) break;
+        float r = ld_act(R + tok * d + col);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[j] = fmaf(r, sp[tl][j], acc[j]);
+      }
+    }
+  }
+  if (col < d) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < kn) atomicAdd(dW + (size_t)col * K1 + k0 + j, acc[j] * scale);
+  }
+}
+extern "C" int mapdit_patch_embed_wgrad(const void* R, const float* x, float* dW, int n_samples, int channels, int input_size,
+                                        int patch, int d, float scale, int dtype, void* stream) {
+  MAPDIT_REQUIRE(R && x && dW && n_samples > 0 && input_size % patch == 0, "patch_embed_wgrad: bad args");
+  const int g = input_size / patch, K1 = patch * patch * channels + 1;
+  const int64_t m_total = (int64_t)n_samples * g * g;
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaMemsetAsync(dW, 0, (size_t)d * K1 * sizeof(float), s);
+  dim3 grid((unsigned)((m_total + 255) / 256), (unsigned)((d + 255) / 256));
+  for (int k0 = 0; k0 < K1; k0 += 32) {
+    if (dtype == MAPDIT_F32)
+      patch_embed_wgrad_kernel<float><<<grid, 256, 0, s>>>((const float*)R, x, dW, m_total, channels, input_size, patch, d, k0, scale);
+    else
+      patch_embed_wgrad_kernel<bf16><<<grid, 256, 0, s>>>((const bf16*)R, x, dW, m_total, channels, input_size, patch, d, k0, scale);
+    MAPDIT_LAUNCH_CHECK("patch_embed_wgrad");
+  }
   return MAPDIT_OK;
 }
 

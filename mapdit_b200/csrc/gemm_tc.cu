@@ -21,7 +21,7 @@ namespace {
 using namespace tc;
 
 constexpr int BM = 128, BK = 64, UK = 16;
-constexpr int NUM_THREADS = 256;
+constexpr int NUM_THREADS = 384;  // warps 0-3: TMA / MMA / TMEM alloc / spare, warps 4-11: epilogue
 constexpr int SMEM_LIMIT = 227 * 1024;
 
 template <int BN>
@@ -129,7 +129,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 4);
+      mbar_init(&tempty[a], 8);
     }
     fence_barrier_init();
   }
@@ -189,26 +189,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     }
   } else if (warp >= 4) {
     // ------------------------------------------------ epilogue (TMEM lane quarter = warp % 4)
-    const int q = warp - 4;
+    // 8 epilogue warps: TMEM lane quarter = warp % 4, the two warps of a quarter take alternate column chunks
+    const int q = warp & 3, half = (warp - 4) >> 2;
     uint32_t acc = 0, acc_phase = 0;
     float gsc = 0.f, inv_den = 1.f;
     if (ep.epilogue == MAPDIT_EPI_RESID_MOD) {
       gsc = *ep.gain;
       inv_den = 1.0f / mod_den(gsc);
     }
+    const bool reads_resid = ep.epilogue == MAPDIT_EPI_RESID || ep.epilogue == MAPDIT_EPI_RESID_MOD || ep.epilogue == MAPDIT_EPI_SILU_BWD;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m_blk = tile / num_n_blocks, n_blk = tile - m_blk * num_n_blocks;
-      mbar_wait(&tfull[acc], acc_phase);
-      tc_fence_after();
       const int row = m_blk * BM + q * 32 + lane;
       const bool row_ok = row < ep.M;
-      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
       const long long sample = row_ok ? row / ep.tokens : 0;
+      // the residual / pre-activation row segment of the first chunk is fetched before waiting for the accumulator
+      uint4 pre[4];
+      auto prefetch = [&](int c) {
+        const int col = n_blk * BN + c;
+        const int nvalid = min(32, ep.N - col);
+        const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(ep.resid) + (long long)row * ep.ldo + col);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) pre[g] = (row_ok && g * 8 < nvalid) ? src[g] : make_uint4(0, 0, 0, 0);
+      };
+      if (reads_resid && half * 32 < BN) prefetch(half * 32);
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
 
       if (ep.epilogue == MAPDIT_EPI_QKNORM) {
         // 64 columns (= one head) at a time
         if constexpr (BN % 64 == 0) {
-          for (int c = 0; c < BN; c += 64) {
+          for (int c = half * 64; c < BN; c += 128) {
             uint32_t r0[32], r1[32];
             tmem_ld32(t_row + c, r0);
             tmem_ld32(t_row + c + 32, r1);
@@ -239,7 +251,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           }
         }
       } else {
-        for (int c = 0; c < BN; c += 32) {
+        for (int c = half * 32; c < BN; c += 64) {
           uint32_t r[32];
           tmem_ld32(t_row + c, r);
           tmem_ld_wait();
@@ -248,6 +260,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           float f[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(r[j]);
+          float xo[32];
+          if (reads_resid) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&pre[g]);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float2 t2 = __bfloat1622float2(hp[j]);
+                xo[g * 8 + 2 * j] = t2.x;
+                xo[g * 8 + 2 * j + 1] = t2.y;
+              }
+            }
+            if (c + 64 < BN) prefetch(c + 64);  // next chunk's residual while this one is processed
+          }
           if (!row_ok || nvalid <= 0) continue;
           const long long off = (long long)row * ep.ldo + col;
           if (ep.epilogue == MAPDIT_EPI_STORE) {
@@ -257,20 +283,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = silu_fast(f[j]);
             store_row32(ep.out, off, f, nvalid, false);
+          } else if (ep.epilogue == MAPDIT_EPI_SILU_BWD) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float sg = __fdividef(1.0f, 1.0f + __expf(-xo[j]));
+              f[j] *= sg * fmaf(xo[j], 1.0f - sg, 1.0f) * (1.0f / MP_SILU_DIV);
+            }
+            store_row32(ep.out, off, f, nvalid, false);
           } else {  // RESID / RESID_MOD
-            float xo[32], gt[32];
-            load_row32_bf16(ep.resid, off, xo, nvalid);
+            float gt[32];
             if (ep.aux) store_row32(ep.aux, off, f, nvalid, false);  // raw branch output, needed for d(gate)
             load_row32_f32(ep.gate + sample * ep.ldmod + col, gt, nvalid);
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = fmaf(MP_RES_T, gt[j] * f[j] - xo[j], xo[j]) * (1.0f / MP_RES_DEN);
             store_row32(ep.out, off, f, nvalid, false);
             if (ep.epilogue == MAPDIT_EPI_RESID_MOD) {
-              float sh[32];
-              load_row32_f32(ep.shift + sample * ep.ldmod + col, sh, nvalid);
+              load_row32_f32(ep.shift + sample * ep.ldmod + col, xo, nvalid);
               load_row32_f32(ep.scale + sample * ep.ldmod + col, gt, nvalid);
 #pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = lerp_t(f[j] * gt[j], sh[j], gsc) * inv_den;
+              for (int j = 0; j < 32; ++j) f[j] = lerp_t(f[j] * gt[j], xo[j], gsc) * inv_den;
               store_row32(ep.out2, off, f, nvalid, false);
             }
           }
@@ -361,6 +392,7 @@ extern "C" int mapdit_gemm_bf16(const mapdit_gemm_args* g, void* stream) {
     epi = MAPDIT_EPI_STORE;  // head_dim 72 (DiT-XL): plain store, then the row-wise normalise kernel
     post_qknorm = true;
   }
+  if (epi == MAPDIT_EPI_SILU_BWD) MAPDIT_REQUIRE(g->resid != nullptr, "gemm_bf16: SILU_BWD epilogue needs the pre-activation in `resid`");
   if (epi == MAPDIT_EPI_RESID || epi == MAPDIT_EPI_RESID_MOD) {
     MAPDIT_REQUIRE(g->resid && g->gate && g->tokens > 0 && g->ldmod % 4 == 0, "gemm_bf16: residual epilogue needs resid/gate/tokens");
     if (epi == MAPDIT_EPI_RESID_MOD) MAPDIT_REQUIRE(g->out2 && g->shift && g->scale && g->gain, "gemm_bf16: modulate epilogue needs out2/shift/scale/gain");

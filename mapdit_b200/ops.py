@@ -203,6 +203,12 @@ def patchify(x, P, patch):
     check(lib().mapdit_patchify(_ptr(x), _ptr(P), n, c, s, patch, _stream()), "patchify")
 
 
+def patch_embed_wgrad(R, x, dW, patch, scale):
+    n, c, s, _ = x.shape
+    check(lib().mapdit_patch_embed_wgrad(_ptr(R), _ptr(x), _ptr(dW), n, c, s, patch, R.shape[1], float(scale), _dt(R), _stream()),
+          "patch_embed_wgrad")
+
+
 def axpby(x, y, a, accumulate=False):
     check(lib().mapdit_axpby(_ptr(x), _ptr(y), float(a), int(accumulate), x.numel(), _stream()), "axpby")
 

@@ -61,6 +61,15 @@ def test_gemm_bf16_fused_epilogues(N, T, D):
     ops.gemm_bf16(h, w1, u, epilogue=_lib.EPI_MPSILU, out2=pre)
     assert rel_l2(u.float(), F.silu(z) / 0.596) < 3e-3
     assert rel_l2(pre.float(), z) < 3e-3
+    # SILU_BWD: dgrad of fc2 fused with MPSiLU's backward, dz = (dy @ W2) * d/dz[silu(z)/0.596]
+    dy = rnd(M, D, seed=11).bfloat16()
+    w2t = rnd(4 * D, D, seed=12, scale=D ** -0.5).bfloat16()
+    zb = pre.clone()
+    dz = torch.empty(M, 4 * D, device="cuda", dtype=torch.bfloat16)
+    ops.gemm_bf16(dy, w2t, dz, epilogue=_lib.EPI_SILU_BWD, resid=zb)
+    zf = zb.float()
+    sg = torch.sigmoid(zf)
+    assert rel_l2(dz.float(), (dy.float() @ w2t.float().t()) * sg * (1 + zf * (1 - sg)) / 0.596) < 3e-3
     # RESID_MOD, in place on x
     x = rnd(M, D, seed=6).bfloat16()
     mods = rnd(N, 6 * D, seed=7)
