@@ -85,8 +85,12 @@ def lib():
         L.mapdit_abi_version.restype = _i
         L.mapdit_launch_count.restype = _i64
         L.mapdit_modulate_bwd_partials.argtypes = [_i, _i]
+        L.mapdit_set_option.argtypes = [C.c_char_p, _i]
+        L.mapdit_set_option.restype = _i
         L.mapdit_modulate_bwd_partials.restype = _i
         _lib = L
+        if os.environ.get("MAPDIT_GEMM_2CTA") is not None:
+            L.mapdit_set_option(b"gemm_2cta", int(os.environ["MAPDIT_GEMM_2CTA"]))
     return _lib
 
 
@@ -111,3 +115,7 @@ def note_graph_replay(kernels_in_graph: int):
 
 def total_launches() -> int:
     return launch_count() + _replayed
+
+
+def set_option(name: str, value: int):
+    check(lib().mapdit_set_option(name.encode(), int(value)), "set_option")

@@ -1,0 +1,226 @@
+// 2-CTA variant of the bf16 tcgen05 GEMM: a CTA pair (cluster of 2, one TPC) computes a 256 x BN tile with
+// tcgen05.mma.cta_group::2.  Each CTA loads its own 128 rows of A and only HALF of the B tile; the tensor core
+// reads both halves across the pair, so every SM ingests (128 + BN/2) rows per k-block instead of (128 + BN):
+// the 1-CTA kernel is operand-delivery bound (profiles/r1_gemm_tc_ncu_summary.md), this cuts that traffic by 1/3
+// and frees shared memory for a 7-stage ring.  Same warp roles, barriers and fused epilogues as gemm_tc.cu; the
+// leader CTA (cluster rank 0) issues the MMAs, commits are multicast to both CTAs' barriers, and both CTAs'
+// epilogue warps release the accumulator stage on the leader's barrier.
+#include "gemm_epilogue.cuh"
+
+namespace {
+using namespace tc;
+using namespace gemm_epi;
+
+constexpr int BM = 128, BK = 64, UK = 16;  // BM = rows per CTA (256 per pair)
+constexpr int NUM_THREADS = 384;
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;  // clears the CTA-parity bit of a shared::cluster address -> leader CTA
+
+template <int BN>
+struct Cfg2 {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int BH_BYTES = (BN / 2) * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + BH_BYTES;
+  static constexpr int MAX_STAGES = (227 * 1024 - 2048) / STAGE_BYTES;
+  static constexpr int STAGES = MAX_STAGES > 8 ? 8 : MAX_STAGES;
+  static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// both CTAs load into their own smem; the transaction bytes are credited to the LEADER's mbarrier
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"((uint64_t)m), "r"(smem_u32(bar) & PEER_MASK), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_ss_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (once the issued MMAs retire) on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_MASK) : "memory");
+}
+template <uint32_t NCOLS>
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t* smem_slot) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "n"(NCOLS) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <uint32_t NCOLS>
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const EpiParams ep,
+                int num_m_blocks, int num_n_blocks, int num_k_blocks) {
+  using C = Cfg2<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* empty = full + C::STAGES;
+  uint64_t* tfull = empty + C::STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const int total_tiles = ((num_m_blocks + 1) >> 1) * num_n_blocks;  // 256-row tiles
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tma_a);
+    prefetch_tmap(&tma_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], 16);  // 8 epilogue warps of each CTA of the pair
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_2cta<C::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------------------------ TMA producer (both CTAs)
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+      const int m_pair = tile / num_n_blocks, n_blk = tile - m_pair * num_n_blocks;
+      const int m_blk = 2 * m_pair + (int)rank;
+      for (int kb = 0; kb < num_k_blocks; ++kb) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * C::STAGE_BYTES;
+        if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * C::STAGE_BYTES);
+        tma_load_2d_2sm(sa, &tma_a, &full[stage], kb * BK, m_blk * BM);
+        tma_load_2d_2sm(sa + C::A_BYTES, &tma_b, &full[stage], kb * BK, n_blk * BN + (int)rank * (BN / 2));
+        if (++stage == C::STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0 && rank == 0) {
+    // ------------------------------------------------ MMA issuer (leader CTA only)
+    constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0, acc = 0, acc_phase = 0;
+    for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+      mbar_wait(&tempty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < num_k_blocks; ++kb) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + stage * C::STAGE_BYTES);
+        const uint32_t b_addr = a_addr + C::A_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / UK; ++k)
+          umma_ss_2cta(d_tmem, make_smem_desc(a_addr + k * UK * 2, 16, 1024), make_smem_desc(b_addr + k * UK * 2, 16, 1024), idesc,
+                       (kb | k) != 0 ? 1u : 0u);
+        umma_commit_2cta(&empty[stage]);
+        if (++stage == C::STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      umma_commit_2cta(&tfull[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------ epilogue (both CTAs, own 128 rows)
+    const int q = warp & 3, half = (warp - 4) >> 2;
+    uint32_t acc = 0, acc_phase = 0;
+    float gsc = 0.f, inv_den = 1.f;
+    if (ep.epilogue == MAPDIT_EPI_RESID_MOD) {
+      gsc = *ep.gain;
+      inv_den = 1.0f / mod_den(gsc);
+    }
+    for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+      const int m_pair = tile / num_n_blocks, n_blk = tile - m_pair * num_n_blocks;
+      const int row = (2 * m_pair + (int)rank) * BM + q * 32 + lane;
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+      run_tile<BN>(ep, t_row, row, n_blk, half, gsc, inv_den, [&]() {
+        mbar_wait(&tfull[acc], acc_phase);
+        tc_fence_after();
+      });
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&tempty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // nobody leaves while the peer may still read its smem / signal its barriers
+  if (warp == 2) tmem_dealloc_2cta<C::TMEM_COLS>(tmem_base);
+}
+
+template <int BN>
+int launch2(const mapdit_gemm_args* g, const EpiParams& ep, cudaStream_t stream, int num_sms) {
+  using C = Cfg2<BN>;
+  CUtensorMap ta, tb;
+  const uint64_t dims_a[2] = {(uint64_t)g->k, (uint64_t)g->m}, dims_b[2] = {(uint64_t)g->k, (uint64_t)g->n};
+  const uint64_t str_a[1] = {(uint64_t)g->lda * 2}, str_b[1] = {(uint64_t)g->ldb * 2};
+  const uint32_t box_a[2] = {BK, BM}, box_b[2] = {BK, BN / 2};
+  CUresult r1 = mapdit_encode_tmap(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g->a, dims_a, str_a, box_a, CU_TENSOR_MAP_SWIZZLE_128B);
+  CUresult r2 = mapdit_encode_tmap(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g->b, dims_b, str_b, box_b, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) {
+    mapdit_set_error("gemm_bf16(2cta): cuTensorMapEncodeTiled failed (%d, %d)", (int)r1, (int)r2);
+    return MAPDIT_ERR_CUDA;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      mapdit_set_error("gemm_bf16(2cta): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return MAPDIT_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  const int mb = (g->m + BM - 1) / BM, nb = (g->n + BN - 1) / BN, kb = (g->k + BK - 1) / BK;
+  const int tiles = ((mb + 1) / 2) * nb;
+  const int max_clusters = num_sms / 2;
+  const int clusters = tiles < max_clusters ? tiles : max_clusters;
+  gemm_tc2_kernel<BN><<<2 * clusters, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, ep, mb, nb, kb);
+  return MAPDIT_OK;
+}
+}  // namespace
+
+// returns MAPDIT_ERR_UNSUPPORTED (without setting an error) when the shape should go to the 1-CTA kernel
+int mapdit_gemm_bf16_2cta(const mapdit_gemm_args* g, const gemm_epi::EpiParams& ep, cudaStream_t stream, int num_sms) {
+  const int mb = (g->m + BM - 1) / BM;
+  if (g->n % 256 == 0 && (long long)((mb + 1) / 2) * (g->n / 256) >= num_sms / 2) return launch2<256>(g, ep, stream, num_sms);
+  if (g->n % 128 == 0 && (long long)((mb + 1) / 2) * (g->n / 128) >= num_sms) return launch2<128>(g, ep, stream, num_sms);
+  return MAPDIT_ERR_UNSUPPORTED;
+}

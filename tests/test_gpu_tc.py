@@ -18,12 +18,14 @@ def rnd(*shape, seed=0, scale=1.0):
 
 
 SHAPES = [(128, 32, 64), (256, 256, 64), (128, 64, 128), (512, 1152, 384), (200, 96, 384), (4096, 2304, 768), (8192, 768, 3072),
-          (1000, 1536, 384), (256, 4608, 768), (384, 384, 1536)]
+          (1000, 1536, 384), (256, 4608, 768), (384, 384, 1536), (5248, 1024, 128), (5200, 1024, 192), (16384, 1152, 384)]
 
 
 @pytest.mark.parametrize("m,n,k", SHAPES)
-def test_gemm_bf16_store(m, n, k):
-    from mapdit_b200 import ops
+@pytest.mark.parametrize("two_cta", [0, 1])
+def test_gemm_bf16_store(m, n, k, two_cta):
+    from mapdit_b200 import _lib, ops
+    _lib.set_option("gemm_2cta", two_cta)  # 1 = cta_group::2 kernel where the shape qualifies
     a, b = rnd(m, k, seed=1).bfloat16(), rnd(n, k, seed=2, scale=k ** -0.5).bfloat16()
     ref = a.double() @ b.double().t()
     out32 = torch.full((m, n), float("nan"), device="cuda")
@@ -39,9 +41,11 @@ def test_gemm_bf16_store(m, n, k):
     assert rel_l2(out32, ref) < 1e-5
 
 
-@pytest.mark.parametrize("N,T,D", [(2, 64, 384), (3, 256, 256), (1, 256, 768), (33, 64, 384)])
-def test_gemm_bf16_fused_epilogues(N, T, D):
+@pytest.mark.parametrize("N,T,D", [(2, 64, 384), (3, 256, 256), (1, 256, 768), (33, 64, 384), (40, 256, 256), (41, 128, 768)])
+@pytest.mark.parametrize("two_cta", [0, 1])
+def test_gemm_bf16_fused_epilogues(N, T, D, two_cta):
     from mapdit_b200 import _lib, ops
+    _lib.set_option("gemm_2cta", two_cta)
     M, hd = N * T, 64
     h = rnd(M, D, seed=3).bfloat16()
     wqkv = rnd(3 * D, D, seed=4, scale=D ** -0.5).bfloat16()
