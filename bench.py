@@ -83,14 +83,23 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------- reference arm (CPU)
-def run_reference(args):
+def run_reference(args, workload=None, emit=True):
     """The reference's own implementation of the path cannot travel to the GPU box (it is a Python repo mounted
     read-only in the build container), so this arm times its pinned CPU restatement (oracle/, kind 'port') on all
     host cores, on a bounded sample of the same workload."""
     import torch
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
-        return
+        return None
+    workload = workload or args.workload
+    if workload == "both":
+        line = run_reference(args, "train", emit=False)
+        sl = run_reference(args, "sample", emit=False)
+        line["metric"] = "dit_b2_map_train_img_per_s (+ sample50 img/s in `sample50`)"
+        line["sample50"] = {k: sl[k] for k in ("value", "unit", "ms_per_step", "cpu_baseline", "e2e")}
+        print(json.dumps(line), flush=True)
+        return line
+        return line
     from oracle import mapdit_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
@@ -101,7 +110,7 @@ def run_reference(args):
     x = torch.randn(B, 4, 32, 32, generator=g)
     y = torch.randint(0, 1000, (B,), generator=g)
     times = []
-    if args.workload == "train":
+    if workload == "train":
         p = O.make_params(sd)
         T = O.make_tables("")
         opt = torch.optim.Adam([v for v in p.values() if v.requires_grad], lr=1e-2, betas=(0.9, 0.99))
@@ -117,9 +126,9 @@ def run_reference(args):
     else:
         T = O.make_tables(str(SAMPLING_STEPS))
         tm = torch.tensor(T.timestep_map)
-        nsub = 2 if args.workload == "sample" else 1
+        nsub = 2 if workload == "sample" else 1
         sample = (f"{MODEL} {nsub} of {SAMPLING_STEPS} sampling steps at batch {B} on the CPU oracle, scaled to {SAMPLING_STEPS} steps"
-                  if args.workload == "sample" else f"{MODEL} eval forward at batch {B} on the CPU oracle")
+                  if workload == "sample" else f"{MODEL} eval forward at batch {B} on the CPU oracle")
 
         def step():
             img = x
@@ -128,9 +137,9 @@ def run_reference(args):
                     i = T.num_timesteps - 1 - k
                     tt = torch.full((B,), i, dtype=torch.long)
                     out = O.dit_forward(sd, cfg, img, tm[tt], y)
-                    if args.workload == "sample":
+                    if workload == "sample":
                         img = O.p_sample_step(T, out, img, tt, torch.randn_like(img))["sample"]
-        per_step_images = B * nsub / SAMPLING_STEPS if args.workload == "sample" else B
+        per_step_images = B * nsub / SAMPLING_STEPS if workload == "sample" else B
     for i in range(args.warmup + args.steps):
         t0 = time.perf_counter()
         step()
@@ -139,13 +148,15 @@ def run_reference(args):
     ms = 1e3 * sum(times) / len(times)
     value = per_step_images / (ms / 1e3)
     unit = "img/s"
-    line = {"impl": "reference", "metric": metric_name(args.workload), "value": value, "unit": unit, "n_gpus": args.gpus,
+    line = {"impl": "reference", "metric": metric_name(workload), "value": value, "unit": unit, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(args.workload), "model": MODEL, "batch_per_step": B},
+            "config": {"workload": workload_name(workload), "model": MODEL, "batch_per_step": B},
             "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    if emit:
+        print(json.dumps(line), flush=True)
+    return line
 
 
 def metric_name(w):
@@ -246,18 +257,20 @@ def kernel_roofline(cfg, B, pk):
     return roof
 
 
-def run_ours(args):
+def run_ours(args, workload, finalize=True):
     import torch
     import torch.distributed as dist
     import mapdit_b200 as M
     from mapdit_b200 import _lib
+    if args.gemm_2cta is not None:
+        _lib.set_option("gemm_2cta", args.gemm_2cta)
     from oracle import mapdit_oracle as O  # weights only (deterministic init) + cpu_baseline leg
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
-    if world > 1:
+    if world > 1 and not dist.is_initialized():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     cfg = O.config_for(MODEL)
@@ -274,9 +287,9 @@ def run_ours(args):
     t_host = torch.randint(0, 1000, (B,), generator=g).pin_memory()
     z_dev, y_dev, t_dev = z_host.to(dev), y_host.to(dev), t_host.to(dev)
     out_host = torch.empty(B, 4, 32, 32).pin_memory()
-    diffusion = M.create_diffusion(str(SAMPLING_STEPS) if args.workload == "sample" else "")
+    diffusion = M.create_diffusion(str(SAMPLING_STEPS) if workload == "sample" else "")
 
-    if args.workload == "sample":
+    if workload == "sample":
         model.eval()
         gather = [torch.empty(B, 4, 32, 32, device=dev) for _ in range(world)] if world > 1 else None
 
@@ -297,7 +310,7 @@ def run_ours(args):
         images_per_step = B
         flops_step = fl["fwd"] * B * SAMPLING_STEPS
         h2d, d2h = z_host.numel() * 4 + y_host.numel() * 8, out_host.numel() * 4
-    elif args.workload == "forward":
+    elif workload == "forward":
         model.eval()
 
         def step_dev():
@@ -370,20 +383,24 @@ def run_ours(args):
             step_tf = flops_step * args.steps / (ms / 1e3) / 1e12
             roof["step_tflops_per_gpu"] = round(step_tf, 1)
             roof["step_frac_of_sustained"] = round(step_tf / pk["tf_sustained"], 4)
-        cpu = cpu_baseline(args.workload) if not args.no_cpu_baseline else None
-        line = {"metric": metric_name(args.workload), "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
+        cpu = cpu_baseline(workload) if not args.no_cpu_baseline else None
+        line = {"metric": metric_name(workload), "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-                "config": {"workload": workload_name(args.workload), "model": MODEL, "batch_per_gpu": B, "global_batch": B * world,
+                "config": {"workload": workload_name(workload), "model": MODEL, "batch_per_gpu": B, "global_batch": B * world,
                            "parallelism": f"dp{world}" if world > 1 else "single",
                            "l2": "per-step working set (activations ~100 MB per [M,D] tensor, 2.4 GB per block) exceeds the 126 MB L2; no flush needed",
                            "weights": "random init (numpy PCG64 seed 0), reference init distributions", "clip_denoised": False},
                 "e2e": {"value": e2e_value, "unit": "img/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": launches, "clocks": clk, "roofline": roof, "cpu_baseline": cpu}
-        print(json.dumps(line), flush=True)
-    if world > 1:
+    else:
+        line = None
+    del model
+    torch.cuda.empty_cache()
+    if world > 1 and finalize:
         dist.destroy_process_group()
+    return line
 
 
 def main():
@@ -392,9 +409,10 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("MAPDIT_BENCH_WORKLOAD", "sample"), choices=["sample", "train", "forward"])
+    ap.add_argument("--workload", default=os.environ.get("MAPDIT_BENCH_WORKLOAD", "both"), choices=["both", "sample", "train", "forward"])
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--gemm-2cta", type=int, default=None, help="override the GEMM kernel choice: 1 = cta_group::2 256xBN tiles, 0 = 1-CTA 128xBN")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -407,7 +425,23 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
                "--master-port", "29541", os.path.abspath(__file__)] + sys.argv[1:]
         sys.exit(subprocess.call(cmd))
-    run_ours(args)
+    if args.workload == "both":
+        # BASELINE.json's metric has two halves: the training step is the primary value, the 50-step sampler rides along
+        line = run_ours(args, "train", finalize=False)
+        sline = run_ours(args, "sample", finalize=True)
+        if line is not None:
+            line["metric"] = "dit_b2_map_train_img_per_s (+ sample50 img/s in `sample50`)"
+            keep = ("value", "unit", "ms_per_step", "e2e", "gpu_launches", "clocks", "cpu_baseline")
+            line["sample50"] = {k: sline[k] for k in keep}
+            line["sample50"]["metric"] = sline["metric"]
+            line["sample50"]["workload"] = sline["config"]["workload"]
+            if sline.get("roofline"):
+                line["sample50"]["step_tflops_per_gpu"] = sline["roofline"]["step_tflops_per_gpu"]
+                line["sample50"]["step_frac_of_sustained"] = sline["roofline"]["step_frac_of_sustained"]
+    else:
+        line = run_ours(args, args.workload)
+    if line is not None:
+        print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":

@@ -32,21 +32,23 @@ struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int MAX_STAGES = (SMEM_LIMIT - 2048) / STAGE_BYTES;
+  static constexpr int MAX_STAGES = (SMEM_LIMIT - 2048 - STG_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = MAX_STAGES > 8 ? 8 : MAX_STAGES;
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES /*epilogue staging*/ + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const EpiParams ep,
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+               const __grid_constant__ EpiTmaps etm, const EpiParams ep,
                int num_m_blocks, int num_n_blocks, int num_k_blocks) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint8_t* staging = smem + C::STAGES * C::STAGE_BYTES;  // 8 x 4 KB, 1024-aligned
+  uint64_t* full = reinterpret_cast<uint64_t*>(staging + STG_BYTES);
   uint64_t* empty = full + C::STAGES;
   uint64_t* tfull = empty + C::STAGES;
   uint64_t* tempty = tfull + 2;
@@ -134,11 +136,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       gsc = *ep.gain;
       inv_den = 1.0f / mod_den(gsc);
     }
+    Stager st{staging + (warp - 4) * STG_BYTES_PER_WARP, 0u, lane, 0};
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m_blk = tile / num_n_blocks, n_blk = tile - m_blk * num_n_blocks;
       const int row = m_blk * BM + q * 32 + lane;
+      st.row0 = m_blk * BM + q * 32;
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
-      run_tile<BN>(ep, t_row, row, n_blk, half, gsc, inv_den, [&]() {
+      run_tile<BN>(ep, etm, st, t_row, row, n_blk, half, gsc, inv_den, [&]() {
         mbar_wait(&tfull[acc], acc_phase);
         tc_fence_after();
       });
@@ -148,6 +152,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    st.drain();  // all TMA stores of this warp have completed before the CTA may exit
   }
 
   tc_fence_before();
@@ -180,7 +185,12 @@ int launch(const mapdit_gemm_args* g, const EpiParams& ep, cudaStream_t stream, 
   const int mb = (g->m + BM - 1) / BM, nb = (g->n + BN - 1) / BN, kb = (g->k + BK - 1) / BK;
   const int tiles = mb * nb;
   const int grid = tiles < num_sms ? tiles : num_sms;
-  gemm_tc_kernel<BN><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, ep, mb, nb, kb);
+  EpiTmaps etm;
+  if (make_store_maps(&etm, ep) != 0) {
+    mapdit_set_error("gemm_bf16: cuTensorMapEncodeTiled (store maps) failed");
+    return MAPDIT_ERR_CUDA;
+  }
+  gemm_tc_kernel<BN><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, etm, ep, mb, nb, kb);
   return MAPDIT_OK;
 }
 

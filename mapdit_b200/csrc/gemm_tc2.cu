@@ -20,10 +20,10 @@ struct Cfg2 {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int BH_BYTES = (BN / 2) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + BH_BYTES;
-  static constexpr int MAX_STAGES = (227 * 1024 - 2048) / STAGE_BYTES;
+  static constexpr int MAX_STAGES = (227 * 1024 - 2048 - STG_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = MAX_STAGES > 8 ? 8 : MAX_STAGES;
   static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + 1024 + 256;
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -71,13 +71,15 @@ __device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr) {
 
 template <int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
-gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const EpiParams ep,
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                const __grid_constant__ EpiTmaps etm, const EpiParams ep,
                 int num_m_blocks, int num_n_blocks, int num_k_blocks) {
   using C = Cfg2<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint8_t* staging = smem + C::STAGES * C::STAGE_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(staging + STG_BYTES);
   uint64_t* empty = full + C::STAGES;
   uint64_t* tfull = empty + C::STAGES;
   uint64_t* tempty = tfull + 2;
@@ -165,11 +167,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
       gsc = *ep.gain;
       inv_den = 1.0f / mod_den(gsc);
     }
+    Stager st{staging + (warp - 4) * STG_BYTES_PER_WARP, 0u, lane, 0};
     for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
       const int m_pair = tile / num_n_blocks, n_blk = tile - m_pair * num_n_blocks;
       const int row = (2 * m_pair + (int)rank) * BM + q * 32 + lane;
+      st.row0 = (2 * m_pair + (int)rank) * BM + q * 32;
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
-      run_tile<BN>(ep, t_row, row, n_blk, half, gsc, inv_den, [&]() {
+      run_tile<BN>(ep, etm, st, t_row, row, n_blk, half, gsc, inv_den, [&]() {
         mbar_wait(&tfull[acc], acc_phase);
         tc_fence_after();
       });
@@ -179,6 +183,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    st.drain();
   }
 
   tc_fence_before();
@@ -212,7 +217,12 @@ int launch2(const mapdit_gemm_args* g, const EpiParams& ep, cudaStream_t stream,
   const int tiles = ((mb + 1) / 2) * nb;
   const int max_clusters = num_sms / 2;
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
-  gemm_tc2_kernel<BN><<<2 * clusters, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, ep, mb, nb, kb);
+  EpiTmaps etm;
+  if (make_store_maps(&etm, ep) != 0) {
+    mapdit_set_error("gemm_bf16(2cta): cuTensorMapEncodeTiled (store maps) failed");
+    return MAPDIT_ERR_CUDA;
+  }
+  gemm_tc2_kernel<BN><<<2 * clusters, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, etm, ep, mb, nb, kb);
   return MAPDIT_OK;
 }
 }  // namespace
