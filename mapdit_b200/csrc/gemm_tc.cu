@@ -226,7 +226,7 @@ CUresult mapdit_encode_tmap(CUtensorMap* map, CUtensorMapDataType dt, uint32_t r
 }
 
 int mapdit_gemm_bf16_2cta(const mapdit_gemm_args* g, const gemm_epi::EpiParams& ep, cudaStream_t stream, int num_sms);
-static int g_use_2cta = 0;
+static int g_use_2cta = 1;  // CTA-pair kernel by default where the shape qualifies (A/B: bench.py --gemm-2cta 0)
 
 // runtime switches (benchmark A/B): "gemm_2cta" = 0/1
 extern "C" int mapdit_set_option(const char* name, int value) {
