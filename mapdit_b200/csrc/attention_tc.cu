@@ -32,7 +32,7 @@ __device__ __forceinline__ float ex2(float x) {
 
 __global__ void __launch_bounds__(NTHREADS, 2)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, bf16* __restrict__ o,
-               float* __restrict__ lse, int tokens, int heads) {
+               float* __restrict__ lse, int tokens, int heads, int n_samples) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -40,7 +40,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
   uint8_t* sKV = sQ + Q_BYTES;            // stage s: K at sKV + s*2*KV_BYTES, V right after
   uint8_t* sP = sKV + 2 * 2 * KV_BYTES;   // 2 buffers
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * P_BYTES);
-  uint64_t* bar_q = bars;
+  uint64_t* q_full = bars;
   uint64_t* kv_full = bars + 1;
   uint64_t* kv_empty = bars + 3;
   uint64_t* s_full = bars + 5;
@@ -48,19 +48,21 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
   uint64_t* p_full = bars + 9;
   uint64_t* p_empty = bars + 11;
   uint64_t* o_full = bars + 13;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* q_empty = bars + 14;
+  uint64_t* o_empty = bars + 15;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qt = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
   const int D = heads * HD;
-  const int q0 = qt * QT;
   const int nkb = tokens / KB;
-  const int row_base = n * tokens;
+  const int nqt = (tokens + QT - 1) / QT;
+  const int total_items = nqt * heads * n_samples;  // persistent: each CTA walks items blockIdx.x, +gridDim.x, ...
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tm_q);
     prefetch_tmap(&tm_kv);
-    mbar_init(bar_q, 1);
+    mbar_init(q_full, 1);
+    mbar_init(q_empty, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&kv_full[i], 1);
       mbar_init(&kv_empty[i], 1);
@@ -70,6 +72,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
       mbar_init(&p_empty[i], 1);
     }
     mbar_init(o_full, 1);
+    mbar_init(o_empty, 4);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
@@ -79,26 +82,32 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
   if (warp == 0 && lane == 0) {
-    // ------------------------------------------------ TMA producer
-    mbar_arrive_expect_tx(bar_q, Q_BYTES);
-    tma_load_2d(sQ, &tm_q, bar_q, h * HD, row_base + q0);
-    for (int j = 0; j < nkb; ++j) {
-      const int s = j & 1;
-      mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1);
-      uint8_t* k_dst = sKV + s * 2 * KV_BYTES;
-      mbar_arrive_expect_tx(&kv_full[s], 2 * KV_BYTES);
-      tma_load_2d(k_dst, &tm_kv, &kv_full[s], D + h * HD, row_base + j * KB);
-      tma_load_2d(k_dst + KV_BYTES, &tm_kv, &kv_full[s], 2 * D + h * HD, row_base + j * KB);
+    // ------------------------------------------------ TMA producer (runs ahead into the next item)
+    uint32_t g = 0, it = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
+      const int qt = item % nqt, rest = item / nqt, h = rest % heads, n = rest / heads;
+      const int row_base = n * tokens;
+      mbar_wait(q_empty, (it & 1) ^ 1);
+      mbar_arrive_expect_tx(q_full, Q_BYTES);
+      tma_load_2d(sQ, &tm_q, q_full, h * HD, row_base + qt * QT);
+      for (int j = 0; j < nkb; ++j, ++g) {
+        const int s = g & 1;
+        mbar_wait(&kv_empty[s], ((g >> 1) & 1) ^ 1);
+        uint8_t* k_dst = sKV + s * 2 * KV_BYTES;
+        mbar_arrive_expect_tx(&kv_full[s], 2 * KV_BYTES);
+        tma_load_2d(k_dst, &tm_kv, &kv_full[s], D + h * HD, row_base + j * KB);
+        tma_load_2d(k_dst + KV_BYTES, &tm_kv, &kv_full[s], 2 * D + h * HD, row_base + j * KB);
+      }
     }
   } else if (warp == 1 && lane == 0) {
     // ------------------------------------------------ MMA issuer
     constexpr uint32_t idesc_s = make_idesc_bf16(QT, KB, 0, 0);   // S = Q K^T : both K-major
     constexpr uint32_t idesc_o = make_idesc_bf16(QT, HD, 0, 1);   // O = P V   : V is MN-major (d contiguous)
     const uint32_t q_addr = smem_u32(sQ);
-    auto issue_s = [&](int j) {
-      const int s = j & 1;
-      mbar_wait(&kv_full[s], (j >> 1) & 1);
-      mbar_wait(&s_empty[s], ((j >> 1) & 1) ^ 1);
+    auto issue_s = [&](uint32_t gg) {
+      const int s = gg & 1;
+      mbar_wait(&kv_full[s], (gg >> 1) & 1);
+      mbar_wait(&s_empty[s], ((gg >> 1) & 1) ^ 1);
       tc_fence_after();
       const uint32_t k_addr = smem_u32(sKV + s * 2 * KV_BYTES);
 #pragma unroll
@@ -107,96 +116,116 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
                 k != 0);
       umma_commit(&s_full[s]);
     };
-    mbar_wait(bar_q, 0);
-    issue_s(0);
-    for (int j = 0; j < nkb; ++j) {
-      const int s = j & 1;
-      if (j + 1 < nkb) issue_s(j + 1);
-      mbar_wait(&p_full[s], (j >> 1) & 1);
-      tc_fence_after();
-      const uint32_t p_addr = smem_u32(sP + s * P_BYTES);
-      const uint32_t v_addr = smem_u32(sKV + s * 2 * KV_BYTES + KV_BYTES);
+    uint32_t g = 0, it = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
+      mbar_wait(q_full, it & 1);
+      issue_s(g);
+      if (nkb == 1) umma_commit(q_empty);  // Q tile free once the item's last S MMA retires
+      for (int j = 0; j < nkb; ++j) {
+        const uint32_t gg = g + j;
+        const int s = gg & 1;
+        if (j + 1 < nkb) {
+          issue_s(gg + 1);
+          if (j + 2 == nkb) umma_commit(q_empty);
+        }
+        if (j == 0) mbar_wait(o_empty, (it & 1) ^ 1);  // previous item's O has been read out of TMEM
+        mbar_wait(&p_full[s], (gg >> 1) & 1);
+        tc_fence_after();
+        const uint32_t p_addr = smem_u32(sP + s * P_BYTES);
+        const uint32_t v_addr = smem_u32(sKV + s * 2 * KV_BYTES + KV_BYTES);
 #pragma unroll
-      for (int k = 0; k < KB / 16; ++k)  // 16 keys per MMA: P advances 32 B along K, V advances two 8-row groups
-        umma_ss(tmem_base + 128, make_smem_desc(p_addr + k * 32, 16, 1024), make_smem_desc(v_addr + k * 2048, 1024, 1024), idesc_o,
-                (j | k) != 0);
-      umma_commit(&kv_empty[s]);
-      umma_commit(&p_empty[s]);
+        for (int k = 0; k < KB / 16; ++k)  // 16 keys per MMA: P advances 32 B along K, V advances two 8-row groups
+          umma_ss(tmem_base + 128, make_smem_desc(p_addr + k * 32, 16, 1024), make_smem_desc(v_addr + k * 2048, 1024, 1024), idesc_o,
+                  (j | k) != 0);
+        umma_commit(&kv_empty[s]);
+        umma_commit(&p_empty[s]);
+      }
+      umma_commit(o_full);
+      g += nkb;
     }
-    umma_commit(o_full);
   } else if (warp >= 2) {
     // ------------------------------------------------ softmax + epilogue; TMEM lane quarter = warp % 4
     const int qq = warp & 3;
     const int r = qq * 32 + lane;  // query row inside the tile
     const uint32_t t_lane = tmem_base + ((uint32_t)(qq * 32) << 16);
     const float c1 = 0.125f * 1.4426950408889634f, c2 = 8.0f * 1.4426950408889634f;
-    float rowsum = 0.f;
-    for (int j = 0; j < nkb; ++j) {
-      const int s = j & 1;
-      const uint32_t ph = (j >> 1) & 1;
-      mbar_wait(&s_full[s], ph);
+    uint32_t g = 0, it = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
+      const int qt = item % nqt, rest = item / nqt, h = rest % heads, n = rest / heads;
+      const int row_base = n * tokens, q0 = qt * QT;
+      float rowsum = 0.f;
+      for (int j = 0; j < nkb; ++j) {
+        const uint32_t gg = g + j;
+        const int s = gg & 1;
+        const uint32_t ph = (gg >> 1) & 1;
+        mbar_wait(&s_full[s], ph);
+        tc_fence_after();
+        uint32_t a0[32], a1[32];
+        tmem_ld32(t_lane + s * KB, a0);
+        tmem_ld32(t_lane + s * KB + 32, a1);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[s]);
+        uint32_t pk[32];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float p0 = ex2(fmaf(__uint_as_float(a0[2 * i]), c1, -c2)), p1 = ex2(fmaf(__uint_as_float(a0[2 * i + 1]), c1, -c2));
+          __nv_bfloat162 b = __floats2bfloat162_rn(p0, p1);
+          float2 back = __bfloat1622float2(b);
+          rowsum += back.x + back.y;
+          pk[i] = *reinterpret_cast<uint32_t*>(&b);
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float p0 = ex2(fmaf(__uint_as_float(a1[2 * i]), c1, -c2)), p1 = ex2(fmaf(__uint_as_float(a1[2 * i + 1]), c1, -c2));
+          __nv_bfloat162 b = __floats2bfloat162_rn(p0, p1);
+          float2 back = __bfloat1622float2(b);
+          rowsum += back.x + back.y;
+          pk[16 + i] = *reinterpret_cast<uint32_t*>(&b);
+        }
+        mbar_wait(&p_empty[s], ph ^ 1);
+        // row r of the [128 x 64] bf16 K-major SWIZZLE_128B tile: 16-byte chunk c lives at c ^ (r % 8)
+        uint8_t* prow = sP + s * P_BYTES + (r >> 3) * 1024 + (r & 7) * 128;
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          *reinterpret_cast<uint4*>(prow + ((c ^ (r & 7)) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[s]);
+      }
+      g += nkb;
+      mbar_wait(o_full, it & 1);
       tc_fence_after();
-      uint32_t a0[32], a1[32];
-      tmem_ld32(t_lane + s * KB, a0);
-      tmem_ld32(t_lane + s * KB + 32, a1);
+      uint32_t o0[32], o1[32];
+      tmem_ld32(t_lane + 128, o0);
+      tmem_ld32(t_lane + 160, o1);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[s]);
-      uint32_t pk[32];
+      if (lane == 0) mbar_arrive(o_empty);
+      if (q0 + r < tokens) {
+        const float inv = 1.0f / rowsum;
+        if (lse) lse[(size_t)(row_base + q0 + r) * heads + h] = 8.0f + logf(rowsum);
+        bf16* dst = o + (size_t)(row_base + q0 + r) * D + h * HD;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        float p0 = ex2(fmaf(__uint_as_float(a0[2 * i]), c1, -c2)), p1 = ex2(fmaf(__uint_as_float(a0[2 * i + 1]), c1, -c2));
-        __nv_bfloat162 b = __floats2bfloat162_rn(p0, p1);
-        float2 back = __bfloat1622float2(b);
-        rowsum += back.x + back.y;
-        pk[i] = *reinterpret_cast<uint32_t*>(&b);
-      }
+        for (int c = 0; c < 4; ++c) {
+          uint4 u;
+          u.x = pack_bf16(__uint_as_float(o0[8 * c]) * inv, __uint_as_float(o0[8 * c + 1]) * inv);
+          u.y = pack_bf16(__uint_as_float(o0[8 * c + 2]) * inv, __uint_as_float(o0[8 * c + 3]) * inv);
+          u.z = pack_bf16(__uint_as_float(o0[8 * c + 4]) * inv, __uint_as_float(o0[8 * c + 5]) * inv);
+          u.w = pack_bf16(__uint_as_float(o0[8 * c + 6]) * inv, __uint_as_float(o0[8 * c + 7]) * inv);
+          *reinterpret_cast<uint4*>(dst + 8 * c) = u;
+        }
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        float p0 = ex2(fmaf(__uint_as_float(a1[2 * i]), c1, -c2)), p1 = ex2(fmaf(__uint_as_float(a1[2 * i + 1]), c1, -c2));
-        __nv_bfloat162 b = __floats2bfloat162_rn(p0, p1);
-        float2 back = __bfloat1622float2(b);
-        rowsum += back.x + back.y;
-        pk[16 + i] = *reinterpret_cast<uint32_t*>(&b);
-      }
-      mbar_wait(&p_empty[s], ph ^ 1);
-      // row r of the [128 x 64] bf16 K-major SWIZZLE_128B tile: 16-byte chunk c lives at c ^ (r % 8)
-      uint8_t* prow = sP + s * P_BYTES + (r >> 3) * 1024 + (r & 7) * 128;
-#pragma unroll
-      for (int c = 0; c < 8; ++c)
-        *reinterpret_cast<uint4*>(prow + ((c ^ (r & 7)) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[s]);
-    }
-    mbar_wait(o_full, 0);
-    tc_fence_after();
-    uint32_t o0[32], o1[32];
-    tmem_ld32(t_lane + 128, o0);
-    tmem_ld32(t_lane + 160, o1);
-    tmem_ld_wait();
-    if (q0 + r < tokens) {
-      const float inv = 1.0f / rowsum;
-      if (lse) lse[(size_t)(row_base + q0 + r) * heads + h] = 8.0f + logf(rowsum);
-      bf16* dst = o + (size_t)(row_base + q0 + r) * D + h * HD;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint4 u;
-        u.x = pack_bf16(__uint_as_float(o0[8 * c]) * inv, __uint_as_float(o0[8 * c + 1]) * inv);
-        u.y = pack_bf16(__uint_as_float(o0[8 * c + 2]) * inv, __uint_as_float(o0[8 * c + 3]) * inv);
-        u.z = pack_bf16(__uint_as_float(o0[8 * c + 4]) * inv, __uint_as_float(o0[8 * c + 5]) * inv);
-        u.w = pack_bf16(__uint_as_float(o0[8 * c + 6]) * inv, __uint_as_float(o0[8 * c + 7]) * inv);
-        *reinterpret_cast<uint4*>(dst + 8 * c) = u;
-      }
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint4 u;
-        u.x = pack_bf16(__uint_as_float(o1[8 * c]) * inv, __uint_as_float(o1[8 * c + 1]) * inv);
-        u.y = pack_bf16(__uint_as_float(o1[8 * c + 2]) * inv, __uint_as_float(o1[8 * c + 3]) * inv);
-        u.z = pack_bf16(__uint_as_float(o1[8 * c + 4]) * inv, __uint_as_float(o1[8 * c + 5]) * inv);
-        u.w = pack_bf16(__uint_as_float(o1[8 * c + 6]) * inv, __uint_as_float(o1[8 * c + 7]) * inv);
-        *reinterpret_cast<uint4*>(dst + 32 + 8 * c) = u;
+        for (int c = 0; c < 4; ++c) {
+          uint4 u;
+          u.x = pack_bf16(__uint_as_float(o1[8 * c]) * inv, __uint_as_float(o1[8 * c + 1]) * inv);
+          u.y = pack_bf16(__uint_as_float(o1[8 * c + 2]) * inv, __uint_as_float(o1[8 * c + 3]) * inv);
+          u.z = pack_bf16(__uint_as_float(o1[8 * c + 4]) * inv, __uint_as_float(o1[8 * c + 5]) * inv);
+          u.w = pack_bf16(__uint_as_float(o1[8 * c + 6]) * inv, __uint_as_float(o1[8 * c + 7]) * inv);
+          *reinterpret_cast<uint4*>(dst + 32 + 8 * c) = u;
+        }
       }
     }
   }
@@ -229,8 +258,11 @@ int mapdit_attn_tc_fwd(const void* qkv, void* o, float* lse, int n, int tokens, 
     }
     attr_set = true;
   }
-  dim3 grid((tokens + QT - 1) / QT, heads, n);
-  attn_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tq, tkv, (bf16*)o, lse, tokens, heads);
+  const int items = ((tokens + QT - 1) / QT) * heads * n;
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  const int grid = items < 2 * sms ? items : 2 * sms;  // persistent, two CTAs per SM
+  attn_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tq, tkv, (bf16*)o, lse, tokens, heads, n);
   MAPDIT_LAUNCH_CHECK("attn_tc_fwd");
   return MAPDIT_OK;
 }
