@@ -20,8 +20,8 @@ constexpr int HD = 64, QT = 128, KB = 64;
 constexpr int Q_BYTES = QT * HD * 2;   // 16 KB
 constexpr int KV_BYTES = KB * HD * 2;  // 8 KB each
 constexpr int P_BYTES = QT * KB * 2;   // 16 KB
-constexpr int SMEM_BYTES = Q_BYTES + 2 * 2 * KV_BYTES + 2 * P_BYTES + 1024 + 256;
-constexpr int NTHREADS = 192;
+constexpr int SMEM_BYTES = Q_BYTES + 2 * 2 * KV_BYTES + 2 * P_BYTES + 2 * 2 * QT * 4 /*row-sum exchange*/ + 1024 + 256;
+constexpr int NTHREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 softmax (two warps per TMEM lane quarter, 32 key columns each)
 constexpr uint32_t TMEM_COLS = 256;  // S0 [0,64) S1 [64,128) O [128,192)
 
 __device__ __forceinline__ float ex2(float x) {
@@ -39,7 +39,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
   uint8_t* sQ = smem;
   uint8_t* sKV = sQ + Q_BYTES;            // stage s: K at sKV + s*2*KV_BYTES, V right after
   uint8_t* sP = sKV + 2 * 2 * KV_BYTES;   // 2 buffers
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * P_BYTES);
+  float* sRS = reinterpret_cast<float*>(sP + 2 * P_BYTES);  // [2 (item parity)][2 (column half)][128 rows]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sRS + 2 * 2 * QT);
   uint64_t* q_full = bars;
   uint64_t* kv_full = bars + 1;
   uint64_t* kv_empty = bars + 3;
@@ -67,12 +68,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
       mbar_init(&kv_full[i], 1);
       mbar_init(&kv_empty[i], 1);
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], 4);
-      mbar_init(&p_full[i], 4);
+      mbar_init(&s_empty[i], 8);
+      mbar_init(&p_full[i], 8);
       mbar_init(&p_empty[i], 1);
     }
     mbar_init(o_full, 1);
-    mbar_init(o_empty, 4);
+    mbar_init(o_empty, 8);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
@@ -144,9 +145,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
       g += nkb;
     }
   } else if (warp >= 2) {
-    // ------------------------------------------------ softmax + epilogue; TMEM lane quarter = warp % 4
-    const int qq = warp & 3;
-    const int r = qq * 32 + lane;  // query row inside the tile
+    // ------------------------------------------------ softmax + epilogue
+    // TMEM lane quarter = warp % 4; the two warps of a quarter split the 64 key columns (and the 64 output channels)
+    const int qq = warp & 3, ch = (warp - 2) >> 2;  // ch = column half 0/1
+    const int r = qq * 32 + lane;                    // query row inside the tile
     const uint32_t t_lane = tmem_base + ((uint32_t)(qq * 32) << 16);
     const float c1 = 0.125f * 1.4426950408889634f, c2 = 8.0f * 1.4426950408889634f;
     uint32_t g = 0, it = 0;
@@ -160,14 +162,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         const uint32_t ph = (gg >> 1) & 1;
         mbar_wait(&s_full[s], ph);
         tc_fence_after();
-        uint32_t a0[32], a1[32];
-        tmem_ld32(t_lane + s * KB, a0);
-        tmem_ld32(t_lane + s * KB + 32, a1);
+        uint32_t a0[32];
+        tmem_ld32(t_lane + s * KB + ch * 32, a0);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_empty[s]);
-        uint32_t pk[32];
+        uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           float p0 = ex2(fmaf(__uint_as_float(a0[2 * i]), c1, -c2)), p1 = ex2(fmaf(__uint_as_float(a0[2 * i + 1]), c1, -c2));
@@ -176,38 +177,34 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
           rowsum += back.x + back.y;
           pk[i] = *reinterpret_cast<uint32_t*>(&b);
         }
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float p0 = ex2(fmaf(__uint_as_float(a1[2 * i]), c1, -c2)), p1 = ex2(fmaf(__uint_as_float(a1[2 * i + 1]), c1, -c2));
-          __nv_bfloat162 b = __floats2bfloat162_rn(p0, p1);
-          float2 back = __bfloat1622float2(b);
-          rowsum += back.x + back.y;
-          pk[16 + i] = *reinterpret_cast<uint32_t*>(&b);
-        }
         mbar_wait(&p_empty[s], ph ^ 1);
-        // row r of the [128 x 64] bf16 K-major SWIZZLE_128B tile: 16-byte chunk c lives at c ^ (r % 8)
+        // row r of the [128 x 64] bf16 K-major SWIZZLE_128B tile: 16-byte chunk c lives at c ^ (r % 8); this warp owns chunks 4ch..4ch+3
         uint8_t* prow = sP + s * P_BYTES + (r >> 3) * 1024 + (r & 7) * 128;
 #pragma unroll
-        for (int c = 0; c < 8; ++c)
-          *reinterpret_cast<uint4*>(prow + ((c ^ (r & 7)) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+        for (int c = 0; c < 4; ++c)
+          *reinterpret_cast<uint4*>(prow + (((ch * 4 + c) ^ (r & 7)) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[s]);
       }
       g += nkb;
+      // combine the two column halves' row sums (double-buffered by item parity; 256 softmax threads)
+      float* rs = sRS + (it & 1) * 2 * QT;
+      rs[ch * QT + r] = rowsum;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float total = rs[r] + rs[QT + r];
       mbar_wait(o_full, it & 1);
       tc_fence_after();
-      uint32_t o0[32], o1[32];
-      tmem_ld32(t_lane + 128, o0);
-      tmem_ld32(t_lane + 160, o1);
+      uint32_t o0[32];
+      tmem_ld32(t_lane + 128 + ch * 32, o0);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(o_empty);
       if (q0 + r < tokens) {
-        const float inv = 1.0f / rowsum;
-        if (lse) lse[(size_t)(row_base + q0 + r) * heads + h] = 8.0f + logf(rowsum);
-        bf16* dst = o + (size_t)(row_base + q0 + r) * D + h * HD;
+        const float inv = 1.0f / total;
+        if (lse && ch == 0) lse[(size_t)(row_base + q0 + r) * heads + h] = 8.0f + logf(total);
+        bf16* dst = o + (size_t)(row_base + q0 + r) * D + h * HD + ch * 32;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint4 u;
@@ -216,15 +213,6 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
           u.z = pack_bf16(__uint_as_float(o0[8 * c + 4]) * inv, __uint_as_float(o0[8 * c + 5]) * inv);
           u.w = pack_bf16(__uint_as_float(o0[8 * c + 6]) * inv, __uint_as_float(o0[8 * c + 7]) * inv);
           *reinterpret_cast<uint4*>(dst + 8 * c) = u;
-        }
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint4 u;
-          u.x = pack_bf16(__uint_as_float(o1[8 * c]) * inv, __uint_as_float(o1[8 * c + 1]) * inv);
-          u.y = pack_bf16(__uint_as_float(o1[8 * c + 2]) * inv, __uint_as_float(o1[8 * c + 3]) * inv);
-          u.z = pack_bf16(__uint_as_float(o1[8 * c + 4]) * inv, __uint_as_float(o1[8 * c + 5]) * inv);
-          u.w = pack_bf16(__uint_as_float(o1[8 * c + 6]) * inv, __uint_as_float(o1[8 * c + 7]) * inv);
-          *reinterpret_cast<uint4*>(dst + 32 + 8 * c) = u;
         }
       }
     }
