@@ -20,7 +20,8 @@ constexpr int HD = 64, QT = 128, KB = 64;
 constexpr int Q_BYTES = QT * HD * 2;   // 16 KB
 constexpr int KV_BYTES = KB * HD * 2;  // 8 KB each
 constexpr int P_BYTES = QT * KB * 2;   // 16 KB
-constexpr int SMEM_BYTES = Q_BYTES + 2 * 2 * KV_BYTES + 2 * P_BYTES + 2 * 2 * QT * 4 /*row-sum exchange*/ + 1024 + 256;
+constexpr int NS = 3;  // K/V ring depth (TMA latency ~ 2 us >> one block's compute)
+constexpr int SMEM_BYTES = Q_BYTES + NS * 2 * KV_BYTES + 2 * P_BYTES + 2 * 2 * QT * 4 /*row-sum exchange*/ + 1024 + 256;
 constexpr int NTHREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 softmax (two warps per TMEM lane quarter, 32 key columns each)
 constexpr uint32_t TMEM_COLS = 256;  // S0 [0,64) S1 [64,128) O [128,192)
 
@@ -38,20 +39,20 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   uint8_t* sQ = smem;
   uint8_t* sKV = sQ + Q_BYTES;            // stage s: K at sKV + s*2*KV_BYTES, V right after
-  uint8_t* sP = sKV + 2 * 2 * KV_BYTES;   // 2 buffers
+  uint8_t* sP = sKV + NS * 2 * KV_BYTES;  // 2 buffers
   float* sRS = reinterpret_cast<float*>(sP + 2 * P_BYTES);  // [2 (item parity)][2 (column half)][128 rows]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sRS + 2 * 2 * QT);
   uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;
-  uint64_t* kv_empty = bars + 3;
-  uint64_t* s_full = bars + 5;
-  uint64_t* s_empty = bars + 7;
-  uint64_t* p_full = bars + 9;
-  uint64_t* p_empty = bars + 11;
-  uint64_t* o_full = bars + 13;
-  uint64_t* q_empty = bars + 14;
-  uint64_t* o_empty = bars + 15;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* kv_full = bars + 1;          // [NS]
+  uint64_t* kv_empty = kv_full + NS;     // [NS]
+  uint64_t* s_full = kv_empty + NS;      // [2]
+  uint64_t* s_empty = s_full + 2;
+  uint64_t* p_full = s_empty + 2;
+  uint64_t* p_empty = p_full + 2;
+  uint64_t* o_full = p_empty + 2;
+  uint64_t* q_empty = o_full + 1;
+  uint64_t* o_empty = q_empty + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int D = heads * HD;
@@ -64,9 +65,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     prefetch_tmap(&tm_kv);
     mbar_init(q_full, 1);
     mbar_init(q_empty, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < NS; ++i) {
       mbar_init(&kv_full[i], 1);
       mbar_init(&kv_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
       mbar_init(&s_empty[i], 8);
       mbar_init(&p_full[i], 8);
@@ -92,8 +95,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
       mbar_arrive_expect_tx(q_full, Q_BYTES);
       tma_load_2d(sQ, &tm_q, q_full, h * HD, row_base + qt * QT);
       for (int j = 0; j < nkb; ++j, ++g) {
-        const int s = g & 1;
-        mbar_wait(&kv_empty[s], ((g >> 1) & 1) ^ 1);
+        const int s = g % NS;
+        mbar_wait(&kv_empty[s], ((g / NS) & 1) ^ 1);
         uint8_t* k_dst = sKV + s * 2 * KV_BYTES;
         mbar_arrive_expect_tx(&kv_full[s], 2 * KV_BYTES);
         tma_load_2d(k_dst, &tm_kv, &kv_full[s], D + h * HD, row_base + j * KB);
@@ -106,11 +109,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     constexpr uint32_t idesc_o = make_idesc_bf16(QT, HD, 0, 1);   // O = P V   : V is MN-major (d contiguous)
     const uint32_t q_addr = smem_u32(sQ);
     auto issue_s = [&](uint32_t gg) {
-      const int s = gg & 1;
-      mbar_wait(&kv_full[s], (gg >> 1) & 1);
+      const int s = gg & 1, kvs = gg % NS;
+      mbar_wait(&kv_full[kvs], (gg / NS) & 1);
       mbar_wait(&s_empty[s], ((gg >> 1) & 1) ^ 1);
       tc_fence_after();
-      const uint32_t k_addr = smem_u32(sKV + s * 2 * KV_BYTES);
+      const uint32_t k_addr = smem_u32(sKV + kvs * 2 * KV_BYTES);
 #pragma unroll
       for (int k = 0; k < HD / 16; ++k)
         umma_ss(tmem_base + s * KB, make_smem_desc(q_addr + k * 32, 16, 1024), make_smem_desc(k_addr + k * 32, 16, 1024), idesc_s,
@@ -133,12 +136,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         mbar_wait(&p_full[s], (gg >> 1) & 1);
         tc_fence_after();
         const uint32_t p_addr = smem_u32(sP + s * P_BYTES);
-        const uint32_t v_addr = smem_u32(sKV + s * 2 * KV_BYTES + KV_BYTES);
+        const int kvs = gg % NS;
+        const uint32_t v_addr = smem_u32(sKV + kvs * 2 * KV_BYTES + KV_BYTES);
 #pragma unroll
         for (int k = 0; k < KB / 16; ++k)  // 16 keys per MMA: P advances 32 B along K, V advances two 8-row groups
           umma_ss(tmem_base + 128, make_smem_desc(p_addr + k * 32, 16, 1024), make_smem_desc(v_addr + k * 2048, 1024, 1024), idesc_o,
                   (j | k) != 0);
-        umma_commit(&kv_empty[s]);
+        umma_commit(&kv_empty[kvs]);
         umma_commit(&p_empty[s]);
       }
       umma_commit(o_full);
