@@ -207,6 +207,13 @@ int mapdit_embed_rows_bwd(const int64_t* idx, const uint8_t* drop_mask, int64_t 
                           const float* g, float* dtable, int n, int d, float eps, void* stream);
 int mapdit_patchify(const float* x, float* P, int n_samples, int channels, int input_size, int patch, void* stream);
 int mapdit_axpby(const float* x, float* y, float a, int accumulate, int64_t n, void* stream);
+/* rotation modulation (UNPINNED: no reference code): h = R(rot[n,:] * gain) x (* scale), pairs (2i, 2i+1);
+ * backward: R (+)= R^T (dh*scale), dscale, drot, dgain partials (mapdit_modulate_bwd_partials() of them) */
+int mapdit_rotmod_fwd(const void* x, void* h, const float* rot, const float* scale, const float* gain, int64_t ldmod, int m,
+                      int d, int tokens, int dtype, void* stream);
+int mapdit_rotmod_bwd(const void* dh, const void* x, void* R, const float* rot, const float* scale, const float* gain,
+                      float* drot, float* dscale, float* dg_partial, int64_t ldmod, int n_samples, int d, int tokens,
+                      int accumulate, int dtype, void* stream);
 /* x_embedder weight gradient dW[D, p*p*C+1] = scale * R[M, D]^T · (patchify(x)|1), patches gathered on the fly (src/dit.py:81-84) */
 int mapdit_patch_embed_wgrad(const void* R, const float* x, float* dW, int n_samples, int channels, int input_size,
                              int patch, int d, float scale, int dtype, void* stream);

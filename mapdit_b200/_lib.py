@@ -50,6 +50,8 @@ SIGNATURES = {
     "mapdit_embed_rows_bwd": [_p, _p, _i64, _p, _p, _p, _i, _i, _f, _p],
     "mapdit_patchify": [_p, _p, _i, _i, _i, _i, _p],
     "mapdit_axpby": [_p, _p, _f, _i, _i64, _p],
+    "mapdit_rotmod_fwd": [_p, _p, _p, _p, _p, _i64, _i, _i, _i, _i, _p],
+    "mapdit_rotmod_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _i, _i, _i, _p],
     "mapdit_patch_embed_wgrad": [_p, _p, _p, _i, _i, _i, _i, _i, _f, _i, _p],
     "mapdit_patch_embed": [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _i, _i, _i, _i, _p],
     "mapdit_fourier": [_p, _p, _p, _p, _i, _i, _p],

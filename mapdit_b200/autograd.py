@@ -60,7 +60,7 @@ class Trainer:
         f = dict(device=dev, dtype=torch.float32)
         ppc2 = m.final_layer.linear.weight.shape[0]
         K1 = m.x_embedder.weight.shape[1]
-        W = L * 6 * D + 2 * D
+        W = L * self.e.layout["width"] + 2 * D
         B = dict(
             e=torch.empty(N, 256, **f), t1=torch.empty(N, D, **f), t1s=torch.empty(N, D, **f), temb=torch.empty(N, D, **f),
             yemb=torch.empty(N, D, **f), c=torch.empty(N, D, **f), cs=torch.empty(N, D, **f),
@@ -125,40 +125,71 @@ class Trainer:
         ops.mp_scale_from_lin(B["lsg"], f.sigma_scale.reference.data, B["ssg"])
         mods = B["mods"]
 
-        def mod(i, j):
-            return mods[:, i * 6 * D + j * D:]
+        lay = e.layout
+        adaln = m.modulation == "adaln"
+        fbase = L * lay["width"]
 
-        ops.patch_embed(x, W.wx, m.pos_embed, B["xin"][0], B["h1"][0], mod(0, 0), mod(0, 1), blk[0].gain_msa.data, ld, m.patch_size)
+        def mod(i, name):
+            return mods[:, i * lay["width"] + lay[name]:]
+
+        def modulate_block(i, branch, src, dst):
+            gain = (blk[i].gain_msa if branch == "a" else blk[i].gain_mlp).data
+            if adaln:
+                ops.modulate(src, dst, mod(i, "shift_" + branch), mod(i, "scale_" + branch), gain, ld, T)
+            else:
+                sc = mod(i, "scale_" + branch) if ("scale_" + branch) in lay else None
+                ops.rotmod(src, dst, mod(i, "rot_" + branch), sc, gain, ld, T)
+
+        def modulate_next(i, src, dst):
+            if i + 1 < L:
+                modulate_block(i + 1, "a", src, dst)
+            else:
+                ops.modulate(src, dst, mods[:, fbase:], mods[:, fbase + D:], f.gain_mod.data, ld, T)
+
+        fused = bf and adaln
+        if bf and hd != 64:
+            raise NotImplementedError("bf16 training needs head_dim 64 (DiT-XL uses 72): use compute_dtype='fp32'")
+        if adaln:
+            ops.patch_embed(x, W.wx, m.pos_embed, B["xin"][0], B["h1"][0], mod(0, "shift_a"), mod(0, "scale_a"), blk[0].gain_msa.data,
+                            ld, m.patch_size)
+        else:
+            ops.patch_embed(x, W.wx, m.pos_embed, B["xin"][0], None, None, None, None, ld, m.patch_size)
+            modulate_block(0, "a", B["xin"][0], B["h1"][0])
         for i in range(L):
             xin, h1, qkv, o, a, xmid, h2, z, u, b = (B[k][i] for k in ("xin", "h1", "qkv", "o", "a", "xmid", "h2", "z", "u", "b"))
             xnext, hnext = B["xin"][i + 1], B["h1"][i + 1]
-            if i + 1 < L:
-                nsh, nsc, ngn = mod(i + 1, 0), mod(i + 1, 1), blk[i + 1].gain_msa.data
-            else:
-                nsh, nsc, ngn = mods[:, L * 6 * D:], mods[:, L * 6 * D + D:], f.gain_mod.data
-            if bf:
-                ops.gemm_bf16(h1, W.wqkv[i], qkv, epilogue=_lib.EPI_QKNORM, tokens=T, head_dim=hd, qk_cols=2 * D,
-                              aux=B["sc"][i] if hd == 64 else None)
-                if hd != 64:
-                    raise NotImplementedError("bf16 training needs head_dim 64 (DiT-XL uses 72): use compute_dtype='fp32'")
+            if fused:
+                if i + 1 < L:
+                    nsh, nsc, ngn = mod(i + 1, "shift_a"), mod(i + 1, "scale_a"), blk[i + 1].gain_msa.data
+                else:
+                    nsh, nsc, ngn = mods[:, fbase:], mods[:, fbase + D:], f.gain_mod.data
+                ops.gemm_bf16(h1, W.wqkv[i], qkv, epilogue=_lib.EPI_QKNORM, tokens=T, head_dim=hd, qk_cols=2 * D, aux=B["sc"][i])
                 ops.cos_attn(qkv, o, N, T, H, hd, lse=B["lse"][i])
-                ops.gemm_bf16(o, W.wo[i], xmid, epilogue=_lib.EPI_RESID_MOD, out2=h2, resid=xin, gate=mod(i, 2), shift=mod(i, 3),
-                              scale=mod(i, 4), gain=blk[i].gain_mlp.data, ldmod=ld, tokens=T, aux=a)
+                ops.gemm_bf16(o, W.wo[i], xmid, epilogue=_lib.EPI_RESID_MOD, out2=h2, resid=xin, gate=mod(i, "gate_a"),
+                              shift=mod(i, "shift_m"), scale=mod(i, "scale_m"), gain=blk[i].gain_mlp.data, ldmod=ld, tokens=T, aux=a)
                 ops.gemm_bf16(h2, W.w1[i], u, epilogue=_lib.EPI_MPSILU, out2=z)
-                ops.gemm_bf16(u, W.w2[i], xnext, epilogue=_lib.EPI_RESID_MOD, out2=hnext, resid=xmid, gate=mod(i, 5), shift=nsh,
+                ops.gemm_bf16(u, W.w2[i], xnext, epilogue=_lib.EPI_RESID_MOD, out2=hnext, resid=xmid, gate=mod(i, "gate_m"), shift=nsh,
                               scale=nsc, gain=ngn, ldmod=ld, tokens=T, aux=b)
+            elif bf:
+                ops.gemm_bf16(h1, W.wqkv[i], qkv, epilogue=_lib.EPI_QKNORM, tokens=T, head_dim=hd, qk_cols=2 * D, aux=B["sc"][i])
+                ops.cos_attn(qkv, o, N, T, H, hd, lse=B["lse"][i])
+                ops.gemm_bf16(o, W.wo[i], xmid, epilogue=_lib.EPI_RESID, resid=xin, gate=mod(i, "gate_a"), ldmod=ld, tokens=T, aux=a)
+                modulate_block(i, "m", xmid, h2)
+                ops.gemm_bf16(h2, W.w1[i], u, epilogue=_lib.EPI_MPSILU, out2=z)
+                ops.gemm_bf16(u, W.w2[i], xnext, epilogue=_lib.EPI_RESID, resid=xmid, gate=mod(i, "gate_m"), ldmod=ld, tokens=T, aux=b)
+                modulate_next(i, xnext, hnext)
             else:
                 ops.gemm_f32(h1, W.wqkv[i], out=qkv)
                 ops.qk_normalize_save(qkv, B["sc"][i], D, hd)
                 ops.cos_attn(qkv, o, N, T, H, hd, lse=B["lse"][i])
                 ops.gemm_f32(o, W.wo[i], out=a)
-                ops.resid(xin, a, xmid, mod(i, 2), ld, T)
-                ops.modulate(xmid, h2, mod(i, 3), mod(i, 4), blk[i].gain_mlp.data, ld, T)
+                ops.resid(xin, a, xmid, mod(i, "gate_a"), ld, T)
+                modulate_block(i, "m", xmid, h2)
                 ops.gemm_f32(h2, W.w1[i], out=z)
                 ops.mp_silu(z, u)
                 ops.gemm_f32(u, W.w2[i], out=b)
-                ops.resid(xmid, b, xnext, mod(i, 5), ld, T)
-                ops.modulate(xnext, hnext, nsh, nsc, ngn, ld, T)
+                ops.resid(xmid, b, xnext, mod(i, "gate_m"), ld, T)
+                modulate_next(i, xnext, hnext)
         hF = B["h1"][L]
         if bf:
             ops.gemm_bf16(hF, W.wfl, B["lin"])
@@ -217,8 +248,25 @@ class Trainer:
         npart = ops.modulate_bwd_partials(N, D)
         grads = {}
 
-        def mod(buf, i, j):
-            return buf[:, i * 6 * D + j * D:]
+        lay = e.layout
+        adaln = m.modulation == "adaln"
+        fbase = L * lay["width"]
+
+        def mod(buf, i, name):
+            return buf[:, i * lay["width"] + lay[name]:]
+
+        def modulate_block_bwd(i, branch, dh_, x_, accumulate):
+            """backward of the block-i modulation: R (+)= d/dx, per-sample vector grads into dmods, returns d(gain)"""
+            gp = blk[i].gain_msa if branch == "a" else blk[i].gain_mlp
+            if adaln:
+                ops.modulate_bwd(dh_, x_, R, mod(mods, i, "shift_" + branch), mod(mods, i, "scale_" + branch), gp.data,
+                                 mod(dmods, i, "shift_" + branch), mod(dmods, i, "scale_" + branch), B["dgp"], ld, N, T, accumulate)
+            else:
+                has_sc = ("scale_" + branch) in lay
+                ops.rotmod_bwd(dh_, x_, R, mod(mods, i, "rot_" + branch), mod(mods, i, "scale_" + branch) if has_sc else None, gp.data,
+                               mod(dmods, i, "rot_" + branch), mod(dmods, i, "scale_" + branch) if has_sc else None, B["dgp"], ld, N, T,
+                               accumulate)
+            grads[id(gp)] = self._scalar_from_partials(B, npart, gp)
 
         R, dY, dh, dqkv, dU = B["R"], B["dY"], B["dh"], B["dqkv"], B["dU"]
         # ---- final layer (src/blocks/final_layer.py:53-59)
@@ -239,15 +287,15 @@ class Trainer:
         hF, xF = B["h1"][L], B["xin"][L]
         self._wgrad(B["dlin"], hF, f.linear.weight, bf, B, grads)
         self._dgrad(B["dlin"], W.wfl, getattr(W, "wfl_t", None), dh, bf)
-        ops.modulate_bwd(dh, xF, R, mods[:, L * 6 * D:], mods[:, L * 6 * D + D:], f.gain_mod.data, dmods[:, L * 6 * D:],
-                         dmods[:, L * 6 * D + D:], B["dgp"], ld, N, T, False)
+        ops.modulate_bwd(dh, xF, R, mods[:, fbase:], mods[:, fbase + D:], f.gain_mod.data, dmods[:, fbase:],
+                         dmods[:, fbase + D:], B["dgp"], ld, N, T, False)
         grads[id(f.gain_mod)] = self._scalar_from_partials(B, npart, f.gain_mod)
         # ---- blocks, last to first
         for i in range(L - 1, -1, -1):
             xin, h1, qkv, o, a, xmid, h2, z, u, b = (B[k][i] for k in ("xin", "h1", "qkv", "o", "a", "xmid", "h2", "z", "u", "b"))
             wt = (lambda name: getattr(W, name)[i]) if bf else (lambda name: None)
             # MLP branch
-            ops.resid_bwd(R, b, dY, mod(mods, i, 5), mod(dmods, i, 5), ld, N, T)
+            ops.resid_bwd(R, b, dY, mod(mods, i, "gate_m"), mod(dmods, i, "gate_m"), ld, N, T)
             self._wgrad(dY, u, blk[i].mlp.net[2].weight, bf, B, grads)
             if bf:  # dgrad of fc2 with MPSiLU's backward fused into the epilogue
                 ops.gemm_bf16(dY, W.w2_t[i], dU, epilogue=_lib.EPI_SILU_BWD, resid=z)
@@ -256,20 +304,16 @@ class Trainer:
                 ops.mp_silu_bwd(dU, z, dU)
             self._wgrad(dU, h2, blk[i].mlp.net[0].weight, bf, B, grads)
             self._dgrad(dU, W.w1[i], wt("w1_t"), dh, bf)
-            ops.modulate_bwd(dh, xmid, R, mod(mods, i, 3), mod(mods, i, 4), blk[i].gain_mlp.data, mod(dmods, i, 3), mod(dmods, i, 4),
-                             B["dgp"], ld, N, T, True)
-            grads[id(blk[i].gain_mlp)] = self._scalar_from_partials(B, npart, blk[i].gain_mlp)
+            modulate_block_bwd(i, "m", dh, xmid, True)
             # attention branch
-            ops.resid_bwd(R, a, dY, mod(mods, i, 2), mod(dmods, i, 2), ld, N, T)
+            ops.resid_bwd(R, a, dY, mod(mods, i, "gate_a"), mod(dmods, i, "gate_a"), ld, N, T)
             self._wgrad(dY, o, blk[i].attn.out_proj.weight, bf, B, grads)
             self._dgrad(dY, W.wo[i], wt("wo_t"), dh, bf)
             ops.cos_attn_bwd(qkv, o, dh, B["lse"][i], dqkv, B["delta"], N, T, H, hd)
             ops.qk_norm_bwd(dqkv, qkv, B["sc"][i], D, hd)
             self._wgrad(dqkv, h1, blk[i].attn.qkv_proj.weight, bf, B, grads)
             self._dgrad(dqkv, W.wqkv[i], wt("wqkv_t"), dh, bf)
-            ops.modulate_bwd(dh, xin, R, mod(mods, i, 0), mod(mods, i, 1), blk[i].gain_msa.data, mod(dmods, i, 0), mod(dmods, i, 1),
-                             B["dgp"], ld, N, T, True)
-            grads[id(blk[i].gain_msa)] = self._scalar_from_partials(B, npart, blk[i].gain_msa)
+            modulate_block_bwd(i, "a", dh, xin, True)
             if self.grad_hook is not None:
                 self.grad_hook([(p, grads[id(p)]) for p in blk[i].parameters() if id(p) in grads])
         # ---- patch embed (src/dit.py:81-84): x0 = (lin + pos)/2/sqrt(.5) -> d lin = R * 0.5/sqrt(.5)
@@ -292,11 +336,11 @@ class Trainer:
         for i in range(L):
             p = blk[i].modulation[1].weight
             g = self._gbuf(p)
-            ops.weight_norm_bwd(p.data, dWm[i * 6 * D:(i + 1) * 6 * D], g)
+            ops.weight_norm_bwd(p.data, dWm[i * lay["width"]:(i + 1) * lay["width"]], g)
             grads[id(p)] = g
         p = f.modulation[1].weight
         g = self._gbuf(p)
-        ops.weight_norm_bwd(p.data, dWm[L * 6 * D:], g)
+        ops.weight_norm_bwd(p.data, dWm[fbase:], g)
         grads[id(p)] = g
         # ---- conditioning path (src/dit.py:86-88)
         ops.cond_combine_bwd(B["c"], B["dc"], B["dcs"], B["dab"])

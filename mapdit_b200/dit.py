@@ -14,6 +14,19 @@ import torch.nn as nn
 
 from .engine import Engine
 
+def mod_layout(modulation, D):
+    """column offsets of one block's modulation vector (fp32 [N, width]); a = attention branch, m = MLP branch"""
+    h = D // 2
+    if modulation == "adaln":
+        return dict(width=6 * D, shift_a=0, scale_a=D, gate_a=2 * D, shift_m=3 * D, scale_m=4 * D, gate_m=5 * D)
+    if modulation == "rotation_scaling":
+        return dict(width=5 * D, rot_a=0, scale_a=h, gate_a=h + D, rot_m=h + 2 * D, scale_m=2 * h + 2 * D, gate_m=2 * h + 3 * D)
+    if modulation == "rotation":
+        return dict(width=3 * D, rot_a=0, gate_a=h, rot_m=h + D, gate_m=2 * h + D)
+    raise ValueError(modulation)
+
+
+MOD_LAYOUTS = ("adaln", "rotation_scaling", "rotation")
 MAP_FLAGS = ("use_cosine_attention", "use_weight_normalization", "use_forced_weight_normalization", "use_mp_residual",
              "use_mp_silu", "use_no_layernorm", "use_mp_pos_enc", "use_mp_embedding")
 
@@ -74,11 +87,15 @@ class Attention(nn.Module):
 class DiTBlock(nn.Module):
     """src/blocks/dit_block.py:11-29"""
 
-    def __init__(self, hidden_size, num_heads, mlp_ratio=4.0):
+    def __init__(self, hidden_size, num_heads, mlp_ratio=4.0, modulation="adaln"):
         super().__init__()
         self.attn = Attention(hidden_size, num_heads)
         self.mlp = MLP(hidden_size, hidden_size, mlp_ratio=mlp_ratio)
-        self.modulation = nn.Sequential(MPSiLU(), MPLinearChunk(hidden_size, hidden_size, 6))
+        if modulation == "adaln":      # shift, scale, gate x 2 (src/blocks/dit_block.py:24-27)
+            self.modulation = nn.Sequential(MPSiLU(), MPLinearChunk(hidden_size, hidden_size, 6))
+        else:                          # rotation (D/2) [+ scale (D)] + gate (D), x 2 -- UNPINNED (SURVEY.md §A.8)
+            width = {"rotation_scaling": 5 * hidden_size, "rotation": 3 * hidden_size}[modulation]
+            self.modulation = nn.Sequential(MPSiLU(), MPLinearChunk(hidden_size, width, 1))
         self.gain_msa = nn.Parameter(torch.tensor(0.0))
         self.gain_mlp = nn.Parameter(torch.tensor(0.0))
 
@@ -165,8 +182,9 @@ class DiT(nn.Module):
                 raise NotImplementedError(
                     f"{k}=False: the reference snapshot hard-codes every MaP switch on and ships no 'off' branch "
                     "(SURVEY.md §0.1); only the pinned behaviour has CUDA kernels in this round")
-        if modulation != "adaln":
-            raise NotImplementedError("rotation modulation has no reference code (SURVEY.md §A.8); not built in this round")
+        if modulation not in MOD_LAYOUTS:
+            raise ValueError(f"modulation must be one of {sorted(MOD_LAYOUTS)}")
+        self.modulation = modulation
         if not learn_sigma:
             raise NotImplementedError("learn_sigma=False raises TypeError in the reference (src/blocks/final_layer.py:60-61)")
         assert compute_dtype in ("bf16", "fp32")
@@ -185,7 +203,7 @@ class DiT(nn.Module):
         self.t_embedder = TimestepEmbedder(hidden_size)
         self.y_embedder = LabelEmbedder(num_classes, hidden_size, class_dropout_prob)
         self.register_buffer("pos_embed", sincos_pos_embed(hidden_size, input_size // patch_size))
-        self.blocks = nn.ModuleList([DiTBlock(hidden_size, num_heads, mlp_ratio=mlp_ratio) for _ in range(depth)])
+        self.blocks = nn.ModuleList([DiTBlock(hidden_size, num_heads, mlp_ratio=mlp_ratio, modulation=modulation) for _ in range(depth)])
         self.final_layer = FinalLayer(hidden_size, patch_size, self.out_channels)
         self._engine = None
 

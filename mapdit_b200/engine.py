@@ -46,6 +46,11 @@ class Engine:
         self._dirty = True
 
     @property
+    def layout(self):
+        from .dit import mod_layout
+        return mod_layout(self.m.modulation, self.m.hidden_size)
+
+    @property
     def trainer(self):
         if getattr(self, "_trainer", None) is None:
             from .autograd import Trainer
@@ -73,8 +78,8 @@ class Engine:
             W.wt2 = torch.empty(D, D, **f32)
             W.wmu = torch.empty(8, D, **f32)
             W.wsg = torch.empty(8, D, **f32)
-            W.modw = 6 * D
-            W.mod_total = L * 6 * D + 2 * D
+            W.modw = self.layout["width"]
+            W.mod_total = L * W.modw + 2 * D
             W.wmod = torch.empty(W.mod_total, D, **wd)
             Hm = m.blocks[0].mlp.hidden_dim
             W.wqkv = [torch.empty(3 * D, D, **wd) for _ in range(L)]
@@ -143,7 +148,7 @@ class Engine:
             e=torch.empty(N, 256, **f), t1=torch.empty(N, D, **f), t1s=torch.empty(N, D, **f), temb=torch.empty(N, D, **f),
             yemb=torch.empty(N, D, **f), c=torch.empty(N, D, **f), cs=torch.empty(N, D, **f),
             cs16=torch.empty(N, D, device=dev, dtype=torch.bfloat16),
-            mods=torch.empty(N, m.depth * 6 * D + 2 * D, **f), smu=torch.empty(N, **f), ssg=torch.empty(N, **f),
+            mods=torch.empty(N, m.depth * self.layout["width"] + 2 * D, **f), smu=torch.empty(N, **f), ssg=torch.empty(N, **f),
         )
         if mode == "fp32":
             ws["tmp"] = torch.empty(M, D, **a)
@@ -196,37 +201,68 @@ class Engine:
         ops.mp_scale(ws["c"], W.wsg, f.sigma_scale.reference.data, ws["ssg"])
 
         mods = ws["mods"]
+        lay = self.layout
+        adaln = m.modulation == "adaln"
+        fbase = L * lay["width"]  # final layer: [shift | scale]
 
-        def mod(i, j):  # column slice j of block i's modulation output
-            return mods[:, i * 6 * D + j * D:]
+        def mod(i, name):  # column slice `name` of block i's modulation output
+            return mods[:, i * lay["width"] + lay[name]:]
+
+        def modulate_block(i, branch, src, dst):
+            """h = block-i modulation of the residual stream for branch 'a' (attention) / 'm' (MLP), standalone kernel"""
+            gain = (blk[i].gain_msa if branch == "a" else blk[i].gain_mlp).data
+            if adaln:
+                ops.modulate(src, dst, mod(i, "shift_" + branch), mod(i, "scale_" + branch), gain, ld, T)
+            else:
+                sc = mod(i, "scale_" + branch) if ("scale_" + branch) in lay else None
+                ops.rotmod(src, dst, mod(i, "rot_" + branch), sc, gain, ld, T)
+
+        def modulate_next(i, src, dst):
+            if i + 1 < L:
+                modulate_block(i + 1, "a", src, dst)
+            else:
+                ops.modulate(src, dst, mods[:, fbase:], mods[:, fbase + D:], f.gain_mod.data, ld, T)
 
         blk = m.blocks
+        fused = bf and adaln  # modulate fused into the residual GEMM epilogues
         # ---- patch embed + first modulate (src/dit.py:81-84)
-        ops.patch_embed(x, W.wx, m.pos_embed, ws["x"], ws["h"], mod(0, 0), mod(0, 1), blk[0].gain_msa.data, ld, m.patch_size)
         X, Hb = ws["x"], ws["h"]
+        if adaln:
+            ops.patch_embed(x, W.wx, m.pos_embed, X, Hb, mod(0, "shift_a"), mod(0, "scale_a"), blk[0].gain_msa.data, ld, m.patch_size)
+        else:
+            ops.patch_embed(x, W.wx, m.pos_embed, X, None, None, None, None, ld, m.patch_size)
+            modulate_block(0, "a", X, Hb)
         for i in range(L):
-            nxt_shift, nxt_scale, nxt_gain = ((mod(i + 1, 0), mod(i + 1, 1), blk[i + 1].gain_msa.data) if i + 1 < L else
-                                              (mods[:, L * 6 * D:], mods[:, L * 6 * D + D:], f.gain_mod.data))
-            if bf:
+            if fused:
+                nxt_shift, nxt_scale, nxt_gain = ((mod(i + 1, "shift_a"), mod(i + 1, "scale_a"), blk[i + 1].gain_msa.data) if i + 1 < L
+                                                  else (mods[:, fbase:], mods[:, fbase + D:], f.gain_mod.data))
                 ops.gemm_bf16(Hb, W.wqkv[i], ws["qkv"], epilogue=_lib.EPI_QKNORM, tokens=T, head_dim=hd, qk_cols=2 * D)
                 ops.cos_attn(ws["qkv"], ws["o"], N, T, H, hd)
-                ops.gemm_bf16(ws["o"], W.wo[i], X, epilogue=_lib.EPI_RESID_MOD, out2=Hb, resid=X, gate=mod(i, 2),
-                              shift=mod(i, 3), scale=mod(i, 4), gain=blk[i].gain_mlp.data, ldmod=ld, tokens=T)
+                ops.gemm_bf16(ws["o"], W.wo[i], X, epilogue=_lib.EPI_RESID_MOD, out2=Hb, resid=X, gate=mod(i, "gate_a"),
+                              shift=mod(i, "shift_m"), scale=mod(i, "scale_m"), gain=blk[i].gain_mlp.data, ldmod=ld, tokens=T)
                 ops.gemm_bf16(Hb, W.w1[i], ws["u"], epilogue=_lib.EPI_MPSILU)
-                ops.gemm_bf16(ws["u"], W.w2[i], X, epilogue=_lib.EPI_RESID_MOD, out2=Hb, resid=X, gate=mod(i, 5),
+                ops.gemm_bf16(ws["u"], W.w2[i], X, epilogue=_lib.EPI_RESID_MOD, out2=Hb, resid=X, gate=mod(i, "gate_m"),
                               shift=nxt_shift, scale=nxt_scale, gain=nxt_gain, ldmod=ld, tokens=T)
+            elif bf:  # rotation modulation: residual fused into the GEMM, rotation as a standalone kernel
+                ops.gemm_bf16(Hb, W.wqkv[i], ws["qkv"], epilogue=_lib.EPI_QKNORM, tokens=T, head_dim=hd, qk_cols=2 * D)
+                ops.cos_attn(ws["qkv"], ws["o"], N, T, H, hd)
+                ops.gemm_bf16(ws["o"], W.wo[i], X, epilogue=_lib.EPI_RESID, resid=X, gate=mod(i, "gate_a"), ldmod=ld, tokens=T)
+                modulate_block(i, "m", X, Hb)
+                ops.gemm_bf16(Hb, W.w1[i], ws["u"], epilogue=_lib.EPI_MPSILU)
+                ops.gemm_bf16(ws["u"], W.w2[i], X, epilogue=_lib.EPI_RESID, resid=X, gate=mod(i, "gate_m"), ldmod=ld, tokens=T)
+                modulate_next(i, X, Hb)
             else:
                 ops.gemm_f32(Hb, W.wqkv[i], out=ws["qkv"])
                 ops.qk_normalize(ws["qkv"], D, hd)
                 ops.cos_attn(ws["qkv"], ws["o"], N, T, H, hd)
                 ops.gemm_f32(ws["o"], W.wo[i], out=ws["tmp"])
-                ops.resid(X, ws["tmp"], X, mod(i, 2), ld, T)
-                ops.modulate(X, Hb, mod(i, 3), mod(i, 4), blk[i].gain_mlp.data, ld, T)
+                ops.resid(X, ws["tmp"], X, mod(i, "gate_a"), ld, T)
+                modulate_block(i, "m", X, Hb)
                 ops.gemm_f32(Hb, W.w1[i], out=ws["u"])
                 ops.mp_silu(ws["u"], ws["u"])
                 ops.gemm_f32(ws["u"], W.w2[i], out=ws["tmp"])
-                ops.resid(X, ws["tmp"], X, mod(i, 5), ld, T)
-                ops.modulate(X, Hb, nxt_shift, nxt_scale, nxt_gain, ld, T)
+                ops.resid(X, ws["tmp"], X, mod(i, "gate_m"), ld, T)
+                modulate_next(i, X, Hb)
         # ---- final layer (src/blocks/final_layer.py:53-59, src/dit.py:95-100)
         if bf:
             ops.gemm_bf16(Hb, W.wfl, ws["lin"])

@@ -209,6 +209,17 @@ def patch_embed_wgrad(R, x, dW, patch, scale):
           "patch_embed_wgrad")
 
 
+def rotmod(x, h, rot, scale, gain, ldmod, tokens):
+    m, d = x.shape
+    check(lib().mapdit_rotmod_fwd(_ptr(x), _ptr(h), _ptr(rot), _ptr(scale), _ptr(gain), ldmod, m, d, tokens, _dt(x), _stream()), "rotmod_fwd")
+
+
+def rotmod_bwd(dh, x, R, rot, scale, gain, drot, dscale, dg_partial, ldmod, n_samples, tokens, accumulate):
+    d = dh.shape[1]
+    check(lib().mapdit_rotmod_bwd(_ptr(dh), _ptr(x), _ptr(R), _ptr(rot), _ptr(scale), _ptr(gain), _ptr(drot), _ptr(dscale),
+                                  _ptr(dg_partial), ldmod, n_samples, d, tokens, int(accumulate), _dt(dh), _stream()), "rotmod_bwd")
+
+
 def axpby(x, y, a, accumulate=False):
     check(lib().mapdit_axpby(_ptr(x), _ptr(y), float(a), int(accumulate), x.numel(), _stream()), "axpby")
 

@@ -42,8 +42,10 @@ def test_unbuilt_variants_fail_loudly():
     import mapdit_b200 as M
     with pytest.raises(NotImplementedError):
         M.DIT_MODELS["DiT-XS/8"](in_channels=4, input_size=32, num_classes=10, use_mp_silu=False)
-    with pytest.raises(NotImplementedError):
-        M.DIT_MODELS["DiT-XS/8"](in_channels=4, input_size=32, num_classes=10, modulation="rotation")
+    with pytest.raises(ValueError):
+        M.DIT_MODELS["DiT-XS/8"](in_channels=4, input_size=32, num_classes=10, modulation="bogus")
+    m = M.DIT_MODELS["DiT-XS/8"](in_channels=4, input_size=32, num_classes=10, modulation="rotation_scaling")
+    assert m.blocks[0].modulation[1].weight.shape == (5 * 256, 256)  # 6D -> 5D: the README's "~5.4 % fewer parameters"
     with pytest.raises(TypeError):
         M.DIT_MODELS["DiT-XS/8"](in_channels=4, input_size=32, num_classes=10, bogus=True)
 
