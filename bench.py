@@ -253,7 +253,10 @@ def kernel_roofline(cfg, B, pk):
     dom = res["fc1_gemm_mpsilu"]
     roof = {"bound": "tensor", "kernel": "gemm_tc_kernel<256> (fc1, fused mp_silu epilogue), M=%d N=%d K=%d" % (M, 4 * D, D),
             "achieved": dom["tflops"], "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": round(dom["tflops"] / pk["tf_burst"], 4),
-            "peak_source": f"MEASURED_PEAKS.json bf16 burst ({pk['src']})", "traffic": None, "per_kernel": res}
+            "peak_source": f"MEASURED_PEAKS.json bf16 burst ({pk['src']})",
+            # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the ncu --set full capture
+            # (profiles/r1_gemm_tc2_ncu_summary.md): 105.4 + 350.6 MB; algorithmic bytes (A + B + out) = 503 MB
+            "traffic": 456.0e6, "traffic_unit": "B/launch (ncu, profiles/r1_gemm_tc2_ncu_summary.md)", "per_kernel": res}
     return roof
 
 
