@@ -154,13 +154,17 @@ int mapdit_cfg_combine(float* out, int n_half, int channels, int hw, float cfg_s
  * :870): rows 0 sqrt_alphas_cumprod, 1 sqrt_one_minus_alphas_cumprod, 2 sqrt_recip_alphas_cumprod,
  * 3 sqrt_recipm1_alphas_cumprod, 4 posterior_mean_coef1, 5 posterior_mean_coef2,
  * 6 posterior_log_variance_clipped, 7 log(betas).                                              */
-#define MAPDIT_DIFF_ROWS 8
+#define MAPDIT_DIFF_ROWS 10 /* rows 8, 9: alphas_cumprod, alphas_cumprod_prev (DDIM) */
 
 /* ---- K5: fused diffusion step (diffusion/gaussian_diffusion.py:285-293,320-323,334-339,410-416)
  * t: int64 [N] respaced step index per sample.  sample may alias x.  pred_xstart nullable.     */
 int mapdit_diffusion_step(const float* model_out, const float* x, const float* noise, const int64_t* t,
                           const float* tables, int steps, float* sample, float* pred_xstart, int n_samples,
                           int channels, int hw, int clip_denoised, void* stream);
+/* DDIM step (diffusion/gaussian_diffusion.py:513-560); noise may be null when eta == 0 */
+int mapdit_ddim_step(const float* model_out, const float* x, const float* noise, const int64_t* t, const float* tables,
+                     int steps, float* sample, float* pred_xstart, int n_samples, int channels, int hw, int clip_denoised,
+                     float eta, void* stream);
 /* ---- K6: fused q_sample + loss (diffusion/gaussian_diffusion.py:215-230,682-713,747-783;
  * diffusion/diffusion_utils.py:10-36,62-88).                                                    */
 int mapdit_q_sample(const float* x0, const float* noise, const int64_t* t, const float* tables, int steps,

@@ -61,6 +61,7 @@ SIGNATURES = {
     "mapdit_final_unpatchify": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
     "mapdit_cfg_combine": [_p, _i, _i, _i, _f, _p],
     "mapdit_diffusion_step": [_p, _p, _p, _p, _p, _i, _p, _p, _i, _i, _i, _i, _p],
+    "mapdit_ddim_step": [_p, _p, _p, _p, _p, _i, _p, _p, _i, _i, _i, _i, _f, _p],
     "mapdit_q_sample": [_p, _p, _p, _p, _i, _p, _i, _i, _p],
     "mapdit_loss_fwd_bwd": [_p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
     "mapdit_p_mean_variance": [_p, _p, _p, _p, _i, _p, _p, _p, _p, _i, _i, _i, _i, _p],

@@ -48,6 +48,41 @@ extern "C" int mapdit_diffusion_step(const float* model_out, const float* x, con
   return MAPDIT_OK;
 }
 
+// DDIM step (diffusion/gaussian_diffusion.py:513-560), "next" row N4: x0 from eps (clip), eps re-derived from the clipped x0,
+// sigma = eta sqrt((1-abar_prev)/(1-abar)) sqrt(1-abar/abar_prev), sample = x0 sqrt(abar_prev) + sqrt(1-abar_prev-sigma^2) eps + [t!=0] sigma noise
+__global__ void __launch_bounds__(256) ddim_step_kernel(const float* __restrict__ mo, const float* __restrict__ x,
+                                                        const float* __restrict__ noise, const int64_t* __restrict__ t,
+                                                        const float* __restrict__ tab, int steps, float* __restrict__ sample,
+                                                        float* __restrict__ x0out, int64_t total, int chw, int clip, float eta) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int64_t n = i / chw;
+  int r = (int)(i - n * chw);
+  int ti = (int)t[n];
+  const float srac = tab[2 * steps + ti], srm1 = tab[3 * steps + ti], ab = tab[8 * steps + ti], abp = tab[9 * steps + ti];
+  const float eps_m = mo[n * 2 * chw + r];
+  const float xv = x[i];
+  float x0 = FS(FM(srac, xv), FM(srm1, eps_m));
+  if (clip) x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
+  const float eps = FS(FM(srac, xv), x0) / srm1;
+  const float sigma = FM(FM(eta, sqrtf(FS(1.0f, abp) / FS(1.0f, ab))), sqrtf(FS(1.0f, ab / abp)));
+  const float mean = FA(FM(x0, sqrtf(abp)), FM(sqrtf(FS(FS(1.0f, abp), FM(sigma, sigma))), eps));
+  const float mask = (ti != 0) ? 1.0f : 0.0f;
+  sample[i] = FA(mean, FM(FM(mask, sigma), noise ? noise[i] : 0.0f));
+  if (x0out) x0out[i] = x0;
+}
+extern "C" int mapdit_ddim_step(const float* model_out, const float* x, const float* noise, const int64_t* t, const float* tables,
+                                int steps, float* sample, float* pred_xstart, int n_samples, int channels, int hw, int clip_denoised,
+                                float eta, void* stream) {
+  MAPDIT_REQUIRE(model_out && x && t && tables && sample && n_samples > 0 && steps > 0, "ddim_step: bad args");
+  int chw = channels * hw;
+  int64_t total = (int64_t)n_samples * chw;
+  ddim_step_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(model_out, x, noise, t, tables, steps, sample,
+                                                                                      pred_xstart, total, chw, clip_denoised, eta);
+  MAPDIT_LAUNCH_CHECK("ddim_step");
+  return MAPDIT_OK;
+}
+
 // p_mean_variance as separate tensors (gaussian_diffusion.py:254-332), for callers that want the dict
 __global__ void __launch_bounds__(256) p_mean_variance_kernel(const float* __restrict__ mo, const float* __restrict__ x,
                                                               const int64_t* __restrict__ t, const float* __restrict__ tab, int steps,

@@ -140,7 +140,7 @@ class GaussianDiffusion:
         if tab is None:
             rows = [self.sqrt_alphas_cumprod, self.sqrt_one_minus_alphas_cumprod, self.sqrt_recip_alphas_cumprod,
                     self.sqrt_recipm1_alphas_cumprod, self.posterior_mean_coef1, self.posterior_mean_coef2,
-                    self.posterior_log_variance_clipped, np.log(self.betas)]
+                    self.posterior_log_variance_clipped, np.log(self.betas), self.alphas_cumprod, self.alphas_cumprod_prev]
             tab = th.from_numpy(np.stack(rows)).to(device=device).float().contiguous()
             self._dev_tables[key] = tab
         return tab
@@ -262,12 +262,12 @@ class GaussianDiffusion:
         """index of respaced step i in the model's own time axis (identity here; SpacedDiffusion remaps)"""
         return i
 
-    def _graphed_loop(self, dit, uses_cfg, img, indices, clip_denoised, model_kwargs, want_xstart):
+    def _graphed_loop(self, dit, uses_cfg, img, indices, clip_denoised, model_kwargs, want_xstart, ddim_eta=None):
         y = model_kwargs["y"]
         cfg_scale = float(model_kwargs["cfg_scale"]) if uses_cfg else None
         N = img.shape[0]
         dev = img.device
-        key = (id(dit), N, tuple(img.shape), str(dev), uses_cfg, cfg_scale, bool(clip_denoised), dit.compute_dtype, dit.training)
+        key = (id(dit), N, tuple(img.shape), str(dev), uses_cfg, cfg_scale, bool(clip_denoised), dit.compute_dtype, dit.training, ddim_eta)
         st = self._graphs.get(key)
         tab = self.device_tables(dev)
         with th.no_grad():
@@ -281,7 +281,10 @@ class GaussianDiffusion:
                         mo = dit.forward_with_cfg(st["img"], st["tm"], st["y"], cfg_scale)
                     else:
                         mo = dit.forward(st["img"], st["tm"], st["y"])
-                    ops.diffusion_step(mo, st["img"], st["noise"], st["t"], tab, st["img"], st["x0"], clip_denoised)
+                    if ddim_eta is None:
+                        ops.diffusion_step(mo, st["img"], st["noise"], st["t"], tab, st["img"], st["x0"], clip_denoised)
+                    else:
+                        ops.ddim_step(mo, st["img"], st["noise"], st["t"], tab, st["img"], st["x0"], clip_denoised, ddim_eta)
 
                 st["y"].copy_(y)
                 st["img"].copy_(img)
@@ -339,14 +342,55 @@ class GaussianDiffusion:
         raise NotImplementedError(f"{name} is outside the accelerated hot path (SURVEY.md §2 row 8: never called by the "
                                   "reference scripts); DDIM is a 'next' row (N4)")
 
-    def ddim_sample(self, *a, **k):
-        self._off_path("ddim_sample")
+    def ddim_sample(self, model, x, t, clip_denoised=True, denoised_fn=None, cond_fn=None, model_kwargs=None, eta=0.0):
+        """gaussian_diffusion.py:513-560 -> dict(sample, pred_xstart); one fused kernel per step ("next" row N4)"""
+        self._require_kernels("ddim_sample")
+        if denoised_fn is not None or cond_fn is not None:
+            self._off_path("ddim_sample with denoised_fn / cond_fn")
+        B, C = x.shape[:2]
+        assert t.shape == (B,)
+        model_output, _ = self._call_model(model, x, t, model_kwargs)
+        assert model_output.shape == (B, C * 2, *x.shape[2:])
+        noise = _randn_like(x)
+        xc = x.contiguous().float()
+        sample, x0 = th.empty_like(xc), th.empty_like(xc)
+        ops.ddim_step(model_output.contiguous().float(), xc, noise.contiguous().float(), t.contiguous().long(),
+                      self.device_tables(xc.device), sample, x0, clip_denoised, eta)
+        return {"sample": sample, "pred_xstart": x0}
 
-    def ddim_sample_loop(self, *a, **k):
-        self._off_path("ddim_sample_loop")
+    def ddim_sample_loop(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None, cond_fn=None, model_kwargs=None,
+                         device=None, progress=False, eta=0.0):
+        """gaussian_diffusion.py:600-631"""
+        final = None
+        for sample in self.ddim_sample_loop_progressive(model, shape, noise=noise, clip_denoised=clip_denoised, denoised_fn=denoised_fn,
+                                                        cond_fn=cond_fn, model_kwargs=model_kwargs, device=device, progress=progress,
+                                                        eta=eta, _want_xstart=False):
+            final = sample
+        return final["sample"]
 
-    def ddim_sample_loop_progressive(self, *a, **k):
-        self._off_path("ddim_sample_loop_progressive")
+    def ddim_sample_loop_progressive(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None, cond_fn=None,
+                                     model_kwargs=None, device=None, progress=False, eta=0.0, _want_xstart=True):
+        """gaussian_diffusion.py:633-680; same CUDA-graph step loop as p_sample_loop_progressive with the DDIM update kernel"""
+        self._require_kernels("ddim_sample_loop")
+        if device is None:
+            device = next(model.parameters()).device
+        assert isinstance(shape, (tuple, list))
+        img = noise if noise is not None else th.randn(*shape, device=device)
+        indices = list(range(self.num_timesteps))[::-1]
+        if progress:
+            from tqdm.auto import tqdm
+            indices = tqdm(indices)
+        dit, uses_cfg = _is_dit_callable(model)
+        if dit is not None and denoised_fn is None and cond_fn is None and th.device(device).type == "cuda":
+            yield from self._graphed_loop(dit, uses_cfg, img, indices, clip_denoised, model_kwargs or {}, _want_xstart, ddim_eta=float(eta))
+            return
+        for i in indices:
+            t = th.tensor([i] * shape[0], device=device)
+            with th.no_grad():
+                out = self.ddim_sample(model, img, t, clip_denoised=clip_denoised, denoised_fn=denoised_fn, cond_fn=cond_fn,
+                                       model_kwargs=model_kwargs, eta=eta)
+                yield out
+                img = out["sample"]
 
     def ddim_reverse_sample(self, *a, **k):
         self._off_path("ddim_reverse_sample")

@@ -66,6 +66,9 @@ class SpacedDiffusion(GaussianDiffusion):
     def p_sample(self, model, *args, **kwargs):
         return super().p_sample(self._wrap_model(model), *args, **kwargs)
 
+    def ddim_sample(self, model, *args, **kwargs):
+        return super().ddim_sample(self._wrap_model(model), *args, **kwargs)
+
     def training_losses(self, model, *args, **kwargs):
         return super().training_losses(self._wrap_model(model), *args, **kwargs)
 

@@ -266,6 +266,12 @@ def diffusion_step(model_out, x, noise, t, tables, sample, pred_xstart, clip_den
                                       _ptr(pred_xstart), n, c, h * w, int(clip_denoised), _stream()), "diffusion_step")
 
 
+def ddim_step(model_out, x, noise, t, tables, sample, pred_xstart, clip_denoised, eta):
+    n, c, h, w = x.shape
+    check(lib().mapdit_ddim_step(_ptr(model_out), _ptr(x), _ptr(noise), _ptr(t), _ptr(tables), tables.shape[1], _ptr(sample),
+                                 _ptr(pred_xstart), n, c, h * w, int(clip_denoised), float(eta), _stream()), "ddim_step")
+
+
 def q_sample(x0, noise, t, tables, x_t):
     n = x0.shape[0]
     check(lib().mapdit_q_sample(_ptr(x0), _ptr(noise), _ptr(t), _ptr(tables), tables.shape[1], _ptr(x_t), n, x0[0].numel(), _stream()),

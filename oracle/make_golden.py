@@ -154,6 +154,20 @@ def diffusion_case(tag):
         rec[f"ps_sample_clip{int(clip)}"] = out["sample"].numpy()
         rec[f"ps_x0_clip{int(clip)}"] = out["pred_xstart"].numpy()
     rec["ps_t"] = t50.numpy()
+    # DDIM steps (gaussian_diffusion.py:513-560) on the ddim25 spacing, eta 0 and 0.7
+    d25 = create_diffusion(timestep_respacing="ddim25")
+    t25 = torch.tensor([0, 1, 7, 12, 23, 24])
+    rec["dd_t"] = t25.numpy()
+    for eta in (0.0, 0.7):
+        for clip in (True, False):
+            real = gd.th.randn_like
+            gd.th.randn_like = lambda x: noise
+            try:
+                out = d25.ddim_sample(lambda *a, **k: mo, x0, t25, clip_denoised=clip, eta=eta)
+            finally:
+                gd.th.randn_like = real
+            rec[f"dd_sample_eta{eta}_clip{int(clip)}"] = out["sample"].numpy()
+            rec[f"dd_x0_eta{eta}_clip{int(clip)}"] = out["pred_xstart"].numpy()
     np.savez_compressed(os.path.join(OUT, f"{tag}.npz"), **rec)
     print(tag, "ok")
 

@@ -428,6 +428,8 @@ def make_tables(respacing="", diffusion_steps: int = 1000) -> DiffusionTables:
         "posterior_mean_coef1": betas * np.sqrt(prev) / (1.0 - acp),
         "posterior_mean_coef2": (1.0 - prev) * np.sqrt(alphas) / (1.0 - acp),
         "log_betas": np.log(betas),
+        "alphas_cumprod": acp,
+        "alphas_cumprod_prev": prev,
     }
     return T
 
@@ -464,6 +466,18 @@ def p_sample_step(T: DiffusionTables, model_out, x, t, noise, clip_denoised=True
     mask = (t != 0).float().view(-1, *([1] * (x.ndim - 1)))
     sample = out["mean"] + mask * torch.exp(0.5 * out["log_variance"]) * noise
     return {"sample": sample, "pred_xstart": out["pred_xstart"]}
+
+
+def ddim_step(T: DiffusionTables, model_out, x, t, noise, clip_denoised=True, eta=0.0):
+    """gaussian_diffusion.py:528-560 (no cond_fn)."""
+    out = p_mean_variance(T, model_out, x, t, clip_denoised)
+    eps = (_ext(T.tabs["sqrt_recip_alphas_cumprod"], t, x.ndim) * x - out["pred_xstart"]) / _ext(T.tabs["sqrt_recipm1_alphas_cumprod"], t, x.ndim)
+    ab = _ext(T.tabs["alphas_cumprod"], t, x.ndim)
+    abp = _ext(T.tabs["alphas_cumprod_prev"], t, x.ndim)
+    sigma = eta * torch.sqrt((1 - abp) / (1 - ab)) * torch.sqrt(1 - ab / abp)
+    mean_pred = out["pred_xstart"] * torch.sqrt(abp) + torch.sqrt(1 - abp - sigma ** 2) * eps
+    mask = (t != 0).float().view(-1, *([1] * (x.ndim - 1)))
+    return {"sample": mean_pred + mask * sigma * noise, "pred_xstart": out["pred_xstart"]}
 
 
 def p_sample_loop(T: DiffusionTables, model_fn: Callable, x_T, noises: Sequence[torch.Tensor],

@@ -224,5 +224,17 @@ def test_diffusion_step_and_loss(dev):
             assert rel_l2(out2["sample"].cpu(), g[f"ps_sample_clip{clip}"]) < 1e-6
     finally:
         gd._randn_like = real
+    # DDIM step against the reference's golden output (eta 0 and 0.7, noise injected)
+    d25 = create_diffusion("ddim25")
+    t25 = torch.from_numpy(g["dd_t"]).to(dev)
+    gd._randn_like = lambda x: noise
+    try:
+        for eta in (0.0, 0.7):
+            for clip in (1, 0):
+                out = d25.ddim_sample(lambda *a, **k: mo, x0, t25, clip_denoised=bool(clip), eta=eta)
+                assert rel_l2(out["sample"].cpu(), g[f"dd_sample_eta{eta}_clip{clip}"]) < 2e-6
+                assert rel_l2(out["pred_xstart"].cpu(), g[f"dd_x0_eta{eta}_clip{clip}"]) < 1e-6
+    finally:
+        gd._randn_like = real
     xt = d.q_sample(x0, torch.from_numpy(g["tl_t"]).to(dev), noise=noise)
     assert rel_l2(xt.cpu(), O.q_sample(T, x0.cpu(), torch.from_numpy(g["tl_t"]), noise.cpu())) < 1e-6

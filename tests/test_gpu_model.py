@@ -139,3 +139,35 @@ def test_weight_cache_follows_parameter_updates():
         ref = O.dit_forward({k: v.cpu() for k, v in sd2.items()}, cfg, x.cpu(), t.cpu(), y.cpu())
     assert rel_l2(a, b) > 1e-3
     assert rel_l2(b.cpu(), ref) < FP32_TOL
+
+
+@pytest.mark.parametrize("dtype,tol", [("fp32", 2e-5), ("bf16", 5e-2)])
+def test_ddim_loop_vs_oracle(dtype, tol):
+    """DDIM sampling ("next" row N4) through the CUDA-graph step loop: 5 deterministic steps (eta = 0) and eta = 0.5
+    against the oracle's loop built from its golden-pinned ddim_step."""
+    import mapdit_b200 as M
+    from mapdit_b200.diffusion import gaussian_diffusion as gd
+    m, cfg, sd = build("DiT-XS/8", 17, dtype)
+    g = torch.Generator().manual_seed(8)
+    z = torch.randn(2, 4, 32, 32, generator=g)
+    y = torch.tensor([4, 900])
+    noises = [torch.randn(2, 4, 32, 32, generator=g) for _ in range(5)]
+    d = M.create_diffusion("ddim5")
+    T = O.make_tables("ddim5")
+    tm = torch.tensor(T.timestep_map)
+    for eta in (0.0, 0.5):
+        img = z
+        with torch.no_grad():
+            for k, i in enumerate(range(4, -1, -1)):
+                t = torch.full((2,), i, dtype=torch.long)
+                img = O.ddim_step(T, O.dit_forward(sd, cfg, img, tm[t], y), img, t, noises[k], True, eta)["sample"]
+        it = iter(noises)
+        real = gd._randn_like
+        gd._randn_like = lambda x: next(it).cuda()
+        try:
+            out = d.ddim_sample_loop(m.forward, z.shape, z.cuda(), model_kwargs=dict(y=y.cuda()), device="cuda", eta=eta)
+        finally:
+            gd._randn_like = real
+        e = rel_l2(out.cpu(), img)
+        print(f"ddim eta={eta} {dtype}: rel-L2 vs oracle after 5 steps {e:.2e}")
+        assert e < tol

@@ -82,7 +82,7 @@ def test_diffusion_tables_and_maps():
         assert T.timestep_map == [int(v) for v in g[f"{key}::timestep_map"]]
         np.testing.assert_allclose(T.betas, g[f"{key}::betas"], rtol=1e-13)
         for k, v in T.tabs.items():
-            if k == "log_betas":
+            if k in ("log_betas", "alphas_cumprod", "alphas_cumprod_prev"):
                 continue
             np.testing.assert_allclose(v, g[f"{key}::{k}"], rtol=1e-12, atol=0, err_msg=f"{key}::{k}")
     T = O.make_tables("50")
@@ -103,6 +103,17 @@ def test_training_losses_and_p_sample_synthetic():
                               torch.from_numpy(g["tl_noise"]), clip_denoised=bool(clip))
         assert rel_l2(out["sample"], g[f"ps_sample_clip{clip}"]) < 1e-6
         assert rel_l2(out["pred_xstart"], g[f"ps_x0_clip{clip}"]) < 1e-6
+
+
+def test_ddim_step_synthetic():
+    g = load("diffusion")
+    mo, x, noise, t = (torch.from_numpy(g[k]) for k in ("tl_mo", "tl_x0", "tl_noise", "dd_t"))
+    T = O.make_tables("ddim25")
+    for eta in (0.0, 0.7):
+        for clip in (1, 0):
+            out = O.ddim_step(T, mo, x, t, noise, clip_denoised=bool(clip), eta=eta)
+            assert rel_l2(out["sample"], g[f"dd_sample_eta{eta}_clip{clip}"]) < 1e-6
+            assert rel_l2(out["pred_xstart"], g[f"dd_x0_eta{eta}_clip{clip}"]) < 1e-6
 
 
 @pytest.mark.parametrize("tag", ["loop_xs8", "loop_xs4_cfg"])
