@@ -56,11 +56,15 @@ def test_rotation_training_gradients(modulation, dtype, tol):
     oterms, ograds = O.train_step_grads(p, cfg, O.make_tables(""), x, t, y, noise, drop_mask=drop)
     assert rel_l2(terms["loss"].detach().cpu(), oterms["loss"].detach()) < (2e-5 if dtype == "fp32" else 3e-2)
     worst = 0.0
+    gain_scale = max(float(v.abs()) for k, v in ograds.items() if v.dim() == 0)
     for k, prm in m.named_parameters():
+        if dtype == "bf16" and prm.dim() == 0:
+            # a scalar gain's gradient is a sum of +/- terms over every token and channel pair: under bf16 rounding the
+            # cancellation leaves an ABSOLUTE error set by the size of the summands, so it is bounded against the largest
+            # gain gradient of the model rather than against its own (possibly tiny) value
+            assert abs(float(prm.grad) - float(ograds[k])) < 0.1 * gain_scale, (k, float(prm.grad), float(ograds[k]))
+            continue
         e = rel_l2(prm.grad.cpu(), ograds[k])
         worst = max(worst, e)
-        # the scalar gains' gradients are sums of +/- terms over every token and channel pair: under bf16 rounding the
-        # cancellation leaves a larger relative error on those single numbers than on the weight matrices
-        ptol = 0.3 if (dtype == "bf16" and prm.dim() == 0) else tol
-        assert e < ptol, (k, e)
+        assert e < tol, (k, e)
     print(f"{modulation} {dtype}: worst per-parameter grad rel-L2 vs oracle {worst:.2e}")
