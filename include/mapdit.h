@@ -104,6 +104,10 @@ int mapdit_gemm_bf16_tn(const void* dy, int64_t ldy, const void* x, int64_t ldx,
 int mapdit_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                      float bias_corr1, float bias_corr2, float grad_scale, void* stream);
 
+/* multi-tensor EMA update (src/ema.py:135-140): for each chunk {float* dst; const float* src; int64 n} of the device
+ * table, dst = lerp(dst, src, weight) with torch.lerp's rounding */
+int mapdit_multi_lerp(const void* chunk_table, int n_chunks, float weight, void* stream);
+
 /* ---- K3 standalone elementwise ops (fp32 mode and fallbacks); dtype = activation dtype ------ */
 /* h = modulate(x, shift, scale, g) = lerp(x*scale, shift, g)/sqrt((1-g)^2+g^2)  (src/utils.py:11-16) */
 int mapdit_modulate_fwd(const void* x, void* h, const float* shift, const float* scale, const float* gain,

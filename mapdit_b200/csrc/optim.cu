@@ -44,3 +44,25 @@ extern "C" int mapdit_adam_step(float* p, const float* g, float* m, float* v, in
   MAPDIT_LAUNCH_CHECK("adam_step");
   return MAPDIT_OK;
 }
+
+// Multi-tensor EMA update ("next" row N2, src/ema.py:135-140: param.lerp_(model_param, beta) for every parameter of every
+// tracked copy): one launch per EMA copy over a device-resident chunk table {dst, src, count}.
+struct LerpChunk {
+  float* dst;
+  const float* src;
+  long long n;
+};
+__global__ void __launch_bounds__(256) multi_lerp_kernel(const LerpChunk* __restrict__ table, float w) {
+  const LerpChunk c = table[blockIdx.x];
+  for (long long i = threadIdx.x; i < c.n; i += 256) {
+    float a = c.dst[i], b = c.src[i];
+    float d = b - a;
+    c.dst[i] = (w < 0.5f) ? fmaf(w, d, a) : b - d * (1.0f - w);  // torch.lerp's two-branch form
+  }
+}
+extern "C" int mapdit_multi_lerp(const void* chunk_table, int n_chunks, float weight, void* stream) {
+  MAPDIT_REQUIRE(chunk_table && n_chunks > 0, "multi_lerp: bad args");
+  multi_lerp_kernel<<<n_chunks, 256, 0, (cudaStream_t)stream>>>((const LerpChunk*)chunk_table, weight);
+  MAPDIT_LAUNCH_CHECK("multi_lerp");
+  return MAPDIT_OK;
+}

@@ -109,6 +109,10 @@ def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0):
                                  1.0 - beta1 ** step, 1.0 - beta2 ** step, float(grad_scale), _stream()), "adam_step")
 
 
+def multi_lerp(chunk_table, n_chunks, weight):
+    check(lib().mapdit_multi_lerp(_ptr(chunk_table), n_chunks, float(weight), _stream()), "multi_lerp")
+
+
 def modulate(x, h, shift, scale, gain, ldmod, tokens):
     m, d = x.shape
     check(lib().mapdit_modulate_fwd(_ptr(x), _ptr(h), _ptr(shift), _ptr(scale), _ptr(gain), ldmod, m, d, tokens, _dt(x),

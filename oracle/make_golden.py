@@ -207,8 +207,61 @@ def loop_case(tag, name, B, seed, steps, use_cfg):
     print(tag, "ok", [float(np.abs(rec[f'samples_clip{c}'][-1]).mean()) for c in (1, 0)])
 
 
+def ema_case(tag):
+    """Reference src/ema.py host math + a post-hoc reconstruction from four synthetic fp16 snapshots."""
+    import tempfile
+    from src import ema as R
+    stds = np.array([0.05, 0.1, 0.075])
+    rec = dict(stds=stds, gammas=R.std_to_gamma(stds), back=R.gamma_to_std(R.std_to_gamma(stds)))
+    rec["beta_ts"] = np.array([1, 2, 100, 40000])
+    rec["betas"] = np.array([[R.calc_beta(s, t) for t in rec["beta_ts"]] for s in (0.05, 0.1)])
+    snaps = [(0.05, 500), (0.1, 500), (0.05, 1000), (0.1, 1000)]
+    rec["snap_stds"] = np.array([s for s, _ in snaps])
+    rec["snap_ts"] = np.array([t for _, t in snaps])
+    rec["weights"] = R.solve_weights(rec["snap_ts"], R.std_to_gamma(rec["snap_stds"]), 1000, R.std_to_gamma(0.075))
+    g = np.random.default_rng(77)
+    with tempfile.TemporaryDirectory() as d:
+        for i, (s, t) in enumerate(snaps):
+            sd = {"a.weight": torch.from_numpy(g.standard_normal((5, 7), dtype=np.float32)).half(),
+                  "b": torch.from_numpy(g.standard_normal((3,), dtype=np.float32)).half()}
+            rec[f"snap{i}_a"], rec[f"snap{i}_b"] = sd["a.weight"].float().numpy(), sd["b"].float().numpy()
+            torch.save({"std": s, "t": t, "state_dict": sd}, os.path.join(d, f"{s:.3f}_{t:07d}.pt"))
+        out = R.calculate_posthoc_ema(0.075, d, verbose=False)
+        rec["posthoc_a"], rec["posthoc_b"] = out["a.weight"].numpy(), out["b"].numpy()
+        hit = R.calculate_posthoc_ema(0.1, d, verbose=False)
+        rec["exact_a"] = hit["a.weight"].float().numpy()
+    # EMA.update semantics on a tiny module: three updates of two tracked copies (src/ema.py:124-140)
+    net = torch.nn.Linear(6, 4)
+    with torch.no_grad():
+        net.weight.copy_(torch.from_numpy(g.standard_normal((4, 6), dtype=np.float32)))
+        net.bias.copy_(torch.from_numpy(g.standard_normal((4,), dtype=np.float32)))
+    with tempfile.TemporaryDirectory() as d:
+        e = R.EMA(net, d)
+        rec["upd_w0"], rec["upd_b0"] = net.weight.detach().numpy().copy(), net.bias.detach().numpy().copy()
+        deltas = []
+        for t in (1, 2, 3):
+            dw = torch.from_numpy(g.standard_normal((4, 6), dtype=np.float32))
+            db = torch.from_numpy(g.standard_normal((4,), dtype=np.float32))
+            deltas.append((dw.numpy(), db.numpy()))
+            with torch.no_grad():
+                net.weight.add_(dw)
+                net.bias.add_(db)
+            e.update(t, net)
+        rec["upd_dw"] = np.stack([a for a, _ in deltas])
+        rec["upd_db"] = np.stack([b for _, b in deltas])
+        for s in (0.05, 0.1):
+            rec[f"upd_w_{s}"] = e.emas[s].weight.numpy().copy()
+            rec[f"upd_b_{s}"] = e.emas[s].bias.numpy().copy()
+    np.savez_compressed(os.path.join(OUT, f"{tag}.npz"), **rec)
+    print(tag, "ok")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    if len(sys.argv) > 1:  # regenerate selected fixtures only: python oracle/make_golden.py ema
+        for a in sys.argv[1:]:
+            {"ema": lambda: ema_case("ema")}[a]()
+        sys.exit(0)
     eval_case("eval_xs8", "DiT-XS/8", 3, 1)
     eval_case("eval_s4", "DiT-S/4", 2, 2)
     eval_case("eval_xs2", "DiT-XS/2", 1, 3)
@@ -218,3 +271,4 @@ if __name__ == "__main__":
     diffusion_case("diffusion")
     loop_case("loop_xs8", "DiT-XS/8", 2, 7, 6, False)
     loop_case("loop_xs4_cfg", "DiT-XS/4", 1, 8, 5, True)
+    ema_case("ema")

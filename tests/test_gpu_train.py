@@ -153,3 +153,50 @@ def test_fused_train_step_matches_adam(dtype):
     print(f"{dtype}: worst parameter-update rel-L2 after 2 steps = {worst:.2e}")
     assert worst < (5e-3 if dtype == "fp32" else 0.5)
     assert m.state_dict().keys() == sd.keys()
+
+
+@pytest.mark.gpu
+def test_ema_update_matches_reference_golden(tmp_path):
+    """EMA.update (src/ema.py:124-140) through the multi-tensor lerp kernel vs the unmodified reference's result."""
+    import os
+    from conftest import GOLDEN
+    from mapdit_b200.ema import EMA
+    g = np.load(os.path.join(GOLDEN, "ema.npz"))
+    net = torch.nn.Linear(6, 4).cuda()
+    with torch.no_grad():
+        net.weight.copy_(torch.from_numpy(g["upd_w0"]))
+        net.bias.copy_(torch.from_numpy(g["upd_b0"]))
+    e = EMA(net, str(tmp_path))
+    for i, t in enumerate((1, 2, 3)):
+        with torch.no_grad():
+            net.weight.add_(torch.from_numpy(g["upd_dw"][i]).cuda())
+            net.bias.add_(torch.from_numpy(g["upd_db"][i]).cuda())
+        e.update(t, net)
+    for s in (0.05, 0.1):
+        np.testing.assert_allclose(e.emas[s].weight.cpu().numpy(), g[f"upd_w_{s}"], rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(e.emas[s].bias.cpu().numpy(), g[f"upd_b_{s}"], rtol=1e-6, atol=1e-7)
+    e.save_snapshot(3)
+    snap = torch.load(tmp_path / "ema" / "0.050_0000003.pt", weights_only=True)
+    assert snap["std"] == 0.05 and snap["t"] == 3 and snap["state_dict"]["weight"].dtype == torch.float16
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("w", [0.0, 0.3, 0.5, 0.9, 1.0])
+def test_multi_lerp_matches_torch_lerp_on_a_model(w):
+    import copy
+    import mapdit_b200 as M
+    from mapdit_b200.ema import EMA
+    m = M.DIT_MODELS["DiT-XS/8"](in_channels=4, input_size=32, num_classes=10).cuda()
+    e = EMA.__new__(EMA)
+    e.emas, e._tables = {0.05: copy.deepcopy(m).eval().requires_grad_(False)}, {}
+    want = {k: v.detach().clone() for k, v in e.emas[0.05].named_parameters()}
+    with torch.no_grad():
+        for p in m.parameters():
+            p.add_(torch.randn_like(p))
+        for k, v in want.items():
+            v.lerp_(m.get_parameter(k), w)
+    from mapdit_b200 import ops
+    tab, n = e._table(0.05, m)
+    ops.multi_lerp(tab, n, w)
+    for k, v in e.emas[0.05].named_parameters():
+        torch.testing.assert_close(v, want[k], rtol=1e-6, atol=1e-7)

@@ -102,3 +102,24 @@ def test_off_path_entry_points_say_so():
         d.calc_bpd_loop(None, None)
     with pytest.raises(NotImplementedError):
         M.create_diffusion("", predict_xstart=True).training_losses(None, torch.zeros(1, 4, 8, 8), torch.zeros(1).long())
+
+
+def test_ema_host_math_matches_reference_golden(tmp_path):
+    """src/ema.py:10-114 — std<->gamma, beta schedule, post-hoc weights and reconstruction from fp16 snapshots."""
+    from mapdit_b200 import ema as E
+    g = np.load(os.path.join(GOLDEN, "ema.npz"))
+    np.testing.assert_allclose(E.std_to_gamma(g["stds"]), g["gammas"], rtol=1e-12)
+    np.testing.assert_allclose(E.gamma_to_std(g["gammas"]), g["back"], rtol=1e-12)
+    for i, s in enumerate((0.05, 0.1)):
+        np.testing.assert_allclose([E.calc_beta(s, t) for t in g["beta_ts"]], g["betas"][i], rtol=1e-12)
+    w = E.solve_weights(g["snap_ts"], E.std_to_gamma(g["snap_stds"]), 1000, E.std_to_gamma(0.075))
+    np.testing.assert_allclose(w, g["weights"], rtol=1e-10)
+    for i, (s, t) in enumerate(zip(g["snap_stds"], g["snap_ts"])):
+        sd = {"a.weight": torch.from_numpy(g[f"snap{i}_a"]).half(), "b": torch.from_numpy(g[f"snap{i}_b"]).half()}
+        torch.save({"std": float(s), "t": int(t), "state_dict": sd}, tmp_path / f"{s:.3f}_{int(t):07d}.pt")
+    out = E.calculate_posthoc_ema(0.075, str(tmp_path), verbose=False)
+    np.testing.assert_allclose(out["a.weight"].numpy(), g["posthoc_a"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(out["b"].numpy(), g["posthoc_b"], rtol=1e-6, atol=1e-7)
+    hit = E.calculate_posthoc_ema(0.1, str(tmp_path), verbose=False)
+    assert hit["a.weight"].dtype == torch.float16  # exact-std hit returns the stored fp16 snapshot (src/ema.py:93-98)
+    np.testing.assert_array_equal(hit["a.weight"].float().numpy(), g["exact_a"])
