@@ -1,0 +1,113 @@
+#!/usr/bin/env python
+"""N-GPU == 1-GPU check of the data-parallel paths, run under torchrun on a multi-GPU box:
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29555 tools/dp_check.py
+
+Training: every rank runs two TrainStep steps on its shard of a global batch (NCCL all-reduce of the gradient
+buckets); rank 0 then repeats the two steps alone on the concatenated batch and the parameters are compared.
+Sampling: every rank samples its shard, one all_gather, compared against rank 0 sampling the whole batch.
+Prints one JSON line; exit code 1 on mismatch.
+"""
+import json
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+import mapdit_b200 as M  # noqa: E402
+from mapdit_b200.diffusion import gaussian_diffusion as gd  # noqa: E402
+from mapdit_b200.parallel import gather_samples, shard_range  # noqa: E402
+from mapdit_b200.train import TrainStep  # noqa: E402
+from oracle import mapdit_oracle as O  # noqa: E402  (deterministic weight init only)
+
+
+def rel(a, b):
+    return float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    name = os.environ.get("DP_MODEL", "DiT-S/2")
+    per = int(os.environ.get("DP_BATCH", "16"))
+    cfg = O.config_for(name)
+    sd = O.init_state_dict(cfg, seed=0)
+    G = per * world
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(G, 4, 32, 32, generator=g)
+    y = torch.randint(0, 1000, (G,), generator=g)
+    t = torch.randint(0, 1000, (G,), generator=g)
+    noise = torch.randn(2, G, 4, 32, 32, generator=g)
+    drop = torch.rand(G, generator=g) < 0.1
+    lo, hi = shard_range(G, rank, world)
+    res = {"world": world, "model": name, "global_batch": G}
+
+    def run_train(w, sl):
+        m = M.DIT_MODELS[name](in_channels=4, input_size=32, num_classes=1000)
+        m.load_state_dict(sd)
+        m = m.to(dev).train()
+        ts = TrainStep(m, M.create_diffusion(""), world_size=w)
+        if w == 1:
+            ts.reducer.ready = lambda i: None   # single-process replay on a multi-rank job: no collective
+            ts.reducer.finish = lambda: None
+        losses = []
+        for k in range(2):
+            losses.append(ts.step(x[sl].to(dev), t[sl].to(dev), y[sl].to(dev), noise[k, sl].to(dev), drop_mask=drop[sl].to(dev)))
+        torch.cuda.synchronize()
+        return {n: p.detach().clone() for n, p in m.named_parameters()}, torch.stack(losses)
+
+    p_dp, loss_dp = run_train(world, slice(lo, hi))
+    dist.all_reduce(loss_dp)
+    loss_dp /= world
+    # replicas stay bit-identical
+    flat = torch.cat([v.reshape(-1) for v in p_dp.values()])
+    ref0 = flat.clone()
+    dist.broadcast(ref0, 0)
+    res["replicas_bit_identical"] = bool(torch.equal(flat, ref0))
+    ok = res["replicas_bit_identical"]
+    if rank == 0:
+        p_1, loss_1 = run_train(1, slice(0, G))
+        worst = max(rel(p_dp[n], p_1[n]) for n in p_1)
+        upd = max(rel(p_dp[n] - sd[n].to(dev), p_1[n] - sd[n].to(dev)) for n in p_1 if p_1[n].ndim == 2)
+        res.update(train_param_rel_l2_worst=worst, train_update_rel_l2_worst=upd, loss_rel=rel(loss_dp, loss_1))
+        # bf16 kernels: per-sample results do not depend on the batch they sit in, but split-K wgrad sums and the
+        # per-rank partial sums are added in a different order -> small fp32/bf16 noise, Adam normalises tiny grads
+        ok &= worst < 2e-3 and res["loss_rel"] < 1e-4
+    dist.barrier()
+
+    # ---- sampling: batch-sharded, one final gather
+    m = M.DIT_MODELS[name](in_channels=4, input_size=32, num_classes=1000)
+    m.load_state_dict(sd)
+    m = m.to(dev).eval()
+    d = M.create_diffusion("5")
+    ns = [torch.randn(G, 4, 32, 32, generator=g) for _ in range(5)]
+
+    def sample(sl):
+        it = iter(ns)
+        real = gd._randn_like
+        gd._randn_like = lambda v: next(it)[sl].to(dev)
+        try:
+            return d.p_sample_loop(m.forward, (hi - lo if sl != slice(0, G) else G, 4, 32, 32), x[sl].to(dev),
+                                   model_kwargs=dict(y=y[sl].to(dev)), device=dev).clone()
+        finally:
+            gd._randn_like = real
+
+    full = gather_samples(sample(slice(lo, hi)))
+    if rank == 0:
+        one = sample(slice(0, G))
+        res["sample_rel_l2"] = rel(full, one)
+        ok &= res["sample_rel_l2"] < 1e-5 or bool(torch.equal(full, one))
+        print(json.dumps(res), flush=True)
+    okt = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+    dist.destroy_process_group()
+    sys.exit(0 if int(okt) else 1)
+
+
+if __name__ == "__main__":
+    main()
