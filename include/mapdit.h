@@ -35,11 +35,24 @@ int mapdit_abi_version(void);
 /* number of kernels launched by this library since load (bench.py's gpu_launches) */
 int64_t mapdit_launch_count(void);
 
+/* ---- README "--use-*" switches turned OFF (README.md:59-66).  The reference snapshot hard-codes every switch on and
+ * ships no "off" branch, so these variants are UNPINNED: their oracle is this repo's own
+ * restatement of the vanilla DiT ops.  The word is per host thread and is read at launch time by the entry points
+ * that have a variant (resid, mp_silu, cond_combine, patch_embed, embed_rows, the fused GEMM epilogues, attention
+ * dispatch, and their backward kernels); returns the previous word.                                              */
+#define MAPDIT_VAR_PLAIN_RESID 1  /* use_mp_residual=False : x + gate*y instead of mp_sum(x, gate*y, 0.3)            */
+#define MAPDIT_VAR_PLAIN_SILU 2   /* use_mp_silu=False     : silu(x) instead of silu(x)/0.596                        */
+#define MAPDIT_VAR_PLAIN_POS 4    /* use_mp_pos_enc=False  : x + pos instead of mp_sum(x, pos, 0.5)                  */
+#define MAPDIT_VAR_PLAIN_EMBED 8  /* use_mp_embedding=False: plain table gather, c = t_emb + y_emb                   */
+#define MAPDIT_VAR_DOT_ATTN 16    /* use_cosine_attention=False: unbounded logits -> running-max softmax kernels     */
+int mapdit_set_variant(int flags);
+
 /* ---- K1: weight normalisation --------------------------------------------------------------
  * Replaces normalize()/chunk_normalize() + the forced in-place normalisation
  * (src/utils.py:19-34, src/basic/mp_linear.py:37-46,67-75, src/basic/mp_embedding.py:16-22).
  * For each row r of w[rows, cols]:
- *   force != 0 : w[r] <- w[r]*sqrt(cols)/(||w[r]||+eps)   (written back in place, train mode)
+ *   force > 0  : w[r] <- w[r]*sqrt(cols)/(||w[r]||+eps)   (written back in place, train mode)
+ *   force < 0  : no normalisation at all, eff = w (use_weight_normalization=False, UNPINNED)
  *   eff = w[r]/(||w[r]||+eps) (= normalize(w)/sqrt(cols)), computed from the (forced) row and
  *   written to any of eff_f32 [rows, cols], eff_bf16 [rows, cols], eff_bf16_t [cols, ld_t >= rows]
  *   (transposed copy for dgrad).  inv_norm [rows] (optional) receives 1/(||w||+eps) of the
@@ -137,6 +150,14 @@ int mapdit_cos_attn_bwd(const void* qkv, const void* o, const void* dout, const 
 int mapdit_patch_embed(const float* x, const float* wx_eff, const float* pos, void* x0, void* h,
                        const float* shift, const float* scale, const float* gain, int64_t ldmod,
                        int n_samples, int channels, int input_size, int patch, int d, int dtype, void* stream);
+/* use_mp_embedding=False (UNPINNED): vanilla-DiT sinusoidal features e[n, :dim/2] = cos(t f), e[n, dim/2:] = sin(t f) */
+int mapdit_timestep_sincos(const int64_t* t, float* e, int n, int dim, float max_period, void* stream);
+/* use_no_layernorm=False (UNPINNED): h = LayerNorm(x; eps 1e-6, no affine) * (1 + scale) + shift; stats [M, 2] = {mean, rstd} (nullable) */
+int mapdit_ln_modulate_fwd(const void* x, void* h, const float* shift, const float* scale, float* stats, int64_t ldmod, int m,
+                           int d, int tokens, int dtype, void* stream);
+int mapdit_ln_modulate_bwd(const void* dh, const void* x, void* R /* nullable */, const float* stats, const float* scale,
+                           float* dshift, float* dscale, int64_t ldmod, int n_samples, int d, int tokens, int accumulate,
+                           int dtype, void* stream);
 /* e[n, j] = sqrt(2) cos(fl(fl(t*scale_j)+shift_j)) (src/blocks/timestep_embedder.py:18-21) */
 int mapdit_fourier(const int64_t* t, const float* scale, const float* shift, float* e, int n, int channels, void* stream);
 /* out[n,:] = normalize(table[idx[n],:]) (src/basic/mp_embedding.py:21-24); drop: idx -> null_idx where mask */

@@ -30,6 +30,10 @@ SIGNATURES = {
     "mapdit_gemm_bf16": [C.POINTER(GemmArgs), _p],
     "mapdit_gemm_bf16_tn": [_p, _i64, _p, _i64, _p, _i64, _i, _i, _i, _p],
     "mapdit_multi_lerp": [_p, _i, _f, _p],
+    "mapdit_set_variant": [_i],
+    "mapdit_timestep_sincos": [_p, _p, _i, _i, _f, _p],
+    "mapdit_ln_modulate_fwd": [_p, _p, _p, _p, _p, _i64, _i, _i, _i, _i, _p],
+    "mapdit_ln_modulate_bwd": [_p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _i, _i, _i, _p],
     "mapdit_adam_step": [_p, _p, _p, _p, _i64, _f, _f, _f, _f, _f, _f, _f, _p],
     "mapdit_modulate_fwd": [_p, _p, _p, _p, _p, _i64, _i, _i, _i, _i, _p],
     "mapdit_resid_fwd": [_p, _p, _p, _p, _i64, _i, _i, _i, _i, _p],

@@ -83,11 +83,28 @@ class Trainer:
             dmods16=torch.empty(N, W, device=dev, dtype=torch.bfloat16) if mode == "bf16" else None,
             dWs=torch.empty(max(Hm * D, W * D), **f),  # scratch for d(effective weight), largest weight
         )
+        if not m.flags["use_no_layernorm"]:  # LayerNorm statistics {mean, rstd} per token row, per modulate site
+            B["ln1"] = [torch.empty(M, 2, **f) for _ in range(L + 1)]  # index L = final layer
+            B["ln2"] = [torch.empty(M, 2, **f) for _ in range(L)]
         self._bufs[key] = B
         return B
 
     # ------------------------------------------------------------------ forward
     def forward(self, x, t, y, drop_mask):
+        prev = ops.set_variant(self.m.variant)
+        try:
+            return self._forward(x, t, y, drop_mask)
+        finally:
+            ops.set_variant(prev)
+
+    def backward(self, saved, dout):
+        prev = ops.set_variant(self.m.variant)
+        try:
+            return self._backward(saved, dout)
+        finally:
+            ops.set_variant(prev)
+
+    def _forward(self, x, t, y, drop_mask):
         e, m = self.e, self.m
         mode = m.compute_dtype
         bf = mode == "bf16"
@@ -104,7 +121,12 @@ class Trainer:
         f = m.final_layer
         blk = m.blocks
 
-        ops.fourier(t, m.t_embedder.embedding.scale, m.t_embedder.embedding.shift, B["e"])
+        fl = m.flags
+        ln, cosine = not fl["use_no_layernorm"], fl["use_cosine_attention"]
+        if fl["use_mp_embedding"]:
+            ops.fourier(t, m.t_embedder.embedding.scale, m.t_embedder.embedding.shift, B["e"])
+        else:
+            ops.timestep_sincos(t, B["e"])
         ops.gemm_f32(B["e"], W.wt1, out=B["t1"])
         ops.mp_silu(B["t1"], B["t1s"])
         ops.gemm_f32(B["t1s"], W.wt2, out=B["temb"])
@@ -134,7 +156,10 @@ class Trainer:
 
         def modulate_block(i, branch, src, dst):
             gain = (blk[i].gain_msa if branch == "a" else blk[i].gain_mlp).data
-            if adaln:
+            if ln:
+                ops.ln_modulate(src, dst, mod(i, "shift_" + branch), mod(i, "scale_" + branch),
+                                B["ln1" if branch == "a" else "ln2"][i], ld, T)
+            elif adaln:
                 ops.modulate(src, dst, mod(i, "shift_" + branch), mod(i, "scale_" + branch), gain, ld, T)
             else:
                 sc = mod(i, "scale_" + branch) if ("scale_" + branch) in lay else None
@@ -143,13 +168,21 @@ class Trainer:
         def modulate_next(i, src, dst):
             if i + 1 < L:
                 modulate_block(i + 1, "a", src, dst)
+            elif ln:
+                ops.ln_modulate(src, dst, mods[:, fbase:], mods[:, fbase + D:], B["ln1"][L], ld, T)
             else:
                 ops.modulate(src, dst, mods[:, fbase:], mods[:, fbase + D:], f.gain_mod.data, ld, T)
 
-        fused = bf and adaln
-        if bf and hd != 64:
-            raise NotImplementedError("bf16 training needs head_dim 64 (DiT-XL uses 72): use compute_dtype='fp32'")
-        if adaln:
+        def qkv_proj(i, src, dst):
+            if cosine and hd == 64:
+                ops.gemm_bf16(src, W.wqkv[i], dst, epilogue=_lib.EPI_QKNORM, tokens=T, head_dim=hd, qk_cols=2 * D, aux=B["sc"][i])
+            else:  # head_dim 72 (DiT-XL) or plain dot-product attention: plain store + standalone normalisation
+                ops.gemm_bf16(src, W.wqkv[i], dst)
+                if cosine:
+                    ops.qk_normalize_save(dst, B["sc"][i], D, hd)
+
+        fused = bf and adaln and not ln and cosine and hd == 64
+        if adaln and not ln:
             ops.patch_embed(x, W.wx, m.pos_embed, B["xin"][0], B["h1"][0], mod(0, "shift_a"), mod(0, "scale_a"), blk[0].gain_msa.data,
                             ld, m.patch_size)
         else:
@@ -171,7 +204,7 @@ class Trainer:
                 ops.gemm_bf16(u, W.w2[i], xnext, epilogue=_lib.EPI_RESID_MOD, out2=hnext, resid=xmid, gate=mod(i, "gate_m"), shift=nsh,
                               scale=nsc, gain=ngn, ldmod=ld, tokens=T, aux=b)
             elif bf:
-                ops.gemm_bf16(h1, W.wqkv[i], qkv, epilogue=_lib.EPI_QKNORM, tokens=T, head_dim=hd, qk_cols=2 * D, aux=B["sc"][i])
+                qkv_proj(i, h1, qkv)
                 ops.cos_attn(qkv, o, N, T, H, hd, lse=B["lse"][i])
                 ops.gemm_bf16(o, W.wo[i], xmid, epilogue=_lib.EPI_RESID, resid=xin, gate=mod(i, "gate_a"), ldmod=ld, tokens=T, aux=a)
                 modulate_block(i, "m", xmid, h2)
@@ -180,7 +213,8 @@ class Trainer:
                 modulate_next(i, xnext, hnext)
             else:
                 ops.gemm_f32(h1, W.wqkv[i], out=qkv)
-                ops.qk_normalize_save(qkv, B["sc"][i], D, hd)
+                if cosine:
+                    ops.qk_normalize_save(qkv, B["sc"][i], D, hd)
                 ops.cos_attn(qkv, o, N, T, H, hd, lse=B["lse"][i])
                 ops.gemm_f32(o, W.wo[i], out=a)
                 ops.resid(xin, a, xmid, mod(i, "gate_a"), ld, T)
@@ -216,9 +250,17 @@ class Trainer:
             ops.gemm_bf16_tn(dy, xin, dW)
         else:
             ops.gemm_f32(dy, xin, out=dW, trans_a=True, trans_b=True)
+        grads[id(param)] = self._wn_bwd(param, dW)
+
+    def _wn_bwd(self, param, dW):
+        """gradient of the raw parameter from the gradient of its effective weight (tangent projection of the
+        weight normalisation, or the identity with use_weight_normalization=False)"""
         g = self._gbuf(param)
-        ops.weight_norm_bwd(param.data, dW, g)
-        grads[id(param)] = g
+        if self.m.flags["use_weight_normalization"]:
+            ops.weight_norm_bwd(param.data, dW, g)
+        else:
+            ops.axpby(dW, g, 1.0)
+        return g
 
     def _gbuf(self, p):
         """gradient destination of parameter p: a view of the caller's flat gradient buffer, or a fresh tensor"""
@@ -232,7 +274,7 @@ class Trainer:
         return g
 
     # ------------------------------------------------------------------ backward
-    def backward(self, saved, dout):
+    def _backward(self, saved, dout):
         e, m = self.e, self.m
         N, mode, dev = saved["N"], saved["mode"], saved["dev"]
         bf = mode == "bf16"
@@ -255,9 +297,22 @@ class Trainer:
         def mod(buf, i, name):
             return buf[:, i * lay["width"] + lay[name]:]
 
+        fl = m.flags
+        ln, cosine = not fl["use_no_layernorm"], fl["use_cosine_attention"]
+
+        def zero_gain_grad(gp):  # LayerNorm adaLN does not use the gain parameter
+            g = self._gbuf(gp)
+            g.zero_()
+            grads[id(gp)] = g
+
         def modulate_block_bwd(i, branch, dh_, x_, accumulate):
             """backward of the block-i modulation: R (+)= d/dx, per-sample vector grads into dmods, returns d(gain)"""
             gp = blk[i].gain_msa if branch == "a" else blk[i].gain_mlp
+            if ln:
+                ops.ln_modulate_bwd(dh_, x_, R, B["ln1" if branch == "a" else "ln2"][i], mod(mods, i, "scale_" + branch),
+                                    mod(dmods, i, "shift_" + branch), mod(dmods, i, "scale_" + branch), ld, N, T, accumulate)
+                zero_gain_grad(gp)
+                return
             if adaln:
                 ops.modulate_bwd(dh_, x_, R, mod(mods, i, "shift_" + branch), mod(mods, i, "scale_" + branch), gp.data,
                                  mod(dmods, i, "shift_" + branch), mod(dmods, i, "scale_" + branch), B["dgp"], ld, N, T, accumulate)
@@ -281,15 +336,17 @@ class Trainer:
         for dl, p in ((B["dlmu"], f.mean_scale.linear.weight), (B["dlsg"], f.sigma_scale.linear.weight)):
             dW = B["dWs"][: 8 * D].view(8, D)
             ops.gemm_f32(dl, B["c"], out=dW, trans_a=True, trans_b=True)
-            g = self._gbuf(p)
-            ops.weight_norm_bwd(p.data, dW, g)
-            grads[id(p)] = g
+            grads[id(p)] = self._wn_bwd(p, dW)
         hF, xF = B["h1"][L], B["xin"][L]
         self._wgrad(B["dlin"], hF, f.linear.weight, bf, B, grads)
         self._dgrad(B["dlin"], W.wfl, getattr(W, "wfl_t", None), dh, bf)
-        ops.modulate_bwd(dh, xF, R, mods[:, fbase:], mods[:, fbase + D:], f.gain_mod.data, dmods[:, fbase:],
-                         dmods[:, fbase + D:], B["dgp"], ld, N, T, False)
-        grads[id(f.gain_mod)] = self._scalar_from_partials(B, npart, f.gain_mod)
+        if ln:
+            ops.ln_modulate_bwd(dh, xF, R, B["ln1"][L], mods[:, fbase + D:], dmods[:, fbase:], dmods[:, fbase + D:], ld, N, T, False)
+            zero_gain_grad(f.gain_mod)
+        else:
+            ops.modulate_bwd(dh, xF, R, mods[:, fbase:], mods[:, fbase + D:], f.gain_mod.data, dmods[:, fbase:],
+                             dmods[:, fbase + D:], B["dgp"], ld, N, T, False)
+            grads[id(f.gain_mod)] = self._scalar_from_partials(B, npart, f.gain_mod)
         # ---- blocks, last to first
         for i in range(L - 1, -1, -1):
             xin, h1, qkv, o, a, xmid, h2, z, u, b = (B[k][i] for k in ("xin", "h1", "qkv", "o", "a", "xmid", "h2", "z", "u", "b"))
@@ -310,7 +367,8 @@ class Trainer:
             self._wgrad(dY, o, blk[i].attn.out_proj.weight, bf, B, grads)
             self._dgrad(dY, W.wo[i], wt("wo_t"), dh, bf)
             ops.cos_attn_bwd(qkv, o, dh, B["lse"][i], dqkv, B["delta"], N, T, H, hd)
-            ops.qk_norm_bwd(dqkv, qkv, B["sc"][i], D, hd)
+            if cosine:
+                ops.qk_norm_bwd(dqkv, qkv, B["sc"][i], D, hd)
             self._wgrad(dqkv, h1, blk[i].attn.qkv_proj.weight, bf, B, grads)
             self._dgrad(dqkv, W.wqkv[i], wt("wqkv_t"), dh, bf)
             modulate_block_bwd(i, "a", dh, xin, True)
@@ -319,10 +377,8 @@ class Trainer:
         # ---- patch embed (src/dit.py:81-84): x0 = (lin + pos)/2/sqrt(.5) -> d lin = R * 0.5/sqrt(.5)
         K1 = m.x_embedder.weight.shape[1]
         dWx = B["dWs"][: D * K1].view(D, K1)
-        ops.patch_embed_wgrad(R, saved["x"], dWx, m.patch_size, 0.5 / 0.7071067811865476)
-        g = self._gbuf(m.x_embedder.weight)
-        ops.weight_norm_bwd(m.x_embedder.weight.data, dWx, g)
-        grads[id(m.x_embedder.weight)] = g
+        ops.patch_embed_wgrad(R, saved["x"], dWx, m.patch_size, 0.5 / 0.7071067811865476 if fl["use_mp_pos_enc"] else 1.0)
+        grads[id(m.x_embedder.weight)] = self._wn_bwd(m.x_embedder.weight, dWx)
         # ---- modulation GEMM of all blocks + final (one wgrad / dgrad over the concatenated weight)
         Wtot = dmods.shape[1]
         dWm = B["dWs"][: Wtot * D].view(Wtot, D)
@@ -335,13 +391,9 @@ class Trainer:
             ops.gemm_f32(dmods, B["cs"], out=dWm, trans_a=True, trans_b=True)
         for i in range(L):
             p = blk[i].modulation[1].weight
-            g = self._gbuf(p)
-            ops.weight_norm_bwd(p.data, dWm[i * lay["width"]:(i + 1) * lay["width"]], g)
-            grads[id(p)] = g
+            grads[id(p)] = self._wn_bwd(p, dWm[i * lay["width"]:(i + 1) * lay["width"]])
         p = f.modulation[1].weight
-        g = self._gbuf(p)
-        ops.weight_norm_bwd(p.data, dWm[fbase:], g)
-        grads[id(p)] = g
+        grads[id(p)] = self._wn_bwd(p, dWm[fbase:])
         # ---- conditioning path (src/dit.py:86-88)
         ops.cond_combine_bwd(B["c"], B["dc"], B["dcs"], B["dab"])
         table = m.y_embedder.embedding.weight
@@ -352,16 +404,12 @@ class Trainer:
         p2, p1 = m.t_embedder.mlp.net[2].weight, m.t_embedder.mlp.net[0].weight
         dW = B["dWs"][: D * D].view(D, D)
         ops.gemm_f32(B["dab"], B["t1s"], out=dW, trans_a=True, trans_b=True)
-        g = self._gbuf(p2)
-        ops.weight_norm_bwd(p2.data, dW, g)
-        grads[id(p2)] = g
+        grads[id(p2)] = self._wn_bwd(p2, dW)
         ops.gemm_f32(B["dab"], W.wt2, out=B["dt1s"], trans_b=True)
         ops.mp_silu_bwd(B["dt1s"], B["t1"], B["dt1s"])
         dW = B["dWs"][: D * 256].view(D, 256)
         ops.gemm_f32(B["dt1s"], B["e"], out=dW, trans_a=True, trans_b=True)
-        g = self._gbuf(p1)
-        ops.weight_norm_bwd(p1.data, dW, g)
-        grads[id(p1)] = g
+        grads[id(p1)] = self._wn_bwd(p1, dW)
         if self.grad_hook is not None:
             done = {id(q) for b_ in blk for q in b_.parameters() if q is not b_.modulation[1].weight}
             self.grad_hook([(q, grads[id(q)]) for q in m.parameters() if id(q) not in done])

@@ -399,7 +399,7 @@ int encode2d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uin
 extern "C" int mapdit_cos_attn_bwd(const void* qkv, const void* o, const void* dout, const float* lse, void* dqkv, float* delta,
                                    int n_samples, int tokens, int heads, int head_dim, int dtype, void* stream) {
   MAPDIT_REQUIRE(qkv && o && dout && lse && dqkv && delta && n_samples > 0 && tokens > 0, "cos_attn_bwd: bad args");
-  if (!(dtype == MAPDIT_BF16 && head_dim == HD && tokens % CB == 0))
+  if (!(dtype == MAPDIT_BF16 && head_dim == HD && tokens % CB == 0) || (mapdit_variant() & MAPDIT_VAR_DOT_ATTN))
     return mapdit_attn_bwd_simt(qkv, o, dout, lse, dqkv, delta, n_samples, tokens, heads, head_dim, dtype, stream);
   const int D = heads * HD;
   const uint64_t rows = (uint64_t)n_samples * tokens;

@@ -176,10 +176,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           float p0 = ex2(fmaf(__uint_as_float(a0[2 * i]), c1, -c2)), p1 = ex2(fmaf(__uint_as_float(a0[2 * i + 1]), c1, -c2));
-          __nv_bfloat162 b = __floats2bfloat162_rn(p0, p1);
-          float2 back = __bfloat1622float2(b);
-          rowsum += back.x + back.y;
-          pk[i] = *reinterpret_cast<uint32_t*>(&b);
+          rowsum += p0 + p1;  // fp32 sum of the unrounded probabilities (the bf16 rounding of P is unbiased noise on top)
+          pk[i] = pack_bf16(p0, p1);
         }
         mbar_wait(&p_empty[s], ph ^ 1);
         // row r of the [128 x 64] bf16 K-major SWIZZLE_128B tile: 16-byte chunk c lives at c ^ (r % 8); this warp owns chunks 4ch..4ch+3

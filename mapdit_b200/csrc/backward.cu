@@ -13,12 +13,13 @@
 template <typename T>
 __global__ void __launch_bounds__(256) resid_bwd_kernel(T* __restrict__ R, const T* __restrict__ y, T* __restrict__ dy,
                                                         const float* __restrict__ gate, float* __restrict__ dgate, int64_t ldmod,
-                                                        int d, int tokens) {
+                                                        int d, int tokens, int var) {
   __shared__ float red[8][256];
   const int n = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int col = blockIdx.x * 256 + lane * 8;
   const bool ok = col < d;
-  const float ca = (1.0f - MP_RES_T) / MP_RES_DEN, cb = MP_RES_T / MP_RES_DEN;
+  const bool plain = var & MAPDIT_VAR_PLAIN_RESID;  // x + gate*y instead of mp_sum(x, gate*y, 0.3)
+  const float ca = plain ? 1.0f : (1.0f - MP_RES_T) / MP_RES_DEN, cb = plain ? 1.0f : MP_RES_T / MP_RES_DEN;
   float g[8], acc[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -58,9 +59,9 @@ extern "C" int mapdit_resid_bwd(void* R, const void* y, void* dy, const float* g
   MAPDIT_REQUIRE(R && y && dy && gate && dgate && n_samples > 0 && d > 0 && tokens > 0 && d % 8 == 0, "resid_bwd: bad args");
   dim3 grid((d + 255) / 256, n_samples);
   if (dtype == MAPDIT_F32)
-    resid_bwd_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((float*)R, (const float*)y, (float*)dy, gate, dgate, ldmod, d, tokens);
+    resid_bwd_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((float*)R, (const float*)y, (float*)dy, gate, dgate, ldmod, d, tokens, mapdit_variant());
   else
-    resid_bwd_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((bf16*)R, (const bf16*)y, (bf16*)dy, gate, dgate, ldmod, d, tokens);
+    resid_bwd_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((bf16*)R, (const bf16*)y, (bf16*)dy, gate, dgate, ldmod, d, tokens, mapdit_variant());
   MAPDIT_LAUNCH_CHECK("resid_bwd");
   return MAPDIT_OK;
 }
@@ -167,19 +168,20 @@ extern "C" int mapdit_sum_partials(const float* partials, int n, float* out, int
 // u = silu(z)/0.596 :  dz = du * sigma(z) (1 + z (1 - sigma(z))) / 0.596
 // ------------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void mp_silu_bwd_kernel(const T* du, const T* __restrict__ z, T* dz, int64_t n) {
+__global__ void mp_silu_bwd_kernel(const T* du, const T* __restrict__ z, T* dz, int64_t n, int var) {
+  const float div = silu_div_v(var);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float zv = ld_act(z + i);
     float s = 1.0f / (1.0f + expf(-zv));
-    st_act(dz + i, ld_act(du + i) * (s * (1.0f + zv * (1.0f - s))) / MP_SILU_DIV);
+    st_act(dz + i, ld_act(du + i) * (s * (1.0f + zv * (1.0f - s))) / div);
   }
 }
 extern "C" int mapdit_mp_silu_bwd(const void* du, const void* z, void* dz, int64_t n, int dtype, void* stream) {
   MAPDIT_REQUIRE(du && z && dz && n > 0, "mp_silu_bwd: bad args");
   int64_t b = (n + 255) / 256;
   int grid = (int)(b < 148 * 16 ? b : 148 * 16);
-  if (dtype == MAPDIT_F32) mp_silu_bwd_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)du, (const float*)z, (float*)dz, n);
-  else mp_silu_bwd_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)du, (const bf16*)z, (bf16*)dz, n);
+  if (dtype == MAPDIT_F32) mp_silu_bwd_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)du, (const float*)z, (float*)dz, n, mapdit_variant());
+  else mp_silu_bwd_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)du, (const bf16*)z, (bf16*)dz, n, mapdit_variant());
   MAPDIT_LAUNCH_CHECK("mp_silu_bwd");
   return MAPDIT_OK;
 }
@@ -393,17 +395,17 @@ extern "C" int mapdit_mp_scale_from_lin(const float* l, const float* ref, float*
 // ------------------------------------------------------------------------------------------------
 // c = (a+b) * 0.5 / sqrt(.5), cs = silu(c)/0.596 :  dc_total = dc + dcs * silu'(c)/0.596 ; da = db = dc_total * 0.5/sqrt(.5)
 __global__ void cond_combine_bwd_kernel(const float* __restrict__ c, const float* __restrict__ dc, const float* __restrict__ dcs,
-                                        float* __restrict__ dab, int64_t n) {
+                                        float* __restrict__ dab, int64_t n, int var) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float cv = c[i];
   float s = 1.0f / (1.0f + expf(-cv));
-  float tot = (dc ? dc[i] : 0.f) + dcs[i] * (s * (1.0f + cv * (1.0f - s))) / MP_SILU_DIV;
-  dab[i] = tot * (0.5f / MP_HALF_DEN);
+  float tot = (dc ? dc[i] : 0.f) + dcs[i] * (s * (1.0f + cv * (1.0f - s))) / silu_div_v(var);
+  dab[i] = (var & MAPDIT_VAR_PLAIN_EMBED) ? tot : tot * (0.5f / MP_HALF_DEN);
 }
 extern "C" int mapdit_cond_combine_bwd(const float* c, const float* dc, const float* dcs, float* dab, int64_t n, void* stream) {
   MAPDIT_REQUIRE(c && dcs && dab && n > 0, "cond_combine_bwd: bad args");
-  cond_combine_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(c, dc, dcs, dab, n);
+  cond_combine_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(c, dc, dcs, dab, n, mapdit_variant());
   MAPDIT_LAUNCH_CHECK("cond_combine_bwd");
   return MAPDIT_OK;
 }
@@ -411,12 +413,17 @@ extern "C" int mapdit_cond_combine_bwd(const float* c, const float* dc, const fl
 // label embedding: out[n] = normalize(E[id]) -> dE[id] += sqrt(d)/(r+eps) (G - v (v.G)/(r (r+eps)))  (rows may repeat: atomics)
 __global__ void __launch_bounds__(256) embed_rows_bwd_kernel(const int64_t* __restrict__ idx, const uint8_t* __restrict__ drop,
                                                              int64_t null_idx, const float* __restrict__ table,
-                                                             const float* __restrict__ g, float* __restrict__ dtable, int d, float eps) {
+                                                             const float* __restrict__ g, float* __restrict__ dtable, int d, float eps,
+                                                             int var) {
   __shared__ float red[32];
   int n = blockIdx.x;
   int64_t id = idx[n];
   if (drop && drop[n]) id = null_idx;
   const float* row = table + id * d;
+  if (var & MAPDIT_VAR_PLAIN_EMBED) {
+    for (int i = threadIdx.x; i < d; i += blockDim.x) atomicAdd(dtable + id * d + i, g[(size_t)n * d + i]);
+    return;
+  }
   float ss = 0.f, dot = 0.f;
   for (int i = threadIdx.x; i < d; i += blockDim.x) {
     ss = fmaf(row[i], row[i], ss);
@@ -431,7 +438,7 @@ __global__ void __launch_bounds__(256) embed_rows_bwd_kernel(const int64_t* __re
 extern "C" int mapdit_embed_rows_bwd(const int64_t* idx, const uint8_t* drop_mask, int64_t null_idx, const float* table,
                                      const float* g, float* dtable, int n, int d, float eps, void* stream) {
   MAPDIT_REQUIRE(idx && table && g && dtable && n > 0 && d > 0, "embed_rows_bwd: bad args");
-  embed_rows_bwd_kernel<<<n, 256, 0, (cudaStream_t)stream>>>(idx, drop_mask, null_idx, table, g, dtable, d, eps);
+  embed_rows_bwd_kernel<<<n, 256, 0, (cudaStream_t)stream>>>(idx, drop_mask, null_idx, table, g, dtable, d, eps, mapdit_variant());
   MAPDIT_LAUNCH_CHECK("embed_rows_bwd");
   return MAPDIT_OK;
 }
@@ -540,5 +547,72 @@ extern "C" int mapdit_axpby(const float* x, float* y, float a, int accumulate, i
   MAPDIT_REQUIRE(x && y && n > 0, "axpby: bad args");
   axpby_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, y, a, accumulate, n);
   MAPDIT_LAUNCH_CHECK("axpby");
+  return MAPDIT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// adaLN with LayerNorm (use_no_layernorm=False, UNPINNED): h = xh (1 + scale) + shift, xh = (x - mean) rstd.
+//   dshift = sum_t dh ; dscale = sum_t dh xh ; dxh = dh (1 + scale) ; dx = rstd (dxh - mean_c(dxh) - xh mean_c(dxh xh)) ; R (+)= dx
+// Kernel 1: one warp per row (dx into R).  Kernel 2: column strips per sample (dshift/dscale), deterministic.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) ln_modulate_bwd_rows_kernel(const T* __restrict__ dh, const T* __restrict__ x, T* R,
+                                                                   const float2* __restrict__ stats, const float* __restrict__ scale,
+                                                                   int64_t ldmod, int m, int d, int tokens, int accumulate) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= m) return;
+  const float2 st = stats[row];
+  const int64_t n = row / tokens;
+  const size_t off = (size_t)row * d;
+  float s1 = 0.f, s2 = 0.f;
+  for (int i = lane; i < d; i += 32) {
+    const float g = ld_act(dh + off + i) * (1.0f + scale[n * ldmod + i]);
+    const float xh = (ld_act(x + off + i) - st.x) * st.y;
+    s1 += g;
+    s2 = __fmaf_rn(g, xh, s2);
+  }
+  s1 = warp_sum(s1) / (float)d;
+  s2 = warp_sum(s2) / (float)d;
+  for (int i = lane; i < d; i += 32) {
+    const float g = ld_act(dh + off + i) * (1.0f + scale[n * ldmod + i]);
+    const float xh = (ld_act(x + off + i) - st.x) * st.y;
+    float dx = st.y * (g - s1 - xh * s2);
+    if (accumulate) dx += ld_act(R + off + i);
+    st_act(R + off + i, dx);
+  }
+}
+template <typename T>
+__global__ void __launch_bounds__(256) ln_modulate_bwd_cols_kernel(const T* __restrict__ dh, const T* __restrict__ x,
+                                                                   const float2* __restrict__ stats, float* __restrict__ dshift,
+                                                                   float* __restrict__ dscale, int64_t ldmod, int d, int tokens) {
+  const int n = blockIdx.y, c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= d) return;
+  float a = 0.f, b = 0.f;
+  for (int t = 0; t < tokens; ++t) {
+    const size_t row = (size_t)n * tokens + t;
+    const float2 st = stats[row];
+    const float g = ld_act(dh + row * d + c);
+    a += g;
+    b = __fmaf_rn(g, (ld_act(x + row * d + c) - st.x) * st.y, b);
+  }
+  dshift[n * ldmod + c] = a;
+  dscale[n * ldmod + c] = b;
+}
+extern "C" int mapdit_ln_modulate_bwd(const void* dh, const void* x, void* R, const float* stats, const float* scale, float* dshift,
+                                      float* dscale, int64_t ldmod, int n_samples, int d, int tokens, int accumulate, int dtype,
+                                      void* stream) {
+  MAPDIT_REQUIRE(dh && x && stats && scale && dshift && dscale && n_samples > 0 && d > 0 && tokens > 0, "ln_modulate_bwd: bad args");
+  const int m = n_samples * tokens;
+  cudaStream_t s = (cudaStream_t)stream;
+  dim3 gc((d + 255) / 256, n_samples);
+  if (dtype == MAPDIT_F32) {
+    if (R) ln_modulate_bwd_rows_kernel<float><<<(m + 7) / 8, 256, 0, s>>>((const float*)dh, (const float*)x, (float*)R, (const float2*)stats, scale, ldmod, m, d, tokens, accumulate);
+    ln_modulate_bwd_cols_kernel<float><<<gc, 256, 0, s>>>((const float*)dh, (const float*)x, (const float2*)stats, dshift, dscale, ldmod, d, tokens);
+  } else {
+    if (R) ln_modulate_bwd_rows_kernel<bf16><<<(m + 7) / 8, 256, 0, s>>>((const bf16*)dh, (const bf16*)x, (bf16*)R, (const float2*)stats, scale, ldmod, m, d, tokens, accumulate);
+    ln_modulate_bwd_cols_kernel<bf16><<<gc, 256, 0, s>>>((const bf16*)dh, (const bf16*)x, (const float2*)stats, dshift, dscale, ldmod, d, tokens);
+  }
+  MAPDIT_LAUNCH_CHECK("ln_modulate_bwd");
+  mapdit_count_launch(R ? 1 : 0);
   return MAPDIT_OK;
 }

@@ -9,6 +9,7 @@
 
 void mapdit_set_error(const char* fmt, ...);
 void mapdit_count_launch(int n = 1);
+int mapdit_variant();  // host: this thread's MAPDIT_VAR_* word (mapdit_set_variant), passed to kernels as a launch argument
 
 #define MAPDIT_REQUIRE(cond, ...)        \
   do {                                   \
@@ -59,6 +60,12 @@ __device__ __forceinline__ float modulate_f(float x, float shift, float scale, f
 }
 __device__ __forceinline__ float resid_f(float x, float gate, float y) { return lerp_t(x, gate * y, MP_RES_T) / MP_RES_DEN; }
 __device__ __forceinline__ float mp_silu_f(float x) { return (x / (1.0f + expf(-x))) / MP_SILU_DIV; }
+// README "--use-*" switches turned off (UNPINNED): plain residual / plain SiLU
+__device__ __forceinline__ float resid_v(float x, float gate, float y, int var) {
+  return (var & MAPDIT_VAR_PLAIN_RESID) ? __fmaf_rn(gate, y, x) : resid_f(x, gate, y);
+}
+__device__ __forceinline__ float mp_silu_v(float x, int var) { return (var & MAPDIT_VAR_PLAIN_SILU) ? x / (1.0f + expf(-x)) : mp_silu_f(x); }
+__device__ __forceinline__ float silu_div_v(int var) { return (var & MAPDIT_VAR_PLAIN_SILU) ? 1.0f : MP_SILU_DIV; }
 
 // 8 consecutive activations <-> registers (16-byte accesses for bf16, 2 x 16 bytes for fp32); p must be 16-byte aligned
 __device__ __forceinline__ void load8(const float* p, float (&f)[8]) {

@@ -20,6 +20,13 @@ void mapdit_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void mapdit_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+static thread_local int g_variant = 0;
+int mapdit_variant() { return g_variant; }
+extern "C" int mapdit_set_variant(int flags) {
+  int old = g_variant;
+  g_variant = flags;
+  return old;
+}
 
 extern "C" const char* mapdit_last_error(void) { return g_err; }
 extern "C" int mapdit_abi_version(void) { return 1; }
@@ -44,7 +51,15 @@ __global__ void __launch_bounds__(256) weight_norm_fwd_kernel(float* __restrict_
   }
   float nrm = sqrtf(block_sum(ss, red));
   float inv;
-  if (force) {
+  if (force < 0) {  // use_weight_normalization=False: the effective weight is the raw weight
+    inv = 1.0f;
+    for (int i = threadIdx.x; i < cols; i += blockDim.x) {
+      float e = row[i];
+      if (eff_f32) eff_f32[(size_t)r * cols + i] = e;
+      if (eff_bf16) eff_bf16[(size_t)r * cols + i] = __float2bfloat16_rn(e);
+      if (eff_bf16_t) eff_bf16_t[(size_t)i * ld_t + r] = __float2bfloat16_rn(e);
+    }
+  } else if (force) {
     // w <- w*sqrt(n)/(||w||+eps)  (src/utils.py:19-23), then eff is computed from the forced row
     const float sq = sqrtf((float)cols);
     const float den = nrm + eps;
@@ -75,9 +90,155 @@ __global__ void __launch_bounds__(256) weight_norm_fwd_kernel(float* __restrict_
   if (inv_norm && threadIdx.x == 0) inv_norm[r] = inv;
 }
 
+// Tiled flavour for the big block weights (cols % 4 == 0), two launches:
+//  (1) wn_norms_kernel: one warp per row, float4 loads, 4 loads in flight per lane -> {den, inv} per row into a scratch;
+//  (2) wn_apply_kernel: one CTA per 64x64 tile: float4 write-back / fp32 copy, 8-byte bf16 stores, and the transposed
+//      bf16 copy (the dgrad operand) through a shared-memory transpose so that it leaves as 32-byte row segments instead
+//      of scattered 2-byte stores.
+constexpr int WN_ROWS = 64, WN_TCOLS = 64, WN_PITCH = WN_TCOLS + 2;
+__global__ void __launch_bounds__(256) wn_norms_kernel(const float* __restrict__ w, int rows, int cols, float eps, int force,
+                                                       float2* __restrict__ scratch, float* __restrict__ inv_norm) {
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const float4* row4 = reinterpret_cast<const float4*>(w + (size_t)r * cols);
+  const int n4 = cols / 4;
+  const float sq = sqrtf((float)cols);
+  float ss = 0.f;
+#pragma unroll 4
+  for (int i = lane; i < n4; i += 32) {
+    const float4 v = row4[i];
+    ss = __fmaf_rn(v.x, v.x, ss);
+    ss = __fmaf_rn(v.y, v.y, ss);
+    ss = __fmaf_rn(v.z, v.z, ss);
+    ss = __fmaf_rn(v.w, v.w, ss);
+  }
+  const float nrm = sqrtf(warp_sum(ss));
+  float den = 1.f, inv;
+  if (force < 0) {
+    inv = 1.0f;
+  } else if (force) {
+    den = nrm + eps;
+    float ss2 = 0.f;
+#pragma unroll 4
+    for (int i = lane; i < n4; i += 32) {
+      const float4 v = row4[i];
+      const float a = (v.x * sq) / den, b = (v.y * sq) / den, c = (v.z * sq) / den, d = (v.w * sq) / den;
+      ss2 = __fmaf_rn(a, a, ss2);
+      ss2 = __fmaf_rn(b, b, ss2);
+      ss2 = __fmaf_rn(c, c, ss2);
+      ss2 = __fmaf_rn(d, d, ss2);
+    }
+    inv = 1.0f / (sqrtf(warp_sum(ss2)) + eps);
+  } else {
+    inv = 1.0f / (nrm + eps);
+  }
+  if (lane == 0) {
+    scratch[r] = make_float2(den, inv);
+    if (inv_norm) inv_norm[r] = inv;
+  }
+}
+
+__global__ void __launch_bounds__(256) wn_apply_kernel(float* __restrict__ w, int rows, int cols, int force,
+                                                       const float2* __restrict__ scratch, float* __restrict__ eff_f32,
+                                                       bf16* __restrict__ eff_bf16, bf16* __restrict__ eff_bf16_t, int64_t ld_t) {
+  __shared__ __align__(16) bf16 tile[WN_ROWS * WN_PITCH];
+  const int r0 = blockIdx.x * WN_ROWS, c0 = blockIdx.y * WN_TCOLS;
+  const float sq = sqrtf((float)cols);
+  const int tr = threadIdx.x >> 4, tc = (threadIdx.x & 15) * 4;  // 16 rows x 16 float4 per pass, 4 passes
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int rr = tr + 16 * k, r = r0 + rr, c = c0 + tc;
+    if (r < rows && c < cols) {
+      const size_t off = (size_t)r * cols + c;
+      const float2 di = scratch[r];
+      float4 v = *reinterpret_cast<const float4*>(w + off);
+      if (force > 0) {
+        v.x = (v.x * sq) / di.x;
+        v.y = (v.y * sq) / di.x;
+        v.z = (v.z * sq) / di.x;
+        v.w = (v.w * sq) / di.x;
+        *reinterpret_cast<float4*>(w + off) = v;
+      }
+      const float4 e = make_float4(v.x * di.y, v.y * di.y, v.z * di.y, v.w * di.y);
+      if (eff_f32) *reinterpret_cast<float4*>(eff_f32 + off) = e;
+      const __nv_bfloat162 lo = __floats2bfloat162_rn(e.x, e.y), hi = __floats2bfloat162_rn(e.z, e.w);
+      if (eff_bf16) {
+        uint2 u;
+        u.x = *reinterpret_cast<const uint32_t*>(&lo);
+        u.y = *reinterpret_cast<const uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(eff_bf16 + off) = u;
+      }
+      if (eff_bf16_t) {
+        __nv_bfloat162* t2 = reinterpret_cast<__nv_bfloat162*>(tile + rr * WN_PITCH + tc);
+        t2[0] = lo;
+        t2[1] = hi;
+      }
+    }
+  }
+  if (eff_bf16_t) {
+    __syncthreads();
+    const bool t_vec = r0 + WN_ROWS <= rows && (ld_t % 8) == 0 && ((reinterpret_cast<uintptr_t>(eff_bf16_t) & 15) == 0);
+    const int c = threadIdx.x >> 2, seg = (threadIdx.x & 3) * 16;  // output row c0+c, source rows seg..seg+15
+    if (c0 + c < cols) {
+      bf16* dst = eff_bf16_t + (size_t)(c0 + c) * ld_t + r0 + seg;
+      if (t_vec) {
+        uint32_t pk[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          __nv_bfloat162 b2;
+          b2.x = tile[(seg + 2 * j) * WN_PITCH + c];
+          b2.y = tile[(seg + 2 * j + 1) * WN_PITCH + c];
+          pk[j] = *reinterpret_cast<const uint32_t*>(&b2);
+        }
+        reinterpret_cast<uint4*>(dst)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        reinterpret_cast<uint4*>(dst)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      } else {
+        for (int j = 0; j < 16; ++j)
+          if (r0 + seg + j < rows) dst[j] = tile[(seg + j) * WN_PITCH + c];
+      }
+    }
+  }
+}
+
+// per-row {den, inv} scratch of the tiled path: grown on demand outside stream capture, one per device
+static float2* wn_scratch(int rows, cudaStream_t stream) {
+  static float2* buf[16] = {};
+  static int cap[16] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 16) return nullptr;
+  if (cap[dev] >= rows) return buf[dev];
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) return nullptr;
+  const int want = rows < 65536 ? 65536 : rows;
+  float2* p = nullptr;
+  if (cudaMalloc(&p, (size_t)want * sizeof(float2)) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  // the old buffer (if any) may still be in use by queued kernels: leak it (happens at most a few times per process)
+  buf[dev] = p;
+  cap[dev] = want;
+  return p;
+}
+
 extern "C" int mapdit_weight_norm_fwd(float* w, int rows, int cols, float eps, int force, float* eff_f32, void* eff_bf16,
                                       void* eff_bf16_t, int64_t ld_t, float* inv_norm, void* stream) {
   MAPDIT_REQUIRE(w && rows > 0 && cols > 0, "weight_norm_fwd: bad args");
+  const bool aligned = ((reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(eff_f32)) & 15) == 0 &&
+                       (reinterpret_cast<uintptr_t>(eff_bf16) & 7) == 0;
+  float2* scratch = (cols % 4 == 0 && rows >= 16 && aligned) ? wn_scratch(rows, (cudaStream_t)stream) : nullptr;
+  if (scratch) {
+    wn_norms_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(w, rows, cols, eps, force, scratch, inv_norm);
+    MAPDIT_LAUNCH_CHECK("weight_norm_fwd(norms)");
+    if (force > 0 || eff_f32 || eff_bf16 || eff_bf16_t) {
+      dim3 grid((rows + WN_ROWS - 1) / WN_ROWS, (cols + WN_TCOLS - 1) / WN_TCOLS);
+      wn_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w, rows, cols, force, scratch, eff_f32, (bf16*)eff_bf16, (bf16*)eff_bf16_t,
+                                                             ld_t > 0 ? ld_t : rows);
+      MAPDIT_LAUNCH_CHECK("weight_norm_fwd(apply)");
+    }
+    return MAPDIT_OK;
+  }
   weight_norm_fwd_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(w, cols, eps, force, eff_f32, (bf16*)eff_bf16,
                                                                   (bf16*)eff_bf16_t, inv_norm, rows, ld_t > 0 ? ld_t : rows);
   MAPDIT_LAUNCH_CHECK("weight_norm_fwd");
@@ -105,9 +266,57 @@ __global__ void __launch_bounds__(256) weight_norm_bwd_kernel(const float* __res
   }
 }
 
+// float4 flavour, one warp per row (cols % 4 == 0)
+__global__ void __launch_bounds__(256) weight_norm_bwd_vec_kernel(const float* __restrict__ v, const float* __restrict__ g,
+                                                                  float* __restrict__ gv, int rows, int cols, float eps,
+                                                                  int accumulate) {
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const size_t off = (size_t)r * cols;
+  const float4* v4 = reinterpret_cast<const float4*>(v + off);
+  const float4* g4 = reinterpret_cast<const float4*>(g + off);
+  float4* o4 = reinterpret_cast<float4*>(gv + off);
+  float ss = 0.f, dot = 0.f;
+#pragma unroll 4
+  for (int i = lane; i < cols / 4; i += 32) {
+    const float4 a = v4[i], b = g4[i];
+    ss = __fmaf_rn(a.x, a.x, ss);
+    ss = __fmaf_rn(a.y, a.y, ss);
+    ss = __fmaf_rn(a.z, a.z, ss);
+    ss = __fmaf_rn(a.w, a.w, ss);
+    dot = __fmaf_rn(a.x, b.x, dot);
+    dot = __fmaf_rn(a.y, b.y, dot);
+    dot = __fmaf_rn(a.z, b.z, dot);
+    dot = __fmaf_rn(a.w, b.w, dot);
+  }
+  const float rn = sqrtf(warp_sum(ss));
+  dot = warp_sum(dot);
+  const float inv = 1.0f / (rn + eps);
+  const float coef = dot / (fmaxf(rn, 1e-30f) * (rn + eps));
+#pragma unroll 4
+  for (int i = lane; i < cols / 4; i += 32) {
+    const float4 a = v4[i], b = g4[i];
+    float4 o = make_float4((b.x - a.x * coef) * inv, (b.y - a.y * coef) * inv, (b.z - a.z * coef) * inv, (b.w - a.w * coef) * inv);
+    if (accumulate) {
+      const float4 p = o4[i];
+      o.x += p.x;
+      o.y += p.y;
+      o.z += p.z;
+      o.w += p.w;
+    }
+    o4[i] = o;
+  }
+}
+
 extern "C" int mapdit_weight_norm_bwd(const float* v, const float* g_eff, float* grad_v, int rows, int cols, float eps,
                                       int accumulate, void* stream) {
   MAPDIT_REQUIRE(v && g_eff && grad_v && rows > 0 && cols > 0, "weight_norm_bwd: bad args");
+  const bool al16 = ((reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(g_eff) | reinterpret_cast<uintptr_t>(grad_v)) & 15) == 0;
+  if (cols % 4 == 0 && cols >= 128 && al16) {
+    weight_norm_bwd_vec_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(v, g_eff, grad_v, rows, cols, eps, accumulate);
+    MAPDIT_LAUNCH_CHECK("weight_norm_bwd");
+    return MAPDIT_OK;
+  }
   weight_norm_bwd_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(v, g_eff, grad_v, cols, eps, accumulate);
   MAPDIT_LAUNCH_CHECK("weight_norm_bwd");
   return MAPDIT_OK;
@@ -145,12 +354,12 @@ extern "C" int mapdit_modulate_fwd(const void* x, void* h, const float* shift, c
 
 template <typename T>
 __global__ void resid_kernel(const T* __restrict__ x, const T* __restrict__ y, T* __restrict__ xo, const float* __restrict__ gate,
-                             int64_t ldmod, int64_t total, int d, int tokens) {
+                             int64_t ldmod, int64_t total, int d, int tokens, int var) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t row = i / d;
     int col = (int)(i - row * d);
     int64_t n = row / tokens;
-    st_act(xo + i, resid_f(ld_act(x + i), gate[n * ldmod + col], ld_act(y + i)));
+    st_act(xo + i, resid_v(ld_act(x + i), gate[n * ldmod + col], ld_act(y + i), var));
   }
 }
 
@@ -160,17 +369,17 @@ extern "C" int mapdit_resid_fwd(const void* x, const void* y, void* xout, const 
   int64_t total = (int64_t)m * d;
   int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
   if (dtype == MAPDIT_F32)
-    resid_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x, (const float*)y, (float*)xout, gate, ldmod, total, d, tokens);
+    resid_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x, (const float*)y, (float*)xout, gate, ldmod, total, d, tokens, mapdit_variant());
   else
-    resid_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)y, (bf16*)xout, gate, ldmod, total, d, tokens);
+    resid_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)y, (bf16*)xout, gate, ldmod, total, d, tokens, mapdit_variant());
   MAPDIT_LAUNCH_CHECK("resid_fwd");
   return MAPDIT_OK;
 }
 
 template <typename TI, typename TO>
-__global__ void mp_silu_kernel(const TI* __restrict__ x, TO* __restrict__ y, int64_t n) {
+__global__ void mp_silu_kernel(const TI* __restrict__ x, TO* __restrict__ y, int64_t n, int var) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    st_act(y + i, mp_silu_f(ld_act(x + i)));
+    st_act(y + i, mp_silu_v(ld_act(x + i), var));
 }
 template <typename TI, typename TO>
 __global__ void cast_kernel(const TI* __restrict__ x, TO* __restrict__ y, int64_t n) {
@@ -187,10 +396,10 @@ extern "C" int mapdit_mp_silu_fwd(const void* x, void* y, int64_t n, int in_dtyp
   MAPDIT_REQUIRE(x && y && n > 0, "mp_silu_fwd: bad args");
   cudaStream_t s = (cudaStream_t)stream;
   int grid = ew_grid(n);
-  if (in_dtype == MAPDIT_F32 && out_dtype == MAPDIT_F32) mp_silu_kernel<float, float><<<grid, 256, 0, s>>>((const float*)x, (float*)y, n);
-  else if (in_dtype == MAPDIT_F32) mp_silu_kernel<float, bf16><<<grid, 256, 0, s>>>((const float*)x, (bf16*)y, n);
-  else if (out_dtype == MAPDIT_F32) mp_silu_kernel<bf16, float><<<grid, 256, 0, s>>>((const bf16*)x, (float*)y, n);
-  else mp_silu_kernel<bf16, bf16><<<grid, 256, 0, s>>>((const bf16*)x, (bf16*)y, n);
+  if (in_dtype == MAPDIT_F32 && out_dtype == MAPDIT_F32) mp_silu_kernel<float, float><<<grid, 256, 0, s>>>((const float*)x, (float*)y, n, mapdit_variant());
+  else if (in_dtype == MAPDIT_F32) mp_silu_kernel<float, bf16><<<grid, 256, 0, s>>>((const float*)x, (bf16*)y, n, mapdit_variant());
+  else if (out_dtype == MAPDIT_F32) mp_silu_kernel<bf16, float><<<grid, 256, 0, s>>>((const bf16*)x, (float*)y, n, mapdit_variant());
+  else mp_silu_kernel<bf16, bf16><<<grid, 256, 0, s>>>((const bf16*)x, (bf16*)y, n, mapdit_variant());
   MAPDIT_LAUNCH_CHECK("mp_silu_fwd");
   return MAPDIT_OK;
 }
@@ -255,7 +464,7 @@ __global__ void __launch_bounds__(256) patch_embed_kernel(const float* __restric
                                                           const float* __restrict__ pos, T* __restrict__ x0, T* __restrict__ h,
                                                           const float* __restrict__ shift, const float* __restrict__ scale,
                                                           const float* __restrict__ gain, int64_t ldmod, int64_t m_total, int C,
-                                                          int S, int p, int d) {
+                                                          int S, int p, int d, int var) {
   extern __shared__ float sp[];  // [16][K1]
   const int g = S / p, T_ = g * g, K = p * p * C, K1 = K + 1;
   const int64_t tok0 = (int64_t)blockIdx.x * 16;
@@ -295,7 +504,8 @@ __global__ void __launch_bounds__(256) patch_embed_kernel(const float* __restric
     if (tok >= m_total) break;
     int64_t n = tok / T_;
     int tt = (int)(tok - n * T_);
-    float v = lerp_t(acc[j], pos[(size_t)tt * d + col], 0.5f) / MP_HALF_DEN;
+    const float pv = pos[(size_t)tt * d + col];
+    float v = (var & MAPDIT_VAR_PLAIN_POS) ? acc[j] + pv : lerp_t(acc[j], pv, 0.5f) / MP_HALF_DEN;
     st_act(x0 + tok * d + col, v);
     if (h) {
       // modulate sees the value as stored in the residual stream
@@ -315,9 +525,9 @@ extern "C" int mapdit_patch_embed(const float* x, const float* wx_eff, const flo
   size_t smem = (size_t)16 * K1 * sizeof(float);
   dim3 grid((unsigned)((m_total + 15) / 16), (unsigned)((d + 255) / 256));
   if (dtype == MAPDIT_F32)
-    patch_embed_kernel<float><<<grid, 256, smem, (cudaStream_t)stream>>>(x, wx_eff, pos, (float*)x0, (float*)h, shift, scale, gain, ldmod, m_total, channels, input_size, patch, d);
+    patch_embed_kernel<float><<<grid, 256, smem, (cudaStream_t)stream>>>(x, wx_eff, pos, (float*)x0, (float*)h, shift, scale, gain, ldmod, m_total, channels, input_size, patch, d, mapdit_variant());
   else
-    patch_embed_kernel<bf16><<<grid, 256, smem, (cudaStream_t)stream>>>(x, wx_eff, pos, (bf16*)x0, (bf16*)h, shift, scale, gain, ldmod, m_total, channels, input_size, patch, d);
+    patch_embed_kernel<bf16><<<grid, 256, smem, (cudaStream_t)stream>>>(x, wx_eff, pos, (bf16*)x0, (bf16*)h, shift, scale, gain, ldmod, m_total, channels, input_size, patch, d, mapdit_variant());
   MAPDIT_LAUNCH_CHECK("patch_embed");
   return MAPDIT_OK;
 }
@@ -341,14 +551,74 @@ extern "C" int mapdit_fourier(const int64_t* t, const float* scale, const float*
   return MAPDIT_OK;
 }
 
+// Sinusoidal timestep features of the vanilla DiT (use_mp_embedding=False; UNPINNED, Peebles & Xie timestep_embedding):
+// e[n, j] = cos(t f_j), e[n, half + j] = sin(t f_j), f_j = exp(-ln(max_period) j / half)
+__global__ void timestep_sincos_kernel(const int64_t* __restrict__ t, float* __restrict__ e, int n, int dim, float max_period) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int half = dim / 2;
+  if (i >= n * half) return;
+  int r = i / half, j = i - r * half;
+  const float f = expf(-logf(max_period) * (float)j / (float)half);
+  const float arg = __fmul_rn((float)t[r], f);
+  e[(size_t)r * dim + j] = cosf(arg);
+  e[(size_t)r * dim + half + j] = sinf(arg);
+}
+extern "C" int mapdit_timestep_sincos(const int64_t* t, float* e, int n, int dim, float max_period, void* stream) {
+  MAPDIT_REQUIRE(t && e && n > 0 && dim > 0 && dim % 2 == 0, "timestep_sincos: bad args");
+  timestep_sincos_kernel<<<(n * (dim / 2) + 255) / 256, 256, 0, (cudaStream_t)stream>>>(t, e, n, dim, max_period);
+  MAPDIT_LAUNCH_CHECK("timestep_sincos");
+  return MAPDIT_OK;
+}
+
+// adaLN with LayerNorm (use_no_layernorm=False; UNPINNED, vanilla DiT block): h = LN(x) (1 + scale) + shift, LN without
+// affine, eps 1e-6, biased variance.  One warp per token row; stats[row] = {mean, rstd} (nullable) for the backward.
+template <typename T>
+__global__ void __launch_bounds__(256) ln_modulate_kernel(const T* __restrict__ x, T* __restrict__ h, const float* __restrict__ shift,
+                                                          const float* __restrict__ scale, float2* __restrict__ stats, int64_t ldmod,
+                                                          int m, int d, int tokens) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= m) return;
+  const T* xr = x + (size_t)row * d;
+  float s = 0.f;
+  for (int i = lane; i < d; i += 32) s += ld_act(xr + i);
+  const float mean = warp_sum(s) / (float)d;
+  float v = 0.f;
+  for (int i = lane; i < d; i += 32) {
+    const float c = ld_act(xr + i) - mean;
+    v = __fmaf_rn(c, c, v);
+  }
+  const float rstd = rsqrtf(warp_sum(v) / (float)d + 1e-6f);
+  if (stats && lane == 0) stats[row] = make_float2(mean, rstd);
+  const int64_t n = row / tokens;
+  for (int i = lane; i < d; i += 32) {
+    const float xh = (ld_act(xr + i) - mean) * rstd;
+    st_act(h + (size_t)row * d + i, __fmaf_rn(xh, 1.0f + scale[n * ldmod + i], shift[n * ldmod + i]));
+  }
+}
+extern "C" int mapdit_ln_modulate_fwd(const void* x, void* h, const float* shift, const float* scale, float* stats, int64_t ldmod,
+                                      int m, int d, int tokens, int dtype, void* stream) {
+  MAPDIT_REQUIRE(x && h && shift && scale && m > 0 && d > 0 && tokens > 0, "ln_modulate_fwd: bad args");
+  const int grid = (m + 7) / 8;
+  if (dtype == MAPDIT_F32)
+    ln_modulate_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x, (float*)h, shift, scale, (float2*)stats, ldmod, m, d, tokens);
+  else
+    ln_modulate_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)h, shift, scale, (float2*)stats, ldmod, m, d, tokens);
+  MAPDIT_LAUNCH_CHECK("ln_modulate_fwd");
+  return MAPDIT_OK;
+}
+
 __global__ void __launch_bounds__(256) embed_rows_kernel(const int64_t* __restrict__ idx, const uint8_t* __restrict__ drop,
                                                          int64_t null_idx, const float* __restrict__ table, float* __restrict__ out,
-                                                         int d, float eps) {
+                                                         int d, float eps, int var) {
   __shared__ float red[32];
   int n = blockIdx.x;
   int64_t id = idx[n];
   if (drop && drop[n]) id = null_idx;
   const float* row = table + id * d;
+  if (var & MAPDIT_VAR_PLAIN_EMBED) {  // nn.Embedding: plain gather
+    for (int i = threadIdx.x; i < d; i += blockDim.x) out[(size_t)n * d + i] = row[i];
+    return;
+  }
   float ss = 0.f;
   for (int i = threadIdx.x; i < d; i += blockDim.x) ss = __fmaf_rn(row[i], row[i], ss);
   float nrm = sqrtf(block_sum(ss, red));
@@ -358,24 +628,24 @@ __global__ void __launch_bounds__(256) embed_rows_kernel(const int64_t* __restri
 extern "C" int mapdit_embed_rows(const int64_t* idx, const uint8_t* drop_mask, int64_t null_idx, const float* table, float* out,
                                  int n, int d, float eps, void* stream) {
   MAPDIT_REQUIRE(idx && table && out && n > 0 && d > 0, "embed_rows: bad args");
-  embed_rows_kernel<<<n, 256, 0, (cudaStream_t)stream>>>(idx, drop_mask, null_idx, table, out, d, eps);
+  embed_rows_kernel<<<n, 256, 0, (cudaStream_t)stream>>>(idx, drop_mask, null_idx, table, out, d, eps, mapdit_variant());
   MAPDIT_LAUNCH_CHECK("embed_rows");
   return MAPDIT_OK;
 }
 
 __global__ void cond_combine_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ c,
-                                    float* __restrict__ cs32, bf16* __restrict__ cs16, int64_t n) {
+                                    float* __restrict__ cs32, bf16* __restrict__ cs16, int64_t n, int var) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  float v = lerp_t(a[i], b[i], 0.5f) / MP_HALF_DEN;
+  float v = (var & MAPDIT_VAR_PLAIN_EMBED) ? a[i] + b[i] : lerp_t(a[i], b[i], 0.5f) / MP_HALF_DEN;
   if (c) c[i] = v;
-  float s = mp_silu_f(v);
+  float s = mp_silu_v(v, var);
   if (cs32) cs32[i] = s;
   if (cs16) cs16[i] = __float2bfloat16_rn(s);
 }
 extern "C" int mapdit_cond_combine(const float* a, const float* b, float* c, float* cs_f32, void* cs_bf16, int64_t n, void* stream) {
   MAPDIT_REQUIRE(a && b && n > 0, "cond_combine: bad args");
-  cond_combine_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a, b, c, cs_f32, (bf16*)cs_bf16, n);
+  cond_combine_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a, b, c, cs_f32, (bf16*)cs_bf16, n, mapdit_variant());
   MAPDIT_LAUNCH_CHECK("cond_combine");
   return MAPDIT_OK;
 }

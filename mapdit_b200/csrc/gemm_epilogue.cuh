@@ -26,6 +26,7 @@ struct EpiParams {
   long long ldo, ldmod;
   int M, N, tokens, qk_cols, epilogue, out_f32;
   float eps;
+  int variant;  // MAPDIT_VAR_* word of the launching thread
 };
 
 // TMA store descriptors of the (up to) three bf16 [M, N] outputs: out, out2, aux
@@ -33,7 +34,7 @@ struct alignas(64) EpiTmaps {
   CUtensorMap out, out2, aux;
 };
 
-__device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)) * (1.0f / MP_SILU_DIV); }
+__device__ __forceinline__ float silu_fast(float x, float mul) { return __fdividef(x, 1.0f + __expf(-x)) * mul; }
 
 struct Stager {
   uint8_t* base;  // this warp's 4 KB
@@ -109,6 +110,8 @@ __device__ __forceinline__ void run_tile(const EpiParams& ep, const EpiTmaps& tm
     for (int g = 0; g < 4; ++g) pre[g] = (row_ok && g * 8 < nvalid) ? src[g] : make_uint4(0, 0, 0, 0);
   };
   if (reads_resid && half * 32 < BN) prefetch(half * 32);
+  const float silu_mul = (ep.variant & MAPDIT_VAR_PLAIN_SILU) ? 1.0f : 1.0f / MP_SILU_DIV;
+  const bool plain_res = ep.variant & MAPDIT_VAR_PLAIN_RESID;
   wait_acc();
 
   if (ep.epilogue == MAPDIT_EPI_QKNORM) {
@@ -177,13 +180,13 @@ __device__ __forceinline__ void run_tile(const EpiParams& ep, const EpiTmaps& tm
     } else if (ep.epilogue == MAPDIT_EPI_MPSILU) {
       if (ep.out2) st.store(&tm.out2, f, col);  // pre-activation for the backward
 #pragma unroll
-      for (int j = 0; j < 32; ++j) f[j] = silu_fast(f[j]);
+      for (int j = 0; j < 32; ++j) f[j] = silu_fast(f[j], silu_mul);
       st.store(&tm.out, f, col);
     } else if (ep.epilogue == MAPDIT_EPI_SILU_BWD) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const float sg = __fdividef(1.0f, 1.0f + __expf(-xo[j]));
-        f[j] *= sg * fmaf(xo[j], 1.0f - sg, 1.0f) * (1.0f / MP_SILU_DIV);
+        f[j] *= sg * fmaf(xo[j], 1.0f - sg, 1.0f) * silu_mul;
       }
       st.store(&tm.out, f, col);
     } else {  // RESID / RESID_MOD
@@ -191,7 +194,8 @@ __device__ __forceinline__ void run_tile(const EpiParams& ep, const EpiTmaps& tm
       if (ep.aux) st.store(&tm.aux, f, col);  // raw branch output, needed for d(gate)
       load_row32_f32(ep.gate + sample * ep.ldmod + col, gt, row_ok ? nvalid : 0);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) f[j] = fmaf(MP_RES_T, gt[j] * f[j] - xo[j], xo[j]) * (1.0f / MP_RES_DEN);
+      for (int j = 0; j < 32; ++j)
+        f[j] = plain_res ? fmaf(gt[j], f[j], xo[j]) : fmaf(MP_RES_T, gt[j] * f[j] - xo[j], xo[j]) * (1.0f / MP_RES_DEN);
       st.store(&tm.out, f, col);
       if (ep.epilogue == MAPDIT_EPI_RESID_MOD) {
         load_row32_f32(ep.shift + sample * ep.ldmod + col, xo, row_ok ? nvalid : 0);

@@ -259,7 +259,7 @@ extern "C" int mapdit_gemm_bf16(const mapdit_gemm_args* g, void* stream) {
   EpiParams ep;
   ep.out = g->out; ep.out2 = g->out2; ep.resid = g->resid; ep.gate = g->gate; ep.shift = g->shift; ep.scale = g->scale;
   ep.gain = g->gain; ep.aux = g->aux; ep.ldo = g->ldo; ep.ldmod = g->ldmod; ep.M = g->m; ep.N = g->n; ep.tokens = g->tokens > 0 ? g->tokens : 1;
-  ep.qk_cols = g->qk_cols; ep.epilogue = epi; ep.out_f32 = (g->out_dtype == MAPDIT_F32); ep.eps = g->eps;
+  ep.qk_cols = g->qk_cols; ep.epilogue = epi; ep.out_f32 = (g->out_dtype == MAPDIT_F32); ep.eps = g->eps; ep.variant = mapdit_variant();
 
   const int sms = num_sms_cached();
   cudaStream_t s = (cudaStream_t)stream;

@@ -155,12 +155,14 @@ def _sincos_1d(dim, pos):
     return np.concatenate([np.sin(out), np.cos(out)], axis=1)
 
 
-def sincos_pos_embed(dim, grid):
-    """constant table of src/pos_embed.py:4-61, row-normalised as in src/dit.py:45-47."""
+def sincos_pos_embed(dim, grid, normalized=True):
+    """constant table of src/pos_embed.py:4-61, row-normalised as in src/dit.py:45-47 (raw with use_mp_pos_enc=False)."""
     coords = np.arange(grid, dtype=np.float32)
     mesh = np.stack(np.meshgrid(coords, coords), axis=0).reshape(2, 1, grid, grid)
     emb = np.concatenate([_sincos_1d(dim // 2, mesh[0]), _sincos_1d(dim // 2, mesh[1])], axis=1)
     t = torch.from_numpy(emb).float().unsqueeze(0)
+    if not normalized:
+        return t
     norm = torch.linalg.vector_norm(t, dim=-1, keepdim=True)
     return t * math.sqrt(dim) / (norm + 1e-4)
 
@@ -175,15 +177,16 @@ class DiT(nn.Module):
                  class_dropout_prob=0.1, num_classes=1000, learn_sigma=True, compute_dtype="bf16", modulation="adaln",
                  **flags):
         super().__init__()
-        for k, v in flags.items():
+        for k in flags:
             if k not in MAP_FLAGS:
                 raise TypeError(f"DiT got an unexpected keyword argument '{k}'")
-            if not v:
-                raise NotImplementedError(
-                    f"{k}=False: the reference snapshot hard-codes every MaP switch on and ships no 'off' branch "
-                    "(SURVEY.md §0.1); only the pinned behaviour has CUDA kernels in this round")
+        # README.md:59-66 switches.  "On" is the snapshot's hard-coded behaviour (pinned by the reference); the "off"
+        # branches are this repo's restatement of the vanilla DiT ops (UNPINNED), same parameters/keys.
+        self.flags = {k: bool(flags.get(k, True)) for k in MAP_FLAGS}
         if modulation not in MOD_LAYOUTS:
             raise ValueError(f"modulation must be one of {sorted(MOD_LAYOUTS)}")
+        if not self.flags["use_no_layernorm"] and modulation != "adaln":
+            raise NotImplementedError("use_no_layernorm=False (LayerNorm + adaLN) is only defined for modulation='adaln'")
         self.modulation = modulation
         if not learn_sigma:
             raise NotImplementedError("learn_sigma=False raises TypeError in the reference (src/blocks/final_layer.py:60-61)")
@@ -202,10 +205,24 @@ class DiT(nn.Module):
         self.x_embedder = MPLinear(patch_size * patch_size * in_channels + 1, hidden_size)
         self.t_embedder = TimestepEmbedder(hidden_size)
         self.y_embedder = LabelEmbedder(num_classes, hidden_size, class_dropout_prob)
-        self.register_buffer("pos_embed", sincos_pos_embed(hidden_size, input_size // patch_size))
+        self.register_buffer("pos_embed", sincos_pos_embed(hidden_size, input_size // patch_size,
+                                                           normalized=self.flags["use_mp_pos_enc"]))
         self.blocks = nn.ModuleList([DiTBlock(hidden_size, num_heads, mlp_ratio=mlp_ratio, modulation=modulation) for _ in range(depth)])
         self.final_layer = FinalLayer(hidden_size, patch_size, self.out_channels)
+        if not self.flags["use_weight_normalization"]:
+            # without weight normalisation N(0,1) weights would scale activations by sqrt(fan_in) per layer
+            with torch.no_grad():
+                for name, p in self.named_parameters():
+                    if p.dim() == 2 and name != "y_embedder.embedding.weight":
+                        p.mul_(1.0 / math.sqrt(p.shape[1]))
         self._engine = None
+
+    @property
+    def variant(self) -> int:
+        """MAPDIT_VAR_* word (include/mapdit.h) of this model's switched-off MaP flags"""
+        f = self.flags
+        return ((0 if f["use_mp_residual"] else 1) | (0 if f["use_mp_silu"] else 2) | (0 if f["use_mp_pos_enc"] else 4)
+                | (0 if f["use_mp_embedding"] else 8) | (0 if f["use_cosine_attention"] else 16))
 
     # the engine holds workspaces / CUDA graphs: never deep-copied or serialised with the module
     def __deepcopy__(self, memo):

@@ -88,7 +88,9 @@ class Engine:
             W.w2 = [torch.empty(D, Hm, **wd) for _ in range(L)]
             W.wfl = torch.empty_like(m.final_layer.linear.weight, **wd)
             self._w[mode] = W
-        force = bool(train)
+        fl = m.flags
+        # 1 = forced write-back + normalise (train), 0 = normalise only, -1 = raw weights (use_weight_normalization=False)
+        force = -1 if not fl["use_weight_normalization"] else int(bool(train) and fl["use_forced_weight_normalization"])
         want_t = bool(train) and mode == "bf16"  # transposed bf16 copies feed the dgrad GEMMs
         if want_t and not hasattr(W, "wqkv_t"):
             wd = dict(device=dev, dtype=wdt)
@@ -110,7 +112,7 @@ class Engine:
         norm(m.x_embedder.weight, W.wx)
         norm(m.t_embedder.mlp.net[0].weight, W.wt1)
         norm(m.t_embedder.mlp.net[2].weight, W.wt2)
-        if force:  # the embedding table is normalised in place too (src/basic/mp_embedding.py:16-19)
+        if force > 0 and fl["use_mp_embedding"]:  # the embedding table is normalised in place too (src/basic/mp_embedding.py:16-19)
             ops.weight_norm_fwd(m.y_embedder.embedding.weight.data, force=True)
         tget = (lambda name, i: getattr(W, name)[i]) if want_t else (lambda name, i: None)
         for i, b in enumerate(m.blocks):
@@ -167,6 +169,13 @@ class Engine:
         return self._forward_impl(x, t, y, train, drop_mask, mode, save=None)
 
     def _forward_impl(self, x, t, y, train, drop_mask, mode, save):
+        prev = ops.set_variant(self.m.variant)
+        try:
+            return self._forward_body(x, t, y, train, drop_mask, mode, save)
+        finally:
+            ops.set_variant(prev)
+
+    def _forward_body(self, x, t, y, train, drop_mask, mode, save):
         m = self.m
         N = x.shape[0]
         dev = x.device
@@ -181,7 +190,11 @@ class Engine:
         bf = mode == "bf16"
 
         # ---- conditioning (fp32; src/dit.py:86-88, timestep_embedder.py:18-43, label_embedder.py:29-34)
-        ops.fourier(t, m.t_embedder.embedding.scale, m.t_embedder.embedding.shift, ws["e"])
+        fl = m.flags
+        if fl["use_mp_embedding"]:
+            ops.fourier(t, m.t_embedder.embedding.scale, m.t_embedder.embedding.shift, ws["e"])
+        else:
+            ops.timestep_sincos(t, ws["e"])
         ops.gemm_f32(ws["e"], W.wt1, out=ws["t1"])
         ops.mp_silu(ws["t1"], ws["t1s"])
         ops.gemm_f32(ws["t1s"], W.wt2, out=ws["temb"])
@@ -203,6 +216,8 @@ class Engine:
         mods = ws["mods"]
         lay = self.layout
         adaln = m.modulation == "adaln"
+        ln = not fl["use_no_layernorm"]  # vanilla adaLN: LayerNorm then x(1+scale)+shift (UNPINNED)
+        cosine = fl["use_cosine_attention"]
         fbase = L * lay["width"]  # final layer: [shift | scale]
 
         def mod(i, name):  # column slice `name` of block i's modulation output
@@ -211,7 +226,9 @@ class Engine:
         def modulate_block(i, branch, src, dst):
             """h = block-i modulation of the residual stream for branch 'a' (attention) / 'm' (MLP), standalone kernel"""
             gain = (blk[i].gain_msa if branch == "a" else blk[i].gain_mlp).data
-            if adaln:
+            if ln:
+                ops.ln_modulate(src, dst, mod(i, "shift_" + branch), mod(i, "scale_" + branch), None, ld, T)
+            elif adaln:
                 ops.modulate(src, dst, mod(i, "shift_" + branch), mod(i, "scale_" + branch), gain, ld, T)
             else:
                 sc = mod(i, "scale_" + branch) if ("scale_" + branch) in lay else None
@@ -220,14 +237,26 @@ class Engine:
         def modulate_next(i, src, dst):
             if i + 1 < L:
                 modulate_block(i + 1, "a", src, dst)
+            elif ln:
+                ops.ln_modulate(src, dst, mods[:, fbase:], mods[:, fbase + D:], None, ld, T)
             else:
                 ops.modulate(src, dst, mods[:, fbase:], mods[:, fbase + D:], f.gain_mod.data, ld, T)
 
+        def qkv_proj(i, src):
+            """qkv GEMM (+ q/k L2 normalisation: fused epilogue for head_dim 64, standalone kernel otherwise)"""
+            if cosine and hd == 64:
+                ops.gemm_bf16(src, W.wqkv[i], ws["qkv"], epilogue=_lib.EPI_QKNORM, tokens=T, head_dim=hd, qk_cols=2 * D)
+            else:
+                ops.gemm_bf16(src, W.wqkv[i], ws["qkv"])
+                if cosine:
+                    ops.qk_normalize(ws["qkv"], D, hd)
+
         blk = m.blocks
-        fused = bf and adaln  # modulate fused into the residual GEMM epilogues
+        # modulate fused into the residual GEMM epilogues (the pinned all-flags-on configuration)
+        fused = bf and adaln and not ln and cosine and hd == 64
         # ---- patch embed + first modulate (src/dit.py:81-84)
         X, Hb = ws["x"], ws["h"]
-        if adaln:
+        if adaln and not ln:
             ops.patch_embed(x, W.wx, m.pos_embed, X, Hb, mod(0, "shift_a"), mod(0, "scale_a"), blk[0].gain_msa.data, ld, m.patch_size)
         else:
             ops.patch_embed(x, W.wx, m.pos_embed, X, None, None, None, None, ld, m.patch_size)
@@ -243,8 +272,8 @@ class Engine:
                 ops.gemm_bf16(Hb, W.w1[i], ws["u"], epilogue=_lib.EPI_MPSILU)
                 ops.gemm_bf16(ws["u"], W.w2[i], X, epilogue=_lib.EPI_RESID_MOD, out2=Hb, resid=X, gate=mod(i, "gate_m"),
                               shift=nxt_shift, scale=nxt_scale, gain=nxt_gain, ldmod=ld, tokens=T)
-            elif bf:  # rotation modulation: residual fused into the GEMM, rotation as a standalone kernel
-                ops.gemm_bf16(Hb, W.wqkv[i], ws["qkv"], epilogue=_lib.EPI_QKNORM, tokens=T, head_dim=hd, qk_cols=2 * D)
+            elif bf:  # rotation / LayerNorm modulation, plain attention, head_dim != 64: residual fused, rest standalone
+                qkv_proj(i, Hb)
                 ops.cos_attn(ws["qkv"], ws["o"], N, T, H, hd)
                 ops.gemm_bf16(ws["o"], W.wo[i], X, epilogue=_lib.EPI_RESID, resid=X, gate=mod(i, "gate_a"), ldmod=ld, tokens=T)
                 modulate_block(i, "m", X, Hb)
@@ -253,7 +282,8 @@ class Engine:
                 modulate_next(i, X, Hb)
             else:
                 ops.gemm_f32(Hb, W.wqkv[i], out=ws["qkv"])
-                ops.qk_normalize(ws["qkv"], D, hd)
+                if cosine:
+                    ops.qk_normalize(ws["qkv"], D, hd)
                 ops.cos_attn(ws["qkv"], ws["o"], N, T, H, hd)
                 ops.gemm_f32(ws["o"], W.wo[i], out=ws["tmp"])
                 ops.resid(X, ws["tmp"], X, mod(i, "gate_a"), ld, T)

@@ -37,6 +37,7 @@ def weight_norm_fwd(w, force=False, eff_f32=None, eff_bf16=None, eff_bf16_t=None
     rows, cols = w.shape
     for e in (eff_f32, eff_bf16):
         assert e is None or (e.is_contiguous() and e.numel() == w.numel())
+    # force: True/1 = forced write-back + normalise, False/0 = normalise only, -1 = plain copy (no weight normalisation)
     check(lib().mapdit_weight_norm_fwd(_ptr(w), rows, cols, EPS, int(force), _ptr(eff_f32), _ptr(eff_bf16),
                                        _ptr(eff_bf16_t), ld_t, _ptr(inv_norm), _stream()), "weight_norm_fwd")
 
@@ -111,6 +112,27 @@ def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0):
 
 def multi_lerp(chunk_table, n_chunks, weight):
     check(lib().mapdit_multi_lerp(_ptr(chunk_table), n_chunks, float(weight), _stream()), "multi_lerp")
+
+
+def set_variant(flags: int) -> int:
+    """select the README --use-* "off" variants for subsequent launches of this thread; returns the previous word"""
+    return lib().mapdit_set_variant(int(flags))
+
+
+def timestep_sincos(t, e, max_period=10000.0):
+    check(lib().mapdit_timestep_sincos(_ptr(t), _ptr(e), t.shape[0], e.shape[1], float(max_period), _stream()), "timestep_sincos")
+
+
+def ln_modulate(x, h, shift, scale, stats, ldmod, tokens):
+    m, d = x.shape
+    check(lib().mapdit_ln_modulate_fwd(_ptr(x), _ptr(h), _ptr(shift), _ptr(scale), _ptr(stats), ldmod, m, d, tokens, _dt(x), _stream()),
+          "ln_modulate_fwd")
+
+
+def ln_modulate_bwd(dh, x, R, stats, scale, dshift, dscale, ldmod, n_samples, tokens, accumulate):
+    d = dh.shape[1]
+    check(lib().mapdit_ln_modulate_bwd(_ptr(dh), _ptr(x), _ptr(R), _ptr(stats), _ptr(scale), _ptr(dshift), _ptr(dscale), ldmod,
+                                       n_samples, d, tokens, int(accumulate), _dt(dh), _stream()), "ln_modulate_bwd")
 
 
 def modulate(x, h, shift, scale, gain, ldmod, tokens):

@@ -28,9 +28,9 @@ class TrainStep:
         groups.append([b.modulation[1].weight for b in m.blocks])
         seen = {id(p) for g in groups for p in g}
         groups.append([p for p in m.parameters() if id(p) not in seen])
-        order = [p for g in groups for p in g]
-        total = sum(p.numel() for p in order)
-        self.flat_p = torch.empty(total, device=dev, dtype=torch.float32)
+        pad = lambda n: (n + 63) // 64 * 64  # every parameter starts 256-byte aligned (vectorised kernels, TMA)
+        total = sum(pad(p.numel()) for g in groups for p in g)
+        self.flat_p = torch.zeros(total, device=dev, dtype=torch.float32)
         self.flat_g = torch.zeros(total, device=dev, dtype=torch.float32)
         self.flat_m = torch.zeros(total, device=dev, dtype=torch.float32)
         self.flat_v = torch.zeros(total, device=dev, dtype=torch.float32)
@@ -43,7 +43,7 @@ class TrainStep:
                 self.flat_p[off:off + n].copy_(p.data.reshape(-1))
                 p.data = self.flat_p[off:off + n].view(p.shape)
                 self.grad_views[id(p)] = self.flat_g[off:off + n].view(p.shape)
-                off += n
+                off += pad(n)
             self.slices.append((start, off))
         self._group_of = {}
         for gi, g in enumerate(groups):

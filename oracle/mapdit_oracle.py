@@ -122,7 +122,7 @@ def unpatchify(x, input_size, p):
     return x.reshape(B, C, g * p, g * p)
 
 
-def pos_embed_table(dim: int, grid: int) -> torch.Tensor:
+def pos_embed_table(dim: int, grid: int, normalized: bool = True) -> torch.Tensor:
     """2-D sincos table, w-coordinate first half / h-coordinate second half, then row-normalised
     (src/pos_embed.py:4-61, src/dit.py:45-48).  Returns [1, grid*grid, dim] fp32."""
     def one_d(d, pos):
@@ -134,7 +134,8 @@ def pos_embed_table(dim: int, grid: int) -> torch.Tensor:
     gw = np.arange(grid, dtype=np.float32)
     mesh = np.stack(np.meshgrid(gw, gh), axis=0).reshape(2, 1, grid, grid)
     emb = np.concatenate([one_d(dim // 2, mesh[0]), one_d(dim // 2, mesh[1])], axis=1)
-    return normalize(torch.from_numpy(emb).float().unsqueeze(0))
+    raw = torch.from_numpy(emb).float().unsqueeze(0)
+    return normalize(raw) if normalized else raw  # raw table: use_mp_pos_enc=False (UNPINNED, vanilla DiT)
 
 
 # --------------------------------------------------------------------------------------
@@ -192,7 +193,7 @@ def init_state_dict(cfg: DiTConfig, seed: int = 0, nondegenerate: bool = True) -
     sd: Dict[str, torch.Tensor] = {}
     for k, shp in param_shapes(cfg).items():
         if k == "pos_embed":
-            sd[k] = pos_embed_table(cfg.hidden_size, cfg.input_size // cfg.patch_size)
+            sd[k] = pos_embed_table(cfg.hidden_size, cfg.input_size // cfg.patch_size, normalized=cfg.use_mp_pos_enc)
         elif k.endswith("embedding.scale"):
             sd[k] = torch.from_numpy((2 * np.pi * rng.standard_normal(shp)).astype(np.float32))
         elif k.endswith("embedding.shift"):
@@ -205,7 +206,15 @@ def init_state_dict(cfg: DiTConfig, seed: int = 0, nondegenerate: bool = True) -
         elif k.endswith("sigma_scale.reference"):
             sd[k] = (torch.from_numpy(rng.standard_normal(shp).astype(np.float32)) if nondegenerate else torch.zeros(shp))
         else:
-            sd[k] = torch.from_numpy(rng.standard_normal(shp, dtype=np.float32))
+            w = rng.standard_normal(shp, dtype=np.float32)
+            # UNPINNED "off" inits: without weight normalisation the N(0,1) weights of the snapshot would blow the
+            # activations up by sqrt(fan_in) per layer, so they are drawn with std 1/sqrt(fan_in); a plain
+            # nn.Embedding table keeps std 1 (its rows then have the same magnitude as the normalised ones)
+            if k == "y_embedder.embedding.weight":
+                pass
+            elif not cfg.use_weight_normalization:
+                w = w / math.sqrt(shp[-1])
+            sd[k] = torch.from_numpy(w.astype(np.float32))
     return sd
 
 
@@ -241,6 +250,28 @@ def mp_embedding(idx, w, train, cfg):
 def fourier_features(t, scale, shift):
     """sqrt(2)*cos(outer(t, scale) + shift) in fp32 (src/blocks/timestep_embedder.py:18-21)."""
     return math.sqrt(2) * torch.cos(torch.outer(t.to(scale.dtype), scale) + shift).to(torch.float32)
+
+
+def timestep_sincos(t, dim=256, max_period=10000.0):
+    """UNPINNED (use_mp_embedding=False): sinusoidal features of the vanilla DiT (Peebles & Xie, timestep_embedding):
+    [cos(t f) | sin(t f)], f_j = exp(-ln(max_period) j / half); fp32 throughout."""
+    half = dim // 2
+    freqs = torch.exp(-math.log(max_period) * torch.arange(half, dtype=torch.float32) / half)
+    args = t[:, None].float() * freqs[None]
+    return torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
+
+
+def layer_norm(x):
+    """UNPINNED (use_no_layernorm=False): LayerNorm(elementwise_affine=False, eps=1e-6) of the vanilla DiT block."""
+    return F.layer_norm(x, (x.shape[-1],), eps=1e-6)
+
+
+def block_modulate(x, shift, scale, gain, cfg):
+    """modulate (src/utils.py:11-12) or, with use_no_layernorm=False (UNPINNED), the vanilla adaLN
+    LN(x)*(1+scale)+shift (the gain parameter is then unused)."""
+    if cfg.use_no_layernorm:
+        return modulate(x, shift, scale, gain)
+    return layer_norm(x) * (1 + scale.unsqueeze(1)) + shift.unsqueeze(1)
 
 
 def attention(x, p, pre, cfg, train):
@@ -282,9 +313,9 @@ def dit_block(x, c, p, i, cfg, train):
     res = (lambda a, b: mp_sum(a, b, t=0.3)) if cfg.use_mp_residual else (lambda a, b: a + b)
     if cfg.modulation == "adaln":
         sh1, sc1, g1, sh2, sc2, g2 = m.chunk(6, dim=-1)
-        h = modulate(x, sh1, sc1, p[pre + "gain_msa"])
+        h = block_modulate(x, sh1, sc1, p[pre + "gain_msa"], cfg)
         x = res(x, g1.unsqueeze(1) * attention(h, p, pre, cfg, train))
-        h = modulate(x, sh2, sc2, p[pre + "gain_mlp"])
+        h = block_modulate(x, sh2, sc2, p[pre + "gain_mlp"], cfg)
         x = res(x, g2.unsqueeze(1) * mlp(h, p[pre + "mlp.net.0.weight"], p[pre + "mlp.net.2.weight"], train, cfg))
         return x
     # ---- UNPINNED rotation variants (self-referential) ----
@@ -313,9 +344,9 @@ def mp_scale(c, w, ref, train, cfg):
 
 def final_layer(x, c, p, cfg, train):
     """src/blocks/final_layer.py:53-61 (learn_sigma=True is the only working branch)."""
-    m = mp_linear(mp_silu(c), p["final_layer.modulation.1.weight"], train, cfg)
+    m = mp_linear(mp_silu(c) if cfg.use_mp_silu else F.silu(c), p["final_layer.modulation.1.weight"], train, cfg)
     shift, scale = m.chunk(2, dim=-1)
-    xm = modulate(x, shift, scale, p["final_layer.gain_mod"])
+    xm = block_modulate(x, shift, scale, p["final_layer.gain_mod"], cfg)
     y = mp_linear(xm, p["final_layer.linear.weight"], train, cfg)
     mean, sigma = y.chunk(2, dim=-1)
     s_mu = mp_scale(c, p["final_layer.mean_scale.linear.weight"], p["final_layer.mean_scale.reference"], train, cfg)
@@ -330,15 +361,19 @@ def dit_forward(p: Dict[str, torch.Tensor], cfg: DiTConfig, x, t, y, train: bool
     pinned; with ``train`` and no mask the oracle draws it the same way the reference does."""
     P = patchify(x, cfg.patch_size)
     P = torch.cat([P, torch.ones_like(P[:, :, :1])], dim=-1)
-    h = mp_sum(mp_linear(P, p["x_embedder.weight"], train, cfg), p["pos_embed"], t=0.5)
-    e = fourier_features(t, p["t_embedder.embedding.scale"], p["t_embedder.embedding.shift"])
+    h = mp_linear(P, p["x_embedder.weight"], train, cfg)
+    h = mp_sum(h, p["pos_embed"], t=0.5) if cfg.use_mp_pos_enc else h + p["pos_embed"]  # "off": UNPINNED
+    if cfg.use_mp_embedding:
+        e = fourier_features(t, p["t_embedder.embedding.scale"], p["t_embedder.embedding.shift"])
+    else:
+        e = timestep_sincos(t, p["t_embedder.embedding.scale"].shape[0])
     temb = mlp(e, p["t_embedder.mlp.net.0.weight"], p["t_embedder.mlp.net.2.weight"], train, cfg)
     if train and cfg.class_dropout_prob > 0:
         if drop_mask is None:
             drop_mask = torch.rand(y.shape[0], device=y.device) < cfg.class_dropout_prob
         y = torch.where(drop_mask, cfg.num_classes, y)
     yemb = mp_embedding(y, p["y_embedder.embedding.weight"], train, cfg)
-    c = mp_sum(temb, yemb, t=0.5)
+    c = mp_sum(temb, yemb, t=0.5) if cfg.use_mp_embedding else temb + yemb
     if taps is not None:
         taps["x0"], taps["c"] = h, c
     for i in range(cfg.depth):

@@ -40,8 +40,10 @@ def test_state_dict_contract_matches_reference(name):
 
 def test_unbuilt_variants_fail_loudly():
     import mapdit_b200 as M
-    with pytest.raises(NotImplementedError):
-        M.DIT_MODELS["DiT-XS/8"](in_channels=4, input_size=32, num_classes=10, use_mp_silu=False)
+    with pytest.raises(NotImplementedError):  # LayerNorm adaLN is only defined for the adaln layout
+        M.DIT_MODELS["DiT-XS/8"](in_channels=4, input_size=32, num_classes=10, use_no_layernorm=False, modulation="rotation")
+    off = M.DIT_MODELS["DiT-XS/8"](in_channels=4, input_size=32, num_classes=10, use_mp_silu=False, use_cosine_attention=False)
+    assert off.variant == 2 | 16 and off.state_dict().keys() == M.DIT_MODELS["DiT-XS/8"](in_channels=4, input_size=32, num_classes=10).state_dict().keys()
     with pytest.raises(ValueError):
         M.DIT_MODELS["DiT-XS/8"](in_channels=4, input_size=32, num_classes=10, modulation="bogus")
     m = M.DIT_MODELS["DiT-XS/8"](in_channels=4, input_size=32, num_classes=10, modulation="rotation_scaling")
