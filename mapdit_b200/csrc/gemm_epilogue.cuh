@@ -34,6 +34,12 @@ struct alignas(64) EpiTmaps {
   CUtensorMap out, out2, aux;
 };
 
+// 16-byte streaming global load that does not allocate in L1
+__device__ __forceinline__ uint4 ld_stream(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.global.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
 __device__ __forceinline__ float silu_fast(float x, float mul) { return __fdividef(x, 1.0f + __expf(-x)) * mul; }
 
 struct Stager {
@@ -109,6 +115,20 @@ __device__ __forceinline__ void run_tile(const EpiParams& ep, const EpiTmaps& tm
 #pragma unroll
     for (int g = 0; g < 4; ++g) pre[g] = (row_ok && g * 8 < nvalid) ? src[g] : make_uint4(0, 0, 0, 0);
   };
+  // The per-sample vectors (gate, shift, scale: one 128-byte line per 32-column chunk each) are read by every lane at the
+  // same address right before use; ncu showed their L2 round trips exposed twice per chunk (long-scoreboard stalls on the
+  // first FFMA/FMUL).  Lanes 0-2 pull the NEXT chunk's lines into L1 one chunk ahead; the streaming residual loads bypass
+  // L1 allocation so the ~24 KB of L1 left beside the operand ring keeps them.
+  const bool has_vecs = ep.epilogue == MAPDIT_EPI_RESID || ep.epilogue == MAPDIT_EPI_RESID_MOD;
+  auto prefetch_vecs = [&](int c) {
+    const int col = n_blk * BN + c;
+    const int lane = st.lane;
+    if (!has_vecs || c >= BN || col >= ep.N || lane > 2) return;
+    const float* base = lane == 0 ? ep.gate : (lane == 1 ? ep.shift : ep.scale);
+    if (lane > 0 && ep.epilogue != MAPDIT_EPI_RESID_MOD) return;
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(base + sample * ep.ldmod + col));
+  };
+  prefetch_vecs(half * 32);
   if (reads_resid && half * 32 < BN) prefetch(half * 32);
   const float silu_mul = (ep.variant & MAPDIT_VAR_PLAIN_SILU) ? 1.0f : 1.0f / MP_SILU_DIV;
   const bool plain_res = ep.variant & MAPDIT_VAR_PLAIN_RESID;
@@ -170,6 +190,7 @@ __device__ __forceinline__ void run_tile(const EpiParams& ep, const EpiTmaps& tm
       }
       if (c + 64 < BN) prefetch(c + 64);  // next chunk's residual while this one is processed
     }
+    prefetch_vecs(c + 64);
     if (nvalid <= 0) continue;  // warp-uniform
     if (ep.epilogue == MAPDIT_EPI_STORE) {
       if (ep.out_f32) {
