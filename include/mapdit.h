@@ -117,6 +117,11 @@ int mapdit_gemm_bf16_tn(const void* dy, int64_t ldy, const void* x, int64_t ldx,
 int mapdit_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                      float bias_corr1, float bias_corr2, float grad_scale, void* stream);
 
+/* N3, device-side CustomDataset.__getitem__ (train.py:168-176): out[n] = ((means[idx[n]] + eps[n]*stds[idx[n]]) - ch_mean[c]) / ch_std[c];
+ * means/stds [items, C, H*W] resident in HBM, idx int64 [n], eps/out [n, C, H*W] */
+int mapdit_latent_sample(const float* means, const float* stds, const int64_t* idx, const float* eps, const float* ch_mean,
+                         const float* ch_std, float* out, int n, int channels, int hw, void* stream);
+
 /* multi-tensor EMA update (src/ema.py:135-140): for each chunk {float* dst; const float* src; int64 n} of the device
  * table, dst = lerp(dst, src, weight) with torch.lerp's rounding */
 int mapdit_multi_lerp(const void* chunk_table, int n_chunks, float weight, void* stream);

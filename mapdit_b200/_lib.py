@@ -31,6 +31,7 @@ SIGNATURES = {
     "mapdit_gemm_bf16_tn": [_p, _i64, _p, _i64, _p, _i64, _i, _i, _i, _p],
     "mapdit_multi_lerp": [_p, _i, _f, _p],
     "mapdit_set_variant": [_i],
+    "mapdit_latent_sample": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
     "mapdit_timestep_sincos": [_p, _p, _i, _i, _f, _p],
     "mapdit_ln_modulate_fwd": [_p, _p, _p, _p, _p, _i64, _i, _i, _i, _i, _p],
     "mapdit_ln_modulate_bwd": [_p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _i, _i, _i, _p],

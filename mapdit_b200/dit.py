@@ -238,6 +238,17 @@ class DiT(nn.Module):
             self._engine = eng
         return new
 
+    def load_state_dict(self, state_dict, *args, **kwargs):
+        """accepts the `_orig_mod.` key prefix of checkpoints written from the reference's torch.compile-wrapped model
+        (train.py:46,124-128)"""
+        pre = "_orig_mod."
+        if any(k.startswith(pre) for k in state_dict):
+            state_dict = {(k[len(pre):] if k.startswith(pre) else k): v for k, v in state_dict.items()}
+        out = super().load_state_dict(state_dict, *args, **kwargs)
+        if self._engine is not None:
+            self._engine.invalidate()
+        return out
+
     def __getstate__(self):
         st = self.__dict__.copy()
         st["_engine"] = None

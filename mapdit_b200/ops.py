@@ -114,6 +114,13 @@ def multi_lerp(chunk_table, n_chunks, weight):
     check(lib().mapdit_multi_lerp(_ptr(chunk_table), n_chunks, float(weight), _stream()), "multi_lerp")
 
 
+def latent_sample(means, stds, idx, eps, ch_mean, ch_std, out):
+    n, c = out.shape[0], out.shape[1]
+    hw = out[0, 0].numel()
+    check(lib().mapdit_latent_sample(_ptr(means), _ptr(stds), _ptr(idx), _ptr(eps), _ptr(ch_mean), _ptr(ch_std), _ptr(out), n, c, hw,
+                                     _stream()), "latent_sample")
+
+
 def set_variant(flags: int) -> int:
     """select the README --use-* "off" variants for subsequent launches of this thread; returns the previous word"""
     return lib().mapdit_set_variant(int(flags))

@@ -14,9 +14,12 @@ from .parallel import GradReducer
 
 
 class TrainStep:
-    def __init__(self, model, diffusion, lr=1e-2, betas=(0.9, 0.99), eps=1e-8, world_size=1):
+    def __init__(self, model, diffusion, lr=1e-2, betas=(0.9, 0.99), eps=1e-8, world_size=1, lr_lambda=None, ema=None):
+        """`lr_lambda(step)` multiplies `lr` like the reference's LambdaLR (train.py:66,104: the k-th optimiser step, 0-based,
+        uses lr * lr_lambda(k)); `ema` (mapdit_b200.ema.EMA) is updated after every step like train.py:105."""
         self.model, self.diffusion = model, diffusion
         self.lr, self.betas, self.eps = lr, betas, eps
+        self.lr_lambda, self.ema = lr_lambda, ema
         self.world = world_size
         self.step_count = 0
         m = model
@@ -34,7 +37,7 @@ class TrainStep:
         self.flat_g = torch.zeros(total, device=dev, dtype=torch.float32)
         self.flat_m = torch.zeros(total, device=dev, dtype=torch.float32)
         self.flat_v = torch.zeros(total, device=dev, dtype=torch.float32)
-        self.grad_views, self.slices = {}, []
+        self.grad_views, self.slices, self.offset_of = {}, [], {}
         off = 0
         for g in groups:
             start = off
@@ -43,6 +46,7 @@ class TrainStep:
                 self.flat_p[off:off + n].copy_(p.data.reshape(-1))
                 p.data = self.flat_p[off:off + n].view(p.shape)
                 self.grad_views[id(p)] = self.flat_g[off:off + n].view(p.shape)
+                self.offset_of[id(p)] = off
                 off += pad(n)
             self.slices.append((start, off))
         self._group_of = {}
@@ -85,9 +89,12 @@ class TrainStep:
             ops.loss_fwd_bwd(out, x0, x_t, noise, tl, tab, loss, None, None, dout, gs, gs)
             tr.backward(saved, dout)
             self.reducer.finish()
+            lr = self.lr * (self.lr_lambda(self.step_count) if self.lr_lambda is not None else 1.0)
             self.step_count += 1
-            ops.adam_step(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.lr, self.betas[0], self.betas[1], self.eps,
+            ops.adam_step(self.flat_p, self.flat_g, self.flat_m, self.flat_v, lr, self.betas[0], self.betas[1], self.eps,
                           self.step_count, grad_scale=1.0 / self.world)
+            if self.ema is not None:
+                self.ema.update(self.step_count, m)
         tr.grad_buffers = None
         tr.grad_hook = None
         return loss.mean()

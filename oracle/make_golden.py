@@ -252,6 +252,16 @@ def ema_case(tag):
         for s in (0.05, 0.1):
             rec[f"upd_w_{s}"] = e.emas[s].weight.numpy().copy()
             rec[f"upd_b_{s}"] = e.emas[s].bias.numpy().copy()
+    # LR schedule factor (train.py:179-197): the function is lifted out of the reference's train.py source (the module
+    # itself imports torchvision/yaml and opens a dataset), default recipe num_lin_warmup=1000 / start_decay=20000 + edge cases
+    import ast
+    src = open(os.path.join(REF, "train.py")).read()
+    fn = next(n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "create_lr_lambda")
+    ns = {"math": __import__("math")}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "train.py", "exec"), ns)
+    steps = np.array([0, 1, 5, 998, 999, 1000, 19999, 20000, 20001, 80000, 400000])
+    rec["lr_steps"] = steps
+    rec["lr_factors"] = np.array([[ns["create_lr_lambda"](w, d)(int(s)) for s in steps] for w, d in ((1000, 20000), (1, 10), (100, 100))])
     np.savez_compressed(os.path.join(OUT, f"{tag}.npz"), **rec)
     print(tag, "ok")
 

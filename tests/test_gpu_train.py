@@ -200,3 +200,79 @@ def test_multi_lerp_matches_torch_lerp_on_a_model(w):
     ops.multi_lerp(tab, n, w)
     for k, v in e.emas[0.05].named_parameters():
         torch.testing.assert_close(v, want[k], rtol=1e-6, atol=1e-7)
+
+
+def test_latent_dataset_matches_reference_getitem():
+    """train.py:144-176 CustomDataset.__getitem__ + Normalize as one device kernel over HBM-resident posterior tables"""
+    from mapdit_b200.data import LatentDataset
+    g = torch.Generator().manual_seed(11)
+    items = 37
+    means, stds = torch.randn(items, 4, 32, 32, generator=g), torch.rand(items, 4, 32, 32, generator=g)
+    labels = torch.randint(0, 1000, (items,), generator=g)
+    stats = {"mean": torch.tensor([0.1, -0.2, 0.3, 0.05]), "std": torch.tensor([0.9, 1.1, 1.3, 0.7])}
+    ds = LatentDataset(tensors=dict(posterior_means=means, posterior_stds=stds, labels=labels, stats=stats))
+    assert len(ds) == items and ds.channels == 4 and ds.data_size == 32
+    idx = torch.tensor([5, 0, 36, 5, 17])
+    eps = torch.randn(5, 4, 32, 32, generator=g)
+    x, y = ds.sample_batch(idx.cuda(), eps.cuda())
+    feat = means[idx] + eps * stds[idx]  # mean + eps*std, then torchvision Normalize: (x - mean[c]) / std[c]
+    ref = (feat - stats["mean"].view(1, 4, 1, 1)) / stats["std"].view(1, 4, 1, 1)
+    assert torch.equal(x.cpu(), ref)
+    assert torch.equal(y.cpu(), labels[idx])
+    nb = sum(1 for _ in ds.batches(8))
+    assert nb == items // 8
+
+
+def test_checkpoint_roundtrips_through_torch_adam(tmp_path):
+    """{"model", "opt"} checkpoint (train.py:124-132) written by TrainStep resumes a torch.optim.Adam run on the oracle, and
+    loads back into a fresh TrainStep; LambdaLR factor and EMA hook ride along (train.py:66,104-105)"""
+    import mapdit_b200 as M
+    from mapdit_b200 import data
+    from mapdit_b200.ema import EMA
+    from mapdit_b200.train import TrainStep
+    name = "DiT-XS/8"
+    cfg = O.config_for(name)
+    sd = O.init_state_dict(cfg, seed=23)
+    gen = torch.Generator().manual_seed(6)
+    batches = [(torch.randn(4, 4, 32, 32, generator=gen), torch.randint(0, 1000, (4,), generator=gen), torch.randint(0, 1000, (4,), generator=gen),
+                torch.randn(4, 4, 32, 32, generator=gen)) for _ in range(3)]
+    drop = torch.tensor([False, False, True, False])
+    lam = data.create_lr_lambda(3, 2)
+
+    def new_ts(state):
+        m = M.DIT_MODELS[name](in_channels=4, input_size=32, num_classes=1000, compute_dtype="fp32")
+        m.load_state_dict(state)
+        m = m.cuda().train()
+        return m, TrainStep(m, M.create_diffusion(""), lr=1e-2, lr_lambda=lam)
+
+    m, ts = new_ts(sd)
+    ts.ema = EMA(m, str(tmp_path), stds=[0.05])
+    for x, t, y, n in batches[:2]:
+        ts.step(x.cuda(), t.cuda(), y.cuda(), n.cuda(), drop_mask=drop.cuda())
+    path = tmp_path / "0000002.pt"
+    data.save_checkpoint(str(path), m, ts)
+    ck = torch.load(path, weights_only=True)
+    assert all(k.startswith("_orig_mod.") for k in ck["model"]) and set(ck) == {"model", "opt"}
+    # (1) the reference side: torch.optim.Adam + LambdaLR resume on the oracle's parameters
+    p = O.make_params({k[len("_orig_mod."):]: v.cpu() for k, v in ck["model"].items()})
+    plist = [p[k] for k, _ in m.named_parameters()]
+    opt = torch.optim.Adam(plist, lr=1e-2, betas=(0.9, 0.99))
+    opt.load_state_dict({"state": {i: {k: v.cpu() for k, v in s.items()} for i, s in ck["opt"]["state"].items()},
+                         "param_groups": ck["opt"]["param_groups"]})
+    for g_ in opt.param_groups:
+        g_["lr"] = 1e-2 * lam(2)
+    x, t, y, n = batches[2]
+    opt.zero_grad()
+    O.train_step_grads(p, cfg, O.make_tables(""), x, t, y, n, drop_mask=drop)
+    opt.step()
+    # (2) our side: a fresh TrainStep resumed from the file
+    m2, ts2 = new_ts(sd)
+    data.load_checkpoint(str(path), m2, ts2)
+    assert ts2.step_count == 2
+    ts2.step(x.cuda(), t.cuda(), y.cuda(), n.cuda(), drop_mask=drop.cuda())
+    before = {k[len("_orig_mod."):]: v for k, v in ck["model"].items()}
+    worst = max(rel_l2(prm.detach().cpu() - before[k].cpu(), p[k].detach() - before[k].cpu()) for k, prm in m2.named_parameters() if prm.dim() == 2)
+    print(f"resumed third step, worst update rel-L2 vs torch Adam on the oracle: {worst:.2e}")
+    assert worst < 5e-3
+    # EMA hook ran with the reference's step numbering
+    assert ts.ema.emas[0.05].blocks[0].attn.qkv_proj.weight.is_cuda

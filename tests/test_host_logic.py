@@ -125,3 +125,29 @@ def test_ema_host_math_matches_reference_golden(tmp_path):
     hit = E.calculate_posthoc_ema(0.1, str(tmp_path), verbose=False)
     assert hit["a.weight"].dtype == torch.float16  # exact-std hit returns the stored fp16 snapshot (src/ema.py:93-98)
     np.testing.assert_array_equal(hit["a.weight"].float().numpy(), g["exact_a"])
+
+
+def test_lr_schedule_and_experiment_layout_match_reference(tmp_path):
+    """train.py:179-214: LambdaLR factor (golden from the reference's own function) and the NNN-Model/checkpoints layout"""
+    from mapdit_b200 import data
+    g = np.load(os.path.join(GOLDEN, "ema.npz"))
+    for row, (w, d) in zip(g["lr_factors"], ((1000, 20000), (1, 10), (100, 100))):
+        lam = data.create_lr_lambda(w, d)
+        np.testing.assert_allclose([lam(int(s)) for s in g["lr_steps"]], row, rtol=1e-15)
+    e0 = data.setup_experiment("DiT-B/2", str(tmp_path))
+    e1 = data.setup_experiment("DiT-B/2", str(tmp_path))
+    assert os.path.basename(e0) == "000-DiT-B-2" and os.path.basename(e1) == "001-DiT-B-2"
+    assert os.path.isdir(os.path.join(e1, "checkpoints"))
+    data.save_config(e0, dict(model="DiT-B/2", lr=1e-2, stats_mean=[0.1, 0.2]))
+    import yaml
+    assert yaml.safe_load(open(os.path.join(e0, "config.yaml")))["model"] == "DiT-B/2"
+
+
+def test_state_dict_accepts_compiled_prefix():
+    """checkpoints of the reference carry `_orig_mod.` keys (train.py:46,124-128)"""
+    import mapdit_b200 as M
+    cfg = O.config_for("DiT-XS/8")
+    sd = O.init_state_dict(cfg, seed=3)
+    m = M.DIT_MODELS["DiT-XS/8"](in_channels=4, input_size=32, num_classes=1000)
+    m.load_state_dict({"_orig_mod." + k: v for k, v in sd.items()})
+    assert all(torch.equal(m.state_dict()[k], v) for k, v in sd.items())
