@@ -106,8 +106,11 @@ typedef struct mapdit_gemm_args {
 
 int mapdit_gemm_bf16(const mapdit_gemm_args* args, void* stream);
 int mapdit_sizeof_gemm_args(void); /* lets a binding check its struct mirror */
-/* runtime switches: "gemm_2cta" (0/1) selects the cta_group::2 256xBN kernel for large-M GEMMs */
+/* runtime switches: "gemm_2cta" (0/1) selects the cta_group::2 256xBN kernel for large-M GEMMs;
+ * "attn_v2" (0/1) selects the one-CTA-per-SM ping-pong attention forward for tokens % 256 == 0 */
 int mapdit_set_option(const char* name, int value);
+/* developer hook: device buffer of >= 1024 int64 that CTA 0 of the attn_v2 kernel fills with clock64 stamps (null = off) */
+int mapdit_attn_debug_buffer(void* buf);
 /* weight gradient C[N_out, K_in] (fp32) = dY[M, N_out]^T · X[M, K_in] on tcgen05, operands read MN-major in place
  * (autograd of F.linear, src/basic/mp_linear.py:46,75); split-K with fp32 vector reductions when N_out*K_in is small */
 int mapdit_gemm_bf16_tn(const void* dy, int64_t ldy, const void* x, int64_t ldx, float* c, int64_t ldc, int m_tokens,

@@ -1,0 +1,341 @@
+// K4, second generation: cosine attention forward with one CTA per SM and two query tiles in flight
+// (head_dim 64, tokens a multiple of 256).  Replaces src/layers/attention.py:43-49 like attention_tc.cu, which stays for
+// token counts that are only a multiple of 64.
+//
+// What ncu said about the first kernel (profiles/r1_attn_ncu_summary.md): XU 44 %, tensor 20 %, no saturated pipe — the
+// softmax warps spent their time on the S-ready wait, the P store to shared memory + fence.proxy.async, the row-sum
+// exchange and the per-tile epilogue, with the two CTAs of an SM drifting into lock-step.  This kernel removes those:
+//   * one work item = (sample, head, 256 queries): two 128-row query tiles A and B share every 64-key K/V block (half
+//     the K/V traffic); each tile has a double-buffered S in TMEM, so S(g+1) is computed while softmax works on S(g)
+//     (with single buffers ncu showed the softmax warps 38 % of their samples waiting for the next S);
+//   * P never touches shared memory: it is written back over its own S columns in TMEM (tcgen05.st, bf16 pairs) and is
+//     the A operand of the PV MMA straight from TMEM;
+//   * the row sum comes out of the tensor core: V is extended by a constant panel of ones (N = 80), so column 64 of the
+//     O accumulator is sum_k P[r,k] of exactly the bf16 P the numerator used — no FADDs, no cross-warp exchange;
+//   * a third warpgroup normalises and stores O, so the softmax warpgroups go straight on to the next item.
+// Warps: 0-3 softmax A, 4-7 softmax B, 8-11 epilogue (TMEM lane quarter = warp % 4), 12 TMA producer, 13 / 14 MMA issuers of
+// tile A / B.  One issuer per tile because a clock64 timeline of the kernel showed the issue of these small MMAs
+// (N = 64 / 80: 32-40 tensor-pipe clocks each) costing ~80-100 clocks of the issuing thread apiece: a single issuer serving
+// both tiles was the bottleneck (softmax warps 38 % of their samples waiting for S, tensor pipe 22 % active).
+// (Sixteen softmax warps, two per lane quarter splitting the key columns behind a pair barrier, measured 11 % slower.)
+// TMEM (512 columns): S_A/P_A buffers [0,64) [64,128)  S_B/P_B [128,192) [192,256)  O_A [256,336)  O_B [352,432).
+// Logits are bounded (|q.k|/8 <= 8): p = exp(logit - 8), no running max, no rescaling of O.
+#include "tc_common.cuh"
+
+namespace {
+using namespace tc;
+
+#ifndef ATTN2_KB
+#define ATTN2_KB 128
+#endif
+constexpr int HD = 64, QT = 128, KB = ATTN2_KB;  // keys per step: 128 with one S buffer per tile, or 64 with two
+constexpr int SBUF = 128 / KB;                    // S buffers per tile (each tile owns 128 TMEM columns)
+constexpr int Q_BYTES = 2 * QT * HD * 2;  // both query tiles of an item: 32 KB
+constexpr int K_BYTES = KB * HD * 2;      // 8 KB
+constexpr int KV_BYTES = 2 * K_BYTES;     // K block then V block
+constexpr int ONES_BYTES = KB * 128;      // [64 keys x 128 B] of bf16 1.0: the second (16-channel) N panel of V
+constexpr int NS = KB == 64 ? 4 : 3;
+constexpr int SMEM_BYTES = 2 * Q_BYTES + NS * KV_BYTES + ONES_BYTES + 1024 + 512;
+constexpr int NTHREADS = 15 * 32;
+constexpr int W_EPI = 8, W_TMA = 12, W_MMA = 13;  // warps 13 and 14 issue the MMAs of tile A and tile B
+constexpr uint32_t TMEM_COLS = 512;
+__host__ __device__ constexpr uint32_t col_s(int x, int b) { return (uint32_t)(x * 128 + b * KB); }
+__host__ __device__ constexpr uint32_t col_o(int x) { return x ? 352u : 256u; }
+constexpr int ON = 80;  // PV accumulator width: 64 channels + 16 row-sum columns
+
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// D[tmem] (+)= A[tmem] * B[smem]
+__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+      "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld1(uint32_t taddr, uint32_t& v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+attn_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, bf16* __restrict__ o,
+                float* __restrict__ lse, int tokens, int heads, int n_samples, long long* __restrict__ dbg) {
+  // optional timeline of CTA 0 (tools/attn_timeline.py): dbg[role*256 + 4*g + e] = clock64 at event e of step g
+#define DBG(role, g, e)                                                                             \
+  do {                                                                                               \
+    if (dbg && blockIdx.x == 0 && (g) < 64 && lane == 0) dbg[(role) * 256 + 4 * (g) + (e)] = clock64(); \
+  } while (0)
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* sQ = smem;                       // [2 buffers][256 x 64]
+  uint8_t* sKV = sQ + 2 * Q_BYTES;          // stage s: K at sKV + s*KV_BYTES, V right after
+  uint8_t* sOnes = sKV + NS * KV_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + ONES_BYTES);
+  uint64_t* q_full = bars;              // [2]
+  uint64_t* q_empty = q_full + 2;       // [2]
+  uint64_t* kv_full = q_empty + 2;      // [NS]
+  uint64_t* kv_empty = kv_full + NS;    // [NS]
+  uint64_t* s_full = kv_empty + NS;     // [tile][buffer]
+  uint64_t* p_full = s_full + 4;        // [tile][buffer]
+  uint64_t* o_full = p_full + 4;        // [2]
+  uint64_t* o_empty = o_full + 2;       // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int D = heads * HD;
+  const int nkb = tokens / KB;
+  const int npair = tokens / (2 * QT);
+  const int total_items = npair * heads * n_samples;
+
+  // constant ones panel (generic-proxy writes, made visible to the tensor core's async proxy below)
+  for (int i = threadIdx.x; i < ONES_BYTES / 16; i += NTHREADS)
+    reinterpret_cast<uint4*>(sOnes)[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+  fence_proxy_async();
+  if (warp == W_TMA && lane == 0) {
+    prefetch_tmap(&tm_q);
+    prefetch_tmap(&tm_kv);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], 2);
+      mbar_init(&s_full[2 * i], 1);
+      mbar_init(&s_full[2 * i + 1], 1);
+      mbar_init(&p_full[2 * i], 4);
+      mbar_init(&p_full[2 * i + 1], 4);
+      mbar_init(&o_full[i], 1);
+      mbar_init(&o_empty[i], 4);
+    }
+    for (int i = 0; i < NS; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 2);  // one commit per MMA issuer
+    }
+    fence_barrier_init();
+  }
+  if (warp == W_MMA) tmem_alloc<TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+  if (warp == W_TMA) {
+    if (lane == 0) {
+      // ------------------------------------------------ TMA producer
+      uint32_t g = 0, it = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
+        const int pr = item % npair, rest = item / npair, h = rest % heads, n = rest / heads;
+        const int row_base = n * tokens;
+        const int qb = it & 1;
+        mbar_wait(&q_empty[qb], ((it >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&q_full[qb], Q_BYTES);
+        tma_load_2d(sQ + qb * Q_BYTES, &tm_q, &q_full[qb], h * HD, row_base + pr * 2 * QT);
+        for (int j = 0; j < nkb; ++j, ++g) {
+          const int s = g % NS;
+          mbar_wait(&kv_empty[s], ((g / NS) & 1) ^ 1);
+          uint8_t* dst = sKV + s * KV_BYTES;
+          mbar_arrive_expect_tx(&kv_full[s], KV_BYTES);
+          tma_load_2d(dst, &tm_kv, &kv_full[s], D + h * HD, row_base + j * KB);
+          tma_load_2d(dst + K_BYTES, &tm_kv, &kv_full[s], 2 * D + h * HD, row_base + j * KB);
+        }
+      }
+    }
+  } else if (warp >= W_MMA) {
+    {
+      const int x = warp - W_MMA;  // this issuer's query tile
+      // ------------------------------------------------ MMA issuer: a flat software pipeline over (item, key block) steps.
+      // The WHOLE warp runs this loop (waits included) and one elected lane issues the tcgen05 instructions: inside an
+      // `if (lane == 0)` region the compiler cannot prove the descriptors warp-uniform and wraps every UTCHMMA operand in an
+      // ELECT / R2UR.BROADCAST waterfall loop, which for these small MMAs (32-40 tensor clocks each) cost more than the MMA.
+      const bool leader = elect_one();
+      constexpr uint32_t idesc_s = make_idesc_bf16(QT, KB, 0, 0);  // S = Q K^T, both K-major
+      constexpr uint32_t idesc_o = make_idesc_bf16(QT, ON, 0, 1);  // O = P V, P from TMEM, V MN-major (+ ones panel)
+      const int my_items = (total_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+      const uint32_t total_steps = (uint32_t)my_items * nkb;
+      const uint32_t ones_addr = smem_u32(sOnes);
+      auto issue_s = [&](uint32_t g) {  // S_x(g) = Q_x K_g^T into buffer g & 1, then signal tile x's softmax warps
+        const uint32_t it = g / nkb, b = g % SBUF;
+        if (g - it * nkb == 0) mbar_wait(&q_full[it & 1], (it >> 1) & 1);
+        mbar_wait(&kv_full[g % NS], (g / NS) & 1);
+        tc_fence_after();
+        const uint32_t q_addr = smem_u32(sQ + (it & 1) * Q_BYTES + x * (QT * HD * 2));
+        const uint32_t k_addr = smem_u32(sKV + (g % NS) * KV_BYTES);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          if (leader)
+            umma_ss(tmem_base + col_s(x, b), make_smem_desc(q_addr + k * 32, 16, 1024), make_smem_desc(k_addr + k * 32, 16, 1024),
+                    idesc_s, k != 0);
+        if (leader) umma_commit(&s_full[2 * x + b]);
+        // the query tiles of an item are free once S_B of its last key block has been issued
+        if (leader && g - it * nkb + 1 == (uint32_t)nkb) umma_commit(&q_empty[it & 1]);
+      };
+      for (uint32_t g = 0; g < (uint32_t)SBUF && g < total_steps; ++g) issue_s(g);
+      for (uint32_t g = 0; g < total_steps; ++g) {
+        const uint32_t it = g / nkb, j = g - it * nkb, b = g % SBUF;
+        const bool last_j = (j + 1 == (uint32_t)nkb);
+        const uint32_t v_addr = smem_u32(sKV + (g % NS) * KV_BYTES + K_BYTES);
+        {
+          if (j == 0) mbar_wait(&o_empty[x], (it & 1) ^ 1);  // the epilogue has read the previous item's O_x
+          mbar_wait(&p_full[2 * x + b], (g / SBUF) & 1);
+          tc_fence_after();
+          DBG(x, g, 0);  // MMA warp: P_x(g) seen
+#pragma unroll
+          for (int k = 0; k < KB / 16; ++k)  // 16 keys per MMA: P advances 8 TMEM columns, V two 8-row groups
+            if (leader)
+              umma_ts(tmem_base + col_o(x), tmem_base + col_s(x, b) + k * 8,
+                      make_smem_desc(v_addr + k * 2048, ones_addr - v_addr, 1024), idesc_o, (j | k) != 0);
+          if (leader && last_j) umma_commit(&o_full[x]);
+          if (leader) umma_commit(&kv_empty[g % NS]);  // V_g is done with (K_g since S_x(g), two steps ago)
+          if (g + SBUF < total_steps) issue_s(g + SBUF);  // reuses buffer b right behind the PV that read P from it
+          DBG(x, g, 1);  // MMA warp: PV_x(g) and S_x(g+2) issued
+        }
+      }
+    }
+  } else if (warp < W_EPI) {
+    // ------------------------------------------------ softmax warpgroups: thread = query row, 64 logits per step
+    const int x = warp >> 2, qq = warp & 3;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(qq * 32) << 16);
+    const float c1 = 0.125f * 1.4426950408889634f, c2 = 8.0f * 1.4426950408889634f;
+    const int my_items = (total_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const uint32_t total_steps = (uint32_t)my_items * nkb;
+    // explicit ping-pong: the two warpgroups take turns in the exponential phase (named barriers 1 + x: "tile x may go"),
+    // so they never share the MUFU and one tile's exp phase covers the other's MMA phase; left alone they fall into
+    // lock-step (timeline: both 2x slower in the exp phase, then both idle while the tensor core works)
+    if (x == 1) asm volatile("bar.arrive 1, 256;" ::: "memory");  // tile A goes first
+    for (uint32_t g = 0; g < total_steps; ++g) {
+      const uint32_t b = g % SBUF, t_s = t_lane + col_s(x, b);
+      if (qq == 0) DBG(2 + x, g, 0);  // softmax: starts waiting for S_x(g)
+      mbar_wait(&s_full[2 * x + b], (g / SBUF) & 1);
+      tc_fence_after();
+      if (x == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
+      else asm volatile("bar.sync 2, 256;" ::: "memory");
+      if (qq == 0) DBG(2 + x, g, 1);  // softmax: S_x(g) seen and our turn
+      // 32-column chunks, software pipelined: the tcgen05.ld of chunk c+1 is in flight while chunk c is exponentiated.
+      // P (bf16 pairs) overwrites the first half of its own S buffer: chunk c lands on columns [16c, 16c+16), all already in
+      // registers, while the load in flight reads columns >= 32(c+1).
+      uint32_t sa[32], sb[32];
+      tmem_ld32(t_s, sa);
+#pragma unroll
+      for (int c = 0; c < KB / 32; ++c) {
+        uint32_t(&cur)[32] = (c & 1) ? sb : sa;
+        uint32_t(&nxt)[32] = (c & 1) ? sa : sb;
+        tmem_ld_wait();
+        if (c + 1 < KB / 32) tmem_ld32(t_s + (c + 1) * 32, nxt);
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          pk[i] = pack_bf16(ex2f(fmaf(__uint_as_float(cur[2 * i]), c1, -c2)), ex2f(fmaf(__uint_as_float(cur[2 * i + 1]), c1, -c2)));
+        tmem_st16(t_s + c * 16, pk);
+      }
+      if (x == 0) asm volatile("bar.arrive 2, 256;" ::: "memory");  // the exponentials are issued: the other tile's turn
+      else asm volatile("bar.arrive 1, 256;" ::: "memory");
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[2 * x + b]);
+      if (qq == 0) DBG(2 + x, g, 2);  // softmax: P_x(g) published
+    }
+  } else {
+    // ------------------------------------------------ epilogue warpgroup: O / rowsum -> global, log-sum-exp
+    const int qq = warp & 3;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(qq * 32) << 16);
+    uint32_t it = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
+      const int pr = item % npair, rest = item / npair, h = rest % heads, n = rest / heads;
+#pragma unroll
+      for (int x = 0; x < 2; ++x) {
+        const size_t grow = (size_t)n * tokens + pr * 2 * QT + x * QT + qq * 32 + lane;
+        mbar_wait(&o_full[x], it & 1);
+        tc_fence_after();
+        uint32_t ov[32], rs;
+        tmem_ld32(t_lane + col_o(x), ov);
+        tmem_ld1(t_lane + col_o(x) + 64, rs);
+        tmem_ld_wait();
+        const float total = __uint_as_float(rs);
+        const float inv = 1.0f / total;
+        if (lse) lse[grow * heads + h] = 8.0f + logf(total);
+        bf16* dst = o + grow * D + h * HD;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          if (half == 1) {
+            tmem_ld32(t_lane + col_o(x) + 32, ov);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&o_empty[x]);
+          }
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint4 u;
+            u.x = pack_bf16(__uint_as_float(ov[8 * c]) * inv, __uint_as_float(ov[8 * c + 1]) * inv);
+            u.y = pack_bf16(__uint_as_float(ov[8 * c + 2]) * inv, __uint_as_float(ov[8 * c + 3]) * inv);
+            u.z = pack_bf16(__uint_as_float(ov[8 * c + 4]) * inv, __uint_as_float(ov[8 * c + 5]) * inv);
+            u.w = pack_bf16(__uint_as_float(ov[8 * c + 6]) * inv, __uint_as_float(ov[8 * c + 7]) * inv);
+            *reinterpret_cast<uint4*>(dst + half * 32 + 8 * c) = u;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == W_MMA) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+}  // namespace
+
+bool mapdit_attn_tc2_supported(int tokens, int hd) { return hd == HD && tokens % (2 * QT) == 0 && tokens >= 2 * QT; }
+
+static long long* g_attn_dbg = nullptr;
+extern "C" int mapdit_attn_debug_buffer(void* p) {  // developer hook: timeline buffer of >= 1024 int64 (or null)
+  g_attn_dbg = (long long*)p;
+  return MAPDIT_OK;
+}
+
+int mapdit_attn_tc2_fwd(const void* qkv, void* o, float* lse, int n, int tokens, int heads, int hd, void* stream) {
+  const int D = heads * hd;
+  CUtensorMap tq, tkv;
+  const uint64_t dims[2] = {(uint64_t)3 * D, (uint64_t)n * tokens};
+  const uint64_t strides[1] = {(uint64_t)3 * D * 2};
+  const uint32_t box_q[2] = {HD, 2 * QT}, box_kv[2] = {HD, KB};
+  CUresult r1 = mapdit_encode_tmap(&tq, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, qkv, dims, strides, box_q, CU_TENSOR_MAP_SWIZZLE_128B);
+  CUresult r2 = mapdit_encode_tmap(&tkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, qkv, dims, strides, box_kv, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) {
+    mapdit_set_error("attn_tc2_fwd: cuTensorMapEncodeTiled failed (%d, %d)", (int)r1, (int)r2);
+    return MAPDIT_ERR_CUDA;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) {
+      mapdit_set_error("attn_tc2_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return MAPDIT_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  const int items = (tokens / (2 * QT)) * heads * n;
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  const int grid = items < sms ? items : sms;  // persistent, one CTA per SM (512 TMEM columns)
+  attn_tc2_kernel<<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tq, tkv, (bf16*)o, lse, tokens, heads, n, g_attn_dbg);
+  MAPDIT_LAUNCH_CHECK("attn_tc2_fwd");
+  return MAPDIT_OK;
+}

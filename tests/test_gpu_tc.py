@@ -96,16 +96,26 @@ def test_gemm_bf16_fused_epilogues(N, T, D, two_cta):
     assert rel_l2(xio.float(), xn) < 3e-3
 
 
-@pytest.mark.parametrize("N,T,H", [(2, 256, 6), (3, 64, 4), (1, 1024, 2), (5, 256, 12), (2, 128, 4)])
-def test_cos_attn_bf16(N, T, H):
-    from mapdit_b200 import ops
+@pytest.mark.parametrize("v2", [1, 0])
+@pytest.mark.parametrize("N,T,H", [(2, 256, 6), (3, 64, 4), (1, 1024, 2), (5, 256, 12), (2, 128, 4), (40, 256, 12), (3, 512, 5)])
+def test_cos_attn_bf16(N, T, H, v2):
+    """both tcgen05 forward kernels (attn_v2: one CTA per SM, P in TMEM, ones-column row sum; v1: P through smem)"""
+    from mapdit_b200 import _lib, ops
     hd, D = 64, H * 64
     qkv = rnd(N * T, 3 * D, seed=9)
     ops.qk_normalize(qkv, D, hd)
     qkv16 = qkv.bfloat16()
     q, k, v = qkv16.float().view(N, T, 3, H, hd).permute(2, 0, 3, 1, 4)
     ref = F.scaled_dot_product_attention(q.double(), k.double(), v.double(), scale=1 / math.sqrt(hd)).transpose(1, 2).reshape(N * T, D)
-    o = torch.empty(N * T, D, device="cuda", dtype=torch.bfloat16)
-    ops.cos_attn(qkv16, o, N, T, H, hd)
+    ref_lse = torch.logsumexp(q.double() @ k.double().transpose(-1, -2) / math.sqrt(hd), dim=-1).permute(0, 2, 1).reshape(N * T, H)
+    o = torch.full((N * T, D), float("nan"), device="cuda", dtype=torch.bfloat16)
+    lse = torch.full((N * T, H), float("nan"), device="cuda")
+    _lib.set_option("attn_v2", v2)
+    try:
+        ops.cos_attn(qkv16, o, N, T, H, hd, lse=lse)
+        torch.cuda.synchronize()
+    finally:
+        _lib.set_option("attn_v2", 1)
     # P is rounded to bf16 before the PV product on the tensor-core path
     assert rel_l2(o.float(), ref) < 6e-3
+    assert float((lse.double() - ref_lse).abs().max()) < 2e-2

@@ -159,7 +159,11 @@ def main():
     ap.add_argument("names", nargs="*")
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--json", default=None)
+    ap.add_argument("--opt", action="append", default=[], help="runtime option name=value (mapdit_set_option), e.g. attn_v2=0")
     a = ap.parse_args()
+    for kv in a.opt:
+        k, v = kv.split("=")
+        _lib.set_option(k, int(v))
     tf, hbm = peaks()
     res = {}
     all_cases = cases()
