@@ -122,7 +122,8 @@ attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_cons
       tma_load_2d(dst, &tm_qkv_blk, &kv_full[s], D + h * HD, row_base + j * CB);
       tma_load_2d(dst + BLK_BYTES, &tm_qkv_blk, &kv_full[s], 2 * D + h * HD, row_base + j * CB);
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
+    const bool leader = elect_one();  // whole warp runs the loop, one lane issues (see tc_common.cuh)
     constexpr uint32_t idesc_s = make_idesc_bf16(RT, CB, 0, 0);  // S / dP: both operands K-major
     constexpr uint32_t idesc_q = make_idesc_bf16(RT, HD, 0, 1);  // dQ += dS K_j: K_j MN-major (d contiguous)
     const uint32_t q_addr = smem_u32(sQ), do_addr = smem_u32(sdO), ds_addr = smem_u32(sdS);
@@ -134,11 +135,11 @@ attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_cons
       const uint32_t k_addr = smem_u32(sKV + s * 2 * BLK_BYTES), v_addr = k_addr + BLK_BYTES;
 #pragma unroll
       for (int k = 0; k < HD / 16; ++k)
-        umma_ss(tmem_base, make_smem_desc(q_addr + k * 32, 16, 1024), make_smem_desc(k_addr + k * 32, 16, 1024), idesc_s, k != 0);
+        if (leader) umma_ss(tmem_base, make_smem_desc(q_addr + k * 32, 16, 1024), make_smem_desc(k_addr + k * 32, 16, 1024), idesc_s, k != 0);
 #pragma unroll
       for (int k = 0; k < HD / 16; ++k)
-        umma_ss(tmem_base + 64, make_smem_desc(do_addr + k * 32, 16, 1024), make_smem_desc(v_addr + k * 32, 16, 1024), idesc_s, k != 0);
-      umma_commit(s_full);
+        if (leader) umma_ss(tmem_base + 64, make_smem_desc(do_addr + k * 32, 16, 1024), make_smem_desc(v_addr + k * 32, 16, 1024), idesc_s, k != 0);
+      if (leader) umma_commit(s_full);
     };
     mbar_wait(bar_q, 0);
     scores(0);
@@ -150,12 +151,12 @@ attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_cons
       const uint32_t k_addr = smem_u32(sKV + s * 2 * BLK_BYTES);
 #pragma unroll
       for (int k = 0; k < CB / 16; ++k)
-        umma_ss(tmem_base + 128, make_smem_desc(ds_addr + k * 32, 16, 1024), make_smem_desc(k_addr + k * 2048, 1024, 1024), idesc_q,
+        if (leader) umma_ss(tmem_base + 128, make_smem_desc(ds_addr + k * 32, 16, 1024), make_smem_desc(k_addr + k * 2048, 1024, 1024), idesc_q,
                 (j | k) != 0);
-      umma_commit(&kv_empty[s]);
-      umma_commit(ds_empty);
+      if (leader) umma_commit(&kv_empty[s]);
+      if (leader) umma_commit(ds_empty);
     }
-    umma_commit(o_full);
+    if (leader) umma_commit(o_full);
   } else if (warp >= 2) {
     const int qq = warp & 3;
     const int r = qq * 32 + lane;
@@ -287,7 +288,8 @@ attn_bwd_dkv_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_con
       tma_load_2d(dst, &tm_qkv_blk, &qd_full[s], h * HD, row_base + j * CB);
       tma_load_2d(dst + BLK_BYTES, &tm_do_blk, &qd_full[s], h * HD, row_base + j * CB);
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
+    const bool leader = elect_one();  // whole warp runs the loop, one lane issues (see tc_common.cuh)
     constexpr uint32_t idesc_s = make_idesc_bf16(RT, CB, 0, 0);  // S^T = K Q_j^T, dP^T = V dO_j^T
     constexpr uint32_t idesc_a = make_idesc_bf16(RT, HD, 0, 1);  // dV += P^T dO_j, dK += dS^T Q_j : B MN-major
     const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), pt_addr = smem_u32(sPt), dst_addr = smem_u32(sdSt);
@@ -299,11 +301,11 @@ attn_bwd_dkv_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_con
       const uint32_t q_addr = smem_u32(sQdO + s * 2 * BLK_BYTES), do_addr = q_addr + BLK_BYTES;
 #pragma unroll
       for (int k = 0; k < HD / 16; ++k)
-        umma_ss(tmem_base, make_smem_desc(k_addr + k * 32, 16, 1024), make_smem_desc(q_addr + k * 32, 16, 1024), idesc_s, k != 0);
+        if (leader) umma_ss(tmem_base, make_smem_desc(k_addr + k * 32, 16, 1024), make_smem_desc(q_addr + k * 32, 16, 1024), idesc_s, k != 0);
 #pragma unroll
       for (int k = 0; k < HD / 16; ++k)
-        umma_ss(tmem_base + 64, make_smem_desc(v_addr + k * 32, 16, 1024), make_smem_desc(do_addr + k * 32, 16, 1024), idesc_s, k != 0);
-      umma_commit(s_full);
+        if (leader) umma_ss(tmem_base + 64, make_smem_desc(v_addr + k * 32, 16, 1024), make_smem_desc(do_addr + k * 32, 16, 1024), idesc_s, k != 0);
+      if (leader) umma_commit(s_full);
     };
     mbar_wait(bar_kv, 0);
     scores(0);
@@ -315,16 +317,16 @@ attn_bwd_dkv_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_con
       const uint32_t q_addr = smem_u32(sQdO + s * 2 * BLK_BYTES), do_addr = q_addr + BLK_BYTES;
 #pragma unroll
       for (int k = 0; k < CB / 16; ++k)
-        umma_ss(tmem_base + 192, make_smem_desc(pt_addr + k * 32, 16, 1024), make_smem_desc(do_addr + k * 2048, 1024, 1024), idesc_a,
+        if (leader) umma_ss(tmem_base + 192, make_smem_desc(pt_addr + k * 32, 16, 1024), make_smem_desc(do_addr + k * 2048, 1024, 1024), idesc_a,
                 (j | k) != 0);
 #pragma unroll
       for (int k = 0; k < CB / 16; ++k)
-        umma_ss(tmem_base + 128, make_smem_desc(dst_addr + k * 32, 16, 1024), make_smem_desc(q_addr + k * 2048, 1024, 1024), idesc_a,
+        if (leader) umma_ss(tmem_base + 128, make_smem_desc(dst_addr + k * 32, 16, 1024), make_smem_desc(q_addr + k * 2048, 1024, 1024), idesc_a,
                 (j | k) != 0);
-      umma_commit(&qd_empty[s]);
-      umma_commit(p_empty);
+      if (leader) umma_commit(&qd_empty[s]);
+      if (leader) umma_commit(p_empty);
     }
-    umma_commit(o_full);
+    if (leader) umma_commit(o_full);
   } else if (warp >= 2) {
     const int qq = warp & 3;
     const int r = qq * 32 + lane;  // key row of the tile

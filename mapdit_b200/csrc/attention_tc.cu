@@ -103,7 +103,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         tma_load_2d(k_dst + KV_BYTES, &tm_kv, &kv_full[s], 2 * D + h * HD, row_base + j * KB);
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
+    const bool leader = elect_one();  // whole warp runs the loop, one lane issues (see tc_common.cuh)
     // ------------------------------------------------ MMA issuer
     constexpr uint32_t idesc_s = make_idesc_bf16(QT, KB, 0, 0);   // S = Q K^T : both K-major
     constexpr uint32_t idesc_o = make_idesc_bf16(QT, HD, 0, 1);   // O = P V   : V is MN-major (d contiguous)
@@ -116,21 +117,21 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
       const uint32_t k_addr = smem_u32(sKV + kvs * 2 * KV_BYTES);
 #pragma unroll
       for (int k = 0; k < HD / 16; ++k)
-        umma_ss(tmem_base + s * KB, make_smem_desc(q_addr + k * 32, 16, 1024), make_smem_desc(k_addr + k * 32, 16, 1024), idesc_s,
+        if (leader) umma_ss(tmem_base + s * KB, make_smem_desc(q_addr + k * 32, 16, 1024), make_smem_desc(k_addr + k * 32, 16, 1024), idesc_s,
                 k != 0);
-      umma_commit(&s_full[s]);
+      if (leader) umma_commit(&s_full[s]);
     };
     uint32_t g = 0, it = 0;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
       mbar_wait(q_full, it & 1);
       issue_s(g);
-      if (nkb == 1) umma_commit(q_empty);  // Q tile free once the item's last S MMA retires
+      if (nkb == 1) if (leader) umma_commit(q_empty);  // Q tile free once the item's last S MMA retires
       for (int j = 0; j < nkb; ++j) {
         const uint32_t gg = g + j;
         const int s = gg & 1;
         if (j + 1 < nkb) {
           issue_s(gg + 1);
-          if (j + 2 == nkb) umma_commit(q_empty);
+          if (j + 2 == nkb) if (leader) umma_commit(q_empty);
         }
         if (j == 0) mbar_wait(o_empty, (it & 1) ^ 1);  // previous item's O has been read out of TMEM
         mbar_wait(&p_full[s], (gg >> 1) & 1);
@@ -140,12 +141,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         const uint32_t v_addr = smem_u32(sKV + kvs * 2 * KV_BYTES + KV_BYTES);
 #pragma unroll
         for (int k = 0; k < KB / 16; ++k)  // 16 keys per MMA: P advances 32 B along K, V advances two 8-row groups
-          umma_ss(tmem_base + 128, make_smem_desc(p_addr + k * 32, 16, 1024), make_smem_desc(v_addr + k * 2048, 1024, 1024), idesc_o,
+          if (leader) umma_ss(tmem_base + 128, make_smem_desc(p_addr + k * 32, 16, 1024), make_smem_desc(v_addr + k * 2048, 1024, 1024), idesc_o,
                   (j | k) != 0);
-        umma_commit(&kv_empty[kvs]);
-        umma_commit(&p_empty[s]);
+        if (leader) umma_commit(&kv_empty[kvs]);
+        if (leader) umma_commit(&p_empty[s]);
       }
-      umma_commit(o_full);
+      if (leader) umma_commit(o_full);
       g += nkb;
     }
   } else if (warp >= 2) {

@@ -96,7 +96,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
+    const bool leader = elect_one();  // whole warp runs the loop, one lane issues (see tc_common.cuh)
     // ------------------------------------------------ MMA issuer
     constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
     int stage = 0;
@@ -114,15 +115,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         for (int k = 0; k < BK / UK; ++k) {
           const uint64_t adesc = make_smem_desc(a_addr + k * UK * 2, 16, 1024);
           const uint64_t bdesc = make_smem_desc(b_addr + k * UK * 2, 16, 1024);
-          umma_ss(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+          if (leader) umma_ss(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
         }
-        umma_commit(&empty[stage]);  // frees the smem slot when these MMAs retire
+        if (leader) umma_commit(&empty[stage]);  // frees the smem slot when these MMAs retire
         if (++stage == C::STAGES) {
           stage = 0;
           phase ^= 1;
         }
       }
-      umma_commit(&tfull[acc]);  // accumulator complete -> epilogue
+      if (leader) umma_commit(&tfull[acc]);  // accumulator complete -> epilogue
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }

@@ -130,7 +130,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
         }
       }
     }
-  } else if (warp == 1 && lane == 0 && rank == 0) {
+  } else if (warp == 1 && rank == 0) {
+    const bool leader = elect_one();  // whole warp runs the loop, one lane issues (see tc_common.cuh)
     // ------------------------------------------------ MMA issuer (leader CTA only)
     constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN, 0, 0);
     int stage = 0;
@@ -146,15 +147,15 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
         const uint32_t b_addr = a_addr + C::A_BYTES;
 #pragma unroll
         for (int k = 0; k < BK / UK; ++k)
-          umma_ss_2cta(d_tmem, make_smem_desc(a_addr + k * UK * 2, 16, 1024), make_smem_desc(b_addr + k * UK * 2, 16, 1024), idesc,
+          if (leader) umma_ss_2cta(d_tmem, make_smem_desc(a_addr + k * UK * 2, 16, 1024), make_smem_desc(b_addr + k * UK * 2, 16, 1024), idesc,
                        (kb | k) != 0 ? 1u : 0u);
-        umma_commit_2cta(&empty[stage]);
+        if (leader) umma_commit_2cta(&empty[stage]);
         if (++stage == C::STAGES) {
           stage = 0;
           phase ^= 1;
         }
       }
-      umma_commit_2cta(&tfull[acc]);
+      if (leader) umma_commit_2cta(&tfull[acc]);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }

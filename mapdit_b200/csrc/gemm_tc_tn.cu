@@ -89,7 +89,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
+    const bool leader = elect_one();  // whole warp runs the loop, one lane issues (see tc_common.cuh)
     constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 1, 1);  // both operands MN-major
     int stage = 0;
     uint32_t phase = 0, acc = 0, acc_phase = 0;
@@ -108,15 +109,15 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         for (int k = 0; k < BK / UK; ++k) {  // 16 tokens = two 8-row groups = 2 KB inside every panel
           const uint64_t adesc = make_smem_desc(a_addr + k * 2048, PANEL_BYTES, 1024);
           const uint64_t bdesc = make_smem_desc(b_addr + k * 2048, PANEL_BYTES, 1024);
-          umma_ss(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          if (leader) umma_ss(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
         }
-        umma_commit(&empty[stage]);
+        if (leader) umma_commit(&empty[stage]);
         if (++stage == Cf::STAGES) {
           stage = 0;
           phase ^= 1;
         }
       }
-      umma_commit(&tfull[acc]);
+      if (leader) umma_commit(&tfull[acc]);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }

@@ -129,6 +129,20 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// One elected lane of a fully converged warp.  The MMA-issuer warps run their whole loop warp-uniformly and guard only the
+// tcgen05 instructions with this predicate: inside an `if (lane == 0)` region the compiler cannot prove the descriptors
+// warp-uniform and wraps every UTCHMMA operand in an ELECT / R2UR.BROADCAST waterfall loop (seen in SASS), which costs more
+// than a small MMA itself.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&t);
