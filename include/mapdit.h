@@ -59,6 +59,12 @@ int mapdit_set_variant(int flags);
  *   row that eff was computed from (needed by the backward).                                  */
 int mapdit_weight_norm_fwd(float* w, int rows, int cols, float eps, int force, float* eff_f32,
                            void* eff_bf16, void* eff_bf16_t, int64_t ld_t /* 0 = rows */, float* inv_norm, void* stream);
+/* The same for many weights in two launches.  descs: device table of n_desc rows of 10 x int64
+ * {w, eff_f32, eff_bf16, eff_bf16_t (pointers, nullable), ld_t, rows, cols (cols % 4 == 0, 16-byte aligned pointers), group0, tile0,
+ * row0}: group0 = sum over earlier tensors of ceil(rows/8), tile0 = sum of ceil(rows/64)*ceil(cols/64), row0 = sum of rows;
+ * scratch: float2[total rows]. */
+int mapdit_weight_norm_fwd_multi(const void* descs, int n_desc, int total_groups, int total_tiles, float eps, int force,
+                                 void* scratch, void* stream);
 /* Backward of eff = v/(||v||+eps) per row: given G = dL/d eff [rows, cols]
  * and the (forced) weights v, grad_v = (G - v (v·G)/(r (r+eps)))/(r+eps); accumulate==0 overwrites. */
 int mapdit_weight_norm_bwd(const float* v, const float* g_eff, float* grad_v, int rows, int cols,

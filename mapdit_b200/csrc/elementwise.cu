@@ -96,9 +96,9 @@ __global__ void __launch_bounds__(256) weight_norm_fwd_kernel(float* __restrict_
 //      bf16 copy (the dgrad operand) through a shared-memory transpose so that it leaves as 32-byte row segments instead
 //      of scattered 2-byte stores.
 constexpr int WN_ROWS = 64, WN_TCOLS = 64, WN_PITCH = WN_TCOLS + 2;
-__global__ void __launch_bounds__(256) wn_norms_kernel(const float* __restrict__ w, int rows, int cols, float eps, int force,
-                                                       float2* __restrict__ scratch, float* __restrict__ inv_norm) {
-  const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+__device__ __forceinline__ void wn_norms_body(const float* __restrict__ w, int rows, int cols, float eps, int force,
+                                              float2* __restrict__ scratch, float* __restrict__ inv_norm, int group) {
+  const int r = group * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (r >= rows) return;
   const float4* row4 = reinterpret_cast<const float4*>(w + (size_t)r * cols);
   const int n4 = cols / 4;
@@ -137,12 +137,15 @@ __global__ void __launch_bounds__(256) wn_norms_kernel(const float* __restrict__
     if (inv_norm) inv_norm[r] = inv;
   }
 }
+__global__ void __launch_bounds__(256) wn_norms_kernel(const float* __restrict__ w, int rows, int cols, float eps, int force,
+                                                       float2* __restrict__ scratch, float* __restrict__ inv_norm) {
+  wn_norms_body(w, rows, cols, eps, force, scratch, inv_norm, blockIdx.x);
+}
 
-__global__ void __launch_bounds__(256) wn_apply_kernel(float* __restrict__ w, int rows, int cols, int force,
-                                                       const float2* __restrict__ scratch, float* __restrict__ eff_f32,
-                                                       bf16* __restrict__ eff_bf16, bf16* __restrict__ eff_bf16_t, int64_t ld_t) {
-  __shared__ __align__(16) bf16 tile[WN_ROWS * WN_PITCH];
-  const int r0 = blockIdx.x * WN_ROWS, c0 = blockIdx.y * WN_TCOLS;
+__device__ __forceinline__ void wn_apply_body(float* __restrict__ w, int rows, int cols, int force, const float2* __restrict__ scratch,
+                                              float* __restrict__ eff_f32, bf16* __restrict__ eff_bf16, bf16* __restrict__ eff_bf16_t,
+                                              int64_t ld_t, int tile_r, int tile_c, bf16* tile) {
+  const int r0 = tile_r * WN_ROWS, c0 = tile_c * WN_TCOLS;
   const float sq = sqrtf((float)cols);
   const int tr = threadIdx.x >> 4, tc = (threadIdx.x & 15) * 4;  // 16 rows x 16 float4 per pass, 4 passes
 #pragma unroll
@@ -198,6 +201,55 @@ __global__ void __launch_bounds__(256) wn_apply_kernel(float* __restrict__ w, in
       }
     }
   }
+}
+__global__ void __launch_bounds__(256) wn_apply_kernel(float* __restrict__ w, int rows, int cols, int force,
+                                                       const float2* __restrict__ scratch, float* __restrict__ eff_f32,
+                                                       bf16* __restrict__ eff_bf16, bf16* __restrict__ eff_bf16_t, int64_t ld_t) {
+  __shared__ __align__(16) bf16 tile[WN_ROWS * WN_PITCH];
+  wn_apply_body(w, rows, cols, force, scratch, eff_f32, eff_bf16, eff_bf16_t, ld_t, blockIdx.x, blockIdx.y, tile);
+}
+
+// Multi-tensor flavour: every tiled-eligible weight of the model in TWO launches (the training step re-normalises 60+
+// matrices; one launch pair per matrix left the kernels latency bound at ~1.1 TB/s).  `descs` is a device table of
+// 10 x int64 rows {w, eff_f32, eff_bf16, eff_bf16_t, ld_t, rows, cols, group0, tile0, row0}: group0 / tile0 are this
+// tensor's first CTA index in the norms / apply grids, row0 its first row in the {den, inv} scratch.
+struct WnDesc {
+  float* w;
+  float* eff_f32;
+  bf16* eff_bf16;
+  bf16* eff_bf16_t;
+  long long ld_t, rows, cols, group0, tile0, row0;
+};
+__device__ __forceinline__ int wn_find(const WnDesc* __restrict__ d, int n, long long idx, bool tiles) {
+  int lo = 0, hi = n - 1;  // last descriptor whose first CTA index is <= idx
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if ((tiles ? d[mid].tile0 : d[mid].group0) <= idx) lo = mid;
+    else hi = mid - 1;
+  }
+  return lo;
+}
+__global__ void __launch_bounds__(256) wn_norms_multi_kernel(const WnDesc* __restrict__ descs, int n, float eps, int force,
+                                                             float2* __restrict__ scratch) {
+  const WnDesc d = descs[wn_find(descs, n, blockIdx.x, false)];
+  wn_norms_body(d.w, (int)d.rows, (int)d.cols, eps, force, scratch + d.row0, nullptr, (int)(blockIdx.x - d.group0));
+}
+__global__ void __launch_bounds__(256) wn_apply_multi_kernel(const WnDesc* __restrict__ descs, int n, int force,
+                                                             const float2* __restrict__ scratch) {
+  __shared__ __align__(16) bf16 tile[WN_ROWS * WN_PITCH];
+  const WnDesc d = descs[wn_find(descs, n, blockIdx.x, true)];
+  const int t = (int)(blockIdx.x - d.tile0), tiles_c = ((int)d.cols + WN_TCOLS - 1) / WN_TCOLS;
+  wn_apply_body(d.w, (int)d.rows, (int)d.cols, force, scratch + d.row0, d.eff_f32, d.eff_bf16, d.eff_bf16_t, d.ld_t, t / tiles_c,
+                t % tiles_c, tile);
+}
+extern "C" int mapdit_weight_norm_fwd_multi(const void* descs, int n_desc, int total_groups, int total_tiles, float eps, int force,
+                                            void* scratch, void* stream) {
+  MAPDIT_REQUIRE(descs && scratch && n_desc > 0 && total_groups > 0 && total_tiles > 0, "weight_norm_fwd_multi: bad args");
+  wn_norms_multi_kernel<<<total_groups, 256, 0, (cudaStream_t)stream>>>((const WnDesc*)descs, n_desc, eps, force, (float2*)scratch);
+  MAPDIT_LAUNCH_CHECK("weight_norm_fwd_multi(norms)");
+  wn_apply_multi_kernel<<<total_tiles, 256, 0, (cudaStream_t)stream>>>((const WnDesc*)descs, n_desc, force, (const float2*)scratch);
+  MAPDIT_LAUNCH_CHECK("weight_norm_fwd_multi(apply)");
+  return MAPDIT_OK;
 }
 
 // per-row {den, inv} scratch of the tiled path: grown on demand outside stream capture, one per device

@@ -102,12 +102,20 @@ class Engine:
             W.wfl_t = torch.empty(D, m.final_layer.linear.weight.shape[0], **wd)
             W.wmod_t = torch.empty(D, W.mod_total, **wd)
 
+        batch = []  # big weights go through ONE multi-tensor launch pair (ops.WeightNormBatch)
+
         def norm(p, out, out_t=None, ld_t=0):
             kw = {"eff_bf16": out} if out.dtype == torch.bfloat16 else {"eff_f32": out}
             if want_t and out_t is not None:
                 kw["eff_bf16_t"] = out_t
                 kw["ld_t"] = ld_t
-            ops.weight_norm_fwd(p.data, force=force, **kw)
+            w = p.data
+            ok = (w.shape[1] % 4 == 0 and w.shape[0] >= 16 and w.is_contiguous() and w.data_ptr() % 16 == 0
+                  and out.data_ptr() % 16 == 0 and (kw.get("eff_bf16_t") is None or kw["eff_bf16_t"].data_ptr() % 2 == 0))
+            if ok:
+                batch.append((w, kw.get("eff_f32"), kw.get("eff_bf16"), kw.get("eff_bf16_t"), kw.get("ld_t", 0)))
+            else:
+                ops.weight_norm_fwd(w, force=force, **kw)
 
         norm(m.x_embedder.weight, W.wx)
         norm(m.t_embedder.mlp.net[0].weight, W.wt1)
@@ -126,6 +134,14 @@ class Engine:
         norm(f.linear.weight, W.wfl, W.wfl_t if want_t else None)
         norm(f.mean_scale.linear.weight, W.wmu)
         norm(f.sigma_scale.linear.weight, W.wsg)
+        if batch:
+            key = (mode, want_t)
+            sigb = tuple(t.data_ptr() for it in batch for t in it[:4] if t is not None)
+            wb = getattr(self, "_wn_batches", {}).get(key)
+            if wb is None or wb[0] != sigb:
+                wb = (sigb, ops.WeightNormBatch(batch, dev))
+                self.__dict__.setdefault("_wn_batches", {})[key] = wb
+            wb[1].run(force)
         self._w_sig[mode] = self._signature()
         self._dirty = bool(train)  # forced WN rewrote the parameters without bumping versions
         return W

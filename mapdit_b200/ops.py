@@ -42,6 +42,29 @@ def weight_norm_fwd(w, force=False, eff_f32=None, eff_bf16=None, eff_bf16_t=None
                                        _ptr(eff_bf16_t), ld_t, _ptr(inv_norm), _stream()), "weight_norm_fwd")
 
 
+class WeightNormBatch:
+    """descriptor table for mapdit_weight_norm_fwd_multi: `items` = [(w, eff_f32|None, eff_bf16|None, eff_bf16_t|None, ld_t)]"""
+
+    def __init__(self, items, device):
+        rows_tab, g0, t0, r0 = [], 0, 0, 0
+        for w, e32, e16, e16t, ld_t in items:
+            rows, cols = w.shape
+            assert w.dtype == torch.float32 and w.is_contiguous() and cols % 4 == 0 and w.data_ptr() % 16 == 0
+            rows_tab.append([w.data_ptr(), e32.data_ptr() if e32 is not None else 0, e16.data_ptr() if e16 is not None else 0,
+                             e16t.data_ptr() if e16t is not None else 0, ld_t if ld_t else rows, rows, cols, g0, t0, r0])
+            g0 += (rows + 7) // 8
+            t0 += ((rows + 63) // 64) * ((cols + 63) // 64)
+            r0 += rows
+        self.table = torch.tensor(rows_tab, dtype=torch.int64).to(device)
+        self.n, self.groups, self.tiles = len(rows_tab), g0, t0
+        self.scratch = torch.empty(r0, 2, device=device, dtype=torch.float32)
+        self.signature = tuple(r[0] for r in rows_tab)
+
+    def run(self, force):
+        check(lib().mapdit_weight_norm_fwd_multi(_ptr(self.table), self.n, self.groups, self.tiles, EPS, int(force), _ptr(self.scratch),
+                                                 _stream()), "weight_norm_fwd_multi")
+
+
 def weight_norm_bwd(v, g_eff, grad_v, accumulate=False):
     rows, cols = v.shape
     assert v.is_contiguous() and g_eff.is_contiguous() and grad_v.is_contiguous()
