@@ -159,6 +159,11 @@ int mapdit_cos_attn_fwd(const void* qkv, void* o, float* lse /* nullable: [M, H]
 int mapdit_cos_attn_bwd(const void* qkv, const void* o, const void* dout, const float* lse, void* dqkv, float* delta,
                         int n_samples, int tokens, int heads, int head_dim, int dtype, void* stream);
 
+/* the same followed by the backward of the q/k L2 normalisation (sc [M, 2H] = sqrt(hd)/(||v||+eps) from the forward): dqkv receives
+ * d/d(raw q, raw k, v); fused into the dq/dk epilogues on the tcgen05 path */
+int mapdit_cos_attn_bwd_qknorm(const void* qkv, const void* o, const void* dout, const float* lse, const float* sc, float eps,
+                               void* dqkv, float* delta, int n_samples, int tokens, int heads, int head_dim, int dtype, void* stream);
+
 /* ---- embedders / final layer ------------------------------------------------------------------ */
 /* x0 = mp_sum(patchify(x)|1 · Wx^T, pos, .5) (src/dit.py:81-84); optional h = modulate(x0,...).   */
 int mapdit_patch_embed(const float* x, const float* wx_eff, const float* pos, void* x0, void* h,

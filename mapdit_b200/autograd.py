@@ -366,9 +366,10 @@ class Trainer:
             ops.resid_bwd(R, a, dY, mod(mods, i, "gate_a"), mod(dmods, i, "gate_a"), ld, N, T)
             self._wgrad(dY, o, blk[i].attn.out_proj.weight, bf, B, grads)
             self._dgrad(dY, W.wo[i], wt("wo_t"), dh, bf)
-            ops.cos_attn_bwd(qkv, o, dh, B["lse"][i], dqkv, B["delta"], N, T, H, hd)
-            if cosine:
-                ops.qk_norm_bwd(dqkv, qkv, B["sc"][i], D, hd)
+            if cosine:  # attention backward with the q/k normalisation backward fused into its dq / dk epilogues
+                ops.cos_attn_bwd_qknorm(qkv, o, dh, B["lse"][i], B["sc"][i], dqkv, B["delta"], N, T, H, hd)
+            else:
+                ops.cos_attn_bwd(qkv, o, dh, B["lse"][i], dqkv, B["delta"], N, T, H, hd)
             self._wgrad(dqkv, h1, blk[i].attn.qkv_proj.weight, bf, B, grads)
             self._dgrad(dqkv, W.wqkv[i], wt("wqkv_t"), dh, bf)
             modulate_block_bwd(i, "a", dh, xin, True)

@@ -59,13 +59,59 @@ __device__ __forceinline__ void store_out_row(bf16* dst, const uint32_t (&a)[32]
   }
 }
 
+// dq / dk epilogue with the backward of the q/k L2 normalisation fused in (src/layers/attention.py:43-45; closed form in
+// backward.cu qk_norm_bwd): the thread owns the whole 64-channel gradient row G = acc * att_scale of the NORMALISED head
+// y = sqrt(hd) v / (r + eps); with s = sqrt(hd)/(r+eps) saved by the forward, dv = s (G - y (y.G)(r+eps)/(hd r)).
+__device__ __forceinline__ void store_out_row_qknorm(bf16* dst, const bf16* __restrict__ yrow, const uint32_t (&a)[32],
+                                                     const uint32_t (&b)[32], float att_scale, float s, float eps) {
+  float y[64];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const uint4 u = reinterpret_cast<const uint4*>(yrow)[c];
+    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 t = __bfloat1622float2(h2[e]);
+      y[8 * c + 2 * e] = t.x;
+      y[8 * c + 2 * e + 1] = t.y;
+    }
+  }
+  float dot = 0.f;
+#pragma unroll
+  for (int c = 0; c < 32; ++c) dot = fmaf(y[c], __uint_as_float(a[c]), fmaf(y[32 + c], __uint_as_float(b[c]), dot));
+  dot *= att_scale;
+  const float rpe = 8.0f / s;
+  const float r = fmaxf(rpe - eps, 1e-30f);
+  const float coef = dot * rpe / (64.0f * r);
+  const float ga = s * att_scale;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint4 u;
+    u.x = pack_bf16(fmaf(ga, __uint_as_float(a[8 * c]), -s * coef * y[8 * c]), fmaf(ga, __uint_as_float(a[8 * c + 1]), -s * coef * y[8 * c + 1]));
+    u.y = pack_bf16(fmaf(ga, __uint_as_float(a[8 * c + 2]), -s * coef * y[8 * c + 2]), fmaf(ga, __uint_as_float(a[8 * c + 3]), -s * coef * y[8 * c + 3]));
+    u.z = pack_bf16(fmaf(ga, __uint_as_float(a[8 * c + 4]), -s * coef * y[8 * c + 4]), fmaf(ga, __uint_as_float(a[8 * c + 5]), -s * coef * y[8 * c + 5]));
+    u.w = pack_bf16(fmaf(ga, __uint_as_float(a[8 * c + 6]), -s * coef * y[8 * c + 6]), fmaf(ga, __uint_as_float(a[8 * c + 7]), -s * coef * y[8 * c + 7]));
+    *reinterpret_cast<uint4*>(dst + 8 * c) = u;
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint4 u;
+    u.x = pack_bf16(fmaf(ga, __uint_as_float(b[8 * c]), -s * coef * y[32 + 8 * c]), fmaf(ga, __uint_as_float(b[8 * c + 1]), -s * coef * y[32 + 8 * c + 1]));
+    u.y = pack_bf16(fmaf(ga, __uint_as_float(b[8 * c + 2]), -s * coef * y[32 + 8 * c + 2]), fmaf(ga, __uint_as_float(b[8 * c + 3]), -s * coef * y[32 + 8 * c + 3]));
+    u.z = pack_bf16(fmaf(ga, __uint_as_float(b[8 * c + 4]), -s * coef * y[32 + 8 * c + 4]), fmaf(ga, __uint_as_float(b[8 * c + 5]), -s * coef * y[32 + 8 * c + 5]));
+    u.w = pack_bf16(fmaf(ga, __uint_as_float(b[8 * c + 6]), -s * coef * y[32 + 8 * c + 6]), fmaf(ga, __uint_as_float(b[8 * c + 7]), -s * coef * y[32 + 8 * c + 7]));
+    *reinterpret_cast<uint4*>(dst + 32 + 8 * c) = u;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ dQ
 constexpr int DQ_SMEM = 2 * ROW_BYTES + 2 * 2 * BLK_BYTES + ROW_BYTES + 1024 + 256;
 
 __global__ void __launch_bounds__(NTHREADS, 2)
 attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_constant__ CUtensorMap tm_qkv_blk,
                const __grid_constant__ CUtensorMap tm_do_row, const bf16* __restrict__ o, const bf16* __restrict__ dout,
-               const float* __restrict__ lse, float* __restrict__ delta, bf16* __restrict__ dqkv, int tokens, int heads) {
+               const float* __restrict__ lse, float* __restrict__ delta, bf16* __restrict__ dqkv, int tokens, int heads,
+               const bf16* __restrict__ qkv, const float* __restrict__ sc, float eps) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -215,7 +261,10 @@ attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_cons
     tmem_ld32(t_lane + 128, a0);
     tmem_ld32(t_lane + 160, a1);
     tmem_ld_wait();
-    if (row_ok) store_out_row(dqkv + grow * 3 * D + h * HD, a0, a1, 0.125f);
+    if (row_ok) {
+      if (sc) store_out_row_qknorm(dqkv + grow * 3 * D + h * HD, qkv + grow * 3 * D + h * HD, a0, a1, 0.125f, sc[grow * 2 * heads + h], eps);
+      else store_out_row(dqkv + grow * 3 * D + h * HD, a0, a1, 0.125f);
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -228,7 +277,7 @@ constexpr int DKV_SMEM = 2 * ROW_BYTES + 2 * 2 * BLK_BYTES + 2 * ROW_BYTES + 2 *
 __global__ void __launch_bounds__(NTHREADS, 2)
 attn_bwd_dkv_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_constant__ CUtensorMap tm_qkv_blk,
                 const __grid_constant__ CUtensorMap tm_do_blk, const float* __restrict__ lse, const float* __restrict__ delta,
-                bf16* __restrict__ dqkv, int tokens, int heads) {
+                bf16* __restrict__ dqkv, int tokens, int heads, const bf16* __restrict__ qkv, const float* __restrict__ sc, float eps) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -379,7 +428,11 @@ attn_bwd_dkv_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_con
     tmem_ld32(t_lane + 128, a0);
     tmem_ld32(t_lane + 160, a1);
     tmem_ld_wait();
-    if (row_ok) store_out_row(dqkv + grow * 3 * D + D + h * HD, a0, a1, 0.125f);
+    if (row_ok) {
+      if (sc) store_out_row_qknorm(dqkv + grow * 3 * D + D + h * HD, qkv + grow * 3 * D + D + h * HD, a0, a1, 0.125f,
+                                   sc[grow * 2 * heads + heads + h], eps);
+      else store_out_row(dqkv + grow * 3 * D + D + h * HD, a0, a1, 0.125f);
+    }
     tmem_ld32(t_lane + 192, a0);
     tmem_ld32(t_lane + 224, a1);
     tmem_ld_wait();
@@ -398,11 +451,19 @@ int encode2d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uin
 }
 }  // namespace
 
-extern "C" int mapdit_cos_attn_bwd(const void* qkv, const void* o, const void* dout, const float* lse, void* dqkv, float* delta,
-                                   int n_samples, int tokens, int heads, int head_dim, int dtype, void* stream) {
+extern "C" int mapdit_qk_norm_bwd(void* dqkv, const void* qkv, const float* sc, int m, int d, int head_dim, float eps, int dtype,
+                                  void* stream);
+
+// sc == nullptr: gradients w.r.t. the normalised q^, k^ (and v).  sc != nullptr: the q/k normalisation backward is applied
+// as well (fused into the dq / dk epilogues on the tcgen05 path, a separate kernel behind the CUDA-core path).
+static int attn_bwd_impl(const void* qkv, const void* o, const void* dout, const float* lse, const float* sc, float eps, void* dqkv,
+                         float* delta, int n_samples, int tokens, int heads, int head_dim, int dtype, void* stream) {
   MAPDIT_REQUIRE(qkv && o && dout && lse && dqkv && delta && n_samples > 0 && tokens > 0, "cos_attn_bwd: bad args");
-  if (!(dtype == MAPDIT_BF16 && head_dim == HD && tokens % CB == 0) || (mapdit_variant() & MAPDIT_VAR_DOT_ATTN))
-    return mapdit_attn_bwd_simt(qkv, o, dout, lse, dqkv, delta, n_samples, tokens, heads, head_dim, dtype, stream);
+  if (!(dtype == MAPDIT_BF16 && head_dim == HD && tokens % CB == 0) || (mapdit_variant() & MAPDIT_VAR_DOT_ATTN)) {
+    int rc = mapdit_attn_bwd_simt(qkv, o, dout, lse, dqkv, delta, n_samples, tokens, heads, head_dim, dtype, stream);
+    if (rc != MAPDIT_OK || !sc) return rc;
+    return mapdit_qk_norm_bwd(dqkv, qkv, sc, n_samples * tokens, heads * head_dim, head_dim, eps, dtype, stream);
+  }
   const int D = heads * HD;
   const uint64_t rows = (uint64_t)n_samples * tokens;
   CUtensorMap t_qkv_row, t_qkv_blk, t_do_row, t_do_blk;
@@ -425,9 +486,21 @@ extern "C" int mapdit_cos_attn_bwd(const void* qkv, const void* o, const void* d
   dim3 grid((tokens + RT - 1) / RT, heads, n_samples);
   cudaStream_t s = (cudaStream_t)stream;
   attn_bwd_dq_tc<<<grid, NTHREADS, DQ_SMEM, s>>>(t_qkv_row, t_qkv_blk, t_do_row, (const bf16*)o, (const bf16*)dout, lse, delta,
-                                                 (bf16*)dqkv, tokens, heads);
+                                                 (bf16*)dqkv, tokens, heads, (const bf16*)qkv, sc, eps);
   MAPDIT_LAUNCH_CHECK("cos_attn_bwd(dq)");
-  attn_bwd_dkv_tc<<<grid, NTHREADS, DKV_SMEM, s>>>(t_qkv_row, t_qkv_blk, t_do_blk, lse, delta, (bf16*)dqkv, tokens, heads);
+  attn_bwd_dkv_tc<<<grid, NTHREADS, DKV_SMEM, s>>>(t_qkv_row, t_qkv_blk, t_do_blk, lse, delta, (bf16*)dqkv, tokens, heads,
+                                                   (const bf16*)qkv, sc, eps);
   MAPDIT_LAUNCH_CHECK("cos_attn_bwd(dkv)");
   return MAPDIT_OK;
+}
+
+extern "C" int mapdit_cos_attn_bwd(const void* qkv, const void* o, const void* dout, const float* lse, void* dqkv, float* delta,
+                                   int n_samples, int tokens, int heads, int head_dim, int dtype, void* stream) {
+  return attn_bwd_impl(qkv, o, dout, lse, nullptr, 0.f, dqkv, delta, n_samples, tokens, heads, head_dim, dtype, stream);
+}
+extern "C" int mapdit_cos_attn_bwd_qknorm(const void* qkv, const void* o, const void* dout, const float* lse, const float* sc, float eps,
+                                          void* dqkv, float* delta, int n_samples, int tokens, int heads, int head_dim, int dtype,
+                                          void* stream) {
+  MAPDIT_REQUIRE(sc != nullptr, "cos_attn_bwd_qknorm: sc is required");
+  return attn_bwd_impl(qkv, o, dout, lse, sc, eps, dqkv, delta, n_samples, tokens, heads, head_dim, dtype, stream);
 }

@@ -198,6 +198,12 @@ def cos_attn_bwd(qkv, o, dout, lse, dqkv, delta, n_samples, tokens, heads, head_
                                     head_dim, _dt(qkv), _stream()), "cos_attn_bwd")
 
 
+def cos_attn_bwd_qknorm(qkv, o, dout, lse, sc, dqkv, delta, n_samples, tokens, heads, head_dim):
+    """attention backward + q/k normalisation backward: dqkv = d/d(raw q, raw k, v)"""
+    check(lib().mapdit_cos_attn_bwd_qknorm(_ptr(qkv), _ptr(o), _ptr(dout), _ptr(lse), _ptr(sc), EPS, _ptr(dqkv), _ptr(delta), n_samples,
+                                           tokens, heads, head_dim, _dt(qkv), _stream()), "cos_attn_bwd_qknorm")
+
+
 def resid_bwd(R, y, dy, gate, dgate, ldmod, n_samples, tokens):
     d = R.shape[1]
     check(lib().mapdit_resid_bwd(_ptr(R), _ptr(y), _ptr(dy), _ptr(gate), _ptr(dgate), ldmod, n_samples, d, tokens, _dt(R), _stream()),

@@ -276,3 +276,32 @@ def test_checkpoint_roundtrips_through_torch_adam(tmp_path):
     assert worst < 5e-3
     # EMA hook ran with the reference's step numbering
     assert ts.ema.emas[0.05].blocks[0].attn.qkv_proj.weight.is_cuda
+
+
+@pytest.mark.parametrize("N,T,H,dtype", [(2, 256, 4, torch.bfloat16), (3, 64, 2, torch.bfloat16), (2, 64, 2, torch.float32)])
+def test_attention_backward_with_fused_qk_norm(N, T, H, dtype):
+    """cos_attn_bwd_qknorm (q/k-normalisation backward fused into the dq/dk epilogues on the tcgen05 path, separate kernel
+    behind the CUDA-core path) == autograd through normalize + SDPA (src/layers/attention.py:43-47)"""
+    from mapdit_b200 import ops
+    hd, D = 64, H * 64
+    raw = rnd(N * T, 3 * D, seed=13)
+    qkv = raw.clone()
+    sc = torch.empty(N * T, 2 * H, device="cuda")
+    ops.qk_normalize_save(qkv, sc, D, hd)
+    qkv = qkv.to(dtype)
+    dout = rnd(N * T, D, seed=14).to(dtype)
+    o = torch.empty(N * T, D, device="cuda", dtype=dtype)
+    lse = torch.empty(N * T, H, device="cuda")
+    ops.cos_attn(qkv, o, N, T, H, hd, lse=lse)
+    dqkv = torch.full_like(qkv, float("nan"))
+    delta = torch.empty(N * T, H, device="cuda")
+    ops.cos_attn_bwd_qknorm(qkv, o, dout, lse, sc, dqkv, delta, N, T, H, hd)
+    r = raw.double().requires_grad_(True)
+    r3 = r.view(N * T, 3, H, hd)
+    qn = r3[:, :2] * math.sqrt(hd) / (r3[:, :2].norm(dim=-1, keepdim=True) + 1e-4)
+    full = torch.cat([qn, r3[:, 2:]], 1).view(N, T, 3, H, hd).permute(2, 0, 3, 1, 4)
+    ro = F.scaled_dot_product_attention(full[0], full[1], full[2], scale=1 / math.sqrt(hd)).transpose(1, 2).reshape(N * T, D)
+    (ro * dout.double()).sum().backward()
+    e = rel_l2(dqkv.float(), r.grad)
+    print(f"fused attention + qk-norm backward {dtype}: rel-L2 vs autograd {e:.2e}")
+    assert e < (3e-5 if dtype == torch.float32 else 2.5e-2)
