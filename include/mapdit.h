@@ -238,6 +238,11 @@ int mapdit_resid_bwd(void* R, const void* y, void* dy, const float* gate, float*
 int mapdit_modulate_bwd(const void* dh, const void* x, void* R, const float* shift, const float* scale, const float* gain,
                         float* dshift, float* dscale, float* dg_partial, int64_t ldmod, int n_samples, int d, int tokens,
                         int accumulate, int dtype, void* stream);
+/* mapdit_modulate_bwd followed, in the same pass, by mapdit_resid_bwd of the residual that precedes it in the block
+ * (y, gate, dgate: that residual's branch output and gate; dy: its output gradient): 6 passes over [M, D] instead of 8 */
+int mapdit_modulate_resid_bwd(const void* dh, const void* x, void* R, const float* shift, const float* scale, const float* gain,
+                              float* dshift, float* dscale, float* dg_partial, const void* y, void* dy, const float* gate,
+                              float* dgate, int64_t ldmod, int n_samples, int d, int tokens, int accumulate, int dtype, void* stream);
 int mapdit_modulate_bwd_partials(int n_samples, int d);
 int mapdit_sum_partials(const float* partials, int n, float* out, int accumulate, void* stream);
 int mapdit_mp_silu_bwd(const void* du, const void* z, void* dz, int64_t n, int dtype, void* stream);

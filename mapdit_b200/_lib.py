@@ -47,6 +47,7 @@ SIGNATURES = {
     "mapdit_cos_attn_bwd_qknorm": [_p, _p, _p, _p, _p, _f, _p, _p, _i, _i, _i, _i, _i, _p],
     "mapdit_resid_bwd": [_p, _p, _p, _p, _p, _i64, _i, _i, _i, _i, _p],
     "mapdit_modulate_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _i, _i, _i, _p],
+    "mapdit_modulate_resid_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _i, _i, _i, _p],
     "mapdit_sum_partials": [_p, _i, _p, _i, _p],
     "mapdit_mp_silu_bwd": [_p, _p, _p, _i64, _i, _p],
     "mapdit_qk_normalize_save": [_p, _p, _i, _i, _i, _f, _i, _p],

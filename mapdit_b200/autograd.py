@@ -305,9 +305,23 @@ class Trainer:
             g.zero_()
             grads[id(gp)] = g
 
-        def modulate_block_bwd(i, branch, dh_, x_, accumulate):
-            """backward of the block-i modulation: R (+)= d/dx, per-sample vector grads into dmods, returns d(gain)"""
+        fuse_resid = adaln and not ln  # the residual backward that follows a modulate backward runs in the same kernel
+
+        def resid_of(i, branch):
+            """(y, gate, dgate) of block i's residual after branch 'a' / 'm'"""
+            return (B["a" if branch == "a" else "b"][i], mod(mods, i, "gate_" + branch), mod(dmods, i, "gate_" + branch))
+
+        def modulate_block_bwd(i, branch, dh_, x_, accumulate, then_resid=None):
+            """backward of the block-i modulation: R (+)= d/dx, per-sample vector grads into dmods, returns d(gain).
+            `then_resid` = (i', branch') also applies the backward of that residual to the updated R (fused kernel)."""
             gp = blk[i].gain_msa if branch == "a" else blk[i].gain_mlp
+            if then_resid is not None:
+                y_, gate_, dgate_ = resid_of(*then_resid)
+                ops.modulate_resid_bwd(dh_, x_, R, mod(mods, i, "shift_" + branch), mod(mods, i, "scale_" + branch), gp.data,
+                                       mod(dmods, i, "shift_" + branch), mod(dmods, i, "scale_" + branch), B["dgp"], y_, dY, gate_,
+                                       dgate_, ld, N, T, accumulate)
+                grads[id(gp)] = self._scalar_from_partials(B, npart, gp)
+                return
             if ln:
                 ops.ln_modulate_bwd(dh_, x_, R, B["ln1" if branch == "a" else "ln2"][i], mod(mods, i, "scale_" + branch),
                                     mod(dmods, i, "shift_" + branch), mod(dmods, i, "scale_" + branch), ld, N, T, accumulate)
@@ -344,15 +358,21 @@ class Trainer:
             ops.ln_modulate_bwd(dh, xF, R, B["ln1"][L], mods[:, fbase + D:], dmods[:, fbase:], dmods[:, fbase + D:], ld, N, T, False)
             zero_gain_grad(f.gain_mod)
         else:
-            ops.modulate_bwd(dh, xF, R, mods[:, fbase:], mods[:, fbase + D:], f.gain_mod.data, dmods[:, fbase:],
-                             dmods[:, fbase + D:], B["dgp"], ld, N, T, False)
+            if fuse_resid:  # + the backward of the last block's MLP residual
+                y_, gate_, dgate_ = resid_of(L - 1, "m")
+                ops.modulate_resid_bwd(dh, xF, R, mods[:, fbase:], mods[:, fbase + D:], f.gain_mod.data, dmods[:, fbase:],
+                                       dmods[:, fbase + D:], B["dgp"], y_, dY, gate_, dgate_, ld, N, T, False)
+            else:
+                ops.modulate_bwd(dh, xF, R, mods[:, fbase:], mods[:, fbase + D:], f.gain_mod.data, dmods[:, fbase:],
+                                 dmods[:, fbase + D:], B["dgp"], ld, N, T, False)
             grads[id(f.gain_mod)] = self._scalar_from_partials(B, npart, f.gain_mod)
         # ---- blocks, last to first
         for i in range(L - 1, -1, -1):
             xin, h1, qkv, o, a, xmid, h2, z, u, b = (B[k][i] for k in ("xin", "h1", "qkv", "o", "a", "xmid", "h2", "z", "u", "b"))
             wt = (lambda name: getattr(W, name)[i]) if bf else (lambda name: None)
             # MLP branch
-            ops.resid_bwd(R, b, dY, mod(mods, i, "gate_m"), mod(dmods, i, "gate_m"), ld, N, T)
+            if not fuse_resid:
+                ops.resid_bwd(R, b, dY, mod(mods, i, "gate_m"), mod(dmods, i, "gate_m"), ld, N, T)
             self._wgrad(dY, u, blk[i].mlp.net[2].weight, bf, B, grads)
             if bf:  # dgrad of fc2 with MPSiLU's backward fused into the epilogue
                 ops.gemm_bf16(dY, W.w2_t[i], dU, epilogue=_lib.EPI_SILU_BWD, resid=z)
@@ -361,9 +381,10 @@ class Trainer:
                 ops.mp_silu_bwd(dU, z, dU)
             self._wgrad(dU, h2, blk[i].mlp.net[0].weight, bf, B, grads)
             self._dgrad(dU, W.w1[i], wt("w1_t"), dh, bf)
-            modulate_block_bwd(i, "m", dh, xmid, True)
+            modulate_block_bwd(i, "m", dh, xmid, True, then_resid=(i, "a") if fuse_resid else None)
             # attention branch
-            ops.resid_bwd(R, a, dY, mod(mods, i, "gate_a"), mod(dmods, i, "gate_a"), ld, N, T)
+            if not fuse_resid:
+                ops.resid_bwd(R, a, dY, mod(mods, i, "gate_a"), mod(dmods, i, "gate_a"), ld, N, T)
             self._wgrad(dY, o, blk[i].attn.out_proj.weight, bf, B, grads)
             self._dgrad(dY, W.wo[i], wt("wo_t"), dh, bf)
             if cosine:  # attention backward with the q/k normalisation backward fused into its dq / dk epilogues
@@ -372,7 +393,7 @@ class Trainer:
                 ops.cos_attn_bwd(qkv, o, dh, B["lse"][i], dqkv, B["delta"], N, T, H, hd)
             self._wgrad(dqkv, h1, blk[i].attn.qkv_proj.weight, bf, B, grads)
             self._dgrad(dqkv, W.wqkv[i], wt("wqkv_t"), dh, bf)
-            modulate_block_bwd(i, "a", dh, xin, True)
+            modulate_block_bwd(i, "a", dh, xin, True, then_resid=(i - 1, "m") if (fuse_resid and i > 0) else None)
             if self.grad_hook is not None:
                 self.grad_hook([(p, grads[id(p)]) for p in blk[i].parameters() if id(p) in grads])
         # ---- patch embed (src/dit.py:81-84): x0 = (lin + pos)/2/sqrt(.5) -> d lin = R * 0.5/sqrt(.5)

@@ -220,6 +220,13 @@ def modulate_bwd(dh, x, R, shift, scale, gain, dshift, dscale, dg_partial, ldmod
                                     _ptr(dg_partial), ldmod, n_samples, d, tokens, int(accumulate), _dt(dh), _stream()), "modulate_bwd")
 
 
+def modulate_resid_bwd(dh, x, R, shift, scale, gain, dshift, dscale, dg_partial, y, dy, gate, dgate, ldmod, n_samples, tokens, accumulate):
+    d = dh.shape[1]
+    check(lib().mapdit_modulate_resid_bwd(_ptr(dh), _ptr(x), _ptr(R), _ptr(shift), _ptr(scale), _ptr(gain), _ptr(dshift), _ptr(dscale),
+                                          _ptr(dg_partial), _ptr(y), _ptr(dy), _ptr(gate), _ptr(dgate), ldmod, n_samples, d, tokens,
+                                          int(accumulate), _dt(dh), _stream()), "modulate_resid_bwd")
+
+
 def sum_partials(partials, n, out, accumulate=False):
     check(lib().mapdit_sum_partials(_ptr(partials), n, _ptr(out), int(accumulate), _stream()), "sum_partials")
 
