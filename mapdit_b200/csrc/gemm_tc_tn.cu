@@ -187,13 +187,23 @@ int launch(const void* dy, long long ldy, const void* x, long long ldx, float* c
   }
   const int mb = (n_out + BM - 1) / BM, nb = (k_in + BN - 1) / BN, kb = (m_tokens + BK - 1) / BK;
   const int tiles = mb * nb;
+  // Split-K so that the persistent grid runs whole waves: cost ~ ceil(items / SMs) rounds x (k-blocks per item).  The former
+  // "2 x SMs / tiles" rule gave 2.2-2.4 waves (3 rounds) for the qkv / fc1 / fc2 weight gradients of DiT-B/2.
   int splits = 1;
   if (tiles < 2 * sms) {
-    splits = (2 * sms + tiles - 1) / tiles;
-    if (splits > kb) splits = kb;
-    // make every split non-empty
-    const int per = (kb + splits - 1) / splits;
-    splits = (kb + per - 1) / per;
+    long long best_cost = -1;
+    const int max_s = kb < 32 ? kb : 32;
+    for (int sp = 1; sp <= max_s; ++sp) {
+      const int per = (kb + sp - 1) / sp;
+      const int real = (kb + per - 1) / per;  // every split non-empty
+      if (real != sp) continue;
+      const long long rounds = ((long long)tiles * sp + sms - 1) / sms;
+      const long long cost = rounds * (per + 6);  // + a few k-blocks' worth of per-item prologue / epilogue / reduction
+      if (best_cost < 0 || cost < best_cost) {
+        best_cost = cost;
+        splits = sp;
+      }
+    }
   }
   if (splits > 1) {
     cudaError_t e = cudaMemset2DAsync(c, (size_t)ldc * 4, 0, (size_t)k_in * 4, (size_t)n_out, stream);
