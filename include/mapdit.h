@@ -267,6 +267,7 @@ int mapdit_rotmod_fwd(const void* x, void* h, const float* rot, const float* sca
 int mapdit_rotmod_bwd(const void* dh, const void* x, void* R, const float* rot, const float* scale, const float* gain,
                       float* drot, float* dscale, float* dg_partial, int64_t ldmod, int n_samples, int d, int tokens,
                       int accumulate, int dtype, void* stream);
+int mapdit_rotmod_bwd_partials(int n_samples, int d); /* number of dgain partials mapdit_rotmod_bwd writes */
 /* x_embedder weight gradient dW[D, p*p*C+1] = scale * R[M, D]^T · (patchify(x)|1), patches gathered on the fly (src/dit.py:81-84) */
 int mapdit_patch_embed_wgrad(const void* R, const float* x, float* dW, int n_samples, int channels, int input_size,
                              int patch, int d, float scale, int dtype, void* stream);

@@ -100,6 +100,8 @@ def lib():
         L.mapdit_set_option.argtypes = [C.c_char_p, _i]
         L.mapdit_set_option.restype = _i
         L.mapdit_modulate_bwd_partials.restype = _i
+        L.mapdit_rotmod_bwd_partials.argtypes = [_i, _i]
+        L.mapdit_rotmod_bwd_partials.restype = _i
         _lib = L
         if os.environ.get("MAPDIT_GEMM_2CTA") is not None:
             L.mapdit_set_option(b"gemm_2cta", int(os.environ["MAPDIT_GEMM_2CTA"]))

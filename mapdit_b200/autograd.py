@@ -287,7 +287,7 @@ class Trainer:
         f = m.final_layer
         blk = m.blocks
         mods, dmods = B["mods"], B["dmods"]
-        npart = ops.modulate_bwd_partials(N, D)
+        npart = ops.modulate_bwd_partials(N, D) if m.modulation == "adaln" else ops.rotmod_bwd_partials(N, D)
         grads = {}
 
         lay = e.layout
@@ -365,7 +365,7 @@ class Trainer:
             else:
                 ops.modulate_bwd(dh, xF, R, mods[:, fbase:], mods[:, fbase + D:], f.gain_mod.data, dmods[:, fbase:],
                                  dmods[:, fbase + D:], B["dgp"], ld, N, T, False)
-            grads[id(f.gain_mod)] = self._scalar_from_partials(B, npart, f.gain_mod)
+            grads[id(f.gain_mod)] = self._scalar_from_partials(B, ops.modulate_bwd_partials(N, D), f.gain_mod)
         # ---- blocks, last to first
         for i in range(L - 1, -1, -1):
             xin, h1, qkv, o, a, xmid, h2, z, u, b = (B[k][i] for k in ("xin", "h1", "qkv", "o", "a", "xmid", "h2", "z", "u", "b"))

@@ -75,7 +75,34 @@ extern "C" int mapdit_resid_bwd(void* R, const void* y, void* dy, const float* g
 // FUSE: the residual backward that always follows in the block schedule (mapdit_resid_bwd on the freshly updated R, with the
 // branch output y and gate of the PREVIOUS residual) runs in the same pass: R'' = ca_r R', dy = cb_r gate R', dgate = sum_t cb_r y R'
 // — 6 passes over [M, D] instead of 8, and R' is never rounded to bf16 in between.
-template <typename T, bool FUSE>
+// V = columns per lane.  V = 4 (CTA = 128 columns) keeps the fused kernel under 80 registers so four CTAs fit per SM: the
+// first fused version (V = 8, 114 registers, two CTAs per SM) ran at 48 % of the HBM peak, below the two kernels it replaced.
+template <int V> struct VecIO;
+template <> struct VecIO<8> {
+  template <typename T> static __device__ __forceinline__ void ld(const T* p, float (&f)[8]) { load8(p, f); }
+  template <typename T> static __device__ __forceinline__ void st(T* p, const float (&f)[8]) { store8(p, f); }
+};
+template <> struct VecIO<4> {
+  static __device__ __forceinline__ void ld(const float* p, float (&f)[4]) {
+    const float4 a = *reinterpret_cast<const float4*>(p);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+  }
+  static __device__ __forceinline__ void ld(const bf16* p, float (&f)[4]) {
+    const uint2 u = *reinterpret_cast<const uint2*>(p);
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
+  }
+  static __device__ __forceinline__ void st(float* p, const float (&f)[4]) { *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]); }
+  static __device__ __forceinline__ void st(bf16* p, const float (&f)[4]) {
+    uint2 u;
+    *reinterpret_cast<__nv_bfloat162*>(&u.x) = __floats2bfloat162_rn(f[0], f[1]);
+    *reinterpret_cast<__nv_bfloat162*>(&u.y) = __floats2bfloat162_rn(f[2], f[3]);
+    *reinterpret_cast<uint2*>(p) = u;
+  }
+};
+
+template <typename T, bool FUSE, int V>
 __global__ void __launch_bounds__(256) modulate_bwd_kernel(const T* __restrict__ dh, const T* __restrict__ x, T* R,
                                                            const float* __restrict__ shift, const float* __restrict__ scale,
                                                            const float* __restrict__ gain, float* __restrict__ dshift,
@@ -83,22 +110,23 @@ __global__ void __launch_bounds__(256) modulate_bwd_kernel(const T* __restrict__
                                                            int d, int tokens, int accumulate, const T* __restrict__ y,
                                                            T* __restrict__ dy, const float* __restrict__ gate,
                                                            float* __restrict__ dgate, int var) {
-  __shared__ float red_sc[8][256];
-  __shared__ float red_sh[8][256];
-  __shared__ float red_gt[FUSE ? 8 : 1][256];
+  constexpr int CW = 32 * V;  // columns per CTA
+  __shared__ float red_sc[8][CW];
+  __shared__ float red_sh[8][CW];
+  __shared__ float red_gt[FUSE ? 8 : 1][CW];
   __shared__ float red[32];
   const bool plain_res = var & MAPDIT_VAR_PLAIN_RESID;
   const float ca_r = plain_res ? 1.0f : (1.0f - MP_RES_T) / MP_RES_DEN, cb_r = plain_res ? 1.0f : MP_RES_T / MP_RES_DEN;
-  float gt[8], a_gt[8];
+  float gt[V], a_gt[V];
   const int n = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int col = blockIdx.x * 256 + lane * 8;
+  const int col = blockIdx.x * CW + lane * V;
   const bool ok = col < d;
   const float g = *gain;
   const float den = mod_den(g);
   const float ca = (1.0f - g) / den, cb = g / den, cd = 1.0f / den;
-  float sc[8], sh[8], a_sc[8], a_sh[8], a_g = 0.f;
+  float sc[V], sh[V], a_sc[V], a_sh[V], a_g = 0.f;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
+  for (int j = 0; j < V; ++j) {
     sc[j] = ok ? scale[n * ldmod + col + j] : 0.f;
     sh[j] = ok ? shift[n * ldmod + col + j] : 0.f;
     a_sc[j] = 0.f;
@@ -111,28 +139,28 @@ __global__ void __launch_bounds__(256) modulate_bwd_kernel(const T* __restrict__
   if (ok) {
     for (int t = warp; t < tokens; t += 8) {
       const size_t off = ((size_t)n * tokens + t) * d + col;
-      float gh[8], xv[8], r[8];
-      load8(dh + off, gh);
-      load8(x + off, xv);
+      float gh[V], xv[V], r[V];
+      VecIO<V>::ld(dh + off, gh);
+      VecIO<V>::ld(x + off, xv);
       if (R) {
-        if (accumulate) load8(R + off, r);
+        if (accumulate) VecIO<V>::ld(R + off, r);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) r[j] = (accumulate ? r[j] : 0.f) + ca * sc[j] * gh[j];
+        for (int j = 0; j < V; ++j) r[j] = (accumulate ? r[j] : 0.f) + ca * sc[j] * gh[j];
         if (FUSE) {
-          float yv[8], o1[8];
-          load8(y + off, yv);
+          float yv[V], o1[V];
+          VecIO<V>::ld(y + off, yv);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
+          for (int j = 0; j < V; ++j) {
             o1[j] = gt[j] * r[j];
             a_gt[j] = fmaf(cb_r * yv[j], r[j], a_gt[j]);
             r[j] *= ca_r;
           }
-          store8(dy + off, o1);
+          VecIO<V>::st(dy + off, o1);
         }
-        store8(R + off, r);
+        VecIO<V>::st(R + off, r);
       }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < V; ++j) {
         a_sc[j] = fmaf(ca * xv[j], gh[j], a_sc[j]);
         a_sh[j] += gh[j];
         a_g = fmaf(gh[j], sh[j] - xv[j] * sc[j], a_g);
@@ -140,14 +168,14 @@ __global__ void __launch_bounds__(256) modulate_bwd_kernel(const T* __restrict__
     }
   }
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    red_sc[warp][lane * 8 + j] = a_sc[j];
-    red_sh[warp][lane * 8 + j] = a_sh[j];
-    if (FUSE) red_gt[warp][lane * 8 + j] = a_gt[j];
+  for (int j = 0; j < V; ++j) {
+    red_sc[warp][lane * V + j] = a_sc[j];
+    red_sh[warp][lane * V + j] = a_sh[j];
+    if (FUSE) red_gt[warp][lane * V + j] = a_gt[j];
   }
   float tot = block_sum(a_g * cd, red);  // contains the __syncthreads that publishes red_sc / red_sh
-  const int c = blockIdx.x * 256 + threadIdx.x;
-  if (c < d) {
+  const int c = blockIdx.x * CW + threadIdx.x;
+  if (threadIdx.x < CW && c < d) {
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) {
@@ -170,11 +198,11 @@ extern "C" int mapdit_modulate_bwd(const void* dh, const void* x, void* R, const
                                    float* dshift, float* dscale, float* dg_partial, int64_t ldmod, int n_samples, int d, int tokens,
                                    int accumulate, int dtype, void* stream) {
   MAPDIT_REQUIRE(dh && x && shift && scale && gain && dshift && dscale && dg_partial && n_samples > 0 && d % 8 == 0, "modulate_bwd: bad args");
-  dim3 grid((d + 255) / 256, n_samples);
+  dim3 grid((d + 127) / 128, n_samples);
   if (dtype == MAPDIT_F32)
-    modulate_bwd_kernel<float, false><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)dh, (const float*)x, (float*)R, shift, scale, gain, dshift, dscale, dg_partial, ldmod, d, tokens, accumulate, nullptr, nullptr, nullptr, nullptr, 0);
+    modulate_bwd_kernel<float, false, 4><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)dh, (const float*)x, (float*)R, shift, scale, gain, dshift, dscale, dg_partial, ldmod, d, tokens, accumulate, nullptr, nullptr, nullptr, nullptr, 0);
   else
-    modulate_bwd_kernel<bf16, false><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)dh, (const bf16*)x, (bf16*)R, shift, scale, gain, dshift, dscale, dg_partial, ldmod, d, tokens, accumulate, nullptr, nullptr, nullptr, nullptr, 0);
+    modulate_bwd_kernel<bf16, false, 4><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)dh, (const bf16*)x, (bf16*)R, shift, scale, gain, dshift, dscale, dg_partial, ldmod, d, tokens, accumulate, nullptr, nullptr, nullptr, nullptr, 0);
   MAPDIT_LAUNCH_CHECK("modulate_bwd");
   return MAPDIT_OK;
 }
@@ -185,16 +213,16 @@ extern "C" int mapdit_modulate_resid_bwd(const void* dh, const void* x, void* R,
   MAPDIT_REQUIRE(dh && x && R && shift && scale && gain && dshift && dscale && dg_partial && y && dy && gate && dgate && n_samples > 0 &&
                      d % 8 == 0,
                  "modulate_resid_bwd: bad args");
-  dim3 grid((d + 255) / 256, n_samples);
+  dim3 grid((d + 127) / 128, n_samples);
   const int var = mapdit_variant();
   if (dtype == MAPDIT_F32)
-    modulate_bwd_kernel<float, true><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)dh, (const float*)x, (float*)R, shift, scale, gain, dshift, dscale, dg_partial, ldmod, d, tokens, accumulate, (const float*)y, (float*)dy, gate, dgate, var);
+    modulate_bwd_kernel<float, true, 4><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)dh, (const float*)x, (float*)R, shift, scale, gain, dshift, dscale, dg_partial, ldmod, d, tokens, accumulate, (const float*)y, (float*)dy, gate, dgate, var);
   else
-    modulate_bwd_kernel<bf16, true><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)dh, (const bf16*)x, (bf16*)R, shift, scale, gain, dshift, dscale, dg_partial, ldmod, d, tokens, accumulate, (const bf16*)y, (bf16*)dy, gate, dgate, var);
+    modulate_bwd_kernel<bf16, true, 4><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)dh, (const bf16*)x, (bf16*)R, shift, scale, gain, dshift, dscale, dg_partial, ldmod, d, tokens, accumulate, (const bf16*)y, (bf16*)dy, gate, dgate, var);
   MAPDIT_LAUNCH_CHECK("modulate_resid_bwd");
   return MAPDIT_OK;
 }
-extern "C" int mapdit_modulate_bwd_partials(int n_samples, int d) { return ((d + 255) / 256) * n_samples; }
+extern "C" int mapdit_modulate_bwd_partials(int n_samples, int d) { return ((d + 127) / 128) * n_samples; }
 
 // out[0] (+)= sum(partials[0..n))   -- single CTA, fixed order
 __global__ void __launch_bounds__(256) sum_partials_kernel(const float* __restrict__ p, int n, float* __restrict__ out, int accumulate) {

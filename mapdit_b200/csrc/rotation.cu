@@ -135,3 +135,4 @@ extern "C" int mapdit_rotmod_bwd(const void* dh, const void* x, void* R, const f
   MAPDIT_LAUNCH_CHECK("rotmod_bwd");
   return MAPDIT_OK;
 }
+extern "C" int mapdit_rotmod_bwd_partials(int n_samples, int d) { return ((d + 255) / 256) * n_samples; }

@@ -214,6 +214,10 @@ def modulate_bwd_partials(n_samples, d):
     return lib().mapdit_modulate_bwd_partials(n_samples, d)
 
 
+def rotmod_bwd_partials(n_samples, d):
+    return lib().mapdit_rotmod_bwd_partials(n_samples, d)
+
+
 def modulate_bwd(dh, x, R, shift, scale, gain, dshift, dscale, dg_partial, ldmod, n_samples, tokens, accumulate):
     d = dh.shape[1]
     check(lib().mapdit_modulate_bwd(_ptr(dh), _ptr(x), _ptr(R), _ptr(shift), _ptr(scale), _ptr(gain), _ptr(dshift), _ptr(dscale),

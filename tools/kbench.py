@@ -90,6 +90,18 @@ def cases():
             ops.modulate_bwd(dh, x, R, mods, mods[:, D:], gain, dmods, dmods[:, D:], dgp, 6 * D, B, T, True)
         return fn, ("hbm", M * D * 2 * 4)
 
+    def modulate_resid_bwd():
+        sets = [(mk(M, D), mk(M, D), mk(M, D), mk(M, D), mk(M, D)) for _ in range(2)]
+        dgp = torch.empty(ops.modulate_bwd_partials(B, D), device=dev)
+        it = [0]
+
+        def fn():
+            dh, x, R, y, dy = sets[it[0] % 2]
+            it[0] += 1
+            ops.modulate_resid_bwd(dh, x, R, mods, mods[:, D:], gain, dmods, dmods[:, D:], dgp, y, dy, mods[:, 2 * D:], dmods[:, 2 * D:],
+                                   6 * D, B, T, True)
+        return fn, ("hbm", M * D * 2 * 6)
+
     def resid_bwd():
         sets = [(mk(M, D), mk(M, D), mk(M, D)) for _ in range(3)]
         it = [0]
@@ -141,6 +153,7 @@ def cases():
     c["wn_bwd_3072x768"] = wn_bwd(3072, 768)
     c["modulate_bwd"] = modulate_bwd
     c["resid_bwd"] = resid_bwd
+    c["modulate_resid_bwd"] = modulate_resid_bwd
     c["qk_norm_bwd"] = qk_norm_bwd
     c["adam_130M"] = adam
     c["gemm_qkv"] = gemm(3 * D, D, _lib.EPI_QKNORM)
