@@ -179,12 +179,12 @@ attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_cons
       mbar_wait(s_empty, (j & 1) ^ 1);
       tc_fence_after();
       const uint32_t k_addr = smem_u32(sKV + s * 2 * BLK_BYTES), v_addr = k_addr + BLK_BYTES;
+      // the S and dP chains accumulate into different TMEM tiles: issued alternately so consecutive MMAs are independent
 #pragma unroll
-      for (int k = 0; k < HD / 16; ++k)
+      for (int k = 0; k < HD / 16; ++k) {
         if (leader) umma_ss(tmem_base, make_smem_desc(q_addr + k * 32, 16, 1024), make_smem_desc(k_addr + k * 32, 16, 1024), idesc_s, k != 0);
-#pragma unroll
-      for (int k = 0; k < HD / 16; ++k)
         if (leader) umma_ss(tmem_base + 64, make_smem_desc(do_addr + k * 32, 16, 1024), make_smem_desc(v_addr + k * 32, 16, 1024), idesc_s, k != 0);
+      }
       if (leader) umma_commit(s_full);
     };
     mbar_wait(bar_q, 0);
@@ -349,11 +349,10 @@ attn_bwd_dkv_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_con
       tc_fence_after();
       const uint32_t q_addr = smem_u32(sQdO + s * 2 * BLK_BYTES), do_addr = q_addr + BLK_BYTES;
 #pragma unroll
-      for (int k = 0; k < HD / 16; ++k)
+      for (int k = 0; k < HD / 16; ++k) {  // S^T and dP^T chains interleaved (independent accumulators)
         if (leader) umma_ss(tmem_base, make_smem_desc(k_addr + k * 32, 16, 1024), make_smem_desc(q_addr + k * 32, 16, 1024), idesc_s, k != 0);
-#pragma unroll
-      for (int k = 0; k < HD / 16; ++k)
         if (leader) umma_ss(tmem_base + 64, make_smem_desc(v_addr + k * 32, 16, 1024), make_smem_desc(do_addr + k * 32, 16, 1024), idesc_s, k != 0);
+      }
       if (leader) umma_commit(s_full);
     };
     mbar_wait(bar_kv, 0);
@@ -365,13 +364,12 @@ attn_bwd_dkv_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_con
       tc_fence_after();
       const uint32_t q_addr = smem_u32(sQdO + s * 2 * BLK_BYTES), do_addr = q_addr + BLK_BYTES;
 #pragma unroll
-      for (int k = 0; k < CB / 16; ++k)
+      for (int k = 0; k < CB / 16; ++k) {  // dV and dK chains interleaved
         if (leader) umma_ss(tmem_base + 192, make_smem_desc(pt_addr + k * 32, 16, 1024), make_smem_desc(do_addr + k * 2048, 1024, 1024), idesc_a,
                 (j | k) != 0);
-#pragma unroll
-      for (int k = 0; k < CB / 16; ++k)
         if (leader) umma_ss(tmem_base + 128, make_smem_desc(dst_addr + k * 32, 16, 1024), make_smem_desc(q_addr + k * 2048, 1024, 1024), idesc_a,
                 (j | k) != 0);
+      }
       if (leader) umma_commit(&qd_empty[s]);
       if (leader) umma_commit(p_empty);
     }
