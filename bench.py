@@ -280,7 +280,10 @@ def run_ours(args, workload, finalize=True):
     dev = torch.device("cuda", local)
     B = args.batch
     torch.manual_seed(0)  # same replica on every rank
-    model = M.DIT_MODELS[MODEL](in_channels=4, input_size=32, num_classes=1000, compute_dtype=args.dtype)
+    S = args.input_size
+    off = {k: False for k in ("use_cosine_attention", "use_weight_normalization", "use_forced_weight_normalization", "use_mp_residual",
+                              "use_mp_silu", "use_no_layernorm", "use_mp_pos_enc", "use_mp_embedding")} if args.flags_off else {}
+    model = M.DIT_MODELS[MODEL](in_channels=4, input_size=S, num_classes=1000, compute_dtype=args.dtype, **off)
     with torch.no_grad():  # the reference initialises the gains to 0 (shift path unused): give them values like a trained net
         for name, prm in model.named_parameters():
             if prm.dim() == 0:
@@ -291,16 +294,16 @@ def run_ours(args, workload, finalize=True):
     pk = peaks()
     g = torch.Generator().manual_seed(1 + rank)
     # host-side (pinned) inputs for the e2e leg, device-resident copies for the kernel-only leg
-    z_host = torch.randn(B, 4, 32, 32, generator=g).pin_memory()
+    z_host = torch.randn(B, 4, S, S, generator=g).pin_memory()
     y_host = torch.randint(0, 1000, (B,), generator=g).pin_memory()
     t_host = torch.randint(0, 1000, (B,), generator=g).pin_memory()
     z_dev, y_dev, t_dev = z_host.to(dev), y_host.to(dev), t_host.to(dev)
-    out_host = torch.empty(B, 4, 32, 32).pin_memory()
+    out_host = torch.empty(B, 4, S, S).pin_memory()
     diffusion = M.create_diffusion(str(SAMPLING_STEPS) if workload == "sample" else "")
 
     if workload == "sample":
         model.eval()
-        gather = [torch.empty(B, 4, 32, 32, device=dev) for _ in range(world)] if world > 1 else None
+        gather = [torch.empty(B, 4, S, S, device=dev) for _ in range(world)] if world > 1 else None
 
         def step_dev():
             s = diffusion.p_sample_loop(model.forward, z_dev.shape, z_dev, clip_denoised=False, model_kwargs=dict(y=y_dev), device=dev)
@@ -326,7 +329,7 @@ def run_ours(args, workload, finalize=True):
             with torch.no_grad():
                 return model(z_dev, t_dev, y_dev)
 
-        out8 = torch.empty(B, 8, 32, 32).pin_memory()
+        out8 = torch.empty(B, 8, S, S).pin_memory()
 
         def step_e2e():
             with torch.no_grad():
@@ -340,7 +343,7 @@ def run_ours(args, workload, finalize=True):
         from mapdit_b200.train import TrainStep
         model.train()
         ts = TrainStep(model, diffusion, lr=1e-2, betas=(0.9, 0.99), world_size=world)
-        noise_dev = torch.randn(B, 4, 32, 32, device=dev)
+        noise_dev = torch.randn(B, 4, S, S, device=dev)
         noise_host = noise_dev.cpu().pin_memory()
 
         def step_dev():
@@ -422,9 +425,18 @@ def main():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--gemm-2cta", type=int, default=None, help="override the GEMM kernel choice: 1 = cta_group::2 256xBN tiles, 0 = 1-CTA 128xBN")
+    ap.add_argument("--model", default=None, help="other BASELINE.json configs (e.g. DiT-S/2, DiT-L/2, DiT-XL/2); default DiT-B/2")
+    ap.add_argument("--input-size", type=int, default=32, help="latent size (64 for BASELINE config 5)")
+    ap.add_argument("--sampling-steps", type=int, default=None, help="respaced steps of the sample workload (default 50)")
+    ap.add_argument("--flags-off", action="store_true", help="AdaLN baseline of BASELINE config 4: every --use-* MaP switch off")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    global MODEL, SAMPLING_STEPS
+    if args.model:
+        MODEL = args.model
+    if args.sampling_steps:
+        SAMPLING_STEPS = args.sampling_steps
     if args.impl == "reference":
         run_reference(args)
         return
