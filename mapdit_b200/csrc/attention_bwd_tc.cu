@@ -16,6 +16,10 @@
 int mapdit_attn_bwd_simt(const void* qkv, const void* o, const void* dout, const float* lse, void* dqkv, float* delta, int n_samples,
                          int tokens, int heads, int head_dim, int dtype, void* stream);
 
+int mapdit_attn_mma_bwd(const void* qkv, const void* o, const void* dout, const float* lse, void* dqkv, float* delta, int n, int tokens,
+                        int heads, int hd, void* stream);
+bool mapdit_attn_mma_supported(int tokens, int hd);
+
 namespace {
 using namespace tc;
 
@@ -458,7 +462,9 @@ static int attn_bwd_impl(const void* qkv, const void* o, const void* dout, const
                          float* delta, int n_samples, int tokens, int heads, int head_dim, int dtype, void* stream) {
   MAPDIT_REQUIRE(qkv && o && dout && lse && dqkv && delta && n_samples > 0 && tokens > 0, "cos_attn_bwd: bad args");
   if (!(dtype == MAPDIT_BF16 && head_dim == HD && tokens % CB == 0) || (mapdit_variant() & MAPDIT_VAR_DOT_ATTN)) {
-    int rc = mapdit_attn_bwd_simt(qkv, o, dout, lse, dqkv, delta, n_samples, tokens, heads, head_dim, dtype, stream);
+    int rc = (dtype == MAPDIT_BF16 && mapdit_attn_mma_supported(tokens, head_dim))
+                 ? mapdit_attn_mma_bwd(qkv, o, dout, lse, dqkv, delta, n_samples, tokens, heads, head_dim, stream)
+                 : mapdit_attn_bwd_simt(qkv, o, dout, lse, dqkv, delta, n_samples, tokens, heads, head_dim, dtype, stream);
     if (rc != MAPDIT_OK || !sc) return rc;
     return mapdit_qk_norm_bwd(dqkv, qkv, sc, n_samples * tokens, heads * head_dim, head_dim, eps, dtype, stream);
   }

@@ -6,6 +6,8 @@ int mapdit_attn_tc_fwd(const void* qkv, void* o, float* lse, int n, int tokens, 
 bool mapdit_attn_tc_supported(int tokens, int hd);
 int mapdit_attn_tc2_fwd(const void* qkv, void* o, float* lse, int n, int tokens, int heads, int hd, void* stream);
 bool mapdit_attn_tc2_supported(int tokens, int hd);
+int mapdit_attn_mma_fwd(const void* qkv, void* o, float* lse, int n, int tokens, int heads, int hd, void* stream);
+bool mapdit_attn_mma_supported(int tokens, int hd);
 int g_mapdit_attn_v2 = 1;  // runtime option "attn_v2": the one-CTA-per-SM ping-pong kernel where the shape qualifies
 
 extern "C" int mapdit_cos_attn_fwd(const void* qkv, void* o, float* lse, int n_samples, int tokens, int heads, int head_dim, int dtype,
@@ -18,5 +20,8 @@ extern "C" int mapdit_cos_attn_fwd(const void* qkv, void* o, float* lse, int n_s
     return mapdit_attn_tc2_fwd(qkv, o, lse, n_samples, tokens, heads, head_dim, stream);
   if (dtype == MAPDIT_BF16 && cosine && mapdit_attn_tc_supported(tokens, head_dim))
     return mapdit_attn_tc_fwd(qkv, o, lse, n_samples, tokens, heads, head_dim, stream);
+  // head_dim 72 (DiT-XL) and plain dot-product attention: warp-level tensor-core MMAs with a running max
+  if (dtype == MAPDIT_BF16 && mapdit_attn_mma_supported(tokens, head_dim))
+    return mapdit_attn_mma_fwd(qkv, o, lse, n_samples, tokens, heads, head_dim, stream);
   return mapdit_attn_simt_fwd(qkv, o, lse, n_samples, tokens, heads, head_dim, dtype, stream);
 }

@@ -305,3 +305,36 @@ def test_attention_backward_with_fused_qk_norm(N, T, H, dtype):
     e = rel_l2(dqkv.float(), r.grad)
     print(f"fused attention + qk-norm backward {dtype}: rel-L2 vs autograd {e:.2e}")
     assert e < (3e-5 if dtype == torch.float32 else 2.5e-2)
+
+
+@pytest.mark.parametrize("N,T,H,hd,cosine", [(2, 128, 3, 72, True), (1, 1024, 2, 72, True), (2, 256, 4, 64, False), (3, 64, 2, 32, False)])
+def test_generic_mma_attention_forward_backward(N, T, H, hd, cosine):
+    """attention_mma.cu (warp-level tensor-core MMAs, running-max softmax): head_dim 72 (DiT-XL) and plain dot-product attention
+    (use_cosine_attention=False, unbounded logits), forward + log-sum-exp + backward vs fp64 autograd of SDPA"""
+    from mapdit_b200 import ops
+    D = H * hd
+    qkv = rnd(N * T, 3 * D, seed=17) * (1.0 if cosine else 1.5)
+    if cosine:
+        ops.qk_normalize(qkv, D, hd)
+    qkv = qkv.bfloat16()
+    dout = rnd(N * T, D, seed=18).bfloat16()
+    o = torch.full((N * T, D), float("nan"), device="cuda", dtype=torch.bfloat16)
+    lse = torch.full((N * T, H), float("nan"), device="cuda")
+    dqkv = torch.full_like(qkv, float("nan"))
+    delta = torch.empty(N * T, H, device="cuda")
+    prev = ops.set_variant(0 if cosine else 16)
+    try:
+        ops.cos_attn(qkv, o, N, T, H, hd, lse=lse)
+        ops.cos_attn_bwd(qkv, o, dout, lse, dqkv, delta, N, T, H, hd)
+        torch.cuda.synchronize()
+    finally:
+        ops.set_variant(prev)
+    ref_in = qkv.double().requires_grad_(True)
+    q, k, v = ref_in.view(N, T, 3, H, hd).permute(2, 0, 3, 1, 4)
+    ro = F.scaled_dot_product_attention(q, k, v, scale=1 / math.sqrt(hd)).transpose(1, 2).reshape(N * T, D)
+    (ro * dout.double()).sum().backward()
+    ref_lse = torch.logsumexp(q.detach() @ k.detach().transpose(-1, -2) / math.sqrt(hd), dim=-1).permute(0, 2, 1).reshape(N * T, H)
+    e_o, e_g = rel_l2(o.float(), ro.detach()), rel_l2(dqkv.float(), ref_in.grad)
+    print(f"mma attention N={N} T={T} H={H} hd={hd} cosine={cosine}: o {e_o:.2e}, dqkv {e_g:.2e}")
+    assert e_o < 8e-3 and e_g < 2.5e-2
+    assert float((lse.double() - ref_lse).abs().max()) < 2e-2
