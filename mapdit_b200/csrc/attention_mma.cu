@@ -50,6 +50,22 @@ __device__ __forceinline__ void load_tile(bf16* __restrict__ s, const bf16* __re
   }
 }
 
+// the same with cp.async (16-byte chunks, zero fill for the padding channels): completes with cp_async_wait
+template <int HD, int HDP, int P>
+__device__ __forceinline__ void load_tile_async(bf16* __restrict__ s, const bf16* __restrict__ g, size_t ld) {
+  constexpr int CH = HDP / 8;
+  for (int i = threadIdx.x; i < 64 * CH; i += NT) {
+    const int r = i / CH, c = (i - r * CH) * 8;
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s + r * P + c);
+    const bf16* src = g + (size_t)r * ld + (c < HD ? c : 0);
+    const int nbytes = c < HD ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
+  }
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // A fragments (16 rows of this warp x HDP) from a [64][P] tile
 template <int HDP, int P>
 __device__ __forceinline__ void load_a_frags(uint32_t (&a)[HDP / 16][4], const bf16* s, int warp, int lane) {
@@ -116,14 +132,17 @@ template <int HD, int HDP>
 __global__ void __launch_bounds__(NT) attn_mma_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ o, float* __restrict__ lse,
                                                           int tokens, int heads, float scale_log2) {
   constexpr int P = HDP + 8;
-  __shared__ __align__(16) bf16 sQ[BM * P];
-  __shared__ __align__(16) bf16 sK[BN * P];
-  __shared__ __align__(16) bf16 sV[BN * P];
+  extern __shared__ __align__(16) uint8_t smem_fwd[];
+  bf16* sQ = reinterpret_cast<bf16*>(smem_fwd);
+  bf16* sKV = sQ + BM * P;  // stage b: K at sKV + b*2*BN*P, V right after
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * BM;
   const size_t D = (size_t)heads * HD, ld = 3 * D;
   const bf16* base = qkv + (size_t)n * tokens * ld + (size_t)h * HD;
   load_tile<HD, HDP, P>(sQ, base + (size_t)q0 * ld, ld);
+  load_tile_async<HD, HDP, P>(sKV, base + D, ld);
+  load_tile_async<HD, HDP, P>(sKV + BN * P, base + 2 * D, ld);
+  cp_async_commit();
   __syncthreads();
   uint32_t aq[HDP / 16][4];
   load_a_frags<HDP, P>(aq, sQ, warp, lane);
@@ -133,10 +152,18 @@ __global__ void __launch_bounds__(NT) attn_mma_fwd_kernel(const bf16* __restrict
 #pragma unroll
     for (int e = 0; e < 4; ++e) acc[i][e] = 0.f;
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;  // rows g and g + 8, in log2 units
-  for (int k0 = 0; k0 < tokens; k0 += BN) {
-    __syncthreads();
-    load_tile<HD, HDP, P>(sK, base + (size_t)k0 * ld + D, ld);
-    load_tile<HD, HDP, P>(sV, base + (size_t)k0 * ld + 2 * D, ld);
+  for (int k0 = 0, it = 0; k0 < tokens; k0 += BN, ++it) {
+    const bf16* sK = sKV + (it & 1) * 2 * BN * P;
+    const bf16* sV = sK + BN * P;
+    if (k0 + BN < tokens) {  // prefetch the next K/V block into the other stage while this one is consumed
+      bf16* nk = sKV + ((it + 1) & 1) * 2 * BN * P;
+      load_tile_async<HD, HDP, P>(nk, base + (size_t)(k0 + BN) * ld + D, ld);
+      load_tile_async<HD, HDP, P>(nk + BN * P, base + (size_t)(k0 + BN) * ld + 2 * D, ld);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
     __syncthreads();
     float s[8][4];
     gemm_abt<HDP, P>(s, aq, sK, lane);
@@ -176,6 +203,7 @@ __global__ void __launch_bounds__(NT) attn_mma_fwd_kernel(const bf16* __restrict
       acc[i][3] *= c1;
     }
     gemm_pb<HDP, P>(acc, s, sV, lane);
+    __syncthreads();  // everyone is done with this stage before the next iteration's prefetch overwrites it
   }
   l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
   l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
@@ -200,8 +228,8 @@ __global__ void __launch_bounds__(NT) attn_mma_dq_kernel(const bf16* __restrict_
   extern __shared__ __align__(16) uint8_t smem_dq[];
   bf16* sQ = reinterpret_cast<bf16*>(smem_dq);
   bf16* sdO = sQ + BM * P;
-  bf16* sK = sdO + BM * P;
-  bf16* sV = sK + BN * P;
+  bf16* sKV = sdO + BM * P;  // two stages of {K, V}
+  bf16* sK = sKV;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2;
   const int n = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * BM;
   const size_t D = (size_t)heads * HD, ld = 3 * D;
@@ -233,14 +261,26 @@ __global__ void __launch_bounds__(NT) attn_mma_dq_kernel(const bf16* __restrict_
 #pragma unroll
     for (int e = 0; e < 4; ++e) acc[i][e] = 0.f;
   const float sl2 = scale * 1.4426950408889634f;
-  for (int k0 = 0; k0 < tokens; k0 += BN) {
-    __syncthreads();
-    load_tile<HD, HDP, P>(sK, base + (size_t)k0 * ld + D, ld);
-    load_tile<HD, HDP, P>(sV, base + (size_t)k0 * ld + 2 * D, ld);
+  __syncthreads();  // the O tile parked in stage 0 has been consumed
+  load_tile_async<HD, HDP, P>(sKV, base + D, ld);
+  load_tile_async<HD, HDP, P>(sKV + BN * P, base + 2 * D, ld);
+  cp_async_commit();
+  for (int k0 = 0, it = 0; k0 < tokens; k0 += BN, ++it) {
+    const bf16* sKc = sKV + (it & 1) * 2 * BN * P;
+    const bf16* sVc = sKc + BN * P;
+    if (k0 + BN < tokens) {
+      bf16* nk = sKV + ((it + 1) & 1) * 2 * BN * P;
+      load_tile_async<HD, HDP, P>(nk, base + (size_t)(k0 + BN) * ld + D, ld);
+      load_tile_async<HD, HDP, P>(nk + BN * P, base + (size_t)(k0 + BN) * ld + 2 * D, ld);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
     __syncthreads();
     float s[8][4], dp[8][4];
-    gemm_abt<HDP, P>(s, aq, sK, lane);
-    gemm_abt<HDP, P>(dp, ado, sV, lane);
+    gemm_abt<HDP, P>(s, aq, sKc, lane);
+    gemm_abt<HDP, P>(dp, ado, sVc, lane);
 #pragma unroll
     for (int nb = 0; nb < 8; ++nb) {
       s[nb][0] = ex2a(fmaf(s[nb][0], sl2, -L0)) * (dp[nb][0] - d0);
@@ -248,7 +288,8 @@ __global__ void __launch_bounds__(NT) attn_mma_dq_kernel(const bf16* __restrict_
       s[nb][2] = ex2a(fmaf(s[nb][2], sl2, -L1)) * (dp[nb][2] - d1);
       s[nb][3] = ex2a(fmaf(s[nb][3], sl2, -L1)) * (dp[nb][3] - d1);
     }
-    gemm_pb<HDP, P>(acc, s, sK, lane);
+    gemm_pb<HDP, P>(acc, s, sKc, lane);
+    __syncthreads();
   }
   store_rows<HD, HDP>(dqkv + row * ld + (size_t)h * HD, ld, acc, scale, scale, lane);
 }
@@ -262,10 +303,8 @@ __global__ void __launch_bounds__(NT) attn_mma_dkv_kernel(const bf16* __restrict
   extern __shared__ __align__(16) uint8_t smem_dkv[];
   bf16* sK = reinterpret_cast<bf16*>(smem_dkv);
   bf16* sV = sK + BM * P;
-  bf16* sQ = sV + BM * P;
-  bf16* sdO = sQ + BN * P;
-  float* sL = reinterpret_cast<float*>(sdO + BN * P);  // [64] lse * log2e of the query block
-  float* sD = sL + BN;                                 // [64] delta
+  bf16* sQdO = sV + BM * P;  // two stages of {Q, dO}
+  float* sLD = reinterpret_cast<float*>(sQdO + 4 * BN * P);  // two stages of {lse * log2e [64], delta [64]} of the query block
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, t = lane & 3;
   const int n = blockIdx.z, h = blockIdx.y, k0 = blockIdx.x * BM;
   const size_t D = (size_t)heads * HD, ld = 3 * D;
@@ -282,14 +321,28 @@ __global__ void __launch_bounds__(NT) attn_mma_dkv_kernel(const bf16* __restrict
 #pragma unroll
     for (int e = 0; e < 4; ++e) dk[i][e] = dv[i][e] = 0.f;
   const float sl2 = scale * 1.4426950408889634f;
-  for (int q0 = 0; q0 < tokens; q0 += BN) {
-    __syncthreads();
-    load_tile<HD, HDP, P>(sQ, base + (size_t)q0 * ld, ld);
-    load_tile<HD, HDP, P>(sdO, dout + ((size_t)n * tokens + q0) * D + (size_t)h * HD, D);
+  auto prefetch = [&](int q0, int stage) {
+    bf16* nq = sQdO + stage * 2 * BN * P;
+    load_tile_async<HD, HDP, P>(nq, base + (size_t)q0 * ld, ld);
+    load_tile_async<HD, HDP, P>(nq + BN * P, dout + ((size_t)n * tokens + q0) * D + (size_t)h * HD, D);
+    cp_async_commit();
     if (threadIdx.x < BN) {
       const size_t qr = (size_t)n * tokens + q0 + threadIdx.x;
-      sL[threadIdx.x] = lse[qr * heads + h] * 1.4426950408889634f;
-      sD[threadIdx.x] = delta[qr * heads + h];
+      sLD[stage * 2 * BN + threadIdx.x] = lse[qr * heads + h] * 1.4426950408889634f;
+      sLD[stage * 2 * BN + BN + threadIdx.x] = delta[qr * heads + h];
+    }
+  };
+  prefetch(0, 0);
+  for (int q0 = 0, it = 0; q0 < tokens; q0 += BN, ++it) {
+    const bf16* sQ = sQdO + (it & 1) * 2 * BN * P;
+    const bf16* sdO = sQ + BN * P;
+    const float* sL = sLD + (it & 1) * 2 * BN;
+    const float* sD = sL + BN;
+    if (q0 + BN < tokens) {
+      prefetch(q0 + BN, (it + 1) & 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
     }
     __syncthreads();
     float s[8][4], dp[8][4];
@@ -312,6 +365,7 @@ __global__ void __launch_bounds__(NT) attn_mma_dkv_kernel(const bf16* __restrict
     }
     gemm_pb<HDP, P>(dv, s, sdO, lane);
     gemm_pb<HDP, P>(dk, dp, sQ, lane);
+    __syncthreads();
   }
   const size_t row = (size_t)n * tokens + k0 + warp * 16;
   store_rows<HD, HDP>(dqkv + row * ld + D + (size_t)h * HD, ld, dk, scale, scale, lane);
@@ -320,15 +374,21 @@ __global__ void __launch_bounds__(NT) attn_mma_dkv_kernel(const bf16* __restrict
 
 template <int HD, int HDP>
 int launch_fwd(const void* qkv, void* o, float* lse, int n, int tokens, int heads, cudaStream_t s) {
+  constexpr int SM_FWD = 5 * 64 * (HDP + 8) * 2;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(attn_mma_fwd_kernel<HD, HDP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_FWD);
+    attr = true;
+  }
   dim3 grid(tokens / BM, heads, n);
-  attn_mma_fwd_kernel<HD, HDP><<<grid, NT, 0, s>>>((const bf16*)qkv, (bf16*)o, lse, tokens, heads, 1.4426950408889634f / sqrtf((float)HD));
+  attn_mma_fwd_kernel<HD, HDP><<<grid, NT, SM_FWD, s>>>((const bf16*)qkv, (bf16*)o, lse, tokens, heads, 1.4426950408889634f / sqrtf((float)HD));
   return MAPDIT_OK;
 }
 template <int HD, int HDP>
 int launch_bwd(const void* qkv, const void* o, const void* dout, const float* lse, void* dqkv, float* delta, int n, int tokens, int heads,
                cudaStream_t s) {
   constexpr int P = HDP + 8;
-  constexpr int SM_DQ = 4 * 64 * P * 2, SM_DKV = 4 * 64 * P * 2 + 2 * 64 * 4;
+  constexpr int SM_DQ = 6 * 64 * P * 2, SM_DKV = 6 * 64 * P * 2 + 4 * 64 * 4;
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(attn_mma_dq_kernel<HD, HDP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_DQ);
