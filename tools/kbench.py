@@ -173,10 +173,12 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--json", default=None)
     ap.add_argument("--opt", action="append", default=[], help="runtime option name=value (mapdit_set_option), e.g. attn_v2=0")
+    ap.add_argument("--variant", type=int, default=0, help="MAPDIT_VAR_* word (16 = dot-product attention -> mma.sync kernels)")
     a = ap.parse_args()
     for kv in a.opt:
         k, v = kv.split("=")
         _lib.set_option(k, int(v))
+    ops.set_variant(a.variant)
     tf, hbm = peaks()
     res = {}
     all_cases = cases()
