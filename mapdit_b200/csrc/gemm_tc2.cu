@@ -231,7 +231,11 @@ int launch2(const mapdit_gemm_args* g, const EpiParams& ep, cudaStream_t stream,
 // returns MAPDIT_ERR_UNSUPPORTED (without setting an error) when the shape should go to the 1-CTA kernel
 int mapdit_gemm_bf16_2cta(const mapdit_gemm_args* g, const gemm_epi::EpiParams& ep, cudaStream_t stream, int num_sms) {
   const int mb = (g->m + BM - 1) / BM;
-  if (g->n % 256 == 0 && (long long)((mb + 1) / 2) * (g->n / 256) >= num_sms / 2) return launch2<256>(g, ep, stream, num_sms);
+  // 256-wide tiles also when N is only a multiple of 128 and the clipped last tile wastes <= 12.5 % of the MMA work
+  // (N = 1152, 3456: DiT-S qkv, DiT-XL): half the B-operand traffic per FLOP of the 128-wide kernel
+  const int nb256 = (g->n + 255) / 256;
+  const bool wide_ok = g->n % 256 == 0 || (g->n % 128 == 0 && (long long)nb256 * 256 * 8 <= (long long)g->n * 9);
+  if (wide_ok && (long long)((mb + 1) / 2) * nb256 >= num_sms / 2) return launch2<256>(g, ep, stream, num_sms);
   if (g->n % 128 == 0 && (long long)((mb + 1) / 2) * (g->n / 128) >= num_sms) return launch2<128>(g, ep, stream, num_sms);
   return MAPDIT_ERR_UNSUPPORTED;
 }

@@ -41,7 +41,7 @@ def test_gemm_bf16_store(m, n, k, two_cta):
     assert rel_l2(out32, ref) < 1e-5
 
 
-@pytest.mark.parametrize("N,T,D", [(2, 64, 384), (3, 256, 256), (1, 256, 768), (33, 64, 384), (40, 256, 256), (41, 128, 768)])
+@pytest.mark.parametrize("N,T,D", [(2, 64, 384), (3, 256, 256), (1, 256, 768), (33, 64, 384), (40, 256, 256), (41, 128, 768), (160, 64, 384)])
 @pytest.mark.parametrize("two_cta", [0, 1])
 def test_gemm_bf16_fused_epilogues(N, T, D, two_cta):
     from mapdit_b200 import _lib, ops
