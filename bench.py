@@ -24,6 +24,11 @@ os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 MODEL = "DiT-B/2"
 SAMPLING_STEPS = 50
+# BASELINE.json configs[2] / north_star target: "DiT-B/2 MaP (all mp flags + rotation-and-scaling modulation)".  The reference
+# snapshot ships only the MP-AdaLN modulation ("adaln", the parity-pinned variant): it is timed too and reported in `adaln`.
+MODULATION = "rotation_scaling"
+MOD_NAMES = {"adaln": "MP-AdaLN modulation (reference snapshot)", "rotation_scaling": "rotation-and-scaling modulation",
+             "rotation": "rotation modulation"}
 
 
 def flops_per_image(model):
@@ -33,7 +38,8 @@ def flops_per_image(model):
     lin = T * L * 24 * D * D
     attn = T * L * 4 * T * D
     emb = T * (2 * (p * p * C + 1) * D + 2 * D * 2 * p * p * C)
-    cond = L * 12 * D * D + 4 * D * D + 2 * (256 * D + D * D) + 32 * D
+    modw = {"adaln": 6, "rotation_scaling": 5, "rotation": 3}[getattr(model, "modulation", "adaln")]  # modulation GEMM width / D
+    cond = L * 2 * modw * D * D + 4 * D * D + 2 * (256 * D + D * D) + 32 * D
     return dict(fwd=lin + attn + emb + cond, train=3 * (lin + emb + cond) + 3.5 * attn)
 
 
@@ -106,7 +112,7 @@ def run_reference(args, workload=None, emit=True):
     from oracle import mapdit_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cfg = O.config_for(MODEL)
+    cfg = O.config_for(MODEL, modulation=MODULATION)
     sd = O.init_state_dict(cfg, seed=0)
     B = 8
     g = torch.Generator().manual_seed(1)
@@ -154,7 +160,7 @@ def run_reference(args, workload=None, emit=True):
     line = {"impl": "reference", "metric": metric_name(workload), "value": value, "unit": unit, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(workload), "model": MODEL, "batch_per_step": B},
+            "config": {"workload": workload_name(workload), "model": MODEL, "modulation": MODULATION, "batch_per_step": B},
             "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     if emit:
@@ -167,9 +173,10 @@ def metric_name(w):
 
 
 def workload_name(w):
-    return {"sample": f"{MODEL} MaP, {SAMPLING_STEPS}-step respaced p_sample_loop, 32x32x4 latents, batch 256/GPU, no CFG",
-            "train": f"{MODEL} MaP training step (training_losses + backward + Adam), 32x32x4 latents, batch 256/GPU",
-            "forward": f"{MODEL} MaP eval forward, 32x32x4 latents, batch 256/GPU"}[w]
+    mp = f"{MODEL} MaP + {MOD_NAMES[MODULATION]}"
+    return {"sample": f"{mp}, {SAMPLING_STEPS}-step respaced p_sample_loop, 32x32x4 latents, batch 256/GPU, no CFG",
+            "train": f"{mp} training step (training_losses + backward + Adam), 32x32x4 latents, batch 256/GPU",
+            "forward": f"{mp} eval forward, 32x32x4 latents, batch 256/GPU"}[w]
 
 
 # --------------------------------------------------------------------------------------------- our arm (B200)
@@ -178,7 +185,7 @@ def cpu_baseline(workload, seconds_budget=20.0):
     from oracle import mapdit_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cfg = O.config_for(MODEL)
+    cfg = O.config_for(MODEL, modulation=MODULATION)
     sd = O.init_state_dict(cfg, seed=0)
     B = 8
     g = torch.Generator().manual_seed(1)
@@ -243,12 +250,22 @@ def kernel_roofline(model, B, pk):
     mods = torch.randn(B, 6 * D, device=dev)
     gain = torch.tensor(0.3, device=dev)
     res = {}
+    rot = getattr(model, "modulation", "adaln") != "adaln"
+    cs = torch.empty(B, D, device=dev)
+    ops.rot_table(mods[:, D:], gain, cs, 6 * D, D)
+
+    def resid_mod(a, w):  # residual + next modulation fused into the GEMM epilogue (rotation table or shift/scale/gain)
+        if rot:
+            return ops.gemm_bf16(a, w, x, epilogue=_lib.EPI_RESID_ROT, out2=h, resid=x, gate=mods, shift=cs, scale=mods[:, 2 * D:],
+                                 ldmod=6 * D, ldrot=D, tokens=T)
+        return ops.gemm_bf16(a, w, x, epilogue=_lib.EPI_RESID_MOD, out2=h, resid=x, gate=mods, shift=mods[:, D:], scale=mods[:, 2 * D:],
+                             gain=gain, ldmod=6 * D, tokens=T)
     cases = {
         "qkv_gemm_qknorm": (lambda: ops.gemm_bf16(h, wqkv, qkv, epilogue=_lib.EPI_QKNORM, tokens=T, head_dim=D // H, qk_cols=2 * D), 2 * M * D * 3 * D),
         "attn": (lambda: ops.cos_attn(qkv, o, B, T, H, D // H), 4 * M * T * D),
-        "out_gemm_resid_mod": (lambda: ops.gemm_bf16(o, wo, x, epilogue=_lib.EPI_RESID_MOD, out2=h, resid=x, gate=mods, shift=mods[:, D:], scale=mods[:, 2 * D:], gain=gain, ldmod=6 * D, tokens=T), 2 * M * D * D),
+        "out_gemm_resid_mod": (lambda: resid_mod(o, wo), 2 * M * D * D),
         "fc1_gemm_mpsilu": (lambda: ops.gemm_bf16(h, w1, u4, epilogue=_lib.EPI_MPSILU), 2 * M * D * 4 * D),
-        "fc2_gemm_resid_mod": (lambda: ops.gemm_bf16(u4, w2, x, epilogue=_lib.EPI_RESID_MOD, out2=h, resid=x, gate=mods, shift=mods[:, D:], scale=mods[:, 2 * D:], gain=gain, ldmod=6 * D, tokens=T), 2 * M * 4 * D * D),
+        "fc2_gemm_resid_mod": (lambda: resid_mod(u4, w2), 2 * M * 4 * D * D),
     }
     for k, (fn, fl) in cases.items():
         ms = time_kernel(fn)
@@ -283,7 +300,7 @@ def run_ours(args, workload, finalize=True):
     S = args.input_size
     off = {k: False for k in ("use_cosine_attention", "use_weight_normalization", "use_forced_weight_normalization", "use_mp_residual",
                               "use_mp_silu", "use_no_layernorm", "use_mp_pos_enc", "use_mp_embedding")} if args.flags_off else {}
-    model = M.DIT_MODELS[MODEL](in_channels=4, input_size=S, num_classes=1000, compute_dtype=args.dtype, **off)
+    model = M.DIT_MODELS[MODEL](in_channels=4, input_size=S, num_classes=1000, compute_dtype=args.dtype, modulation=MODULATION, **off)
     with torch.no_grad():  # the reference initialises the gains to 0 (shift path unused): give them values like a trained net
         for name, prm in model.named_parameters():
             if prm.dim() == 0:
@@ -342,6 +359,8 @@ def run_ours(args, workload, finalize=True):
     else:
         from mapdit_b200.train import TrainStep
         model.train()
+        if args.wgrad_stream is not None:
+            model.engine.trainer.wgrad_stream = bool(args.wgrad_stream)
         ts = TrainStep(model, diffusion, lr=1e-2, betas=(0.9, 0.99), world_size=world)
         noise_dev = torch.randn(B, 4, S, S, device=dev)
         noise_host = noise_dev.cpu().pin_memory()
@@ -399,7 +418,8 @@ def run_ours(args, workload, finalize=True):
         line = {"metric": metric_name(workload), "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-                "config": {"workload": workload_name(workload), "model": MODEL, "batch_per_gpu": B, "global_batch": B * world,
+                "config": {"workload": workload_name(workload), "model": MODEL, "modulation": MODULATION, "batch_per_gpu": B,
+                           "global_batch": B * world,
                            "parallelism": f"dp{world}" if world > 1 else "single",
                            "l2": "per-step working set (activations ~100 MB per [M,D] tensor, 2.4 GB per block) exceeds the 126 MB L2; no flush needed",
                            "weights": "random init (torch seed 0), reference init distributions, gains 0.3", "clip_denoised": False},
@@ -425,14 +445,22 @@ def main():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--gemm-2cta", type=int, default=None, help="override the GEMM kernel choice: 1 = cta_group::2 256xBN tiles, 0 = 1-CTA 128xBN")
+    ap.add_argument("--wgrad-stream", type=int, default=None, help="A/B: 0 = weight-gradient GEMMs on the main stream, 1 = on a second stream (default)")
     ap.add_argument("--model", default=None, help="other BASELINE.json configs (e.g. DiT-S/2, DiT-L/2, DiT-XL/2); default DiT-B/2")
     ap.add_argument("--input-size", type=int, default=32, help="latent size (64 for BASELINE config 5)")
     ap.add_argument("--sampling-steps", type=int, default=None, help="respaced steps of the sample workload (default 50)")
     ap.add_argument("--flags-off", action="store_true", help="AdaLN baseline of BASELINE config 4: every --use-* MaP switch off")
+    ap.add_argument("--modulation", default=None, choices=["adaln", "rotation_scaling", "rotation"],
+                    help="default rotation_scaling (BASELINE configs[2]); adaln = the reference snapshot's MP-AdaLN")
+    ap.add_argument("--no-adaln-arm", action="store_true", help="skip the extra MP-AdaLN timing of the default run")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    global MODEL, SAMPLING_STEPS
+    global MODEL, SAMPLING_STEPS, MODULATION
+    if args.modulation:
+        MODULATION = args.modulation
+    if args.flags_off:
+        MODULATION = "adaln"
     if args.model:
         MODEL = args.model
     if args.sampling_steps:
@@ -449,8 +477,25 @@ def main():
     if args.workload == "both":
         # BASELINE.json's metric has two halves: the training step is the primary value, the 50-step sampler rides along
         line = run_ours(args, "train", finalize=False)
-        sline = run_ours(args, "sample", finalize=True)
+        sline = run_ours(args, "sample", finalize=False)
+        adaln = None
+        if MODULATION != "adaln" and not args.no_adaln_arm:
+            # the parity-pinned variant (the only modulation the reference snapshot has code for), device-timed only
+            main_mod, MODULATION = MODULATION, "adaln"
+            args.no_roofline, args.no_cpu_baseline = True, True
+            at, asmp = run_ours(args, "train", finalize=False), run_ours(args, "sample", finalize=False)
+            MODULATION = main_mod
+            if at is not None:
+                adaln = {"modulation": "adaln", "note": "reference snapshot's MP-AdaLN modulation (parity pinned by the reference)",
+                         "train": {k: at[k] for k in ("value", "unit", "ms_per_step", "gpu_launches")},
+                         "sample50": {k: asmp[k] for k in ("value", "unit", "ms_per_step", "gpu_launches")},
+                         "e2e": {"train": at["e2e"], "sample50": asmp["e2e"]}}
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            dist.destroy_process_group()
         if line is not None:
+            if adaln is not None:
+                line["adaln"] = adaln
             line["metric"] = "dit_b2_map_train_img_per_s (+ sample50 img/s in `sample50`)"
             keep = ("value", "unit", "ms_per_step", "e2e", "gpu_launches", "clocks", "cpu_baseline")
             line["sample50"] = {k: sline[k] for k in keep}

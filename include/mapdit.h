@@ -87,6 +87,9 @@ int mapdit_gemm_f32(const float* a, int64_t sam, int64_t sak, const float* b, in
                                    (src/blocks/dit_block.py:35-36, src/utils.py:11-16)                            */
 #define MAPDIT_EPI_RESID 4      /* x' = mp_sum(x, gate*acc, .3) only                                              */
 #define MAPDIT_EPI_SILU_BWD 5   /* out = acc * d/dz[silu(z)/0.596], z = `resid` (dgrad of fc2 fused with MPSiLU's backward) */
+#define MAPDIT_EPI_RESID_ROT 6  /* x' = mp_sum(x, gate*acc, .3); h = R(theta) x' (* scale): rotation modulation (README.md:1,3 of the
+                                   reference; no reference code, SURVEY.md §A.8 — UNPINNED).  `shift` points at the per-sample
+                                   (cos, sin) table of mapdit_rot_table (leading dimension `ldrot`), `scale` may be null  */
 
 typedef struct mapdit_gemm_args {
   const void* a;   /* bf16 [M, K] */
@@ -108,6 +111,7 @@ typedef struct mapdit_gemm_args {
   int epilogue;
   int out_dtype;   /* MAPDIT_BF16 or MAPDIT_F32 (EPI_STORE only) */
   float eps;
+  int64_t ldrot;   /* EPI_RESID_ROT: leading dimension of the (cos, sin) table `shift` points into (0 = ldmod) */
 } mapdit_gemm_args;
 
 int mapdit_gemm_bf16(const mapdit_gemm_args* args, void* stream);
@@ -268,6 +272,16 @@ int mapdit_rotmod_bwd(const void* dh, const void* x, void* R, const float* rot, 
                       float* drot, float* dscale, float* dg_partial, int64_t ldmod, int n_samples, int d, int tokens,
                       int accumulate, int dtype, void* stream);
 int mapdit_rotmod_bwd_partials(int n_samples, int d); /* number of dgain partials mapdit_rotmod_bwd writes */
+/* the same followed, in the same pass, by the backward of the residual that precedes the modulation in the block schedule
+ * (mapdit_resid_bwd on the updated R with branch output y / gate): R'' = .7/den R', dy = .3/den gate R', dgate = sum_t .3/den y R' */
+int mapdit_rotmod_resid_bwd(const void* dh, const void* x, void* R, const float* rot, const float* scale, const float* gain,
+                            float* drot, float* dscale, float* dg_partial, const void* y, void* dy, const float* gate,
+                            float* dgate, int64_t ldmod, int n_samples, int d, int tokens, int accumulate, int dtype,
+                            void* stream);
+/* per-sample rotation table for MAPDIT_EPI_RESID_ROT: cs[n, 2i] = cos(rot[n, i] * gain), cs[n, 2i+1] = sin(rot[n, i] * gain),
+ * i < d/2; the second {rot2, gain2, cs2} triple is optional (both branches of a block in one launch) */
+int mapdit_rot_table(const float* rot, const float* gain, float* cs, const float* rot2, const float* gain2, float* cs2,
+                     int64_t ldmod, int64_t ldcs, int n_samples, int d, void* stream);
 /* x_embedder weight gradient dW[D, p*p*C+1] = scale * R[M, D]^T · (patchify(x)|1), patches gathered on the fly (src/dit.py:81-84) */
 int mapdit_patch_embed_wgrad(const void* R, const float* x, float* dW, int n_samples, int channels, int input_size,
                              int patch, int d, float scale, int dtype, void* stream);

@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmapdit.so")
 
 F32, BF16 = 0, 1
-EPI_STORE, EPI_QKNORM, EPI_MPSILU, EPI_RESID_MOD, EPI_RESID, EPI_SILU_BWD = 0, 1, 2, 3, 4, 5
+EPI_STORE, EPI_QKNORM, EPI_MPSILU, EPI_RESID_MOD, EPI_RESID, EPI_SILU_BWD, EPI_RESID_ROT = 0, 1, 2, 3, 4, 5, 6
 
 _p, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 
@@ -20,7 +20,7 @@ class GemmArgs(C.Structure):
     _fields_ = [("a", _p), ("b", _p), ("out", _p), ("out2", _p), ("resid", _p), ("gate", _p), ("shift", _p),
                 ("scale", _p), ("gain", _p), ("aux", _p), ("lda", _i64), ("ldb", _i64), ("ldo", _i64), ("ldmod", _i64),
                 ("m", _i), ("n", _i), ("k", _i), ("tokens", _i), ("head_dim", _i), ("qk_cols", _i),
-                ("epilogue", _i), ("out_dtype", _i), ("eps", _f)]
+                ("epilogue", _i), ("out_dtype", _i), ("eps", _f), ("ldrot", _i64)]
 
 
 SIGNATURES = {
@@ -61,6 +61,8 @@ SIGNATURES = {
     "mapdit_axpby": [_p, _p, _f, _i, _i64, _p],
     "mapdit_rotmod_fwd": [_p, _p, _p, _p, _p, _i64, _i, _i, _i, _i, _p],
     "mapdit_rotmod_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _i, _i, _i, _p],
+    "mapdit_rotmod_resid_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _i, _i, _i, _p],
+    "mapdit_rot_table": [_p, _p, _p, _p, _p, _p, _i64, _i64, _i, _i, _p],
     "mapdit_patch_embed_wgrad": [_p, _p, _p, _i, _i, _i, _i, _i, _f, _i, _p],
     "mapdit_patch_embed": [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _i, _i, _i, _i, _p],
     "mapdit_fourier": [_p, _p, _p, _p, _i, _i, _p],

@@ -9,6 +9,8 @@ Gradient flow per block (reverse of src/blocks/dit_block.py:32-37), R = dL/dx re
   resid_bwd -> fc2 wgrad/dgrad -> mp_silu_bwd -> fc1 wgrad/dgrad -> modulate_bwd (+= R)
   resid_bwd -> out-proj wgrad/dgrad -> attention bwd -> qk_norm_bwd -> qkv wgrad/dgrad -> modulate_bwd (+= R)
 """
+import os
+
 import torch
 
 from . import _lib, ops
@@ -43,6 +45,14 @@ class Trainer:
         self._bufs = {}
         self.grad_buffers = None  # optional {id(param): preallocated grad tensor} (TrainStep's flat buffer)
         self.grad_hook = None  # optional callable(list_of_(param, grad)) fired as soon as a block's grads are final
+        # bf16 path: the weight-gradient GEMMs (+ their weight-norm backward) are issued on a second stream.  They are off the
+        # critical path of the backward (nothing downstream reads dW), use 58 registers x 256 threads and ~193 KB of shared
+        # memory, so the HBM-bound elementwise backward kernels of the main stream co-reside with them on every SM instead
+        # of running alone on an idle tensor pipe.  MAPDIT_WGRAD_STREAM=0 turns it off (A/B in bench.py --wgrad-stream).
+        self.wgrad_stream = os.environ.get("MAPDIT_WGRAD_STREAM", "1") != "0"
+        self._side = None      # the second stream
+        self._side_on = False  # active inside the current backward
+        self._side_reads = {}  # scratch buffer name -> event recorded after the side-stream GEMM that last read it
 
     # ------------------------------------------------------------------ buffers
     def buffers(self, N, mode, dev):
@@ -74,7 +84,7 @@ class Trainer:
             u=[torch.empty(M, Hm, **a) for _ in range(L)], b=[torch.empty(M, D, **a) for _ in range(L)],
             lin=torch.empty(M, ppc2, **a),
             # backward scratch
-            R=torch.empty(M, D, **a), dY=torch.empty(M, D, **a), dh=torch.empty(M, D, **a), dqkv=torch.empty(M, 3 * D, **a),
+            R=torch.empty(M, D, **a), dY=torch.empty(M, D, **a), dY2=torch.empty(M, D, **a), dh=torch.empty(M, D, **a), dqkv=torch.empty(M, 3 * D, **a),
             dU=torch.empty(M, Hm, **a), dlin=torch.empty(M, ppc2, **a), dmods=torch.empty(N, W, **f),
             delta=torch.empty(M, H, **f), dgp=torch.empty(ops.modulate_bwd_partials(N, D), **f),
             dsmu=torch.empty(N, **f), dssg=torch.empty(N, **f), dlmu=torch.empty(N, 8, **f), dlsg=torch.empty(N, 8, **f),
@@ -83,6 +93,8 @@ class Trainer:
             dmods16=torch.empty(N, W, device=dev, dtype=torch.bfloat16) if mode == "bf16" else None,
             dWs=torch.empty(max(Hm * D, W * D), **f),  # scratch for d(effective weight), largest weight
         )
+        if m.modulation != "adaln":  # (cos, sin) tables for the EPI_RESID_ROT epilogue (see Engine.workspace)
+            B["rotcs"] = torch.empty(N, L * 2 * D, **f)
         if not m.flags["use_no_layernorm"]:  # LayerNorm statistics {mean, rstd} per token row, per modulate site
             B["ln1"] = [torch.empty(M, 2, **f) for _ in range(L + 1)]  # index L = final layer
             B["ln2"] = [torch.empty(M, 2, **f) for _ in range(L)]
@@ -99,9 +111,16 @@ class Trainer:
 
     def backward(self, saved, dout):
         prev = ops.set_variant(self.m.variant)
+        self._side_on = bool(self.wgrad_stream and saved["mode"] == "bf16")
+        if self._side_on and (self._side is None or self._side.device != saved["dev"]):
+            self._side = torch.cuda.Stream(device=saved["dev"])
         try:
-            return self._backward(saved, dout)
+            out = self._backward(saved, dout)
+            self._join_side()  # every gradient is complete on the caller's stream
+            return out
         finally:
+            self._side_on = False
+            self._side_reads.clear()
             ops.set_variant(prev)
 
     def _forward(self, x, t, y, drop_mask):
@@ -182,6 +201,13 @@ class Trainer:
                     ops.qk_normalize_save(dst, B["sc"][i], D, hd)
 
         fused = bf and adaln and not ln and cosine and hd == 64
+        fused_rot = bf and not adaln and not ln and cosine and hd == 64
+        if fused_rot:
+            rcs = B["rotcs"]
+            for i in range(L):
+                ops.rot_table(mod(i, "rot_a"), blk[i].gain_msa.data, rcs[:, (2 * i) * D:], ld, D,
+                              mod(i, "rot_m"), blk[i].gain_mlp.data, rcs[:, (2 * i + 1) * D:])
+            has_sc = "scale_a" in lay
         if adaln and not ln:
             ops.patch_embed(x, W.wx, m.pos_embed, B["xin"][0], B["h1"][0], mod(0, "shift_a"), mod(0, "scale_a"), blk[0].gain_msa.data,
                             ld, m.patch_size)
@@ -203,6 +229,20 @@ class Trainer:
                 ops.gemm_bf16(h2, W.w1[i], u, epilogue=_lib.EPI_MPSILU, out2=z)
                 ops.gemm_bf16(u, W.w2[i], xnext, epilogue=_lib.EPI_RESID_MOD, out2=hnext, resid=xmid, gate=mod(i, "gate_m"), shift=nsh,
                               scale=nsc, gain=ngn, ldmod=ld, tokens=T, aux=b)
+            elif fused_rot:
+                ops.gemm_bf16(h1, W.wqkv[i], qkv, epilogue=_lib.EPI_QKNORM, tokens=T, head_dim=hd, qk_cols=2 * D, aux=B["sc"][i])
+                ops.cos_attn(qkv, o, N, T, H, hd, lse=B["lse"][i])
+                ops.gemm_bf16(o, W.wo[i], xmid, epilogue=_lib.EPI_RESID_ROT, out2=h2, resid=xin, gate=mod(i, "gate_a"),
+                              shift=rcs[:, (2 * i + 1) * D:], scale=mod(i, "scale_m") if has_sc else None, ldmod=ld,
+                              ldrot=rcs.stride(0), tokens=T, aux=a)
+                ops.gemm_bf16(h2, W.w1[i], u, epilogue=_lib.EPI_MPSILU, out2=z)
+                if i + 1 < L:
+                    ops.gemm_bf16(u, W.w2[i], xnext, epilogue=_lib.EPI_RESID_ROT, out2=hnext, resid=xmid, gate=mod(i, "gate_m"),
+                                  shift=rcs[:, (2 * i + 2) * D:], scale=mod(i + 1, "scale_a") if has_sc else None, ldmod=ld,
+                                  ldrot=rcs.stride(0), tokens=T, aux=b)
+                else:
+                    ops.gemm_bf16(u, W.w2[i], xnext, epilogue=_lib.EPI_RESID_MOD, out2=hnext, resid=xmid, gate=mod(i, "gate_m"),
+                                  shift=mods[:, fbase:], scale=mods[:, fbase + D:], gain=f.gain_mod.data, ldmod=ld, tokens=T, aux=b)
             elif bf:
                 qkv_proj(i, h1, qkv)
                 ops.cos_attn(qkv, o, N, T, H, hd, lse=B["lse"][i])
@@ -242,20 +282,47 @@ class Trainer:
         else:
             ops.gemm_f32(dy, w_eff, out=out, trans_b=True)
 
-    def _wgrad(self, dy, xin, param, bf, B, grads, rows=None):
-        """param.grad = weight_norm_bwd(forced param, dy^T @ xin)"""
+    def _wgrad(self, dy, xin, param, bf, B, grads, reads=None):
+        """param.grad = weight_norm_bwd(forced param, dy^T @ xin).  `reads` names the scratch buffer `dy` lives in: with the
+        second stream active the caller must call _before_write(name) before the main stream overwrites that buffer."""
         n_out, k_in = param.shape
         dW = B["dWs"][: n_out * k_in].view(n_out, k_in)
+        g = self._gbuf(param)
+        if self._side_on:
+            main = torch.cuda.current_stream()
+            ev = torch.cuda.Event()
+            ev.record(main)
+            self._side.wait_event(ev)  # dy (and every earlier main-stream use of the dWs scratch) is complete
+            with torch.cuda.stream(self._side):
+                ops.gemm_bf16_tn(dy, xin, dW)
+                grads[id(param)] = self._wn_bwd(param, dW, g)
+                if reads is not None:
+                    done = torch.cuda.Event()
+                    done.record(self._side)
+                    self._side_reads[reads] = done
+            return
         if bf:
             ops.gemm_bf16_tn(dy, xin, dW)
         else:
             ops.gemm_f32(dy, xin, out=dW, trans_a=True, trans_b=True)
-        grads[id(param)] = self._wn_bwd(param, dW)
+        grads[id(param)] = self._wn_bwd(param, dW, g)
 
-    def _wn_bwd(self, param, dW):
+    def _before_write(self, name):
+        """main stream is about to overwrite scratch buffer `name`: wait for the side-stream GEMM that still reads it"""
+        ev = self._side_reads.pop(name, None)
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
+
+    def _join_side(self):
+        if self._side_on:
+            torch.cuda.current_stream().wait_stream(self._side)
+            self._side_reads.clear()
+
+    def _wn_bwd(self, param, dW, g=None):
         """gradient of the raw parameter from the gradient of its effective weight (tangent projection of the
         weight normalisation, or the identity with use_weight_normalization=False)"""
-        g = self._gbuf(param)
+        if g is None:
+            g = self._gbuf(param)
         if self.m.flags["use_weight_normalization"]:
             ops.weight_norm_bwd(param.data, dW, g)
         else:
@@ -305,21 +372,30 @@ class Trainer:
             g.zero_()
             grads[id(gp)] = g
 
-        fuse_resid = adaln and not ln  # the residual backward that follows a modulate backward runs in the same kernel
+        fuse_resid = not ln  # the residual backward that follows a modulate / rotation backward runs in the same kernel
 
         def resid_of(i, branch):
-            """(y, gate, dgate) of block i's residual after branch 'a' / 'm'"""
-            return (B["a" if branch == "a" else "b"][i], mod(mods, i, "gate_" + branch), mod(dmods, i, "gate_" + branch))
+            """(y, gate, dgate, dy) of block i's residual after branch 'a' / 'm'; the two branches use separate dy buffers so the
+            side-stream weight-gradient GEMM of one can still read its dy while the main stream produces the other's"""
+            self._before_write("dYa" if branch == "a" else "dYm")
+            return (B["a" if branch == "a" else "b"][i], mod(mods, i, "gate_" + branch), mod(dmods, i, "gate_" + branch),
+                    dYa if branch == "a" else dYm)
 
         def modulate_block_bwd(i, branch, dh_, x_, accumulate, then_resid=None):
             """backward of the block-i modulation: R (+)= d/dx, per-sample vector grads into dmods, returns d(gain).
             `then_resid` = (i', branch') also applies the backward of that residual to the updated R (fused kernel)."""
             gp = blk[i].gain_msa if branch == "a" else blk[i].gain_mlp
             if then_resid is not None:
-                y_, gate_, dgate_ = resid_of(*then_resid)
-                ops.modulate_resid_bwd(dh_, x_, R, mod(mods, i, "shift_" + branch), mod(mods, i, "scale_" + branch), gp.data,
-                                       mod(dmods, i, "shift_" + branch), mod(dmods, i, "scale_" + branch), B["dgp"], y_, dY, gate_,
-                                       dgate_, ld, N, T, accumulate)
+                y_, gate_, dgate_, dY_ = resid_of(*then_resid)
+                if adaln:
+                    ops.modulate_resid_bwd(dh_, x_, R, mod(mods, i, "shift_" + branch), mod(mods, i, "scale_" + branch), gp.data,
+                                           mod(dmods, i, "shift_" + branch), mod(dmods, i, "scale_" + branch), B["dgp"], y_, dY_, gate_,
+                                           dgate_, ld, N, T, accumulate)
+                else:
+                    has_sc = ("scale_" + branch) in lay
+                    ops.rotmod_resid_bwd(dh_, x_, R, mod(mods, i, "rot_" + branch), mod(mods, i, "scale_" + branch) if has_sc else None,
+                                         gp.data, mod(dmods, i, "rot_" + branch), mod(dmods, i, "scale_" + branch) if has_sc else None,
+                                         B["dgp"], y_, dY_, gate_, dgate_, ld, N, T, accumulate)
                 grads[id(gp)] = self._scalar_from_partials(B, npart, gp)
                 return
             if ln:
@@ -337,7 +413,7 @@ class Trainer:
                                accumulate)
             grads[id(gp)] = self._scalar_from_partials(B, npart, gp)
 
-        R, dY, dh, dqkv, dU = B["R"], B["dY"], B["dh"], B["dqkv"], B["dU"]
+        R, dYm, dYa, dh, dqkv, dU = B["R"], B["dY"], B["dY2"], B["dh"], B["dqkv"], B["dU"]
         # ---- final layer (src/blocks/final_layer.py:53-59)
         ops.final_bwd(dout, B["lin"], B["smu"], B["ssg"], B["dlin"], B["dsmu"], B["dssg"], m.patch_size)
         gref_mu, gref_sg = self._gbuf(f.mean_scale.reference), self._gbuf(f.sigma_scale.reference)
@@ -359,9 +435,9 @@ class Trainer:
             zero_gain_grad(f.gain_mod)
         else:
             if fuse_resid:  # + the backward of the last block's MLP residual
-                y_, gate_, dgate_ = resid_of(L - 1, "m")
+                y_, gate_, dgate_, dY_ = resid_of(L - 1, "m")
                 ops.modulate_resid_bwd(dh, xF, R, mods[:, fbase:], mods[:, fbase + D:], f.gain_mod.data, dmods[:, fbase:],
-                                       dmods[:, fbase + D:], B["dgp"], y_, dY, gate_, dgate_, ld, N, T, False)
+                                       dmods[:, fbase + D:], B["dgp"], y_, dY_, gate_, dgate_, ld, N, T, False)
             else:
                 ops.modulate_bwd(dh, xF, R, mods[:, fbase:], mods[:, fbase + D:], f.gain_mod.data, dmods[:, fbase:],
                                  dmods[:, fbase + D:], B["dgp"], ld, N, T, False)
@@ -372,30 +448,43 @@ class Trainer:
             wt = (lambda name: getattr(W, name)[i]) if bf else (lambda name: None)
             # MLP branch
             if not fuse_resid:
-                ops.resid_bwd(R, b, dY, mod(mods, i, "gate_m"), mod(dmods, i, "gate_m"), ld, N, T)
-            self._wgrad(dY, u, blk[i].mlp.net[2].weight, bf, B, grads)
+                self._before_write("dYm")
+                ops.resid_bwd(R, b, dYm, mod(mods, i, "gate_m"), mod(dmods, i, "gate_m"), ld, N, T)
+            self._wgrad(dYm, u, blk[i].mlp.net[2].weight, bf, B, grads, reads="dYm")
+            self._before_write("dU")
             if bf:  # dgrad of fc2 with MPSiLU's backward fused into the epilogue
-                ops.gemm_bf16(dY, W.w2_t[i], dU, epilogue=_lib.EPI_SILU_BWD, resid=z)
+                ops.gemm_bf16(dYm, W.w2_t[i], dU, epilogue=_lib.EPI_SILU_BWD, resid=z)
             else:
-                self._dgrad(dY, W.w2[i], None, dU, bf)
+                self._dgrad(dYm, W.w2[i], None, dU, bf)
                 ops.mp_silu_bwd(dU, z, dU)
-            self._wgrad(dU, h2, blk[i].mlp.net[0].weight, bf, B, grads)
+            self._wgrad(dU, h2, blk[i].mlp.net[0].weight, bf, B, grads, reads="dU")
             self._dgrad(dU, W.w1[i], wt("w1_t"), dh, bf)
             modulate_block_bwd(i, "m", dh, xmid, True, then_resid=(i, "a") if fuse_resid else None)
             # attention branch
             if not fuse_resid:
-                ops.resid_bwd(R, a, dY, mod(mods, i, "gate_a"), mod(dmods, i, "gate_a"), ld, N, T)
-            self._wgrad(dY, o, blk[i].attn.out_proj.weight, bf, B, grads)
-            self._dgrad(dY, W.wo[i], wt("wo_t"), dh, bf)
+                self._before_write("dYa")
+                ops.resid_bwd(R, a, dYa, mod(mods, i, "gate_a"), mod(dmods, i, "gate_a"), ld, N, T)
+            self._wgrad(dYa, o, blk[i].attn.out_proj.weight, bf, B, grads, reads="dYa")
+            self._dgrad(dYa, W.wo[i], wt("wo_t"), dh, bf)
+            self._before_write("dqkv")
             if cosine:  # attention backward with the q/k normalisation backward fused into its dq / dk epilogues
                 ops.cos_attn_bwd_qknorm(qkv, o, dh, B["lse"][i], B["sc"][i], dqkv, B["delta"], N, T, H, hd)
             else:
                 ops.cos_attn_bwd(qkv, o, dh, B["lse"][i], dqkv, B["delta"], N, T, H, hd)
-            self._wgrad(dqkv, h1, blk[i].attn.qkv_proj.weight, bf, B, grads)
+            self._wgrad(dqkv, h1, blk[i].attn.qkv_proj.weight, bf, B, grads, reads="dqkv")
             self._dgrad(dqkv, W.wqkv[i], wt("wqkv_t"), dh, bf)
             modulate_block_bwd(i, "a", dh, xin, True, then_resid=(i - 1, "m") if (fuse_resid and i > 0) else None)
             if self.grad_hook is not None:
-                self.grad_hook([(p, grads[id(p)]) for p in blk[i].parameters() if id(p) in grads])
+                pairs = [(p, grads[id(p)]) for p in blk[i].parameters() if id(p) in grads]
+                if self._side_on:  # the block's weight gradients complete on the second stream: fire the hook (NCCL) there
+                    ev = torch.cuda.Event()
+                    ev.record(torch.cuda.current_stream())
+                    self._side.wait_event(ev)  # ... after the gain gradients the main stream just produced
+                    with torch.cuda.stream(self._side):
+                        self.grad_hook(pairs)
+                else:
+                    self.grad_hook(pairs)
+        self._join_side()  # the tail uses the dWs scratch on the main stream
         # ---- patch embed (src/dit.py:81-84): x0 = (lin + pos)/2/sqrt(.5) -> d lin = R * 0.5/sqrt(.5)
         K1 = m.x_embedder.weight.shape[1]
         dWx = B["dWs"][: D * K1].view(D, K1)

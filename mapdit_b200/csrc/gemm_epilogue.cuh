@@ -24,6 +24,7 @@ struct EpiParams {
   const float* gain;
   void* aux;
   long long ldo, ldmod;
+  long long ldshift;  // leading dimension of `shift` (= ldmod except for the RESID_ROT (cos, sin) table)
   int M, N, tokens, qk_cols, epilogue, out_f32;
   float eps;
   int variant;  // MAPDIT_VAR_* word of the launching thread
@@ -104,7 +105,8 @@ __device__ __forceinline__ void load_row32_f32(const float* p, float (&f)[32], i
 template <int BN, typename WaitFn>
 __device__ __forceinline__ void run_tile(const EpiParams& ep, const EpiTmaps& tm, Stager& st, uint32_t t_row, int row, int n_blk, int half,
                                          float gsc, float inv_den, WaitFn wait_acc) {
-  const bool reads_resid = ep.epilogue == MAPDIT_EPI_RESID || ep.epilogue == MAPDIT_EPI_RESID_MOD || ep.epilogue == MAPDIT_EPI_SILU_BWD;
+  const bool mod2 = ep.epilogue == MAPDIT_EPI_RESID_MOD || ep.epilogue == MAPDIT_EPI_RESID_ROT;  // writes h to out2
+  const bool reads_resid = ep.epilogue == MAPDIT_EPI_RESID || mod2 || ep.epilogue == MAPDIT_EPI_SILU_BWD;
   const bool row_ok = row < ep.M;
   const long long sample = row_ok ? row / ep.tokens : 0;
   uint4 pre[4];
@@ -119,14 +121,14 @@ __device__ __forceinline__ void run_tile(const EpiParams& ep, const EpiTmaps& tm
   // same address right before use; ncu showed their L2 round trips exposed twice per chunk (long-scoreboard stalls on the
   // first FFMA/FMUL).  Lanes 0-2 pull the NEXT chunk's lines into L1 one chunk ahead; the streaming residual loads bypass
   // L1 allocation so the ~24 KB of L1 left beside the operand ring keeps them.
-  const bool has_vecs = ep.epilogue == MAPDIT_EPI_RESID || ep.epilogue == MAPDIT_EPI_RESID_MOD;
+  const bool has_vecs = ep.epilogue == MAPDIT_EPI_RESID || mod2;
   auto prefetch_vecs = [&](int c) {
     const int col = n_blk * BN + c;
     const int lane = st.lane;
     if (!has_vecs || c >= BN || col >= ep.N || lane > 2) return;
     const float* base = lane == 0 ? ep.gate : (lane == 1 ? ep.shift : ep.scale);
-    if (lane > 0 && ep.epilogue != MAPDIT_EPI_RESID_MOD) return;
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(base + sample * ep.ldmod + col));
+    if (lane > 0 && (!mod2 || base == nullptr)) return;
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(base + sample * (lane == 1 ? ep.ldshift : ep.ldmod) + col));
   };
   prefetch_vecs(half * 32);
   if (reads_resid && half * 32 < BN) prefetch(half * 32);
@@ -210,7 +212,7 @@ __device__ __forceinline__ void run_tile(const EpiParams& ep, const EpiTmaps& tm
         f[j] *= sg * fmaf(xo[j], 1.0f - sg, 1.0f) * silu_mul;
       }
       st.store(&tm.out, f, col);
-    } else {  // RESID / RESID_MOD
+    } else {  // RESID / RESID_MOD / RESID_ROT
       float gt[32];
       if (ep.aux) st.store(&tm.aux, f, col);  // raw branch output, needed for d(gate)
       load_row32_f32(ep.gate + sample * ep.ldmod + col, gt, row_ok ? nvalid : 0);
@@ -223,6 +225,21 @@ __device__ __forceinline__ void run_tile(const EpiParams& ep, const EpiTmaps& tm
         load_row32_f32(ep.scale + sample * ep.ldmod + col, gt, row_ok ? nvalid : 0);
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = lerp_t(f[j] * gt[j], xo[j], gsc) * inv_den;
+        st.store(&tm.out2, f, col);
+      } else if (ep.epilogue == MAPDIT_EPI_RESID_ROT) {
+        // rotation modulation (UNPINNED): channel pair (2i, 2i+1) of x' rotated by theta_i; xo = 16 (cos, sin) pairs
+        load_row32_f32(ep.shift + sample * ep.ldshift + col, xo, row_ok ? nvalid : 0);
+#pragma unroll
+        for (int p = 0; p < 16; ++p) {
+          const float a = f[2 * p], b = f[2 * p + 1];
+          f[2 * p] = a * xo[2 * p] - b * xo[2 * p + 1];
+          f[2 * p + 1] = fmaf(a, xo[2 * p + 1], b * xo[2 * p]);
+        }
+        if (ep.scale) {
+          load_row32_f32(ep.scale + sample * ep.ldmod + col, gt, row_ok ? nvalid : 0);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] *= gt[j];
+        }
         st.store(&tm.out2, f, col);
       }
     }

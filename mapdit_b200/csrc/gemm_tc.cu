@@ -257,14 +257,18 @@ extern "C" int mapdit_gemm_bf16(const mapdit_gemm_args* g, void* stream) {
     post_qknorm = true;
   }
   if (epi == MAPDIT_EPI_SILU_BWD) MAPDIT_REQUIRE(g->resid != nullptr, "gemm_bf16: SILU_BWD epilogue needs the pre-activation in `resid`");
-  if (epi == MAPDIT_EPI_RESID || epi == MAPDIT_EPI_RESID_MOD) {
+  MAPDIT_REQUIRE(epi >= MAPDIT_EPI_STORE && epi <= MAPDIT_EPI_RESID_ROT, "gemm_bf16: unknown epilogue");
+  if (epi == MAPDIT_EPI_RESID || epi == MAPDIT_EPI_RESID_MOD || epi == MAPDIT_EPI_RESID_ROT) {
     MAPDIT_REQUIRE(g->resid && g->gate && g->tokens > 0 && g->ldmod % 4 == 0, "gemm_bf16: residual epilogue needs resid/gate/tokens");
     if (epi == MAPDIT_EPI_RESID_MOD) MAPDIT_REQUIRE(g->out2 && g->shift && g->scale && g->gain, "gemm_bf16: modulate epilogue needs out2/shift/scale/gain");
+    if (epi == MAPDIT_EPI_RESID_ROT)
+      MAPDIT_REQUIRE(g->out2 && g->shift && g->ldrot % 4 == 0 && ((uintptr_t)g->shift & 15) == 0,
+                     "gemm_bf16: rotation epilogue needs out2 and the 16-byte aligned (cos, sin) table in `shift`");
   }
   MAPDIT_REQUIRE(epi == MAPDIT_EPI_STORE || g->out_dtype == MAPDIT_BF16, "gemm_bf16: fused epilogues write bf16");
   EpiParams ep;
   ep.out = g->out; ep.out2 = g->out2; ep.resid = g->resid; ep.gate = g->gate; ep.shift = g->shift; ep.scale = g->scale;
-  ep.gain = g->gain; ep.aux = g->aux; ep.ldo = g->ldo; ep.ldmod = g->ldmod; ep.M = g->m; ep.N = g->n; ep.tokens = g->tokens > 0 ? g->tokens : 1;
+  ep.gain = g->gain; ep.aux = g->aux; ep.ldo = g->ldo; ep.ldmod = g->ldmod; ep.ldshift = (epi == MAPDIT_EPI_RESID_ROT && g->ldrot > 0) ? g->ldrot : g->ldmod; ep.M = g->m; ep.N = g->n; ep.tokens = g->tokens > 0 ? g->tokens : 1;
   ep.qk_cols = g->qk_cols; ep.epilogue = epi; ep.out_f32 = (g->out_dtype == MAPDIT_F32); ep.eps = g->eps; ep.variant = mapdit_variant();
 
   const int sms = num_sms_cached();

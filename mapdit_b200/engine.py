@@ -170,6 +170,8 @@ class Engine:
         )
         if mode == "fp32":
             ws["tmp"] = torch.empty(M, D, **a)
+        if m.modulation != "adaln":  # (cos, sin) tables of every block's two rotations, read by the EPI_RESID_ROT epilogue
+            ws["rotcs"] = torch.empty(N, m.depth * 2 * D, **f)
         self._ws[key] = ws
         return ws
 
@@ -270,6 +272,14 @@ class Engine:
         blk = m.blocks
         # modulate fused into the residual GEMM epilogues (the pinned all-flags-on configuration)
         fused = bf and adaln and not ln and cosine and hd == 64
+        # the same for rotation(+scaling) modulation: BASELINE.json's headline configuration (UNPINNED)
+        fused_rot = bf and not adaln and not ln and cosine and hd == 64
+        if fused_rot:
+            rcs = ws["rotcs"]
+            for i in range(L):
+                ops.rot_table(mod(i, "rot_a"), blk[i].gain_msa.data, rcs[:, (2 * i) * D:], ld, D,
+                              mod(i, "rot_m"), blk[i].gain_mlp.data, rcs[:, (2 * i + 1) * D:])
+            has_sc = "scale_a" in lay
         # ---- patch embed + first modulate (src/dit.py:81-84)
         X, Hb = ws["x"], ws["h"]
         if adaln and not ln:
@@ -288,7 +298,21 @@ class Engine:
                 ops.gemm_bf16(Hb, W.w1[i], ws["u"], epilogue=_lib.EPI_MPSILU)
                 ops.gemm_bf16(ws["u"], W.w2[i], X, epilogue=_lib.EPI_RESID_MOD, out2=Hb, resid=X, gate=mod(i, "gate_m"),
                               shift=nxt_shift, scale=nxt_scale, gain=nxt_gain, ldmod=ld, tokens=T)
-            elif bf:  # rotation / LayerNorm modulation, plain attention, head_dim != 64: residual fused, rest standalone
+            elif fused_rot:
+                ops.gemm_bf16(Hb, W.wqkv[i], ws["qkv"], epilogue=_lib.EPI_QKNORM, tokens=T, head_dim=hd, qk_cols=2 * D)
+                ops.cos_attn(ws["qkv"], ws["o"], N, T, H, hd)
+                ops.gemm_bf16(ws["o"], W.wo[i], X, epilogue=_lib.EPI_RESID_ROT, out2=Hb, resid=X, gate=mod(i, "gate_a"),
+                              shift=rcs[:, (2 * i + 1) * D:], scale=mod(i, "scale_m") if has_sc else None, ldmod=ld,
+                              ldrot=rcs.stride(0), tokens=T)
+                ops.gemm_bf16(Hb, W.w1[i], ws["u"], epilogue=_lib.EPI_MPSILU)
+                if i + 1 < L:
+                    ops.gemm_bf16(ws["u"], W.w2[i], X, epilogue=_lib.EPI_RESID_ROT, out2=Hb, resid=X, gate=mod(i, "gate_m"),
+                                  shift=rcs[:, (2 * i + 2) * D:], scale=mod(i + 1, "scale_a") if has_sc else None, ldmod=ld,
+                                  ldrot=rcs.stride(0), tokens=T)
+                else:  # the final layer keeps the MP-AdaLN modulate (src/blocks/final_layer.py:53-59)
+                    ops.gemm_bf16(ws["u"], W.w2[i], X, epilogue=_lib.EPI_RESID_MOD, out2=Hb, resid=X, gate=mod(i, "gate_m"),
+                                  shift=mods[:, fbase:], scale=mods[:, fbase + D:], gain=f.gain_mod.data, ldmod=ld, tokens=T)
+            elif bf:  # LayerNorm modulation, plain attention, head_dim != 64: residual fused, rest standalone
                 qkv_proj(i, Hb)
                 ops.cos_attn(ws["qkv"], ws["o"], N, T, H, hd)
                 ops.gemm_bf16(ws["o"], W.wo[i], X, epilogue=_lib.EPI_RESID, resid=X, gate=mod(i, "gate_a"), ldmod=ld, tokens=T)

@@ -92,7 +92,7 @@ def gemm_f32(a, b, out=None, trans_a=False, trans_b=False, accumulate=False):
 
 
 def gemm_bf16(a, b, out, epilogue=_lib.EPI_STORE, out2=None, resid=None, gate=None, shift=None, scale=None, gain=None,
-              ldmod=0, tokens=1, head_dim=0, qk_cols=0, aux=None):
+              ldmod=0, tokens=1, head_dim=0, qk_cols=0, aux=None, ldrot=0):
     """out = epilogue(a[M,K] @ b[N,K]^T) on the tcgen05 path (bf16 operands, fp32 accumulate)."""
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
     assert a.stride(1) == 1 and b.stride(1) == 1 and out.stride(1) == 1
@@ -108,7 +108,7 @@ def gemm_bf16(a, b, out, epilogue=_lib.EPI_STORE, out2=None, resid=None, gate=No
                     gain=gain.data_ptr() if gain is not None else None,
                     aux=aux.data_ptr() if aux is not None else None,
                     lda=a.stride(0), ldb=b.stride(0), ldo=out.stride(0), ldmod=ldmod, m=m, n=n, k=k, tokens=tokens,
-                    head_dim=head_dim, qk_cols=qk_cols, epilogue=epilogue, out_dtype=_dt(out), eps=EPS)
+                    head_dim=head_dim, qk_cols=qk_cols, epilogue=epilogue, out_dtype=_dt(out), eps=EPS, ldrot=ldrot)
     check(lib().mapdit_gemm_bf16(C.byref(args), _stream()), "gemm_bf16")
     return out
 
@@ -291,6 +291,19 @@ def rotmod_bwd(dh, x, R, rot, scale, gain, drot, dscale, dg_partial, ldmod, n_sa
     d = dh.shape[1]
     check(lib().mapdit_rotmod_bwd(_ptr(dh), _ptr(x), _ptr(R), _ptr(rot), _ptr(scale), _ptr(gain), _ptr(drot), _ptr(dscale),
                                   _ptr(dg_partial), ldmod, n_samples, d, tokens, int(accumulate), _dt(dh), _stream()), "rotmod_bwd")
+
+
+def rotmod_resid_bwd(dh, x, R, rot, scale, gain, drot, dscale, dg_partial, y, dy, gate, dgate, ldmod, n_samples, tokens, accumulate):
+    d = dh.shape[1]
+    check(lib().mapdit_rotmod_resid_bwd(_ptr(dh), _ptr(x), _ptr(R), _ptr(rot), _ptr(scale), _ptr(gain), _ptr(drot), _ptr(dscale),
+                                        _ptr(dg_partial), _ptr(y), _ptr(dy), _ptr(gate), _ptr(dgate), ldmod, n_samples, d, tokens,
+                                        int(accumulate), _dt(dh), _stream()), "rotmod_resid_bwd")
+
+
+def rot_table(rot, gain, cs, ldmod, d, rot2=None, gain2=None, cs2=None):
+    """cs[n, 2i | 2i+1] = cos | sin(rot[n, i] * gain): the per-sample table the EPI_RESID_ROT GEMM epilogue reads"""
+    check(lib().mapdit_rot_table(_ptr(rot), _ptr(gain), _ptr(cs), _ptr(rot2), _ptr(gain2), _ptr(cs2), ldmod, cs.stride(0),
+                                 cs.shape[0], d, _stream()), "rot_table")
 
 
 def axpby(x, y, a, accumulate=False):

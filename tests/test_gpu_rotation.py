@@ -68,3 +68,55 @@ def test_rotation_training_gradients(modulation, dtype, tol):
         worst = max(worst, e)
         assert e < tol, (k, e)
     print(f"{modulation} {dtype}: worst per-parameter grad rel-L2 vs oracle {worst:.2e}")
+
+
+@pytest.mark.parametrize("N,T,D", [(3, 64, 256), (2, 256, 768), (5, 16, 384)])
+@pytest.mark.parametrize("with_scale", [True, False])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_rotmod_backward_kernels_match_autograd(N, T, D, with_scale, dtype):
+    """mapdit_rotmod_bwd and the fused mapdit_rotmod_resid_bwd (rotation backward + the preceding residual's backward in one
+    pass) against torch autograd of the same formulas in fp64 (self-referential: the formula is the oracle's rotate_pairs)."""
+    from mapdit_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    M, ld = N * T, 5 * D + 8
+    mods = torch.randn(N, ld, generator=g).cuda()
+    gain = torch.tensor(0.37, device="cuda")
+    x = torch.randn(M, D, generator=g).cuda().to(dtype)
+    dh = torch.randn(M, D, generator=g).cuda().to(dtype)
+    R0 = torch.randn(M, D, generator=g).cuda().to(dtype)
+    y = torch.randn(M, D, generator=g).cuda().to(dtype)
+    rot, scale, gate = mods[:, :D // 2], mods[:, D:2 * D], mods[:, 2 * D:3 * D]
+    n_of_row = torch.arange(M, device="cuda") // T
+
+    xd = x.double().requires_grad_(True)
+    rd, sd_, gd_ = rot.double().clone().requires_grad_(True), scale.double().clone().requires_grad_(True), gain.double().clone().requires_grad_(True)
+    th = (rd * gd_)[n_of_row]
+    xe, xo = xd[:, 0::2], xd[:, 1::2]
+    hrot = torch.stack([xe * th.cos() - xo * th.sin(), xe * th.sin() + xo * th.cos()], dim=-1).reshape(M, D)
+    hout = hrot * sd_[n_of_row] if with_scale else hrot
+    (hout * dh.double()).sum().backward()
+    R1 = R0.double() + xd.grad  # residual-stream gradient after the rotation backward
+    ca, cb = 0.7 / (0.7 ** 2 + 0.3 ** 2) ** 0.5, 0.3 / (0.7 ** 2 + 0.3 ** 2) ** 0.5
+    dy_ref = cb * gate.double()[n_of_row] * R1
+    dgate_ref = (cb * y.double() * R1).view(N, T, D).sum(1)
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+
+    for fused in (False, True):
+        dmods = torch.full((N, ld), float("nan"), device="cuda")
+        drot, dscale, dgate = dmods[:, :D // 2], dmods[:, D:2 * D], dmods[:, 2 * D:3 * D]
+        dgp = torch.full((ops.rotmod_bwd_partials(N, D),), float("nan"), device="cuda")
+        R = R0.clone()
+        sc_arg, dsc_arg = (scale, dscale) if with_scale else (None, None)
+        if fused:
+            dy = torch.full_like(R, float("nan"))
+            ops.rotmod_resid_bwd(dh, x, R, rot, sc_arg, gain, drot, dsc_arg, dgp, y, dy, gate, dgate, ld, N, T, True)
+            assert rel_l2(R.double(), ca * R1) < tol
+            assert rel_l2(dy.double(), dy_ref) < tol
+            assert rel_l2(dgate.double(), dgate_ref) < tol
+        else:
+            ops.rotmod_bwd(dh, x, R, rot, sc_arg, gain, drot, dsc_arg, dgp, ld, N, T, True)
+            assert rel_l2(R.double(), R1) < tol
+        assert rel_l2(drot.double(), rd.grad) < tol
+        if with_scale:
+            assert rel_l2(dscale.double(), sd_.grad) < tol
+        assert abs(float(dgp.double().sum()) - float(gd_.grad)) < tol * max(1.0, float(dgp.double().abs().sum()))

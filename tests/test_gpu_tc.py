@@ -94,6 +94,23 @@ def test_gemm_bf16_fused_epilogues(N, T, D, two_cta):
     xio = x.clone()
     ops.gemm_bf16(h, wo, xio, epilogue=_lib.EPI_RESID, resid=xio, gate=mods[:, 2 * D:], ldmod=mods.shape[1], tokens=T)
     assert rel_l2(xio.float(), xn) < 3e-3
+    # RESID_ROT (rotation modulation, UNPINNED: SURVEY.md §A.8): h = R(rot * gain) x' (* scale), (cos, sin) table from rot_table
+    rot = mods[:, 5 * D:5 * D + D // 2]
+    cs = torch.full((N, 2 * D + 8), float("nan"), device="cuda")  # table in a wider buffer: column slice at offset 8, own ld
+    ops.rot_table(rot, gain, cs[:, 8:], mods.shape[1], D, rot, gain, cs[:, 8 + D:])
+    th = (rot * g).double()
+    assert float((cs[:, 8:8 + D:2].double() - th.cos()).abs().max()) < 1e-6 and float((cs[:, 9:9 + D:2].double() - th.sin()).abs().max()) < 1e-6
+    assert torch.equal(cs[:, 8:8 + D], cs[:, 8 + D:])
+    thr = th.float()[n_of_row]
+    xe, xo_ = xn[:, 0::2], xn[:, 1::2]
+    rotated = torch.stack([xe * thr.cos() - xo_ * thr.sin(), xe * thr.sin() + xo_ * thr.cos()], dim=-1).reshape(M, D)
+    for sc_arg, href in ((mods[:, 4 * D:], rotated * scale), (None, rotated)):
+        xio = x.clone()
+        hout = torch.full_like(x, float("nan"))
+        ops.gemm_bf16(h, wo, xio, epilogue=_lib.EPI_RESID_ROT, out2=hout, resid=xio, gate=mods[:, 2 * D:], shift=cs[:, 8:], scale=sc_arg,
+                      ldmod=mods.shape[1], ldrot=cs.stride(0), tokens=T)
+        assert rel_l2(xio.float(), xn) < 3e-3
+        assert rel_l2(hout.float(), href) < 3e-3
 
 
 @pytest.mark.parametrize("v2", [1, 0])
