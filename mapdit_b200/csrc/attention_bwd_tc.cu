@@ -20,6 +20,10 @@ int mapdit_attn_mma_bwd(const void* qkv, const void* o, const void* dout, const 
                         int heads, int hd, void* stream);
 bool mapdit_attn_mma_supported(int tokens, int hd);
 
+int g_mapdit_attn_bwd_fused = 1;  // mapdit_set_option("attn_bwd_fused", 0/1): single fused kernel for tokens == 256
+
+extern long long* g_attn_dbg;  // developer timeline hook (mapdit_attn_debug_buffer)
+
 namespace {
 using namespace tc;
 
@@ -445,6 +449,533 @@ attn_bwd_dkv_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_con
   if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
+// ------------------------------------------------------------------------------------------------ fused dQ, dK, dV (tokens == 256)
+// One persistent CTA per SM walks (sample, head) items; everything an item needs stays on chip: Q, K, V, dO as eight
+// [128 x 64] TMA tiles (128 KB), S^T / dP^T / dV / dK / dQ_0 / dQ_1 in the 512 TMEM columns.  Rows (TMEM lanes) are KEYS:
+//   S^T = K_kt Q_qb^T, dP^T = V_kt dO_qb^T                      (M = 128 keys, N = 128 queries, K = 64)
+//   P^T = exp2(S^T c - L_q), dS^T = P^T (dP^T - delta_q)         8 softmax warps, bf16 -> two [128 x 128] staging tiles
+//   dV_kt += P^T dO_qb, dK_kt += dS^T Q_qb                       (A K-major from the staging tiles, B = dO / Q tile MN-major)
+//   dQ_qb += dS K_kt                                             (A = the SAME dS^T tile read MN-major, B = K tile MN-major)
+// 5 GEMMs per logit block instead of the 7 of the dq + dkv kernel pair (S and dP are not recomputed) and Q/K/V/dO are read
+// from HBM once.  Iteration order (kt, qb): even items (0,0) (0,1) (1,1) (1,0), odd items (0,1) (0,0) (1,0) (1,1): the query
+// block an item finishes with is the one the next item needs last, so every input tile has about one iteration between
+// its release and the first MMA that needs its refill.  Each tile has its own full/empty barrier pair.
+// Outputs never touch the LSU's global path (row-per-thread 16-byte stores cost 32 line transactions per instruction and
+// were 60 % of the first version's time): a finished accumulator row is converted in registers, written into a dead
+// input tile (dK in place over the K tile whose rows are also the k^ the q/k-norm backward needs, dV over the V tile, dQ
+// into a 16 KB staging tile) and leaves through per-warp TMA stores; the tile is released to the producer when the store
+// has read it.
+constexpr int F_T = 256;
+constexpr int F_TILE = RT * HD * 2;              // 16 KB
+constexpr int F_STG = 2 * F_TILE;                // [128 keys x 128 queries] bf16 = two 64-query panels
+constexpr int F_NTHREADS = 320;                  // warp 0 TMA, warp 1 MMA, warps 2-9 softmax / epilogue
+constexpr int F_SMEM = 9 * F_TILE + 2 * F_STG + 4 * F_T * 4 + 256 + 1024;
+enum { TK0 = 0, TK1 = 1, TV0 = 2, TV1 = 3, TQ0 = 4, TQ1 = 5, TD0 = 6, TD1 = 7, TOUT = 8 };
+
+__device__ __forceinline__ void load_row_sw128(const uint8_t* tile, int r, float (&y)[64]) {
+  const uint8_t* prow = tile + (r >> 3) * 1024 + (r & 7) * 128;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const uint4 u = *reinterpret_cast<const uint4*>(prow + ((c ^ (r & 7)) << 4));
+    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 t = __bfloat1622float2(h2[e]);
+      y[8 * c + 2 * e] = t.x;
+      y[8 * c + 2 * e + 1] = t.y;
+    }
+  }
+}
+__device__ __forceinline__ void load_row_global(const bf16* __restrict__ yrow, float (&y)[64]) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const uint4 u = reinterpret_cast<const uint4*>(yrow)[c];
+    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 t = __bfloat1622float2(h2[e]);
+      y[8 * c + 2 * e] = t.x;
+      y[8 * c + 2 * e + 1] = t.y;
+    }
+  }
+}
+// accumulator row (a | b = 64 fp32) -> 64 bf16 packed; plain scale, or the q/k-normalisation backward (see store_out_row_qknorm)
+__device__ __forceinline__ void pack_row(const uint32_t (&a)[32], const uint32_t (&b)[32], float scale, uint32_t (&out)[32]) {
+#pragma unroll
+  for (int c = 0; c < 16; ++c) {
+    out[c] = pack_bf16(__uint_as_float(a[2 * c]) * scale, __uint_as_float(a[2 * c + 1]) * scale);
+    out[16 + c] = pack_bf16(__uint_as_float(b[2 * c]) * scale, __uint_as_float(b[2 * c + 1]) * scale);
+  }
+}
+__device__ __forceinline__ void pack_row_qknorm(const uint32_t (&a)[32], const uint32_t (&b)[32], const float (&y)[64], float att_scale,
+                                                float s, float eps, uint32_t (&out)[32]) {
+  float dot = 0.f;
+#pragma unroll
+  for (int c = 0; c < 32; ++c) dot = fmaf(y[c], __uint_as_float(a[c]), fmaf(y[32 + c], __uint_as_float(b[c]), dot));
+  dot *= att_scale;
+  const float rpe = 8.0f / s;
+  const float r = fmaxf(rpe - eps, 1e-30f);
+  const float sco = -s * (dot * rpe / (64.0f * r));
+  const float ga = s * att_scale;
+#pragma unroll
+  for (int c = 0; c < 16; ++c) {
+    out[c] = pack_bf16(fmaf(ga, __uint_as_float(a[2 * c]), sco * y[2 * c]), fmaf(ga, __uint_as_float(a[2 * c + 1]), sco * y[2 * c + 1]));
+    out[16 + c] = pack_bf16(fmaf(ga, __uint_as_float(b[2 * c]), sco * y[32 + 2 * c]), fmaf(ga, __uint_as_float(b[2 * c + 1]), sco * y[32 + 2 * c + 1]));
+  }
+}
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* m, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"((uint64_t)m), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"((uint64_t)m), "r"(smem_u32(smem_src)),
+               "r"(c0), "r"(c1)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(F_NTHREADS, 1)
+attn_bwd_fused_tc(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
+                  const __grid_constant__ CUtensorMap tm_out, const float* __restrict__ lse, const float* __restrict__ delta, int heads,
+                  int total_items, const bf16* __restrict__ qkv, const float* __restrict__ sc, float eps, long long* __restrict__ dbg) {
+  // optional timeline of CTA 0 (tools/attn_bwd_timeline.py): dbg[role*256 + 4*g + e] = clock64 at event e of iteration g
+#define FSTAMP(role, g, e) \
+  do { \
+    if (dbg && blockIdx.x == 0 && (g) < 64 && lane == 0) dbg[(role) * 256 + 4 * (g) + (e)] = clock64(); \
+  } while (0)
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* sTile = smem;                      // 8 input tiles + the dQ output staging tile, index = T* enum
+  uint8_t* sPt = sTile + 9 * F_TILE;
+  uint8_t* sdSt = sPt + F_STG;
+  float* sL = reinterpret_cast<float*>(sdSt + F_STG);  // [2][256] log2-domain log-sum-exp of the item's queries
+  float* sDl = sL + 2 * F_T;                            // [2][256] delta
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDl + 2 * F_T);
+  uint64_t* full = bars;         // [8]
+  uint64_t* empty = bars + 8;    // [8]
+  uint64_t* s_full = bars + 16;
+  uint64_t* s_empty = bars + 17;
+  uint64_t* p_full = bars + 18;
+  uint64_t* p_empty = bars + 19;
+  uint64_t* acc_free = bars + 20;  // dV / dK accumulators read out (8 warps)
+  uint64_t* dq_free = bars + 21;   // the previous item's last dQ accumulator read out (4 warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int D = heads * HD;
+  const int my_items = blockIdx.x < total_items ? (total_items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int G = my_items * 4;  // (kt, qb) iterations of this CTA
+  // iteration i of item `it`: key tile i >> 1, query block {0,1,1,0}[i] (even items) / {1,0,0,1}[i] (odd items)
+  auto qb_of = [](int g) { return (((g & 3) == 1 || (g & 3) == 2) ? 1 : 0) ^ ((g >> 2) & 1); };
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tm_qkv);
+    prefetch_tmap(&tm_do);
+    prefetch_tmap(&tm_out);
+    for (int i = 0; i < 8; ++i) {
+      mbar_init(&full[i], 1);
+      // K / V tiles are also written and TMA-stored by four epilogue warps before the producer may refill them; the Q tiles
+      // are copied (q^ rows for the dQ epilogue) by four warps
+      mbar_init(&empty[i], i < TD0 ? 5 : 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(s_empty, 8);
+    mbar_init(p_full, 8);
+    mbar_init(p_empty, 1);
+    mbar_init(acc_free, 8);
+    mbar_init(dq_free, 4);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  constexpr uint32_t C_S = 0, C_DP = 128, C_DV = 256, C_DK = 320, C_DQ = 384;
+
+  if (warp == 0 && lane == 0) {
+    for (int it = 0; it < my_items; ++it) {
+      const int item = blockIdx.x + it * gridDim.x;
+      const int n = item / heads, h = item - n * heads;
+      const uint32_t ph = it & 1;
+      const int f = it & 1;  // first query block of this item = the one the previous item released first
+      // The smem tiles are single-buffered, so a tile's refill is issued only ~one iteration before its first MMA: far less
+      // than an HBM round trip under load (2-4 us measured).  Pull the NEXT item's 128 KB into L2 now, one whole item ahead.
+      if (it + 1 < my_items) {
+        const int nitem = item + gridDim.x;
+        const int nn = nitem / heads, nh = nitem - nn * heads;
+#pragma unroll
+        for (int rb = 0; rb < 2; ++rb) {
+          const int row = nn * F_T + rb * RT;
+          tma_prefetch_l2_2d(&tm_qkv, nh * HD, row);
+          tma_prefetch_l2_2d(&tm_qkv, D + nh * HD, row);
+          tma_prefetch_l2_2d(&tm_qkv, 2 * D + nh * HD, row);
+          tma_prefetch_l2_2d(&tm_do, nh * HD, row);
+        }
+      }
+      // tiles in the order the previous item releases them
+      const int order[8] = {TK0, TV0, TQ0 + f, TD0 + f, TQ0 + (f ^ 1), TD0 + (f ^ 1), TK1, TV1};
+      for (int k = 0; k < 8; ++k) {
+        const int t = order[k];
+        mbar_wait(&empty[t], ph ^ 1);
+        if (dbg && blockIdx.x == 0 && it < 8) dbg[3 * 256 + it * 8 + k] = clock64();
+        mbar_arrive_expect_tx(&full[t], F_TILE);
+        const int row = n * F_T + (t & 1) * RT;
+        if (t >= TD0) tma_load_2d(sTile + t * F_TILE, &tm_do, &full[t], h * HD, row);
+        else tma_load_2d(sTile + t * F_TILE, &tm_qkv, &full[t], (t >= TQ0 ? 0 : (t >= TV0 ? 2 * D : D)) + h * HD, row);
+      }
+    }
+  } else if (warp == 1) {
+    const bool leader = elect_one();  // whole warp runs the loop, one lane issues (see tc_common.cuh)
+    constexpr uint32_t idesc_s = make_idesc_bf16(RT, 128, 0, 0);  // S^T / dP^T: both operands K-major
+    constexpr uint32_t idesc_a = make_idesc_bf16(RT, HD, 0, 1);   // dV / dK: A K-major (staging), B MN-major
+    constexpr uint32_t idesc_q = make_idesc_bf16(RT, HD, 1, 1);   // dQ: A = dS^T read MN-major, B = K MN-major
+    const uint32_t tile0 = smem_u32(sTile), pt_addr = smem_u32(sPt), dst_addr = smem_u32(sdSt);
+    auto scores = [&](int g) {
+      const int i = g & 3, kt = i >> 1, qb = qb_of(g);
+      const uint32_t ph = (g >> 2) & 1;
+      if ((i & 1) == 0) {  // first use of this key tile
+        mbar_wait(&full[TK0 + kt], ph);
+        mbar_wait(&full[TV0 + kt], ph);
+      }
+      if (kt == 0) {       // first use of this query block
+        mbar_wait(&full[TQ0 + qb], ph);
+        mbar_wait(&full[TD0 + qb], ph);
+      }
+      mbar_wait(s_empty, (g & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t k_addr = tile0 + (TK0 + kt) * F_TILE, v_addr = tile0 + (TV0 + kt) * F_TILE;
+      const uint32_t q_addr = tile0 + (TQ0 + qb) * F_TILE, do_addr = tile0 + (TD0 + qb) * F_TILE;
+#pragma unroll
+      for (int k = 0; k < HD / 16; ++k) {  // the two chains write different accumulators: issued alternately
+        if (leader) umma_ss(tmem_base + C_S, make_smem_desc(k_addr + k * 32, 16, 1024), make_smem_desc(q_addr + k * 32, 16, 1024), idesc_s, k != 0);
+        if (leader) umma_ss(tmem_base + C_DP, make_smem_desc(v_addr + k * 32, 16, 1024), make_smem_desc(do_addr + k * 32, 16, 1024), idesc_s, k != 0);
+      }
+      if (leader) umma_commit(s_full);
+    };
+    // are the input tiles iteration g touches for the first time loaded?  (non-blocking, warp-uniform)
+    auto tiles_ready = [&](int g) {
+      const int i = g & 3, kt = i >> 1, qb = qb_of(g);
+      const uint32_t ph = (g >> 2) & 1;
+      bool ok = true;
+      if ((i & 1) == 0) ok = mbar_test_wait(smem_u32(&full[TK0 + kt]), ph) && mbar_test_wait(smem_u32(&full[TV0 + kt]), ph);
+      if (kt == 0) ok = ok && mbar_test_wait(smem_u32(&full[TQ0 + qb]), ph) && mbar_test_wait(smem_u32(&full[TD0 + qb]), ph);
+      return __all_sync(0xffffffffu, ok) != 0;
+    };
+    if (G > 0) scores(0);
+    for (int g = 0; g < G; ++g) {
+      // S / dP of the next iteration are issued as soon as their input tiles have landed -- ahead of this iteration's
+      // dV / dK / dQ MMAs if possible (the softmax warps then never wait for S), otherwise while polling for P / dS, and
+      // at the latest after them (they must not queue behind a tile that is still in flight)
+      const int i = g & 3, kt = i >> 1, qb = qb_of(g);
+      bool issued = g + 1 >= G;
+      auto phase2_ready = [&]() {
+        bool ok = mbar_test_wait(smem_u32(p_full), g & 1);
+        // dV / dK restart at i == 2 and at i == 0: the epilogue warps must have read the previous accumulators; the dQ
+        // columns of iteration 1 held the previous item's first block
+        if (i == 2) ok = ok && mbar_test_wait(smem_u32(acc_free), 0);
+        if (i == 0 && g > 0) ok = ok && mbar_test_wait(smem_u32(acc_free), 1);
+        if (i == 1 && g > 4) ok = ok && mbar_test_wait(smem_u32(dq_free), ((g >> 2) - 1) & 1);
+        return __all_sync(0xffffffffu, ok) != 0;
+      };
+      {
+        const long long t0 = clock64();
+        for (;;) {
+          if (!issued && tiles_ready(g + 1)) {
+            scores(g + 1);
+            issued = true;
+          }
+          if (phase2_ready()) break;
+          if (clock64() - t0 > 4000000000LL) {
+            if (lane == 0) printf("mapdit: attn_bwd_fused MMA warp timed out (block %d iteration %d)\n", blockIdx.x, g);
+            __trap();
+          }
+        }
+      }
+      FSTAMP(0, g, 0);
+      FSTAMP(0, g, 1);
+      tc_fence_after();
+      const uint32_t k_addr = tile0 + (TK0 + kt) * F_TILE;
+      const uint32_t q_addr = tile0 + (TQ0 + qb) * F_TILE, do_addr = tile0 + (TD0 + qb) * F_TILE;
+#pragma unroll
+      for (int k = 0; k < 128 / 16; ++k) {
+        const uint32_t a_off = (k >> 2) * F_TILE + (k & 3) * 32;  // K-major: 64-query panel, 16 queries = 32 bytes
+        if (leader) umma_ss(tmem_base + C_DV, make_smem_desc(pt_addr + a_off, 16, 1024), make_smem_desc(do_addr + k * 2048, 1024, 1024), idesc_a,
+                ((i & 1) | k) != 0);
+        if (leader) umma_ss(tmem_base + C_DK, make_smem_desc(dst_addr + a_off, 16, 1024), make_smem_desc(q_addr + k * 2048, 1024, 1024), idesc_a,
+                ((i & 1) | k) != 0);
+        if (leader) umma_ss(tmem_base + C_DQ + qb * HD, make_smem_desc(dst_addr + k * 2048, F_TILE, 1024), make_smem_desc(k_addr + k * 2048, 1024, 1024),
+                idesc_q, (kt | k) != 0);
+      }
+      if (leader) umma_commit(p_empty);
+      FSTAMP(0, g, 2);
+      if (i == 1) {
+        if (leader) umma_commit(&empty[TK0]);
+        if (leader) umma_commit(&empty[TV0]);
+      } else if (i == 2) {  // the second query block of the item is finished
+        if (leader) umma_commit(&empty[TQ0 + qb]);
+        if (leader) umma_commit(&empty[TD0 + qb]);
+      } else if (i == 3) {
+        if (leader) umma_commit(&empty[TQ0 + qb]);
+        if (leader) umma_commit(&empty[TD0 + qb]);
+        if (leader) umma_commit(&empty[TK1]);
+        if (leader) umma_commit(&empty[TV1]);
+      }
+      if (!issued) scores(g + 1);
+    }
+  } else if (warp >= 2) {
+    const int wq = warp & 3;             // TMEM lane quarter this warp may read
+    const int half = (warp - 2) >> 2;    // which 64-query half of the 128-query block
+    const int r = wq * 32 + lane;        // row of the tile
+    const int tid = threadIdx.x - 64;    // 0..255
+    const uint32_t t_lane = tmem_base + ((uint32_t)(wq * 32) << 16);
+    const float c1 = 0.125f * LOG2E;
+    float nxt_l = 0.f, nxt_d = 0.f;  // the next item's L / delta of query `tid`, in flight across one iteration
+    auto fetch_ld = [&](int item) {  // per-query L (log2 domain) and delta of an item: issue the loads ...
+      const int n = item / heads, h = item - n * heads;
+      const size_t qrow = (size_t)n * F_T + tid;
+      // volatile asm pins the loads here and their first use in commit_ld: left to the compiler, the multiply below is
+      // scheduled right behind the load and the warp sits out a whole HBM round trip (2-4 k cycles under load)
+      asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(nxt_l) : "l"(lse + qrow * heads + h));
+      asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(nxt_d) : "l"(delta + qrow * heads + h));
+    };
+    auto commit_ld = [&](int buf) {  // ... and park them in shared memory once they have arrived
+      asm volatile("" : "+f"(nxt_l), "+f"(nxt_d));
+      sL[buf + tid] = nxt_l * LOG2E;
+      sDl[buf + tid] = nxt_d;
+    };
+    int rel_a = -1, rel_b = -1;  // input tiles this warp TMA-stored from and still has to hand back to the producer
+    auto release_pending = [&]() {  // called where the warp is about to wait anyway: the stores have long read their smem
+      if (rel_a >= 0) {
+        if (lane == 0) {
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          mbar_arrive(&empty[rel_a]);
+          if (rel_b >= 0) mbar_arrive(&empty[rel_b]);
+        }
+        rel_a = rel_b = -1;
+      }
+    };
+    auto signal_free = [&](uint64_t* bar) {  // the accumulator(s) just read are in registers: the MMA warp may overwrite them
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar);
+    };
+    // packed bf16 row -> row r of smem tile `stile`, then this warp's 32-row slab -> dqkv[grow0 + wq*32 .., gcol .. gcol+64) by TMA
+    auto store_slab = [&](uint8_t* stile, const uint32_t (&out)[32], size_t grow0, int gcol) {
+      store_row_sw128(stile, r, out);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) tma_store_2d(&tm_out, stile + wq * 32 * 128, gcol, (int)(grow0 + wq * 32));
+    };
+    // finish a dq / dk accumulator row already in registers: q/k-normalisation backward against the normalised row that sits
+    // in `stile` (k^ in its input tile, q^ stashed in the staging tile), result written over it
+    auto finish_qk = [&](const uint32_t (&a0)[32], const uint32_t (&a1)[32], uint8_t* stile, size_t grow0, int gcol, int sc_col) {
+      uint32_t out[32];
+      if (sc) {
+        float y[64];
+        load_row_sw128(stile, r, y);
+        pack_row_qknorm(a0, a1, y, 0.125f, sc[(grow0 + r) * 2 * heads + sc_col], eps, out);
+      } else {
+        pack_row(a0, a1, 0.125f, out);
+      }
+      store_slab(stile, out, grow0, gcol);
+    };
+    // this thread's q^ row of query block qb -> the dQ staging tile (the dQ epilogue normalises against it and overwrites it)
+    auto stash_q = [&](int qb) {
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the previous dQ store has left the tile
+      __syncwarp();
+      const uint32_t off = (r >> 3) * 1024 + (r & 7) * 128;
+      const uint4* src = reinterpret_cast<const uint4*>(sTile + (TQ0 + qb) * F_TILE + off);
+      uint4* dst = reinterpret_cast<uint4*>(sTile + TOUT * F_TILE + off);
+      uint4 v[8];  // chunk order rotated by the row so the 32 lanes of an access hit all banks (a plain copy: any order works)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) v[c] = src[c ^ (r & 7)];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) dst[c ^ (r & 7)] = v[c];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[TQ0 + qb]);
+    };
+    if (G > 0) {
+      fetch_ld(blockIdx.x);
+      commit_ld(0);
+    }
+    for (int g = 0; g < G; ++g) {
+      const int i = g & 3, qb = qb_of(g), it = g >> 2;
+      const int item = blockIdx.x + it * gridDim.x;
+      const int buf = (it & 1) * F_T;
+      if (warp == 2 && i == 2) FSTAMP(2, g, 1);
+      release_pending();
+      if (warp == 2 && i == 2) FSTAMP(2, g, 2);
+      if (i == 0) {
+        if (warp == 2) FSTAMP(2, g, 1);
+        if (g > 0 && half == 0) stash_q(qb_of(g - 1));  // the previous item's first block, for its dQ read-out below
+        if (warp == 2) FSTAMP(2, g, 2);
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // L / delta of this item (written an iteration or more ago) visible
+      }
+      if (i == 2 && it + 1 < my_items) fetch_ld(item + gridDim.x);
+      if (warp == 2) FSTAMP(1, g, 0);
+      mbar_wait(s_full, g & 1);
+      if (warp == 2) FSTAMP(1, g, 1);
+      tc_fence_after();
+      uint32_t pp[32], pd[32];
+      const float* Lq = sL + buf + qb * RT + half * 64;
+      const float* Dq = sDl + buf + qb * RT + half * 64;
+#pragma unroll
+      for (int c2 = 0; c2 < 2; ++c2) {
+        uint32_t sv[32], dp[32];
+        tmem_ld32(t_lane + C_S + half * 64 + c2 * 32, sv);
+        tmem_ld32(t_lane + C_DP + half * 64 + c2 * 32, dp);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {  // four queries per step: their L and delta are one 16-byte broadcast load each
+          const int c = c2 * 32 + 4 * j;
+          const float4 l4 = *reinterpret_cast<const float4*>(Lq + c), d4 = *reinterpret_cast<const float4*>(Dq + c);
+          const float p0 = ex2(fmaf(__uint_as_float(sv[4 * j]), c1, -l4.x));
+          const float p1 = ex2(fmaf(__uint_as_float(sv[4 * j + 1]), c1, -l4.y));
+          const float p2 = ex2(fmaf(__uint_as_float(sv[4 * j + 2]), c1, -l4.z));
+          const float p3 = ex2(fmaf(__uint_as_float(sv[4 * j + 3]), c1, -l4.w));
+          pp[c2 * 16 + 2 * j] = pack_bf16(p0, p1);
+          pp[c2 * 16 + 2 * j + 1] = pack_bf16(p2, p3);
+          pd[c2 * 16 + 2 * j] = pack_bf16(p0 * (__uint_as_float(dp[4 * j]) - d4.x), p1 * (__uint_as_float(dp[4 * j + 1]) - d4.y));
+          pd[c2 * 16 + 2 * j + 1] = pack_bf16(p2 * (__uint_as_float(dp[4 * j + 2]) - d4.z), p3 * (__uint_as_float(dp[4 * j + 3]) - d4.w));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_empty);
+      if (warp == 2) FSTAMP(1, g, 2);
+      if (g > 0) mbar_wait(p_empty, (g - 1) & 1);  // the MMAs that read the staging tiles (and completed dV/dK/dQ) have retired
+      store_row_sw128(sPt + half * F_TILE, r, pp);
+      store_row_sw128(sdSt + half * F_TILE, r, pd);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+      if (warp == 2) FSTAMP(1, g, 3);
+      if (i == 2 && it + 1 < my_items) commit_ld(buf ^ F_T);
+      // ---- accumulator read-out.  half 0 warps: dV_0 | dQ (second block) | dQ (first block); half 1 warps: dK_0 | - | dV_1, dK_1
+      if (i == 1) {          // the second query block is resident (S of this iteration used it): stash its q^ rows
+        if (half == 0) stash_q(qb);
+        if (warp == 2) FSTAMP(2, g, 0);
+      } else if (i == 2) {   // key tile 0 finished with iteration 1
+        const int n = item / heads, h = item - n * heads;
+        const size_t grow0 = (size_t)n * F_T;
+        uint32_t a0[32], a1[32];
+        tc_fence_after();
+        tmem_ld32(t_lane + (half ? C_DK : C_DV), a0);
+        tmem_ld32(t_lane + (half ? C_DK : C_DV) + 32, a1);
+        tmem_ld_wait();
+        signal_free(acc_free);
+        if (half == 0) {
+          uint32_t out[32];
+          pack_row(a0, a1, 1.0f, out);
+          store_slab(sTile + TV0 * F_TILE, out, grow0, 2 * D + h * HD);
+          rel_a = TV0;
+        } else {
+          finish_qk(a0, a1, sTile + TK0 * F_TILE, grow0, D + h * HD, heads + h);
+          rel_a = TK0;
+        }
+        if (warp == 2) FSTAMP(2, g, 0);
+      } else if (i == 3) {   // the item's second query block finished with iteration 2 (no MMA overwrites dQ before the next item)
+        if (half == 0) {
+          const int n = item / heads, h = item - n * heads;
+          const int qs = qb_of(g - 1);
+          uint32_t a0[32], a1[32];
+          tc_fence_after();
+          tmem_ld32(t_lane + C_DQ + qs * HD, a0);
+          tmem_ld32(t_lane + C_DQ + qs * HD + 32, a1);
+          tmem_ld_wait();
+          finish_qk(a0, a1, sTile + TOUT * F_TILE, (size_t)n * F_T + qs * RT, h * HD, h);
+        }
+        if (warp == 2) FSTAMP(2, g, 0);
+      } else if (g > 0) {    // i == 0: previous item: key tile 1 and its first query block finished with its iteration 3
+        const int pit = item - gridDim.x;
+        const int n = pit / heads, h = pit - n * heads;
+        tc_fence_after();
+        if (half == 0) {
+          const int qf = qb_of(g - 1);
+          uint32_t a0[32], a1[32];
+          signal_free(acc_free);  // (8 arrivals per phase; these warps do not read dV / dK here)
+          tmem_ld32(t_lane + C_DQ + qf * HD, a0);
+          tmem_ld32(t_lane + C_DQ + qf * HD + 32, a1);
+          tmem_ld_wait();
+          signal_free(dq_free);
+          finish_qk(a0, a1, sTile + TOUT * F_TILE, (size_t)n * F_T + qf * RT, h * HD, h);
+        } else {
+          const size_t grow0 = (size_t)n * F_T + RT;
+          uint32_t a0[32], a1[32], outv[32];
+          tmem_ld32(t_lane + C_DV, a0);
+          tmem_ld32(t_lane + C_DV + 32, a1);
+          tmem_ld_wait();
+          pack_row(a0, a1, 1.0f, outv);
+          tmem_ld32(t_lane + C_DK, a0);
+          tmem_ld32(t_lane + C_DK + 32, a1);
+          tmem_ld_wait();
+          signal_free(acc_free);
+          store_slab(sTile + TV1 * F_TILE, outv, grow0, 2 * D + h * HD);
+          finish_qk(a0, a1, sTile + TK1 * F_TILE, grow0, D + h * HD, heads + h);
+          rel_a = TK1;
+          rel_b = TV1;
+        }
+        if (warp == 2) FSTAMP(2, g, 0);
+      }
+    }
+    if (G > 0) {  // last item: key tile 1 and the first query block
+      mbar_wait(p_empty, (G - 1) & 1);
+      tc_fence_after();
+      const int item = blockIdx.x + (my_items - 1) * gridDim.x;
+      const int n = item / heads, h = item - n * heads;
+      uint32_t a0[32], a1[32];
+      if (half == 0) {
+        const int qf = qb_of(G - 1);
+        stash_q(qf);
+        tmem_ld32(t_lane + C_DQ + qf * HD, a0);
+        tmem_ld32(t_lane + C_DQ + qf * HD + 32, a1);
+        tmem_ld_wait();
+        finish_qk(a0, a1, sTile + TOUT * F_TILE, (size_t)n * F_T + qf * RT, h * HD, h);
+      } else {
+        const size_t grow0 = (size_t)n * F_T + RT;
+        uint32_t outv[32];
+        tmem_ld32(t_lane + C_DV, a0);
+        tmem_ld32(t_lane + C_DV + 32, a1);
+        tmem_ld_wait();
+        pack_row(a0, a1, 1.0f, outv);
+        store_slab(sTile + TV1 * F_TILE, outv, grow0, 2 * D + h * HD);
+        tmem_ld32(t_lane + C_DK, a0);
+        tmem_ld32(t_lane + C_DK + 32, a1);
+        tmem_ld_wait();
+        finish_qk(a0, a1, sTile + TK1 * F_TILE, grow0, D + h * HD, heads + h);
+      }
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete before the CTA exits
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+__global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ dout, float* __restrict__ delta,
+                                                         long long m_heads, int heads) {
+  // delta[row, head] = dO_row,head . O_row,head : one thread per (row, head), 128 contiguous bytes of each tensor
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m_heads) return;
+  const uint4* po = reinterpret_cast<const uint4*>(o + i * HD);
+  const uint4* pg = reinterpret_cast<const uint4*>(dout + i * HD);
+  float dl = 0.f;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const uint4 a = po[c], b = pg[c];
+    const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&a);
+    const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&b);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 x = __bfloat1622float2(ha[e]), y = __bfloat1622float2(hb[e]);
+      dl = fmaf(x.x, y.x, fmaf(x.y, y.y, dl));
+    }
+  }
+  delta[i] = dl;
+}
+
 int encode2d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint64_t ld_elems, uint32_t box_rows) {
   const uint64_t dims[2] = {cols, rows};
   const uint64_t strides[1] = {ld_elems * 2};
@@ -487,8 +1018,34 @@ static int attn_bwd_impl(const void* qkv, const void* o, const void* dout, const
     }
     attr_set = true;
   }
-  dim3 grid((tokens + RT - 1) / RT, heads, n_samples);
   cudaStream_t s = (cudaStream_t)stream;
+  if (tokens == F_T && g_mapdit_attn_bwd_fused) {
+    static bool fattr = false;
+    if (!fattr) {
+      if (cudaFuncSetAttribute(attn_bwd_fused_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM) != cudaSuccess) {
+        mapdit_set_error("cos_attn_bwd(fused): cudaFuncSetAttribute failed");
+        return MAPDIT_ERR_CUDA;
+      }
+      fattr = true;
+    }
+    const long long mh = (long long)rows * heads;
+    attn_delta_kernel<<<(unsigned)((mh + 255) / 256), 256, 0, s>>>((const bf16*)o, (const bf16*)dout, delta, mh, heads);
+    MAPDIT_LAUNCH_CHECK("cos_attn_bwd(delta)");
+    const int items = n_samples * heads;
+    int sms = 0, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    CUtensorMap t_out;  // per-warp stores of 32-row slabs of a [128 x 64] smem tile
+    if (encode2d(&t_out, dqkv, 3 * D, rows, 3 * D, 32) != 0) {
+      mapdit_set_error("cos_attn_bwd(fused): cuTensorMapEncodeTiled failed");
+      return MAPDIT_ERR_CUDA;
+    }
+    attn_bwd_fused_tc<<<items < sms ? items : sms, F_NTHREADS, F_SMEM, s>>>(t_qkv_row, t_do_row, t_out, lse, delta, heads, items,
+                                                                           (const bf16*)qkv, sc, eps, g_attn_dbg);
+    MAPDIT_LAUNCH_CHECK("cos_attn_bwd(fused)");
+    return MAPDIT_OK;
+  }
+  dim3 grid((tokens + RT - 1) / RT, heads, n_samples);
   attn_bwd_dq_tc<<<grid, NTHREADS, DQ_SMEM, s>>>(t_qkv_row, t_qkv_blk, t_do_row, (const bf16*)o, (const bf16*)dout, lse, delta,
                                                  (bf16*)dqkv, tokens, heads, (const bf16*)qkv, sc, eps);
   MAPDIT_LAUNCH_CHECK("cos_attn_bwd(dq)");

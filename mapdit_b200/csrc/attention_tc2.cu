@@ -295,7 +295,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 
 bool mapdit_attn_tc2_supported(int tokens, int hd) { return hd == HD && tokens % (2 * QT) == 0 && tokens >= 2 * QT; }
 
-static long long* g_attn_dbg = nullptr;
+long long* g_attn_dbg = nullptr;  // also stamped by attn_bwd_fused_tc (attention_bwd_tc.cu)
 extern "C" int mapdit_attn_debug_buffer(void* p) {  // developer hook: timeline buffer of >= 1024 int64 (or null)
   g_attn_dbg = (long long*)p;
   return MAPDIT_OK;

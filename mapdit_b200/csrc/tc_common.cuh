@@ -37,6 +37,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t addr, uint32_t parity) {
       : "memory");
   return done != 0;
 }
+// non-blocking probe (try_wait may suspend the thread for a hardware-defined interval before it reports "not yet")
+__device__ __forceinline__ bool mbar_test_wait(uint32_t addr, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(addr), "r"(parity)
+      : "memory");
+  return done != 0;
+}
 static __device__ __noinline__ void mbar_wait_slow(uint32_t addr, uint32_t parity) {
   const long long t0 = clock64();
   while (!mbar_try_wait(addr, parity)) {

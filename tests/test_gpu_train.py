@@ -32,7 +32,8 @@ def test_gemm_bf16_tn(m, n, k):
 
 
 @pytest.mark.parametrize("N,T,H,hd,dtype", [(2, 64, 3, 64, torch.float32), (1, 256, 2, 64, torch.float32), (1, 80, 2, 72, torch.float32),
-                                             (2, 128, 2, 64, torch.bfloat16)])
+                                             (2, 128, 2, 64, torch.bfloat16), (1, 256, 2, 64, torch.bfloat16),
+                                             (30, 256, 6, 64, torch.bfloat16)])
 def test_attention_backward(N, T, H, hd, dtype):
     from mapdit_b200 import ops
     D = H * hd
@@ -278,7 +279,8 @@ def test_checkpoint_roundtrips_through_torch_adam(tmp_path):
     assert ts.ema.emas[0.05].blocks[0].attn.qkv_proj.weight.is_cuda
 
 
-@pytest.mark.parametrize("N,T,H,dtype", [(2, 256, 4, torch.bfloat16), (3, 64, 2, torch.bfloat16), (2, 64, 2, torch.float32)])
+@pytest.mark.parametrize("N,T,H,dtype", [(2, 256, 4, torch.bfloat16), (3, 64, 2, torch.bfloat16), (2, 64, 2, torch.float32),
+                                         (26, 256, 12, torch.bfloat16)])
 def test_attention_backward_with_fused_qk_norm(N, T, H, dtype):
     """cos_attn_bwd_qknorm (q/k-normalisation backward fused into the dq/dk epilogues on the tcgen05 path, separate kernel
     behind the CUDA-core path) == autograd through normalize + SDPA (src/layers/attention.py:43-47)"""
@@ -305,6 +307,21 @@ def test_attention_backward_with_fused_qk_norm(N, T, H, dtype):
     e = rel_l2(dqkv.float(), r.grad)
     print(f"fused attention + qk-norm backward {dtype}: rel-L2 vs autograd {e:.2e}")
     assert e < (3e-5 if dtype == torch.float32 else 2.5e-2)
+    if T == 256 and dtype == torch.bfloat16:
+        # tokens == 256 runs the single fused kernel (attn_bwd_fused_tc); the dq + dkv kernel pair must agree with it
+        from mapdit_b200 import _lib
+        _lib.set_option("attn_bwd_fused", 0)
+        try:
+            d2 = torch.full_like(qkv, float("nan"))
+            ops.cos_attn_bwd_qknorm(qkv, o, dout, lse, sc, d2, delta, N, T, H, hd)
+            torch.cuda.synchronize()
+        finally:
+            _lib.set_option("attn_bwd_fused", 1)
+        assert rel_l2(d2.float(), r.grad) < 2.5e-2
+        assert rel_l2(d2.float(), dqkv.float()) < 1e-2
+        for third in range(3):  # per-tensor (dq, dk, dv) so a wrong small tensor cannot hide in the norm of the others
+            sl = slice(third * D, (third + 1) * D)
+            assert rel_l2(dqkv[:, sl].float(), r.grad[:, sl]) < 2.5e-2, third
 
 
 @pytest.mark.parametrize("N,T,H,hd,cosine", [(2, 128, 3, 72, True), (1, 1024, 2, 72, True), (2, 256, 4, 64, False), (3, 64, 2, 32, False)])
