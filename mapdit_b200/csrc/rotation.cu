@@ -94,7 +94,7 @@ __device__ __forceinline__ void st4(bf16* p, const float (&f)[4]) {
 }
 
 template <typename T, bool FUSE>
-__global__ void __launch_bounds__(256) rotmod_bwd_kernel(const T* __restrict__ dh, const T* __restrict__ x, T* R,
+__global__ void __launch_bounds__(256, FUSE ? 2 : 3) rotmod_bwd_kernel(const T* __restrict__ dh, const T* __restrict__ x, T* R,
                                                          const float* __restrict__ rot, const float* __restrict__ scale,
                                                          const float* __restrict__ gain, float* __restrict__ drot,
                                                          float* __restrict__ dscale, float* __restrict__ dg_partial, int64_t ldmod, int d,
@@ -126,36 +126,48 @@ __global__ void __launch_bounds__(256) rotmod_bwd_kernel(const T* __restrict__ d
     a_gt[j] = 0.f;
   }
   if (ok) {
-    for (int t = warp; t < tokens; t += 8) {
-      const size_t off = ((size_t)n * tokens + t) * d + col;
-      float gh[4], xv[4], r[4];
-      ld4(dh + off, gh);
-      ld4(x + off, xv);
-      if (R && accumulate) ld4(R + off, r);
+    constexpr int U = FUSE ? 4 : 2;  // two tokens per trip: every load of both tokens is issued before the first dependent instruction
+    for (int t0 = warp; t0 < tokens; t0 += 8 * U) {
+      float gh[U][4], xv[U][4], r[U][4], yv[U][4];
+      size_t off[U];
+      bool live[U];
 #pragma unroll
-      for (int p = 0; p < 2; ++p) {
-        const float x0 = xv[2 * p], x1 = xv[2 * p + 1];
-        const float r0 = x0 * cs[p] - x1 * sn[p], r1 = x0 * sn[p] + x1 * cs[p];  // rotated x
-        a_sc[2 * p] = fmaf(gh[2 * p], r0, a_sc[2 * p]);
-        a_sc[2 * p + 1] = fmaf(gh[2 * p + 1], r1, a_sc[2 * p + 1]);
-        const float g0 = gh[2 * p] * sc[2 * p], g1 = gh[2 * p + 1] * sc[2 * p + 1];  // d/d(rotated x)
-        a_th[p] += g0 * (-r1) + g1 * r0;                                               // d rotated / d theta = (-r1, r0)
-        const float dx0 = g0 * cs[p] + g1 * sn[p], dx1 = -g0 * sn[p] + g1 * cs[p];
-        r[2 * p] = ((R && accumulate) ? r[2 * p] : 0.f) + dx0;
-        r[2 * p + 1] = ((R && accumulate) ? r[2 * p + 1] : 0.f) + dx1;
+      for (int u = 0; u < U; ++u) {
+        const int t = t0 + 8 * u;
+        live[u] = t < tokens;
+        off[u] = ((size_t)n * tokens + (live[u] ? t : t0)) * d + col;
+        ld4(dh + off[u], gh[u]);
+        ld4(x + off[u], xv[u]);
+        if (R && accumulate) ld4(R + off[u], r[u]);
+        if (FUSE) ld4(y + off[u], yv[u]);
       }
-      if (FUSE) {
-        float yv[4], o1[4];
-        ld4(y + off, yv);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          o1[j] = gt[j] * r[j];
-          a_gt[j] = fmaf(cb_r * yv[j], r[j], a_gt[j]);
-          r[j] *= ca_r;
+      for (int u = 0; u < U; ++u) {
+        if (!live[u]) continue;
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+          const float x0 = xv[u][2 * p], x1 = xv[u][2 * p + 1];
+          const float r0 = x0 * cs[p] - x1 * sn[p], r1 = x0 * sn[p] + x1 * cs[p];  // rotated x
+          a_sc[2 * p] = fmaf(gh[u][2 * p], r0, a_sc[2 * p]);
+          a_sc[2 * p + 1] = fmaf(gh[u][2 * p + 1], r1, a_sc[2 * p + 1]);
+          const float g0 = gh[u][2 * p] * sc[2 * p], g1 = gh[u][2 * p + 1] * sc[2 * p + 1];  // d/d(rotated x)
+          a_th[p] += g0 * (-r1) + g1 * r0;                                                       // d rotated / d theta = (-r1, r0)
+          const float dx0 = g0 * cs[p] + g1 * sn[p], dx1 = -g0 * sn[p] + g1 * cs[p];
+          r[u][2 * p] = ((R && accumulate) ? r[u][2 * p] : 0.f) + dx0;
+          r[u][2 * p + 1] = ((R && accumulate) ? r[u][2 * p + 1] : 0.f) + dx1;
         }
-        st4(dy + off, o1);
+        if (FUSE) {
+          float o1[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            o1[j] = gt[j] * r[u][j];
+            a_gt[j] = fmaf(cb_r * yv[u][j], r[u][j], a_gt[j]);
+            r[u][j] *= ca_r;
+          }
+          st4(dy + off[u], o1);
+        }
+        if (R) st4(R + off[u], r[u]);
       }
-      if (R) st4(R + off, r);
     }
   }
 #pragma unroll
