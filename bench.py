@@ -19,8 +19,16 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# stdout carries exactly one JSON line: NCCL's version/debug banner goes to stderr
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# stdout carries exactly one JSON line.  NCCL prints its version banner to file descriptor 1 from C (NCCL_DEBUG_FILE does not
+# cover it), so fd 1 is pointed at stderr for the whole run and the JSON line is written to the saved descriptor.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit_line(line):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
 
 MODEL = "DiT-B/2"
 SAMPLING_STEPS = 50
@@ -106,7 +114,7 @@ def run_reference(args, workload=None, emit=True):
         sl = run_reference(args, "sample", emit=False)
         line["metric"] = "dit_b2_map_train_img_per_s (+ sample50 img/s in `sample50`)"
         line["sample50"] = {k: sl[k] for k in ("value", "unit", "ms_per_step", "cpu_baseline", "e2e")}
-        print(json.dumps(line), flush=True)
+        emit_line(line)
         return line
         return line
     from oracle import mapdit_oracle as O
@@ -164,7 +172,7 @@ def run_reference(args, workload=None, emit=True):
             "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     if emit:
-        print(json.dumps(line), flush=True)
+        emit_line(line)
     return line
 
 
@@ -473,7 +481,7 @@ def main():
         # convenience: re-launch under torchrun
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
                "--master-port", "29541", os.path.abspath(__file__)] + sys.argv[1:]
-        sys.exit(subprocess.call(cmd))
+        sys.exit(subprocess.call(cmd, stdout=_REAL_STDOUT))
     if args.workload == "both":
         # BASELINE.json's metric has two halves: the training step is the primary value, the 50-step sampler rides along
         line = run_ours(args, "train", finalize=False)
@@ -507,7 +515,7 @@ def main():
     else:
         line = run_ours(args, args.workload)
     if line is not None:
-        print(json.dumps(line), flush=True)
+        emit_line(line)
 
 
 if __name__ == "__main__":
