@@ -956,24 +956,38 @@ attn_bwd_fused_tc(const __grid_constant__ CUtensorMap tm_qkv, const __grid_const
 
 __global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ dout, float* __restrict__ delta,
                                                          long long m_heads, int heads) {
-  // delta[row, head] = dO_row,head . O_row,head : one thread per (row, head), 128 contiguous bytes of each tensor
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= m_heads) return;
-  const uint4* po = reinterpret_cast<const uint4*>(o + i * HD);
-  const uint4* pg = reinterpret_cast<const uint4*>(dout + i * HD);
-  float dl = 0.f;
+  // delta[row, head] = dO_row,head . O_row,head over 64 channels (128 contiguous bytes of each tensor).  Eight lanes share one
+  // (row, head): lane l reads the 16-byte chunk l % 8, so every load instruction of a warp covers 512 contiguous bytes
+  // (a thread-per-row layout touches 32 different lines per instruction and ran at 60 % of the HBM peak); a warp handles
+  // 32 (row, head) pairs per trip, all 16 loads issued before the first use.
+  const int lane = threadIdx.x & 31, sub = lane >> 3, ch = lane & 7;
+  const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long base = warp_id * 32;
+  if (base >= m_heads) return;
+  uint4 a[8], b[8];
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const uint4 a = po[c], b = pg[c];
-    const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&a);
-    const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&b);
+  for (int k = 0; k < 8; ++k) {
+    const long long i = base + k * 4 + sub;
+    const bool ok = i < m_heads;
+    a[k] = ok ? reinterpret_cast<const uint4*>(o + i * HD)[ch] : make_uint4(0, 0, 0, 0);
+    b[k] = ok ? reinterpret_cast<const uint4*>(dout + i * HD)[ch] : make_uint4(0, 0, 0, 0);
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&a[k]);
+    const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&b[k]);
+    float dl = 0.f;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const float2 x = __bfloat1622float2(ha[e]), y = __bfloat1622float2(hb[e]);
       dl = fmaf(x.x, y.x, fmaf(x.y, y.y, dl));
     }
+    dl += __shfl_xor_sync(0xffffffffu, dl, 1);
+    dl += __shfl_xor_sync(0xffffffffu, dl, 2);
+    dl += __shfl_xor_sync(0xffffffffu, dl, 4);
+    const long long i = base + k * 4 + sub;
+    if (ch == 0 && i < m_heads) delta[i] = dl;
   }
-  delta[i] = dl;
 }
 
 int encode2d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint64_t ld_elems, uint32_t box_rows) {
