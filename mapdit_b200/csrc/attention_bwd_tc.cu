@@ -20,7 +20,8 @@ int mapdit_attn_mma_bwd(const void* qkv, const void* o, const void* dout, const 
                         int heads, int hd, void* stream);
 bool mapdit_attn_mma_supported(int tokens, int hd);
 
-int g_mapdit_attn_bwd_fused = 1;  // mapdit_set_option("attn_bwd_fused", 0/1): single fused kernel for tokens == 256
+int g_mapdit_attn_bwd_fused = 2;  // mapdit_set_option("attn_bwd_fused", 0/1/2): tokens == 256: 0 = dq + dkv kernel pair, 1 = fused kernel,
+                                  // 2 = fused kernel with a dedicated read-out warpgroup
 
 extern long long* g_attn_dbg;  // developer timeline hook (mapdit_attn_debug_buffer)
 
@@ -954,6 +955,445 @@ attn_bwd_fused_tc(const __grid_constant__ CUtensorMap tm_qkv, const __grid_const
   if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
+// ------------------------------------------------------------------------------------------------ fused backward, second cut
+// Same data flow, tiles, barriers and MMA schedule as attn_bwd_fused_tc, but the accumulator read-outs have their own four
+// warps (10-13) so the eight softmax warps only do  wait S -> exp -> staging -> publish.  14 warps put four warps on two of
+// the SM sub-partitions, which caps every thread at 128 registers: the exp pass reads TMEM 16 columns at a time, and a q/k-norm
+// read-out makes two passes over its accumulator (dot product, then the output) in 32-column halves instead of holding the whole row.
+constexpr int F2_NTHREADS = 448;
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+// 32 bf16 (columns 32*hf .. 32*hf+31) of row r of a [128 x 64] SWIZZLE_128B tile <-> registers
+__device__ __forceinline__ void load_half_row_sw128(const uint8_t* tile, int r, int hf, float (&y)[32]) {
+  const uint8_t* prow = tile + (r >> 3) * 1024 + (r & 7) * 128;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const uint4 u = *reinterpret_cast<const uint4*>(prow + (((hf * 4 + c) ^ (r & 7)) << 4));
+    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 t = __bfloat1622float2(h2[e]);
+      y[8 * c + 2 * e] = t.x;
+      y[8 * c + 2 * e + 1] = t.y;
+    }
+  }
+}
+__device__ __forceinline__ void store_half_row_sw128(uint8_t* tile, int r, int hf, const uint32_t (&pk)[16]) {
+  uint8_t* prow = tile + (r >> 3) * 1024 + (r & 7) * 128;
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+    *reinterpret_cast<uint4*>(prow + (((hf * 4 + c) ^ (r & 7)) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+}
+
+__global__ void __launch_bounds__(F2_NTHREADS, 1)
+attn_bwd_fused2_tc(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
+                   const __grid_constant__ CUtensorMap tm_out, const float* __restrict__ lse, const float* __restrict__ delta, int heads,
+                   int total_items, const float* __restrict__ sc, float eps, long long* __restrict__ dbg) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* sTile = smem;                      // 8 input tiles + the dQ staging tile, index = T* enum
+  uint8_t* sPt = sTile + 9 * F_TILE;
+  uint8_t* sdSt = sPt + F_STG;
+  float* sL = reinterpret_cast<float*>(sdSt + F_STG);  // [2][256] log2-domain log-sum-exp of the item's queries
+  float* sDl = sL + 2 * F_T;                            // [2][256] delta
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDl + 2 * F_T);
+  uint64_t* full = bars;            // [8] input tile landed
+  uint64_t* empty = bars + 8;       // [8] input tile may be refilled
+  uint64_t* s_full = bars + 16;     // S^T / dP^T of iteration g complete
+  uint64_t* s_empty = bars + 17;    // ... read by the 8 softmax warps
+  uint64_t* p_full = bars + 18;     // [2] 64-query panel `half` of the P^T / dS^T staging tiles of iteration g written (4 warps each)
+  uint64_t* p_empty = bars + 20;    // [2] ... consumed by the dV / dK / dQ MMAs (k-steps 0-3 read panel 0, 4-7 panel 1)
+  uint64_t* acc_free = bars + 22;   // dV / dK read out (4 epilogue warps), twice per item
+  uint64_t* dqs_free = bars + 23;   // dQ of the item's second query block read out
+  uint64_t* dqf_free = bars + 24;   // dQ of the item's first query block read out
+  uint64_t* kv0_ready = bars + 25;  // MMA -> epilogue: dV_0 / dK_0 complete (after iteration 1)
+  uint64_t* dqs_ready = bars + 26;  // dQ (second block) complete (after iteration 2)
+  uint64_t* fin_ready = bars + 27;  // dV_1 / dK_1 / dQ (first block) complete (after iteration 3)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int D = heads * HD;
+  const int my_items = blockIdx.x < total_items ? (total_items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int G = my_items * 4;
+  auto qb_of = [](int g) { return (((g & 3) == 1 || (g & 3) == 2) ? 1 : 0) ^ ((g >> 2) & 1); };
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tm_qkv);
+    prefetch_tmap(&tm_do);
+    prefetch_tmap(&tm_out);
+    for (int i = 0; i < 8; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], i < TD0 ? 5 : 1);  // K / V / Q tiles: the MMA warp + four epilogue warps
+    }
+    mbar_init(s_full, 1);
+    mbar_init(s_empty, 8);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&p_full[i], 4);
+      mbar_init(&p_empty[i], 1);
+    }
+    mbar_init(acc_free, 4);
+    mbar_init(dqs_free, 4);
+    mbar_init(dqf_free, 4);
+    mbar_init(kv0_ready, 1);
+    mbar_init(dqs_ready, 1);
+    mbar_init(fin_ready, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  constexpr uint32_t C_S = 0, C_DP = 128, C_DV = 256, C_DK = 320, C_DQ = 384;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < my_items; ++it) {
+        const int item = blockIdx.x + it * gridDim.x;
+        const int n = item / heads, h = item - n * heads;
+        const uint32_t ph = it & 1;
+        const int f = it & 1;
+        if (it + 1 < my_items) {  // next item's 128 KB into L2, one whole item ahead (see attn_bwd_fused_tc)
+          const int nitem = item + gridDim.x;
+          const int nn = nitem / heads, nh = nitem - nn * heads;
+#pragma unroll
+          for (int rb = 0; rb < 2; ++rb) {
+            const int row = nn * F_T + rb * RT;
+            tma_prefetch_l2_2d(&tm_qkv, nh * HD, row);
+            tma_prefetch_l2_2d(&tm_qkv, D + nh * HD, row);
+            tma_prefetch_l2_2d(&tm_qkv, 2 * D + nh * HD, row);
+            tma_prefetch_l2_2d(&tm_do, nh * HD, row);
+          }
+        }
+        const int order[8] = {TK0, TV0, TQ0 + f, TD0 + f, TQ0 + (f ^ 1), TD0 + (f ^ 1), TK1, TV1};
+        for (int k = 0; k < 8; ++k) {
+          const int t = order[k];
+          mbar_wait(&empty[t], ph ^ 1);
+          mbar_arrive_expect_tx(&full[t], F_TILE);
+          const int row = n * F_T + (t & 1) * RT;
+          if (t >= TD0) tma_load_2d(sTile + t * F_TILE, &tm_do, &full[t], h * HD, row);
+          else tma_load_2d(sTile + t * F_TILE, &tm_qkv, &full[t], (t >= TQ0 ? 0 : (t >= TV0 ? 2 * D : D)) + h * HD, row);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    const bool leader = elect_one();
+    constexpr uint32_t idesc_s = make_idesc_bf16(RT, 128, 0, 0);
+    constexpr uint32_t idesc_a = make_idesc_bf16(RT, HD, 0, 1);
+    constexpr uint32_t idesc_q = make_idesc_bf16(RT, HD, 1, 1);
+    const uint32_t tile0 = smem_u32(sTile), pt_addr = smem_u32(sPt), dst_addr = smem_u32(sdSt);
+    auto scores = [&](int g) {
+      const int i = g & 3, kt = i >> 1, qb = qb_of(g);
+      const uint32_t ph = (g >> 2) & 1;
+      if ((i & 1) == 0) {
+        mbar_wait(&full[TK0 + kt], ph);
+        mbar_wait(&full[TV0 + kt], ph);
+      }
+      if (kt == 0) {
+        mbar_wait(&full[TQ0 + qb], ph);
+        mbar_wait(&full[TD0 + qb], ph);
+      }
+      mbar_wait(s_empty, (g & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t k_addr = tile0 + (TK0 + kt) * F_TILE, v_addr = tile0 + (TV0 + kt) * F_TILE;
+      const uint32_t q_addr = tile0 + (TQ0 + qb) * F_TILE, do_addr = tile0 + (TD0 + qb) * F_TILE;
+#pragma unroll
+      for (int k = 0; k < HD / 16; ++k) {
+        if (leader) umma_ss(tmem_base + C_S, make_smem_desc(k_addr + k * 32, 16, 1024), make_smem_desc(q_addr + k * 32, 16, 1024), idesc_s, k != 0);
+        if (leader) umma_ss(tmem_base + C_DP, make_smem_desc(v_addr + k * 32, 16, 1024), make_smem_desc(do_addr + k * 32, 16, 1024), idesc_s, k != 0);
+      }
+      if (leader) umma_commit(s_full);
+    };
+    auto tiles_ready = [&](int g) {
+      const int i = g & 3, kt = i >> 1, qb = qb_of(g);
+      const uint32_t ph = (g >> 2) & 1;
+      bool ok = true;
+      if ((i & 1) == 0) ok = mbar_test_wait(smem_u32(&full[TK0 + kt]), ph) && mbar_test_wait(smem_u32(&full[TV0 + kt]), ph);
+      if (kt == 0) ok = ok && mbar_test_wait(smem_u32(&full[TQ0 + qb]), ph) && mbar_test_wait(smem_u32(&full[TD0 + qb]), ph);
+      return __all_sync(0xffffffffu, ok) != 0;
+    };
+    if (G > 0) scores(0);
+    for (int g = 0; g < G; ++g) {
+      const int i = g & 3, kt = i >> 1, qb = qb_of(g), it = g >> 2;
+      bool issued = g + 1 >= G;
+      auto phase2_ready = [&]() {
+        bool ok = mbar_test_wait(smem_u32(&p_full[0]), g & 1) && mbar_test_wait(smem_u32(&p_full[1]), g & 1);
+        if (i == 2) ok = ok && mbar_test_wait(smem_u32(acc_free), 0);                         // dV_0 / dK_0 read out
+        if (i == 0 && it > 0) ok = ok && mbar_test_wait(smem_u32(acc_free), 1)                // previous item: dV_1 / dK_1 ...
+                                   && mbar_test_wait(smem_u32(dqs_free), (it - 1) & 1);        // ... and the dQ this block's columns held
+        if (i == 1 && it > 0) ok = ok && mbar_test_wait(smem_u32(dqf_free), (it - 1) & 1);
+        return __all_sync(0xffffffffu, ok) != 0;
+      };
+      {
+        const long long t0 = clock64();
+        for (;;) {
+          if (!issued && tiles_ready(g + 1)) {
+            scores(g + 1);
+            issued = true;
+          }
+          if (phase2_ready()) break;
+          if (clock64() - t0 > 4000000000LL) {
+            if (lane == 0) printf("mapdit: attn_bwd_fused2 MMA warp timed out (block %d iteration %d)\n", blockIdx.x, g);
+            __trap();
+          }
+        }
+      }
+      FSTAMP(0, g, 1);
+      tc_fence_after();
+      const uint32_t k_addr = tile0 + (TK0 + kt) * F_TILE;
+      const uint32_t q_addr = tile0 + (TQ0 + qb) * F_TILE, do_addr = tile0 + (TD0 + qb) * F_TILE;
+      // three independent accumulation chains, issued round-robin (back-to-back MMAs into one accumulator serialise)
+#pragma unroll
+      for (int k = 0; k < 128 / 16; ++k) {
+        const uint32_t a_off = (k >> 2) * F_TILE + (k & 3) * 32;
+        if (leader) umma_ss(tmem_base + C_DV, make_smem_desc(pt_addr + a_off, 16, 1024), make_smem_desc(do_addr + k * 2048, 1024, 1024), idesc_a,
+                ((i & 1) | k) != 0);
+        if (leader) umma_ss(tmem_base + C_DK, make_smem_desc(dst_addr + a_off, 16, 1024), make_smem_desc(q_addr + k * 2048, 1024, 1024), idesc_a,
+                ((i & 1) | k) != 0);
+        if (leader) umma_ss(tmem_base + C_DQ + qb * HD, make_smem_desc(dst_addr + k * 2048, F_TILE, 1024), make_smem_desc(k_addr + k * 2048, 1024, 1024),
+                idesc_q, (kt | k) != 0);
+      }
+      if (leader) umma_commit(&p_empty[0]);
+      if (leader) umma_commit(&p_empty[1]);
+      FSTAMP(0, g, 2);
+      if (i == 1) {
+        if (leader) umma_commit(kv0_ready);
+        if (leader) umma_commit(&empty[TK0]);
+        if (leader) umma_commit(&empty[TV0]);
+      } else if (i == 2) {
+        if (leader) umma_commit(dqs_ready);
+        if (leader) umma_commit(&empty[TQ0 + qb]);
+        if (leader) umma_commit(&empty[TD0 + qb]);
+      } else if (i == 3) {
+        if (leader) umma_commit(fin_ready);
+        if (leader) umma_commit(&empty[TQ0 + qb]);
+        if (leader) umma_commit(&empty[TD0 + qb]);
+        if (leader) umma_commit(&empty[TK1]);
+        if (leader) umma_commit(&empty[TV1]);
+      }
+      if (!issued) scores(g + 1);
+    }
+  } else if (warp < 10) {
+    // ------------------------------------------------------------------ softmax warps: S^T, dP^T -> P^T, dS^T staging tiles
+    const int wq = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int r = wq * 32 + lane;
+    const int tid = threadIdx.x - 64;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(wq * 32) << 16);
+    const float c1 = 0.125f * LOG2E;
+    // per-query L and delta of an item go global -> shared with cp.async: no register holds them across the exp pass (under the
+    // 128-register cap the compiler spilled such a register right behind the load, stalling the warp for an HBM round trip)
+    auto fetch_ld = [&](int item, int buf) {
+      const int n = item / heads, h = item - n * heads;
+      const size_t qrow = (size_t)n * F_T + tid;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(sL + buf + tid)), "l"(lse + qrow * heads + h) : "memory");
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(sDl + buf + tid)), "l"(delta + qrow * heads + h) : "memory");
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto land_ld = [&](int buf) {  // own element arrived: natural log -> log2 domain, then the 256-thread barrier publishes it
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      sL[buf + tid] *= LOG2E;
+    };
+    if (G > 0) fetch_ld(blockIdx.x, 0);
+    for (int g = 0; g < G; ++g) {
+      const int i = g & 3, qb = qb_of(g), it = g >> 2;
+      const int item = blockIdx.x + it * gridDim.x;
+      const int buf = (it & 1) * F_T;
+      if (i == 0) {
+        land_ld(buf);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
+      if (i == 2 && it + 1 < my_items) fetch_ld(item + gridDim.x, buf ^ F_T);
+      if (warp == 2) FSTAMP(1, g, 0);
+      mbar_wait(s_full, g & 1);
+      if (warp == 2) FSTAMP(1, g, 1);
+      tc_fence_after();
+      const float* Lq = sL + buf + qb * RT + half * 64;
+      const float* Dq = sDl + buf + qb * RT + half * 64;
+      // 32 queries at a time, straight into the staging tiles (96 live registers under the 128 cap; holding the whole 64-query
+      // row needed 16-column TMEM loads and four wait round trips: 2.0 k instead of 1.3 k cycles per pass)
+#pragma unroll
+      for (int c2 = 0; c2 < 2; ++c2) {
+        uint32_t sv[32], dp[32], pp[16], pd[16];
+        tmem_ld32(t_lane + C_S + half * 64 + c2 * 32, sv);
+        tmem_ld32(t_lane + C_DP + half * 64 + c2 * 32, dp);
+        tmem_ld_wait();
+        if (c2 == 1) {  // last TMEM read of this iteration: S / dP may be overwritten
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(s_empty);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int c = c2 * 32 + 4 * j;
+          const float4 l4 = *reinterpret_cast<const float4*>(Lq + c), d4 = *reinterpret_cast<const float4*>(Dq + c);
+          const float p0 = ex2(fmaf(__uint_as_float(sv[4 * j]), c1, -l4.x));
+          const float p1 = ex2(fmaf(__uint_as_float(sv[4 * j + 1]), c1, -l4.y));
+          const float p2 = ex2(fmaf(__uint_as_float(sv[4 * j + 2]), c1, -l4.z));
+          const float p3 = ex2(fmaf(__uint_as_float(sv[4 * j + 3]), c1, -l4.w));
+          pp[2 * j] = pack_bf16(p0, p1);
+          pp[2 * j + 1] = pack_bf16(p2, p3);
+          pd[2 * j] = pack_bf16(p0 * (__uint_as_float(dp[4 * j]) - d4.x), p1 * (__uint_as_float(dp[4 * j + 1]) - d4.y));
+          pd[2 * j + 1] = pack_bf16(p2 * (__uint_as_float(dp[4 * j + 2]) - d4.z), p3 * (__uint_as_float(dp[4 * j + 3]) - d4.w));
+        }
+        if (c2 == 0) {
+          if (warp == 2) FSTAMP(1, g, 2);
+          if (g > 0) mbar_wait(&p_empty[half], (g - 1) & 1);  // the MMAs that read this panel of the staging tiles have retired
+        }
+        store_half_row_sw128(sPt + half * F_TILE, r, c2, pp);
+        store_half_row_sw128(sdSt + half * F_TILE, r, c2, pd);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[half]);
+      if (warp == 2) FSTAMP(1, g, 3);
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps 10-13: accumulator read-outs, q^ stashes
+    const int wq = warp & 3;
+    const int r = wq * 32 + lane;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(wq * 32) << 16);
+    auto signal_free = [&](uint64_t* bar) {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar);
+    };
+    auto slab_store = [&](uint8_t* stile, size_t grow0, int gcol) {  // rows of this warp written: 32-row slab -> dqkv by TMA
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) tma_store_2d(&tm_out, stile + wq * 32 * 128, gcol, (int)(grow0 + wq * 32));
+    };
+    auto release = [&](int t0, int t1) {  // the stores issued so far have read their smem: hand input tiles back
+      if (lane == 0) {
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        mbar_arrive(&empty[t0]);
+        if (t1 >= 0) mbar_arrive(&empty[t1]);
+      }
+      __syncwarp();
+    };
+    // dV: plain copy of a finished accumulator into (dead) tile `stile`
+    auto readout_plain = [&](uint32_t col, uint8_t* stile, float scale) {
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        uint32_t a[32], out[16];
+        tmem_ld32(t_lane + col + 32 * hf, a);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 16; ++c) out[c] = pack_bf16(__uint_as_float(a[2 * c]) * scale, __uint_as_float(a[2 * c + 1]) * scale);
+        store_half_row_sw128(stile, r, hf, out);
+      }
+    };
+    // dQ / dK: q/k-normalisation backward against the normalised row in `stile` (see store_out_row_qknorm), written over it.
+    // Two passes over the accumulator in 32-column halves (register cap 128); `done` is signalled after the last TMEM read.
+    auto readout_qk = [&](uint32_t col, uint8_t* stile, float s, uint64_t* done) {
+      float dot = 0.f;
+      if (sc) {
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          uint32_t a[32];
+          float y[32];
+          tmem_ld32(t_lane + col + 32 * hf, a);
+          load_half_row_sw128(stile, r, hf, y);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 32; ++c) dot = fmaf(y[c], __uint_as_float(a[c]), dot);
+        }
+      }
+      dot *= 0.125f;
+      const float rpe = 8.0f / s;
+      const float rr = fmaxf(rpe - eps, 1e-30f);
+      const float sco = sc ? -s * (dot * rpe / (64.0f * rr)) : 0.f;
+      const float ga = (sc ? s : 1.0f) * 0.125f;
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        uint32_t a[32], out[16];
+        float y[32];
+        tmem_ld32(t_lane + col + 32 * hf, a);
+        load_half_row_sw128(stile, r, hf, y);
+        tmem_ld_wait();
+        if (hf == 1 && done) signal_free(done);
+#pragma unroll
+        for (int c = 0; c < 16; ++c)
+          out[c] = pack_bf16(fmaf(ga, __uint_as_float(a[2 * c]), sco * y[2 * c]), fmaf(ga, __uint_as_float(a[2 * c + 1]), sco * y[2 * c + 1]));
+        store_half_row_sw128(stile, r, hf, out);
+      }
+    };
+    auto stash_q = [&](int qb) {  // this thread's q^ row of query block qb -> the dQ staging tile; then the Q tile may be refilled
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      __syncwarp();
+      const uint32_t off = (r >> 3) * 1024 + (r & 7) * 128;
+      const uint4* src = reinterpret_cast<const uint4*>(sTile + (TQ0 + qb) * F_TILE + off);
+      uint4* dst = reinterpret_cast<uint4*>(sTile + TOUT * F_TILE + off);
+      uint4 v[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) v[c] = src[c ^ (r & 7)];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) dst[c ^ (r & 7)] = v[c];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[TQ0 + qb]);
+    };
+    for (int it = 0; it < my_items; ++it) {
+      const int item = blockIdx.x + it * gridDim.x;
+      const int n = item / heads, h = item - n * heads;
+      const uint32_t ph = it & 1;
+      const int qf = it & 1, qs = qf ^ 1;  // first / second query block of this item
+      const size_t row0 = (size_t)n * F_T;
+      float s_q = 1.f, s_k = 1.f;
+      // ---- second query block resident from iteration 1 on: stash its q^ rows (dQ staging tile is free: its last store was read)
+      mbar_wait(&full[TQ0 + qs], ph);
+      stash_q(qs);
+      // ---- key tile 0 complete after iteration 1
+      if (sc) s_k = sc[(row0 + r) * 2 * heads + heads + h];
+      mbar_wait(kv0_ready, ph);
+      tc_fence_after();
+      readout_plain(C_DV, sTile + TV0 * F_TILE, 1.0f);
+      readout_qk(C_DK, sTile + TK0 * F_TILE, s_k, acc_free);
+      slab_store(sTile + TV0 * F_TILE, row0, 2 * D + h * HD);
+      slab_store(sTile + TK0 * F_TILE, row0, D + h * HD);
+      release(TK0, TV0);  // the next item needs these two first: hand them back before anything else
+      if (warp == 10) FSTAMP(2, 4 * it, 0);
+      // ---- dQ of the second block complete after iteration 2
+      if (sc) s_q = sc[(row0 + qs * RT + r) * 2 * heads + h];
+      mbar_wait(dqs_ready, ph);
+      tc_fence_after();
+      readout_qk(C_DQ + qs * HD, sTile + TOUT * F_TILE, s_q, dqs_free);
+      slab_store(sTile + TOUT * F_TILE, row0 + qs * RT, h * HD);
+      if (warp == 10) FSTAMP(2, 4 * it, 1);
+      // ---- first query block: stash (its tile is still resident: this warp's arrival is part of its release)
+      stash_q(qf);
+      // ---- key tile 1 and the first block's dQ complete after iteration 3
+      if (sc) {
+        s_k = sc[(row0 + RT + r) * 2 * heads + heads + h];
+        s_q = sc[(row0 + qf * RT + r) * 2 * heads + h];
+      }
+      mbar_wait(fin_ready, ph);
+      tc_fence_after();
+      readout_plain(C_DV, sTile + TV1 * F_TILE, 1.0f);
+      readout_qk(C_DK, sTile + TK1 * F_TILE, s_k, acc_free);
+      slab_store(sTile + TV1 * F_TILE, row0 + RT, 2 * D + h * HD);
+      slab_store(sTile + TK1 * F_TILE, row0 + RT, D + h * HD);
+      readout_qk(C_DQ + qf * HD, sTile + TOUT * F_TILE, s_q, dqf_free);
+      slab_store(sTile + TOUT * F_TILE, row0 + qf * RT, h * HD);
+      release(TK1, TV1);
+      if (warp == 10) FSTAMP(2, 4 * it, 2);
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete before the CTA exits
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
 __global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ dout, float* __restrict__ delta,
                                                          long long m_heads, int heads) {
   // delta[row, head] = dO_row,head . O_row,head over 64 channels (128 contiguous bytes of each tensor).  Eight lanes share one
@@ -1053,6 +1493,20 @@ static int attn_bwd_impl(const void* qkv, const void* o, const void* dout, const
     if (encode2d(&t_out, dqkv, 3 * D, rows, 3 * D, 32) != 0) {
       mapdit_set_error("cos_attn_bwd(fused): cuTensorMapEncodeTiled failed");
       return MAPDIT_ERR_CUDA;
+    }
+    if (g_mapdit_attn_bwd_fused >= 2) {
+      static bool f2attr = false;
+      if (!f2attr) {
+        if (cudaFuncSetAttribute(attn_bwd_fused2_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM) != cudaSuccess) {
+          mapdit_set_error("cos_attn_bwd(fused2): cudaFuncSetAttribute failed");
+          return MAPDIT_ERR_CUDA;
+        }
+        f2attr = true;
+      }
+      attn_bwd_fused2_tc<<<items < sms ? items : sms, F2_NTHREADS, F_SMEM, s>>>(t_qkv_row, t_do_row, t_out, lse, delta, heads, items, sc, eps,
+                                                                              g_attn_dbg);
+      MAPDIT_LAUNCH_CHECK("cos_attn_bwd(fused2)");
+      return MAPDIT_OK;
     }
     attn_bwd_fused_tc<<<items < sms ? items : sms, F_NTHREADS, F_SMEM, s>>>(t_qkv_row, t_do_row, t_out, lse, delta, heads, items,
                                                                            (const bf16*)qkv, sc, eps, g_attn_dbg);

@@ -120,3 +120,61 @@ def test_rotmod_backward_kernels_match_autograd(N, T, D, with_scale, dtype):
         if with_scale:
             assert rel_l2(dscale.double(), sd_.grad) < tol
         assert abs(float(dgp.double().sum()) - float(gd_.grad)) < tol * max(1.0, float(dgp.double().abs().sum()))
+
+
+def test_rotation_full_size_properties_dit_b2_batch_256():
+    """The bench headline (BASELINE configs[2]: DiT-B/2 + rotation-and-scaling, batch 256, bf16) through size-independent
+    properties: reruns are bit-identical; rows 0..7 of the 256-batch equal the
+    same 8 samples run alone bit for bit (the fused EPI_RESID_ROT epilogue is row-local); the small batch matches the oracle's
+    restatement (SELF-REFERENTIAL)."""
+    import mapdit_b200 as M
+    name = "DiT-B/2"
+    cfg = O.config_for(name, modulation="rotation_scaling")
+    sd = O.init_state_dict(cfg, seed=2)  # non-degenerate: gains ~ U(0.1, 0.5), so the rotation is active
+    m = M.DIT_MODELS[name](in_channels=4, input_size=32, num_classes=1000, modulation="rotation_scaling")
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(256, 4, 32, 32, generator=g).cuda()
+    t = torch.randint(0, 1000, (256,), generator=g).cuda()
+    y = torch.randint(0, 1000, (256,), generator=g).cuda()
+    with torch.no_grad():
+        a = m(x, t, y).clone()
+        b = m(x, t, y).clone()
+        small = m(x[:8], t[:8], y[:8]).clone()
+        ref = O.dit_forward(sd, cfg, x[:2].cpu(), t[:2].cpu(), y[:2].cpu())
+    assert torch.equal(a, b)
+    assert torch.equal(a[:8], small)
+    e = rel_l2(small[:2].cpu(), ref)
+    print(f"DiT-B/2 rotation_scaling bf16: forward rel-L2 vs oracle {e:.2e}")
+    assert e < 3e-2
+
+
+@pytest.mark.parametrize("dtype,tol", [("fp32", 1e-5), ("bf16", 5e-2)])
+def test_rotation_sampling_loop_vs_oracle(dtype, tol):
+    """10-step respaced p_sample_loop (CUDA-graph step loop, fused rotation epilogues in bf16), free-running,
+    shared noise, against the oracle's restatement (SELF-REFERENTIAL)."""
+    import mapdit_b200 as M
+    from mapdit_b200.diffusion import gaussian_diffusion as gd
+    name = "DiT-S/4"
+    cfg = O.config_for(name, modulation="rotation_scaling")
+    sd = O.init_state_dict(cfg, seed=12)
+    m = M.DIT_MODELS[name](in_channels=4, input_size=32, num_classes=1000, compute_dtype=dtype, modulation="rotation_scaling")
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    g = torch.Generator().manual_seed(6)
+    z = torch.randn(4, 4, 32, 32, generator=g)
+    y = torch.randint(0, 1000, (4,), generator=g)
+    noises = [torch.randn(4, 4, 32, 32, generator=g) for _ in range(10)]
+    ref = O.p_sample_loop(O.make_tables("10"), lambda a, b: O.dit_forward(sd, cfg, a, b, y), z, noises, clip_denoised=True)
+    it = iter(noises)
+    real = gd._randn_like
+    gd._randn_like = lambda v: next(it).cuda()
+    try:
+        s = M.create_diffusion("10").p_sample_loop(m.forward, z.shape, z.cuda(), clip_denoised=True, model_kwargs=dict(y=y.cuda()),
+                                                   device="cuda")
+    finally:
+        gd._randn_like = real
+    e = rel_l2(s.cpu(), ref)
+    print(f"DiT-S/4 rotation_scaling {dtype}: 10-step sampling rel-L2 vs oracle {e:.2e}")
+    assert e < tol

@@ -42,6 +42,10 @@ for g in range(24):
     m, s, e = roles[0, g], roles[1, g], roles[2, g]
     print(f"{g:3d} | {rel(m[0]):7d} {rel(m[1]):7d} {rel(m[2]):7d} | {rel(s[0]):7d} {rel(s[1]):7d} {rel(s[2]):7d} {rel(s[3]):7d} | {rel(e[0]):7d} | top {rel(e[1]):7d} {rel(e[2]):7d}")
 prod = d[768:768 + 64].view(8, 8)
+er = roles[2]
+print("read-out warp 10 (fused2 only): per item kv0 done, dQ(second) done, item done:")
+for it in range(6):
+    print(f"  item {it}: " + " ".join(f"{rel(v):7d}" for v in er[4 * it][:3]))
 print("TMA producer: clock at which tile k of item it was seen free (order K0 V0 Q0 dO0 Q1 dO1 K1 V1)")
 for it in range(6):
     print(f"  item {it}: " + " ".join(f"{rel(v):7d}" for v in prod[it]))
