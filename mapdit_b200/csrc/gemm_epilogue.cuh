@@ -30,9 +30,9 @@ struct EpiParams {
   int variant;  // MAPDIT_VAR_* word of the launching thread
 };
 
-// TMA store descriptors of the (up to) three bf16 [M, N] outputs: out, out2, aux
+// TMA store descriptors of the (up to) three bf16 [M, N] outputs: out, out2, aux; load descriptor of the bf16 [M, N] residual
 struct alignas(64) EpiTmaps {
-  CUtensorMap out, out2, aux;
+  CUtensorMap out, out2, aux, resid;
 };
 
 // 16-byte streaming global load that does not allocate in L1
@@ -91,6 +91,40 @@ struct Stager {
   }
 };
 
+// Residual tiles by TMA (2-CTA kernel): the row-per-lane 16-byte loads of `resid` cost 32 line transactions per instruction in
+// the LSU -- 4096 LSU cycles per 128 x 256 tile, the size of a whole K = 768 main loop, which is why the fused out-proj GEMM
+// ran at half the speed of the same GEMM with a plain store.  Each epilogue warp instead has two private 32 x 32 bf16 buffers
+// (64-byte rows, SWIZZLE_64B like the output staging) filled by cp.async.bulk.tensor one chunk ahead; a lane then reads its
+// row with four conflict-free 16-byte shared-memory loads.
+constexpr int RSTG_BYTES_PER_WARP = 2 * 32 * 64;
+constexpr int RSTG_BYTES = 8 * RSTG_BYTES_PER_WARP;
+struct ResidLoader {
+  uint8_t* base;   // this warp's 4 KB
+  uint64_t* bars;  // this warp's two mbarriers (count 1)
+  const CUtensorMap* map;
+  uint32_t issued, consumed;
+  int lane, row0;
+
+  __device__ __forceinline__ void issue(int col) {
+    const uint32_t b = issued & 1;
+    __syncwarp();  // every lane has finished reading what this buffer held two chunks ago
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&bars[b], 32 * 64);
+      tma_load_2d(base + b * 2048, map, &bars[b], col, row0);
+    }
+    ++issued;
+  }
+  __device__ __forceinline__ void consume(uint4 (&pre)[4]) {
+    const uint32_t b = consumed & 1;
+    mbar_wait(&bars[b], (consumed >> 1) & 1);
+    const uint8_t* row = base + b * 2048 + lane * 64;
+    const int sw = (lane >> 1) & 3;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) pre[c] = *reinterpret_cast<const uint4*>(row + ((c ^ sw) << 4));
+    ++consumed;
+  }
+};
+
 __device__ __forceinline__ void store_row32_f32(void* base, long long off, const float (&f)[32], int nvalid) {
   float* p = reinterpret_cast<float*>(base) + off;
 #pragma unroll
@@ -115,7 +149,7 @@ __device__ __forceinline__ void load_row32_f32(const float* p, float (&f)[32], i
 // has been issued so the global-load latency overlaps the tail of the main loop.
 template <int BN, typename WaitFn>
 __device__ __forceinline__ void run_tile(const EpiParams& ep, const EpiTmaps& tm, Stager& st, uint32_t t_row, int row, int n_blk, int half,
-                                         float gsc, float inv_den, WaitFn wait_acc) {
+                                         float gsc, float inv_den, WaitFn wait_acc, ResidLoader* rl = nullptr) {
   const bool mod2 = ep.epilogue == MAPDIT_EPI_RESID_MOD || ep.epilogue == MAPDIT_EPI_RESID_ROT;  // writes h to out2
   const bool reads_resid = ep.epilogue == MAPDIT_EPI_RESID || mod2 || ep.epilogue == MAPDIT_EPI_SILU_BWD;
   const bool row_ok = row < ep.M;
@@ -123,6 +157,13 @@ __device__ __forceinline__ void run_tile(const EpiParams& ep, const EpiTmaps& tm
   uint4 pre[4];
   auto prefetch = [&](int c) {
     const int col = n_blk * BN + c;
+    if (rl) {  // TMA path: the chunk lands in this warp's staging buffer (columns / rows past the edge are zero-filled)
+      if (col < ep.N) {
+        rl->row0 = st.row0;
+        rl->issue(col);
+      }
+      return;
+    }
     const int nvalid = min(32, ep.N - col);
     const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(ep.resid) + (long long)row * ep.ldo + col);
 #pragma unroll
@@ -191,6 +232,11 @@ __device__ __forceinline__ void run_tile(const EpiParams& ep, const EpiTmaps& tm
     for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(r[j]);
     float xo[32];
     if (reads_resid) {
+      if (rl) {
+        // next chunk first (its buffer was consumed one chunk ago), then this chunk out of shared memory
+        if (c + 64 < BN) prefetch(c + 64);
+        if (col < ep.N) rl->consume(pre);
+      }
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&pre[g]);
@@ -201,7 +247,7 @@ __device__ __forceinline__ void run_tile(const EpiParams& ep, const EpiTmaps& tm
           xo[g * 8 + 2 * j + 1] = t2.y;
         }
       }
-      if (c + 64 < BN) prefetch(c + 64);  // next chunk's residual while this one is processed
+      if (!rl && c + 64 < BN) prefetch(c + 64);  // next chunk's residual while this one is processed
     }
     prefetch_vecs(c + 64);
     if (nvalid <= 0) continue;  // warp-uniform
@@ -262,9 +308,10 @@ inline int make_store_maps(EpiTmaps* tm, const EpiParams& ep) {
   const uint64_t dims[2] = {(uint64_t)ep.N, (uint64_t)ep.M};
   const uint64_t strides[1] = {(uint64_t)ep.ldo * 2};
   const uint32_t box[2] = {32, 32};
-  void* outs[3] = {ep.out, ep.out2 ? ep.out2 : ep.out, (ep.aux && ep.epilogue != MAPDIT_EPI_QKNORM) ? ep.aux : ep.out};
-  CUtensorMap* maps[3] = {&tm->out, &tm->out2, &tm->aux};
-  for (int i = 0; i < 3; ++i) {
+  void* outs[4] = {ep.out, ep.out2 ? ep.out2 : ep.out, (ep.aux && ep.epilogue != MAPDIT_EPI_QKNORM) ? ep.aux : ep.out,
+                   ep.resid ? const_cast<void*>(ep.resid) : ep.out};
+  CUtensorMap* maps[4] = {&tm->out, &tm->out2, &tm->aux, &tm->resid};
+  for (int i = 0; i < 4; ++i) {
     CUresult r = mapdit_encode_tmap(maps[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, outs[i], dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B);
     if (r != CUDA_SUCCESS) return (int)r;
   }

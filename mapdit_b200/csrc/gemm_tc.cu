@@ -229,6 +229,7 @@ CUresult mapdit_encode_tmap(CUtensorMap* map, CUtensorMapDataType dt, uint32_t r
 int mapdit_gemm_bf16_2cta(const mapdit_gemm_args* g, const gemm_epi::EpiParams& ep, cudaStream_t stream, int num_sms);
 extern int g_mapdit_attn_v2;
 extern int g_mapdit_attn_bwd_fused;
+int g_mapdit_gemm_2cta_bn = 0;
 static int g_use_2cta = 1;  // CTA-pair kernel by default where the shape qualifies (A/B: bench.py --gemm-2cta 0)
 
 // runtime switches (benchmark A/B): "gemm_2cta" = 0/1
@@ -239,6 +240,10 @@ extern "C" int mapdit_set_option(const char* name, int value) {
   }
   if (name && !strcmp(name, "attn_v2")) {
     g_mapdit_attn_v2 = value;
+    return MAPDIT_OK;
+  }
+  if (name && !strcmp(name, "gemm_2cta_bn")) {
+    g_mapdit_gemm_2cta_bn = value;
     return MAPDIT_OK;
   }
   if (name && !strcmp(name, "attn_bwd_fused")) {

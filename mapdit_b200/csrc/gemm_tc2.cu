@@ -20,10 +20,10 @@ struct Cfg2 {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int BH_BYTES = (BN / 2) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + BH_BYTES;
-  static constexpr int MAX_STAGES = (227 * 1024 - 2048 - STG_BYTES) / STAGE_BYTES;
+  static constexpr int MAX_STAGES = (227 * 1024 - 2048 - STG_BYTES - RSTG_BYTES) / STAGE_BYTES;  // 5 for BN = 256 (6 measured no faster)
   static constexpr int STAGES = MAX_STAGES > 8 ? 8 : MAX_STAGES;
   static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + 1024 + 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + RSTG_BYTES + 1024 + 512;
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -79,11 +79,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   uint8_t* staging = smem + C::STAGES * C::STAGE_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(staging + STG_BYTES);
+  uint8_t* rstaging = staging + STG_BYTES;  // residual tiles (ResidLoader), 4 KB per epilogue warp
+  uint64_t* full = reinterpret_cast<uint64_t*>(rstaging + RSTG_BYTES);
   uint64_t* empty = full + C::STAGES;
   uint64_t* tfull = empty + C::STAGES;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* rbar = tempty + 2;  // [8 warps][2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rbar + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -93,6 +95,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tma_a);
     prefetch_tmap(&tma_b);
+    prefetch_tmap(&etm.resid);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
@@ -103,6 +106,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
       mbar_init(&tfull[a], 1);
       mbar_init(&tempty[a], 16);  // 8 epilogue warps of each CTA of the pair
     }
+    for (int i = 0; i < 16; ++i) mbar_init(&rbar[i], 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc_2cta<C::TMEM_COLS>(tmem_slot);
@@ -169,6 +173,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
       inv_den = 1.0f / mod_den(gsc);
     }
     Stager st{staging + (warp - 4) * STG_BYTES_PER_WARP, 0u, lane, 0};
+    ResidLoader rl{rstaging + (warp - 4) * RSTG_BYTES_PER_WARP, rbar + 2 * (warp - 4), &etm.resid, 0u, 0u, lane, 0};
     for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
       const int m_pair = tile / num_n_blocks, n_blk = tile - m_pair * num_n_blocks;
       const int row = (2 * m_pair + (int)rank) * BM + q * 32 + lane;
@@ -177,7 +182,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
       run_tile<BN>(ep, etm, st, t_row, row, n_blk, half, gsc, inv_den, [&]() {
         mbar_wait(&tfull[acc], acc_phase);
         tc_fence_after();
-      });
+      }, &rl);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&tempty[acc]);
@@ -235,6 +240,8 @@ int mapdit_gemm_bf16_2cta(const mapdit_gemm_args* g, const gemm_epi::EpiParams& 
   // (N = 1152, 3456: DiT-S qkv, DiT-XL): half the B-operand traffic per FLOP of the 128-wide kernel
   const int nb256 = (g->n + 255) / 256;
   const bool wide_ok = g->n % 256 == 0 || (g->n % 128 == 0 && (long long)nb256 * 256 * 8 <= (long long)g->n * 9);
+  extern int g_mapdit_gemm_2cta_bn;  // developer switch (mapdit_set_option "gemm_2cta_bn"): 0 = auto, 128 / 256 = force that tile width
+  if (g_mapdit_gemm_2cta_bn == 128 && g->n % 128 == 0) return launch2<128>(g, ep, stream, num_sms);
   if (wide_ok && (long long)((mb + 1) / 2) * nb256 >= num_sms / 2) return launch2<256>(g, ep, stream, num_sms);
   if (g->n % 128 == 0 && (long long)((mb + 1) / 2) * (g->n / 128) >= num_sms) return launch2<128>(g, ep, stream, num_sms);
   return MAPDIT_ERR_UNSUPPORTED;
