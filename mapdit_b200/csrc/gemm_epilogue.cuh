@@ -132,7 +132,23 @@ __device__ __forceinline__ void store_row32_f32(void* base, long long off, const
     if (g * 4 < nvalid) *reinterpret_cast<float4*>(p + g * 4) = make_float4(f[g * 4], f[g * 4 + 1], f[g * 4 + 2], f[g * 4 + 3]);
 }
 
+// nvalid must be warp-uniform.  The full-chunk case takes eight unpredicated 16-byte loads: with a per-load predicate the
+// compiler re-materialises the global-memory descriptor (two R2UR) in front of every LDG, which serialised the loads and left
+// their latency fully exposed three times per chunk (ncu: the FFMA/FMUL behind these loads were the top stall of the epilogue).
 __device__ __forceinline__ void load_row32_f32(const float* p, float (&f)[32], int nvalid) {
+  if (nvalid >= 32) {
+    float4 u[8];
+#pragma unroll
+    for (int g = 0; g < 8; ++g) u[g] = reinterpret_cast<const float4*>(p)[g];
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      f[g * 4] = u[g].x;
+      f[g * 4 + 1] = u[g].y;
+      f[g * 4 + 2] = u[g].z;
+      f[g * 4 + 3] = u[g].w;
+    }
+    return;
+  }
 #pragma unroll
   for (int g = 0; g < 8; ++g) {
     float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -182,8 +198,12 @@ __device__ __forceinline__ void run_tile(const EpiParams& ep, const EpiTmaps& tm
     if (lane > 0 && (!mod2 || base == nullptr)) return;
     asm volatile("prefetch.global.L1 [%0];" ::"l"(base + sample * (lane == 1 ? ep.ldshift : ep.ldmod) + col));
   };
-  prefetch_vecs(half * 32);
-  if (reads_resid && half * 32 < BN) prefetch(half * 32);
+  // each of the two warps of a lane quarter owns one contiguous half of the tile's columns: consecutive chunks (and their
+  // TMA stores / residual loads) then touch the two halves of the same 128-byte lines back to back
+  constexpr int CSPAN = BN >= 64 ? BN / 2 : BN;  // BN = 32: only `half` 0 has a chunk
+  const int c_begin = half * CSPAN, c_end = BN >= 64 ? c_begin + CSPAN : (half == 0 ? BN : 0);
+  prefetch_vecs(c_begin);
+  if (reads_resid && c_begin < c_end) prefetch(c_begin);
   const float silu_mul = (ep.variant & MAPDIT_VAR_PLAIN_SILU) ? 1.0f : 1.0f / MP_SILU_DIV;
   const bool plain_res = ep.variant & MAPDIT_VAR_PLAIN_RESID;
   wait_acc();
@@ -221,7 +241,7 @@ __device__ __forceinline__ void run_tile(const EpiParams& ep, const EpiTmaps& tm
     }
     return;
   }
-  for (int c = half * 32; c < BN; c += 64) {
+  for (int c = c_begin; c < c_end; c += 32) {
     uint32_t r[32];
     tmem_ld32(t_row + c, r);
     tmem_ld_wait();
@@ -234,7 +254,7 @@ __device__ __forceinline__ void run_tile(const EpiParams& ep, const EpiTmaps& tm
     if (reads_resid) {
       if (rl) {
         // next chunk first (its buffer was consumed one chunk ago), then this chunk out of shared memory
-        if (c + 64 < BN) prefetch(c + 64);
+        if (c + 32 < c_end) prefetch(c + 32);
         if (col < ep.N) rl->consume(pre);
       }
 #pragma unroll
@@ -247,9 +267,9 @@ __device__ __forceinline__ void run_tile(const EpiParams& ep, const EpiTmaps& tm
           xo[g * 8 + 2 * j + 1] = t2.y;
         }
       }
-      if (!rl && c + 64 < BN) prefetch(c + 64);  // next chunk's residual while this one is processed
+      if (!rl && c + 32 < c_end) prefetch(c + 32);  // next chunk's residual while this one is processed
     }
-    prefetch_vecs(c + 64);
+    if (c + 32 < c_end) prefetch_vecs(c + 32);
     if (nvalid <= 0) continue;  // warp-uniform
     if (ep.epilogue == MAPDIT_EPI_STORE) {
       if (ep.out_f32) {
@@ -272,20 +292,20 @@ __device__ __forceinline__ void run_tile(const EpiParams& ep, const EpiTmaps& tm
     } else {  // RESID / RESID_MOD / RESID_ROT
       float gt[32];
       if (ep.aux) st.store(&tm.aux, f, col);  // raw branch output, needed for d(gate)
-      load_row32_f32(ep.gate + sample * ep.ldmod + col, gt, row_ok ? nvalid : 0);
+      load_row32_f32(ep.gate + sample * ep.ldmod + col, gt, nvalid);
 #pragma unroll
       for (int j = 0; j < 32; ++j)
         f[j] = plain_res ? fmaf(gt[j], f[j], xo[j]) : fmaf(MP_RES_T, gt[j] * f[j] - xo[j], xo[j]) * (1.0f / MP_RES_DEN);
       st.store(&tm.out, f, col);
       if (ep.epilogue == MAPDIT_EPI_RESID_MOD) {
-        load_row32_f32(ep.shift + sample * ep.ldmod + col, xo, row_ok ? nvalid : 0);
-        load_row32_f32(ep.scale + sample * ep.ldmod + col, gt, row_ok ? nvalid : 0);
+        load_row32_f32(ep.shift + sample * ep.ldmod + col, xo, nvalid);
+        load_row32_f32(ep.scale + sample * ep.ldmod + col, gt, nvalid);
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = lerp_t(f[j] * gt[j], xo[j], gsc) * inv_den;
         st.store(&tm.out2, f, col);
       } else if (ep.epilogue == MAPDIT_EPI_RESID_ROT) {
         // rotation modulation (UNPINNED): channel pair (2i, 2i+1) of x' rotated by theta_i; xo = 16 (cos, sin) pairs
-        load_row32_f32(ep.shift + sample * ep.ldshift + col, xo, row_ok ? nvalid : 0);
+        load_row32_f32(ep.shift + sample * ep.ldshift + col, xo, nvalid);
 #pragma unroll
         for (int p = 0; p < 16; ++p) {
           const float a = f[2 * p], b = f[2 * p + 1];
@@ -293,7 +313,7 @@ __device__ __forceinline__ void run_tile(const EpiParams& ep, const EpiTmaps& tm
           f[2 * p + 1] = fmaf(a, xo[2 * p + 1], b * xo[2 * p]);
         }
         if (ep.scale) {
-          load_row32_f32(ep.scale + sample * ep.ldmod + col, gt, row_ok ? nvalid : 0);
+          load_row32_f32(ep.scale + sample * ep.ldmod + col, gt, nvalid);
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] *= gt[j];
         }
