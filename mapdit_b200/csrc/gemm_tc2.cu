@@ -7,6 +7,8 @@
 // epilogue warps release the accumulator stage on the leader's barrier.
 #include "gemm_epilogue.cuh"
 
+extern long long* g_attn_dbg;  // developer timeline hook (mapdit_attn_debug_buffer)
+
 namespace {
 using namespace tc;
 using namespace gemm_epi;
@@ -73,7 +75,7 @@ template <int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                 const __grid_constant__ EpiTmaps etm, const EpiParams ep,
-                int num_m_blocks, int num_n_blocks, int num_k_blocks) {
+                int num_m_blocks, int num_n_blocks, int num_k_blocks, long long* __restrict__ dbg) {
   using C = Cfg2<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -143,6 +145,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
     for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
       mbar_wait(&tempty[acc], acc_phase ^ 1);
       tc_fence_after();
+      const int tcount = (tile - cluster_id) / num_clusters;
+      if (dbg && blockIdx.x == 0 && lane == 0 && tcount < 16) dbg[512 + tcount * 4 + 0] = clock64();
       const uint32_t d_tmem = tmem_base + acc * BN;
       for (int kb = 0; kb < num_k_blocks; ++kb) {
         mbar_wait(&full[stage], phase);
@@ -160,6 +164,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
         }
       }
       if (leader) umma_commit_2cta(&tfull[acc]);
+      if (dbg && blockIdx.x == 0 && lane == 0 && tcount < 16) dbg[512 + tcount * 4 + 1] = clock64();
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -179,12 +184,16 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
       const int row = (2 * m_pair + (int)rank) * BM + q * 32 + lane;
       st.row0 = (2 * m_pair + (int)rank) * BM + q * 32;
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+      const int tcount = (tile - cluster_id) / num_clusters;
+      if (dbg && blockIdx.x == 0 && lane == 0 && tcount < 16) dbg[(warp - 4) * 64 + tcount * 4 + 0] = clock64();
       run_tile<BN>(ep, etm, st, t_row, row, n_blk, half, gsc, inv_den, [&]() {
         mbar_wait(&tfull[acc], acc_phase);
         tc_fence_after();
+        if (dbg && blockIdx.x == 0 && lane == 0 && tcount < 16) dbg[(warp - 4) * 64 + tcount * 4 + 1] = clock64();
       }, &rl);
       tc_fence_before();
       __syncwarp();
+      if (dbg && blockIdx.x == 0 && lane == 0 && tcount < 16) dbg[(warp - 4) * 64 + tcount * 4 + 2] = clock64();
       if (lane == 0) mbar_arrive_leader(&tempty[acc]);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
@@ -228,7 +237,7 @@ int launch2(const mapdit_gemm_args* g, const EpiParams& ep, cudaStream_t stream,
     mapdit_set_error("gemm_bf16(2cta): cuTensorMapEncodeTiled (store maps) failed");
     return MAPDIT_ERR_CUDA;
   }
-  gemm_tc2_kernel<BN><<<2 * clusters, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, etm, ep, mb, nb, kb);
+  gemm_tc2_kernel<BN><<<2 * clusters, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, etm, ep, mb, nb, kb, g_attn_dbg);
   return MAPDIT_OK;
 }
 }  // namespace
