@@ -206,6 +206,8 @@ __device__ __forceinline__ void run_tile(const EpiParams& ep, const EpiTmaps& tm
   if (reads_resid && c_begin < c_end) prefetch(c_begin);
   const float silu_mul = (ep.variant & MAPDIT_VAR_PLAIN_SILU) ? 1.0f : 1.0f / MP_SILU_DIV;
   const bool plain_res = ep.variant & MAPDIT_VAR_PLAIN_RESID;
+  const float res_a = plain_res ? 1.0f : (1.0f - MP_RES_T) / MP_RES_DEN, res_b = plain_res ? 1.0f : MP_RES_T / MP_RES_DEN;
+  const float mod_a = (1.0f - gsc) * inv_den, mod_b = gsc * inv_den;
   wait_acc();
 
   if (ep.epilogue == MAPDIT_EPI_QKNORM) {
@@ -293,15 +295,19 @@ __device__ __forceinline__ void run_tile(const EpiParams& ep, const EpiTmaps& tm
       float gt[32];
       if (ep.aux) st.store(&tm.aux, f, col);  // raw branch output, needed for d(gate)
       load_row32_f32(ep.gate + sample * ep.ldmod + col, gt, nvalid);
+      // x' = (0.7 x + 0.3 gate acc)/den as  (b gate) acc + a x  with the constants folded into warp-uniform scalars: two
+      // instructions per element.  (The literal form, with its `plain_res` select and lerp's two-sided formula, compiled to ~13
+      // mostly predicated instructions per element: the fused epilogue issued 28 k warp instructions per 128 x 256 tile, more
+      // issue cycles than the K = 768 main loop has.)
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        f[j] = plain_res ? fmaf(gt[j], f[j], xo[j]) : fmaf(MP_RES_T, gt[j] * f[j] - xo[j], xo[j]) * (1.0f / MP_RES_DEN);
+      for (int j = 0; j < 32; ++j) f[j] = fmaf(gt[j] * res_b, f[j], res_a * xo[j]);
       st.store(&tm.out, f, col);
       if (ep.epilogue == MAPDIT_EPI_RESID_MOD) {
+        // h = lerp(x' scale, shift, g)/den(g) = x' (scale (1-g)/den) + shift g/den
         load_row32_f32(ep.shift + sample * ep.ldmod + col, xo, nvalid);
         load_row32_f32(ep.scale + sample * ep.ldmod + col, gt, nvalid);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = lerp_t(f[j] * gt[j], xo[j], gsc) * inv_den;
+        for (int j = 0; j < 32; ++j) f[j] = fmaf(f[j], gt[j] * mod_a, xo[j] * mod_b);
         st.store(&tm.out2, f, col);
       } else if (ep.epilogue == MAPDIT_EPI_RESID_ROT) {
         // rotation modulation (UNPINNED): channel pair (2i, 2i+1) of x' rotated by theta_i; xo = 16 (cos, sin) pairs
