@@ -21,7 +21,6 @@ import mapdit_b200 as M  # noqa: E402
 from mapdit_b200.diffusion import gaussian_diffusion as gd  # noqa: E402
 from mapdit_b200.parallel import gather_samples, shard_range  # noqa: E402
 from mapdit_b200.train import TrainStep  # noqa: E402
-from oracle import mapdit_oracle as O  # noqa: E402  (deterministic weight init only)
 
 
 def rel(a, b):
@@ -35,8 +34,17 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     name = os.environ.get("DP_MODEL", "DiT-S/2")
     per = int(os.environ.get("DP_BATCH", "16"))
-    cfg = O.config_for(name)
-    sd = O.init_state_dict(cfg, seed=0)
+    # the same replica on every rank: the model's own (reference-distribution) init under a fixed torch seed, with the gains and
+    # the sigma-scale reference moved off their zero init so every code path carries signal
+    torch.manual_seed(0)
+    m0 = M.DIT_MODELS[name](in_channels=4, input_size=32, num_classes=1000)
+    with torch.no_grad():
+        for prm in m0.parameters():
+            if prm.dim() == 0:
+                prm.fill_(0.3)
+        m0.final_layer.sigma_scale.reference.normal_()
+    sd = {k: v.clone() for k, v in m0.state_dict().items()}
+    del m0
     G = per * world
     g = torch.Generator().manual_seed(5)
     x = torch.randn(G, 4, 32, 32, generator=g)
