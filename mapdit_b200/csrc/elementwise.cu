@@ -511,31 +511,112 @@ extern "C" int mapdit_qk_normalize(void* qkv, int m, int d, int head_dim, float 
 // patch embed: x0 = mp_sum(patchify(x)|1 · Wx_eff^T, pos, 0.5)  (+ optional modulate for block 0)
 // CTA = 16 tokens x 256 output channels; patches staged in smem.
 // ------------------------------------------------------------------------------------------------
-template <typename T>
+__device__ __forceinline__ float round_act(float v, float*) { return v; }
+__device__ __forceinline__ float round_act(float v, bf16*) { return __bfloat162float(__float2bfloat16_rn(v)); }
+__device__ __forceinline__ void st_act4(float* p, const float (&v)[4]) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+__device__ __forceinline__ void st_act4(bf16* p, const float (&v)[4]) {
+  uint2 u;
+  *reinterpret_cast<__nv_bfloat162*>(&u.x) = __floats2bfloat162_rn(v[0], v[1]);
+  *reinterpret_cast<__nv_bfloat162*>(&u.y) = __floats2bfloat162_rn(v[2], v[3]);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+
+// Thread = 4 tokens x 4 consecutive channels (64 channel groups x 4 token groups per CTA): a warp stores 256 contiguous bytes per
+// instruction (the former thread-per-channel layout stored 2 bytes per thread and re-read x0 to see its rounding: 0.21 ms per
+// forward for 200 MB of output).  d % 4 == 0 is required for the vector path (all registry models); otherwise VEC = false.
+constexpr int PE_GROUPS = 8;  // token groups (of 16) per CTA on the vector path
+
+template <typename T, bool VEC>
 __global__ void __launch_bounds__(256) patch_embed_kernel(const float* __restrict__ x, const float* __restrict__ wx,
                                                           const float* __restrict__ pos, T* __restrict__ x0, T* __restrict__ h,
                                                           const float* __restrict__ shift, const float* __restrict__ scale,
                                                           const float* __restrict__ gain, int64_t ldmod, int64_t m_total, int C,
                                                           int S, int p, int d, int var) {
-  extern __shared__ float sp[];  // [16][K1]
+  extern __shared__ float sp[];  // [16][K1] patches of one token group, then (VEC) [K1][256] weights of this CTA's channel slab
   const int g = S / p, T_ = g * g, K = p * p * C, K1 = K + 1;
-  const int64_t tok0 = (int64_t)blockIdx.x * 16;
-  for (int i = threadIdx.x; i < 16 * K1; i += blockDim.x) {
-    int tl = i / K1, f = i - tl * K1;
-    int64_t tok = tok0 + tl;
-    float v = 0.f;
-    if (tok < m_total) {
-      if (f == K) v = 1.0f;  // bias column (src/dit.py:82)
-      else {
-        int64_t n = tok / T_;
-        int tt = (int)(tok - n * T_);
-        int hh = tt / g, ww = tt - hh * g;
-        int c = f % C, pp = f / C, p1 = pp / p, p2 = pp - p1 * p;
-        v = x[((n * C + c) * S + (hh * p + p1)) * (int64_t)S + (ww * p + p2)];
+  float gn = 0.f, den = 1.f;
+  if (h) { gn = *gain; den = mod_den(gn); }
+  // patches of 16 consecutive tokens -> sp.  All index arithmetic in 32 bits (a 64-bit division costs ~100 instructions and the
+  // first version did one per element and per output token: more instructions than the FMAs)
+  auto gather = [&](int64_t tok0) {
+    for (int i = threadIdx.x; i < 16 * K1; i += blockDim.x) {
+      const int tl = i / K1, f = i - tl * K1;
+      const int64_t tok = tok0 + tl;
+      float v = 0.f;
+      if (tok < m_total) {
+        if (f == K) v = 1.0f;  // bias column (src/dit.py:82)
+        else {
+          const unsigned tk = (unsigned)tok;
+          const unsigned n = tk / (unsigned)T_, tt = tk - n * (unsigned)T_;
+          const unsigned hh = tt / (unsigned)g, ww = tt - hh * (unsigned)g;
+          const unsigned pp = (unsigned)f / (unsigned)C, c = (unsigned)f - pp * (unsigned)C, p1 = pp / (unsigned)p, p2 = pp - p1 * (unsigned)p;
+          v = x[(((size_t)n * C + c) * S + (hh * p + p1)) * (size_t)S + (ww * p + p2)];
+        }
+      }
+      sp[i] = v;
+    }
+  };
+  if (VEC) {
+    // CTA = PE_GROUPS x 16 tokens x 256 channels; the slab's weights are staged once as [k][channel] (one 16-byte shared-memory
+    // load per k per thread; per-thread strided global weight loads left the kernel latency bound at 0.21 ms per forward)
+    float* sw = sp + 16 * K1;
+    const int c0 = blockIdx.y * 256;
+    for (int i = threadIdx.x; i < 256 * K1; i += blockDim.x) {
+      const int cl = i / K1, k = i - cl * K1;
+      sw[k * 256 + cl] = (c0 + cl < d) ? wx[(size_t)(c0 + cl) * K1 + k] : 0.f;
+    }
+    const int cl = (threadIdx.x & 63) * 4, col = c0 + cl;
+    const int j0 = (threadIdx.x >> 6) * 4;  // first of this thread's 4 tokens of a group
+    for (int grp = 0; grp < PE_GROUPS; ++grp) {
+      const int64_t tok0 = ((int64_t)blockIdx.x * PE_GROUPS + grp) * 16;
+      if (tok0 >= m_total) break;
+      __syncthreads();  // previous group's patches consumed (and, first trip, nothing)
+      gather(tok0);
+      __syncthreads();
+      if (col >= d) continue;
+      float acc[4][4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[j][c] = 0.f;
+      for (int k = 0; k < K1; ++k) {  // same k order per output as the scalar path
+        const float4 w4 = *reinterpret_cast<const float4*>(sw + k * 256 + cl);
+        const float w[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float a = sp[(j0 + j) * K1 + k];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) acc[j][c] = __fmaf_rn(a, w[c], acc[j][c]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int64_t tok = tok0 + j0 + j;
+        if (tok >= m_total) break;
+        const unsigned n = (unsigned)tok / (unsigned)T_;
+        const unsigned tt = (unsigned)tok - n * (unsigned)T_;
+        const float4 pv = *reinterpret_cast<const float4*>(pos + (size_t)tt * d + col);
+        const float pvv[4] = {pv.x, pv.y, pv.z, pv.w};
+        float v[4], hv[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (var & MAPDIT_VAR_PLAIN_POS) v[c] = acc[j][c] + pvv[c];
+          else if (sizeof(T) == 2) v[c] = lerp_t(acc[j][c], pvv[c], 0.5f) * (1.0f / MP_HALF_DEN);  // bf16 output: rounding dominates
+          else v[c] = lerp_t(acc[j][c], pvv[c], 0.5f) / MP_HALF_DEN;
+        }
+        st_act4(x0 + tok * d + col, v);
+        if (h) {  // modulate sees the value as stored in the residual stream
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            hv[c] = modulate_f(round_act(v[c], (T*)nullptr), shift[n * ldmod + col + c], scale[n * ldmod + col + c], gn, den);
+          st_act4(h + tok * d + col, hv);
+        }
       }
     }
-    sp[i] = v;
+    return;
   }
+  const int64_t tok0 = (int64_t)blockIdx.x * 16;
+  gather(tok0);
   __syncthreads();
   const int col = blockIdx.y * 256 + threadIdx.x;
   if (col >= d) return;
@@ -548,8 +629,6 @@ __global__ void __launch_bounds__(256) patch_embed_kernel(const float* __restric
 #pragma unroll
     for (int j = 0; j < 16; ++j) acc[j] = __fmaf_rn(sp[j * K1 + k], w, acc[j]);
   }
-  float gn = 0.f, den = 1.f;
-  if (h) { gn = *gain; den = mod_den(gn); }
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
     int64_t tok = tok0 + j;
@@ -559,11 +638,7 @@ __global__ void __launch_bounds__(256) patch_embed_kernel(const float* __restric
     const float pv = pos[(size_t)tt * d + col];
     float v = (var & MAPDIT_VAR_PLAIN_POS) ? acc[j] + pv : lerp_t(acc[j], pv, 0.5f) / MP_HALF_DEN;
     st_act(x0 + tok * d + col, v);
-    if (h) {
-      // modulate sees the value as stored in the residual stream
-      float xs = ld_act(x0 + tok * d + col);
-      st_act(h + tok * d + col, modulate_f(xs, shift[n * ldmod + col], scale[n * ldmod + col], gn, den));
-    }
+    if (h) st_act(h + tok * d + col, modulate_f(round_act(v, (T*)nullptr), shift[n * ldmod + col], scale[n * ldmod + col], gn, den));
   }
 }
 
@@ -573,13 +648,22 @@ extern "C" int mapdit_patch_embed(const float* x, const float* wx_eff, const flo
   MAPDIT_REQUIRE(x && wx_eff && pos && x0 && n_samples > 0 && input_size % patch == 0, "patch_embed: bad args");
   int g = input_size / patch;
   int64_t m_total = (int64_t)n_samples * g * g;
+  MAPDIT_REQUIRE(m_total < (1LL << 31), "patch_embed: more than 2^31 tokens");
   int K1 = patch * patch * channels + 1;
-  size_t smem = (size_t)16 * K1 * sizeof(float);
-  dim3 grid((unsigned)((m_total + 15) / 16), (unsigned)((d + 255) / 256));
-  if (dtype == MAPDIT_F32)
-    patch_embed_kernel<float><<<grid, 256, smem, (cudaStream_t)stream>>>(x, wx_eff, pos, (float*)x0, (float*)h, shift, scale, gain, ldmod, m_total, channels, input_size, patch, d, mapdit_variant());
-  else
-    patch_embed_kernel<bf16><<<grid, 256, smem, (cudaStream_t)stream>>>(x, wx_eff, pos, (bf16*)x0, (bf16*)h, shift, scale, gain, ldmod, m_total, channels, input_size, patch, d, mapdit_variant());
+  const bool vec = d % 4 == 0 && ((uintptr_t)x0 & 15) == 0 && (!h || ((uintptr_t)h & 15) == 0) && ((uintptr_t)pos & 15) == 0 &&
+                   (size_t)(16 + 256) * K1 * sizeof(float) <= 48 * 1024;
+  size_t smem = (size_t)(16 + (vec ? 256 : 0)) * K1 * sizeof(float);
+  const int64_t groups = (m_total + 15) / 16;
+  dim3 grid((unsigned)(vec ? (groups + PE_GROUPS - 1) / PE_GROUPS : groups), (unsigned)((d + 255) / 256));
+  const int var = mapdit_variant();
+  cudaStream_t s = (cudaStream_t)stream;
+#define PE_LAUNCH(TT, V) patch_embed_kernel<TT, V><<<grid, 256, smem, s>>>(x, wx_eff, pos, (TT*)x0, (TT*)h, shift, scale, gain, ldmod, m_total, channels, input_size, patch, d, var)
+  if (dtype == MAPDIT_F32) {
+    if (vec) PE_LAUNCH(float, true); else PE_LAUNCH(float, false);
+  } else {
+    if (vec) PE_LAUNCH(bf16, true); else PE_LAUNCH(bf16, false);
+  }
+#undef PE_LAUNCH
   MAPDIT_LAUNCH_CHECK("patch_embed");
   return MAPDIT_OK;
 }
