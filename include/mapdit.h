@@ -116,10 +116,13 @@ typedef struct mapdit_gemm_args {
 
 int mapdit_gemm_bf16(const mapdit_gemm_args* args, void* stream);
 int mapdit_sizeof_gemm_args(void); /* lets a binding check its struct mirror */
-/* runtime switches: "gemm_2cta" (0/1) selects the cta_group::2 256xBN kernel for large-M GEMMs;
- * "attn_v2" (0/1) selects the one-CTA-per-SM ping-pong attention forward for tokens % 256 == 0 */
+/* runtime switches (A/B and developer use; defaults are the fast paths): "gemm_2cta" (0/1) selects the cta_group::2 256xBN kernel
+ * for large-M GEMMs; "gemm_2cta_bn" (0 = auto, 128 = force 128-wide pair tiles); "attn_v2" (0/1) selects the one-CTA-per-SM
+ * ping-pong attention forward for tokens % 256 == 0; "attn_bwd_fused" (tokens == 256: 0 = dq + dkv kernel pair, 1 = single fused
+ * kernel, 2 = fused kernel with a dedicated read-out warpgroup, the default) */
 int mapdit_set_option(const char* name, int value);
-/* developer hook: device buffer of >= 1024 int64 that CTA 0 of the attn_v2 kernel fills with clock64 stamps (null = off) */
+/* developer hook: device buffer of >= 1024 int64 that CTA 0 of the attn_v2 / attn_bwd_fused / 2-CTA GEMM kernels fills with
+ * clock64 stamps (null = off); read by tools/attn_timeline.py, tools/attn_bwd_timeline.py, tools/gemm_timeline.py */
 int mapdit_attn_debug_buffer(void* buf);
 /* weight gradient C[N_out, K_in] (fp32) = dY[M, N_out]^T · X[M, K_in] on tcgen05, operands read MN-major in place
  * (autograd of F.linear, src/basic/mp_linear.py:46,75); split-K with fp32 vector reductions when N_out*K_in is small */
