@@ -151,3 +151,47 @@ def test_state_dict_accepts_compiled_prefix():
     m = M.DIT_MODELS["DiT-XS/8"](in_channels=4, input_size=32, num_classes=1000)
     m.load_state_dict({"_orig_mod." + k: v for k, v in sd.items()})
     assert all(torch.equal(m.state_dict()[k], v) for k, v in sd.items())
+
+
+def test_bench_flops_model_matches_survey_table():
+    """bench.py's algorithmic FLOPs per image (the numerator of `step_frac_of_sustained`) against SURVEY.md §8(d): DiT-B/2 forward
+    46.011 GFLOP, training 139.240 GFLOP; the rotation-and-scaling headline has a 5D-wide modulation GEMM instead of 6D."""
+    import importlib.util
+    import os
+    import types
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    # bench.py re-points file descriptor 1 at import time (stdout guard): give it a scratch descriptor to play with
+    saved = os.dup(1)
+    try:
+        bench = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(bench)
+    finally:
+        os.dup2(saved, 1)
+        os.close(saved)
+    m = types.SimpleNamespace(patch_size=2, in_channels=4, input_size=32, depth=12, hidden_size=768, modulation="adaln")
+    fl = bench.flops_per_image(m)
+    assert abs(fl["fwd"] / 1e9 - 46.011) < 0.01 and abs(fl["train"] / 1e9 - 139.240) < 0.02
+    m.modulation = "rotation_scaling"
+    fr = bench.flops_per_image(m)
+    assert fr["fwd"] == fl["fwd"] - 12 * 2 * 768 * 768  # one D x D slice less per block
+    assert bench.metric_name("train") == "dit_b2_map_train_img_per_s" and "rotation-and-scaling" in bench.workload_name("train")
+
+
+def test_gemm_args_struct_mirror_matches_library():
+    """the ctypes mirror of mapdit_gemm_args (with the ldrot field of the rotation epilogue) has the library's size"""
+    import ctypes as C
+    from mapdit_b200 import _lib
+    L = _lib.lib()
+    L.mapdit_sizeof_gemm_args.restype = C.c_int
+    assert L.mapdit_sizeof_gemm_args() == C.sizeof(_lib.GemmArgs)
+    assert _lib.EPI_RESID_ROT == 6
+
+
+def test_launch_summary_tool_reads_the_committed_profile():
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "launch_summary.py"), os.path.join(root, "profiles", "r2_launches_train.csv")],
+                         capture_output=True, text=True, check=True).stdout
+    assert "360 launches" in out and "gemm_tc2_kernel<256>" in out and "attn_bwd_fused2_tc" in out
