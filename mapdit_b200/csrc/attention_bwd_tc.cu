@@ -1011,7 +1011,7 @@ attn_bwd_fused2_tc(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   uint64_t* s_full = bars + 16;     // S^T / dP^T of iteration g complete
   uint64_t* s_empty = bars + 17;    // ... read by the 8 softmax warps
   uint64_t* p_full = bars + 18;     // [2] 64-query panel `half` of the P^T / dS^T staging tiles of iteration g written (4 warps each)
-  uint64_t* p_empty = bars + 20;    // [2] ... consumed by the dV / dK / dQ MMAs (k-steps 0-3 read panel 0, 4-7 panel 1)
+  uint64_t* p_empty = bars + 20;    // [2] ... consumed by the dV / dK / dQ MMAs (dQ reads both panels in every k-step: both complete together)
   uint64_t* acc_free = bars + 22;   // dV / dK read out (4 epilogue warps), twice per item
   uint64_t* dqs_free = bars + 23;   // dQ of the item's second query block read out
   uint64_t* dqf_free = bars + 24;   // dQ of the item's first query block read out
