@@ -102,6 +102,46 @@ def cases():
                                    6 * D, B, T, True)
         return fn, ("hbm", M * D * 2 * 6)
 
+    def rotmod_resid_bwd():
+        sets = [(mk(M, D), mk(M, D), mk(M, D), mk(M, D), mk(M, D)) for _ in range(2)]
+        dgp = torch.empty(ops.rotmod_bwd_partials(B, D), device=dev)
+        it = [0]
+
+        def fn():
+            dh, x, R, y, dy = sets[it[0] % 2]
+            it[0] += 1
+            ops.rotmod_resid_bwd(dh, x, R, mods, mods[:, D:], gain, dmods, dmods[:, D:], dgp, y, dy, mods[:, 2 * D:], dmods[:, 2 * D:],
+                                 6 * D, B, T, True)
+        return fn, ("hbm", M * D * 2 * 6)
+
+    def patch_embed():
+        x = torch.randn(B, 4, 32, 32, device=dev)
+        wx, pos = torch.randn(D, 17, device=dev) * 0.2, torch.randn(T, D, device=dev)
+        outs = [(mk(M, D), mk(M, D)) for _ in range(2)]
+        it = [0]
+
+        def fn():
+            x0, h = outs[it[0] % 2]
+            it[0] += 1
+            ops.patch_embed(x, wx, pos, x0, h, mods, mods[:, D:], gain, 6 * D, 2)
+        return fn, ("hbm", M * D * 2 * 2)
+
+    def patch_embed_wgrad():
+        x = torch.randn(B, 4, 32, 32, device=dev)
+        Rs = [mk(M, D) for _ in range(3)]
+        dW = torch.empty(D, 17, device=dev)
+        it = [0]
+
+        def fn():
+            it[0] += 1
+            ops.patch_embed_wgrad(Rs[it[0] % 3], x, dW, 2, 1.0)
+        return fn, ("hbm", M * D * 2)
+
+    def gemm_f32_cond():
+        a, w = torch.randn(B, D, device=dev), torch.randn(D, D, device=dev)
+        out = torch.empty(B, D, device=dev)
+        return (lambda: ops.gemm_f32(a, w, out=out)), ("tensor", 2 * B * D * D)
+
     def resid_bwd():
         sets = [(mk(M, D), mk(M, D), mk(M, D)) for _ in range(3)]
         it = [0]
@@ -154,6 +194,10 @@ def cases():
     c["modulate_bwd"] = modulate_bwd
     c["resid_bwd"] = resid_bwd
     c["modulate_resid_bwd"] = modulate_resid_bwd
+    c["rotmod_resid_bwd"] = rotmod_resid_bwd
+    c["patch_embed"] = patch_embed
+    c["patch_embed_wgrad"] = patch_embed_wgrad
+    c["gemm_f32_cond_256x768x768"] = gemm_f32_cond
     c["qk_norm_bwd"] = qk_norm_bwd
     c["adam_130M"] = adam
     c["gemm_qkv"] = gemm(3 * D, D, _lib.EPI_QKNORM)
