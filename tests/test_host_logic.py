@@ -195,3 +195,13 @@ def test_launch_summary_tool_reads_the_committed_profile():
     out = subprocess.run([sys.executable, os.path.join(root, "tools", "launch_summary.py"), os.path.join(root, "profiles", "r2_launches_train.csv")],
                          capture_output=True, text=True, check=True).stdout
     assert "360 launches" in out and "gemm_tc2_kernel<256>" in out and "attn_bwd_fused2_tc" in out
+
+
+def test_epilogue_and_variant_constants_match_header():
+    """the Python mirror of the header's enums (epilogue selectors, dtype codes) cannot drift from include/mapdit.h"""
+    from mapdit_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "mapdit.h")).read()
+    defs = {k: int(v, 0) for k, v in re.findall(r"#define\s+(MAPDIT_[A-Z0-9_]+)\s+(-?(?:0x[0-9a-fA-F]+|\d+))\b", hdr)}
+    for name in ("STORE", "QKNORM", "MPSILU", "RESID_MOD", "RESID", "SILU_BWD", "RESID_ROT"):
+        assert defs[f"MAPDIT_EPI_{name}"] == getattr(_lib, f"EPI_{name}"), name
+    assert len({defs[k] for k in defs if k.startswith("MAPDIT_EPI_")}) == 7  # no two selectors share a value
