@@ -358,17 +358,20 @@ def test_generic_mma_attention_forward_backward(N, T, H, hd, cosine):
 
 
 @pytest.mark.gpu
-def test_thirty_training_steps_follow_the_oracle_loss_curve():
-    """End to end on the bench's configuration family (rotation-and-scaling, 256 tokens, bf16): 30 TrainStep steps on one fixed batch
-    (fused rotation epilogues, fused tcgen05 attention backward, weight-gradient GEMMs on the second stream, fused Adam with the
-    forced weight normalisation).  The CPU oracle + torch.optim.Adam on the same seeds goes 1.3963 -> 0.5067 (recorded from
-    `oracle.train_step_grads`, lr 1e-2, betas (0.9, 0.99), DiT-XS/2, seed 3 / data seed 7; SELF-REFERENTIAL for the rotation part)."""
+@pytest.mark.parametrize("modulation,first,last,tol_last", [("rotation_scaling", 1.3963, 0.5067, 0.03), ("adaln", 1.0976, 0.7912, 0.12)])
+def test_thirty_training_steps_follow_the_oracle_loss_curve(modulation, first, last, tol_last):
+    """End to end on the bench's configuration family (256 tokens, bf16): 30 TrainStep steps on one fixed batch (fused epilogues, fused
+    tcgen05 attention backward, weight-gradient GEMMs on the second stream, fused Adam with the forced weight normalisation).  The
+    CPU oracle + torch.optim.Adam on the same seeds (`oracle.train_step_grads`, lr 1e-2, betas (0.9, 0.99), DiT-XS/2, seed 3 / data
+    seed 7) goes 1.3963 -> 0.5067 with rotation-and-scaling modulation (SELF-REFERENTIAL for the rotation part) and, less smoothly
+    (1.0976, 0.9917, 0.9832, 1.1847, 0.9336 ... 0.7912), with the snapshot's MP-AdaLN; the looser bound there covers the bf16 path
+    taking the step-9 spike differently."""
     import mapdit_b200 as M
     from mapdit_b200.train import TrainStep
     name = "DiT-XS/2"
-    cfg = O.config_for(name, modulation="rotation_scaling")
+    cfg = O.config_for(name, modulation=modulation)
     sd = O.init_state_dict(cfg, seed=3)
-    m = M.DIT_MODELS[name](in_channels=4, input_size=32, num_classes=1000, modulation="rotation_scaling")
+    m = M.DIT_MODELS[name](in_channels=4, input_size=32, num_classes=1000, modulation=modulation)
     m.load_state_dict(sd)
     m = m.cuda().train()
     ts = TrainStep(m, M.create_diffusion(""), lr=1e-2, betas=(0.9, 0.99))
@@ -380,7 +383,7 @@ def test_thirty_training_steps_follow_the_oracle_loss_curve():
     noise = torch.randn(B, 4, 32, 32, generator=g).cuda()
     drop = torch.zeros(B, dtype=torch.bool).cuda()
     losses = [float(ts.step(x, t, y, noise, drop_mask=drop)) for _ in range(30)]
-    print("loss curve:", " ".join(f"{v:.3f}" for v in losses[::3]), f"... {losses[-1]:.4f}  (oracle 1.3963 -> 0.5067)")
-    assert abs(losses[0] - 1.3963) < 3e-2 * 1.3963
-    assert abs(losses[-1] - 0.5067) < 0.03  # measured on B200: 0.5069, the whole curve within 1e-3 of the oracle's
+    print(f"{modulation} loss curve:", " ".join(f"{v:.3f}" for v in losses[::3]), f"... {losses[-1]:.4f}  (oracle {first} -> {last})")
+    assert abs(losses[0] - first) < 3e-2 * first
+    assert abs(losses[-1] - last) < tol_last  # rotation_scaling measured on B200: 0.5069, the whole curve within 1e-3 of the oracle's
     assert all(torch.isfinite(p).all() for p in m.parameters())
