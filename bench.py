@@ -188,45 +188,87 @@ def workload_name(w):
 
 
 # --------------------------------------------------------------------------------------------- our arm (B200)
-def cpu_baseline(workload, seconds_budget=20.0):
+VAL_TRAIN_N, VAL_SAMPLE_N = 8, 4  # sub-batch sizes of the oracle validation legs
+
+
+def make_model(M, dtype, dev, input_size, flags_off):
+    """the bench's synthetic network: torch seed 0, the reference's init distributions, gains / sigma reference moved off their
+    zero init like a trained net (with the reference's zero gains the shift / rotation paths would carry no signal)"""
     import torch
+    torch.manual_seed(0)  # same replica on every rank (and on the CPU for the oracle legs)
+    off = {k: False for k in ("use_cosine_attention", "use_weight_normalization", "use_forced_weight_normalization", "use_mp_residual",
+                              "use_mp_silu", "use_no_layernorm", "use_mp_pos_enc", "use_mp_embedding")} if flags_off else {}
+    model = M.DIT_MODELS[MODEL](in_channels=4, input_size=input_size, num_classes=1000, compute_dtype=dtype, modulation=MODULATION, **off)
+    with torch.no_grad():
+        for name, prm in model.named_parameters():
+            if prm.dim() == 0:
+                prm.fill_(0.3)
+        model.final_layer.sigma_scale.reference.normal_()
+    return model.to(dev) if dev is not None else model, off
+
+
+def host_inputs(B, S, rank):
+    """seeded host-side inputs of one rank (pinned by the caller)"""
+    import torch
+    g = torch.Generator().manual_seed(1 + rank)
+    z = torch.randn(B, 4, S, S, generator=g)
+    y = torch.randint(0, 1000, (B,), generator=g)
+    t = torch.randint(0, 1000, (B,), generator=g)
+    noise = torch.randn(B, 4, S, S, generator=g)
+    drop = torch.rand(B, generator=g) < 0.1
+    step_noises = torch.randn(SAMPLING_STEPS, VAL_SAMPLE_N, 4, S, S, generator=g)
+    return dict(z=z, y=y, t=t, noise=noise, drop=drop, step_noises=step_noises)
+
+
+def cpu_legs(args, workloads, baseline=True):
+    """Rank 0, N = 1, BEFORE any NCCL initialisation (other ranks must not spin on the GPU while the host cores are timed): the
+    pinned CPU oracle (oracle/mapdit_oracle.py) on bounded samples of the same workload with the bench's own weights and inputs.
+    It returns the reported `cpu_baseline` AND the reference values the GPU results are validated against afterwards."""
+    import torch
+    import mapdit_b200 as M
     from oracle import mapdit_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cfg = O.config_for(MODEL, modulation=MODULATION)
-    sd = O.init_state_dict(cfg, seed=0)
-    B = 8
-    g = torch.Generator().manual_seed(1)
-    x = torch.randn(B, 4, 32, 32, generator=g)
-    y = torch.randint(0, 1000, (B,), generator=g)
-    t = torch.randint(0, 1000, (B,), generator=g)
-    if workload == "train":
+    model, off = make_model(M, "fp32", None, args.input_size, args.flags_off)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    del model
+    cfg = O.config_for(MODEL, modulation=MODULATION, input_size=args.input_size, **off)
+    hi = host_inputs(args.batch, args.input_size, 0)
+    out = {}
+    if "train" in workloads:
+        n = VAL_TRAIN_N
         p = O.make_params(sd)
         T = O.make_tables("")
-        opt = torch.optim.Adam([v for v in p.values() if v.requires_grad], lr=1e-2, betas=(0.9, 0.99))
-        noise = torch.randn(B, 4, 32, 32, generator=g)
-
-        def step():
-            opt.zero_grad()
-            O.train_step_grads(p, cfg, T, x, t, y, noise)
-            opt.step()
-        scale, what = B, f"{MODEL} training step at batch {B}"
-    else:
-        def step():
-            with torch.no_grad():
-                O.dit_forward(sd, cfg, x, t, y)
-        scale = B / SAMPLING_STEPS if workload == "sample" else B
-        what = f"{MODEL} eval forward at batch {B}" + (f", x{SAMPLING_STEPS} steps per image" if workload == "sample" else "")
-    step()
-    n, t0 = 0, time.perf_counter()
-    while True:
-        step()
-        n += 1
+        x, t, y, noise, drop = (hi[k][:n] for k in ("z", "t", "y", "noise", "drop"))
+        terms, _ = O.train_step_grads(p, cfg, T, x, t, y, noise, drop_mask=drop)  # step-0 per-sample losses (also the warm-up)
+        rec = {"loss_ref": terms["loss"].detach().clone()}
+        if baseline:
+            opt = torch.optim.Adam([v for v in p.values() if v.requires_grad], lr=1e-2, betas=(0.9, 0.99))
+            k, t0 = 0, time.perf_counter()
+            while True:
+                opt.zero_grad()
+                O.train_step_grads(p, cfg, T, x, t, y, noise, drop_mask=drop)
+                opt.step()
+                k += 1
+                el = time.perf_counter() - t0
+                if el > 15.0 or k >= 10:
+                    break
+            rec["cpu_baseline"] = {"value": n * k / el, "unit": "img/s", "cores": cores, "kind": "port",
+                                   "sample": f"{MODEL} training step (loss + backward + Adam) at batch {n}, {k} iterations in {el:.1f} s "
+                                             "on the pinned CPU oracle (oracle/mapdit_oracle.py)"}
+        out["train"] = rec
+    if "sample" in workloads:
+        n = VAL_SAMPLE_N
+        T = O.make_tables(str(SAMPLING_STEPS))
+        z, y = hi["z"][:n], hi["y"][:n]
+        t0 = time.perf_counter()
+        ref = O.p_sample_loop(T, lambda a, b: O.dit_forward(sd, cfg, a, b, y), z, list(hi["step_noises"]), clip_denoised=True)
         el = time.perf_counter() - t0
-        if el > seconds_budget or n >= 10:
-            break
-    return {"value": scale * n / el, "unit": "img/s", "cores": cores, "kind": "port",
-            "sample": f"{what}, {n} iterations in {el:.1f} s on the pinned CPU oracle (oracle/mapdit_oracle.py)"}
+        out["sample"] = {"sample_ref": ref,
+                         "cpu_baseline": {"value": n / el, "unit": "img/s", "cores": cores, "kind": "port",
+                                          "sample": f"{MODEL} full {SAMPLING_STEPS}-step p_sample_loop of {n} images in {el:.1f} s on the "
+                                                    "pinned CPU oracle (oracle/mapdit_oracle.py)"}}
+    return out
 
 
 def time_kernel(fn, iters=10, warm=3):
@@ -245,7 +287,7 @@ def time_kernel(fn, iters=10, warm=3):
 
 def kernel_roofline(model, B, pk):
     """Isolated timing (CUDA events on the launching stream) of the dominant kernel: the fc1 block GEMM
-    (gemm_tc_kernel<256>, fused mp_silu epilogue), plus the other block GEMMs and attention for the table."""
+    (gemm_tc2_kernel<256>: cta_group::2 256 x 256 tiles, fused mp_silu epilogue), plus the other block GEMMs and attention."""
     import torch
     from mapdit_b200 import _lib, ops
     D, T, H = model.hidden_size, (model.input_size // model.patch_size) ** 2, model.num_heads
@@ -279,20 +321,31 @@ def kernel_roofline(model, B, pk):
         ms = time_kernel(fn)
         res[k] = {"ms": round(ms, 4), "tflops": round(fl / ms / 1e9, 1)}
     dom = res["fc1_gemm_mpsilu"]
-    roof = {"bound": "tensor", "kernel": "gemm_tc_kernel<256> (fc1, fused mp_silu epilogue), M=%d N=%d K=%d" % (M, 4 * D, D),
+    # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel at this shape, from the committed ncu --set full
+    # capture of the shipped kernel (tools/ncu_traffic.py writes the file from the .ncu-rep); null when the capture is of another shape
+    traffic, tsrc = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "round2_fc1_gemm_tc2_traffic.json")) as f:
+            tj = json.load(f)
+        if tj.get("m") == M and tj.get("n") == 4 * D and tj.get("k") == D and "gemm_tc2_kernel" in tj.get("kernel", ""):
+            traffic, tsrc = tj["dram_bytes_read"] + tj["dram_bytes_write"], "B/launch (ncu --set full, profiles/round2_fc1_gemm_tc2_traffic.json)"
+    except Exception:
+        pass
+    algo_bytes = 2 * (M * D + 4 * D * D + M * 4 * D)  # A + B + out in bf16 (the eval flavour timed here; training also writes the pre-activation)
+    roof = {"bound": "tensor", "kernel": "gemm_tc2_kernel<256> (fc1, cta_group::2, fused mp_silu epilogue), M=%d N=%d K=%d" % (M, 4 * D, D),
             "achieved": dom["tflops"], "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": round(dom["tflops"] / pk["tf_burst"], 4),
             "peak_source": f"MEASURED_PEAKS.json bf16 burst ({pk['src']})",
-            # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the ncu --set full capture
-            # (profiles/r1_gemm_tc2_ncu_summary.md): 105.4 + 350.6 MB; algorithmic bytes (A + B + out) = 503 MB
-            "traffic": 456.0e6, "traffic_unit": "B/launch (ncu, profiles/r1_gemm_tc2_ncu_summary.md)", "per_kernel": res}
+            "traffic": traffic, "traffic_unit": tsrc, "algorithmic_bytes": algo_bytes, "per_kernel": res}
     return roof
 
 
-def run_ours(args, workload, finalize=True):
+def run_ours(args, workload, finalize=True, cpu=None):
+    """`cpu` = cpu_legs()[workload] (rank 0 at N = 1): the oracle's reference values + the reported cpu_baseline"""
     import torch
     import torch.distributed as dist
     import mapdit_b200 as M
     from mapdit_b200 import _lib
+    from mapdit_b200.diffusion import gaussian_diffusion as gd
     if args.gemm_2cta is not None:
         _lib.set_option("gemm_2cta", args.gemm_2cta)
 
@@ -304,42 +357,37 @@ def run_ours(args, workload, finalize=True):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     B = args.batch
-    torch.manual_seed(0)  # same replica on every rank
     S = args.input_size
-    off = {k: False for k in ("use_cosine_attention", "use_weight_normalization", "use_forced_weight_normalization", "use_mp_residual",
-                              "use_mp_silu", "use_no_layernorm", "use_mp_pos_enc", "use_mp_embedding")} if args.flags_off else {}
-    model = M.DIT_MODELS[MODEL](in_channels=4, input_size=S, num_classes=1000, compute_dtype=args.dtype, modulation=MODULATION, **off)
-    with torch.no_grad():  # the reference initialises the gains to 0 (shift path unused): give them values like a trained net
-        for name, prm in model.named_parameters():
-            if prm.dim() == 0:
-                prm.fill_(0.3)
-        model.final_layer.sigma_scale.reference.normal_()
-    model = model.to(dev)
+    model, _ = make_model(M, args.dtype, dev, S, args.flags_off)
     fl = flops_per_image(model)
     pk = peaks()
-    g = torch.Generator().manual_seed(1 + rank)
     # host-side (pinned) inputs for the e2e leg, device-resident copies for the kernel-only leg
-    z_host = torch.randn(B, 4, S, S, generator=g).pin_memory()
-    y_host = torch.randint(0, 1000, (B,), generator=g).pin_memory()
-    t_host = torch.randint(0, 1000, (B,), generator=g).pin_memory()
+    hi = host_inputs(B, S, rank)
+    z_host, y_host, t_host = hi["z"].pin_memory(), hi["y"].pin_memory(), hi["t"].pin_memory()
     z_dev, y_dev, t_dev = z_host.to(dev), y_host.to(dev), t_host.to(dev)
     out_host = torch.empty(B, 4, S, S).pin_memory()
     diffusion = M.create_diffusion(str(SAMPLING_STEPS) if workload == "sample" else "")
+    validation = {}
+    state = {}
 
     if workload == "sample":
         model.eval()
         gather = [torch.empty(B, 4, S, S, device=dev) for _ in range(world)] if world > 1 else None
+        # clip_denoised=True: on random weights the unclipped x0 prediction of sample.py:52-61 (clip_denoised=False on TRAINED
+        # weights) diverges to inf within ~37 steps; the clamp is one instruction of the fused step kernel, the work is identical
+        CLIP = True
 
         def step_dev():
-            s = diffusion.p_sample_loop(model.forward, z_dev.shape, z_dev, clip_denoised=False, model_kwargs=dict(y=y_dev), device=dev)
+            s = diffusion.p_sample_loop(model.forward, z_dev.shape, z_dev, clip_denoised=CLIP, model_kwargs=dict(y=y_dev), device=dev)
             if world > 1:
                 dist.all_gather(gather, s)
+            state["last"] = s
             return s
 
         def step_e2e():
             z = z_host.to(dev, non_blocking=True)
             y = y_host.to(dev, non_blocking=True)
-            s = diffusion.p_sample_loop(model.forward, z.shape, z, clip_denoised=False, model_kwargs=dict(y=y), device=dev)
+            s = diffusion.p_sample_loop(model.forward, z.shape, z, clip_denoised=CLIP, model_kwargs=dict(y=y), device=dev)
             if world > 1:
                 dist.all_gather(gather, s)
             out_host.copy_(s, non_blocking=True)
@@ -347,12 +395,28 @@ def run_ours(args, workload, finalize=True):
         images_per_step = B
         flops_step = fl["fwd"] * B * SAMPLING_STEPS
         h2d, d2h = z_host.numel() * 4 + y_host.numel() * 8, out_host.numel() * 4
+        if cpu is not None and rank == 0:
+            # end-of-loop divergence of a sub-batch against the CPU oracle on the same weights, start noise and per-step noise
+            n = VAL_SAMPLE_N
+            it = iter(hi["step_noises"].to(dev))
+            real = gd._randn_like
+            gd._randn_like = lambda v: next(it)
+            try:
+                sv = diffusion.p_sample_loop(model.forward, (n, 4, S, S), z_dev[:n].clone(), clip_denoised=True,
+                                             model_kwargs=dict(y=y_dev[:n]), device=dev)
+            finally:
+                gd._randn_like = real
+            ref = cpu["sample_ref"].double()
+            validation["sample_rel_l2_vs_oracle"] = float((sv.cpu().double() - ref).norm() / ref.norm())
+            validation["sample_check"] = (f"{n} images, {SAMPLING_STEPS} steps, shared noise, free running, clip_denoised=True, {args.dtype} vs the "
+                                          "fp32 CPU oracle" + ("" if MODULATION == "adaln" else " (rotation modulation: self-referential oracle)"))
     elif workload == "forward":
         model.eval()
 
         def step_dev():
             with torch.no_grad():
-                return model(z_dev, t_dev, y_dev)
+                state["last"] = model(z_dev, t_dev, y_dev)
+                return state["last"]
 
         out8 = torch.empty(B, 8, S, S).pin_memory()
 
@@ -370,19 +434,30 @@ def run_ours(args, workload, finalize=True):
         if args.wgrad_stream is not None:
             model.engine.trainer.wgrad_stream = bool(args.wgrad_stream)
         ts = TrainStep(model, diffusion, lr=1e-2, betas=(0.9, 0.99), world_size=world)
-        noise_dev = torch.randn(B, 4, S, S, device=dev)
-        noise_host = noise_dev.cpu().pin_memory()
+        noise_host, drop_host = hi["noise"].pin_memory(), hi["drop"].pin_memory()
+        noise_dev, drop_dev = noise_host.to(dev), drop_host.to(dev)
+        losses = []
+        if cpu is not None and rank == 0:
+            # step-0 per-sample losses of a sub-batch against the CPU oracle (same weights, inputs, noise, label-dropout mask)
+            n = VAL_TRAIN_N
+            l0 = ts.compute_grads(z_dev[:n], t_dev[:n], y_dev[:n], noise_dev[:n], drop_dev[:n], reduce=False)
+            ref = cpu["loss_ref"].double()
+            validation["loss_rel_l2_vs_oracle"] = float((l0.cpu().double() - ref).norm() / ref.norm())
+            validation["loss_check"] = (f"per-sample losses of {n} samples before the first optimiser step, {args.dtype} vs the fp32 CPU oracle"
+                                        + ("" if MODULATION == "adaln" else " (rotation modulation: self-referential oracle)"))
 
         def step_dev():
-            return ts.step(z_dev, t_dev, y_dev, noise_dev)
+            loss = ts.step(z_dev, t_dev, y_dev, noise_dev, drop_mask=drop_dev)
+            losses.append(loss)
+            return loss
 
         def step_e2e():
             loss = ts.step(z_host.to(dev, non_blocking=True), t_host.to(dev, non_blocking=True), y_host.to(dev, non_blocking=True),
-                           noise_host.to(dev, non_blocking=True))
+                           noise_host.to(dev, non_blocking=True), drop_mask=drop_host.to(dev, non_blocking=True))
             return float(loss)  # D2H read of the loss, like train.py:99
         images_per_step = B
         flops_step = fl["train"] * B
-        h2d, d2h = (z_host.numel() + noise_host.numel()) * 4 + 2 * B * 8, 4
+        h2d, d2h = (z_host.numel() + noise_host.numel()) * 4 + 2 * B * 8 + B, 4
 
     def barrier():
         if world > 1:
@@ -417,7 +492,23 @@ def run_ours(args, workload, finalize=True):
     if world > 1:
         dist.barrier()
     sampler = ClockSampler(local) if rank == 0 else None
-    ms, launches, clk = timed(step_dev, args.steps, max(args.warmup, 3), sampler)
+    warm = max(args.warmup, 3)
+    ms, launches, clk = timed(step_dev, args.steps, warm, sampler)
+    # self-validation of the timed region's own results (every rank; reported by rank 0)
+    if workload == "train":
+        lv = torch.stack(losses).float().cpu()
+        validation.update(loss_first=float(lv[0]), loss_first_timed=float(lv[warm]), loss_last=float(lv[-1]),
+                          losses_finite=bool(torch.isfinite(lv).all()),
+                          loss_note="the same synthetic batch every step: the loss must fall from loss_first (step 0, before any update)")
+        fin = bool(torch.isfinite(lv).all())
+    else:
+        fin = bool(torch.isfinite(state["last"]).all())
+        validation.update(finite=fin, out_abs_max=float(state["last"].abs().max()))
+    if world > 1:
+        ft = torch.tensor([1 if fin else 0], device=dev)
+        dist.all_reduce(ft, op=dist.ReduceOp.MIN)
+        fin = bool(int(ft))
+    validation["finite_all_ranks"] = fin
     ms_e2e, _, _ = timed(step_e2e, args.steps, 1)
     value = images_per_step * world * args.steps / (ms / 1e3)
     e2e_value = images_per_step * world * args.steps / (ms_e2e / 1e3)
@@ -427,18 +518,18 @@ def run_ours(args, workload, finalize=True):
             step_tf = flops_step * args.steps / (ms / 1e3) / 1e12
             roof["step_tflops_per_gpu"] = round(step_tf, 1)
             roof["step_frac_of_sustained"] = round(step_tf / pk["tf_sustained"], 4)
-        cpu = cpu_baseline(workload) if not args.no_cpu_baseline else None
         line = {"metric": metric_name(workload), "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "warmup": warm, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
                 "config": {"workload": workload_name(workload), "model": MODEL, "modulation": MODULATION, "batch_per_gpu": B,
                            "global_batch": B * world,
                            "parallelism": f"dp{world}" if world > 1 else "single",
                            "l2": "per-step working set (activations ~100 MB per [M,D] tensor, 2.4 GB per block) exceeds the 126 MB L2; no flush needed",
-                           "weights": "random init (torch seed 0), reference init distributions, gains 0.3", "clip_denoised": False},
+                           "weights": "random init (torch seed 0), reference init distributions, gains 0.3", "clip_denoised": True},
                 "e2e": {"value": e2e_value, "unit": "img/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps},
-                "gpu_launches": launches, "clocks": clk, "roofline": roof, "cpu_baseline": cpu}
+                "gpu_launches": launches, "clocks": clk, "roofline": roof, "validation": validation,
+                "cpu_baseline": cpu.get("cpu_baseline") if cpu is not None else None}
     else:
         line = None
     del model
@@ -446,6 +537,28 @@ def run_ours(args, workload, finalize=True):
     if world > 1 and finalize:
         dist.destroy_process_group()
     return line
+
+
+def ref_on_b200(args):
+    """informational: the unmodified reference (oracle/_ref) through its own PyTorch path on this GPU (rank 0, N = 1).  The eager
+    arms are timed live; the torch.compile arms (minutes of compilation) come from the committed run of tools/ref_on_b200.py."""
+    out = {"what": "unmodified reference DiT-B/2 (MP-AdaLN) on this B200 through its own PyTorch path; compare with `adaln`",
+           "batch": args.batch}
+    try:
+        with open(os.path.join(ROOT, "profiles", "round2_ref_on_b200.json")) as f:
+            out["recorded"] = {"source": "profiles/round2_ref_on_b200.json (tools/ref_on_b200.py --compile on a B200 of this pool)", **json.load(f)}
+    except Exception:
+        out["recorded"] = None
+    if args.no_ref_on_b200:
+        return out
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import ref_on_b200 as R
+        out["live"] = R.measure(MODEL, args.batch, arms=("eager_tf32", "eager_bf16_autocast"), train_steps=3, sampling_steps=SAMPLING_STEPS,
+                                input_size=args.input_size)
+    except Exception as e:  # noqa: BLE001
+        out["live"] = {"unavailable": f"{type(e).__name__}: {str(e)[:200]}"}
+    return out
 
 
 def main():
@@ -468,6 +581,7 @@ def main():
     ap.add_argument("--no-adaln-arm", action="store_true", help="skip the extra MP-AdaLN timing of the default run")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-on-b200", action="store_true", help="skip the live eager timing of the unmodified reference on the GPU")
     args = ap.parse_args()
     global MODEL, SAMPLING_STEPS, MODULATION
     if args.modulation:
@@ -487,21 +601,33 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
                "--master-port", "29541", os.path.abspath(__file__)] + sys.argv[1:]
         sys.exit(subprocess.call(cmd, stdout=_REAL_STDOUT))
+    rank = int(os.environ.get("RANK", "0"))
+    # CPU legs (oracle reference values + the reported cpu_baseline): rank 0 at N = 1 only, before anything touches NCCL or the GPU
+    do_cpu = rank == 0 and world == 1 and not args.no_cpu_baseline
+    wl = ["train", "sample"] if args.workload == "both" else ([args.workload] if args.workload in ("train", "sample") else [])
+    cpu = cpu_legs(args, wl) if (do_cpu and wl) else {}
     if args.workload == "both":
         # BASELINE.json's metric has two halves: the training step is the primary value, the 50-step sampler rides along
-        line = run_ours(args, "train", finalize=False)
-        sline = run_ours(args, "sample", finalize=False)
+        cpu_adaln = {}
+        if do_cpu and MODULATION != "adaln" and not args.no_adaln_arm:
+            main_mod, MODULATION = MODULATION, "adaln"
+            cpu_adaln = cpu_legs(args, wl, baseline=False)
+            MODULATION = main_mod
+        refb = ref_on_b200(args) if (rank == 0 and world == 1 and not args.flags_off and args.model is None) else None
+        line = run_ours(args, "train", finalize=False, cpu=cpu.get("train"))
+        sline = run_ours(args, "sample", finalize=False, cpu=cpu.get("sample"))
         adaln = None
         if MODULATION != "adaln" and not args.no_adaln_arm:
             # the parity-pinned variant (the only modulation the reference snapshot has code for), device-timed only
             main_mod, MODULATION = MODULATION, "adaln"
-            args.no_roofline, args.no_cpu_baseline = True, True
-            at, asmp = run_ours(args, "train", finalize=False), run_ours(args, "sample", finalize=False)
+            args.no_roofline = True
+            at = run_ours(args, "train", finalize=False, cpu=cpu_adaln.get("train"))
+            asmp = run_ours(args, "sample", finalize=False, cpu=cpu_adaln.get("sample"))
             MODULATION = main_mod
             if at is not None:
                 adaln = {"modulation": "adaln", "note": "reference snapshot's MP-AdaLN modulation (parity pinned by the reference)",
-                         "train": {k: at[k] for k in ("value", "unit", "ms_per_step", "gpu_launches")},
-                         "sample50": {k: asmp[k] for k in ("value", "unit", "ms_per_step", "gpu_launches")},
+                         "train": {k: at[k] for k in ("value", "unit", "ms_per_step", "gpu_launches", "validation")},
+                         "sample50": {k: asmp[k] for k in ("value", "unit", "ms_per_step", "gpu_launches", "validation")},
                          "e2e": {"train": at["e2e"], "sample50": asmp["e2e"]}}
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized():
@@ -510,7 +636,9 @@ def main():
             if adaln is not None:
                 line["adaln"] = adaln
             line["metric"] = "dit_b2_map_train_img_per_s (+ sample50 img/s in `sample50`)"
-            keep = ("value", "unit", "ms_per_step", "e2e", "gpu_launches", "clocks", "cpu_baseline")
+            if refb is not None:
+                line["ref_on_b200"] = refb
+            keep = ("value", "unit", "ms_per_step", "e2e", "gpu_launches", "clocks", "cpu_baseline", "validation")
             line["sample50"] = {k: sline[k] for k in keep}
             line["sample50"]["metric"] = sline["metric"]
             line["sample50"]["workload"] = sline["config"]["workload"]
@@ -518,7 +646,7 @@ def main():
                 line["sample50"]["step_tflops_per_gpu"] = sline["roofline"]["step_tflops_per_gpu"]
                 line["sample50"]["step_frac_of_sustained"] = sline["roofline"]["step_frac_of_sustained"]
     else:
-        line = run_ours(args, args.workload)
+        line = run_ours(args, args.workload, cpu=cpu.get(args.workload))
     if line is not None:
         emit_line(line)
 

@@ -69,6 +69,9 @@ int mapdit_weight_norm_fwd_multi(const void* descs, int n_desc, int total_groups
  * and the (forced) weights v, grad_v = (G - v (v·G)/(r (r+eps)))/(r+eps); accumulate==0 overwrites. */
 int mapdit_weight_norm_bwd(const float* v, const float* g_eff, float* grad_v, int rows, int cols,
                            float eps, int accumulate, void* stream);
+/* the same for several tensors in ONE launch, in place (g holds G on entry and grad_v on return; cols % 4 == 0, 16-byte aligned).
+ * table: int64[n_items][5] = {v ptr, g ptr, rows, cols, group0}; group0 = sum over earlier items of ceil(rows/8); n_groups = total */
+int mapdit_weight_norm_bwd_multi(const void* table, int n_items, int n_groups, float eps, void* stream);
 
 /* ---- fp32 GEMM (mode a: CUDA-core FFMA, strided) --------------------------------------------
  * C[m,n] (+)= sum_k A(m,k) * B(n,k), A element (m,k) at a[m*sam + k*sak], B element (n,k) at
@@ -132,6 +135,9 @@ int mapdit_gemm_bf16_tn(const void* dy, int64_t ldy, const void* x, int64_t ldx,
  * m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2; p -= lr * (m/bc1) / (sqrt(v/bc2) + eps) */
 int mapdit_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                      float bias_corr1, float bias_corr2, float grad_scale, void* stream);
+/* the same with bf16 gradients: the data-parallel path all-reduces a bf16 copy of the gradient span (train.py:91-96 under DDP) */
+int mapdit_adam_step_g16(float* p, const void* g_bf16, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                         float bias_corr1, float bias_corr2, float grad_scale, void* stream);
 
 /* N3, device-side CustomDataset.__getitem__ (train.py:168-176): out[n] = ((means[idx[n]] + eps[n]*stds[idx[n]]) - ch_mean[c]) / ch_std[c];
  * means/stds [items, C, H*W] resident in HBM, idx int64 [n], eps/out [n, C, H*W] */
@@ -155,6 +161,9 @@ int mapdit_mp_silu_fwd(const void* x, void* y, int64_t n, int in_dtype, int out_
 int mapdit_qk_normalize(void* qkv, int m, int d, int head_dim, float eps, int dtype, void* stream);
 /* dtype casts */
 int mapdit_cast(const void* src, void* dst, int64_t n, int src_dtype, int dst_dtype, void* stream);
+/* the same for a [rows, cols] window of row-major matrices with leading dimensions ld_src / ld_dst */
+int mapdit_cast_2d(const void* src, int64_t ld_src, void* dst, int64_t ld_dst, int rows, int cols, int src_dtype, int dst_dtype,
+                   void* stream);
 
 /* ---- K4: cosine attention --------------------------------------------------------------------
  * o[M, D] = merge_heads(softmax(q^ k^T / sqrt(hd)) v) for qkv[M, 3D] whose q,k heads are already

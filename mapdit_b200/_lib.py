@@ -26,6 +26,9 @@ class GemmArgs(C.Structure):
 SIGNATURES = {
     "mapdit_weight_norm_fwd": [_p, _i, _i, _f, _i, _p, _p, _p, _i64, _p, _p],
     "mapdit_weight_norm_bwd": [_p, _p, _p, _i, _i, _f, _i, _p],
+    "mapdit_weight_norm_bwd_multi": [_p, _i, _i, _f, _p],
+    "mapdit_adam_step_g16": [_p, _p, _p, _p, _i64, _f, _f, _f, _f, _f, _f, _f, _p],
+    "mapdit_cast_2d": [_p, _i64, _p, _i64, _i, _i, _i, _i, _p],
     "mapdit_weight_norm_fwd_multi": [_p, _i, _i, _i, _f, _i, _p, _p],
     "mapdit_gemm_f32": [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i, _i, _i, _i, _p],
     "mapdit_gemm_bf16": [C.POINTER(GemmArgs), _p],

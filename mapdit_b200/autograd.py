@@ -53,6 +53,12 @@ class Trainer:
         self._side = None      # the second stream
         self._side_on = False  # active inside the current backward
         self._side_reads = {}  # scratch buffer name -> event recorded after the side-stream GEMM that last read it
+        self._wn_pending = []  # (param, grad buffer holding d(effective weight)) awaiting the multi-tensor weight-norm backward
+        self._wn_tables = {}   # pointer signature -> ops.WeightNormBwdBatch (device-resident descriptor table)
+        # the saved activations live in ONE workspace per (batch, mode, device): a second train-mode forward overwrites what the
+        # first one saved.  Every forward stamps the workspace; a backward whose stamp is stale raises instead of returning
+        # gradients of the wrong activations (the reference's autograd keeps both graphs alive).
+        self._generation = 0
 
     # ------------------------------------------------------------------ buffers
     def buffers(self, N, mode, dev):
@@ -91,7 +97,7 @@ class Trainer:
             dc=torch.empty(N, D, **f), dcs=torch.empty(N, D, **f), dab=torch.empty(N, D, **f), dt1s=torch.empty(N, D, **f),
             P=torch.empty(M, K1, **f), R32=torch.empty(M, D, **f) if mode == "bf16" else None,
             dmods16=torch.empty(N, W, device=dev, dtype=torch.bfloat16) if mode == "bf16" else None,
-            dWs=torch.empty(max(Hm * D, W * D), **f),  # scratch for d(effective weight), largest weight
+            dWs=torch.empty(D * max(D, 256, K1), **f),  # d(effective weight) scratch of the small fp32 conditioning-path weights
         )
         if m.modulation != "adaln":  # (cos, sin) tables for the EPI_RESID_ROT epilogue (see Engine.workspace)
             B["rotcs"] = torch.empty(N, L * 2 * D, **f)
@@ -105,22 +111,35 @@ class Trainer:
     def forward(self, x, t, y, drop_mask):
         prev = ops.set_variant(self.m.variant)
         try:
-            return self._forward(x, t, y, drop_mask)
+            with torch.cuda.device(x.device):  # kernels launch on the current device's stream: make it the tensors' device
+                out, saved = self._forward(x, t, y, drop_mask)
+            self._generation += 1
+            B = self.buffers(saved["N"], saved["mode"], saved["dev"])
+            B["generation"] = saved["generation"] = self._generation
+            return out, saved
         finally:
             ops.set_variant(prev)
 
     def backward(self, saved, dout):
+        B = self.buffers(saved["N"], saved["mode"], saved["dev"])
+        if B.get("generation") != saved.get("generation"):
+            raise RuntimeError(
+                "mapdit_b200: backward through a DiT forward whose saved activations were overwritten by a later train-mode "
+                "forward of the same batch size (one forward may be outstanding per model and batch size; run forward -> "
+                "backward pairs, or concatenate the inputs into one batch)")
         prev = ops.set_variant(self.m.variant)
         self._side_on = bool(self.wgrad_stream and saved["mode"] == "bf16")
         if self._side_on and (self._side is None or self._side.device != saved["dev"]):
             self._side = torch.cuda.Stream(device=saved["dev"])
         try:
-            out = self._backward(saved, dout)
-            self._join_side()  # every gradient is complete on the caller's stream
+            with torch.cuda.device(saved["dev"]):
+                out = self._backward(saved, dout)
+                self._join_side()  # every gradient is complete on the caller's stream
             return out
         finally:
             self._side_on = False
             self._side_reads.clear()
+            self._wn_pending = []
             ops.set_variant(prev)
 
     def _forward(self, x, t, y, drop_mask):
@@ -285,27 +304,53 @@ class Trainer:
     def _wgrad(self, dy, xin, param, bf, B, grads, reads=None):
         """param.grad = weight_norm_bwd(forced param, dy^T @ xin).  `reads` names the scratch buffer `dy` lives in: with the
         second stream active the caller must call _before_write(name) before the main stream overwrites that buffer."""
-        n_out, k_in = param.shape
-        dW = B["dWs"][: n_out * k_in].view(n_out, k_in)
         g = self._gbuf(param)
+        grads[id(param)] = g
+        # the GEMM writes d(effective weight) straight into the gradient buffer; _flush_wn turns every pending buffer of a block
+        # into d(raw weight) in ONE in-place multi-tensor launch (was a scratch buffer + one weight_norm_bwd launch per weight)
+        batched = self.m.flags["use_weight_normalization"] and ops.WeightNormBwdBatch.supports(param.data, g)
         if self._side_on:
             main = torch.cuda.current_stream()
             ev = torch.cuda.Event()
             ev.record(main)
-            self._side.wait_event(ev)  # dy (and every earlier main-stream use of the dWs scratch) is complete
+            self._side.wait_event(ev)  # dy is complete
             with torch.cuda.stream(self._side):
-                ops.gemm_bf16_tn(dy, xin, dW)
-                grads[id(param)] = self._wn_bwd(param, dW, g)
+                ops.gemm_bf16_tn(dy, xin, g)
+                if batched:
+                    self._wn_pending.append((param, g))
+                elif self.m.flags["use_weight_normalization"]:
+                    ops.weight_norm_bwd(param.data, g.clone(), g)
                 if reads is not None:
                     done = torch.cuda.Event()
                     done.record(self._side)
                     self._side_reads[reads] = done
             return
         if bf:
-            ops.gemm_bf16_tn(dy, xin, dW)
+            ops.gemm_bf16_tn(dy, xin, g)
         else:
-            ops.gemm_f32(dy, xin, out=dW, trans_a=True, trans_b=True)
-        grads[id(param)] = self._wn_bwd(param, dW, g)
+            ops.gemm_f32(dy, xin, out=g, trans_a=True, trans_b=True)
+        if batched:
+            self._wn_pending.append((param, g))
+        elif self.m.flags["use_weight_normalization"]:
+            ops.weight_norm_bwd(param.data, g.clone(), g)
+
+    def _flush_wn(self):
+        """weight-norm backward of every pending weight gradient, in place, one launch (on the stream the GEMMs ran on)"""
+        if not self._wn_pending:
+            return
+        items = [(p.data, g) for p, g in self._wn_pending]
+        self._wn_pending = []
+        sig = tuple(t.data_ptr() for it in items for t in it)
+        tab = self._wn_tables.get(sig)
+        if tab is None:
+            if len(self._wn_tables) > 256:  # autograd path: fresh gradient tensors every call
+                self._wn_tables.clear()
+            tab = self._wn_tables[sig] = ops.WeightNormBwdBatch(items, items[0][0].device)
+        if self._side_on:
+            with torch.cuda.stream(self._side):
+                tab.run()
+        else:
+            tab.run()
 
     def _before_write(self, name):
         """main stream is about to overwrite scratch buffer `name`: wait for the side-stream GEMM that still reads it"""
@@ -429,6 +474,7 @@ class Trainer:
             grads[id(p)] = self._wn_bwd(p, dW)
         hF, xF = B["h1"][L], B["xin"][L]
         self._wgrad(B["dlin"], hF, f.linear.weight, bf, B, grads)
+        self._flush_wn()
         self._dgrad(B["dlin"], W.wfl, getattr(W, "wfl_t", None), dh, bf)
         if ln:
             ops.ln_modulate_bwd(dh, xF, R, B["ln1"][L], mods[:, fbase + D:], dmods[:, fbase:], dmods[:, fbase + D:], ld, N, T, False)
@@ -474,6 +520,15 @@ class Trainer:
             self._wgrad(dqkv, h1, blk[i].attn.qkv_proj.weight, bf, B, grads, reads="dqkv")
             self._dgrad(dqkv, W.wqkv[i], wt("wqkv_t"), dh, bf)
             modulate_block_bwd(i, "a", dh, xin, True, then_resid=(i - 1, "m") if (fuse_resid and i > 0) else None)
+            # block i's modulation vectors have their final gradient: its modulation-weight gradient now (not in one GEMM over
+            # all blocks after the loop), so it rides in the block's all-reduce bucket and overlaps the rest of the backward
+            sl = slice(i * lay["width"], (i + 1) * lay["width"])
+            if bf:
+                ops.cast_2d(dmods[:, sl], B["dmods16"][:, sl])
+                self._wgrad(B["dmods16"][:, sl], B["cs16"], blk[i].modulation[1].weight, bf, B, grads)
+            else:
+                self._wgrad(dmods[:, sl], B["cs"], blk[i].modulation[1].weight, bf, B, grads)
+            self._flush_wn()
             if self.grad_hook is not None:
                 pairs = [(p, grads[id(p)]) for p in blk[i].parameters() if id(p) in grads]
                 if self._side_on:  # the block's weight gradients complete on the second stream: fire the hook (NCCL) there
@@ -490,21 +545,16 @@ class Trainer:
         dWx = B["dWs"][: D * K1].view(D, K1)
         ops.patch_embed_wgrad(R, saved["x"], dWx, m.patch_size, 0.5 / 0.7071067811865476 if fl["use_mp_pos_enc"] else 1.0)
         grads[id(m.x_embedder.weight)] = self._wn_bwd(m.x_embedder.weight, dWx)
-        # ---- modulation GEMM of all blocks + final (one wgrad / dgrad over the concatenated weight)
-        Wtot = dmods.shape[1]
-        dWm = B["dWs"][: Wtot * D].view(Wtot, D)
+        # ---- modulation GEMM: one dgrad over the concatenated weight of all blocks + final layer (the blocks' weight gradients
+        # were taken inside the loop), the final layer's weight gradient
         if bf:
-            ops.cast(dmods, B["dmods16"])
+            ops.cast_2d(dmods[:, fbase:], B["dmods16"][:, fbase:])
             ops.gemm_bf16(B["dmods16"], W.wmod_t, B["dcs"])
-            ops.gemm_bf16_tn(B["dmods16"], B["cs16"], dWm)
+            self._wgrad(B["dmods16"][:, fbase:], B["cs16"], f.modulation[1].weight, bf, B, grads)
         else:
             ops.gemm_f32(dmods, W.wmod, out=B["dcs"], trans_b=True)
-            ops.gemm_f32(dmods, B["cs"], out=dWm, trans_a=True, trans_b=True)
-        for i in range(L):
-            p = blk[i].modulation[1].weight
-            grads[id(p)] = self._wn_bwd(p, dWm[i * lay["width"]:(i + 1) * lay["width"]])
-        p = f.modulation[1].weight
-        grads[id(p)] = self._wn_bwd(p, dWm[fbase:])
+            self._wgrad(dmods[:, fbase:], B["cs"], f.modulation[1].weight, bf, B, grads)
+        self._flush_wn()
         # ---- conditioning path (src/dit.py:86-88)
         ops.cond_combine_bwd(B["c"], B["dc"], B["dcs"], B["dab"])
         table = m.y_embedder.embedding.weight
@@ -521,7 +571,8 @@ class Trainer:
         dW = B["dWs"][: D * 256].view(D, 256)
         ops.gemm_f32(B["dt1s"], B["e"], out=dW, trans_a=True, trans_b=True)
         grads[id(p1)] = self._wn_bwd(p1, dW)
+        self._join_side()  # the final layer's modulation-weight gradient ran on the second stream
         if self.grad_hook is not None:
-            done = {id(q) for b_ in blk for q in b_.parameters() if q is not b_.modulation[1].weight}
+            done = {id(q) for b_ in blk for q in b_.parameters()}
             self.grad_hook([(q, grads[id(q)]) for q in m.parameters() if id(q) not in done])
         return [grads[id(p)] for p in m.parameters()]

@@ -374,6 +374,54 @@ extern "C" int mapdit_weight_norm_bwd(const float* v, const float* g_eff, float*
   return MAPDIT_OK;
 }
 
+// Multi-tensor, IN-PLACE flavour: the weight-gradient GEMMs write d(effective weight) straight into the gradient buffers and one
+// launch per block turns all of them into d(raw weight) (was one launch per weight: 66 per DiT-B/2 step).  One warp per row; a
+// row is read twice (dot products, then the projection) and each element is overwritten by the thread that read it.
+struct WnBwdItem {
+  const float* v;
+  float* g;
+  long long rows, cols, group0;  // group0 = first 8-row group of this tensor in the launch
+};
+__global__ void __launch_bounds__(256) weight_norm_bwd_multi_kernel(const WnBwdItem* __restrict__ table, int n_items, float eps) {
+  int it = 0;
+  while (it + 1 < n_items && (long long)blockIdx.x >= table[it + 1].group0) ++it;
+  const WnBwdItem t = table[it];
+  const long long r = ((long long)blockIdx.x - t.group0) * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= t.rows) return;
+  const int cols = (int)t.cols;
+  const float4* v4 = reinterpret_cast<const float4*>(t.v + r * cols);
+  float4* g4 = reinterpret_cast<float4*>(t.g + r * cols);
+  float ss = 0.f, dot = 0.f;
+#pragma unroll 4
+  for (int i = lane; i < cols / 4; i += 32) {
+    const float4 a = v4[i], b = g4[i];
+    ss = __fmaf_rn(a.x, a.x, ss);
+    ss = __fmaf_rn(a.y, a.y, ss);
+    ss = __fmaf_rn(a.z, a.z, ss);
+    ss = __fmaf_rn(a.w, a.w, ss);
+    dot = __fmaf_rn(a.x, b.x, dot);
+    dot = __fmaf_rn(a.y, b.y, dot);
+    dot = __fmaf_rn(a.z, b.z, dot);
+    dot = __fmaf_rn(a.w, b.w, dot);
+  }
+  const float rn = sqrtf(warp_sum(ss));
+  dot = warp_sum(dot);
+  const float inv = 1.0f / (rn + eps);
+  const float coef = dot / (fmaxf(rn, 1e-30f) * (rn + eps));
+#pragma unroll 4
+  for (int i = lane; i < cols / 4; i += 32) {
+    const float4 a = v4[i], b = g4[i];
+    g4[i] = make_float4((b.x - a.x * coef) * inv, (b.y - a.y * coef) * inv, (b.z - a.z * coef) * inv, (b.w - a.w * coef) * inv);
+  }
+}
+extern "C" int mapdit_weight_norm_bwd_multi(const void* table, int n_items, int n_groups, float eps, void* stream) {
+  MAPDIT_REQUIRE(table && n_items > 0 && n_groups > 0, "weight_norm_bwd_multi: bad args");
+  weight_norm_bwd_multi_kernel<<<n_groups, 256, 0, (cudaStream_t)stream>>>((const WnBwdItem*)table, n_items, eps);
+  MAPDIT_LAUNCH_CHECK("weight_norm_bwd_multi");
+  return MAPDIT_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // K3 standalone: modulate, residual, mp_silu, qk-normalise, casts
 // ------------------------------------------------------------------------------------------------
@@ -465,6 +513,33 @@ extern "C" int mapdit_cast(const void* src, void* dst, int64_t n, int src_dtype,
   else if (src_dtype == MAPDIT_F32) cast_kernel<float, float><<<grid, 256, 0, s>>>((const float*)src, (float*)dst, n);
   else cast_kernel<bf16, bf16><<<grid, 256, 0, s>>>((const bf16*)src, (bf16*)dst, n);
   MAPDIT_LAUNCH_CHECK("cast");
+  return MAPDIT_OK;
+}
+
+// strided 2-D cast (a column slice of a [rows, ld] matrix): the per-block slices of the modulation-vector gradients
+template <typename TI, typename TO>
+__global__ void cast2d_kernel(const TI* __restrict__ x, int64_t ldx, TO* __restrict__ y, int64_t ldy, int64_t rows, int cols) {
+  const int64_t total = rows * cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cols;
+    const int c = (int)(i - r * cols);
+    st_act(y + r * ldy + c, ld_act(x + r * ldx + c));
+  }
+}
+extern "C" int mapdit_cast_2d(const void* src, int64_t ld_src, void* dst, int64_t ld_dst, int rows, int cols, int src_dtype,
+                              int dst_dtype, void* stream) {
+  MAPDIT_REQUIRE(src && dst && rows > 0 && cols > 0 && ld_src >= cols && ld_dst >= cols, "cast_2d: bad args");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int grid = ew_grid((int64_t)rows * cols);
+  if (src_dtype == MAPDIT_F32 && dst_dtype == MAPDIT_BF16)
+    cast2d_kernel<float, bf16><<<grid, 256, 0, s>>>((const float*)src, ld_src, (bf16*)dst, ld_dst, rows, cols);
+  else if (src_dtype == MAPDIT_BF16 && dst_dtype == MAPDIT_F32)
+    cast2d_kernel<bf16, float><<<grid, 256, 0, s>>>((const bf16*)src, ld_src, (float*)dst, ld_dst, rows, cols);
+  else if (src_dtype == MAPDIT_F32)
+    cast2d_kernel<float, float><<<grid, 256, 0, s>>>((const float*)src, ld_src, (float*)dst, ld_dst, rows, cols);
+  else
+    cast2d_kernel<bf16, bf16><<<grid, 256, 0, s>>>((const bf16*)src, ld_src, (bf16*)dst, ld_dst, rows, cols);
+  MAPDIT_LAUNCH_CHECK("cast_2d");
   return MAPDIT_OK;
 }
 

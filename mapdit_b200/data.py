@@ -103,7 +103,10 @@ def adam_state_dict(train_step):
         n = p.numel()
         state[i] = {"step": torch.tensor(float(ts.step_count)), "exp_avg": ts.flat_m[lo:lo + n].view(p.shape).clone(),
                     "exp_avg_sq": ts.flat_v[lo:lo + n].view(p.shape).clone()}
-    group = dict(lr=ts.lr, betas=tuple(ts.betas), eps=ts.eps, weight_decay=0, amsgrad=False, maximize=False, foreach=None,
+    # under the reference's LambdaLR (train.py:66,104) "lr" is the already-scheduled value of the NEXT step and the base value
+    # lives in "initial_lr"; without a schedule torch writes no "initial_lr"
+    cur = ts.lr * (ts.lr_lambda(ts.step_count) if ts.lr_lambda is not None else 1.0)
+    group = dict(lr=cur, **({"initial_lr": ts.lr} if ts.lr_lambda is not None else {}), betas=tuple(ts.betas), eps=ts.eps, weight_decay=0, amsgrad=False, maximize=False, foreach=None,
                  capturable=False, differentiable=False, fused=None, decoupled_weight_decay=False, params=list(range(len(params))))
     return {"state": state if ts.step_count > 0 else {}, "param_groups": [group]}
 
@@ -120,7 +123,8 @@ def load_adam_state_dict(train_step, sd):
         ts.flat_v[lo:lo + n].copy_(st["exp_avg_sq"].reshape(-1))
         ts.step_count = int(st["step"])
     g = sd["param_groups"][0]
-    ts.lr, ts.betas, ts.eps = g["lr"], tuple(g["betas"]), g["eps"]
+    # base learning rate: LambdaLR keeps it in "initial_lr" ("lr" is already multiplied by the schedule factor)
+    ts.lr, ts.betas, ts.eps = g.get("initial_lr", g["lr"]), tuple(g["betas"]), g["eps"]
 
 
 def save_checkpoint(path, model, train_step=None, compiled_prefix=True):

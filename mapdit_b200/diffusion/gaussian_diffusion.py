@@ -267,8 +267,15 @@ class GaussianDiffusion:
         cfg_scale = float(model_kwargs["cfg_scale"]) if uses_cfg else None
         N = img.shape[0]
         dev = img.device
-        key = (id(dit), N, tuple(img.shape), str(dev), uses_cfg, cfg_scale, bool(clip_denoised), dit.compute_dtype, dit.training, ddim_eta)
+        # the captured graph bakes in raw pointers of parameters and buffers (gains, embedding table, pos_embed, the engine's
+        # weight buffers): the key carries them, so re-pointed parameters (TrainStep's flat span, .to(), a recycled id()) miss
+        ptrs = tuple(p.data_ptr() for p in dit.parameters()) + tuple(b.data_ptr() for b in dit.buffers())
+        key = (id(dit), ptrs, N, tuple(img.shape), str(dev), uses_cfg, cfg_scale, bool(clip_denoised), dit.compute_dtype, dit.training,
+               ddim_eta)
         st = self._graphs.get(key)
+        if st is None:  # drop stale graphs of the same model object (their pointers are dead)
+            for k in [k for k in self._graphs if k[0] == id(dit) and k[1] != ptrs]:
+                del self._graphs[k]
         tab = self.device_tables(dev)
         with th.no_grad():
             if st is None:
@@ -392,11 +399,82 @@ class GaussianDiffusion:
                 yield out
                 img = out["sample"]
 
-    def ddim_reverse_sample(self, *a, **k):
-        self._off_path("ddim_reverse_sample")
+    # ------------------------------------------------------------------ evaluation helpers (never called by the reference scripts)
+    # Thin host-side passthroughs: the model call and p_mean_variance run on the kernels, the handful of
+    # [N, C, H, W] elementwise expressions around them are plain tensor arithmetic — these are not on the hot path.
+    def _coef(self, table, t, like):
+        """table[t] broadcast against `like` (gaussian_diffusion.py:861-873)"""
+        v = th.from_numpy(np.asarray(table)).to(device=t.device)[t.long()].float()
+        return v.view(-1, *([1] * (like.dim() - 1)))
 
-    def calc_bpd_loop(self, *a, **k):
-        self._off_path("calc_bpd_loop")
+    def condition_score(self, cond_fn, p_mean_var, x, t, model_kwargs=None):
+        """gaussian_diffusion.py:358-374: guidance applied to the predicted epsilon (Song et al.)"""
+        abar = self._coef(self.alphas_cumprod, t, x)
+        x0 = p_mean_var["pred_xstart"]
+        eps = (self._coef(self.sqrt_recip_alphas_cumprod, t, x) * x - x0) / self._coef(self.sqrt_recipm1_alphas_cumprod, t, x)
+        eps = eps - (1 - abar).sqrt() * cond_fn(x, t, **(model_kwargs or {}))
+        out = dict(p_mean_var)
+        out["pred_xstart"] = self._coef(self.sqrt_recip_alphas_cumprod, t, x) * x - self._coef(self.sqrt_recipm1_alphas_cumprod, t, x) * eps
+        out["mean"] = (self._coef(self.posterior_mean_coef1, t, x) * out["pred_xstart"] + self._coef(self.posterior_mean_coef2, t, x) * x)
+        return out
+
+    def ddim_reverse_sample(self, model, x, t, clip_denoised=True, denoised_fn=None, cond_fn=None, model_kwargs=None, eta=0.0):
+        """gaussian_diffusion.py:562-598: one step of the deterministic DDIM ODE run forwards, x_t -> x_{t+1}"""
+        assert eta == 0.0, "Reverse ODE only for deterministic path"
+        out = self.p_mean_variance(model, x, t, clip_denoised=clip_denoised, denoised_fn=denoised_fn, model_kwargs=model_kwargs)
+        if cond_fn is not None:
+            out = self.condition_score(cond_fn, out, x, t, model_kwargs=model_kwargs)
+        x0 = out["pred_xstart"]
+        eps = (self._coef(self.sqrt_recip_alphas_cumprod, t, x) * x - x0) / self._coef(self.sqrt_recipm1_alphas_cumprod, t, x)
+        abar_next = self._coef(self.alphas_cumprod_next, t, x)
+        return {"sample": x0 * abar_next.sqrt() + (1 - abar_next).sqrt() * eps, "pred_xstart": x0}
+
+    def _vb_terms_bpd(self, model, x_start, x_t, t, clip_denoised=True, model_kwargs=None):
+        """gaussian_diffusion.py:682-713 -> dict(output [N] in bits, pred_xstart): KL(q(x_{t-1}|x_t,x_0) || p) or, at t == 0, the
+        discretised-Gaussian decoder NLL (diffusion_utils.py:10-36,62-88)"""
+        out = self.p_mean_variance(model, x_t, t, clip_denoised=clip_denoised, model_kwargs=model_kwargs)
+        q_mean = self._coef(self.posterior_mean_coef1, t, x_t) * x_start + self._coef(self.posterior_mean_coef2, t, x_t) * x_t
+        q_logvar = self._coef(self.posterior_log_variance_clipped, t, x_t)
+        p_mean, p_logvar = out["mean"], out["log_variance"]
+        kl = 0.5 * (-1.0 + p_logvar - q_logvar + th.exp(q_logvar - p_logvar) + (q_mean - p_mean) ** 2 * th.exp(-p_logvar))
+        kl = kl.flatten(1).mean(1) / np.log(2.0)
+        # decoder NLL of x_start under N(p_mean, exp(p_logvar)) discretised to 256 bins on [-1, 1]
+        cdf = lambda v: 0.5 * (1.0 + th.tanh(np.sqrt(2.0 / np.pi) * (v + 0.044715 * v ** 3)))
+        centered, inv_std = x_start - p_mean, th.exp(-0.5 * p_logvar)
+        cdf_plus, cdf_min = cdf(inv_std * (centered + 1.0 / 255.0)), cdf(inv_std * (centered - 1.0 / 255.0))
+        log_probs = th.where(x_start < -0.999, th.log(cdf_plus.clamp(min=1e-12)),
+                             th.where(x_start > 0.999, th.log((1.0 - cdf_min).clamp(min=1e-12)),
+                                      th.log((cdf_plus - cdf_min).clamp(min=1e-12))))
+        nll = -log_probs.flatten(1).mean(1) / np.log(2.0)
+        return {"output": th.where(t == 0, nll, kl), "pred_xstart": out["pred_xstart"]}
+
+    def _prior_bpd(self, x_start):
+        """gaussian_diffusion.py:789-804: KL(q(x_T | x_0) || N(0, I)) in bits per dimension"""
+        t = th.full((x_start.shape[0],), self.num_timesteps - 1, device=x_start.device, dtype=th.long)
+        mean = self._coef(self.sqrt_alphas_cumprod, t, x_start) * x_start
+        logvar = self._coef(self.log_one_minus_alphas_cumprod, t, x_start)
+        kl = 0.5 * (-1.0 - logvar + th.exp(logvar) + mean ** 2)
+        return kl.flatten(1).mean(1) / np.log(2.0)
+
+    def calc_bpd_loop(self, model, x_start, clip_denoised=True, model_kwargs=None):
+        """gaussian_diffusion.py:806-858 -> dict(total_bpd [N], prior_bpd [N], vb / xstart_mse / mse [N, T])"""
+        x_start = x_start.float()
+        n = x_start.shape[0]
+        vb, xstart_mse, mse = [], [], []
+        for i in range(self.num_timesteps - 1, -1, -1):
+            t = th.full((n,), i, device=x_start.device, dtype=th.long)
+            noise = _randn_like(x_start)
+            x_t = self.q_sample(x_start, t, noise=noise)
+            with th.no_grad():
+                out = self._vb_terms_bpd(model, x_start, x_t, t, clip_denoised=clip_denoised, model_kwargs=model_kwargs)
+            vb.append(out["output"])
+            xstart_mse.append(((out["pred_xstart"] - x_start) ** 2).flatten(1).mean(1))
+            eps = ((self._coef(self.sqrt_recip_alphas_cumprod, t, x_t) * x_t - out["pred_xstart"])
+                   / self._coef(self.sqrt_recipm1_alphas_cumprod, t, x_t))
+            mse.append(((eps - noise) ** 2).flatten(1).mean(1))
+        vb, xstart_mse, mse = th.stack(vb, dim=1), th.stack(xstart_mse, dim=1), th.stack(mse, dim=1)
+        prior = self._prior_bpd(x_start)
+        return {"total_bpd": vb.sum(dim=1) + prior, "prior_bpd": prior, "vb": vb, "xstart_mse": xstart_mse, "mse": mse}
 
 
 class _ModelWrapperBase:

@@ -75,6 +75,9 @@ class SpacedDiffusion(GaussianDiffusion):
     def condition_mean(self, cond_fn, *args, **kwargs):
         return super().condition_mean(self._wrap_model(cond_fn), *args, **kwargs)
 
+    def condition_score(self, cond_fn, *args, **kwargs):
+        return super().condition_score(self._wrap_model(cond_fn), *args, **kwargs)
+
     def _timestep_for_model(self, i):
         return self.timestep_map[i]
 

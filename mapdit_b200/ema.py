@@ -111,6 +111,11 @@ class EMA:
         for std in self.emas:
             tab, n = self._table(std, model)
             ops.multi_lerp(tab, n, float(calc_beta(std, t)))
+            # the copy's parameters moved through raw pointers (no version bump): drop its cached effective weights, or
+            # later eval forwards / graphed sampling loops of the copy would keep using the old normalised weights
+            eng = getattr(self.emas[std], "_engine", None)
+            if eng is not None:
+                eng.invalidate()
 
     @torch.no_grad()
     def save_snapshot(self, t):

@@ -184,7 +184,8 @@ class Engine:
         if torch.is_grad_enabled() and any(p.requires_grad for p in m.parameters()) and train:
             from .autograd import dit_forward_autograd
             return dit_forward_autograd(self, x, t, y, drop_mask)
-        return self._forward_impl(x, t, y, train, drop_mask, mode, save=None)
+        with torch.cuda.device(x.device):  # kernels launch on the current device's stream: make it the tensors' device
+            return self._forward_impl(x, t, y, train, drop_mask, mode, save=None)
 
     def _forward_impl(self, x, t, y, train, drop_mask, mode, save):
         prev = ops.set_variant(self.m.variant)

@@ -72,6 +72,28 @@ def weight_norm_bwd(v, g_eff, grad_v, accumulate=False):
           "weight_norm_bwd")
 
 
+class WeightNormBwdBatch:
+    """descriptor table for mapdit_weight_norm_bwd_multi: `items` = [(v, g)], g = d(effective weight) on entry, d(v) on return"""
+
+    def __init__(self, items, device):
+        rows_tab, g0 = [], 0
+        for v, g in items:
+            rows, cols = v.shape
+            assert v.dtype == g.dtype == torch.float32 and v.is_contiguous() and g.is_contiguous() and g.shape == v.shape
+            assert cols % 4 == 0 and v.data_ptr() % 16 == 0 and g.data_ptr() % 16 == 0
+            rows_tab.append([v.data_ptr(), g.data_ptr(), rows, cols, g0])
+            g0 += (rows + 7) // 8
+        self.table = torch.tensor(rows_tab, dtype=torch.int64).to(device)
+        self.n, self.groups = len(rows_tab), g0
+
+    @staticmethod
+    def supports(v, g):
+        return v.dim() == 2 and v.shape[1] % 4 == 0 and v.is_contiguous() and g.is_contiguous() and v.data_ptr() % 16 == 0 and g.data_ptr() % 16 == 0
+
+    def run(self):
+        check(lib().mapdit_weight_norm_bwd_multi(_ptr(self.table), self.n, self.groups, EPS, _stream()), "weight_norm_bwd_multi")
+
+
 def gemm_f32(a, b, out=None, trans_a=False, trans_b=False, accumulate=False):
     """out[m,n] (+)= sum_k A(m,k) B(n,k).  a is [m,k] (or [k,m] with trans_a), b is [n,k] (or [k,n] with
     trans_b); 2-D fp32 with arbitrary strides."""
@@ -133,6 +155,14 @@ def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0):
                                  1.0 - beta1 ** step, 1.0 - beta2 ** step, float(grad_scale), _stream()), "adam_step")
 
 
+def adam_step_g16(p, g16, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0):
+    """adam_step with the gradient span in bf16 (the all-reduced copy of the data-parallel path)"""
+    n = p.numel()
+    assert g16.dtype == torch.bfloat16 and g16.numel() == n and p.is_contiguous() and g16.is_contiguous()
+    check(lib().mapdit_adam_step_g16(_ptr(p), _ptr(g16), _ptr(m), _ptr(v), n, float(lr), float(beta1), float(beta2), float(eps),
+                                     1.0 - beta1 ** step, 1.0 - beta2 ** step, float(grad_scale), _stream()), "adam_step_g16")
+
+
 def multi_lerp(chunk_table, n_chunks, weight):
     check(lib().mapdit_multi_lerp(_ptr(chunk_table), n_chunks, float(weight), _stream()), "multi_lerp")
 
@@ -186,6 +216,13 @@ def qk_normalize(qkv, d, head_dim):
 
 def cast(src, dst):
     check(lib().mapdit_cast(_ptr(src), _ptr(dst), src.numel(), _dt(src), _dt(dst), _stream()), "cast")
+
+
+def cast_2d(src, dst):
+    """dst[r, c] = src[r, c] for 2-D views with unit column stride (column slices of wider matrices)"""
+    assert src.dim() == 2 and src.shape == dst.shape and src.stride(1) == 1 and dst.stride(1) == 1
+    check(lib().mapdit_cast_2d(_ptr(src), src.stride(0), _ptr(dst), dst.stride(0), src.shape[0], src.shape[1], _dt(src), _dt(dst),
+                               _stream()), "cast_2d")
 
 
 def cos_attn(qkv, o, n_samples, tokens, heads, head_dim, lse=None):

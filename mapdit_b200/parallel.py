@@ -36,10 +36,16 @@ class GradReducer:
 
     `slices[i] = (lo, hi)` are contiguous regions of `flat`, ordered as the backward finishes them.  `ready(i)`
     launches the async all-reduce (SUM) of bucket i; `finish()` launches whatever is left and waits for all of
-    them, after which `flat` holds the sum over ranks (the optimiser applies the 1/world factor)."""
+    them, after which `flat` holds the sum over ranks (the optimiser applies the 1/world factor).
 
-    def __init__(self, flat: torch.Tensor, slices, group=None):
+    With `compressed` (a second flat buffer of the same length, e.g. bf16) and `compress(src_slice, dst_slice)`, each bucket
+    is first copied into `compressed` on the current stream and THAT slice is all-reduced: afterwards `compressed` holds the
+    rank sum and `flat` keeps the local gradient."""
+
+    def __init__(self, flat: torch.Tensor, slices, group=None, compressed=None, compress=None):
         self.flat, self.slices, self.group = flat, list(slices), group
+        self.compressed, self.compress = compressed, compress
+        assert compressed is None or (compressed.numel() == flat.numel() and compress is not None)
         self._works, self._done = [], set()
 
     def start_step(self):
@@ -51,7 +57,11 @@ class GradReducer:
             return
         lo, hi = self.slices[i]
         if hi > lo:
-            self._works.append(dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            buf = self.flat[lo:hi]
+            if self.compressed is not None:
+                self.compress(buf, self.compressed[lo:hi])
+                buf = self.compressed[lo:hi]
+            self._works.append(dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
         self._done.add(i)
 
     def finish(self):

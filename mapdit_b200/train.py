@@ -14,9 +14,13 @@ from .parallel import GradReducer
 
 
 class TrainStep:
-    def __init__(self, model, diffusion, lr=1e-2, betas=(0.9, 0.99), eps=1e-8, world_size=1, lr_lambda=None, ema=None):
+    def __init__(self, model, diffusion, lr=1e-2, betas=(0.9, 0.99), eps=1e-8, world_size=1, lr_lambda=None, ema=None,
+                 grad_reduce_dtype=None):
         """`lr_lambda(step)` multiplies `lr` like the reference's LambdaLR (train.py:66,104: the k-th optimiser step, 0-based,
-        uses lr * lr_lambda(k)); `ema` (mapdit_b200.ema.EMA) is updated after every step like train.py:105."""
+        uses lr * lr_lambda(k)); `ema` (mapdit_b200.ema.EMA) is updated after every step like train.py:105.
+        `grad_reduce_dtype`: "bf16" (default when world_size > 1; MAPDIT_GRAD_REDUCE overrides) all-reduces a bf16 copy of each
+        gradient bucket — half the NVLink bytes and half the SM time NCCL takes from the backward GEMMs — and Adam reads the
+        reduced bf16 gradients with fp32 moments / parameters; "fp32" reduces the fp32 span in place."""
         self.model, self.diffusion = model, diffusion
         self.lr, self.betas, self.eps = lr, betas, eps
         self.lr_lambda, self.ema = lr_lambda, ema
@@ -24,11 +28,11 @@ class TrainStep:
         self.step_count = 0
         m = model
         dev = next(m.parameters()).device
-        # flat layout: blocks in reverse (minus their modulation weights), then all modulation weights, then the rest
+        # flat layout: blocks in reverse (the order the backward finishes them; a block's modulation weight included: its
+        # gradient is taken inside the block loop), then the embedders / final layer
         groups = []
         for b in reversed(list(m.blocks)):
-            groups.append([p for p in b.parameters() if p is not b.modulation[1].weight])
-        groups.append([b.modulation[1].weight for b in m.blocks])
+            groups.append(list(b.parameters()))
         seen = {id(p) for g in groups for p in g}
         groups.append([p for p in m.parameters() if id(p) not in seen])
         pad = lambda n: (n + 63) // 64 * 64  # every parameter starts 256-byte aligned (vectorised kernels, TMA)
@@ -54,47 +58,77 @@ class TrainStep:
             for p in g:
                 self._group_of[id(p)] = gi
         model.engine.invalidate()
-        self.reducer = GradReducer(self.flat_g, self.slices)
+        import os
+        if grad_reduce_dtype is None:
+            grad_reduce_dtype = os.environ.get("MAPDIT_GRAD_REDUCE", "bf16")
+        assert grad_reduce_dtype in ("bf16", "fp32")
+        self.flat_g16 = None
+        if world_size > 1 and grad_reduce_dtype == "bf16":
+            self.flat_g16 = torch.zeros(total, device=dev, dtype=torch.bfloat16)
+        self.reducer = GradReducer(self.flat_g, self.slices, compressed=self.flat_g16,
+                                   compress=(lambda src, dst: ops.cast(src, dst)) if self.flat_g16 is not None else None)
 
     # gradient hook from the backward: every parameter in `pairs` has its final gradient -> reduce finished buckets.
-    # The last two buckets (all modulation weights; embedders/final layer) only complete at the very end.
+    # The last bucket (embedders / final layer, ~1 % of the span) only completes at the very end.
     def _on_grads(self, pairs):
         for gi in sorted({self._group_of[id(p)] for p, _ in pairs}):
-            if gi < len(self.slices) - 2:
+            if gi < len(self.slices) - 1:
                 self.reducer.ready(gi)
+
+    def compute_grads(self, x, t, y, noise=None, drop_mask=None, loss_divisor=None, reduce=True):
+        """q_sample -> forward -> loss -> backward (-> all-reduce) of the local batch into the flat gradient span `flat_g`
+        (train.py:86-95); returns the per-sample losses [N].  `loss_divisor` (default: the local batch size, i.e. loss.mean())
+        is what the per-sample losses are divided by before the backward — shard gradients taken with the GLOBAL batch size
+        add up to the full-batch gradient."""
+        m, d = self.model, self.diffusion
+        assert m.training, "TrainStep needs model.train() (forced weight normalisation + label dropout)"
+        with torch.cuda.device(x.device):
+            tr = m.engine.trainer
+            tr.grad_buffers = self.grad_views
+            tr.grad_hook = self._on_grads if reduce else None
+            try:
+                self.reducer.start_step()
+                x0 = x.contiguous().float()
+                tl = t.contiguous().long()
+                if noise is None:
+                    noise = torch.randn_like(x0)
+                noise = noise.contiguous().float()
+                N = x0.shape[0]
+                tab = d.device_tables(x0.device)
+                x_t = torch.empty_like(x0)
+                ops.q_sample(x0, noise, tl, tab, x_t)
+                t_model = d._map_tensor(tl.device, tl.dtype)[tl] if hasattr(d, "_map_tensor") else tl
+                with torch.no_grad():
+                    out, saved = tr.forward(x_t, t_model, y, drop_mask)
+                    loss = torch.empty(N, device=x0.device)
+                    dout = torch.empty_like(out)
+                    gs = torch.full((N,), 1.0 / (loss_divisor or N), device=x0.device)
+                    ops.loss_fwd_bwd(out, x0, x_t, noise, tl, tab, loss, None, None, dout, gs, gs)
+                    tr.backward(saved, dout)
+                    if reduce:
+                        self.reducer.finish()
+            finally:
+                tr.grad_buffers = None
+                tr.grad_hook = None
+        return loss
+
+    def apply_grads(self):
+        """one fused Adam launch over the flat span (train.py:96,104: optimizer.step(); scheduler.step()), then the EMA hook"""
+        with torch.cuda.device(self.flat_p.device), torch.no_grad():
+            lr = self.lr * (self.lr_lambda(self.step_count) if self.lr_lambda is not None else 1.0)
+            self.step_count += 1
+            if self.flat_g16 is not None:
+                ops.adam_step_g16(self.flat_p, self.flat_g16, self.flat_m, self.flat_v, lr, self.betas[0], self.betas[1], self.eps,
+                                  self.step_count, grad_scale=1.0 / self.world)
+            else:
+                ops.adam_step(self.flat_p, self.flat_g, self.flat_m, self.flat_v, lr, self.betas[0], self.betas[1], self.eps,
+                              self.step_count, grad_scale=1.0 / self.world)
+            self.model.engine.invalidate()  # parameters moved through raw pointers: cached effective weights are stale
+            if self.ema is not None:
+                self.ema.update(self.step_count, self.model)
 
     def step(self, x, t, y, noise=None, drop_mask=None):
         """one optimisation step on the local batch; returns the mean loss (device scalar)"""
-        m, d = self.model, self.diffusion
-        assert m.training, "TrainStep needs model.train() (forced weight normalisation + label dropout)"
-        tr = m.engine.trainer
-        tr.grad_buffers = self.grad_views
-        tr.grad_hook = self._on_grads
-        self.reducer.start_step()
-        x0 = x.contiguous().float()
-        tl = t.contiguous().long()
-        if noise is None:
-            noise = torch.randn_like(x0)
-        noise = noise.contiguous().float()
-        N = x0.shape[0]
-        tab = d.device_tables(x0.device)
-        x_t = torch.empty_like(x0)
-        ops.q_sample(x0, noise, tl, tab, x_t)
-        t_model = d._map_tensor(tl.device, tl.dtype)[tl] if hasattr(d, "_map_tensor") else tl
-        with torch.no_grad():
-            out, saved = tr.forward(x_t, t_model, y, drop_mask)
-            loss = torch.empty(N, device=x0.device)
-            dout = torch.empty_like(out)
-            gs = torch.full((N,), 1.0 / N, device=x0.device)
-            ops.loss_fwd_bwd(out, x0, x_t, noise, tl, tab, loss, None, None, dout, gs, gs)
-            tr.backward(saved, dout)
-            self.reducer.finish()
-            lr = self.lr * (self.lr_lambda(self.step_count) if self.lr_lambda is not None else 1.0)
-            self.step_count += 1
-            ops.adam_step(self.flat_p, self.flat_g, self.flat_m, self.flat_v, lr, self.betas[0], self.betas[1], self.eps,
-                          self.step_count, grad_scale=1.0 / self.world)
-            if self.ema is not None:
-                self.ema.update(self.step_count, m)
-        tr.grad_buffers = None
-        tr.grad_hook = None
+        loss = self.compute_grads(x, t, y, noise, drop_mask)
+        self.apply_grads()
         return loss.mean()

@@ -42,12 +42,7 @@ def proj_vec(shape, seed):
     return torch.from_numpy(np.random.default_rng(seed).standard_normal(shape)).double()
 
 
-def inputs(cfg, B, seed):
-    g = np.random.default_rng(seed)
-    x = torch.from_numpy(g.standard_normal((B, cfg.in_channels, cfg.input_size, cfg.input_size), dtype=np.float32))
-    t = torch.from_numpy(g.integers(0, 1000, size=(B,))).long()
-    y = torch.from_numpy(g.integers(0, cfg.num_classes, size=(B,))).long()
-    return x, t, y
+inputs = O.seeded_inputs  # (x, t, y) from numpy PCG64: platform stable, so large cases store the seed instead of the tensors
 
 
 def eval_case(tag, name, B, seed):
@@ -77,15 +72,16 @@ def cfg_case(tag, name, B, seed, scale):
     print(tag, out.shape)
 
 
-def train_case(tag, name, B, seed):
-    """One reference training forward/backward (train.py:86-95 without the optimiser)."""
+def train_case(tag, name, B, seed, store_inputs=True):
+    """One reference training forward/backward (train.py:86-95 without the optimiser).  `store_inputs=False` (large batches)
+    keeps x / noise out of the fixture: tests regenerate them with O.seeded_inputs / O.seeded_noise from the stored seed."""
     from diffusion import create_diffusion
     cfg = O.config_for(name)
     sd = O.init_state_dict(cfg, seed=seed)
     m = ref_model(name, cfg, sd).train()
     x, t, y = inputs(cfg, B, seed + 100)
     t[0] = 0  # exercise the decoder-NLL branch
-    noise = torch.from_numpy(np.random.default_rng(seed + 200).standard_normal(x.shape, dtype=np.float32))
+    noise = O.seeded_noise(x.shape, seed + 200)
     torch.manual_seed(seed + 300)
     drop = torch.rand(B) < cfg.class_dropout_prob
     drop[1] = True
@@ -99,9 +95,11 @@ def train_case(tag, name, B, seed):
         terms["loss"].mean().backward()
     finally:
         le.torch.rand = real_rand
-    rec = dict(name=name, seed=seed, x=x.numpy(), t=t.numpy(), y=y.numpy(), noise=noise.numpy(), drop=drop.numpy(),
+    rec = dict(name=name, seed=seed, batch=B, t=t.numpy(), y=y.numpy(), drop=drop.numpy(),
                loss=terms["loss"].detach().numpy(), mse=terms["mse"].detach().numpy(), vb=terms["vb"].detach().numpy(),
-               wsum=checksum(sd))
+               wsum=checksum(sd), xsum=float(x.double().abs().sum()), nsum=float(noise.double().abs().sum()))
+    if store_inputs:
+        rec.update(x=x.numpy(), noise=noise.numpy())
     names, stats = [], []
     for i, (k, p) in enumerate(m.named_parameters()):
         g = p.grad.double()
@@ -170,6 +168,39 @@ def diffusion_case(tag):
             rec[f"dd_x0_eta{eta}_clip{int(clip)}"] = out["pred_xstart"].numpy()
     np.savez_compressed(os.path.join(OUT, f"{tag}.npz"), **rec)
     print(tag, "ok")
+
+
+def eval_helpers_case(tag):
+    """Reference calc_bpd_loop (gaussian_diffusion.py:806-858) and ddim_reverse_sample (:562-598) on a synthetic model output."""
+    from diffusion import create_diffusion
+    import diffusion.gaussian_diffusion as gd
+    g = np.random.default_rng(23)
+    B = 5
+    x0 = torch.from_numpy(g.standard_normal((B, 4, 8, 8), dtype=np.float32)).clamp(-1.3, 1.3)
+    x0[0, 0, 0, :4] = torch.tensor([-1.0, 1.0, 0.9995, -0.9995])
+    mo = torch.from_numpy(g.standard_normal((B, 8, 8, 8), dtype=np.float32))
+    d10 = create_diffusion(timestep_respacing="10")
+    noises = [torch.from_numpy(g.standard_normal((B, 4, 8, 8), dtype=np.float32)) for _ in range(10)]
+    rec = dict(x0=x0.numpy(), mo=mo.numpy(), noises=np.stack([n.numpy() for n in noises]))
+    for clip in (True, False):
+        it = iter(noises)
+        real = gd.th.randn_like
+        gd.th.randn_like = lambda x: next(it)
+        try:
+            out = d10.calc_bpd_loop(lambda *a, **k: mo, x0, clip_denoised=clip)
+        finally:
+            gd.th.randn_like = real
+        for k, v in out.items():
+            rec[f"bpd_{k}_clip{int(clip)}"] = v.numpy()
+    d25 = create_diffusion(timestep_respacing="ddim25")
+    t25 = torch.tensor([0, 1, 7, 12, 24])
+    rec["rev_t"] = t25.numpy()
+    for clip in (True, False):
+        out = d25.ddim_reverse_sample(lambda *a, **k: mo, x0, t25, clip_denoised=clip)
+        rec[f"rev_sample_clip{int(clip)}"] = out["sample"].numpy()
+        rec[f"rev_x0_clip{int(clip)}"] = out["pred_xstart"].numpy()
+    np.savez_compressed(os.path.join(OUT, f"{tag}.npz"), **rec)
+    print(tag, "ok", rec["bpd_total_bpd_clip1"])
 
 
 def loop_case(tag, name, B, seed, steps, use_cfg):
@@ -270,7 +301,12 @@ if __name__ == "__main__":
     torch.set_num_threads(8)
     if len(sys.argv) > 1:  # regenerate selected fixtures only: python oracle/make_golden.py ema
         for a in sys.argv[1:]:
-            {"ema": lambda: ema_case("ema")}[a]()
+            {"ema": lambda: ema_case("ema"),
+             # the bench path's kernels (256 tokens: fused tcgen05 attention backward; 80 x 256 rows: every block GEMM of
+             # DiT-XS/2 qualifies for the cta_group::2 kernel), one t == 0 and one dropped label
+             "train_xs2_b80": lambda: train_case("train_xs2_b80", "DiT-XS/2", 80, 9, store_inputs=False),
+             "eval_b2": lambda: eval_case("eval_b2", "DiT-B/2", 2, 10),
+             "eval_helpers": lambda: eval_helpers_case("eval_helpers")}[a]()
         sys.exit(0)
     eval_case("eval_xs8", "DiT-XS/8", 3, 1)
     eval_case("eval_s4", "DiT-S/4", 2, 2)
@@ -282,3 +318,6 @@ if __name__ == "__main__":
     loop_case("loop_xs8", "DiT-XS/8", 2, 7, 6, False)
     loop_case("loop_xs4_cfg", "DiT-XS/4", 1, 8, 5, True)
     ema_case("ema")
+    train_case("train_xs2_b80", "DiT-XS/2", 80, 9, store_inputs=False)
+    eval_case("eval_b2", "DiT-B/2", 2, 10)
+    eval_helpers_case("eval_helpers")

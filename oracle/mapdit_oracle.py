@@ -572,6 +572,33 @@ def training_losses(T: DiffusionTables, model_fn: Callable, x0, t, noise):
 # --------------------------------------------------------------------------------------
 # training step (reference: train.py:86-96) — used by the CPU baseline and grad-parity tests
 # --------------------------------------------------------------------------------------
+def seeded_inputs(cfg: DiTConfig, B: int, seed: int):
+    """(x, t, y) of the golden fixtures (oracle/make_golden.py) from numpy's PCG64 stream — platform stable, so fixtures of
+    large batches store the seed instead of the tensors"""
+    g = np.random.default_rng(seed)
+    x = torch.from_numpy(g.standard_normal((B, cfg.in_channels, cfg.input_size, cfg.input_size), dtype=np.float32))
+    t = torch.from_numpy(g.integers(0, 1000, size=(B,))).long()
+    y = torch.from_numpy(g.integers(0, cfg.num_classes, size=(B,))).long()
+    return x, t, y
+
+
+def seeded_noise(shape, seed: int) -> torch.Tensor:
+    return torch.from_numpy(np.random.default_rng(seed).standard_normal(tuple(shape), dtype=np.float32))
+
+
+def golden_train_inputs(g, cfg: DiTConfig):
+    """(x, t, y, noise, drop) of a train_* fixture: stored tensors, or regenerated from the stored seed (checked by checksum)"""
+    t, y, drop = (torch.from_numpy(g[k]) for k in ("t", "y", "drop"))
+    if "x" in g.files:
+        return torch.from_numpy(g["x"]), t, y, torch.from_numpy(g["noise"]), drop
+    seed, B = int(g["seed"]), int(g["batch"])
+    x = seeded_inputs(cfg, B, seed + 100)[0]
+    noise = seeded_noise(x.shape, seed + 200)
+    assert abs(float(x.double().abs().sum()) - float(g["xsum"])) <= 1e-9 * float(g["xsum"]), "input generator drifted"
+    assert abs(float(noise.double().abs().sum()) - float(g["nsum"])) <= 1e-9 * float(g["nsum"]), "noise generator drifted"
+    return x, t, y, noise, drop
+
+
 def make_params(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
     out = {}
     for k, v in sd.items():

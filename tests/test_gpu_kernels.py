@@ -238,3 +238,64 @@ def test_diffusion_step_and_loss(dev):
         gd._randn_like = real
     xt = d.q_sample(x0, torch.from_numpy(g["tl_t"]).to(dev), noise=noise)
     assert rel_l2(xt.cpu(), O.q_sample(T, x0.cpu(), torch.from_numpy(g["tl_t"]), noise.cpu())) < 1e-6
+
+
+def test_calc_bpd_loop_and_ddim_reverse_sample_vs_reference_golden(dev):
+    """gaussian_diffusion.py:806-858 / :562-598 of the unmodified reference on a synthetic model output (oracle/make_golden.py
+    eval_helpers_case): host passthroughs over the p_mean_variance / q_sample kernels"""
+    import os
+    from conftest import GOLDEN
+    from mapdit_b200 import create_diffusion
+    from mapdit_b200.diffusion import gaussian_diffusion as gd
+    g = np.load(os.path.join(GOLDEN, "eval_helpers.npz"))
+    x0, mo = torch.from_numpy(g["x0"]).to(dev), torch.from_numpy(g["mo"]).to(dev)
+    d10 = create_diffusion("10")
+    real = gd._randn_like
+    try:
+        for clip in (1, 0):
+            it = iter(torch.from_numpy(g["noises"]).to(dev))
+            gd._randn_like = lambda x: next(it)
+            out = d10.calc_bpd_loop(lambda *a, **k: mo, x0, clip_denoised=bool(clip))
+            for k in ("total_bpd", "prior_bpd", "vb", "xstart_mse", "mse"):
+                e = rel_l2(out[k].cpu(), g[f"bpd_{k}_clip{clip}"])
+                assert e < 2e-5, (k, clip, e)
+    finally:
+        gd._randn_like = real
+    d25 = create_diffusion("ddim25")
+    t25 = torch.from_numpy(g["rev_t"]).to(dev)
+    for clip in (1, 0):
+        out = d25.ddim_reverse_sample(lambda *a, **k: mo, x0, t25, clip_denoised=bool(clip))
+        assert rel_l2(out["sample"].cpu(), g[f"rev_sample_clip{clip}"]) < 2e-6
+        assert rel_l2(out["pred_xstart"].cpu(), g[f"rev_x0_clip{clip}"]) < 1e-6
+
+
+def test_multi_tensor_weight_norm_bwd_cast2d_and_bf16_grad_adam(dev):
+    from mapdit_b200 import ops
+    # in-place multi-tensor weight-norm backward == the single-tensor kernel, tensor by tensor
+    shapes = [(2304, 768), (768, 768), (3072, 768), (768, 3072), (4608, 768), (13, 64)]
+    vs = [rnd(r, c, seed=10 + i) for i, (r, c) in enumerate(shapes)]
+    gs = [rnd(r, c, seed=30 + i) for i, (r, c) in enumerate(shapes)]
+    want = []
+    for v, g in zip(vs, gs):
+        o = torch.empty_like(v)
+        ops.weight_norm_bwd(v, g, o)
+        want.append(o)
+    inplace = [g.clone() for g in gs]
+    ops.WeightNormBwdBatch(list(zip(vs, inplace)), dev).run()
+    for a, b in zip(inplace, want):
+        assert rel_l2(a, b) < 1e-6
+    # strided 2-D cast of a column window
+    src = rnd(37, 500, seed=3)
+    dst = torch.zeros(37, 640, device=dev, dtype=torch.bfloat16)
+    ops.cast_2d(src[:, 100:356], dst[:, 8:264])
+    assert torch.equal(dst[:, 8:264], src[:, 100:356].bfloat16()) and float(dst[:, :8].abs().sum()) == 0 and float(dst[:, 264:].abs().sum()) == 0
+    # Adam with bf16 gradients == Adam with the same gradients widened to fp32 (odd length: scalar tail)
+    n = 4099
+    p0, g32 = rnd(n, seed=5), rnd(n, seed=6)
+    g16 = g32.bfloat16()
+    pa, ma, va = p0.clone(), torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+    pb, mb, vb = p0.clone(), torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+    for step in (1, 2, 3):
+        ops.adam_step(pa, g16.float(), ma, va, 1e-2, 0.9, 0.99, 1e-8, step, grad_scale=0.5)
+        ops.adam_step_g16(pb, g16, mb, vb, 1e-2, 0.9, 0.99, 1e-8, step, grad_scale=0.5)
+    assert torch.equal(pa, pb) and torch.equal(ma, mb) and torch.equal(va, vb)

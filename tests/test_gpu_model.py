@@ -28,7 +28,7 @@ def build(name, seed, dtype, **kw):
     return m.cuda().eval(), cfg, sd
 
 
-@pytest.mark.parametrize("tag", ["eval_xs8", "eval_s4", "eval_xs2"])
+@pytest.mark.parametrize("tag", ["eval_xs8", "eval_s4", "eval_xs2", "eval_b2"])
 @pytest.mark.parametrize("dtype,tol", [("fp32", FP32_TOL), ("bf16", BF16_FWD_TOL)])
 def test_forward_vs_reference_golden(tag, dtype, tol):
     g = load(tag)

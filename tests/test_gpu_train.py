@@ -82,11 +82,14 @@ def _run_train(name, seed, dtype, x, t, y, noise, drop):
     return m, terms, cfg, sd
 
 
-@pytest.mark.parametrize("tag", ["train_xs8", "train_xs4"])
+@pytest.mark.parametrize("tag", ["train_xs8", "train_xs4", "train_xs2_b80"])
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
 def test_training_step_gradients(tag, dtype):
+    """train_xs2_b80 is the bench path in small: 256 tokens (attn_tc2 + the fused tcgen05 attention backward), 80 x 256 rows so that
+    every block GEMM qualifies for the cta_group::2 kernel, weight gradients on the second stream; one t == 0, one dropped label.
+    Reference: train.py:86-95 on the unmodified reference (oracle/make_golden.py)."""
     g = np.load(os.path.join(GOLDEN, tag + ".npz"))
-    x, t, y, noise, drop = (torch.from_numpy(g[k]) for k in ("x", "t", "y", "noise", "drop"))
+    x, t, y, noise, drop = O.golden_train_inputs(g, O.config_for(str(g["name"])))
     m, terms, cfg, sd = _run_train(str(g["name"]), int(g["seed"]), dtype, x, t, y, noise, drop)
     ltol = 2e-5 if dtype == "fp32" else 3e-2
     for k in ("loss", "mse", "vb"):
@@ -387,3 +390,162 @@ def test_thirty_training_steps_follow_the_oracle_loss_curve(modulation, first, l
     assert abs(losses[0] - first) < 3e-2 * first
     assert abs(losses[-1] - last) < tol_last  # rotation_scaling measured on B200: 0.5069, the whole curve within 1e-3 of the oracle's
     assert all(torch.isfinite(p).all() for p in m.parameters())
+
+
+@pytest.mark.parametrize("wgrad_stream", [True, False])
+def test_full_size_backward_equals_sum_of_shard_gradients(wgrad_stream):
+    """The benchmark size (DiT-B/2, batch 256, bf16; the CPU oracle is too slow there): the gradient span of one 256-sample
+    TrainStep backward equals the sum of the eight 32-sample shard backwards taken with the same 1/256 loss weight.  Covers what
+    the small reference-pinned cases cannot: the second-stream weight gradients and their event protocol (`_before_write`), split-K
+    weight gradients at 65,536 rows, the per-block modulation-weight gradients and the multi-tensor weight-norm backward.  The
+    32-sample path is the one tied to the reference by test_training_step_gradients[train_xs2_b80]."""
+    import mapdit_b200 as M
+    from mapdit_b200.train import TrainStep
+    torch.manual_seed(0)
+    m = M.DIT_MODELS["DiT-B/2"](in_channels=4, input_size=32, num_classes=1000)
+    with torch.no_grad():
+        for prm in m.parameters():
+            if prm.dim() == 0:
+                prm.fill_(0.3)
+        m.final_layer.sigma_scale.reference.normal_()
+    m = m.cuda().train()
+    m.engine.trainer.wgrad_stream = wgrad_stream
+    ts = TrainStep(m, M.create_diffusion(""))
+    g = torch.Generator().manual_seed(9)
+    B, S = 256, 32
+    x, noise = torch.randn(B, 4, 32, 32, generator=g).cuda(), torch.randn(B, 4, 32, 32, generator=g).cuda()
+    t, y = torch.randint(0, 1000, (B,), generator=g).cuda(), torch.randint(0, 1000, (B,), generator=g).cuda()
+    t[0] = 0
+    drop = (torch.rand(B, generator=g) < 0.1).cuda()
+    ts.compute_grads(x[:S], t[:S], y[:S], noise[:S], drop[:S])  # the first train-mode forward writes the forced normalisation back
+    loss_full = ts.compute_grads(x, t, y, noise, drop).clone()
+    g_full = ts.flat_g.clone()
+    again = ts.compute_grads(x, t, y, noise, drop)
+    assert torch.equal(again, loss_full)
+    acc, losses = torch.zeros_like(g_full, dtype=torch.float64), []
+    for s in range(B // S):
+        sl = slice(s * S, (s + 1) * S)
+        losses.append(ts.compute_grads(x[sl], t[sl], y[sl], noise[sl], drop[sl], loss_divisor=B).clone())
+        acc += ts.flat_g.double()
+    torch.cuda.synchronize()
+    assert torch.isfinite(g_full).all() and float(g_full.abs().max()) > 0
+    assert rel_l2(torch.cat(losses), loss_full) < 1e-6  # per-sample results do not depend on the batch they sit in
+    worst = ("", 0.0)
+    for name, prm in m.named_parameters():
+        lo, n = ts.offset_of[id(prm)], prm.numel()
+        e = rel_l2(g_full[lo:lo + n], acc[lo:lo + n])
+        worst = max(worst, (name, e), key=lambda v: v[1])
+        assert e < 2e-3, (name, e)
+    print(f"DiT-B/2 B=256 wgrad_stream={wgrad_stream}: worst per-parameter |full - sum of shards| rel-L2 = {worst[1]:.2e} ({worst[0]})")
+
+
+def test_two_outstanding_forwards_raise_instead_of_returning_wrong_gradients():
+    """the saved activations of a train-mode forward live in one workspace per batch size: a backward through an overwritten
+    forward must fail loudly"""
+    import mapdit_b200 as M
+    m = M.DIT_MODELS["DiT-XS/8"](in_channels=4, input_size=32, num_classes=10).cuda().train()
+    x, t, y = rnd(2, 4, 32, 32, seed=1), torch.tensor([3, 500]).cuda(), torch.tensor([1, 2]).cuda()
+    a = m(x, t, y)
+    b = m(x * 0.5, t, y)
+    with pytest.raises(RuntimeError, match="overwritten"):
+        a.sum().backward()
+    b.sum().backward()  # the latest forward is intact
+    assert all(p.grad is not None for p in m.parameters())
+
+
+def test_ema_copy_forward_follows_updates_and_graph_cache_follows_repointed_parameters(tmp_path):
+    """(1) EMA.update writes the copies through raw pointers: their cached effective weights must be dropped (ADVICE r1);
+    (2) TrainStep re-points every parameter into its flat span: a sampling graph captured before must not be replayed."""
+    import copy
+    import mapdit_b200 as M
+    from mapdit_b200.ema import EMA
+    from mapdit_b200.train import TrainStep
+    torch.manual_seed(1)
+    m = M.DIT_MODELS["DiT-XS/8"](in_channels=4, input_size=32, num_classes=10).cuda().eval()
+    with torch.no_grad():
+        for prm in m.parameters():
+            if prm.dim() == 0:
+                prm.fill_(0.3)
+    e = EMA(m, str(tmp_path), stds=[0.05])
+    x, t, y = rnd(2, 4, 32, 32, seed=2), torch.tensor([30, 700]).cuda(), torch.tensor([1, 2]).cuda()
+    with torch.no_grad():
+        before = e.emas[0.05](x, t, y).clone()
+        for prm in m.parameters():
+            prm.add_(torch.randn_like(prm) * 0.5)
+        e.update(2, m)
+        after = e.emas[0.05](x, t, y).clone()
+        fresh = copy.deepcopy(e.emas[0.05])
+        want = fresh(x, t, y)
+    assert not torch.equal(before, after)
+    assert torch.equal(after, want)
+    # graph cache
+    d = M.create_diffusion("3")
+    z = rnd(2, 4, 32, 32, seed=3)
+    from mapdit_b200.diffusion import gaussian_diffusion as gd
+    noises = [rnd(2, 4, 32, 32, seed=10 + k) for k in range(3)]
+
+    def sample(model):
+        it = iter(noises)
+        real = gd._randn_like
+        gd._randn_like = lambda v: next(it)
+        try:
+            return d.p_sample_loop(model.forward, z.shape, z, model_kwargs=dict(y=y), device="cuda").clone()
+        finally:
+            gd._randn_like = real
+    s0 = sample(m)
+    m.train()
+    ts = TrainStep(m, M.create_diffusion(""))  # re-points the parameters into the flat span
+    with torch.no_grad():
+        ts.flat_p.mul_(1.0)
+        m.blocks[0].attn.qkv_proj.weight.add_(torch.randn_like(m.blocks[0].attn.qkv_proj.weight))
+    m.eval()
+    s1 = sample(m)
+    ref = copy.deepcopy(m)
+    s2 = sample(ref)
+    assert not torch.equal(s0, s1)
+    assert torch.equal(s1, s2)
+
+
+def test_adam_state_dict_interoperates_with_torch_lambda_lr():
+    """an UNMODIFIED torch.optim.Adam + LambdaLR state dict (train.py:57,66): 'lr' is the scheduled value, 'initial_lr' the base"""
+    import mapdit_b200 as M
+    from mapdit_b200 import data
+    from mapdit_b200.train import TrainStep
+    lam = data.create_lr_lambda(10, 20)
+    m = M.DIT_MODELS["DiT-XS/8"](in_channels=4, input_size=32, num_classes=10).cuda().train()
+    plist = [torch.nn.Parameter(p.detach().cpu().clone()) for p in m.parameters()]
+    opt = torch.optim.Adam(plist, lr=3e-3, betas=(0.9, 0.99))
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lam)
+    for _ in range(4):
+        for p in plist:
+            p.grad = torch.ones_like(p)
+        opt.step()
+        sched.step()
+    ts = TrainStep(m, M.create_diffusion(""), lr=1.0, lr_lambda=lam)
+    data.load_adam_state_dict(ts, opt.state_dict())
+    assert ts.step_count == 4 and abs(ts.lr - 3e-3) < 1e-12
+    assert abs(ts.lr * lam(ts.step_count) - opt.param_groups[0]["lr"]) < 1e-12  # the next step uses torch's scheduled value
+    sd = data.adam_state_dict(ts)
+    assert abs(sd["param_groups"][0]["initial_lr"] - 3e-3) < 1e-12 and abs(sd["param_groups"][0]["lr"] - opt.param_groups[0]["lr"]) < 1e-12
+    opt2 = torch.optim.Adam(plist, lr=7.0)
+    opt2.load_state_dict({"state": {i: {k: v.cpu() for k, v in st.items()} for i, st in sd["state"].items()}, "param_groups": sd["param_groups"]})
+    assert abs(opt2.param_groups[0]["lr"] - opt.param_groups[0]["lr"]) < 1e-12
+
+
+def test_two_rank_data_parallel_matches_single_process():
+    """tools/dp_check.py under torchrun on 2 GPUs (NCCL): two TrainStep steps on batch shards (bf16 bucketed all-reduce) == the
+    same two steps on the concatenated batch in one process, replicas bit-identical, batch-sharded sampling == unsharded."""
+    import json
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29577", os.path.join(root, "tools", "dp_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    print(r.stdout[-2000:], r.stderr[-2000:])
+    assert r.returncode == 0 and lines, r.stderr[-2000:]
+    res = json.loads(lines[-1])
+    assert res["replicas_bit_identical"] and res["train_param_rel_l2_worst"] < 2e-3 and res["sample_rel_l2"] < 1e-5

@@ -99,9 +99,7 @@ def test_off_path_entry_points_say_so():
     import mapdit_b200 as M
     d = M.create_diffusion("ddim25")
     with pytest.raises(NotImplementedError):
-        d.ddim_reverse_sample(None, None, None)
-    with pytest.raises(NotImplementedError):
-        d.calc_bpd_loop(None, None)
+        d.ddim_sample(None, torch.zeros(1, 4, 8, 8), torch.zeros(1).long(), cond_fn=lambda *a, **k: None)
     with pytest.raises(NotImplementedError):
         M.create_diffusion("", predict_xstart=True).training_losses(None, torch.zeros(1, 4, 8, 8), torch.zeros(1).long())
 

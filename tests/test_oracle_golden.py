@@ -20,7 +20,7 @@ def wsum(sd):
     return float(sum(v.double().abs().sum().item() for v in sd.values()))
 
 
-@pytest.mark.parametrize("tag", ["eval_xs8", "eval_s4", "eval_xs2"])
+@pytest.mark.parametrize("tag", ["eval_xs8", "eval_s4", "eval_xs2", "eval_b2"])
 def test_eval_forward(tag):
     g = load(tag)
     cfg = O.config_for(str(g["name"]))
@@ -49,15 +49,14 @@ def test_state_dict_contract():
     assert n == 32_855_849
 
 
-@pytest.mark.parametrize("tag", ["train_xs8", "train_xs4"])
+@pytest.mark.parametrize("tag", ["train_xs8", "train_xs4", "train_xs2_b80"])
 def test_train_step_grads(tag):
     g = load(tag)
     cfg = O.config_for(str(g["name"]))
     p = O.make_params(O.init_state_dict(cfg, seed=int(g["seed"])))
     T = O.make_tables("")
-    terms, grads = O.train_step_grads(p, cfg, T, torch.from_numpy(g["x"]), torch.from_numpy(g["t"]),
-                                      torch.from_numpy(g["y"]), torch.from_numpy(g["noise"]),
-                                      drop_mask=torch.from_numpy(g["drop"]))
+    x, t, y, noise, drop = O.golden_train_inputs(g, cfg)
+    terms, grads = O.train_step_grads(p, cfg, T, x, t, y, noise, drop_mask=drop)
     for k in ("loss", "mse", "vb"):
         assert rel_l2(terms[k].detach(), g[k]) < 1e-5, k
     names = [str(s) for s in g["grad_names"]]

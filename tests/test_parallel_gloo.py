@@ -40,6 +40,16 @@ def _worker(rank, world, port, out):
     red2.start_step()
     red2.finish()
     ok &= bool(torch.allclose(g_local / world, torch.full((4,), (world - 1) / 2)))
+    # compressed reduction (TrainStep's bf16 gradient all-reduce): the rank sum lands in the bf16 copy, the fp32 span keeps
+    # the local gradient; values chosen exactly representable in bf16
+    loc = torch.arange(64, dtype=torch.float32) * (rank + 1)
+    c16 = torch.zeros(64, dtype=torch.bfloat16)
+    red3 = GradReducer(loc, [(32, 64), (0, 32)], compressed=c16, compress=lambda a, b: b.copy_(a))
+    red3.start_step()
+    red3.ready(0)
+    red3.finish()
+    ok &= bool(torch.equal(c16.float(), torch.arange(64, dtype=torch.float32) * sum(r + 1 for r in range(world))))
+    ok &= bool(torch.equal(loc, torch.arange(64, dtype=torch.float32) * (rank + 1)))
     # final gather is rank-major
     s = gather_samples(torch.full((2, 3), float(rank)))
     ok &= s.shape == (2 * world, 3) and bool((s[:2] == 0).all()) and bool((s[2:4] == 1).all())
