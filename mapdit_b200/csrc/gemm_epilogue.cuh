@@ -329,6 +329,204 @@ __device__ __forceinline__ void run_tile(const EpiParams& ep, const EpiTmaps& tm
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------------
+// Fused residual epilogues, second generation (2-CTA kernel, tokens % 32 == 0 so that a warp's 32 rows lie in one sample).
+//
+// What bounded the first generation (15-17 k cycles per 256 x 256 tile against a 6-9 k main loop, the MMA warp idle
+// on its accumulator stages) and what replaces it:
+//   * the three per-sample vectors of a chunk (gate | shift | scale, or gate | (cos, sin) | scale) were read by every lane from
+//     global memory right before use: three exposed L2 round trips per 32-column chunk.  Now each warp stages the vectors of its
+//     whole column half ONCE per tile in shared memory, already multiplied by the warp-uniform constants, before it waits for
+//     the accumulator — the loads overlap the main loop and the chunk loop reads them back as broadcast 16-byte loads;
+//   * up to three TMA stores per chunk rotated through two staging buffers, so every chunk waited for a store issued moments
+//     earlier.  Now no buffer is reused within a chunk: three rotating buffers receive the residual tile by TMA and are
+//     overwritten in place with x' (the lane that read a row writes it back) and stored from there; aux and h have their own
+//     buffer each; every wait is for a store issued a whole chunk earlier;
+//   * the residual for chunk c+1 is requested at the start of chunk c.
+// The arithmetic (and therefore every output bit) is the same as run_tile's.
+constexpr int FR_XBUFS = 3;
+constexpr int FR_BUF_BYTES_PER_WARP = (FR_XBUFS + 2) * 2048;
+__host__ __device__ constexpr int fr_vec_bytes_per_warp(int bn) { return 3 * (bn / 2) * 4; }
+__host__ __device__ constexpr int fr_bytes(int bn) { return 8 * (FR_BUF_BYTES_PER_WARP + fr_vec_bytes_per_warp(bn)); }
+
+__device__ __forceinline__ void bulk_wait_read(int k) {  // k warp-uniform, 0..3
+  if (k <= 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  else if (k == 1) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+  else if (k == 2) asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
+  else asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"((uint64_t)map), "r"(smem_u32(smem_src)),
+               "r"(c0), "r"(c1)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
+struct FusedResid {
+  uint8_t* bufs;   // this warp's (FR_XBUFS + 2) x 2 KB: X[0..2] residual landing + x' staging, then aux, then h
+  float* vec;      // this warp's 3 x (BN/2) floats
+  uint64_t* bars;  // this warp's FR_XBUFS mbarriers (count 1)
+  uint32_t issued, consumed;
+  int lane;
+
+  __device__ __forceinline__ void drain() {
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    __syncwarp();
+  }
+};
+
+template <int BN, typename WaitFn>
+__device__ __forceinline__ void run_tile_fused_resid(const EpiParams& ep, const EpiTmaps& tm, FusedResid& fr, uint32_t t_row, int row0,
+                                                     int n_blk, int half, float gsc, float inv_den, WaitFn wait_acc) {
+  constexpr int CSPAN = BN / 2, NCHUNK = CSPAN / 32;
+  const int lane = fr.lane;
+  const int col0 = n_blk * BN + half * CSPAN;
+  const bool mod = ep.epilogue == MAPDIT_EPI_RESID_MOD, rot = ep.epilogue == MAPDIT_EPI_RESID_ROT;
+  const bool has_h = mod || rot, has_aux = ep.aux != nullptr;
+  const int groups = 1 + (has_h ? 1 : 0) + (has_aux ? 1 : 0);  // TMA stores committed per chunk
+  const long long sample = row0 < ep.M ? row0 / ep.tokens : 0;
+  const bool plain_res = ep.variant & MAPDIT_VAR_PLAIN_RESID;
+  const float res_a = plain_res ? 1.0f : (1.0f - MP_RES_T) / MP_RES_DEN, res_b = plain_res ? 1.0f : MP_RES_T / MP_RES_DEN;
+  const float mod_a = (1.0f - gsc) * inv_den, mod_b = gsc * inv_den;
+  uint8_t* abuf = fr.bufs + FR_XBUFS * 2048;
+  uint8_t* hbuf = abuf + 2048;
+  const int sw = (lane >> 1) & 3;
+
+  // ---- (1) this tile's per-sample vectors -> shared memory, constants folded in (v0 = gate b; MOD: v1 = scale (1-g)/den,
+  // v2 = shift g/den; ROT: v1 = (cos, sin) pairs, v2 = scale or 1)
+  __syncwarp();  // every lane is done reading the previous tile's vectors
+#pragma unroll
+  for (int i = lane; i < CSPAN / 4; i += 32) {
+    const int col = col0 + 4 * i;
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f), v1 = g, v2 = g;
+    if (col < ep.N) {
+      g = *reinterpret_cast<const float4*>(ep.gate + sample * ep.ldmod + col);
+      g.x *= res_b; g.y *= res_b; g.z *= res_b; g.w *= res_b;
+      if (mod) {
+        v1 = *reinterpret_cast<const float4*>(ep.scale + sample * ep.ldmod + col);
+        v2 = *reinterpret_cast<const float4*>(ep.shift + sample * ep.ldmod + col);
+        v1.x *= mod_a; v1.y *= mod_a; v1.z *= mod_a; v1.w *= mod_a;
+        v2.x *= mod_b; v2.y *= mod_b; v2.z *= mod_b; v2.w *= mod_b;
+      } else if (rot) {
+        v1 = *reinterpret_cast<const float4*>(ep.shift + sample * ep.ldshift + col);
+        v2 = ep.scale ? *reinterpret_cast<const float4*>(ep.scale + sample * ep.ldmod + col) : make_float4(1.f, 1.f, 1.f, 1.f);
+      }
+    }
+    *reinterpret_cast<float4*>(fr.vec + 4 * i) = g;
+    *reinterpret_cast<float4*>(fr.vec + CSPAN + 4 * i) = v1;
+    *reinterpret_cast<float4*>(fr.vec + 2 * CSPAN + 4 * i) = v2;
+  }
+  // ---- (2) residual tile of the first chunk
+  auto issue = [&](int ci) {
+    const uint32_t b = fr.issued % FR_XBUFS;
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&fr.bars[b], 32 * 64);
+      tma_load_2d(fr.bufs + b * 2048, &tm.resid, &fr.bars[b], col0 + 32 * ci, row0);
+    }
+    ++fr.issued;
+  };
+  if (col0 < ep.N) {
+    if (lane == 0) bulk_wait_read(groups);  // the x' store that last used this buffer (>= 2 chunks ago) has read it
+    __syncwarp();
+    issue(0);
+  }
+  wait_acc();
+
+#pragma unroll 1
+  for (int ci = 0; ci < NCHUNK; ++ci) {
+    const int col = col0 + 32 * ci;
+    if (col >= ep.N) break;  // warp-uniform
+    uint32_t r[32];
+    tmem_ld32(t_row + half * CSPAN + 32 * ci, r);
+    // this chunk's residual rows -> registers
+    const uint32_t b = fr.consumed % FR_XBUFS;
+    mbar_wait(&fr.bars[b], (fr.consumed / FR_XBUFS) & 1);
+    ++fr.consumed;
+    uint8_t* xrow = fr.bufs + b * 2048 + lane * 64;
+    uint4 pre[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) pre[k] = *reinterpret_cast<const uint4*>(xrow + ((k ^ sw) << 4));
+    // stores issued a whole chunk ago have read their buffers: aux(c-1) [-> abuf is free], x'(c-2) [-> the next landing buffer]
+    if (lane == 0) bulk_wait_read(has_aux ? groups - 1 : groups);
+    __syncwarp();
+    if (ci + 1 < NCHUNK && col + 32 < ep.N) issue(ci + 1);
+    tmem_ld_wait();
+    float f[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(r[j]);
+    if (has_aux) {  // raw branch output, needed for d(gate)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        uint4 u;
+        u.x = pack_bf16(f[8 * k + 0], f[8 * k + 1]);
+        u.y = pack_bf16(f[8 * k + 2], f[8 * k + 3]);
+        u.z = pack_bf16(f[8 * k + 4], f[8 * k + 5]);
+        u.w = pack_bf16(f[8 * k + 6], f[8 * k + 7]);
+        *reinterpret_cast<uint4*>(abuf + lane * 64 + ((k ^ sw) << 4)) = u;
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) tma_store_2d(&tm.aux, abuf, col, row0);
+    }
+    // x' = (b gate) acc + a x, written back over the residual rows and stored from there
+    const float4* vg = reinterpret_cast<const float4*>(fr.vec + 32 * ci);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&pre[k]);
+      const float4 g0 = vg[2 * k], g1 = vg[2 * k + 1];
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 x2 = __bfloat1622float2(hp[j]);
+        f[8 * k + 2 * j] = fmaf(gg[2 * j], f[8 * k + 2 * j], res_a * x2.x);
+        f[8 * k + 2 * j + 1] = fmaf(gg[2 * j + 1], f[8 * k + 2 * j + 1], res_a * x2.y);
+      }
+      uint4 u;
+      u.x = pack_bf16(f[8 * k + 0], f[8 * k + 1]);
+      u.y = pack_bf16(f[8 * k + 2], f[8 * k + 3]);
+      u.z = pack_bf16(f[8 * k + 4], f[8 * k + 5]);
+      u.w = pack_bf16(f[8 * k + 6], f[8 * k + 7]);
+      *reinterpret_cast<uint4*>(xrow + ((k ^ sw) << 4)) = u;
+    }
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) tma_store_2d(&tm.out, fr.bufs + b * 2048, col, row0);
+    if (has_h) {
+      if (lane == 0) bulk_wait_read(groups - 1);  // h(c-1) has been read out of hbuf
+      __syncwarp();
+      const float4* v1 = reinterpret_cast<const float4*>(fr.vec + CSPAN + 32 * ci);
+      const float4* v2 = reinterpret_cast<const float4*>(fr.vec + 2 * CSPAN + 32 * ci);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float4 a0 = v1[2 * k], a1 = v1[2 * k + 1], b0 = v2[2 * k], b1 = v2[2 * k + 1];
+        const float aa[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        float h[8];
+        if (mod) {  // h = x' (scale (1-g)/den) + shift g/den
+#pragma unroll
+          for (int j = 0; j < 8; ++j) h[j] = fmaf(f[8 * k + j], aa[j], bb[j]);
+        } else {  // rotation of channel pairs by (cos, sin) = (aa[2p], aa[2p+1]), then the optional scale
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            const float xa = f[8 * k + 2 * p], xb = f[8 * k + 2 * p + 1];
+            h[2 * p] = (xa * aa[2 * p] - xb * aa[2 * p + 1]) * bb[2 * p];
+            h[2 * p + 1] = fmaf(xa, aa[2 * p + 1], xb * aa[2 * p]) * bb[2 * p + 1];
+          }
+        }
+        uint4 u;
+        u.x = pack_bf16(h[0], h[1]);
+        u.y = pack_bf16(h[2], h[3]);
+        u.z = pack_bf16(h[4], h[5]);
+        u.w = pack_bf16(h[6], h[7]);
+        *reinterpret_cast<uint4*>(hbuf + lane * 64 + ((k ^ sw) << 4)) = u;
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) tma_store_2d(&tm.out2, hbuf, col, row0);
+    }
+  }
+}
+
 // host: descriptors for the bf16 outputs (unused slots alias `out` so every map is valid)
 inline int make_store_maps(EpiTmaps* tm, const EpiParams& ep) {
   const uint64_t dims[2] = {(uint64_t)ep.N, (uint64_t)ep.M};

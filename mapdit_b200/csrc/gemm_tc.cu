@@ -230,6 +230,7 @@ int mapdit_gemm_bf16_2cta(const mapdit_gemm_args* g, const gemm_epi::EpiParams& 
 extern int g_mapdit_attn_v2;
 extern int g_mapdit_attn_bwd_fused;
 int g_mapdit_gemm_2cta_bn = 0;
+int g_mapdit_gemm_fused_resid = 1;  // second-generation residual epilogues of the CTA-pair kernel (gemm_epilogue.cuh)
 static int g_use_2cta = 1;  // CTA-pair kernel by default where the shape qualifies (A/B: bench.py --gemm-2cta 0)
 
 // runtime switches (benchmark A/B): "gemm_2cta" = 0/1
@@ -244,6 +245,10 @@ extern "C" int mapdit_set_option(const char* name, int value) {
   }
   if (name && !strcmp(name, "gemm_2cta_bn")) {
     g_mapdit_gemm_2cta_bn = value;
+    return MAPDIT_OK;
+  }
+  if (name && !strcmp(name, "gemm_fused_resid")) {
+    g_mapdit_gemm_fused_resid = value;
     return MAPDIT_OK;
   }
   if (name && !strcmp(name, "attn_bwd_fused")) {

@@ -8,6 +8,7 @@
 #include "gemm_epilogue.cuh"
 
 extern long long* g_attn_dbg;  // developer timeline hook (mapdit_attn_debug_buffer)
+extern int g_mapdit_gemm_fused_resid;  // developer switch (mapdit_set_option "gemm_fused_resid"): 0 = first-generation epilogue
 
 namespace {
 using namespace tc;
@@ -17,15 +18,18 @@ constexpr int BM = 128, BK = 64, UK = 16;  // BM = rows per CTA (256 per pair)
 constexpr int NUM_THREADS = 384;
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;  // clears the CTA-parity bit of a shared::cluster address -> leader CTA
 
-template <int BN>
+// FUSED = the second-generation residual epilogues (run_tile_fused_resid): per-warp staging of 5 tile buffers + the per-sample
+// vectors instead of the 2 + 2 buffers of the generic path; one operand stage less for BN = 256 (4 instead of 5)
+template <int BN, bool FUSED>
 struct Cfg2 {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int BH_BYTES = (BN / 2) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + BH_BYTES;
-  static constexpr int MAX_STAGES = (227 * 1024 - 2048 - STG_BYTES - RSTG_BYTES) / STAGE_BYTES;  // 5 for BN = 256 (6 measured no faster)
+  static constexpr int EPI_BYTES = FUSED ? fr_bytes(BN) : STG_BYTES + RSTG_BYTES;
+  static constexpr int MAX_STAGES = (227 * 1024 - 2048 - EPI_BYTES) / STAGE_BYTES;  // generic: 5 for BN = 256 (6 measured no faster)
   static constexpr int STAGES = MAX_STAGES > 8 ? 8 : MAX_STAGES;
   static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + RSTG_BYTES + 1024 + 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 + 512;
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -71,23 +75,24 @@ __device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr) {
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
 }
 
-template <int BN>
+template <int BN, bool FUSED>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                 const __grid_constant__ EpiTmaps etm, const EpiParams ep,
                 int num_m_blocks, int num_n_blocks, int num_k_blocks, long long* __restrict__ dbg) {
-  using C = Cfg2<BN>;
+  using C = Cfg2<BN, FUSED>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   uint8_t* staging = smem + C::STAGES * C::STAGE_BYTES;
-  uint8_t* rstaging = staging + STG_BYTES;  // residual tiles (ResidLoader), 4 KB per epilogue warp
-  uint64_t* full = reinterpret_cast<uint64_t*>(rstaging + RSTG_BYTES);
+  // generic: output staging (8 x 4 KB) then residual tiles (ResidLoader, 8 x 4 KB); FUSED: 8 x 10 KB tile buffers then the vectors
+  uint8_t* rstaging = staging + (FUSED ? 8 * FR_BUF_BYTES_PER_WARP : STG_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(staging + C::EPI_BYTES);
   uint64_t* empty = full + C::STAGES;
   uint64_t* tfull = empty + C::STAGES;
   uint64_t* tempty = tfull + 2;
-  uint64_t* rbar = tempty + 2;  // [8 warps][2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rbar + 16);
+  uint64_t* rbar = tempty + 2;  // [8 warps][3] (generic path uses [8][2])
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rbar + 24);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -108,7 +113,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
       mbar_init(&tfull[a], 1);
       mbar_init(&tempty[a], 16);  // 8 epilogue warps of each CTA of the pair
     }
-    for (int i = 0; i < 16; ++i) mbar_init(&rbar[i], 1);
+    for (int i = 0; i < 24; ++i) mbar_init(&rbar[i], 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc_2cta<C::TMEM_COLS>(tmem_slot);
@@ -177,8 +182,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
       gsc = *ep.gain;
       inv_den = 1.0f / mod_den(gsc);
     }
-    Stager st{staging + (warp - 4) * STG_BYTES_PER_WARP, 0u, lane, 0};
-    ResidLoader rl{rstaging + (warp - 4) * RSTG_BYTES_PER_WARP, rbar + 2 * (warp - 4), &etm.resid, 0u, 0u, lane, 0};
+    Stager st{staging + (FUSED ? 0 : (warp - 4) * STG_BYTES_PER_WARP), 0u, lane, 0};
+    ResidLoader rl{rstaging + (FUSED ? 0 : (warp - 4) * RSTG_BYTES_PER_WARP), rbar + 2 * (warp - 4), &etm.resid, 0u, 0u, lane, 0};
+    FusedResid fr{staging + (warp - 4) * FR_BUF_BYTES_PER_WARP, reinterpret_cast<float*>(rstaging + (warp - 4) * fr_vec_bytes_per_warp(BN)),
+                  rbar + FR_XBUFS * (warp - 4), 0u, 0u, lane};
     for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
       const int m_pair = tile / num_n_blocks, n_blk = tile - m_pair * num_n_blocks;
       const int row = (2 * m_pair + (int)rank) * BM + q * 32 + lane;
@@ -186,11 +193,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
       const int tcount = (tile - cluster_id) / num_clusters;
       if (dbg && blockIdx.x == 0 && lane == 0 && tcount < 16) dbg[(warp - 4) * 64 + tcount * 4 + 0] = clock64();
-      run_tile<BN>(ep, etm, st, t_row, row, n_blk, half, gsc, inv_den, [&]() {
+      auto wait_acc = [&]() {
         mbar_wait(&tfull[acc], acc_phase);
         tc_fence_after();
         if (dbg && blockIdx.x == 0 && lane == 0 && tcount < 16) dbg[(warp - 4) * 64 + tcount * 4 + 1] = clock64();
-      }, &rl);
+      };
+      if constexpr (FUSED) run_tile_fused_resid<BN>(ep, etm, fr, t_row, st.row0, n_blk, half, gsc, inv_den, wait_acc);
+      else run_tile<BN>(ep, etm, st, t_row, row, n_blk, half, gsc, inv_den, wait_acc, &rl);
       tc_fence_before();
       __syncwarp();
       if (dbg && blockIdx.x == 0 && lane == 0 && tcount < 16) dbg[(warp - 4) * 64 + tcount * 4 + 2] = clock64();
@@ -198,7 +207,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
-    st.drain();
+    if constexpr (FUSED) fr.drain();
+    else st.drain();
   }
 
   tc_fence_before();
@@ -206,9 +216,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
   if (warp == 2) tmem_dealloc_2cta<C::TMEM_COLS>(tmem_base);
 }
 
-template <int BN>
+template <int BN, bool FUSED>
 int launch2(const mapdit_gemm_args* g, const EpiParams& ep, cudaStream_t stream, int num_sms) {
-  using C = Cfg2<BN>;
+  using C = Cfg2<BN, FUSED>;
   CUtensorMap ta, tb;
   const uint64_t dims_a[2] = {(uint64_t)g->k, (uint64_t)g->m}, dims_b[2] = {(uint64_t)g->k, (uint64_t)g->n};
   const uint64_t str_a[1] = {(uint64_t)g->lda * 2}, str_b[1] = {(uint64_t)g->ldb * 2};
@@ -221,7 +231,7 @@ int launch2(const mapdit_gemm_args* g, const EpiParams& ep, cudaStream_t stream,
   }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<BN, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) {
       mapdit_set_error("gemm_bf16(2cta): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return MAPDIT_ERR_CUDA;
@@ -237,8 +247,24 @@ int launch2(const mapdit_gemm_args* g, const EpiParams& ep, cudaStream_t stream,
     mapdit_set_error("gemm_bf16(2cta): cuTensorMapEncodeTiled (store maps) failed");
     return MAPDIT_ERR_CUDA;
   }
-  gemm_tc2_kernel<BN><<<2 * clusters, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, etm, ep, mb, nb, kb, g_attn_dbg);
+  gemm_tc2_kernel<BN, FUSED><<<2 * clusters, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, etm, ep, mb, nb, kb, g_attn_dbg);
   return MAPDIT_OK;
+}
+
+// the second-generation residual epilogue needs a warp's 32 rows inside one sample and 16-byte aligned per-sample vectors
+bool fused_resid_ok(const mapdit_gemm_args* g, const EpiParams& ep) {
+  if (!g_mapdit_gemm_fused_resid) return false;
+  // 1 (default) = only where the epilogue is the bottleneck: short contractions (K <= 1024: out-proj); with K = 4 D (fc2) the main
+  // loop hides the first-generation epilogue and keeps its fifth operand stage.  2 = always (A/B)
+  if (g_mapdit_gemm_fused_resid == 1 && g->k > 1024) return false;
+  if (ep.epilogue != MAPDIT_EPI_RESID && ep.epilogue != MAPDIT_EPI_RESID_MOD && ep.epilogue != MAPDIT_EPI_RESID_ROT) return false;
+  if (ep.tokens % 32 != 0 || ep.ldmod % 4 != 0 || ep.ldshift % 4 != 0 || ep.N % 4 != 0) return false;
+  auto al16 = [](const void* p) { return p == nullptr || ((uintptr_t)p & 15) == 0; };
+  return ep.resid != nullptr && al16(ep.gate) && al16(ep.shift) && al16(ep.scale);
+}
+template <int BN>
+int launch2_any(const mapdit_gemm_args* g, const EpiParams& ep, cudaStream_t stream, int num_sms) {
+  return fused_resid_ok(g, ep) ? launch2<BN, true>(g, ep, stream, num_sms) : launch2<BN, false>(g, ep, stream, num_sms);
 }
 }  // namespace
 
@@ -250,8 +276,8 @@ int mapdit_gemm_bf16_2cta(const mapdit_gemm_args* g, const gemm_epi::EpiParams& 
   const int nb256 = (g->n + 255) / 256;
   const bool wide_ok = g->n % 256 == 0 || (g->n % 128 == 0 && (long long)nb256 * 256 * 8 <= (long long)g->n * 9);
   extern int g_mapdit_gemm_2cta_bn;  // developer switch (mapdit_set_option "gemm_2cta_bn"): 0 = auto, 128 / 256 = force that tile width
-  if (g_mapdit_gemm_2cta_bn == 128 && g->n % 128 == 0) return launch2<128>(g, ep, stream, num_sms);
-  if (wide_ok && (long long)((mb + 1) / 2) * nb256 >= num_sms / 2) return launch2<256>(g, ep, stream, num_sms);
-  if (g->n % 128 == 0 && (long long)((mb + 1) / 2) * (g->n / 128) >= num_sms) return launch2<128>(g, ep, stream, num_sms);
+  if (g_mapdit_gemm_2cta_bn == 128 && g->n % 128 == 0) return launch2_any<128>(g, ep, stream, num_sms);
+  if (wide_ok && (long long)((mb + 1) / 2) * nb256 >= num_sms / 2) return launch2_any<256>(g, ep, stream, num_sms);
+  if (g->n % 128 == 0 && (long long)((mb + 1) / 2) * (g->n / 128) >= num_sms) return launch2_any<128>(g, ep, stream, num_sms);
   return MAPDIT_ERR_UNSUPPORTED;
 }

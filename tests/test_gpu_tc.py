@@ -41,11 +41,24 @@ def test_gemm_bf16_store(m, n, k, two_cta):
     assert rel_l2(out32, ref) < 1e-5
 
 
-@pytest.mark.parametrize("N,T,D", [(2, 64, 384), (3, 256, 256), (1, 256, 768), (33, 64, 384), (40, 256, 256), (41, 128, 768), (160, 64, 384)])
-@pytest.mark.parametrize("two_cta", [0, 1])
+# the last four shapes reach the cta_group::2 kernel also for the N = D GEMMs (second-generation residual epilogues): 256-wide tiles
+# (N = 256, 768), 128-wide tiles with 64 tokens per sample (N = 384), and a clipped last 256-wide tile (N = 1152)
+@pytest.mark.parametrize("N,T,D", [(2, 64, 384), (3, 256, 256), (1, 256, 768), (33, 64, 384), (40, 256, 256), (41, 128, 768), (160, 64, 384),
+                                   (80, 256, 256), (30, 256, 768), (200, 64, 384), (16, 256, 1152)])
+@pytest.mark.parametrize("two_cta", [0, 1, 2])
 def test_gemm_bf16_fused_epilogues(N, T, D, two_cta):
     from mapdit_b200 import _lib, ops
-    _lib.set_option("gemm_2cta", two_cta)
+    _lib.set_option("gemm_2cta", min(two_cta, 1))
+    _lib.set_option("gemm_fused_resid", 0 if two_cta == 2 else 1)  # 2 = CTA-pair kernel with the first-generation residual epilogue
+    try:
+        _fused_epilogues(N, T, D)
+    finally:
+        _lib.set_option("gemm_fused_resid", 1)
+        _lib.set_option("gemm_2cta", 1)
+
+
+def _fused_epilogues(N, T, D):
+    from mapdit_b200 import _lib, ops
     M, hd = N * T, 64
     h = rnd(M, D, seed=3).bfloat16()
     wqkv = rnd(3 * D, D, seed=4, scale=D ** -0.5).bfloat16()
@@ -86,14 +99,23 @@ def test_gemm_bf16_fused_epilogues(N, T, D, two_cta):
     g = float(gain)
     hn = ((xn * scale) + g * (shift - xn * scale)) / math.sqrt((1 - g) ** 2 + g ** 2)
     xio = x.clone()
-    hout = torch.empty_like(x)
+    hout = torch.full_like(x, float("nan"))
     ops.gemm_bf16(h, wo, xio, epilogue=_lib.EPI_RESID_MOD, out2=hout, resid=xio, gate=mods[:, 2 * D:], shift=mods[:, 3 * D:],
                   scale=mods[:, 4 * D:], gain=gain, ldmod=mods.shape[1], tokens=T)
     assert rel_l2(xio.float(), xn) < 3e-3
     assert rel_l2(hout.float(), hn) < 3e-3
+    # training flavour: separate output, raw branch output saved in `aux`; the same bits as the in-place eval call
+    xo2, hout2, aux = (torch.full_like(x, float("nan")) for _ in range(3))
+    ops.gemm_bf16(h, wo, xo2, epilogue=_lib.EPI_RESID_MOD, out2=hout2, resid=x, gate=mods[:, 2 * D:], shift=mods[:, 3 * D:],
+                  scale=mods[:, 4 * D:], gain=gain, ldmod=mods.shape[1], tokens=T, aux=aux)
+    assert torch.equal(xo2, xio) and torch.equal(hout2, hout)
+    assert rel_l2(aux.float(), y) < 3e-3
     xio = x.clone()
     ops.gemm_bf16(h, wo, xio, epilogue=_lib.EPI_RESID, resid=xio, gate=mods[:, 2 * D:], ldmod=mods.shape[1], tokens=T)
     assert rel_l2(xio.float(), xn) < 3e-3
+    xo2, aux = torch.full_like(x, float("nan")), torch.full_like(x, float("nan"))
+    ops.gemm_bf16(h, wo, xo2, epilogue=_lib.EPI_RESID, resid=x, gate=mods[:, 2 * D:], ldmod=mods.shape[1], tokens=T, aux=aux)
+    assert torch.equal(xo2, xio) and rel_l2(aux.float(), y) < 3e-3
     # RESID_ROT (rotation modulation, UNPINNED: SURVEY.md §A.8): h = R(rot * gain) x' (* scale), (cos, sin) table from rot_table
     rot = mods[:, 5 * D:5 * D + D // 2]
     cs = torch.full((N, 2 * D + 8), float("nan"), device="cuda")  # table in a wider buffer: column slice at offset 8, own ld
@@ -111,6 +133,10 @@ def test_gemm_bf16_fused_epilogues(N, T, D, two_cta):
                       ldmod=mods.shape[1], ldrot=cs.stride(0), tokens=T)
         assert rel_l2(xio.float(), xn) < 3e-3
         assert rel_l2(hout.float(), href) < 3e-3
+        xo2, hout2, aux = (torch.full_like(x, float("nan")) for _ in range(3))
+        ops.gemm_bf16(h, wo, xo2, epilogue=_lib.EPI_RESID_ROT, out2=hout2, resid=x, gate=mods[:, 2 * D:], shift=cs[:, 8:], scale=sc_arg,
+                      ldmod=mods.shape[1], ldrot=cs.stride(0), tokens=T, aux=aux)
+        assert torch.equal(xo2, xio) and torch.equal(hout2, hout) and rel_l2(aux.float(), y) < 3e-3
 
 
 @pytest.mark.parametrize("v2", [1, 0])

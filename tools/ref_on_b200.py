@@ -23,6 +23,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = os.path.join(ROOT, "oracle", "_ref")
 
 
+def _fix_host_compiler():
+    """torch.compile builds small host-side C++ kernels with $CXX; this image's /opt/gcc/bin/g++ wrapper cannot find libgomp.spec
+    (`-fopenmp` fails), the system compiler can"""
+    if os.environ.get("CXX", "").startswith("/opt/gcc") and os.path.exists("/usr/bin/g++"):
+        os.environ["CXX"] = "/usr/bin/g++"
+        os.environ["CC"] = "/usr/bin/gcc"
+
+
 def _import_reference():
     if not os.path.isfile(os.path.join(REF, "src", "models.py")):
         raise RuntimeError("oracle/_ref is missing: run `python oracle/vendor_reference.py` in the build container")
@@ -123,6 +131,7 @@ def main():
     ap.add_argument("--compile", action="store_true", help="also time torch.compile(model) (minutes of compilation)")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "ref_on_b200.json"))
     a = ap.parse_args()
+    _fix_host_compiler()
     import torch
     arms = ["eager_tf32", "eager_bf16_autocast"] + (["compile_tf32", "compile_bf16_autocast"] if a.compile else [])
     res = measure(a.model, a.batch, arms, input_size=a.input_size, log=lambda s: print("[ref_on_b200]", s, file=sys.stderr, flush=True))
