@@ -375,9 +375,9 @@ struct FusedResid {
   }
 };
 
-template <int BN, typename WaitFn>
+template <int BN, typename WaitFn, typename ReleaseFn>
 __device__ __forceinline__ void run_tile_fused_resid(const EpiParams& ep, const EpiTmaps& tm, FusedResid& fr, uint32_t t_row, int row0,
-                                                     int n_blk, int half, float gsc, float inv_den, WaitFn wait_acc) {
+                                                     int n_blk, int half, float gsc, float inv_den, WaitFn wait_acc, ReleaseFn release_acc) {
   constexpr int CSPAN = BN / 2, NCHUNK = CSPAN / 32;
   const int lane = fr.lane;
   const int col0 = n_blk * BN + half * CSPAN;
@@ -425,19 +425,25 @@ __device__ __forceinline__ void run_tile_fused_resid(const EpiParams& ep, const 
     }
     ++fr.issued;
   };
-  if (col0 < ep.N) {
-    if (lane == 0) bulk_wait_read(groups);  // the x' store that last used this buffer (>= 2 chunks ago) has read it
-    __syncwarp();
-    issue(0);
-  }
+  if (lane == 0) bulk_wait_read(groups);  // the x' store that last used the first landing buffer (>= 2 chunks ago) has read it
+  __syncwarp();
+  if (col0 < ep.N) issue(0);
   wait_acc();
+  if (col0 >= ep.N) {  // nothing to do for this warp in a clipped tile (warp-uniform)
+    release_acc();
+    return;
+  }
 
-#pragma unroll 1
+  // accumulator chunks are read one ahead: the tcgen05.ld of chunk c+1 is in flight while chunk c is processed
+  uint32_t ra[32], rb[32];
+  tmem_ld32(t_row + half * CSPAN, ra);
+#pragma unroll
   for (int ci = 0; ci < NCHUNK; ++ci) {
     const int col = col0 + 32 * ci;
     if (col >= ep.N) break;  // warp-uniform
-    uint32_t r[32];
-    tmem_ld32(t_row + half * CSPAN + 32 * ci, r);
+    uint32_t(&r)[32] = (ci & 1) ? rb : ra;
+    uint32_t(&rn)[32] = (ci & 1) ? ra : rb;
+    const bool more = ci + 1 < NCHUNK && col + 32 < ep.N;
     // this chunk's residual rows -> registers
     const uint32_t b = fr.consumed % FR_XBUFS;
     mbar_wait(&fr.bars[b], (fr.consumed / FR_XBUFS) & 1);
@@ -449,8 +455,9 @@ __device__ __forceinline__ void run_tile_fused_resid(const EpiParams& ep, const 
     // stores issued a whole chunk ago have read their buffers: aux(c-1) [-> abuf is free], x'(c-2) [-> the next landing buffer]
     if (lane == 0) bulk_wait_read(has_aux ? groups - 1 : groups);
     __syncwarp();
-    if (ci + 1 < NCHUNK && col + 32 < ep.N) issue(ci + 1);
+    if (more) issue(ci + 1);
     tmem_ld_wait();
+    if (more) tmem_ld32(t_row + half * CSPAN + 32 * (ci + 1), rn);
     float f[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(r[j]);
@@ -464,9 +471,6 @@ __device__ __forceinline__ void run_tile_fused_resid(const EpiParams& ep, const 
         u.w = pack_bf16(f[8 * k + 6], f[8 * k + 7]);
         *reinterpret_cast<uint4*>(abuf + lane * 64 + ((k ^ sw) << 4)) = u;
       }
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) tma_store_2d(&tm.aux, abuf, col, row0);
     }
     // x' = (b gate) acc + a x, written back over the residual rows and stored from there
     const float4* vg = reinterpret_cast<const float4*>(fr.vec + 32 * ci);
@@ -488,9 +492,13 @@ __device__ __forceinline__ void run_tile_fused_resid(const EpiParams& ep, const 
       u.w = pack_bf16(f[8 * k + 6], f[8 * k + 7]);
       *reinterpret_cast<uint4*>(xrow + ((k ^ sw) << 4)) = u;
     }
-    fence_proxy_async();
+    fence_proxy_async();  // one fence for the aux and the x' rows
     __syncwarp();
-    if (lane == 0) tma_store_2d(&tm.out, fr.bufs + b * 2048, col, row0);
+    if (lane == 0) {
+      if (has_aux) tma_store_2d(&tm.aux, abuf, col, row0);
+      tma_store_2d(&tm.out, fr.bufs + b * 2048, col, row0);
+    }
+    if (!more) release_acc();  // every tcgen05.ld of this tile has completed: the MMA warp may reuse the accumulator stage
     if (has_h) {
       if (lane == 0) bulk_wait_read(groups - 1);  // h(c-1) has been read out of hbuf
       __syncwarp();

@@ -198,12 +198,20 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
         tc_fence_after();
         if (dbg && blockIdx.x == 0 && lane == 0 && tcount < 16) dbg[(warp - 4) * 64 + tcount * 4 + 1] = clock64();
       };
-      if constexpr (FUSED) run_tile_fused_resid<BN>(ep, etm, fr, t_row, st.row0, n_blk, half, gsc, inv_den, wait_acc);
-      else run_tile<BN>(ep, etm, st, t_row, row, n_blk, half, gsc, inv_den, wait_acc, &rl);
-      tc_fence_before();
-      __syncwarp();
-      if (dbg && blockIdx.x == 0 && lane == 0 && tcount < 16) dbg[(warp - 4) * 64 + tcount * 4 + 2] = clock64();
-      if (lane == 0) mbar_arrive_leader(&tempty[acc]);
+      if constexpr (FUSED) {
+        run_tile_fused_resid<BN>(ep, etm, fr, t_row, st.row0, n_blk, half, gsc, inv_den, wait_acc, [&]() {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_leader(&tempty[acc]);  // released as soon as the tile's last accumulator chunk is in registers
+        });
+        if (dbg && blockIdx.x == 0 && lane == 0 && tcount < 16) dbg[(warp - 4) * 64 + tcount * 4 + 2] = clock64();
+      } else {
+        run_tile<BN>(ep, etm, st, t_row, row, n_blk, half, gsc, inv_den, wait_acc, &rl);
+        tc_fence_before();
+        __syncwarp();
+        if (dbg && blockIdx.x == 0 && lane == 0 && tcount < 16) dbg[(warp - 4) * 64 + tcount * 4 + 2] = clock64();
+        if (lane == 0) mbar_arrive_leader(&tempty[acc]);
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
