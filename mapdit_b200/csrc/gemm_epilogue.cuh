@@ -368,10 +368,14 @@ struct FusedResid {
   uint64_t* bars;  // this warp's FR_XBUFS mbarriers (count 1)
   uint32_t issued, consumed;
   int lane;
+  long long* fine;  // developer timeline (tools/gemm_timeline.py): 8 clock64 stamps per chunk, or null
 
   __device__ __forceinline__ void drain() {
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     __syncwarp();
+  }
+  __device__ __forceinline__ void stamp(int ci, int e) {
+    if (fine && lane == 0) fine[ci * 8 + e] = clock64();
   }
 };
 
@@ -446,7 +450,9 @@ __device__ __forceinline__ void run_tile_fused_resid(const EpiParams& ep, const 
     const bool more = ci + 1 < NCHUNK && col + 32 < ep.N;
     // this chunk's residual rows -> registers
     const uint32_t b = fr.consumed % FR_XBUFS;
+    fr.stamp(ci, 0);
     mbar_wait(&fr.bars[b], (fr.consumed / FR_XBUFS) & 1);
+    fr.stamp(ci, 1);
     ++fr.consumed;
     uint8_t* xrow = fr.bufs + b * 2048 + lane * 64;
     uint4 pre[4];
@@ -455,8 +461,10 @@ __device__ __forceinline__ void run_tile_fused_resid(const EpiParams& ep, const 
     // stores issued a whole chunk ago have read their buffers: aux(c-1) [-> abuf is free], x'(c-2) [-> the next landing buffer]
     if (lane == 0) bulk_wait_read(has_aux ? groups - 1 : groups);
     __syncwarp();
+    fr.stamp(ci, 2);
     if (more) issue(ci + 1);
     tmem_ld_wait();
+    fr.stamp(ci, 3);
     if (more) tmem_ld32(t_row + half * CSPAN + 32 * (ci + 1), rn);
     float f[32];
 #pragma unroll
@@ -492,16 +500,19 @@ __device__ __forceinline__ void run_tile_fused_resid(const EpiParams& ep, const 
       u.w = pack_bf16(f[8 * k + 6], f[8 * k + 7]);
       *reinterpret_cast<uint4*>(xrow + ((k ^ sw) << 4)) = u;
     }
+    fr.stamp(ci, 4);
     fence_proxy_async();  // one fence for the aux and the x' rows
     __syncwarp();
     if (lane == 0) {
       if (has_aux) tma_store_2d(&tm.aux, abuf, col, row0);
       tma_store_2d(&tm.out, fr.bufs + b * 2048, col, row0);
     }
+    fr.stamp(ci, 5);
     if (!more) release_acc();  // every tcgen05.ld of this tile has completed: the MMA warp may reuse the accumulator stage
     if (has_h) {
       if (lane == 0) bulk_wait_read(groups - 1);  // h(c-1) has been read out of hbuf
       __syncwarp();
+      fr.stamp(ci, 6);
       const float4* v1 = reinterpret_cast<const float4*>(fr.vec + CSPAN + 32 * ci);
       const float4* v2 = reinterpret_cast<const float4*>(fr.vec + 2 * CSPAN + 32 * ci);
 #pragma unroll
@@ -531,6 +542,7 @@ __device__ __forceinline__ void run_tile_fused_resid(const EpiParams& ep, const 
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) tma_store_2d(&tm.out2, hbuf, col, row0);
+      fr.stamp(ci, 7);
     }
   }
 }

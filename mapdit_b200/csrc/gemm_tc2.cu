@@ -185,7 +185,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
     Stager st{staging + (FUSED ? 0 : (warp - 4) * STG_BYTES_PER_WARP), 0u, lane, 0};
     ResidLoader rl{rstaging + (FUSED ? 0 : (warp - 4) * RSTG_BYTES_PER_WARP), rbar + 2 * (warp - 4), &etm.resid, 0u, 0u, lane, 0};
     FusedResid fr{staging + (warp - 4) * FR_BUF_BYTES_PER_WARP, reinterpret_cast<float*>(rstaging + (warp - 4) * fr_vec_bytes_per_warp(BN)),
-                  rbar + FR_XBUFS * (warp - 4), 0u, 0u, lane};
+                  rbar + FR_XBUFS * (warp - 4), 0u, 0u, lane, nullptr};
     for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
       const int m_pair = tile / num_n_blocks, n_blk = tile - m_pair * num_n_blocks;
       const int row = (2 * m_pair + (int)rank) * BM + q * 32 + lane;
@@ -199,6 +199,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
         if (dbg && blockIdx.x == 0 && lane == 0 && tcount < 16) dbg[(warp - 4) * 64 + tcount * 4 + 1] = clock64();
       };
       if constexpr (FUSED) {
+        // fine-grained stamps of warp 4 (first column half) and warp 8 (second) for tiles 2 and 3 of CTA 0
+        fr.fine = (dbg && blockIdx.x == 0 && (warp == 4 || warp == 8) && (tcount == 2 || tcount == 3))
+                      ? dbg + 576 + ((warp == 8 ? 2 : 0) + (tcount - 2)) * 32 : nullptr;
         run_tile_fused_resid<BN>(ep, etm, fr, t_row, st.row0, n_blk, half, gsc, inv_den, wait_acc, [&]() {
           tc_fence_before();
           __syncwarp();

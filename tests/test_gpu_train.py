@@ -108,9 +108,9 @@ def test_training_step_gradients(tag, dtype):
         e = rel_l2(prm.grad.cpu(), ograds[k])
         worst = max(worst, e)
         tol = 2e-4 if dtype == "fp32" else 8e-2
-        if tag == "train_xs2_b80" and k.endswith("_scale.reference"):
-            # the 8-element reference vectors of MPScale: sums over 80 x 1024 output elements with ~1000-fold cancellation
-            # (the fp32 path itself only reaches 2.5e-4 = 2000 ulp here); measured 0.146 in bf16
+        if tag == "train_xs2_b80" and "_scale." in k:
+            # MPScale's parameters (8-element reference vector, 8 x D linear weight): sums over 80 x 1024 output elements with
+            # ~1000-fold cancellation (the fp32 path itself only reaches 2.5e-4 = 2000 ulp here); measured 0.146 in bf16
             tol = 1e-3 if dtype == "fp32" else 0.25
         assert e < tol, (k, e)
         # against the reference's own numbers
@@ -422,12 +422,14 @@ def test_full_size_backward_equals_sum_of_shard_gradients(wgrad_stream):
     t[0] = 0
     drop = (torch.rand(B, generator=g) < 0.1).cuda()
     ts.compute_grads(x[:S], t[:S], y[:S], noise[:S], drop[:S])  # the first train-mode forward writes the forced normalisation back
+    # Every further train-mode forward would re-apply it, moving the fp32 weights in their last bits and flipping the bf16 rounding
+    # of ~0.1 % of them (measured: losses of two identical calls differ by 1.7e-4).  The property tested here needs identical
+    # parameters in every call, so the write-back is switched off from here on (the effective weights are normalised either way).
+    m.flags["use_forced_weight_normalization"] = False
     loss_full = ts.compute_grads(x, t, y, noise, drop).clone()
     g_full = ts.flat_g.clone()
-    # (every train-mode forward re-applies the forced weight normalisation, which moves the fp32 weights in their last bits and
-    # flips the bf16 rounding of a few of them: reruns agree to ~1e-5, not bit for bit)
     again = ts.compute_grads(x, t, y, noise, drop)
-    assert rel_l2(again, loss_full) < 1e-4
+    assert torch.equal(again, loss_full)
     acc, losses = torch.zeros_like(g_full, dtype=torch.float64), []
     for s in range(B // S):
         sl = slice(s * S, (s + 1) * S)
@@ -435,7 +437,7 @@ def test_full_size_backward_equals_sum_of_shard_gradients(wgrad_stream):
         acc += ts.flat_g.double()
     torch.cuda.synchronize()
     assert torch.isfinite(g_full).all() and float(g_full.abs().max()) > 0
-    assert rel_l2(torch.cat(losses), loss_full) < 1e-4  # per-sample results do not depend on the batch they sit in
+    assert torch.equal(torch.cat(losses), loss_full)  # per-sample results do not depend on the batch they sit in
     worst = ("", 0.0)
     for name, prm in m.named_parameters():
         lo, n = ts.offset_of[id(prm)], prm.numel()

@@ -22,3 +22,10 @@ for name, fn in (("store", lambda: ops.gemm_bf16(o, wo, h)),
     print(f"== {name}: per tile of CTA 0: MMA [acc free seen, last MMA issued] | epilogue warp 4: [start, acc ready, done] | warp 11: [start, ready, done]")
     for t in range(10):
         print(f"  tile {t}: MMA {rel(mm[t,0]):7d} {rel(mm[t,1]):7d} | w4 {rel(ew[0,t,0]):7d} {rel(ew[0,t,1]):7d} {rel(ew[0,t,2]):7d} | w11 {rel(ew[7,t,0]):7d} {rel(ew[7,t,1]):7d} {rel(ew[7,t,2]):7d}")
+    if name == "resid_mod":
+        fine = d[576:576 + 128].view(4, 4, 8)  # [warp 4 tile 2, warp 4 tile 3, warp 8 tile 2, warp 8 tile 3][chunk][stamp]
+        ev = ["wait resid", "resid ok", "bulk wait ok", "tmem ld ok", "x' written", "stores issued", "h bulk wait ok", "h store issued"]
+        for wi, wn in enumerate(("w4 tile2", "w4 tile3", "w8 tile2", "w8 tile3")):
+            for c in range(4):
+                row = [rel(fine[wi, c, e]) for e in range(8)]
+                print(f"  {wn} chunk {c}: " + " ".join(f"{ev[e]}={row[e]}" for e in range(8)) + "  | deltas " + " ".join(str(row[e + 1] - row[e]) for e in range(7)))
