@@ -184,8 +184,24 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
     }
     Stager st{staging + (FUSED ? 0 : (warp - 4) * STG_BYTES_PER_WARP), 0u, lane, 0};
     ResidLoader rl{rstaging + (FUSED ? 0 : (warp - 4) * RSTG_BYTES_PER_WARP), rbar + 2 * (warp - 4), &etm.resid, 0u, 0u, lane, 0};
-    FusedResid fr{staging + (warp - 4) * FR_BUF_BYTES_PER_WARP, reinterpret_cast<float*>(rstaging + (warp - 4) * fr_vec_bytes_per_warp(BN)),
-                  rbar + FR_XBUFS * (warp - 4), 0u, 0u, lane, nullptr};
+    FusedResid fr;
+    if constexpr (FUSED) {
+      fr.bufs = staging + (warp - 4) * FR_BUF_BYTES_PER_WARP;
+      fr.vec = reinterpret_cast<float*>(rstaging + (warp - 4) * fr_vec_bytes_per_warp(BN));
+      fr.bars = rbar + FR_XBUFS * (warp - 4);
+      fr.issued = fr.consumed = fr.stores = 0u;
+      fr.lane = lane;
+      fr.first_tile = cluster_id;
+      fr.tile_stride = num_clusters;
+      fr.total_tiles = total_tiles;
+      fr.num_n_blocks = num_n_blocks;
+      fr.row_in_pair = (int)rank * BM + q * 32;
+      fr.half = half;
+      fr.nv_tile = -1;
+      fr.fine = nullptr;
+      fr_issue<BN>(ep, etm, fr, 0u);  // the residual stream runs two chunks ahead of its consumer
+      fr_issue<BN>(ep, etm, fr, 1u);
+    }
     for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
       const int m_pair = tile / num_n_blocks, n_blk = tile - m_pair * num_n_blocks;
       const int row = (2 * m_pair + (int)rank) * BM + q * 32 + lane;
@@ -202,7 +218,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
         // fine-grained stamps of warp 4 (first column half) and warp 8 (second) for tiles 2 and 3 of CTA 0
         fr.fine = (dbg && blockIdx.x == 0 && (warp == 4 || warp == 8) && (tcount == 2 || tcount == 3))
                       ? dbg + 576 + ((warp == 8 ? 2 : 0) + (tcount - 2)) * 32 : nullptr;
-        run_tile_fused_resid<BN>(ep, etm, fr, t_row, st.row0, n_blk, half, gsc, inv_den, wait_acc, [&]() {
+        run_tile_fused_resid<BN>(ep, etm, fr, t_row, tile, gsc, inv_den, wait_acc, [&]() {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_leader(&tempty[acc]);  // released as soon as the tile's last accumulator chunk is in registers
@@ -218,8 +234,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
-    if constexpr (FUSED) fr.drain();
-    else st.drain();
+    if constexpr (!FUSED) st.drain();
   }
 
   tc_fence_before();
