@@ -333,66 +333,66 @@ __device__ __forceinline__ void run_tile(const EpiParams& ep, const EpiTmaps& tm
 // Fused residual epilogues, second generation (2-CTA kernel, tokens % 32 == 0 so that a warp's 32 rows lie in one sample).
 //
 // What bounded the first generation (15-17 k cycles per 256 x 256 tile against a 6-9 k main loop, the MMA warp idle
-// on its accumulator stages; a clock64 timeline of its successor with TMA stores showed ~2.3 k cycles per 32-column chunk of which
-// ~1.3 k were fixed latencies of the asynchronous machinery: cp.async.bulk.wait_group 130-260, fence.proxy.async + TMA store issue
-// ~200 each, an exposed TMA load at the head of every tile 1.5-2 k) and what replaces it:
+// on its accumulator stages) and what replaces it:
 //   * per-sample vectors (gate | shift | scale, or gate | (cos, sin) | scale): every lane used to read them from global memory
-//     right before use, three exposed L2 round trips per chunk.  Each warp now stages the vectors of its whole column half once
-//     per tile in shared memory, already multiplied by the warp-uniform constants; the global loads for the NEXT tile are issued
-//     during the last chunk of the current one;
-//   * the residual arrives by TMA as one flat stream over all chunks of all tiles of this warp, two chunks ahead in three
-//     rotating 32 x 32 buffers: also the first chunk of a tile is in flight long before it is needed, and since the buffers are
-//     only ever read with ordinary loads there is no bulk-group bookkeeping;
-//   * outputs (x', h, aux) leave through the LSU, but coalesced: the 32 x 32 bf16 tile goes row-per-lane into a swizzled
-//     staging buffer and is read back transposed, so that one 16-byte store instruction covers 8 rows x 64 contiguous bytes
-//     (8 line transactions instead of the 32 of a row-per-lane store).  Fire and forget: no fence.proxy.async, no wait_group;
+//     right before use, three exposed L2 round trips per 32-column chunk.  Each warp now stages the vectors of its whole column
+//     half once per tile in shared memory, already multiplied by the warp-uniform constants; the global loads for the NEXT tile
+//     are issued during the last chunk of the current one and only consumed at the head of the next;
+//   * the residual arrives by TMA as one flat stream over all chunks of all tiles of this warp, one chunk ahead in three
+//     rotating 32 x 32 buffers, so the first chunk of a tile is in flight during the last chunk of the previous tile (a clock64
+//     timeline showed 1.5-2 k cycles of exposed TMA latency at the head of every tile before);
+//   * up to three TMA stores per chunk rotated through two staging buffers, so every chunk waited for a store issued moments
+//     earlier.  Now no buffer is reused within a chunk: x' is written back over the residual rows it was computed from (the
+//     lane that read a row writes it) and stored from there, aux and h have their own buffer each, and every
+//     cp.async.bulk.wait_group is for a store issued a whole chunk earlier; one fence.proxy.async covers aux and x';
 //   * accumulator chunks are read one ahead and the accumulator stage is released as soon as the last chunk is in registers.
+// (Tried and dropped: coalesced st.global through a transpose buffer instead of TMA stores: 580-860 cycles per 32 x 32 tile in
+// the LSU against ~200 for fence + TMA store issue; 0.113 ms against 0.095 ms for the out-proj GEMM.)
 // The arithmetic (and therefore every output bit) is the same as run_tile's.
-constexpr int FR_XBUFS = 3, FR_SBUFS = 2;
-constexpr int FR_BUF_BYTES_PER_WARP = (FR_XBUFS + FR_SBUFS) * 2048;
+constexpr int FR_XBUFS = 3;
+constexpr int FR_BUF_BYTES_PER_WARP = (FR_XBUFS + 2) * 2048;
 __host__ __device__ constexpr int fr_vec_bytes_per_warp(int bn) { return 3 * (bn / 2) * 4; }
 __host__ __device__ constexpr int fr_bytes(int bn) { return 8 * (FR_BUF_BYTES_PER_WARP + fr_vec_bytes_per_warp(bn)); }
 
+__device__ __forceinline__ void bulk_wait_read(int k) {  // k warp-uniform, 0..3
+  if (k <= 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  else if (k == 1) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+  else if (k == 2) asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
+  else asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"((uint64_t)map), "r"(smem_u32(smem_src)),
+               "r"(c0), "r"(c1)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
 struct FusedResid {
-  uint8_t* bufs;   // this warp's FR_XBUFS residual landing buffers, then FR_SBUFS store-transpose buffers (2 KB each)
+  uint8_t* bufs;   // this warp's (FR_XBUFS + 2) x 2 KB: X[0..2] residual landing + x' staging, then aux, then h
   float* vec;      // this warp's 3 x (BN/2) floats
   uint64_t* bars;  // this warp's FR_XBUFS mbarriers (count 1)
-  uint32_t issued, consumed, stores;
+  uint32_t consumed;
   int lane;
   // the warp's chunk stream: tile k of this CTA pair is first_tile + k * tile_stride; chunk s belongs to tile s / NCHUNK
   int first_tile, tile_stride, total_tiles, num_n_blocks, row_in_pair;  // row_in_pair = rank * 128 + quarter * 32
   int half;
-  float4 nv[3];     // vectors of the next tile, prefetched (valid when nv_tile == that tile)
+  float4 nv[3];     // raw vectors of the next tile, prefetched (valid when nv_tile == that tile)
   int nv_tile;
   long long* fine;  // developer timeline (tools/gemm_timeline.py): 8 clock64 stamps per chunk, or null
 
+  __device__ __forceinline__ void drain() {
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    __syncwarp();
+  }
   __device__ __forceinline__ void stamp(int ci, int e) {
     if (fine && lane == 0) fine[ci * 8 + e] = clock64();
   }
 };
 
-// packed 32 x 32 bf16 tile (row per lane, 16 words) -> global, coalesced through a transpose buffer
-__device__ __forceinline__ void fr_store_tile(FusedResid& fr, const uint32_t (&w)[16], void* gbase, long long ld, int row0, int col, int N) {
-  uint8_t* sb = fr.bufs + (FR_XBUFS + (fr.stores & (FR_SBUFS - 1))) * 2048;
-  ++fr.stores;
-  const int lane = fr.lane, sw = (lane >> 1) & 3;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(sb + lane * 64 + ((k ^ sw) << 4)) = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
-  __syncwarp();
-  const int unit = lane & 3;
-  bf16* g = reinterpret_cast<bf16*>(gbase) + col + unit * 8;
-  const bool ok = col + unit * 8 < N;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int row = j * 8 + (lane >> 2);
-    const uint4 v = *reinterpret_cast<const uint4*>(sb + row * 64 + ((unit ^ ((row >> 1) & 3)) << 4));
-    if (ok) *reinterpret_cast<uint4*>(g + (long long)(row0 + row) * ld) = v;
-  }
-}
-
+// raw per-sample vectors of `tile` for this lane's four columns: v[0] = gate, MOD: v[1] = scale, v[2] = shift; ROT: v[1] = (cos, sin)
+// pairs, v[2] = scale or 1.  Only loads: the values are first used (fr_stage_vectors) at the head of the tile they belong to.
 template <int BN>
-__device__ __forceinline__ void fr_load_vectors(const EpiParams& ep, const FusedResid& fr, int tile, float gsc, float inv_den, float4 (&v)[3]) {
-  // v[0] = gate b;  MOD: v[1] = scale (1-g)/den, v[2] = shift g/den;  ROT: v[1] = (cos, sin) pairs, v[2] = scale or 1
+__device__ __forceinline__ void fr_load_vectors(const EpiParams& ep, const FusedResid& fr, int tile, float4 (&v)[3]) {
   constexpr int CSPAN = BN / 2;
   static_assert(CSPAN / 4 <= 32, "one float4 per lane covers the column half");
   const int m_pair = tile / fr.num_n_blocks, n_blk = tile - m_pair * fr.num_n_blocks;
@@ -400,23 +400,36 @@ __device__ __forceinline__ void fr_load_vectors(const EpiParams& ep, const Fused
   const int col = n_blk * BN + fr.half * CSPAN + 4 * fr.lane;
   const long long sample = row0 < ep.M ? row0 / ep.tokens : 0;
   const bool mod = ep.epilogue == MAPDIT_EPI_RESID_MOD, rot = ep.epilogue == MAPDIT_EPI_RESID_ROT;
-  const float res_b = (ep.variant & MAPDIT_VAR_PLAIN_RESID) ? 1.0f : MP_RES_T / MP_RES_DEN;
-  const float mod_a = (1.0f - gsc) * inv_den, mod_b = gsc * inv_den;
-  float4 g = make_float4(0.f, 0.f, 0.f, 0.f), v1 = g, v2 = g;
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  v[0] = z; v[1] = z; v[2] = z;
   if (4 * fr.lane < CSPAN && col < ep.N) {
-    g = *reinterpret_cast<const float4*>(ep.gate + sample * ep.ldmod + col);
-    g.x *= res_b; g.y *= res_b; g.z *= res_b; g.w *= res_b;
+    v[0] = *reinterpret_cast<const float4*>(ep.gate + sample * ep.ldmod + col);
     if (mod) {
-      v1 = *reinterpret_cast<const float4*>(ep.scale + sample * ep.ldmod + col);
-      v2 = *reinterpret_cast<const float4*>(ep.shift + sample * ep.ldmod + col);
-      v1.x *= mod_a; v1.y *= mod_a; v1.z *= mod_a; v1.w *= mod_a;
-      v2.x *= mod_b; v2.y *= mod_b; v2.z *= mod_b; v2.w *= mod_b;
+      v[1] = *reinterpret_cast<const float4*>(ep.scale + sample * ep.ldmod + col);
+      v[2] = *reinterpret_cast<const float4*>(ep.shift + sample * ep.ldmod + col);
     } else if (rot) {
-      v1 = *reinterpret_cast<const float4*>(ep.shift + sample * ep.ldshift + col);
-      v2 = ep.scale ? *reinterpret_cast<const float4*>(ep.scale + sample * ep.ldmod + col) : make_float4(1.f, 1.f, 1.f, 1.f);
+      v[1] = *reinterpret_cast<const float4*>(ep.shift + sample * ep.ldshift + col);
+      v[2] = ep.scale ? *reinterpret_cast<const float4*>(ep.scale + sample * ep.ldmod + col) : make_float4(1.f, 1.f, 1.f, 1.f);
     }
   }
-  v[0] = g; v[1] = v1; v[2] = v2;
+}
+// constants folded in (v0 = gate b; MOD: v1 = scale (1-g)/den, v2 = shift g/den) -> this warp's shared-memory vectors
+template <int BN>
+__device__ __forceinline__ void fr_stage_vectors(const EpiParams& ep, FusedResid& fr, float gsc, float inv_den) {
+  constexpr int CSPAN = BN / 2;
+  const float res_b = (ep.variant & MAPDIT_VAR_PLAIN_RESID) ? 1.0f : MP_RES_T / MP_RES_DEN;
+  float4 g = fr.nv[0], v1 = fr.nv[1], v2 = fr.nv[2];
+  g.x *= res_b; g.y *= res_b; g.z *= res_b; g.w *= res_b;
+  if (ep.epilogue == MAPDIT_EPI_RESID_MOD) {
+    const float mod_a = (1.0f - gsc) * inv_den, mod_b = gsc * inv_den;
+    v1.x *= mod_a; v1.y *= mod_a; v1.z *= mod_a; v1.w *= mod_a;
+    v2.x *= mod_b; v2.y *= mod_b; v2.z *= mod_b; v2.w *= mod_b;
+  }
+  if (4 * fr.lane < CSPAN) {
+    *reinterpret_cast<float4*>(fr.vec + 4 * fr.lane) = g;
+    *reinterpret_cast<float4*>(fr.vec + CSPAN + 4 * fr.lane) = v1;
+    *reinterpret_cast<float4*>(fr.vec + 2 * CSPAN + 4 * fr.lane) = v2;
+  }
 }
 
 // request chunk `s` of this warp's residual stream (no-op past the last tile); clipped column chunks load column 0 so that
@@ -447,18 +460,17 @@ __device__ __forceinline__ void run_tile_fused_resid(const EpiParams& ep, const 
   const int col0 = n_blk * BN + half * CSPAN;
   const bool mod = ep.epilogue == MAPDIT_EPI_RESID_MOD, rot = ep.epilogue == MAPDIT_EPI_RESID_ROT;
   const bool has_h = mod || rot, has_aux = ep.aux != nullptr;
+  const int groups = 1 + (has_h ? 1 : 0) + (has_aux ? 1 : 0);  // bulk groups committed per chunk (empty ones for clipped chunks)
   const bool rows_ok = row0 < ep.M;  // M % 32 == 0: a warp's rows are all inside or all outside
   const float res_a = (ep.variant & MAPDIT_VAR_PLAIN_RESID) ? 1.0f : (1.0f - MP_RES_T) / MP_RES_DEN;
+  uint8_t* abuf = fr.bufs + FR_XBUFS * 2048;
+  uint8_t* hbuf = abuf + 2048;
   const int sw = (lane >> 1) & 3;
 
-  // ---- this tile's per-sample vectors -> shared memory (prefetched during the previous tile's last chunk when there was one)
-  if (fr.nv_tile != tile) fr_load_vectors<BN>(ep, fr, tile, gsc, inv_den, fr.nv);
+  // ---- this tile's per-sample vectors -> shared memory (loaded during the previous tile's last chunk when there was one)
+  if (fr.nv_tile != tile) fr_load_vectors<BN>(ep, fr, tile, fr.nv);
   __syncwarp();  // every lane is done reading the previous tile's vectors
-  if (4 * lane < CSPAN) {
-    *reinterpret_cast<float4*>(fr.vec + 4 * lane) = fr.nv[0];
-    *reinterpret_cast<float4*>(fr.vec + CSPAN + 4 * lane) = fr.nv[1];
-    *reinterpret_cast<float4*>(fr.vec + 2 * CSPAN + 4 * lane) = fr.nv[2];
-  }
+  fr_stage_vectors<BN>(ep, fr, gsc, inv_den);
   __syncwarp();
   wait_acc();
 
@@ -476,18 +488,20 @@ __device__ __forceinline__ void run_tile_fused_resid(const EpiParams& ep, const 
     fr.stamp(ci, 0);
     mbar_wait(&fr.bars[b], (fr.consumed / FR_XBUFS) & 1);
     fr.stamp(ci, 1);
-    const uint8_t* xrow = fr.bufs + b * 2048 + lane * 64;
+    uint8_t* xrow = fr.bufs + b * 2048 + lane * 64;
     uint4 pre[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) pre[k] = *reinterpret_cast<const uint4*>(xrow + ((k ^ sw) << 4));
-    __syncwarp();  // the landing buffer of chunk s-1 has been read by every lane: it receives chunk s+2
-    fr_issue<BN>(ep, tm, fr, fr.consumed + 2);
+    // stores issued a whole chunk ago have read their buffers: aux(s-1) [-> abuf is free], x'(s-2) [-> the next landing buffer]
+    if (lane == 0) bulk_wait_read(has_aux ? groups - 1 : groups);
+    __syncwarp();
+    fr_issue<BN>(ep, tm, fr, fr.consumed + 1);
     ++fr.consumed;
     fr.stamp(ci, 2);
-    if (last) {  // the next tile's vectors: the global loads overlap this chunk
+    if (last) {  // the next tile's vectors: issued here, first used at the head of that tile
       const int nt = tile + fr.tile_stride;
       if (nt < fr.total_tiles) {
-        fr_load_vectors<BN>(ep, fr, nt, gsc, inv_den, fr.nv);
+        fr_load_vectors<BN>(ep, fr, nt, fr.nv);
         fr.nv_tile = nt;
       }
     }
@@ -495,17 +509,26 @@ __device__ __forceinline__ void run_tile_fused_resid(const EpiParams& ep, const 
     if (!last) tmem_ld32(t_row + half * CSPAN + 32 * (ci + 1), rn);
     else release_acc();  // every tcgen05.ld of this tile has completed: the MMA warp may reuse the accumulator stage
     fr.stamp(ci, 3);
-    if (col >= ep.N || !rows_ok) continue;  // clipped chunk (warp-uniform): consumed, nothing to write
+    if (col >= ep.N || !rows_ok) {  // clipped chunk (warp-uniform): nothing to write, but the bulk-group count per chunk stays uniform
+      if (lane == 0)
+        for (int gI = 0; gI < groups; ++gI) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      continue;
+    }
     float f[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(r[j]);
-    uint32_t w[16];
     if (has_aux) {  // raw branch output, needed for d(gate)
 #pragma unroll
-      for (int j = 0; j < 16; ++j) w[j] = pack_bf16(f[2 * j], f[2 * j + 1]);
-      fr_store_tile(fr, w, ep.aux, ep.ldo, row0, col, ep.N);
+      for (int k = 0; k < 4; ++k) {
+        uint4 u;
+        u.x = pack_bf16(f[8 * k + 0], f[8 * k + 1]);
+        u.y = pack_bf16(f[8 * k + 2], f[8 * k + 3]);
+        u.z = pack_bf16(f[8 * k + 4], f[8 * k + 5]);
+        u.w = pack_bf16(f[8 * k + 6], f[8 * k + 7]);
+        *reinterpret_cast<uint4*>(abuf + lane * 64 + ((k ^ sw) << 4)) = u;
+      }
     }
-    // x' = (b gate) acc + a x
+    // x' = (b gate) acc + a x, written back over the residual rows and stored from there
     const float4* vg = reinterpret_cast<const float4*>(fr.vec + 32 * ci);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -517,13 +540,26 @@ __device__ __forceinline__ void run_tile_fused_resid(const EpiParams& ep, const 
         const float2 x2 = __bfloat1622float2(hp[j]);
         f[8 * k + 2 * j] = fmaf(gg[2 * j], f[8 * k + 2 * j], res_a * x2.x);
         f[8 * k + 2 * j + 1] = fmaf(gg[2 * j + 1], f[8 * k + 2 * j + 1], res_a * x2.y);
-        w[4 * k + j] = pack_bf16(f[8 * k + 2 * j], f[8 * k + 2 * j + 1]);
       }
+      uint4 u;
+      u.x = pack_bf16(f[8 * k + 0], f[8 * k + 1]);
+      u.y = pack_bf16(f[8 * k + 2], f[8 * k + 3]);
+      u.z = pack_bf16(f[8 * k + 4], f[8 * k + 5]);
+      u.w = pack_bf16(f[8 * k + 6], f[8 * k + 7]);
+      *reinterpret_cast<uint4*>(xrow + ((k ^ sw) << 4)) = u;
     }
     fr.stamp(ci, 4);
-    fr_store_tile(fr, w, ep.out, ep.ldo, row0, col, ep.N);
+    fence_proxy_async();  // one fence for the aux and the x' rows
+    __syncwarp();
+    if (lane == 0) {
+      if (has_aux) tma_store_2d(&tm.aux, abuf, col, row0);
+      tma_store_2d(&tm.out, fr.bufs + b * 2048, col, row0);
+    }
     fr.stamp(ci, 5);
     if (has_h) {
+      if (lane == 0) bulk_wait_read(groups - 1);  // h(s-1) has been read out of hbuf
+      __syncwarp();
+      fr.stamp(ci, 6);
       const float4* v1 = reinterpret_cast<const float4*>(fr.vec + CSPAN + 32 * ci);
       const float4* v2 = reinterpret_cast<const float4*>(fr.vec + 2 * CSPAN + 32 * ci);
 #pragma unroll
@@ -543,11 +579,16 @@ __device__ __forceinline__ void run_tile_fused_resid(const EpiParams& ep, const 
             h[2 * p + 1] = fmaf(xa, aa[2 * p + 1], xb * aa[2 * p]) * bb[2 * p + 1];
           }
         }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) w[4 * k + j] = pack_bf16(h[2 * j], h[2 * j + 1]);
+        uint4 u;
+        u.x = pack_bf16(h[0], h[1]);
+        u.y = pack_bf16(h[2], h[3]);
+        u.z = pack_bf16(h[4], h[5]);
+        u.w = pack_bf16(h[6], h[7]);
+        *reinterpret_cast<uint4*>(hbuf + lane * 64 + ((k ^ sw) << 4)) = u;
       }
-      fr.stamp(ci, 6);
-      fr_store_tile(fr, w, ep.out2, ep.ldo, row0, col, ep.N);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) tma_store_2d(&tm.out2, hbuf, col, row0);
       fr.stamp(ci, 7);
     }
   }

@@ -189,7 +189,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
       fr.bufs = staging + (warp - 4) * FR_BUF_BYTES_PER_WARP;
       fr.vec = reinterpret_cast<float*>(rstaging + (warp - 4) * fr_vec_bytes_per_warp(BN));
       fr.bars = rbar + FR_XBUFS * (warp - 4);
-      fr.issued = fr.consumed = fr.stores = 0u;
+      fr.consumed = 0u;
       fr.lane = lane;
       fr.first_tile = cluster_id;
       fr.tile_stride = num_clusters;
@@ -199,8 +199,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
       fr.half = half;
       fr.nv_tile = -1;
       fr.fine = nullptr;
-      fr_issue<BN>(ep, etm, fr, 0u);  // the residual stream runs two chunks ahead of its consumer
-      fr_issue<BN>(ep, etm, fr, 1u);
+      fr_issue<BN>(ep, etm, fr, 0u);  // the residual stream runs one chunk ahead of its consumer
     }
     for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
       const int m_pair = tile / num_n_blocks, n_blk = tile - m_pair * num_n_blocks;
@@ -234,7 +233,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
-    if constexpr (!FUSED) st.drain();
+    if constexpr (FUSED) fr.drain();
+    else st.drain();
   }
 
   tc_fence_before();
