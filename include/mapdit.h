@@ -93,6 +93,9 @@ int mapdit_gemm_f32(const float* a, int64_t sam, int64_t sak, const float* b, in
 #define MAPDIT_EPI_RESID_ROT 6  /* x' = mp_sum(x, gate*acc, .3); h = R(theta) x' (* scale): rotation modulation (README.md:1,3 of the
                                    reference; no reference code, SURVEY.md §A.8 — UNPINNED).  `shift` points at the per-sample
                                    (cos, sin) table of mapdit_rot_table (leading dimension `ldrot`), `scale` may be null  */
+#define MAPDIT_EPI_STORE_DELTA 7 /* out = acc (bf16) and aux[row, head] (fp32, [M, N/64]) = sum over the head's 64 columns of
+                                  * bf16(acc) * resid: the out-proj dgrad that also emits delta = dO.O for the attention backward
+                                  * (autograd of F.scaled_dot_product_attention, src/layers/attention.py:47); N % 64 == 0 */
 
 typedef struct mapdit_gemm_args {
   const void* a;   /* bf16 [M, K] */
@@ -171,7 +174,9 @@ int mapdit_cast_2d(const void* src, int64_t ld_src, void* dst, int64_t ld_dst, i
  * bf16: tcgen05/TMEM kernel.                                                                   */
 int mapdit_cos_attn_fwd(const void* qkv, void* o, float* lse /* nullable: [M, H] log-sum-exp for the backward */,
                         int n_samples, int tokens, int heads, int head_dim, int dtype, void* stream);
-/* dqkv[M, 3D] <- d/d(q^, k^, v) from dout[M, D]; delta: [M, H] fp32 scratch (src/layers/attention.py:47 autograd) */
+/* dqkv[M, 3D] <- d/d(q^, k^, v) from dout[M, D]; delta: [M, H] fp32 scratch (src/layers/attention.py:47 autograd).
+ * o may be NULL on the fused bf16 path (head_dim 64, tokens == 256) when `delta` already holds dO.O per (row, head), as the
+ * MAPDIT_EPI_STORE_DELTA epilogue of the out-proj dgrad GEMM leaves it */
 int mapdit_cos_attn_bwd(const void* qkv, const void* o, const void* dout, const float* lse, void* dqkv, float* delta,
                         int n_samples, int tokens, int heads, int head_dim, int dtype, void* stream);
 

@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmapdit.so")
 
 F32, BF16 = 0, 1
-EPI_STORE, EPI_QKNORM, EPI_MPSILU, EPI_RESID_MOD, EPI_RESID, EPI_SILU_BWD, EPI_RESID_ROT = 0, 1, 2, 3, 4, 5, 6
+EPI_STORE, EPI_QKNORM, EPI_MPSILU, EPI_RESID_MOD, EPI_RESID, EPI_SILU_BWD, EPI_RESID_ROT, EPI_STORE_DELTA = 0, 1, 2, 3, 4, 5, 6, 7
 
 _p, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 

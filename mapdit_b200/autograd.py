@@ -50,6 +50,7 @@ class Trainer:
         # memory, so the HBM-bound elementwise backward kernels of the main stream co-reside with them on every SM instead
         # of running alone on an idle tensor pipe.  MAPDIT_WGRAD_STREAM=0 turns it off (A/B in bench.py --wgrad-stream).
         self.wgrad_stream = os.environ.get("MAPDIT_WGRAD_STREAM", "1") != "0"
+        self.fuse_delta = os.environ.get("MAPDIT_FUSE_DELTA", "1") != "0"  # delta = dO.O from the out-proj dgrad epilogue
         self._side = None      # the second stream
         self._side_on = False  # active inside the current backward
         self._side_reads = {}  # scratch buffer name -> event recorded after the side-stream GEMM that last read it
@@ -511,10 +512,16 @@ class Trainer:
                 self._before_write("dYa")
                 ops.resid_bwd(R, a, dYa, mod(mods, i, "gate_a"), mod(dmods, i, "gate_a"), ld, N, T)
             self._wgrad(dYa, o, blk[i].attn.out_proj.weight, bf, B, grads, reads="dYa")
-            self._dgrad(dYa, W.wo[i], wt("wo_t"), dh, bf)
+            # bf16, 256 tokens, head_dim 64: the out-proj dgrad GEMM also emits delta = dO.O per (row, head) in its epilogue, so the
+            # fused attention backward does not need a separate pass over dO and O
+            fuse_delta = bf and cosine and hd == 64 and T == 256 and self.fuse_delta
+            if fuse_delta:
+                ops.gemm_bf16(dYa, W.wo_t[i], dh, epilogue=_lib.EPI_STORE_DELTA, resid=o, aux=B["delta"])
+            else:
+                self._dgrad(dYa, W.wo[i], wt("wo_t"), dh, bf)
             self._before_write("dqkv")
             if cosine:  # attention backward with the q/k normalisation backward fused into its dq / dk epilogues
-                ops.cos_attn_bwd_qknorm(qkv, o, dh, B["lse"][i], B["sc"][i], dqkv, B["delta"], N, T, H, hd)
+                ops.cos_attn_bwd_qknorm(qkv, None if fuse_delta else o, dh, B["lse"][i], B["sc"][i], dqkv, B["delta"], N, T, H, hd)
             else:
                 ops.cos_attn_bwd(qkv, o, dh, B["lse"][i], dqkv, B["delta"], N, T, H, hd)
             self._wgrad(dqkv, h1, blk[i].attn.qkv_proj.weight, bf, B, grads, reads="dqkv")

@@ -1445,7 +1445,11 @@ extern "C" int mapdit_qk_norm_bwd(void* dqkv, const void* qkv, const float* sc, 
 // as well (fused into the dq / dk epilogues on the tcgen05 path, a separate kernel behind the CUDA-core path).
 static int attn_bwd_impl(const void* qkv, const void* o, const void* dout, const float* lse, const float* sc, float eps, void* dqkv,
                          float* delta, int n_samples, int tokens, int heads, int head_dim, int dtype, void* stream) {
-  MAPDIT_REQUIRE(qkv && o && dout && lse && dqkv && delta && n_samples > 0 && tokens > 0, "cos_attn_bwd: bad args");
+  MAPDIT_REQUIRE(qkv && dout && lse && dqkv && delta && n_samples > 0 && tokens > 0, "cos_attn_bwd: bad args");
+  // o == NULL: `delta` already holds dO.O (the out-proj dgrad GEMM produced it, MAPDIT_EPI_STORE_DELTA): only the fused kernel
+  // takes that shortcut, every other path computes delta itself from o
+  const bool fused_path = dtype == MAPDIT_BF16 && head_dim == HD && tokens == F_T && g_mapdit_attn_bwd_fused && !(mapdit_variant() & MAPDIT_VAR_DOT_ATTN);
+  MAPDIT_REQUIRE(o || fused_path, "cos_attn_bwd: o may only be omitted (delta precomputed) on the fused tokens == 256 path");
   if (!(dtype == MAPDIT_BF16 && head_dim == HD && tokens % CB == 0) || (mapdit_variant() & MAPDIT_VAR_DOT_ATTN)) {
     int rc = (dtype == MAPDIT_BF16 && mapdit_attn_mma_supported(tokens, head_dim))
                  ? mapdit_attn_mma_bwd(qkv, o, dout, lse, dqkv, delta, n_samples, tokens, heads, head_dim, stream)
@@ -1482,9 +1486,11 @@ static int attn_bwd_impl(const void* qkv, const void* o, const void* dout, const
       }
       fattr = true;
     }
-    const long long mh = (long long)rows * heads;
-    attn_delta_kernel<<<(unsigned)((mh + 255) / 256), 256, 0, s>>>((const bf16*)o, (const bf16*)dout, delta, mh, heads);
-    MAPDIT_LAUNCH_CHECK("cos_attn_bwd(delta)");
+    if (o) {
+      const long long mh = (long long)rows * heads;
+      attn_delta_kernel<<<(unsigned)((mh + 255) / 256), 256, 0, s>>>((const bf16*)o, (const bf16*)dout, delta, mh, heads);
+      MAPDIT_LAUNCH_CHECK("cos_attn_bwd(delta)");
+    }
     const int items = n_samples * heads;
     int sms = 0, dev = 0;
     cudaGetDevice(&dev);

@@ -163,7 +163,7 @@ __device__ __forceinline__ void load_row32_f32(const float* p, float (&f)[32], i
 // One epilogue warp's share of one accumulator tile.  `half` = which of the two warps of a TMEM lane quarter (alternate
 // column chunks).  `wait_acc()` blocks until the accumulator is complete; it is called after the first residual prefetch
 // has been issued so the global-load latency overlaps the tail of the main loop.
-template <int BN, typename WaitFn>
+template <int BN, bool WITH_DELTA = true, typename WaitFn>
 __device__ __forceinline__ void run_tile(const EpiParams& ep, const EpiTmaps& tm, Stager& st, uint32_t t_row, int row, int n_blk, int half,
                                          float gsc, float inv_den, WaitFn wait_acc, ResidLoader* rl = nullptr) {
   const bool mod2 = ep.epilogue == MAPDIT_EPI_RESID_MOD || ep.epilogue == MAPDIT_EPI_RESID_ROT;  // writes h to out2
@@ -204,6 +204,11 @@ __device__ __forceinline__ void run_tile(const EpiParams& ep, const EpiTmaps& tm
   const int c_begin = half * CSPAN, c_end = BN >= 64 ? c_begin + CSPAN : (half == 0 ? BN : 0);
   prefetch_vecs(c_begin);
   if (reads_resid && c_begin < c_end) prefetch(c_begin);
+  if (WITH_DELTA && ep.epilogue == MAPDIT_EPI_STORE_DELTA && rl && half * 64 < BN && n_blk * BN + half * 64 < ep.N) {
+    rl->row0 = st.row0;
+    rl->issue(n_blk * BN + half * 64);
+    rl->issue(n_blk * BN + half * 64 + 32);
+  }
   const float silu_mul = (ep.variant & MAPDIT_VAR_PLAIN_SILU) ? 1.0f : 1.0f / MP_SILU_DIV;
   const bool plain_res = ep.variant & MAPDIT_VAR_PLAIN_RESID;
   const float res_a = plain_res ? 1.0f : (1.0f - MP_RES_T) / MP_RES_DEN, res_b = plain_res ? 1.0f : MP_RES_T / MP_RES_DEN;
@@ -239,6 +244,60 @@ __device__ __forceinline__ void run_tile(const EpiParams& ep, const EpiTmaps& tm
         }
         st.store(&tm.out, f0, col);
         st.store(&tm.out, f1, col + 32);
+      }
+    }
+    return;
+  }
+  if (WITH_DELTA && ep.epilogue == MAPDIT_EPI_STORE_DELTA) {
+    // out = acc; delta[row, head] = sum over the head's 64 columns of bf16(acc) * o (`resid`): the out-proj dgrad emits the
+    // attention backward's delta = dO.O, so no separate pass re-reads dO and O from HBM
+    if constexpr (BN % 64 == 0) {
+      for (int c = half * 64; c < BN; c += 128) {
+        const int col = n_blk * BN + c;
+        if (col >= ep.N) break;  // warp-uniform (N % 64 == 0)
+        uint32_t r0[32], r1[32];
+        tmem_ld32(t_row + c, r0);
+        tmem_ld32(t_row + c + 32, r1);
+        uint4 oa[4], ob[4];
+        if (rl) {  // both 32-column chunks were requested before the accumulator wait (first group) or one group ago
+          rl->consume(oa);
+          rl->consume(ob);
+          if (c + 128 < BN && col + 128 < ep.N) {
+            rl->issue(col + 128);
+            rl->issue(col + 160);
+          }
+        } else {
+          const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(ep.resid) + (long long)row * ep.ldo + col);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            oa[g] = row_ok ? src[g] : make_uint4(0, 0, 0, 0);
+            ob[g] = row_ok ? src[4 + g] : make_uint4(0, 0, 0, 0);
+          }
+        }
+        tmem_ld_wait();
+        float dl = 0.f;
+        // one 32-column chunk at a time (keeps the live registers below the 168 the kernel has): the attention backward reads dO
+        // as bf16, so the dot product uses the rounded values
+        auto chunk = [&](const uint32_t (&r)[32], const uint4 (&ov)[4], int ccol) {
+          float f[32];
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const __nv_bfloat162* ho = reinterpret_cast<const __nv_bfloat162*>(&ov[g]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int e = g * 8 + 2 * j;
+              const float2 d = __bfloat1622float2(__floats2bfloat162_rn(__uint_as_float(r[e]), __uint_as_float(r[e + 1])));
+              const float2 a = __bfloat1622float2(ho[j]);
+              f[e] = d.x;
+              f[e + 1] = d.y;
+              dl = fmaf(d.x, a.x, fmaf(d.y, a.y, dl));
+            }
+          }
+          st.store(&tm.out, f, ccol);
+        };
+        chunk(r0, oa, col);
+        chunk(r1, ob, col + 32);
+        if (row_ok) reinterpret_cast<float*>(ep.aux)[(long long)row * (ep.N >> 6) + (col >> 6)] = dl;
       }
     }
     return;
@@ -599,7 +658,8 @@ inline int make_store_maps(EpiTmaps* tm, const EpiParams& ep) {
   const uint64_t dims[2] = {(uint64_t)ep.N, (uint64_t)ep.M};
   const uint64_t strides[1] = {(uint64_t)ep.ldo * 2};
   const uint32_t box[2] = {32, 32};
-  void* outs[4] = {ep.out, ep.out2 ? ep.out2 : ep.out, (ep.aux && ep.epilogue != MAPDIT_EPI_QKNORM) ? ep.aux : ep.out,
+  void* outs[4] = {ep.out, ep.out2 ? ep.out2 : ep.out,
+                   (ep.aux && ep.epilogue != MAPDIT_EPI_QKNORM && ep.epilogue != MAPDIT_EPI_STORE_DELTA) ? ep.aux : ep.out,
                    ep.resid ? const_cast<void*>(ep.resid) : ep.out};
   CUtensorMap* maps[4] = {&tm->out, &tm->out2, &tm->aux, &tm->resid};
   for (int i = 0; i < 4; ++i) {

@@ -272,7 +272,9 @@ extern "C" int mapdit_gemm_bf16(const mapdit_gemm_args* g, void* stream) {
     post_qknorm = true;
   }
   if (epi == MAPDIT_EPI_SILU_BWD) MAPDIT_REQUIRE(g->resid != nullptr, "gemm_bf16: SILU_BWD epilogue needs the pre-activation in `resid`");
-  MAPDIT_REQUIRE(epi >= MAPDIT_EPI_STORE && epi <= MAPDIT_EPI_RESID_ROT, "gemm_bf16: unknown epilogue");
+  MAPDIT_REQUIRE(epi >= MAPDIT_EPI_STORE && epi <= MAPDIT_EPI_STORE_DELTA, "gemm_bf16: unknown epilogue");
+  if (epi == MAPDIT_EPI_STORE_DELTA)
+    MAPDIT_REQUIRE(g->resid && g->aux && g->n % 64 == 0, "gemm_bf16: STORE_DELTA epilogue needs o in `resid`, delta in `aux` and N % 64 == 0");
   if (epi == MAPDIT_EPI_RESID || epi == MAPDIT_EPI_RESID_MOD || epi == MAPDIT_EPI_RESID_ROT) {
     MAPDIT_REQUIRE(g->resid && g->gate && g->tokens > 0 && g->ldmod % 4 == 0, "gemm_bf16: residual epilogue needs resid/gate/tokens");
     if (epi == MAPDIT_EPI_RESID_MOD) MAPDIT_REQUIRE(g->out2 && g->shift && g->scale && g->gain, "gemm_bf16: modulate epilogue needs out2/shift/scale/gain");
@@ -298,7 +300,7 @@ extern "C" int mapdit_gemm_bf16(const mapdit_gemm_args* g, void* stream) {
     if (rc2 != MAPDIT_ERR_UNSUPPORTED) return rc2;
   }
   const int mb = (g->m + BM - 1) / BM;
-  const bool need64 = (epi == MAPDIT_EPI_QKNORM);
+  const bool need64 = (epi == MAPDIT_EPI_QKNORM || epi == MAPDIT_EPI_STORE_DELTA);
   // largest BN that divides N and still yields >= 2 waves of tiles; otherwise the smallest legal one
   const int cand[5] = {256, 192, 128, 64, 32};
   int bn = 0;

@@ -20,8 +20,9 @@ constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;  // clears the CTA-parity bit of a s
 
 // FUSED = the second-generation residual epilogues (run_tile_fused_resid): per-warp staging of 5 tile buffers + the per-sample
 // vectors instead of the 2 + 2 buffers of the generic path; one operand stage less for BN = 256 (4 instead of 5)
-template <int BN, bool FUSED>
+template <int BN, int KIND>
 struct Cfg2 {
+  static constexpr bool FUSED = KIND == 1;  // KIND: 0 = generic epilogues, 1 = second-generation residual epilogues, 2 = generic + STORE_DELTA
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int BH_BYTES = (BN / 2) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + BH_BYTES;
@@ -75,12 +76,13 @@ __device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr) {
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
 }
 
-template <int BN, bool FUSED>
+template <int BN, int KIND>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                 const __grid_constant__ EpiTmaps etm, const EpiParams ep,
                 int num_m_blocks, int num_n_blocks, int num_k_blocks, long long* __restrict__ dbg) {
-  using C = Cfg2<BN, FUSED>;
+  using C = Cfg2<BN, KIND>;
+  constexpr bool FUSED = C::FUSED;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -224,7 +226,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
         });
         if (dbg && blockIdx.x == 0 && lane == 0 && tcount < 16) dbg[(warp - 4) * 64 + tcount * 4 + 2] = clock64();
       } else {
-        run_tile<BN>(ep, etm, st, t_row, row, n_blk, half, gsc, inv_den, wait_acc, &rl);
+        // the STORE_DELTA branch lives in its own instantiation: compiled into the generic one it pushed the kernel past its 168
+        // registers (104 bytes of spills)
+        run_tile<BN, KIND == 2>(ep, etm, st, t_row, row, n_blk, half, gsc, inv_den, wait_acc, &rl);
         tc_fence_before();
         __syncwarp();
         if (dbg && blockIdx.x == 0 && lane == 0 && tcount < 16) dbg[(warp - 4) * 64 + tcount * 4 + 2] = clock64();
@@ -242,9 +246,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
   if (warp == 2) tmem_dealloc_2cta<C::TMEM_COLS>(tmem_base);
 }
 
-template <int BN, bool FUSED>
+template <int BN, int KIND>
 int launch2(const mapdit_gemm_args* g, const EpiParams& ep, cudaStream_t stream, int num_sms) {
-  using C = Cfg2<BN, FUSED>;
+  using C = Cfg2<BN, KIND>;
   CUtensorMap ta, tb;
   const uint64_t dims_a[2] = {(uint64_t)g->k, (uint64_t)g->m}, dims_b[2] = {(uint64_t)g->k, (uint64_t)g->n};
   const uint64_t str_a[1] = {(uint64_t)g->lda * 2}, str_b[1] = {(uint64_t)g->ldb * 2};
@@ -257,7 +261,7 @@ int launch2(const mapdit_gemm_args* g, const EpiParams& ep, cudaStream_t stream,
   }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<BN, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<BN, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) {
       mapdit_set_error("gemm_bf16(2cta): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return MAPDIT_ERR_CUDA;
@@ -273,7 +277,7 @@ int launch2(const mapdit_gemm_args* g, const EpiParams& ep, cudaStream_t stream,
     mapdit_set_error("gemm_bf16(2cta): cuTensorMapEncodeTiled (store maps) failed");
     return MAPDIT_ERR_CUDA;
   }
-  gemm_tc2_kernel<BN, FUSED><<<2 * clusters, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, etm, ep, mb, nb, kb, g_attn_dbg);
+  gemm_tc2_kernel<BN, KIND><<<2 * clusters, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, etm, ep, mb, nb, kb, g_attn_dbg);
   return MAPDIT_OK;
 }
 
@@ -290,7 +294,8 @@ bool fused_resid_ok(const mapdit_gemm_args* g, const EpiParams& ep) {
 }
 template <int BN>
 int launch2_any(const mapdit_gemm_args* g, const EpiParams& ep, cudaStream_t stream, int num_sms) {
-  return fused_resid_ok(g, ep) ? launch2<BN, true>(g, ep, stream, num_sms) : launch2<BN, false>(g, ep, stream, num_sms);
+  if (ep.epilogue == MAPDIT_EPI_STORE_DELTA) return launch2<BN, 2>(g, ep, stream, num_sms);
+  return fused_resid_ok(g, ep) ? launch2<BN, 1>(g, ep, stream, num_sms) : launch2<BN, 0>(g, ep, stream, num_sms);
 }
 }  // namespace
 

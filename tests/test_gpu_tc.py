@@ -163,3 +163,45 @@ def test_cos_attn_bf16(N, T, H, v2):
     # P is rounded to bf16 before the PV product on the tensor-core path
     assert rel_l2(o.float(), ref) < 6e-3
     assert float((lse.double() - ref_lse).abs().max()) < 2e-2
+
+
+@pytest.mark.parametrize("N,T,H", [(2, 256, 4), (30, 256, 12), (80, 256, 4), (16, 256, 18), (3, 64, 6)])
+@pytest.mark.parametrize("two_cta", [0, 1])
+def test_gemm_store_delta_epilogue_and_attention_backward_without_o(N, T, H, two_cta):
+    """MAPDIT_EPI_STORE_DELTA: the out-proj dgrad GEMM also emits delta[row, head] = dO.O (autograd of SDPA,
+    src/layers/attention.py:47), and the fused attention backward accepts it in place of o (o = NULL)"""
+    from mapdit_b200 import _lib, ops
+    D, M, hd = H * 64, N * T, 64
+    _lib.set_option("gemm_2cta", two_cta)
+    try:
+        dy, wt = rnd(M, D, seed=21).bfloat16(), rnd(D, D, seed=22, scale=D ** -0.5).bfloat16()
+        o = rnd(M, D, seed=23).bfloat16()
+        plain = torch.empty(M, D, device="cuda", dtype=torch.bfloat16)
+        ops.gemm_bf16(dy, wt, plain)
+        dh = torch.full_like(plain, float("nan"))
+        delta = torch.full((M, H), float("nan"), device="cuda")
+        ops.gemm_bf16(dy, wt, dh, epilogue=_lib.EPI_STORE_DELTA, resid=o, aux=delta)
+        assert torch.equal(dh, plain)
+        ref = (plain.double() * o.double()).view(M, H, hd).sum(-1)
+        assert rel_l2(delta, ref) < 1e-5
+    finally:
+        _lib.set_option("gemm_2cta", 1)
+    if T != 256:
+        return
+    qkv = rnd(M, 3 * D, seed=24)
+    sc = torch.empty(M, 2 * H, device="cuda")
+    ops.qk_normalize_save(qkv, sc, D, hd)
+    qkv = qkv.bfloat16()
+    att = torch.empty(M, D, device="cuda", dtype=torch.bfloat16)
+    lse = torch.empty(M, H, device="cuda")
+    ops.cos_attn(qkv, att, N, T, H, hd, lse=lse)
+    d_ref, d_new = torch.full_like(qkv, float("nan")), torch.full_like(qkv, float("nan"))
+    delta_ref = torch.empty(M, H, device="cuda")
+    ops.cos_attn_bwd_qknorm(qkv, att, dh, lse, sc, d_ref, delta_ref, N, T, H, hd)
+    delta2 = torch.full((M, H), float("nan"), device="cuda")
+    ops.gemm_bf16(dy, wt, dh, epilogue=_lib.EPI_STORE_DELTA, resid=att, aux=delta2)
+    assert rel_l2(delta2, delta_ref) < 1e-5
+    ops.cos_attn_bwd_qknorm(qkv, None, dh, lse, sc, d_new, delta2, N, T, H, hd)
+    assert rel_l2(d_new.float(), d_ref.float()) < 2e-3
+    with pytest.raises(RuntimeError):  # delta can only be handed over on the fused tokens == 256 path
+        ops.cos_attn_bwd_qknorm(qkv[: 2 * 64], None, dh[: 2 * 64], lse[: 2 * 64], sc[: 2 * 64], d_new[: 2 * 64], delta2[: 2 * 64], 2, 64, H, hd)

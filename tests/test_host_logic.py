@@ -200,6 +200,6 @@ def test_epilogue_and_variant_constants_match_header():
     from mapdit_b200 import _lib
     hdr = open(os.path.join(ROOT, "include", "mapdit.h")).read()
     defs = {k: int(v, 0) for k, v in re.findall(r"#define\s+(MAPDIT_[A-Z0-9_]+)\s+(-?(?:0x[0-9a-fA-F]+|\d+))\b", hdr)}
-    for name in ("STORE", "QKNORM", "MPSILU", "RESID_MOD", "RESID", "SILU_BWD", "RESID_ROT"):
+    for name in ("STORE", "QKNORM", "MPSILU", "RESID_MOD", "RESID", "SILU_BWD", "RESID_ROT", "STORE_DELTA"):
         assert defs[f"MAPDIT_EPI_{name}"] == getattr(_lib, f"EPI_{name}"), name
-    assert len({defs[k] for k in defs if k.startswith("MAPDIT_EPI_")}) == 7  # no two selectors share a value
+    assert len({defs[k] for k in defs if k.startswith("MAPDIT_EPI_")}) == 8  # no two selectors share a value
