@@ -50,7 +50,10 @@ class Trainer:
         # memory, so the HBM-bound elementwise backward kernels of the main stream co-reside with them on every SM instead
         # of running alone on an idle tensor pipe.  MAPDIT_WGRAD_STREAM=0 turns it off (A/B in bench.py --wgrad-stream).
         self.wgrad_stream = os.environ.get("MAPDIT_WGRAD_STREAM", "1") != "0"
-        self.fuse_delta = os.environ.get("MAPDIT_FUSE_DELTA", "1") != "0"  # delta = dO.O from the out-proj dgrad epilogue
+        # delta = dO.O from the out-proj dgrad epilogue (MAPDIT_EPI_STORE_DELTA) instead of a separate pass over dO and O.  Off by
+        # default: measured on DiT-B/2 batch 256 the step does not get faster (43.6 ms with, 43.3 ms without, call c12 of round 2):
+        # the epilogue's residual-tile round trips cost the K = 768 dgrad GEMM more than the 35 us kernel it replaces
+        self.fuse_delta = os.environ.get("MAPDIT_FUSE_DELTA", "0") == "1"
         self._side = None      # the second stream
         self._side_on = False  # active inside the current backward
         self._side_reads = {}  # scratch buffer name -> event recorded after the side-stream GEMM that last read it

@@ -98,7 +98,7 @@ __device__ __forceinline__ void tmem_ld1(uint32_t taddr, uint32_t& v) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
 }
 
-template <int MODE, bool POLY>
+template <int MODE>
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, bf16* __restrict__ o,
                 float* __restrict__ lse, int tokens, int heads, int n_samples, long long* __restrict__ dbg) {
@@ -319,7 +319,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         tmem_ld_wait();
         if (c + 1 < KB / 32) tmem_ld32(t_s + (c + 1) * 32, nxt);
         uint32_t pk[16];
-        exp_chunk<POLY>(cur, pk, c1, c2);
+        exp_chunk<false>(cur, pk, c1, c2);
         tmem_st16(t_s + c * 16, pk);
       }
       if (x == 0) asm volatile("bar.arrive 2, 256;" ::: "memory");  // the exponentials are issued: the other tile's turn
@@ -342,20 +342,20 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       tmem_ld32(t_s + 64, sa);
       tmem_ld_wait();
       tmem_ld32(t_s + 96, sb);
-      exp_chunk<POLY>(sa, pk, c1, c2);
+      exp_chunk<true>(sa, pk, c1, c2);
       tmem_st16(t_s + 64, pk);
       tmem_ld_wait();
-      exp_chunk<POLY>(sb, pk, c1, c2);
+      exp_chunk<true>(sb, pk, c1, c2);
       tmem_st16(t_s + 80, pk);
       mbar_wait(&s_full[2 * x], par);
       tc_fence_after();
       tmem_ld32(t_s, sa);
       tmem_ld_wait();
       tmem_ld32(t_s + 32, sb);
-      exp_chunk<POLY>(sa, pk, c1, c2);
+      exp_chunk<true>(sa, pk, c1, c2);
       tmem_st16(t_s, pk);
       tmem_ld_wait();
-      exp_chunk<POLY>(sb, pk, c1, c2);
+      exp_chunk<true>(sb, pk, c1, c2);
       tmem_st16(t_s + 16, pk);
       if (x == 0) asm volatile("bar.arrive 2, 256;" ::: "memory");  // the exponentials are issued: the other tile's turn
       else asm volatile("bar.arrive 1, 256;" ::: "memory");
@@ -436,10 +436,8 @@ int mapdit_attn_tc2_fwd(const void* qkv, void* o, float* lse, int n, int tokens,
   }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_tc2_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_tc2_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_tc2_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_tc2_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(attn_tc2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) {
       mapdit_set_error("attn_tc2_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return MAPDIT_ERR_CUDA;
@@ -451,11 +449,10 @@ int mapdit_attn_tc2_fwd(const void* qkv, void* o, float* lse, int n, int tokens,
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
   const int grid = items < sms ? items : sms;  // persistent, one CTA per SM (512 TMEM columns)
   extern int g_mapdit_attn_v2;  // 1 = split-S + polynomial exp2 (MODE 1), 2 = the round-1 schedule (MODE 0)
-  const cudaStream_t st = (cudaStream_t)stream;
-  if (g_mapdit_attn_v2 == 2 || KB != 128) attn_tc2_kernel<0, false><<<grid, NTHREADS, SMEM_BYTES, st>>>(tq, tkv, (bf16*)o, lse, tokens, heads, n, g_attn_dbg);
-  else if (g_mapdit_attn_v2 == 4) attn_tc2_kernel<0, true><<<grid, NTHREADS, SMEM_BYTES, st>>>(tq, tkv, (bf16*)o, lse, tokens, heads, n, g_attn_dbg);
-  else if (g_mapdit_attn_v2 == 5) attn_tc2_kernel<1, false><<<grid, NTHREADS, SMEM_BYTES, st>>>(tq, tkv, (bf16*)o, lse, tokens, heads, n, g_attn_dbg);
-  else attn_tc2_kernel<1, true><<<grid, NTHREADS, SMEM_BYTES, st>>>(tq, tkv, (bf16*)o, lse, tokens, heads, n, g_attn_dbg);
+  if (g_mapdit_attn_v2 == 2 || KB != 128)
+    attn_tc2_kernel<0><<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tq, tkv, (bf16*)o, lse, tokens, heads, n, g_attn_dbg);
+  else
+    attn_tc2_kernel<1><<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tq, tkv, (bf16*)o, lse, tokens, heads, n, g_attn_dbg);
   MAPDIT_LAUNCH_CHECK("attn_tc2_fwd");
   return MAPDIT_OK;
 }

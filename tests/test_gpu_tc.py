@@ -139,11 +139,10 @@ def _fused_epilogues(N, T, D):
         assert torch.equal(xo2, xio) and torch.equal(hout2, hout) and rel_l2(aux.float(), y) < 3e-3
 
 
-@pytest.mark.parametrize("v2", [1, 2, 0])
+@pytest.mark.parametrize("v2", [1, 0])
 @pytest.mark.parametrize("N,T,H", [(2, 256, 6), (3, 64, 4), (1, 1024, 2), (5, 256, 12), (2, 128, 4), (40, 256, 12), (3, 512, 5)])
 def test_cos_attn_bf16(N, T, H, v2):
-    """the tcgen05 forward kernels (attn_v2 = 1: one CTA per SM, P in TMEM, ones-column row sum, split-S schedule with 3/8 of the
-    exponentials on the FMA pipe; 2: the same kernel with the round-1 schedule and MUFU-only exponentials; 0: v1, P through smem)"""
+    """both tcgen05 forward kernels (attn_v2: one CTA per SM, P in TMEM, ones-column row sum; v1: P through smem)"""
     from mapdit_b200 import _lib, ops
     hd, D = 64, H * 64
     qkv = rnd(N * T, 3 * D, seed=9)

@@ -11,7 +11,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from mapdit_b200 import _lib, ops  # noqa: E402
 
 if len(sys.argv) > 2:
-    _lib.set_option("attn_v2", int(sys.argv[2]))  # 1 = split-S + polynomial exp2, 2 = round-1 schedule
+    _lib.set_option("attn_v2", int(sys.argv[2]))
 D, T, H, B = 768, 256, 12, 256
 M = B * T
 qkv = torch.randn(M, 3 * D, device="cuda").bfloat16()
