@@ -20,16 +20,6 @@
 // (Sixteen softmax warps, two per lane quarter splitting the key columns behind a pair barrier, measured 11 % slower.)
 // TMEM (512 columns): S_A/P_A buffers [0,64) [64,128)  S_B/P_B [128,192) [192,256)  O_A [256,336)  O_B [352,432).
 // Logits are bounded (|q.k|/8 <= 8): p = exp(logit - 8), no running max, no rescaling of O.
-//
-// MODE 1 (default, round 2).  The v2 timeline (profiles/r1_attn_ncu_summary.md) had, per tile and 128-key step, an exp phase of
-// ~1440 clocks (MUFU floor 1024) and then ~1500 clocks in which the tile's softmax warps wait for PV(g) and S(g+1): with the two
-// tiles alternating, a step costs max(2 exp, exp + MMA phase) and both terms were ~2900.  Two changes shorten both:
-//   * split S: the 128 logit columns of a step are produced and consumed as two 64-key halves.  P of the upper half is packed in
-//     place over its own S columns ([64, 96) instead of [32, 64)), so after P(g) is published the issuer runs PV_hi(g), S_hi(g+1),
-//     PV_lo(g), S_lo(g+1): the upper half of S(g+1) is ready after ~0.3 of the MMA work instead of all of it, and the softmax
-//     warps exponentiate it while the tensor core finishes the rest;
-//   * 3 of every 8 exponentials leave the MUFU for the FMA pipe: 2^t = 2^round(t) * p(t - round(t)) with a degree-3 minimax
-//     polynomial (rel. error 7.5e-5, a fiftieth of the bf16 rounding P gets anyway), round / scale through the 1.5 * 2^23 trick.
 #include "tc_common.cuh"
 
 namespace {
@@ -58,25 +48,6 @@ __device__ __forceinline__ float ex2f(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// 2^t for t in [-100, 0] on the FMA / integer pipes (no MUFU): n = round(t) through the 1.5 * 2^23 trick, degree-3 minimax
-// polynomial for 2^f on f = t - n in [-0.5, 0.5] (max rel. error 7.5e-5), n added into the exponent field
-__device__ __forceinline__ float exp2_poly(float t) {
-  const float magic = 12582912.0f;
-  const float y = __fadd_rn(t, magic);
-  const float f = __fsub_rn(t, __fsub_rn(y, magic));
-  const float p = fmaf(fmaf(fmaf(0.0551716648f, f, 0.2426111251f), f, 0.6932609677f), f, 0.9999280572f);
-  return __int_as_float(__float_as_int(p) + (__float_as_int(y) << 23));
-}
-// p = 2^(s c1 - c2) for the 32 logits of a chunk, packed as 16 bf16 pairs.  POLY: elements 0, 3 and 6 of every 8 take the polynomial.
-template <bool POLY>
-__device__ __forceinline__ void exp_chunk(const uint32_t (&cur)[32], uint32_t (&pk)[16], float c1, float c2) {
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const float a = fmaf(__uint_as_float(cur[2 * i]), c1, -c2), b = fmaf(__uint_as_float(cur[2 * i + 1]), c1, -c2);
-    const bool pa = POLY && (((2 * i) & 7) == 0 || ((2 * i) & 7) == 6), pb = POLY && ((2 * i + 1) & 7) == 3;
-    pk[i] = pack_bf16(pa ? exp2_poly(a) : ex2f(a), pb ? exp2_poly(b) : ex2f(b));
-  }
-}
 // D[tmem] (+)= A[tmem] * B[smem]
 __device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -98,7 +69,6 @@ __device__ __forceinline__ void tmem_ld1(uint32_t taddr, uint32_t& v) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
 }
 
-template <int MODE>
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, bf16* __restrict__ o,
                 float* __restrict__ lse, int tokens, int heads, int n_samples, long long* __restrict__ dbg) {
@@ -209,7 +179,6 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         // the query tiles of an item are free once S_B of its last key block has been issued
         if (leader && g - it * nkb + 1 == (uint32_t)nkb) umma_commit(&q_empty[it & 1]);
       };
-      if constexpr (MODE == 0) {
       for (uint32_t g = 0; g < (uint32_t)SBUF && g < total_steps; ++g) issue_s(g);
       for (uint32_t g = 0; g < total_steps; ++g) {
         const uint32_t it = g / nkb, j = g - it * nkb, b = g % SBUF;
@@ -231,61 +200,6 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           DBG(x, g, 1);  // MMA warp: PV_x(g) and S_x(g+2) issued
         }
       }
-      } else {
-        // ---- split-S schedule (KB == 128, one S buffer per tile): halves hf = 1 (keys 64..127, columns [64, 128)) and hf = 0
-        static_assert(MODE == 0 || KB == 128, "the split-S schedule is written for 128-key steps");
-        constexpr uint32_t idesc_sh = make_idesc_bf16(QT, 64, 0, 0);
-        auto wait_inputs = [&](uint32_t g) {
-          const uint32_t it = g / nkb;
-          if (g - it * nkb == 0) mbar_wait(&q_full[it & 1], (it >> 1) & 1);
-          mbar_wait(&kv_full[g % NS], (g / NS) & 1);
-          tc_fence_after();
-        };
-        auto issue_s_half = [&](uint32_t g, uint32_t hf) {
-          const uint32_t it = g / nkb;
-          const uint32_t q_addr = smem_u32(sQ + (it & 1) * Q_BYTES + x * (QT * HD * 2));
-          const uint32_t k_addr = smem_u32(sKV + (g % NS) * KV_BYTES) + hf * (64 * HD * 2);
-#pragma unroll
-          for (int k = 0; k < HD / 16; ++k)
-            if (leader)
-              umma_ss(tmem_base + col_s(x, 0) + hf * 64, make_smem_desc(q_addr + k * 32, 16, 1024), make_smem_desc(k_addr + k * 32, 16, 1024),
-                      idesc_sh, k != 0);
-          if (leader) umma_commit(&s_full[2 * x + hf]);
-          if (hf == 0 && leader && g - it * nkb + 1 == (uint32_t)nkb) umma_commit(&q_empty[it & 1]);
-        };
-        if (total_steps > 0) {
-          wait_inputs(0);
-          issue_s_half(0, 1);
-          issue_s_half(0, 0);
-        }
-        for (uint32_t g = 0; g < total_steps; ++g) {
-          const uint32_t it = g / nkb, j = g - it * nkb;
-          const bool last_j = (j + 1 == (uint32_t)nkb), more = g + 1 < total_steps;
-          const uint32_t v_addr = smem_u32(sKV + (g % NS) * KV_BYTES + K_BYTES);
-          if (j == 0) mbar_wait(&o_empty[x], (it & 1) ^ 1);  // the epilogue has read the previous item's O_x
-          mbar_wait(&p_full[2 * x], g & 1);
-          tc_fence_after();
-          DBG(x, g, 0);  // MMA warp: P_x(g) seen
-#pragma unroll
-          for (int k = 4; k < 8; ++k)  // PV over keys 64..127: P_hi sits packed in columns [64, 96)
-            if (leader)
-              umma_ts(tmem_base + col_o(x), tmem_base + col_s(x, 0) + 64 + (k - 4) * 8,
-                      make_smem_desc(v_addr + k * 2048, ones_addr - v_addr, 1024), idesc_o, (j | (k - 4)) != 0);
-          if (more) {  // the upper half of the next S right behind the PV that freed its columns
-            wait_inputs(g + 1);
-            issue_s_half(g + 1, 1);
-          }
-#pragma unroll
-          for (int k = 0; k < 4; ++k)  // PV over keys 0..63: P_lo in columns [0, 32)
-            if (leader)
-              umma_ts(tmem_base + col_o(x), tmem_base + col_s(x, 0) + k * 8, make_smem_desc(v_addr + k * 2048, ones_addr - v_addr, 1024),
-                      idesc_o, 1u);
-          if (leader && last_j) umma_commit(&o_full[x]);
-          if (leader) umma_commit(&kv_empty[g % NS]);  // V_g is done with
-          if (more) issue_s_half(g + 1, 0);
-          DBG(x, g, 1);  // MMA warp: PV_x(g) and S_x(g+1) issued
-        }
-      }
     }
   } else if (warp < W_EPI) {
     // ------------------------------------------------ softmax warpgroups: thread = query row, 64 logits per step
@@ -299,7 +213,6 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     // lock-step (timeline: both 2x slower in the exp phase, then both idle while the tensor core works)
     if (x == 1) asm volatile("bar.arrive 1, 256;" ::: "memory");  // tile A goes first
     for (uint32_t g = 0; g < total_steps; ++g) {
-      if constexpr (MODE == 0) {
       const uint32_t b = g % SBUF, t_s = t_lane + col_s(x, b);
       if (qq == 0) DBG(2 + x, g, 0);  // softmax: starts waiting for S_x(g)
       mbar_wait(&s_full[2 * x + b], (g / SBUF) & 1);
@@ -319,7 +232,9 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         tmem_ld_wait();
         if (c + 1 < KB / 32) tmem_ld32(t_s + (c + 1) * 32, nxt);
         uint32_t pk[16];
-        exp_chunk<false>(cur, pk, c1, c2);
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          pk[i] = pack_bf16(ex2f(fmaf(__uint_as_float(cur[2 * i]), c1, -c2)), ex2f(fmaf(__uint_as_float(cur[2 * i + 1]), c1, -c2)));
         tmem_st16(t_s + c * 16, pk);
       }
       if (x == 0) asm volatile("bar.arrive 2, 256;" ::: "memory");  // the exponentials are issued: the other tile's turn
@@ -329,42 +244,6 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[2 * x + b]);
       if (qq == 0) DBG(2 + x, g, 2);  // softmax: P_x(g) published
-      } else {
-      // split-S: upper half (columns [64, 128), P packed in place at [64, 96)) as soon as it is there, then the lower half
-      const uint32_t t_s = t_lane + col_s(x, 0), par = g & 1;
-      if (qq == 0) DBG(2 + x, g, 0);  // softmax: starts waiting for S_x(g)
-      mbar_wait(&s_full[2 * x + 1], par);
-      tc_fence_after();
-      if (x == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
-      else asm volatile("bar.sync 2, 256;" ::: "memory");
-      if (qq == 0) DBG(2 + x, g, 1);  // softmax: S_x(g) upper half seen and our turn
-      uint32_t sa[32], sb[32], pk[16];
-      tmem_ld32(t_s + 64, sa);
-      tmem_ld_wait();
-      tmem_ld32(t_s + 96, sb);
-      exp_chunk<true>(sa, pk, c1, c2);
-      tmem_st16(t_s + 64, pk);
-      tmem_ld_wait();
-      exp_chunk<true>(sb, pk, c1, c2);
-      tmem_st16(t_s + 80, pk);
-      mbar_wait(&s_full[2 * x], par);
-      tc_fence_after();
-      tmem_ld32(t_s, sa);
-      tmem_ld_wait();
-      tmem_ld32(t_s + 32, sb);
-      exp_chunk<true>(sa, pk, c1, c2);
-      tmem_st16(t_s, pk);
-      tmem_ld_wait();
-      exp_chunk<true>(sb, pk, c1, c2);
-      tmem_st16(t_s + 16, pk);
-      if (x == 0) asm volatile("bar.arrive 2, 256;" ::: "memory");  // the exponentials are issued: the other tile's turn
-      else asm volatile("bar.arrive 1, 256;" ::: "memory");
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[2 * x]);
-      if (qq == 0) DBG(2 + x, g, 2);  // softmax: P_x(g) published
-      }
     }
   } else {
     // ------------------------------------------------ epilogue warpgroup: O / rowsum -> global, log-sum-exp
@@ -436,8 +315,7 @@ int mapdit_attn_tc2_fwd(const void* qkv, void* o, float* lse, int n, int tokens,
   }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_tc2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(attn_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) {
       mapdit_set_error("attn_tc2_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return MAPDIT_ERR_CUDA;
@@ -448,11 +326,7 @@ int mapdit_attn_tc2_fwd(const void* qkv, void* o, float* lse, int n, int tokens,
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
   const int grid = items < sms ? items : sms;  // persistent, one CTA per SM (512 TMEM columns)
-  extern int g_mapdit_attn_v2;  // 1 = split-S + polynomial exp2 (MODE 1), 2 = the round-1 schedule (MODE 0)
-  if (g_mapdit_attn_v2 == 2 || KB != 128)
-    attn_tc2_kernel<0><<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tq, tkv, (bf16*)o, lse, tokens, heads, n, g_attn_dbg);
-  else
-    attn_tc2_kernel<1><<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tq, tkv, (bf16*)o, lse, tokens, heads, n, g_attn_dbg);
+  attn_tc2_kernel<<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tq, tkv, (bf16*)o, lse, tokens, heads, n, g_attn_dbg);
   MAPDIT_LAUNCH_CHECK("attn_tc2_fwd");
   return MAPDIT_OK;
 }
