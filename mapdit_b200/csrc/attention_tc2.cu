@@ -28,14 +28,28 @@ using namespace tc;
 #ifndef ATTN2_KB
 #define ATTN2_KB 128
 #endif
-constexpr int HD = 64, QT = 128, KB = ATTN2_KB;  // keys per step: 128 with one S buffer per tile, or 64 with two
-constexpr int SBUF = 128 / KB;                    // S buffers per tile (each tile owns 128 TMEM columns)
-constexpr int Q_BYTES = 2 * QT * HD * 2;  // both query tiles of an item: 32 KB
-constexpr int K_BYTES = KB * HD * 2;      // 8 KB
-constexpr int KV_BYTES = 2 * K_BYTES;     // K block then V block
-constexpr int ONES_BYTES = KB * 128;      // [64 keys x 128 B] of bf16 1.0: the second (16-channel) N panel of V
-constexpr int NS = KB == 64 ? 4 : 3;
-constexpr int SMEM_BYTES = 2 * Q_BYTES + NS * KV_BYTES + ONES_BYTES + 1024 + 512;
+constexpr int QT = 128, KB = ATTN2_KB;  // keys per step: 128 with one S buffer per tile, or 64 with two
+constexpr int SBUF = 128 / KB;          // S buffers per tile (each tile owns 128 TMEM columns)
+// Head dimension 64: one 64-channel SWIZZLE_128B panel per operand tile.  Head dimension 72 (DiT-XL): TWO panels per tile — the
+// tensor maps are 3-D {72 channels, 3H heads, rows}, so the box that starts at channel 64 reads channels 64..71 and the TMA
+// unit zero-fills the 56 channels past the head's end: in shared memory every head is 128 channels wide with zeros behind
+// channel 72, without a padded copy in HBM.  S = Q K^T then contracts over 80 channels (five K = 16 steps, the last one over the
+// second panel's first 16 channels), PV produces 80 output columns (64 + 16 of the second V panel through the descriptor's
+// leading-dimension stride, which the 64-channel kernel points at its constant ones panel instead).
+template <int HDV>
+struct ACfg {
+  static constexpr int PANELS = HDV == 64 ? 1 : 2;
+  static constexpr int KSTEPS = (HDV + 15) / 16;                // 4 | 5
+  static constexpr int TILE_Q = QT * 64 * 2 * PANELS;           // one 128-query tile: 16 | 32 KB
+  static constexpr int Q_BYTES = 2 * TILE_Q;                    // both query tiles of an item
+  static constexpr int K_BYTES = KB * 64 * 2 * PANELS;          // 16 | 32 KB at 128 keys
+  static constexpr int KV_BYTES = 2 * K_BYTES;                  // K block then V block
+  static constexpr int ONES_BYTES = HDV == 64 ? KB * 128 : 0;   // [keys x 128 B] of bf16 1.0: the row-sum panel of the 64-channel kernel
+  static constexpr int QBUF = HDV == 64 ? 2 : 1;                // query buffers (the two-panel tiles leave room for one)
+  static constexpr int NS = HDV == 64 ? (KB == 64 ? 4 : 3) : 2;  // K/V stages
+  static constexpr int RS_BYTES = HDV == 64 ? 0 : 2 * 2 * QT * 4;  // row sums [item parity][tile][row] (no ones panel at 72)
+  static constexpr int SMEM_BYTES = QBUF * Q_BYTES + NS * KV_BYTES + ONES_BYTES + RS_BYTES + 1024 + 512;
+};
 constexpr int NTHREADS = 15 * 32;
 constexpr int W_EPI = 8, W_TMA = 12, W_MMA = 13;  // warps 13 and 14 issue the MMAs of tile A and tile B
 constexpr uint32_t TMEM_COLS = 512;
@@ -69,9 +83,13 @@ __device__ __forceinline__ void tmem_ld1(uint32_t taddr, uint32_t& v) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
 }
 
+template <int HD>
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, bf16* __restrict__ o,
                 float* __restrict__ lse, int tokens, int heads, int n_samples, long long* __restrict__ dbg) {
+  using A = ACfg<HD>;
+  constexpr int Q_BYTES = A::Q_BYTES, K_BYTES = A::K_BYTES, KV_BYTES = A::KV_BYTES, ONES_BYTES = A::ONES_BYTES, NS = A::NS, QBUF = A::QBUF;
+  constexpr int PANEL_Q = QT * 128, PANEL_K = KB * 128;  // bytes of one 64-channel panel of a query tile / a key block
   // optional timeline of CTA 0 (tools/attn_timeline.py): dbg[role*256 + 4*g + e] = clock64 at event e of step g
 #define DBG(role, g, e)                                                                             \
   do {                                                                                               \
@@ -80,10 +98,11 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-  uint8_t* sQ = smem;                       // [2 buffers][256 x 64]
-  uint8_t* sKV = sQ + 2 * Q_BYTES;          // stage s: K at sKV + s*KV_BYTES, V right after
+  uint8_t* sQ = smem;                       // [QBUF buffers][tile A | tile B], a tile = PANELS x [128 x 64]
+  uint8_t* sKV = sQ + QBUF * Q_BYTES;       // stage s: K at sKV + s*KV_BYTES, V right after
   uint8_t* sOnes = sKV + NS * KV_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + ONES_BYTES);
+  float* sRS = reinterpret_cast<float*>(sOnes + ONES_BYTES);  // head_dim 72 only
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + ONES_BYTES + A::RS_BYTES);
   uint64_t* q_full = bars;              // [2]
   uint64_t* q_empty = q_full + 2;       // [2]
   uint64_t* kv_full = q_empty + 2;      // [NS]
@@ -96,6 +115,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int D = heads * HD;
+  const float sqrt_hd = HD == 64 ? 8.0f : 8.48528137423857f;  // |logit| <= sqrt(head_dim) for L2-normalised q, k
   const int nkb = tokens / KB;
   const int npair = tokens / (2 * QT);
   const int total_items = npair * heads * n_samples;
@@ -136,17 +156,33 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
         const int pr = item % npair, rest = item / npair, h = rest % heads, n = rest / heads;
         const int row_base = n * tokens;
-        const int qb = it & 1;
-        mbar_wait(&q_empty[qb], ((it >> 1) & 1) ^ 1);
+        const int qb = it % QBUF;
+        mbar_wait(&q_empty[qb], ((it / QBUF) & 1) ^ 1);
         mbar_arrive_expect_tx(&q_full[qb], Q_BYTES);
-        tma_load_2d(sQ + qb * Q_BYTES, &tm_q, &q_full[qb], h * HD, row_base + pr * 2 * QT);
+        if constexpr (HD == 64) {
+          tma_load_2d(sQ + qb * Q_BYTES, &tm_q, &q_full[qb], h * HD, row_base + pr * 2 * QT);
+        } else {  // per query tile: panel 0 (channels 0..63), panel 1 (channels 64..71 + zero fill); box = 128 rows
+#pragma unroll
+          for (int x = 0; x < 2; ++x)
+#pragma unroll
+            for (int p = 0; p < 2; ++p)
+              tma_load_3d(sQ + qb * Q_BYTES + x * A::TILE_Q + p * PANEL_Q, &tm_q, &q_full[qb], 64 * p, h, row_base + pr * 2 * QT + x * QT);
+        }
         for (int j = 0; j < nkb; ++j, ++g) {
           const int s = g % NS;
           mbar_wait(&kv_empty[s], ((g / NS) & 1) ^ 1);
           uint8_t* dst = sKV + s * KV_BYTES;
           mbar_arrive_expect_tx(&kv_full[s], KV_BYTES);
-          tma_load_2d(dst, &tm_kv, &kv_full[s], D + h * HD, row_base + j * KB);
-          tma_load_2d(dst + K_BYTES, &tm_kv, &kv_full[s], 2 * D + h * HD, row_base + j * KB);
+          if constexpr (HD == 64) {
+            tma_load_2d(dst, &tm_kv, &kv_full[s], D + h * HD, row_base + j * KB);
+            tma_load_2d(dst + K_BYTES, &tm_kv, &kv_full[s], 2 * D + h * HD, row_base + j * KB);
+          } else {
+#pragma unroll
+            for (int p = 0; p < 2; ++p) {
+              tma_load_3d(dst + p * PANEL_K, &tm_kv, &kv_full[s], 64 * p, heads + h, row_base + j * KB);
+              tma_load_3d(dst + K_BYTES + p * PANEL_K, &tm_kv, &kv_full[s], 64 * p, 2 * heads + h, row_base + j * KB);
+            }
+          }
         }
       }
     }
@@ -162,22 +198,24 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       constexpr uint32_t idesc_o = make_idesc_bf16(QT, ON, 0, 1);  // O = P V, P from TMEM, V MN-major (+ ones panel)
       const int my_items = (total_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
       const uint32_t total_steps = (uint32_t)my_items * nkb;
+      // second N panel of the PV B operand: the constant ones panel (64 channels: column 64 = row sum) or V's own second panel (72)
+      const uint32_t v_lbo = HD == 64 ? 0u : (uint32_t)PANEL_K;
       const uint32_t ones_addr = smem_u32(sOnes);
       auto issue_s = [&](uint32_t g) {  // S_x(g) = Q_x K_g^T into buffer g & 1, then signal tile x's softmax warps
         const uint32_t it = g / nkb, b = g % SBUF;
-        if (g - it * nkb == 0) mbar_wait(&q_full[it & 1], (it >> 1) & 1);
+        if (g - it * nkb == 0) mbar_wait(&q_full[it % QBUF], (it / QBUF) & 1);
         mbar_wait(&kv_full[g % NS], (g / NS) & 1);
         tc_fence_after();
-        const uint32_t q_addr = smem_u32(sQ + (it & 1) * Q_BYTES + x * (QT * HD * 2));
+        const uint32_t q_addr = smem_u32(sQ + (it % QBUF) * Q_BYTES + x * A::TILE_Q);
         const uint32_t k_addr = smem_u32(sKV + (g % NS) * KV_BYTES);
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k)
+        for (int k = 0; k < A::KSTEPS; ++k)  // 16 channels per MMA; step 4 (head_dim 72) is the first 16 channels of the second panel
           if (leader)
-            umma_ss(tmem_base + col_s(x, b), make_smem_desc(q_addr + k * 32, 16, 1024), make_smem_desc(k_addr + k * 32, 16, 1024),
-                    idesc_s, k != 0);
+            umma_ss(tmem_base + col_s(x, b), make_smem_desc(q_addr + (k >> 2) * PANEL_Q + (k & 3) * 32, 16, 1024),
+                    make_smem_desc(k_addr + (k >> 2) * PANEL_K + (k & 3) * 32, 16, 1024), idesc_s, k != 0);
         if (leader) umma_commit(&s_full[2 * x + b]);
         // the query tiles of an item are free once S_B of its last key block has been issued
-        if (leader && g - it * nkb + 1 == (uint32_t)nkb) umma_commit(&q_empty[it & 1]);
+        if (leader && g - it * nkb + 1 == (uint32_t)nkb) umma_commit(&q_empty[it % QBUF]);
       };
       for (uint32_t g = 0; g < (uint32_t)SBUF && g < total_steps; ++g) issue_s(g);
       for (uint32_t g = 0; g < total_steps; ++g) {
@@ -193,7 +231,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           for (int k = 0; k < KB / 16; ++k)  // 16 keys per MMA: P advances 8 TMEM columns, V two 8-row groups
             if (leader)
               umma_ts(tmem_base + col_o(x), tmem_base + col_s(x, b) + k * 8,
-                      make_smem_desc(v_addr + k * 2048, ones_addr - v_addr, 1024), idesc_o, (j | k) != 0);
+                      make_smem_desc(v_addr + k * 2048, HD == 64 ? ones_addr - v_addr : v_lbo, 1024), idesc_o, (j | k) != 0);
           if (leader && last_j) umma_commit(&o_full[x]);
           if (leader) umma_commit(&kv_empty[g % NS]);  // V_g is done with (K_g since S_x(g), two steps ago)
           if (g + SBUF < total_steps) issue_s(g + SBUF);  // reuses buffer b right behind the PV that read P from it
@@ -205,7 +243,8 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     // ------------------------------------------------ softmax warpgroups: thread = query row, 64 logits per step
     const int x = warp >> 2, qq = warp & 3;
     const uint32_t t_lane = tmem_base + ((uint32_t)(qq * 32) << 16);
-    const float c1 = 0.125f * 1.4426950408889634f, c2 = 8.0f * 1.4426950408889634f;
+    const float c1 = (1.0f / sqrt_hd) * 1.4426950408889634f, c2 = sqrt_hd * 1.4426950408889634f;
+    float rsum = 0.f;  // head_dim 72: this row's sum of exponentials over the item's key blocks
     const int my_items = (total_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const uint32_t total_steps = (uint32_t)my_items * nkb;
     // explicit ping-pong: the two warpgroups take turns in the exponential phase (named barriers 1 + x: "tile x may go"),
@@ -233,9 +272,19 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         if (c + 1 < KB / 32) tmem_ld32(t_s + (c + 1) * 32, nxt);
         uint32_t pk[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
-          pk[i] = pack_bf16(ex2f(fmaf(__uint_as_float(cur[2 * i]), c1, -c2)), ex2f(fmaf(__uint_as_float(cur[2 * i + 1]), c1, -c2)));
+        for (int i = 0; i < 16; ++i) {
+          const float pa = ex2f(fmaf(__uint_as_float(cur[2 * i]), c1, -c2)), pb = ex2f(fmaf(__uint_as_float(cur[2 * i + 1]), c1, -c2));
+          if constexpr (HD != 64) rsum += pa + pb;
+          pk[i] = pack_bf16(pa, pb);
+        }
         tmem_st16(t_s + c * 16, pk);
+      }
+      if constexpr (HD != 64) {  // last key block of the item: hand the row sum to the epilogue warp of this lane quarter
+        const uint32_t it = g / nkb;
+        if (g - it * nkb + 1 == (uint32_t)nkb) {
+          sRS[((it & 1) * 2 + x) * QT + qq * 32 + lane] = rsum;
+          rsum = 0.f;
+        }
       }
       if (x == 0) asm volatile("bar.arrive 2, 256;" ::: "memory");  // the exponentials are issued: the other tile's turn
       else asm volatile("bar.arrive 1, 256;" ::: "memory");
@@ -259,16 +308,24 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         tc_fence_after();
         uint32_t ov[32], rs;
         tmem_ld32(t_lane + col_o(x), ov);
-        tmem_ld1(t_lane + col_o(x) + 64, rs);
+        if constexpr (HD == 64) tmem_ld1(t_lane + col_o(x) + 64, rs);
         tmem_ld_wait();
-        const float total = __uint_as_float(rs);
+        float total;
+        if constexpr (HD == 64) total = __uint_as_float(rs);
+        else total = sRS[((it & 1) * 2 + x) * QT + qq * 32 + lane];  // written before the last P was published (ordered by the barriers)
         const float inv = 1.0f / total;
-        if (lse) lse[grow * heads + h] = 8.0f + logf(total);
+        if (lse) lse[grow * heads + h] = sqrt_hd + logf(total);
         bf16* dst = o + grow * D + h * HD;
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
+          uint32_t tail[8];
           if (half == 1) {
             tmem_ld32(t_lane + col_o(x) + 32, ov);
+            if constexpr (HD != 64)
+              asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                           : "=r"(tail[0]), "=r"(tail[1]), "=r"(tail[2]), "=r"(tail[3]), "=r"(tail[4]), "=r"(tail[5]), "=r"(tail[6]), "=r"(tail[7])
+                           : "r"(t_lane + col_o(x) + 64)
+                           : "memory");
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
@@ -283,6 +340,16 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             u.w = pack_bf16(__uint_as_float(ov[8 * c + 6]) * inv, __uint_as_float(ov[8 * c + 7]) * inv);
             *reinterpret_cast<uint4*>(dst + half * 32 + 8 * c) = u;
           }
+          if constexpr (HD != 64) {
+            if (half == 1) {  // channels 64..71
+              uint4 u;
+              u.x = pack_bf16(__uint_as_float(tail[0]) * inv, __uint_as_float(tail[1]) * inv);
+              u.y = pack_bf16(__uint_as_float(tail[2]) * inv, __uint_as_float(tail[3]) * inv);
+              u.z = pack_bf16(__uint_as_float(tail[4]) * inv, __uint_as_float(tail[5]) * inv);
+              u.w = pack_bf16(__uint_as_float(tail[6]) * inv, __uint_as_float(tail[7]) * inv);
+              *reinterpret_cast<uint4*>(dst + 64) = u;
+            }
+          }
         }
       }
     }
@@ -293,7 +360,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 }
 }  // namespace
 
-bool mapdit_attn_tc2_supported(int tokens, int hd) { return hd == HD && tokens % (2 * QT) == 0 && tokens >= 2 * QT; }
+bool mapdit_attn_tc2_supported(int tokens, int hd) { return (hd == 64 || hd == 72) && tokens % (2 * QT) == 0 && tokens >= 2 * QT; }
 
 long long* g_attn_dbg = nullptr;  // also stamped by attn_bwd_fused_tc (attention_bwd_tc.cu)
 extern "C" int mapdit_attn_debug_buffer(void* p) {  // developer hook: timeline buffer of >= 1024 int64 (or null)
@@ -301,21 +368,12 @@ extern "C" int mapdit_attn_debug_buffer(void* p) {  // developer hook: timeline 
   return MAPDIT_OK;
 }
 
-int mapdit_attn_tc2_fwd(const void* qkv, void* o, float* lse, int n, int tokens, int heads, int hd, void* stream) {
-  const int D = heads * hd;
-  CUtensorMap tq, tkv;
-  const uint64_t dims[2] = {(uint64_t)3 * D, (uint64_t)n * tokens};
-  const uint64_t strides[1] = {(uint64_t)3 * D * 2};
-  const uint32_t box_q[2] = {HD, 2 * QT}, box_kv[2] = {HD, KB};
-  CUresult r1 = mapdit_encode_tmap(&tq, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, qkv, dims, strides, box_q, CU_TENSOR_MAP_SWIZZLE_128B);
-  CUresult r2 = mapdit_encode_tmap(&tkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, qkv, dims, strides, box_kv, CU_TENSOR_MAP_SWIZZLE_128B);
-  if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) {
-    mapdit_set_error("attn_tc2_fwd: cuTensorMapEncodeTiled failed (%d, %d)", (int)r1, (int)r2);
-    return MAPDIT_ERR_CUDA;
-  }
+namespace {
+template <int HDV>
+int launch_attn_tc2(const CUtensorMap& tq, const CUtensorMap& tkv, void* o, float* lse, int n, int tokens, int heads, void* stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(attn_tc2_kernel<HDV>, cudaFuncAttributeMaxDynamicSharedMemorySize, ACfg<HDV>::SMEM_BYTES);
     if (e != cudaSuccess) {
       mapdit_set_error("attn_tc2_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return MAPDIT_ERR_CUDA;
@@ -326,7 +384,35 @@ int mapdit_attn_tc2_fwd(const void* qkv, void* o, float* lse, int n, int tokens,
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
   const int grid = items < sms ? items : sms;  // persistent, one CTA per SM (512 TMEM columns)
-  attn_tc2_kernel<<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tq, tkv, (bf16*)o, lse, tokens, heads, n, g_attn_dbg);
+  attn_tc2_kernel<HDV><<<grid, NTHREADS, ACfg<HDV>::SMEM_BYTES, (cudaStream_t)stream>>>(tq, tkv, (bf16*)o, lse, tokens, heads, n, g_attn_dbg);
+  return MAPDIT_OK;
+}
+}  // namespace
+
+int mapdit_attn_tc2_fwd(const void* qkv, void* o, float* lse, int n, int tokens, int heads, int hd, void* stream) {
+  const int D = heads * hd;
+  CUtensorMap tq, tkv;
+  CUresult r1, r2;
+  if (hd == 64) {
+    const uint64_t dims[2] = {(uint64_t)3 * D, (uint64_t)n * tokens};
+    const uint64_t strides[1] = {(uint64_t)3 * D * 2};
+    const uint32_t box_q[2] = {64, 2 * QT}, box_kv[2] = {64, KB};
+    r1 = mapdit_encode_tmap(&tq, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, qkv, dims, strides, box_q, CU_TENSOR_MAP_SWIZZLE_128B);
+    r2 = mapdit_encode_tmap(&tkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, qkv, dims, strides, box_kv, CU_TENSOR_MAP_SWIZZLE_128B);
+  } else {
+    // {channel within head, head of q|k|v, row}: a 64-channel box at channel 64 runs past the head's 72 channels and is zero-filled there
+    const uint64_t dims[3] = {(uint64_t)hd, (uint64_t)3 * heads, (uint64_t)n * tokens};
+    const uint64_t strides[2] = {(uint64_t)hd * 2, (uint64_t)3 * D * 2};
+    const uint32_t box_q[3] = {64, 1, QT}, box_kv[3] = {64, 1, KB};
+    r1 = mapdit_encode_tmap(&tq, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, qkv, dims, strides, box_q, CU_TENSOR_MAP_SWIZZLE_128B);
+    r2 = mapdit_encode_tmap(&tkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, qkv, dims, strides, box_kv, CU_TENSOR_MAP_SWIZZLE_128B);
+  }
+  if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) {
+    mapdit_set_error("attn_tc2_fwd: cuTensorMapEncodeTiled failed (%d, %d)", (int)r1, (int)r2);
+    return MAPDIT_ERR_CUDA;
+  }
+  const int rc = hd == 64 ? launch_attn_tc2<64>(tq, tkv, o, lse, n, tokens, heads, stream) : launch_attn_tc2<72>(tq, tkv, o, lse, n, tokens, heads, stream);
+  if (rc != MAPDIT_OK) return rc;
   MAPDIT_LAUNCH_CHECK("attn_tc2_fwd");
   return MAPDIT_OK;
 }

@@ -284,9 +284,11 @@ int launch2(const mapdit_gemm_args* g, const EpiParams& ep, cudaStream_t stream,
 // the second-generation residual epilogue needs a warp's 32 rows inside one sample and 16-byte aligned per-sample vectors
 bool fused_resid_ok(const mapdit_gemm_args* g, const EpiParams& ep) {
   if (!g_mapdit_gemm_fused_resid) return false;
-  // 1 (default) = only where the epilogue is the bottleneck: short contractions (K <= 1024: out-proj); with K = 4 D (fc2) the main
-  // loop hides the first-generation epilogue and keeps its fifth operand stage.  2 = always (A/B)
-  if (g_mapdit_gemm_fused_resid == 1 && g->k > 1024) return false;
+  // 1 (default) = only where the epilogue is the bottleneck: a short main loop per tile (K x tile width <= 1024 x 256: the out-proj
+  // GEMMs, and fc2 of the D = 384 models on 128-wide tiles); with K = 4 D >= 3072 (fc2 of DiT-B and up) the main loop hides the
+  // first-generation epilogue and keeps its fifth operand stage.  2 = always (A/B)
+  const long long bn_tile = (g->n % 256 == 0 || g->n > 1024) ? 256 : 128;
+  if (g_mapdit_gemm_fused_resid == 1 && (long long)g->k * bn_tile > 1024 * 256) return false;
   if (ep.epilogue != MAPDIT_EPI_RESID && ep.epilogue != MAPDIT_EPI_RESID_MOD && ep.epilogue != MAPDIT_EPI_RESID_ROT) return false;
   if (ep.tokens % 32 != 0 || ep.ldmod % 4 != 0 || ep.ldshift % 4 != 0 || ep.N % 4 != 0) return false;
   auto al16 = [](const void* p) { return p == nullptr || ((uintptr_t)p & 15) == 0; };

@@ -204,3 +204,25 @@ def test_gemm_store_delta_epilogue_and_attention_backward_without_o(N, T, H, two
     assert rel_l2(d_new.float(), d_ref.float()) < 2e-3
     with pytest.raises(RuntimeError):  # delta can only be handed over on the fused tokens == 256 path
         ops.cos_attn_bwd_qknorm(qkv[: 2 * 64], None, dh[: 2 * 64], lse[: 2 * 64], sc[: 2 * 64], d_new[: 2 * 64], delta2[: 2 * 64], 2, 64, H, hd)
+
+
+@pytest.mark.parametrize("N,T,H", [(2, 256, 3), (1, 1024, 2), (3, 512, 16), (40, 256, 4)])
+def test_cos_attn_bf16_head_dim_72(N, T, H):
+    """DiT-XL's head_dim 72 on the tcgen05 forward kernel: two 64-channel panels per operand tile, the second one zero-filled past
+    channel 72 by the TMA unit (3-D tensor map), S over 80 channels, PV with 80 output columns, row sums from the softmax warps"""
+    from mapdit_b200 import ops
+    hd, D = 72, H * 72
+    qkv = rnd(N * T, 3 * D, seed=19)
+    ops.qk_normalize(qkv, D, hd)
+    qkv16 = qkv.bfloat16()
+    q, k, v = qkv16.float().view(N, T, 3, H, hd).permute(2, 0, 3, 1, 4)
+    ref = F.scaled_dot_product_attention(q.double(), k.double(), v.double(), scale=1 / math.sqrt(hd)).transpose(1, 2).reshape(N * T, D)
+    ref_lse = torch.logsumexp(q.double() @ k.double().transpose(-1, -2) / math.sqrt(hd), dim=-1).permute(0, 2, 1).reshape(N * T, H)
+    o = torch.full((N * T, D), float("nan"), device="cuda", dtype=torch.bfloat16)
+    lse = torch.full((N * T, H), float("nan"), device="cuda")
+    ops.cos_attn(qkv16, o, N, T, H, hd, lse=lse)
+    torch.cuda.synchronize()
+    e = rel_l2(o.float(), ref)
+    print(f"head_dim 72 tcgen05 attention N={N} T={T} H={H}: rel-L2 {e:.2e}, lse max abs err {float((lse.double() - ref_lse).abs().max()):.2e}")
+    assert e < 6e-3
+    assert float((lse.double() - ref_lse).abs().max()) < 2e-2
