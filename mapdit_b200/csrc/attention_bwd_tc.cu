@@ -113,21 +113,112 @@ __device__ __forceinline__ void store_out_row_qknorm(bf16* dst, const bf16* __re
   }
 }
 
-// ------------------------------------------------------------------------------------------------ dQ
-constexpr int DQ_SMEM = 2 * ROW_BYTES + 2 * 2 * BLK_BYTES + ROW_BYTES + 1024 + 256;
+// ------------------------------------------------------------------------------------------------ dQ / dK, dV kernel pair
+// Head dimension 64 or 72 (DiT-XL).  At 72 every operand tile is TWO 64-channel SWIZZLE_128B panels: the tensor maps are 3-D
+// {72 channels, heads, rows}, the box that starts at channel 64 reads channels 64..71 and the TMA unit zero-fills the rest, so in
+// shared memory a head is 128 channels wide with zeros behind channel 72 (no padded copy in HBM).  Contractions over channels
+// (S, dP) take five K = 16 steps, accumulators over channels (dQ, dK, dV) are 80 columns wide (64 + the first 16 of the second
+// panel through the descriptor's leading-dimension stride); columns 72..79 are exact zeros and are not stored.
+template <int HDV>
+struct BCfg {
+  static constexpr int PANELS = HDV == 64 ? 1 : 2;
+  static constexpr int KST = (HDV + 15) / 16;            // channel k-steps of S / dP: 4 | 5
+  static constexpr int NACC = HDV == 64 ? 64 : 80;       // accumulator columns of dQ / dK / dV
+  static constexpr int PROW = RT * 128, PBLK = CB * 128;  // one panel of a 128-row tile / a 64-row block
+  static constexpr int ROWB = PROW * PANELS, BLKB = PBLK * PANELS;
+  static constexpr int DQ_SMEM = 2 * ROWB + 2 * 2 * BLKB + ROW_BYTES + 1024 + 256;
+  static constexpr int DKV_SMEM = 2 * ROWB + 2 * 2 * BLKB + 2 * ROW_BYTES + 2 * 2 * CB * 4 + 1024 + 256;
+  static constexpr uint32_t DKV_TMEM = HDV == 64 ? 256 : 512;  // S^T 64 + dP^T 64 + dK NACC + dV NACC
+  static constexpr int CTAS = HDV == 64 ? 2 : 1;               // per SM (shared memory)
+};
+__host__ __device__ constexpr float att_scale_of(int hdv) { return hdv == 64 ? 0.125f : 0.11785113019775793f; }  // 1/sqrt(hd)
+__host__ __device__ constexpr float sqrt_hd_of(int hdv) { return hdv == 64 ? 8.0f : 8.48528137423857f; }
 
-__global__ void __launch_bounds__(NTHREADS, 2)
+// one operand tile (PANELS x [rows x 64]) by TMA.  HDV 64: 2-D map {3D | D columns, rows}, column = part * D + h * 64.  HDV 72: 3-D
+// map {72, heads of the tensor, rows}, head index = part * heads + h, one load per panel.
+template <int HDV>
+__device__ __forceinline__ void load_tile(uint8_t* dst, const CUtensorMap* m, uint64_t* bar, int part, int h, int heads, int row, int panel_bytes) {
+  if constexpr (HDV == 64) {
+    tma_load_2d(dst, m, bar, part * heads * 64 + h * 64, row);
+  } else {
+#pragma unroll
+    for (int p = 0; p < 2; ++p) tma_load_3d(dst + p * panel_bytes, m, bar, 64 * p, part * heads + h, row);
+  }
+}
+// accumulator row (a | b | tail: NACC fp32) of thread = row -> HDV bf16, scaled
+template <int HDV>
+__device__ __forceinline__ void store_acc_row(bf16* dst, const uint32_t (&a)[32], const uint32_t (&b)[32], const uint32_t (&t)[8], float sc) {
+  store_out_row(dst, a, b, sc);
+  if constexpr (HDV != 64) {
+    uint4 u;
+    u.x = pack_bf16(__uint_as_float(t[0]) * sc, __uint_as_float(t[1]) * sc);
+    u.y = pack_bf16(__uint_as_float(t[2]) * sc, __uint_as_float(t[3]) * sc);
+    u.z = pack_bf16(__uint_as_float(t[4]) * sc, __uint_as_float(t[5]) * sc);
+    u.w = pack_bf16(__uint_as_float(t[6]) * sc, __uint_as_float(t[7]) * sc);
+    *reinterpret_cast<uint4*>(dst + 64) = u;
+  }
+}
+// the same with the backward of the q/k L2 normalisation (see store_out_row_qknorm) for a 72-channel head
+__device__ __forceinline__ void store_acc_row_qknorm72(bf16* dst, const bf16* __restrict__ yrow, const uint32_t (&a)[32], const uint32_t (&b)[32],
+                                                       const uint32_t (&t)[8], float att_scale, float s, float eps) {
+  float dot = 0.f;
+#pragma unroll
+  for (int c = 0; c < 9; ++c) {
+    const uint4 u = reinterpret_cast<const uint4*>(yrow)[c];
+    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 y2 = __bfloat1622float2(h2[e]);
+      const int i = 8 * c + 2 * e;
+      const float g0 = __uint_as_float(i < 32 ? a[i & 31] : (i < 64 ? b[i & 31] : t[i & 7]));
+      const float g1 = __uint_as_float(i + 1 < 32 ? a[(i + 1) & 31] : (i + 1 < 64 ? b[(i + 1) & 31] : t[(i + 1) & 7]));
+      dot = fmaf(y2.x, g0, fmaf(y2.y, g1, dot));
+    }
+  }
+  dot *= att_scale;
+  const float rpe = 8.48528137423857f / s;
+  const float r = fmaxf(rpe - eps, 1e-30f);
+  const float coef = dot * rpe / (72.0f * r);
+  const float ga = s * att_scale, sc_y = -s * coef;
+#pragma unroll
+  for (int c = 0; c < 9; ++c) {
+    const uint4 u = reinterpret_cast<const uint4*>(yrow)[c];
+    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+    uint32_t w[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 y2 = __bfloat1622float2(h2[e]);
+      const int i = 8 * c + 2 * e;
+      const float g0 = __uint_as_float(i < 32 ? a[i & 31] : (i < 64 ? b[i & 31] : t[i & 7]));
+      const float g1 = __uint_as_float(i + 1 < 32 ? a[(i + 1) & 31] : (i + 1 < 64 ? b[(i + 1) & 31] : t[(i + 1) & 7]));
+      w[e] = pack_bf16(fmaf(ga, g0, sc_y * y2.x), fmaf(ga, g1, sc_y * y2.y));
+    }
+    *reinterpret_cast<uint4*>(dst + 8 * c) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------ dQ
+template <int HDV>
+__global__ void __launch_bounds__(NTHREADS, BCfg<HDV>::CTAS)
 attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_constant__ CUtensorMap tm_qkv_blk,
                const __grid_constant__ CUtensorMap tm_do_row, const bf16* __restrict__ o, const bf16* __restrict__ dout,
                const float* __restrict__ lse, float* __restrict__ delta, bf16* __restrict__ dqkv, int tokens, int heads,
                const bf16* __restrict__ qkv, const float* __restrict__ sc, float eps) {
+  using B = BCfg<HDV>;
+  constexpr int ROWB = B::ROWB, BLKB = B::BLKB, PROW = B::PROW, PBLK = B::PBLK;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   uint8_t* sQ = smem;
-  uint8_t* sdO = sQ + ROW_BYTES;
-  uint8_t* sKV = sdO + ROW_BYTES;          // stage s: K_j at sKV + s*2*BLK, V_j after it
-  uint8_t* sdS = sKV + 2 * 2 * BLK_BYTES;  // [128 x 64] bf16 K-major
+  uint8_t* sdO = sQ + ROWB;
+  uint8_t* sKV = sdO + ROWB;          // stage s: K_j at sKV + s*2*BLKB, V_j after it
+  uint8_t* sdS = sKV + 2 * 2 * BLKB;  // [128 x 64] bf16 K-major
   uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + ROW_BYTES);
   uint64_t* bar_q = bars;
   uint64_t* kv_full = bars + 1;
@@ -141,7 +232,7 @@ attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_cons
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
-  const int D = heads * HD, q0 = qt * RT, nkb = tokens / CB, row_base = n * tokens;
+  const int D = heads * HDV, q0 = qt * RT, nkb = tokens / CB, row_base = n * tokens;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tm_qkv_row);
@@ -166,33 +257,34 @@ attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_cons
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
   if (warp == 0 && lane == 0) {
-    mbar_arrive_expect_tx(bar_q, 2 * ROW_BYTES);
-    tma_load_2d(sQ, &tm_qkv_row, bar_q, h * HD, row_base + q0);
-    tma_load_2d(sdO, &tm_do_row, bar_q, h * HD, row_base + q0);
+    mbar_arrive_expect_tx(bar_q, 2 * ROWB);
+    load_tile<HDV>(sQ, &tm_qkv_row, bar_q, 0, h, heads, row_base + q0, PROW);
+    load_tile<HDV>(sdO, &tm_do_row, bar_q, 0, h, heads, row_base + q0, PROW);
     for (int j = 0; j < nkb; ++j) {
       const int s = j & 1;
       mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1);
-      uint8_t* dst = sKV + s * 2 * BLK_BYTES;
-      mbar_arrive_expect_tx(&kv_full[s], 2 * BLK_BYTES);
-      tma_load_2d(dst, &tm_qkv_blk, &kv_full[s], D + h * HD, row_base + j * CB);
-      tma_load_2d(dst + BLK_BYTES, &tm_qkv_blk, &kv_full[s], 2 * D + h * HD, row_base + j * CB);
+      uint8_t* dst = sKV + s * 2 * BLKB;
+      mbar_arrive_expect_tx(&kv_full[s], 2 * BLKB);
+      load_tile<HDV>(dst, &tm_qkv_blk, &kv_full[s], 1, h, heads, row_base + j * CB, PBLK);
+      load_tile<HDV>(dst + BLKB, &tm_qkv_blk, &kv_full[s], 2, h, heads, row_base + j * CB, PBLK);
     }
   } else if (warp == 1) {
     const bool leader = elect_one();  // whole warp runs the loop, one lane issues (see tc_common.cuh)
-    constexpr uint32_t idesc_s = make_idesc_bf16(RT, CB, 0, 0);  // S / dP: both operands K-major
-    constexpr uint32_t idesc_q = make_idesc_bf16(RT, HD, 0, 1);  // dQ += dS K_j: K_j MN-major (d contiguous)
+    constexpr uint32_t idesc_s = make_idesc_bf16(RT, CB, 0, 0);       // S / dP: both operands K-major
+    constexpr uint32_t idesc_q = make_idesc_bf16(RT, B::NACC, 0, 1);  // dQ += dS K_j: K_j MN-major (d contiguous)
     const uint32_t q_addr = smem_u32(sQ), do_addr = smem_u32(sdO), ds_addr = smem_u32(sdS);
     auto scores = [&](int j) {
       const int s = j & 1;
       mbar_wait(&kv_full[s], (j >> 1) & 1);
       mbar_wait(s_empty, (j & 1) ^ 1);
       tc_fence_after();
-      const uint32_t k_addr = smem_u32(sKV + s * 2 * BLK_BYTES), v_addr = k_addr + BLK_BYTES;
+      const uint32_t k_addr = smem_u32(sKV + s * 2 * BLKB), v_addr = k_addr + BLKB;
       // the S and dP chains accumulate into different TMEM tiles: issued alternately so consecutive MMAs are independent
 #pragma unroll
-      for (int k = 0; k < HD / 16; ++k) {
-        if (leader) umma_ss(tmem_base, make_smem_desc(q_addr + k * 32, 16, 1024), make_smem_desc(k_addr + k * 32, 16, 1024), idesc_s, k != 0);
-        if (leader) umma_ss(tmem_base + 64, make_smem_desc(do_addr + k * 32, 16, 1024), make_smem_desc(v_addr + k * 32, 16, 1024), idesc_s, k != 0);
+      for (int k = 0; k < B::KST; ++k) {
+        const uint32_t ro = (k >> 2) * PROW + (k & 3) * 32, bo = (k >> 2) * PBLK + (k & 3) * 32;  // panel + 16-channel step
+        if (leader) umma_ss(tmem_base, make_smem_desc(q_addr + ro, 16, 1024), make_smem_desc(k_addr + bo, 16, 1024), idesc_s, k != 0);
+        if (leader) umma_ss(tmem_base + 64, make_smem_desc(do_addr + ro, 16, 1024), make_smem_desc(v_addr + bo, 16, 1024), idesc_s, k != 0);
       }
       if (leader) umma_commit(s_full);
     };
@@ -203,10 +295,10 @@ attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_cons
       if (j + 1 < nkb) scores(j + 1);
       mbar_wait(ds_full, j & 1);
       tc_fence_after();
-      const uint32_t k_addr = smem_u32(sKV + s * 2 * BLK_BYTES);
+      const uint32_t k_addr = smem_u32(sKV + s * 2 * BLKB);
 #pragma unroll
       for (int k = 0; k < CB / 16; ++k)
-        if (leader) umma_ss(tmem_base + 128, make_smem_desc(ds_addr + k * 32, 16, 1024), make_smem_desc(k_addr + k * 2048, 1024, 1024), idesc_q,
+        if (leader) umma_ss(tmem_base + 128, make_smem_desc(ds_addr + k * 32, 16, 1024), make_smem_desc(k_addr + k * 2048, PBLK, 1024), idesc_q,
                 (j | k) != 0);
       if (leader) umma_commit(&kv_empty[s]);
       if (leader) umma_commit(ds_empty);
@@ -218,13 +310,13 @@ attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_cons
     const uint32_t t_lane = tmem_base + ((uint32_t)(qq * 32) << 16);
     const bool row_ok = q0 + r < tokens;
     const size_t grow = (size_t)row_base + q0 + r;
-    // delta_i = dO_i . O_i (128-byte rows straight from global) and L_i
+    // delta_i = dO_i . O_i (the head's rows straight from global) and L_i
     float dl = 0.f, L = 0.f;
     if (row_ok) {
-      const uint4* po = reinterpret_cast<const uint4*>(o + grow * D + h * HD);
-      const uint4* pg = reinterpret_cast<const uint4*>(dout + grow * D + h * HD);
+      const uint4* po = reinterpret_cast<const uint4*>(o + grow * D + h * HDV);
+      const uint4* pg = reinterpret_cast<const uint4*>(dout + grow * D + h * HDV);
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
+      for (int c = 0; c < HDV / 8; ++c) {
         uint4 a = po[c], b = pg[c];
         const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&a);
         const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&b);
@@ -237,7 +329,7 @@ attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_cons
       L = lse[grow * heads + h];
       delta[grow * heads + h] = dl;
     }
-    const float c1 = 0.125f * LOG2E, c2 = L * LOG2E;
+    const float c1 = att_scale_of(HDV) * LOG2E, c2 = L * LOG2E;
     for (int j = 0; j < nkb; ++j) {
       mbar_wait(s_full, j & 1);
       tc_fence_after();
@@ -266,13 +358,20 @@ attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_cons
     }
     mbar_wait(o_full, 0);
     tc_fence_after();
-    uint32_t a0[32], a1[32];
+    uint32_t a0[32], a1[32], tl[8];
     tmem_ld32(t_lane + 128, a0);
     tmem_ld32(t_lane + 160, a1);
+    if constexpr (HDV != 64) tmem_ld8(t_lane + 192, tl);
     tmem_ld_wait();
     if (row_ok) {
-      if (sc) store_out_row_qknorm(dqkv + grow * 3 * D + h * HD, qkv + grow * 3 * D + h * HD, a0, a1, 0.125f, sc[grow * 2 * heads + h], eps);
-      else store_out_row(dqkv + grow * 3 * D + h * HD, a0, a1, 0.125f);
+      bf16* dst = dqkv + grow * 3 * D + h * HDV;
+      if constexpr (HDV == 64) {
+        if (sc) store_out_row_qknorm(dst, qkv + grow * 3 * D + h * HDV, a0, a1, 0.125f, sc[grow * 2 * heads + h], eps);
+        else store_out_row(dst, a0, a1, 0.125f);
+      } else {
+        if (sc) store_acc_row_qknorm72(dst, qkv + grow * 3 * D + h * HDV, a0, a1, tl, att_scale_of(HDV), sc[grow * 2 * heads + h], eps);
+        else store_acc_row<HDV>(dst, a0, a1, tl, att_scale_of(HDV));
+      }
     }
   }
   tc_fence_before();
@@ -281,19 +380,21 @@ attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_cons
 }
 
 // ------------------------------------------------------------------------------------------------ dK, dV
-constexpr int DKV_SMEM = 2 * ROW_BYTES + 2 * 2 * BLK_BYTES + 2 * ROW_BYTES + 2 * 2 * CB * 4 + 1024 + 256;
-
-__global__ void __launch_bounds__(NTHREADS, 2)
+template <int HDV>
+__global__ void __launch_bounds__(NTHREADS, BCfg<HDV>::CTAS)
 attn_bwd_dkv_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_constant__ CUtensorMap tm_qkv_blk,
                 const __grid_constant__ CUtensorMap tm_do_blk, const float* __restrict__ lse, const float* __restrict__ delta,
                 bf16* __restrict__ dqkv, int tokens, int heads, const bf16* __restrict__ qkv, const float* __restrict__ sc, float eps) {
+  using B = BCfg<HDV>;
+  constexpr int ROWB = B::ROWB, BLKB = B::BLKB, PROW = B::PROW, PBLK = B::PBLK;
+  constexpr uint32_t T_DK = 128, T_DV = 128 + B::NACC;  // accumulator columns behind S^T [0, 64) and dP^T [64, 128)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   uint8_t* sK = smem;
-  uint8_t* sV = sK + ROW_BYTES;
-  uint8_t* sQdO = sV + ROW_BYTES;            // stage s: Q_j at sQdO + s*2*BLK, dO_j after it
-  uint8_t* sPt = sQdO + 2 * 2 * BLK_BYTES;   // [128 keys x 64 queries] bf16 K-major
+  uint8_t* sV = sK + ROWB;
+  uint8_t* sQdO = sV + ROWB;             // stage s: Q_j at sQdO + s*2*BLKB, dO_j after it
+  uint8_t* sPt = sQdO + 2 * 2 * BLKB;    // [128 keys x 64 queries] bf16 K-major
   uint8_t* sdSt = sPt + ROW_BYTES;
   float* sL = reinterpret_cast<float*>(sdSt + ROW_BYTES);  // [2][64]
   float* sD = sL + 2 * CB;                                  // [2][64]
@@ -310,7 +411,7 @@ attn_bwd_dkv_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_con
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kt = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
-  const int D = heads * HD, k0 = kt * RT, nqb = tokens / CB, row_base = n * tokens;
+  const int D = heads * HDV, k0 = kt * RT, nqb = tokens / CB, row_base = n * tokens;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tm_qkv_row);
@@ -328,39 +429,40 @@ attn_bwd_dkv_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_con
     mbar_init(o_full, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+  if (warp == 1) tmem_alloc<B::DKV_TMEM>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
   if (warp == 0 && lane == 0) {
-    mbar_arrive_expect_tx(bar_kv, 2 * ROW_BYTES);
-    tma_load_2d(sK, &tm_qkv_row, bar_kv, D + h * HD, row_base + k0);
-    tma_load_2d(sV, &tm_qkv_row, bar_kv, 2 * D + h * HD, row_base + k0);
+    mbar_arrive_expect_tx(bar_kv, 2 * ROWB);
+    load_tile<HDV>(sK, &tm_qkv_row, bar_kv, 1, h, heads, row_base + k0, PROW);
+    load_tile<HDV>(sV, &tm_qkv_row, bar_kv, 2, h, heads, row_base + k0, PROW);
     for (int j = 0; j < nqb; ++j) {
       const int s = j & 1;
       mbar_wait(&qd_empty[s], ((j >> 1) & 1) ^ 1);
-      uint8_t* dst = sQdO + s * 2 * BLK_BYTES;
-      mbar_arrive_expect_tx(&qd_full[s], 2 * BLK_BYTES);
-      tma_load_2d(dst, &tm_qkv_blk, &qd_full[s], h * HD, row_base + j * CB);
-      tma_load_2d(dst + BLK_BYTES, &tm_do_blk, &qd_full[s], h * HD, row_base + j * CB);
+      uint8_t* dst = sQdO + s * 2 * BLKB;
+      mbar_arrive_expect_tx(&qd_full[s], 2 * BLKB);
+      load_tile<HDV>(dst, &tm_qkv_blk, &qd_full[s], 0, h, heads, row_base + j * CB, PBLK);
+      load_tile<HDV>(dst + BLKB, &tm_do_blk, &qd_full[s], 0, h, heads, row_base + j * CB, PBLK);
     }
   } else if (warp == 1) {
     const bool leader = elect_one();  // whole warp runs the loop, one lane issues (see tc_common.cuh)
-    constexpr uint32_t idesc_s = make_idesc_bf16(RT, CB, 0, 0);  // S^T = K Q_j^T, dP^T = V dO_j^T
-    constexpr uint32_t idesc_a = make_idesc_bf16(RT, HD, 0, 1);  // dV += P^T dO_j, dK += dS^T Q_j : B MN-major
+    constexpr uint32_t idesc_s = make_idesc_bf16(RT, CB, 0, 0);       // S^T = K Q_j^T, dP^T = V dO_j^T
+    constexpr uint32_t idesc_a = make_idesc_bf16(RT, B::NACC, 0, 1);  // dV += P^T dO_j, dK += dS^T Q_j : B MN-major
     const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), pt_addr = smem_u32(sPt), dst_addr = smem_u32(sdSt);
     auto scores = [&](int j) {
       const int s = j & 1;
       mbar_wait(&qd_full[s], (j >> 1) & 1);
       mbar_wait(s_empty, (j & 1) ^ 1);
       tc_fence_after();
-      const uint32_t q_addr = smem_u32(sQdO + s * 2 * BLK_BYTES), do_addr = q_addr + BLK_BYTES;
+      const uint32_t q_addr = smem_u32(sQdO + s * 2 * BLKB), do_addr = q_addr + BLKB;
 #pragma unroll
-      for (int k = 0; k < HD / 16; ++k) {  // S^T and dP^T chains interleaved (independent accumulators)
-        if (leader) umma_ss(tmem_base, make_smem_desc(k_addr + k * 32, 16, 1024), make_smem_desc(q_addr + k * 32, 16, 1024), idesc_s, k != 0);
-        if (leader) umma_ss(tmem_base + 64, make_smem_desc(v_addr + k * 32, 16, 1024), make_smem_desc(do_addr + k * 32, 16, 1024), idesc_s, k != 0);
+      for (int k = 0; k < B::KST; ++k) {  // S^T and dP^T chains interleaved (independent accumulators)
+        const uint32_t ro = (k >> 2) * PROW + (k & 3) * 32, bo = (k >> 2) * PBLK + (k & 3) * 32;
+        if (leader) umma_ss(tmem_base, make_smem_desc(k_addr + ro, 16, 1024), make_smem_desc(q_addr + bo, 16, 1024), idesc_s, k != 0);
+        if (leader) umma_ss(tmem_base + 64, make_smem_desc(v_addr + ro, 16, 1024), make_smem_desc(do_addr + bo, 16, 1024), idesc_s, k != 0);
       }
       if (leader) umma_commit(s_full);
     };
@@ -371,12 +473,12 @@ attn_bwd_dkv_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_con
       if (j + 1 < nqb) scores(j + 1);
       mbar_wait(p_full, j & 1);
       tc_fence_after();
-      const uint32_t q_addr = smem_u32(sQdO + s * 2 * BLK_BYTES), do_addr = q_addr + BLK_BYTES;
+      const uint32_t q_addr = smem_u32(sQdO + s * 2 * BLKB), do_addr = q_addr + BLKB;
 #pragma unroll
       for (int k = 0; k < CB / 16; ++k) {  // dV and dK chains interleaved
-        if (leader) umma_ss(tmem_base + 192, make_smem_desc(pt_addr + k * 32, 16, 1024), make_smem_desc(do_addr + k * 2048, 1024, 1024), idesc_a,
+        if (leader) umma_ss(tmem_base + T_DV, make_smem_desc(pt_addr + k * 32, 16, 1024), make_smem_desc(do_addr + k * 2048, PBLK, 1024), idesc_a,
                 (j | k) != 0);
-        if (leader) umma_ss(tmem_base + 128, make_smem_desc(dst_addr + k * 32, 16, 1024), make_smem_desc(q_addr + k * 2048, 1024, 1024), idesc_a,
+        if (leader) umma_ss(tmem_base + T_DK, make_smem_desc(dst_addr + k * 32, 16, 1024), make_smem_desc(q_addr + k * 2048, PBLK, 1024), idesc_a,
                 (j | k) != 0);
       }
       if (leader) umma_commit(&qd_empty[s]);
@@ -388,7 +490,7 @@ attn_bwd_dkv_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_con
     const int r = qq * 32 + lane;  // key row of the tile
     const int tid = threadIdx.x - 64;  // 0..127 among the softmax warps
     const uint32_t t_lane = tmem_base + ((uint32_t)(qq * 32) << 16);
-    const float c1 = 0.125f * LOG2E;
+    const float c1 = att_scale_of(HDV) * LOG2E;
     for (int j = 0; j < nqb; ++j) {
       const int s = j & 1;
       // per-query L and delta of this block -> smem (double-buffered), visible to the 128 softmax threads
@@ -429,25 +531,32 @@ attn_bwd_dkv_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_con
     }
     mbar_wait(o_full, 0);
     tc_fence_after();
-    uint32_t a0[32], a1[32];
+    uint32_t a0[32], a1[32], tl[8];
     const bool row_ok = k0 + r < tokens;
     const size_t grow = (size_t)row_base + k0 + r;
-    tmem_ld32(t_lane + 128, a0);
-    tmem_ld32(t_lane + 160, a1);
+    tmem_ld32(t_lane + T_DK, a0);
+    tmem_ld32(t_lane + T_DK + 32, a1);
+    if constexpr (HDV != 64) tmem_ld8(t_lane + T_DK + 64, tl);
     tmem_ld_wait();
     if (row_ok) {
-      if (sc) store_out_row_qknorm(dqkv + grow * 3 * D + D + h * HD, qkv + grow * 3 * D + D + h * HD, a0, a1, 0.125f,
-                                   sc[grow * 2 * heads + heads + h], eps);
-      else store_out_row(dqkv + grow * 3 * D + D + h * HD, a0, a1, 0.125f);
+      bf16* dst = dqkv + grow * 3 * D + D + h * HDV;
+      if constexpr (HDV == 64) {
+        if (sc) store_out_row_qknorm(dst, qkv + grow * 3 * D + D + h * HDV, a0, a1, 0.125f, sc[grow * 2 * heads + heads + h], eps);
+        else store_out_row(dst, a0, a1, 0.125f);
+      } else {
+        if (sc) store_acc_row_qknorm72(dst, qkv + grow * 3 * D + D + h * HDV, a0, a1, tl, att_scale_of(HDV), sc[grow * 2 * heads + heads + h], eps);
+        else store_acc_row<HDV>(dst, a0, a1, tl, att_scale_of(HDV));
+      }
     }
-    tmem_ld32(t_lane + 192, a0);
-    tmem_ld32(t_lane + 224, a1);
+    tmem_ld32(t_lane + T_DV, a0);
+    tmem_ld32(t_lane + T_DV + 32, a1);
+    if constexpr (HDV != 64) tmem_ld8(t_lane + T_DV + 64, tl);
     tmem_ld_wait();
-    if (row_ok) store_out_row(dqkv + grow * 3 * D + 2 * D + h * HD, a0, a1, 1.0f);
+    if (row_ok) store_acc_row<HDV>(dqkv + grow * 3 * D + 2 * D + h * HDV, a0, a1, tl, 1.0f);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
+  if (warp == 1) tmem_dealloc<B::DKV_TMEM>(tmem_base);
 }
 
 // ------------------------------------------------------------------------------------------------ fused dQ, dK, dV (tokens == 256)
@@ -1441,6 +1550,44 @@ int encode2d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uin
 extern "C" int mapdit_qk_norm_bwd(void* dqkv, const void* qkv, const float* sc, int m, int d, int head_dim, float eps, int dtype,
                                   void* stream);
 
+// head_dim 72 (DiT-XL): the dq + dkv kernel pair on two-panel operand tiles, 3-D tensor maps {72 channels, heads, rows}
+static int attn_bwd_pair72(const void* qkv, const void* o, const void* dout, const float* lse, const float* sc, float eps, void* dqkv,
+                           float* delta, int n_samples, int tokens, int heads, void* stream) {
+  MAPDIT_REQUIRE(o != nullptr, "cos_attn_bwd: o is required for head_dim 72");
+  const int hd = 72, D = heads * hd;
+  const uint64_t rows = (uint64_t)n_samples * tokens;
+  auto enc = [&](CUtensorMap* m, const void* base, int n_heads, uint32_t box_rows) {
+    const uint64_t dims[3] = {(uint64_t)hd, (uint64_t)n_heads, rows};
+    const uint64_t strides[2] = {(uint64_t)hd * 2, (uint64_t)n_heads * hd * 2};
+    const uint32_t box[3] = {64, 1, box_rows};
+    return (int)mapdit_encode_tmap(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+  };
+  CUtensorMap t_qkv_row, t_qkv_blk, t_do_row, t_do_blk;
+  if (enc(&t_qkv_row, qkv, 3 * heads, RT) | enc(&t_qkv_blk, qkv, 3 * heads, CB) | enc(&t_do_row, dout, heads, RT) | enc(&t_do_blk, dout, heads, CB)) {
+    mapdit_set_error("cos_attn_bwd(hd 72): cuTensorMapEncodeTiled failed");
+    return MAPDIT_ERR_CUDA;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e1 = cudaFuncSetAttribute(attn_bwd_dq_tc<72>, cudaFuncAttributeMaxDynamicSharedMemorySize, BCfg<72>::DQ_SMEM);
+    cudaError_t e2 = cudaFuncSetAttribute(attn_bwd_dkv_tc<72>, cudaFuncAttributeMaxDynamicSharedMemorySize, BCfg<72>::DKV_SMEM);
+    if (e1 != cudaSuccess || e2 != cudaSuccess) {
+      mapdit_set_error("cos_attn_bwd(hd 72): cudaFuncSetAttribute failed");
+      return MAPDIT_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  dim3 grid((tokens + RT - 1) / RT, heads, n_samples);
+  attn_bwd_dq_tc<72><<<grid, NTHREADS, BCfg<72>::DQ_SMEM, s>>>(t_qkv_row, t_qkv_blk, t_do_row, (const bf16*)o, (const bf16*)dout, lse, delta,
+                                                             (bf16*)dqkv, tokens, heads, (const bf16*)qkv, sc, eps);
+  MAPDIT_LAUNCH_CHECK("cos_attn_bwd(dq, hd 72)");
+  attn_bwd_dkv_tc<72><<<grid, NTHREADS, BCfg<72>::DKV_SMEM, s>>>(t_qkv_row, t_qkv_blk, t_do_blk, lse, delta, (bf16*)dqkv, tokens, heads,
+                                                               (const bf16*)qkv, sc, eps);
+  MAPDIT_LAUNCH_CHECK("cos_attn_bwd(dkv, hd 72)");
+  return MAPDIT_OK;
+}
+
 // sc == nullptr: gradients w.r.t. the normalised q^, k^ (and v).  sc != nullptr: the q/k normalisation backward is applied
 // as well (fused into the dq / dk epilogues on the tcgen05 path, a separate kernel behind the CUDA-core path).
 static int attn_bwd_impl(const void* qkv, const void* o, const void* dout, const float* lse, const float* sc, float eps, void* dqkv,
@@ -1450,6 +1597,8 @@ static int attn_bwd_impl(const void* qkv, const void* o, const void* dout, const
   // takes that shortcut, every other path computes delta itself from o
   const bool fused_path = dtype == MAPDIT_BF16 && head_dim == HD && tokens == F_T && g_mapdit_attn_bwd_fused && !(mapdit_variant() & MAPDIT_VAR_DOT_ATTN);
   MAPDIT_REQUIRE(o || fused_path, "cos_attn_bwd: o may only be omitted (delta precomputed) on the fused tokens == 256 path");
+  if (dtype == MAPDIT_BF16 && head_dim == 72 && tokens % CB == 0 && !(mapdit_variant() & MAPDIT_VAR_DOT_ATTN))
+    return attn_bwd_pair72(qkv, o, dout, lse, sc, eps, dqkv, delta, n_samples, tokens, heads, stream);  // DiT-XL
   if (!(dtype == MAPDIT_BF16 && head_dim == HD && tokens % CB == 0) || (mapdit_variant() & MAPDIT_VAR_DOT_ATTN)) {
     int rc = (dtype == MAPDIT_BF16 && mapdit_attn_mma_supported(tokens, head_dim))
                  ? mapdit_attn_mma_bwd(qkv, o, dout, lse, dqkv, delta, n_samples, tokens, heads, head_dim, stream)
@@ -1468,8 +1617,8 @@ static int attn_bwd_impl(const void* qkv, const void* o, const void* dout, const
   }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e1 = cudaFuncSetAttribute(attn_bwd_dq_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, DQ_SMEM);
-    cudaError_t e2 = cudaFuncSetAttribute(attn_bwd_dkv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, DKV_SMEM);
+    cudaError_t e1 = cudaFuncSetAttribute(attn_bwd_dq_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, BCfg<64>::DQ_SMEM);
+    cudaError_t e2 = cudaFuncSetAttribute(attn_bwd_dkv_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, BCfg<64>::DKV_SMEM);
     if (e1 != cudaSuccess || e2 != cudaSuccess) {
       mapdit_set_error("cos_attn_bwd: cudaFuncSetAttribute failed");
       return MAPDIT_ERR_CUDA;
@@ -1520,10 +1669,10 @@ static int attn_bwd_impl(const void* qkv, const void* o, const void* dout, const
     return MAPDIT_OK;
   }
   dim3 grid((tokens + RT - 1) / RT, heads, n_samples);
-  attn_bwd_dq_tc<<<grid, NTHREADS, DQ_SMEM, s>>>(t_qkv_row, t_qkv_blk, t_do_row, (const bf16*)o, (const bf16*)dout, lse, delta,
+  attn_bwd_dq_tc<64><<<grid, NTHREADS, BCfg<64>::DQ_SMEM, s>>>(t_qkv_row, t_qkv_blk, t_do_row, (const bf16*)o, (const bf16*)dout, lse, delta,
                                                  (bf16*)dqkv, tokens, heads, (const bf16*)qkv, sc, eps);
   MAPDIT_LAUNCH_CHECK("cos_attn_bwd(dq)");
-  attn_bwd_dkv_tc<<<grid, NTHREADS, DKV_SMEM, s>>>(t_qkv_row, t_qkv_blk, t_do_blk, lse, delta, (bf16*)dqkv, tokens, heads,
+  attn_bwd_dkv_tc<64><<<grid, NTHREADS, BCfg<64>::DKV_SMEM, s>>>(t_qkv_row, t_qkv_blk, t_do_blk, lse, delta, (bf16*)dqkv, tokens, heads,
                                                    (const bf16*)qkv, sc, eps);
   MAPDIT_LAUNCH_CHECK("cos_attn_bwd(dkv)");
   return MAPDIT_OK;

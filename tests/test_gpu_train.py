@@ -557,3 +557,48 @@ def test_two_rank_data_parallel_matches_single_process():
     assert r.returncode == 0 and lines, r.stderr[-2000:]
     res = json.loads(lines[-1])
     assert res["replicas_bit_identical"] and res["train_param_rel_l2_worst"] < 2e-3 and res["sample_rel_l2"] < 1e-5
+
+
+@pytest.mark.parametrize("N,T,H", [(2, 128, 3), (1, 1024, 2), (3, 256, 16), (2, 192, 4)])
+def test_attention_backward_head_dim_72_tcgen05(N, T, H):
+    """DiT-XL's head_dim 72: dq + dkv tcgen05 kernel pair on two-panel operand tiles (3-D TMA maps zero-fill channels 72..127),
+    80-column accumulators, q/k-normalisation backward fused into the dq / dk read-out; vs fp64 autograd through
+    normalize + SDPA (src/layers/attention.py:43-47)"""
+    from mapdit_b200 import ops
+    hd, D = 72, H * 72
+    raw = rnd(N * T, 3 * D, seed=31)
+    qkv = raw.clone()
+    sc = torch.empty(N * T, 2 * H, device="cuda")
+    ops.qk_normalize_save(qkv, sc, D, hd)
+    qkv = qkv.bfloat16()
+    dout = rnd(N * T, D, seed=32).bfloat16()
+    o = torch.empty(N * T, D, device="cuda", dtype=torch.bfloat16)
+    lse = torch.empty(N * T, H, device="cuda")
+    ops.cos_attn(qkv, o, N, T, H, hd, lse=lse)
+    delta = torch.empty(N * T, H, device="cuda")
+    # (1) gradients w.r.t. the normalised q^, k^, v
+    dq1 = torch.full_like(qkv, float("nan"))
+    ops.cos_attn_bwd(qkv, o, dout, lse, dq1, delta, N, T, H, hd)
+    ref_in = qkv.double().requires_grad_(True)
+    q, k, v = ref_in.view(N, T, 3, H, hd).permute(2, 0, 3, 1, 4)
+    ro = F.scaled_dot_product_attention(q, k, v, scale=1 / math.sqrt(hd)).transpose(1, 2).reshape(N * T, D)
+    (ro * dout.double()).sum().backward()
+    e1 = rel_l2(dq1.float(), ref_in.grad)
+    for third in range(3):
+        sl = slice(third * D, (third + 1) * D)
+        assert rel_l2(dq1[:, sl].float(), ref_in.grad[:, sl]) < 2.5e-2, third
+    # (2) with the q/k normalisation backward fused in: gradients w.r.t. the raw q, k
+    dq2 = torch.full_like(qkv, float("nan"))
+    ops.cos_attn_bwd_qknorm(qkv, o, dout, lse, sc, dq2, delta, N, T, H, hd)
+    r = raw.double().requires_grad_(True)
+    r3 = r.view(N * T, 3, H, hd)
+    qn = r3[:, :2] * math.sqrt(hd) / (r3[:, :2].norm(dim=-1, keepdim=True) + 1e-4)
+    full = torch.cat([qn, r3[:, 2:]], 1).view(N, T, 3, H, hd).permute(2, 0, 3, 1, 4)
+    ro = F.scaled_dot_product_attention(full[0], full[1], full[2], scale=1 / math.sqrt(hd)).transpose(1, 2).reshape(N * T, D)
+    (ro * dout.double()).sum().backward()
+    e2 = rel_l2(dq2.float(), r.grad)
+    print(f"head_dim 72 tcgen05 attention backward N={N} T={T} H={H}: d(q^,k^,v) {e1:.2e}, with q/k-norm backward {e2:.2e}")
+    assert e1 < 2.5e-2 and e2 < 2.5e-2
+    for third in range(3):
+        sl = slice(third * D, (third + 1) * D)
+        assert rel_l2(dq2[:, sl].float(), r.grad[:, sl]) < 3e-2, third
