@@ -223,8 +223,8 @@ class Trainer:
                 if cosine:
                     ops.qk_normalize_save(dst, B["sc"][i], D, hd)
 
-        fused = bf and adaln and not ln and cosine and hd == 64
-        fused_rot = bf and not adaln and not ln and cosine and hd == 64
+        fused = bf and adaln and not ln and cosine  # head_dim 72 (DiT-XL) only differs in qkv_proj
+        fused_rot = bf and not adaln and not ln and cosine
         if fused_rot:
             rcs = B["rotcs"]
             for i in range(L):
@@ -245,7 +245,7 @@ class Trainer:
                     nsh, nsc, ngn = mod(i + 1, "shift_a"), mod(i + 1, "scale_a"), blk[i + 1].gain_msa.data
                 else:
                     nsh, nsc, ngn = mods[:, fbase:], mods[:, fbase + D:], f.gain_mod.data
-                ops.gemm_bf16(h1, W.wqkv[i], qkv, epilogue=_lib.EPI_QKNORM, tokens=T, head_dim=hd, qk_cols=2 * D, aux=B["sc"][i])
+                qkv_proj(i, h1, qkv)
                 ops.cos_attn(qkv, o, N, T, H, hd, lse=B["lse"][i])
                 ops.gemm_bf16(o, W.wo[i], xmid, epilogue=_lib.EPI_RESID_MOD, out2=h2, resid=xin, gate=mod(i, "gate_a"),
                               shift=mod(i, "shift_m"), scale=mod(i, "scale_m"), gain=blk[i].gain_mlp.data, ldmod=ld, tokens=T, aux=a)
@@ -253,7 +253,7 @@ class Trainer:
                 ops.gemm_bf16(u, W.w2[i], xnext, epilogue=_lib.EPI_RESID_MOD, out2=hnext, resid=xmid, gate=mod(i, "gate_m"), shift=nsh,
                               scale=nsc, gain=ngn, ldmod=ld, tokens=T, aux=b)
             elif fused_rot:
-                ops.gemm_bf16(h1, W.wqkv[i], qkv, epilogue=_lib.EPI_QKNORM, tokens=T, head_dim=hd, qk_cols=2 * D, aux=B["sc"][i])
+                qkv_proj(i, h1, qkv)
                 ops.cos_attn(qkv, o, N, T, H, hd, lse=B["lse"][i])
                 ops.gemm_bf16(o, W.wo[i], xmid, epilogue=_lib.EPI_RESID_ROT, out2=h2, resid=xin, gate=mod(i, "gate_a"),
                               shift=rcs[:, (2 * i + 1) * D:], scale=mod(i, "scale_m") if has_sc else None, ldmod=ld,

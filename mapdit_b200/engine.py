@@ -271,10 +271,11 @@ class Engine:
                     ops.qk_normalize(ws["qkv"], D, hd)
 
         blk = m.blocks
-        # modulate fused into the residual GEMM epilogues (the pinned all-flags-on configuration)
-        fused = bf and adaln and not ln and cosine and hd == 64
+        # modulate fused into the residual GEMM epilogues (the pinned all-flags-on configuration; head_dim 72 of DiT-XL only
+        # differs in the qkv GEMM: plain store + the row-wise q/k normalisation kernel, see qkv_proj)
+        fused = bf and adaln and not ln and cosine
         # the same for rotation(+scaling) modulation: BASELINE.json's headline configuration (UNPINNED)
-        fused_rot = bf and not adaln and not ln and cosine and hd == 64
+        fused_rot = bf and not adaln and not ln and cosine
         if fused_rot:
             rcs = ws["rotcs"]
             for i in range(L):
@@ -292,7 +293,7 @@ class Engine:
             if fused:
                 nxt_shift, nxt_scale, nxt_gain = ((mod(i + 1, "shift_a"), mod(i + 1, "scale_a"), blk[i + 1].gain_msa.data) if i + 1 < L
                                                   else (mods[:, fbase:], mods[:, fbase + D:], f.gain_mod.data))
-                ops.gemm_bf16(Hb, W.wqkv[i], ws["qkv"], epilogue=_lib.EPI_QKNORM, tokens=T, head_dim=hd, qk_cols=2 * D)
+                qkv_proj(i, Hb)
                 ops.cos_attn(ws["qkv"], ws["o"], N, T, H, hd)
                 ops.gemm_bf16(ws["o"], W.wo[i], X, epilogue=_lib.EPI_RESID_MOD, out2=Hb, resid=X, gate=mod(i, "gate_a"),
                               shift=mod(i, "shift_m"), scale=mod(i, "scale_m"), gain=blk[i].gain_mlp.data, ldmod=ld, tokens=T)
@@ -300,7 +301,7 @@ class Engine:
                 ops.gemm_bf16(ws["u"], W.w2[i], X, epilogue=_lib.EPI_RESID_MOD, out2=Hb, resid=X, gate=mod(i, "gate_m"),
                               shift=nxt_shift, scale=nxt_scale, gain=nxt_gain, ldmod=ld, tokens=T)
             elif fused_rot:
-                ops.gemm_bf16(Hb, W.wqkv[i], ws["qkv"], epilogue=_lib.EPI_QKNORM, tokens=T, head_dim=hd, qk_cols=2 * D)
+                qkv_proj(i, Hb)
                 ops.cos_attn(ws["qkv"], ws["o"], N, T, H, hd)
                 ops.gemm_bf16(ws["o"], W.wo[i], X, epilogue=_lib.EPI_RESID_ROT, out2=Hb, resid=X, gate=mod(i, "gate_a"),
                               shift=rcs[:, (2 * i + 1) * D:], scale=mod(i, "scale_m") if has_sc else None, ldmod=ld,

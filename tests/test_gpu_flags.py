@@ -116,14 +116,17 @@ def test_adaln_baseline_sampling_loop(dtype, tol):
     assert e < tol
 
 
-def test_dit_xl_head_dim_72_runs_in_bf16():
-    """DiT-XL (head_dim 72, BASELINE config 5) on the bf16 path: tcgen05 GEMMs + the generic attention kernels"""
+@pytest.mark.parametrize("patch", [8, 2])
+def test_dit_xl_head_dim_72_runs_in_bf16(patch):
+    """DiT-XL (head_dim 72, BASELINE config 5) on the bf16 path, two blocks deep: tcgen05 GEMMs with the fused residual + modulation
+    epilogues; patch 8 (16 tokens) takes the generic attention kernels, patch 2 (256 tokens) the head_dim-72 tcgen05 attention
+    forward (two-panel tiles) and the tcgen05 dq + dkv backward pair"""
     import mapdit_b200 as M
-    name = "DiT-XL/8"
+    name = f"DiT-XL/{patch}"
     cfg = O.config_for(name)
     cfg.depth = 2
     sd = O.init_state_dict(cfg, seed=5)
-    m = M.DiT(depth=2, hidden_size=1152, patch_size=8, num_heads=16, in_channels=4, input_size=32, num_classes=1000)
+    m = M.DiT(depth=2, hidden_size=1152, patch_size=patch, num_heads=16, in_channels=4, input_size=32, num_classes=1000)
     m.load_state_dict(sd)
     m = m.cuda()
     g = torch.Generator().manual_seed(2)
