@@ -128,8 +128,13 @@ struct BCfg {
   static constexpr int ROWB = PROW * PANELS, BLKB = PBLK * PANELS;
   static constexpr int DQ_SMEM = 2 * ROWB + 2 * 2 * BLKB + ROW_BYTES + 1024 + 256;
   static constexpr int DKV_SMEM = 2 * ROWB + 2 * 2 * BLKB + 2 * ROW_BYTES + 2 * 2 * CB * 4 + 1024 + 256;
-  static constexpr uint32_t DKV_TMEM = HDV == 64 ? 256 : 512;  // S^T 64 + dP^T 64 + dK NACC + dV NACC
   static constexpr int CTAS = HDV == 64 ? 2 : 1;               // per SM (shared memory)
+  // S / dP accumulator buffers.  Two CTAs per SM (head_dim 64) overlap one CTA's softmax with the other's MMAs; the single CTA of
+  // head_dim 72 gets the same overlap from a second S / dP buffer in its otherwise unused TMEM columns: scores(j+1) runs while
+  // the softmax warps still work on block j
+  static constexpr int SB = HDV == 64 ? 1 : 2;
+  static constexpr uint32_t DQ_TMEM = HDV == 64 ? 256 : 512;   // SB x (S 64 + dP 64) + dQ NACC
+  static constexpr uint32_t DKV_TMEM = HDV == 64 ? 256 : 512;  // SB x (S^T 64 + dP^T 64) + dK NACC + dV NACC
 };
 __host__ __device__ constexpr float att_scale_of(int hdv) { return hdv == 64 ? 0.125f : 0.11785113019775793f; }  // 1/sqrt(hd)
 __host__ __device__ constexpr float sqrt_hd_of(int hdv) { return hdv == 64 ? 8.0f : 8.48528137423857f; }
@@ -223,12 +228,14 @@ attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_cons
   uint64_t* bar_q = bars;
   uint64_t* kv_full = bars + 1;
   uint64_t* kv_empty = bars + 3;
-  uint64_t* s_full = bars + 5;
-  uint64_t* s_empty = bars + 6;
-  uint64_t* ds_full = bars + 7;
-  uint64_t* ds_empty = bars + 8;
-  uint64_t* o_full = bars + 9;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  uint64_t* s_full = bars + 5;   // [SB]
+  uint64_t* s_empty = bars + 7;  // [SB]
+  uint64_t* ds_full = bars + 9;
+  uint64_t* ds_empty = bars + 10;
+  uint64_t* o_full = bars + 11;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  constexpr int SB = B::SB;
+  constexpr uint32_t T_DQ = SB * 128;  // dQ accumulator behind the SB x (S [0, 64) | dP [64, 128)) buffers
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
@@ -243,14 +250,16 @@ attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_cons
       mbar_init(&kv_full[i], 1);
       mbar_init(&kv_empty[i], 1);
     }
-    mbar_init(s_full, 1);
-    mbar_init(s_empty, 4);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_empty[i], 4);
+    }
     mbar_init(ds_full, 4);
     mbar_init(ds_empty, 1);
     mbar_init(o_full, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+  if (warp == 1) tmem_alloc<B::DQ_TMEM>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -274,19 +283,20 @@ attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_cons
     constexpr uint32_t idesc_q = make_idesc_bf16(RT, B::NACC, 0, 1);  // dQ += dS K_j: K_j MN-major (d contiguous)
     const uint32_t q_addr = smem_u32(sQ), do_addr = smem_u32(sdO), ds_addr = smem_u32(sdS);
     auto scores = [&](int j) {
-      const int s = j & 1;
+      const int s = j & 1, b = j % SB;
       mbar_wait(&kv_full[s], (j >> 1) & 1);
-      mbar_wait(s_empty, (j & 1) ^ 1);
+      mbar_wait(&s_empty[b], ((j / SB) & 1) ^ 1);
       tc_fence_after();
       const uint32_t k_addr = smem_u32(sKV + s * 2 * BLKB), v_addr = k_addr + BLKB;
+      const uint32_t t_s = tmem_base + b * 128;
       // the S and dP chains accumulate into different TMEM tiles: issued alternately so consecutive MMAs are independent
 #pragma unroll
       for (int k = 0; k < B::KST; ++k) {
         const uint32_t ro = (k >> 2) * PROW + (k & 3) * 32, bo = (k >> 2) * PBLK + (k & 3) * 32;  // panel + 16-channel step
-        if (leader) umma_ss(tmem_base, make_smem_desc(q_addr + ro, 16, 1024), make_smem_desc(k_addr + bo, 16, 1024), idesc_s, k != 0);
-        if (leader) umma_ss(tmem_base + 64, make_smem_desc(do_addr + ro, 16, 1024), make_smem_desc(v_addr + bo, 16, 1024), idesc_s, k != 0);
+        if (leader) umma_ss(t_s, make_smem_desc(q_addr + ro, 16, 1024), make_smem_desc(k_addr + bo, 16, 1024), idesc_s, k != 0);
+        if (leader) umma_ss(t_s + 64, make_smem_desc(do_addr + ro, 16, 1024), make_smem_desc(v_addr + bo, 16, 1024), idesc_s, k != 0);
       }
-      if (leader) umma_commit(s_full);
+      if (leader) umma_commit(&s_full[b]);
     };
     mbar_wait(bar_q, 0);
     scores(0);
@@ -298,7 +308,7 @@ attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_cons
       const uint32_t k_addr = smem_u32(sKV + s * 2 * BLKB);
 #pragma unroll
       for (int k = 0; k < CB / 16; ++k)
-        if (leader) umma_ss(tmem_base + 128, make_smem_desc(ds_addr + k * 32, 16, 1024), make_smem_desc(k_addr + k * 2048, PBLK, 1024), idesc_q,
+        if (leader) umma_ss(tmem_base + T_DQ, make_smem_desc(ds_addr + k * 32, 16, 1024), make_smem_desc(k_addr + k * 2048, PBLK, 1024), idesc_q,
                 (j | k) != 0);
       if (leader) umma_commit(&kv_empty[s]);
       if (leader) umma_commit(ds_empty);
@@ -331,14 +341,15 @@ attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_cons
     }
     const float c1 = att_scale_of(HDV) * LOG2E, c2 = L * LOG2E;
     for (int j = 0; j < nkb; ++j) {
-      mbar_wait(s_full, j & 1);
+      const int b = j % SB;
+      mbar_wait(&s_full[b], (j / SB) & 1);
       tc_fence_after();
       uint32_t pk[32];
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         uint32_t sv[32], dp[32];
-        tmem_ld32(t_lane + half * 32, sv);
-        tmem_ld32(t_lane + 64 + half * 32, dp);
+        tmem_ld32(t_lane + b * 128 + half * 32, sv);
+        tmem_ld32(t_lane + b * 128 + 64 + half * 32, dp);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
@@ -349,7 +360,7 @@ attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_cons
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(s_empty);
+      if (lane == 0) mbar_arrive(&s_empty[b]);
       mbar_wait(ds_empty, (j & 1) ^ 1);
       store_row_sw128(sdS, r, pk);
       fence_proxy_async();
@@ -359,9 +370,9 @@ attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_cons
     mbar_wait(o_full, 0);
     tc_fence_after();
     uint32_t a0[32], a1[32], tl[8];
-    tmem_ld32(t_lane + 128, a0);
-    tmem_ld32(t_lane + 160, a1);
-    if constexpr (HDV != 64) tmem_ld8(t_lane + 192, tl);
+    tmem_ld32(t_lane + T_DQ, a0);
+    tmem_ld32(t_lane + T_DQ + 32, a1);
+    if constexpr (HDV != 64) tmem_ld8(t_lane + T_DQ + 64, tl);
     tmem_ld_wait();
     if (row_ok) {
       bf16* dst = dqkv + grow * 3 * D + h * HDV;
@@ -376,7 +387,7 @@ attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_cons
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
+  if (warp == 1) tmem_dealloc<B::DQ_TMEM>(tmem_base);
 }
 
 // ------------------------------------------------------------------------------------------------ dK, dV
@@ -387,7 +398,8 @@ attn_bwd_dkv_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_con
                 bf16* __restrict__ dqkv, int tokens, int heads, const bf16* __restrict__ qkv, const float* __restrict__ sc, float eps) {
   using B = BCfg<HDV>;
   constexpr int ROWB = B::ROWB, BLKB = B::BLKB, PROW = B::PROW, PBLK = B::PBLK;
-  constexpr uint32_t T_DK = 128, T_DV = 128 + B::NACC;  // accumulator columns behind S^T [0, 64) and dP^T [64, 128)
+  constexpr int SB = B::SB;
+  constexpr uint32_t T_DK = SB * 128, T_DV = SB * 128 + B::NACC;  // accumulators behind the SB x (S^T [0, 64) | dP^T [64, 128)) buffers
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -402,12 +414,12 @@ attn_bwd_dkv_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_con
   uint64_t* bar_kv = bars;
   uint64_t* qd_full = bars + 1;
   uint64_t* qd_empty = bars + 3;
-  uint64_t* s_full = bars + 5;
-  uint64_t* s_empty = bars + 6;
-  uint64_t* p_full = bars + 7;
-  uint64_t* p_empty = bars + 8;
-  uint64_t* o_full = bars + 9;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  uint64_t* s_full = bars + 5;   // [SB]
+  uint64_t* s_empty = bars + 7;  // [SB]
+  uint64_t* p_full = bars + 9;
+  uint64_t* p_empty = bars + 10;
+  uint64_t* o_full = bars + 11;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kt = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
@@ -422,8 +434,10 @@ attn_bwd_dkv_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_con
       mbar_init(&qd_full[i], 1);
       mbar_init(&qd_empty[i], 1);
     }
-    mbar_init(s_full, 1);
-    mbar_init(s_empty, 4);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_empty[i], 4);
+    }
     mbar_init(p_full, 4);
     mbar_init(p_empty, 1);
     mbar_init(o_full, 1);
@@ -453,18 +467,19 @@ attn_bwd_dkv_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_con
     constexpr uint32_t idesc_a = make_idesc_bf16(RT, B::NACC, 0, 1);  // dV += P^T dO_j, dK += dS^T Q_j : B MN-major
     const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), pt_addr = smem_u32(sPt), dst_addr = smem_u32(sdSt);
     auto scores = [&](int j) {
-      const int s = j & 1;
+      const int s = j & 1, b = j % SB;
       mbar_wait(&qd_full[s], (j >> 1) & 1);
-      mbar_wait(s_empty, (j & 1) ^ 1);
+      mbar_wait(&s_empty[b], ((j / SB) & 1) ^ 1);
       tc_fence_after();
       const uint32_t q_addr = smem_u32(sQdO + s * 2 * BLKB), do_addr = q_addr + BLKB;
+      const uint32_t t_s = tmem_base + b * 128;
 #pragma unroll
       for (int k = 0; k < B::KST; ++k) {  // S^T and dP^T chains interleaved (independent accumulators)
         const uint32_t ro = (k >> 2) * PROW + (k & 3) * 32, bo = (k >> 2) * PBLK + (k & 3) * 32;
-        if (leader) umma_ss(tmem_base, make_smem_desc(k_addr + ro, 16, 1024), make_smem_desc(q_addr + bo, 16, 1024), idesc_s, k != 0);
-        if (leader) umma_ss(tmem_base + 64, make_smem_desc(v_addr + ro, 16, 1024), make_smem_desc(do_addr + bo, 16, 1024), idesc_s, k != 0);
+        if (leader) umma_ss(t_s, make_smem_desc(k_addr + ro, 16, 1024), make_smem_desc(q_addr + bo, 16, 1024), idesc_s, k != 0);
+        if (leader) umma_ss(t_s + 64, make_smem_desc(v_addr + ro, 16, 1024), make_smem_desc(do_addr + bo, 16, 1024), idesc_s, k != 0);
       }
-      if (leader) umma_commit(s_full);
+      if (leader) umma_commit(&s_full[b]);
     };
     mbar_wait(bar_kv, 0);
     scores(0);
@@ -500,14 +515,15 @@ attn_bwd_dkv_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_con
         else sD[s * CB + (tid - 64)] = delta[qrow * heads + h];
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      mbar_wait(s_full, j & 1);
+      const int b = j % SB;
+      mbar_wait(&s_full[b], (j / SB) & 1);
       tc_fence_after();
       uint32_t pp[32], pd[32];
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         uint32_t sv[32], dp[32];
-        tmem_ld32(t_lane + half * 32, sv);
-        tmem_ld32(t_lane + 64 + half * 32, dp);
+        tmem_ld32(t_lane + b * 128 + half * 32, sv);
+        tmem_ld32(t_lane + b * 128 + 64 + half * 32, dp);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
@@ -521,7 +537,7 @@ attn_bwd_dkv_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_con
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(s_empty);
+      if (lane == 0) mbar_arrive(&s_empty[b]);
       mbar_wait(p_empty, (j & 1) ^ 1);
       store_row_sw128(sPt, r, pp);
       store_row_sw128(sdSt, r, pd);

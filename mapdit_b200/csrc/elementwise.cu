@@ -569,8 +569,14 @@ __global__ void qk_normalize_kernel(T* __restrict__ qkv, int64_t n_heads_total, 
   }
 }
 
+int mapdit_qk_normalize_vec(void* qkv, float* sc, int m, int d, int head_dim, float eps, void* stream);  // backward.cu
 extern "C" int mapdit_qk_normalize(void* qkv, int m, int d, int head_dim, float eps, int dtype, void* stream) {
   MAPDIT_REQUIRE(qkv && m > 0 && d > 0 && head_dim > 0 && head_dim <= 128 && d % head_dim == 0, "qk_normalize: bad args");
+  if (dtype == MAPDIT_BF16 && head_dim % 8 == 0 && d % 8 == 0 && ((uintptr_t)qkv & 15) == 0) {  // 16-byte chunks, 16 lanes per head
+    mapdit_qk_normalize_vec(qkv, nullptr, m, d, head_dim, eps, stream);
+    MAPDIT_LAUNCH_CHECK("qk_normalize(vec)");
+    return MAPDIT_OK;
+  }
   int heads2 = 2 * (d / head_dim);
   int64_t total = (int64_t)m * heads2;
   int64_t blocks = (total * 32 + 255) / 256;

@@ -299,3 +299,24 @@ def test_multi_tensor_weight_norm_bwd_cast2d_and_bf16_grad_adam(dev):
         ops.adam_step(pa, g16.float(), ma, va, 1e-2, 0.9, 0.99, 1e-8, step, grad_scale=0.5)
         ops.adam_step_g16(pb, g16, mb, vb, 1e-2, 0.9, 0.99, 1e-8, step, grad_scale=0.5)
     assert torch.equal(pa, pb) and torch.equal(ma, mb) and torch.equal(va, vb)
+
+
+@pytest.mark.parametrize("M,H,hd", [(300, 16, 72), (257, 6, 64), (64, 3, 32), (1000, 2, 128)])
+def test_qk_normalize_bf16_vectorised(dev, M, H, hd):
+    """bf16 q/k L2 normalisation with 16-byte accesses (src/layers/attention.py:43-45 for head dims the GEMM epilogue does not fuse):
+    q, k heads scaled to norm sqrt(hd), v untouched, sc = sqrt(hd)/(||v|| + eps) saved for the backward"""
+    from mapdit_b200 import ops
+    D = H * hd
+    raw = (rnd(M, 3 * D, seed=41) * 1.7).bfloat16()
+    ref = raw.float().view(M, 3, H, hd).clone()
+    nrm = ref[:, :2].norm(dim=-1, keepdim=True)
+    want_sc = (math.sqrt(hd) / (nrm + 1e-4)).reshape(M, 2 * H)
+    ref[:, :2] = ref[:, :2] * math.sqrt(hd) / (nrm + 1e-4)
+    a, b = raw.clone(), raw.clone()
+    sc = torch.full((M, 2 * H), float("nan"), device=dev)
+    ops.qk_normalize_save(a, sc, D, hd)
+    ops.qk_normalize(b, D, hd)
+    assert torch.equal(a, b)
+    assert torch.equal(a[:, 2 * D:], raw[:, 2 * D:])
+    assert rel_l2(a.float(), ref.reshape(M, 3 * D)) < 3e-3  # bf16 output rounding
+    assert rel_l2(sc, want_sc) < 1e-6

@@ -3,7 +3,7 @@
 (weight-gradient) stream overlaps the main stream, and the largest gaps.  Developer tool; numbers taken under the
 profiler are not bench values.
 
-    python tools/train_timeline.py [model] [batch] [modulation] [wgrad_stream 0|1]
+    python tools/train_timeline.py [model] [batch] [modulation] [wgrad_stream 0|1] [input_size]
 """
 import collections
 import json
@@ -22,18 +22,19 @@ name = sys.argv[1] if len(sys.argv) > 1 else "DiT-B/2"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 256
 modulation = sys.argv[3] if len(sys.argv) > 3 else "rotation_scaling"
 ws = int(sys.argv[4]) if len(sys.argv) > 4 else 1
+S = int(sys.argv[5]) if len(sys.argv) > 5 else 32
 torch.manual_seed(0)
-m = M.DIT_MODELS[name](in_channels=4, input_size=32, num_classes=1000, modulation=modulation).cuda().train()
+m = M.DIT_MODELS[name](in_channels=4, input_size=S, num_classes=1000, modulation=modulation).cuda().train()
 with torch.no_grad():
     for p in m.parameters():
         if p.dim() == 0:
             p.fill_(0.3)
 m.engine.trainer.wgrad_stream = bool(ws)
 ts = TrainStep(m, M.create_diffusion(""))
-x = torch.randn(B, 4, 32, 32, device="cuda")
+x = torch.randn(B, 4, S, S, device="cuda")
 t = torch.randint(0, 1000, (B,), device="cuda")
 y = torch.randint(0, 1000, (B,), device="cuda")
-n = torch.randn(B, 4, 32, 32, device="cuda")
+n = torch.randn(B, 4, S, S, device="cuda")
 for _ in range(3):
     ts.step(x, t, y, n)
 torch.cuda.synchronize()
@@ -48,7 +49,7 @@ t0 = ev[0]["ts"]
 end = max(e["ts"] + e["dur"] for e in ev)
 streams = collections.defaultdict(list)
 for e in ev:
-    streams[e["args"]["stream"]].append((e["ts"] - t0, e["ts"] - t0 + e["dur"], e["name"]))
+    streams[e["args"]["stream"]].append((e["ts"] - t0, e["ts"] - t0 + e["dur"], e["name"].replace("(anonymous namespace)::", "").replace("void ", "")))
 print(f"{name} B={B} {modulation} wgrad_stream={ws}: {len(ev)} kernels, span {(end - t0) / 1e3:.2f} ms")
 for sid, ks in streams.items():
     busy = sum(b - a for a, b, _ in ks)
@@ -91,5 +92,5 @@ agg = collections.Counter()
 for a, b, nm in allk:
     agg[nm.split("(")[0][-48:]] += b - a
 print("  kernel time by name (in-step, warm):")
-for nm, d in agg.most_common(12):
+for nm, d in agg.most_common(16):
     print(f"    {d / 1e3:7.2f} ms  {nm}")
