@@ -126,8 +126,12 @@ struct BCfg {
   static constexpr int NACC = HDV == 64 ? 64 : 80;       // accumulator columns of dQ / dK / dV
   static constexpr int PROW = RT * 128, PBLK = CB * 128;  // one panel of a 128-row tile / a 64-row block
   static constexpr int ROWB = PROW * PANELS, BLKB = PBLK * PANELS;
-  static constexpr int DQ_SMEM = 2 * ROWB + 2 * 2 * BLKB + ROW_BYTES + 1024 + 256;
-  static constexpr int DKV_SMEM = 2 * ROWB + 2 * 2 * BLKB + 2 * ROW_BYTES + 2 * 2 * CB * 4 + 1024 + 256;
+  // column-block stages (K_j | V_j, or Q_j | dO_j).  Two CTAs per SM hide the TMA latency behind each other at head_dim 64; the
+  // single CTA of head_dim 72 has the shared memory for a deeper ring instead (with two stages a block's tiles were requested only
+  // one block ahead: ncu showed 37 % of the samples in the softmax warps' wait for S)
+  static constexpr int DQ_ST = HDV == 64 ? 2 : 4, DKV_ST = HDV == 64 ? 2 : 3;
+  static constexpr int DQ_SMEM = 2 * ROWB + DQ_ST * 2 * BLKB + ROW_BYTES + 1024 + 256;
+  static constexpr int DKV_SMEM = 2 * ROWB + DKV_ST * 2 * BLKB + 2 * ROW_BYTES + 2 * 2 * CB * 4 + 1024 + 256;
   static constexpr int CTAS = HDV == 64 ? 2 : 1;               // per SM (shared memory)
   // S / dP accumulator buffers.  Two CTAs per SM (head_dim 64) overlap one CTA's softmax with the other's MMAs; the single CTA of
   // head_dim 72 gets the same overlap from a second S / dP buffer in its otherwise unused TMEM columns: scores(j+1) runs while
@@ -223,17 +227,18 @@ attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_cons
   uint8_t* sQ = smem;
   uint8_t* sdO = sQ + ROWB;
   uint8_t* sKV = sdO + ROWB;          // stage s: K_j at sKV + s*2*BLKB, V_j after it
-  uint8_t* sdS = sKV + 2 * 2 * BLKB;  // [128 x 64] bf16 K-major
+  constexpr int NST = B::DQ_ST;
+  uint8_t* sdS = sKV + NST * 2 * BLKB;  // [128 x 64] bf16 K-major
   uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + ROW_BYTES);
   uint64_t* bar_q = bars;
-  uint64_t* kv_full = bars + 1;
-  uint64_t* kv_empty = bars + 3;
-  uint64_t* s_full = bars + 5;   // [SB]
-  uint64_t* s_empty = bars + 7;  // [SB]
-  uint64_t* ds_full = bars + 9;
-  uint64_t* ds_empty = bars + 10;
-  uint64_t* o_full = bars + 11;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* kv_full = bars + 1;   // [NST <= 4]
+  uint64_t* kv_empty = bars + 5;  // [NST <= 4]
+  uint64_t* s_full = bars + 9;    // [SB]
+  uint64_t* s_empty = bars + 11;  // [SB]
+  uint64_t* ds_full = bars + 13;
+  uint64_t* ds_empty = bars + 14;
+  uint64_t* o_full = bars + 15;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
   constexpr int SB = B::SB;
   constexpr uint32_t T_DQ = SB * 128;  // dQ accumulator behind the SB x (S [0, 64) | dP [64, 128)) buffers
 
@@ -246,7 +251,7 @@ attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_cons
     prefetch_tmap(&tm_qkv_blk);
     prefetch_tmap(&tm_do_row);
     mbar_init(bar_q, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < NST; ++i) {
       mbar_init(&kv_full[i], 1);
       mbar_init(&kv_empty[i], 1);
     }
@@ -270,8 +275,8 @@ attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_cons
     load_tile<HDV>(sQ, &tm_qkv_row, bar_q, 0, h, heads, row_base + q0, PROW);
     load_tile<HDV>(sdO, &tm_do_row, bar_q, 0, h, heads, row_base + q0, PROW);
     for (int j = 0; j < nkb; ++j) {
-      const int s = j & 1;
-      mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1);
+      const int s = j % NST;
+      mbar_wait(&kv_empty[s], ((j / NST) & 1) ^ 1);
       uint8_t* dst = sKV + s * 2 * BLKB;
       mbar_arrive_expect_tx(&kv_full[s], 2 * BLKB);
       load_tile<HDV>(dst, &tm_qkv_blk, &kv_full[s], 1, h, heads, row_base + j * CB, PBLK);
@@ -283,8 +288,8 @@ attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_cons
     constexpr uint32_t idesc_q = make_idesc_bf16(RT, B::NACC, 0, 1);  // dQ += dS K_j: K_j MN-major (d contiguous)
     const uint32_t q_addr = smem_u32(sQ), do_addr = smem_u32(sdO), ds_addr = smem_u32(sdS);
     auto scores = [&](int j) {
-      const int s = j & 1, b = j % SB;
-      mbar_wait(&kv_full[s], (j >> 1) & 1);
+      const int s = j % NST, b = j % SB;
+      mbar_wait(&kv_full[s], (j / NST) & 1);
       mbar_wait(&s_empty[b], ((j / SB) & 1) ^ 1);
       tc_fence_after();
       const uint32_t k_addr = smem_u32(sKV + s * 2 * BLKB), v_addr = k_addr + BLKB;
@@ -301,7 +306,7 @@ attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_cons
     mbar_wait(bar_q, 0);
     scores(0);
     for (int j = 0; j < nkb; ++j) {
-      const int s = j & 1;
+      const int s = j % NST;
       if (j + 1 < nkb) scores(j + 1);
       mbar_wait(ds_full, j & 1);
       tc_fence_after();
@@ -406,20 +411,21 @@ attn_bwd_dkv_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_con
   uint8_t* sK = smem;
   uint8_t* sV = sK + ROWB;
   uint8_t* sQdO = sV + ROWB;             // stage s: Q_j at sQdO + s*2*BLKB, dO_j after it
-  uint8_t* sPt = sQdO + 2 * 2 * BLKB;    // [128 keys x 64 queries] bf16 K-major
+  constexpr int NST = B::DKV_ST;
+  uint8_t* sPt = sQdO + NST * 2 * BLKB;  // [128 keys x 64 queries] bf16 K-major
   uint8_t* sdSt = sPt + ROW_BYTES;
   float* sL = reinterpret_cast<float*>(sdSt + ROW_BYTES);  // [2][64]
   float* sD = sL + 2 * CB;                                  // [2][64]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sD + 2 * CB);
   uint64_t* bar_kv = bars;
-  uint64_t* qd_full = bars + 1;
-  uint64_t* qd_empty = bars + 3;
-  uint64_t* s_full = bars + 5;   // [SB]
-  uint64_t* s_empty = bars + 7;  // [SB]
-  uint64_t* p_full = bars + 9;
-  uint64_t* p_empty = bars + 10;
-  uint64_t* o_full = bars + 11;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* qd_full = bars + 1;   // [NST <= 4]
+  uint64_t* qd_empty = bars + 5;  // [NST <= 4]
+  uint64_t* s_full = bars + 9;    // [SB]
+  uint64_t* s_empty = bars + 11;  // [SB]
+  uint64_t* p_full = bars + 13;
+  uint64_t* p_empty = bars + 14;
+  uint64_t* o_full = bars + 15;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kt = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
@@ -430,7 +436,7 @@ attn_bwd_dkv_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_con
     prefetch_tmap(&tm_qkv_blk);
     prefetch_tmap(&tm_do_blk);
     mbar_init(bar_kv, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < NST; ++i) {
       mbar_init(&qd_full[i], 1);
       mbar_init(&qd_empty[i], 1);
     }
@@ -454,8 +460,8 @@ attn_bwd_dkv_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_con
     load_tile<HDV>(sK, &tm_qkv_row, bar_kv, 1, h, heads, row_base + k0, PROW);
     load_tile<HDV>(sV, &tm_qkv_row, bar_kv, 2, h, heads, row_base + k0, PROW);
     for (int j = 0; j < nqb; ++j) {
-      const int s = j & 1;
-      mbar_wait(&qd_empty[s], ((j >> 1) & 1) ^ 1);
+      const int s = j % NST;
+      mbar_wait(&qd_empty[s], ((j / NST) & 1) ^ 1);
       uint8_t* dst = sQdO + s * 2 * BLKB;
       mbar_arrive_expect_tx(&qd_full[s], 2 * BLKB);
       load_tile<HDV>(dst, &tm_qkv_blk, &qd_full[s], 0, h, heads, row_base + j * CB, PBLK);
@@ -467,8 +473,8 @@ attn_bwd_dkv_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_con
     constexpr uint32_t idesc_a = make_idesc_bf16(RT, B::NACC, 0, 1);  // dV += P^T dO_j, dK += dS^T Q_j : B MN-major
     const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), pt_addr = smem_u32(sPt), dst_addr = smem_u32(sdSt);
     auto scores = [&](int j) {
-      const int s = j & 1, b = j % SB;
-      mbar_wait(&qd_full[s], (j >> 1) & 1);
+      const int s = j % NST, b = j % SB;
+      mbar_wait(&qd_full[s], (j / NST) & 1);
       mbar_wait(&s_empty[b], ((j / SB) & 1) ^ 1);
       tc_fence_after();
       const uint32_t q_addr = smem_u32(sQdO + s * 2 * BLKB), do_addr = q_addr + BLKB;
@@ -484,7 +490,7 @@ attn_bwd_dkv_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_con
     mbar_wait(bar_kv, 0);
     scores(0);
     for (int j = 0; j < nqb; ++j) {
-      const int s = j & 1;
+      const int s = j % NST;
       if (j + 1 < nqb) scores(j + 1);
       mbar_wait(p_full, j & 1);
       tc_fence_after();

@@ -188,6 +188,24 @@ def cases():
 
     c["attn_fwd"] = attn
     c["attn_bwd"] = attn_bwd
+
+    # DiT-XL/2 @ 64x64 (BASELINE config 5): 1024 tokens, 16 heads of 72 channels, batch 32
+    XT, XH, XHD, XB = 1024, 16, 72, 32
+    XM, XD = XB * XT, XH * XHD
+
+    def attn_xl():
+        qkv, o = mk(XM, 3 * XD, scale=1.0), mk(XM, XD)
+        lse = torch.empty(XM, XH, device=dev)
+        return (lambda: ops.cos_attn(qkv, o, XB, XT, XH, XHD, lse=lse)), ("tensor", 4 * XM * XT * XD)
+
+    def attn_bwd_xl():
+        qkv, o, do = mk(XM, 3 * XD, scale=1.0), mk(XM, XD), mk(XM, XD)
+        lse = torch.empty(XM, XH, device=dev)
+        ops.cos_attn(qkv, o, XB, XT, XH, XHD, lse=lse)
+        dqkv, delta = torch.empty_like(qkv), torch.empty(XM, XH, device=dev)
+        return (lambda: ops.cos_attn_bwd(qkv, o, do, lse, dqkv, delta, XB, XT, XH, XHD)), ("tensor", 14 * XM * XT * XD)
+    c["attn_fwd_xl"] = attn_xl
+    c["attn_bwd_xl"] = attn_bwd_xl
     c["wn_fwd_3072x768"] = wn_fwd(3072, 768)
     c["wn_fwd_768x3072"] = wn_fwd(768, 3072)
     c["wn_bwd_3072x768"] = wn_bwd(3072, 768)
