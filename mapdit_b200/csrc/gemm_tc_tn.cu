@@ -238,7 +238,9 @@ extern "C" int mapdit_gemm_bf16_tn(const void* dy, int64_t ldy, const void* x, i
   }
   cudaStream_t s = (cudaStream_t)stream;
   int rc;
+  // widest tile that divides K_in: 192 covers the D = 384 / 1152 models (DiT-S, DiT-XL), whose weights are not multiples of 256 columns
   if (k_in % 256 == 0) rc = launch<256>(dy, ldy, x, ldx, c, ldc, m_tokens, n_out, k_in, s, sms);
+  else if (k_in % 192 == 0) rc = launch<192>(dy, ldy, x, ldx, c, ldc, m_tokens, n_out, k_in, s, sms);
   else if (k_in % 128 == 0) rc = launch<128>(dy, ldy, x, ldx, c, ldc, m_tokens, n_out, k_in, s, sms);
   else rc = launch<64>(dy, ldy, x, ldx, c, ldc, m_tokens, n_out, k_in, s, sms);
   if (rc != MAPDIT_OK) return rc;

@@ -20,7 +20,8 @@ def rnd(*shape, seed=0, scale=1.0):
     return (torch.randn(*shape, generator=g) * scale).cuda()
 
 
-@pytest.mark.parametrize("m,n,k", [(256, 128, 64), (1000, 384, 384), (4096, 2304, 768), (8192, 32, 768), (512, 768, 3072), (256, 4608, 768)])
+@pytest.mark.parametrize("m,n,k", [(256, 128, 64), (1000, 384, 384), (4096, 2304, 768), (8192, 32, 768), (512, 768, 3072), (256, 4608, 768),
+                                   (2048, 3456, 1152), (4096, 1152, 1152), (512, 4608, 1152), (300, 192, 576)])
 def test_gemm_bf16_tn(m, n, k):
     """wgrad GEMM: out[n, k] = dy[m, n]^T x[m, k] with both operands read MN-major in place"""
     from mapdit_b200 import ops
