@@ -123,7 +123,8 @@ typedef struct mapdit_gemm_args {
 int mapdit_gemm_bf16(const mapdit_gemm_args* args, void* stream);
 int mapdit_sizeof_gemm_args(void); /* lets a binding check its struct mirror */
 /* runtime switches (A/B and developer use; defaults are the fast paths): "gemm_2cta" (0/1) selects the cta_group::2 256xBN kernel
- * for large-M GEMMs; "gemm_2cta_bn" (0 = auto, 128 = force 128-wide pair tiles); "attn_v2" (0/1) selects the one-CTA-per-SM
+ * for large-M GEMMs; "gemm_2cta_bn" (0 = auto, 128 / 192 / 256 = force that pair-tile width where it applies); "gemm_fused_resid" (0 = first-generation
+ * residual epilogues, 1 = second generation where the main loop is short (default), 2 = always); "attn_v2" (0/1) selects the one-CTA-per-SM
  * ping-pong attention forward for tokens % 256 == 0; "attn_bwd_fused" (tokens == 256: 0 = dq + dkv kernel pair, 1 = single fused
  * kernel, 2 = fused kernel with a dedicated read-out warpgroup, the default) */
 int mapdit_set_option(const char* name, int value);

@@ -287,7 +287,7 @@ bool fused_resid_ok(const mapdit_gemm_args* g, const EpiParams& ep) {
   // 1 (default) = only where the epilogue is the bottleneck: a short main loop per tile (K x tile width <= 1024 x 256: the out-proj
   // GEMMs, and fc2 of the D = 384 models on 128-wide tiles); with K = 4 D >= 3072 (fc2 of DiT-B and up) the main loop hides the
   // first-generation epilogue and keeps its fifth operand stage.  2 = always (A/B)
-  const long long bn_tile = (g->n % 256 == 0 || g->n > 1024) ? 256 : 128;
+  const long long bn_tile = (g->n % 256 == 0 || g->n > 1024) ? 256 : (g->n % 192 == 0 ? 192 : 128);  // an upper bound is enough here
   if (g_mapdit_gemm_fused_resid == 1 && (long long)g->k * bn_tile > 1024 * 256) return false;
   if (ep.epilogue != MAPDIT_EPI_RESID && ep.epilogue != MAPDIT_EPI_RESID_MOD && ep.epilogue != MAPDIT_EPI_RESID_ROT) return false;
   if (ep.tokens % 32 != 0 || ep.ldmod % 4 != 0 || ep.ldshift % 4 != 0 || ep.N % 4 != 0) return false;
@@ -310,6 +310,17 @@ int mapdit_gemm_bf16_2cta(const mapdit_gemm_args* g, const gemm_epi::EpiParams& 
   const bool wide_ok = g->n % 256 == 0 || (g->n % 128 == 0 && (long long)nb256 * 256 * 8 <= (long long)g->n * 9);
   extern int g_mapdit_gemm_2cta_bn;  // developer switch (mapdit_set_option "gemm_2cta_bn"): 0 = auto, 128 / 256 = force that tile width
   if (g_mapdit_gemm_2cta_bn == 128 && g->n % 128 == 0) return launch2_any<128>(g, ep, stream, num_sms);
+  // 192-wide tiles where they divide N and save whole rounds of the persistent grid: a 256 x 256 tiling of the N = 768 GEMMs of
+  // DiT-B/2 (out-proj, fc2, three dgrads per block) is 768 tiles = 10.4 rounds of 74 CTA pairs, i.e. 11 rounds with 46 pairs idle in
+  // the last one; 1024 tiles of 256 x 192 are 13.8 rounds of 3/4 the length (-4.5 %).  Cost model: rounds x tile width.
+  const long long pairs = (mb + 1) / 2, cl = num_sms / 2;
+  auto cost = [&](int bn) { return ((pairs * ((g->n + bn - 1) / bn) + cl - 1) / cl) * bn; };
+  const bool ok192 = g->n % 192 == 0 && pairs * (g->n / 192) >= cl;
+  if (g_mapdit_gemm_2cta_bn == 192 && ok192) return launch2_any<192>(g, ep, stream, num_sms);
+  if (g_mapdit_gemm_2cta_bn == 0 && ok192 && (!wide_ok || cost(192) * 100 <= cost(256) * 97)) {
+    const bool narrow_ok = g->n % 128 == 0 && pairs * (g->n / 128) >= num_sms;
+    if (wide_ok || !narrow_ok || cost(192) * 100 <= cost(128) * 97) return launch2_any<192>(g, ep, stream, num_sms);
+  }
   if (wide_ok && (long long)((mb + 1) / 2) * nb256 >= num_sms / 2) return launch2_any<256>(g, ep, stream, num_sms);
   if (g->n % 128 == 0 && (long long)((mb + 1) / 2) * (g->n / 128) >= num_sms) return launch2_any<128>(g, ep, stream, num_sms);
   return MAPDIT_ERR_UNSUPPORTED;
