@@ -108,8 +108,10 @@ def lib():
         L.mapdit_rotmod_bwd_partials.argtypes = [_i, _i]
         L.mapdit_rotmod_bwd_partials.restype = _i
         _lib = L
-        if os.environ.get("MAPDIT_GEMM_2CTA") is not None:
-            L.mapdit_set_option(b"gemm_2cta", int(os.environ["MAPDIT_GEMM_2CTA"]))
+        for env, opt in (("MAPDIT_GEMM_2CTA", b"gemm_2cta"), ("MAPDIT_GEMM_2CTA_BN", b"gemm_2cta_bn"),
+                         ("MAPDIT_GEMM_FUSED_RESID", b"gemm_fused_resid")):  # developer A/B switches
+            if os.environ.get(env) is not None:
+                L.mapdit_set_option(opt, int(os.environ[env]))
     return _lib
 
 

@@ -310,14 +310,15 @@ int mapdit_gemm_bf16_2cta(const mapdit_gemm_args* g, const gemm_epi::EpiParams& 
   const bool wide_ok = g->n % 256 == 0 || (g->n % 128 == 0 && (long long)nb256 * 256 * 8 <= (long long)g->n * 9);
   extern int g_mapdit_gemm_2cta_bn;  // developer switch (mapdit_set_option "gemm_2cta_bn"): 0 = auto, 128 / 256 = force that tile width
   if (g_mapdit_gemm_2cta_bn == 128 && g->n % 128 == 0) return launch2_any<128>(g, ep, stream, num_sms);
-  // 192-wide tiles where they divide N and save whole rounds of the persistent grid: a 256 x 256 tiling of the N = 768 GEMMs of
-  // DiT-B/2 (out-proj, fc2, three dgrads per block) is 768 tiles = 10.4 rounds of 74 CTA pairs, i.e. 11 rounds with 46 pairs idle in
-  // the last one; 1024 tiles of 256 x 192 are 13.8 rounds of 3/4 the length (-4.5 %).  Cost model: rounds x tile width.
+  // 192-wide tiles where they divide N and save whole rounds of the persistent grid (cost model: rounds x tile width) — but only
+  // for the narrow models' shapes (N not a multiple of 256, or K <= 512).  Measured: DiT-S/2 training 16.80 -> 16.04 ms; on the
+  // N = 768 GEMMs of DiT-B/2 (K >= 768) the extra re-reads of the A tile cost more than the 46 idle CTA pairs of the eleventh round
+  // of a 256 x 256 tiling (out-proj 0.0952 -> 0.0973 ms, fc2 0.2439 -> 0.2550 ms), so those keep 256.
   const long long pairs = (mb + 1) / 2, cl = num_sms / 2;
   auto cost = [&](int bn) { return ((pairs * ((g->n + bn - 1) / bn) + cl - 1) / cl) * bn; };
   const bool ok192 = g->n % 192 == 0 && pairs * (g->n / 192) >= cl;
   if (g_mapdit_gemm_2cta_bn == 192 && ok192) return launch2_any<192>(g, ep, stream, num_sms);
-  if (g_mapdit_gemm_2cta_bn == 0 && ok192 && (!wide_ok || cost(192) * 100 <= cost(256) * 97)) {
+  if (g_mapdit_gemm_2cta_bn == 0 && ok192 && (g->n % 256 != 0 || g->k <= 512) && (!wide_ok || cost(192) * 100 <= cost(256) * 97)) {
     const bool narrow_ok = g->n % 128 == 0 && pairs * (g->n / 128) >= num_sms;
     if (wide_ok || !narrow_ok || cost(192) * 100 <= cost(128) * 97) return launch2_any<192>(g, ep, stream, num_sms);
   }
