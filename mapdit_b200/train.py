@@ -107,6 +107,7 @@ class TrainStep:
                     tr.backward(saved, dout)
                     if reduce:
                         self.reducer.finish()
+                    self._reduced = bool(reduce)
             finally:
                 tr.grad_buffers = None
                 tr.grad_hook = None
@@ -114,6 +115,9 @@ class TrainStep:
 
     def apply_grads(self):
         """one fused Adam launch over the flat span (train.py:96,104: optimizer.step(); scheduler.step()), then the EMA hook"""
+        if self.flat_g16 is not None and not getattr(self, "_reduced", False):
+            raise RuntimeError("TrainStep.apply_grads: the gradients of this step were not all-reduced (compute_grads(reduce=False)); "
+                               "with world_size > 1 the optimiser reads the reduced bf16 copy")
         with torch.cuda.device(self.flat_p.device), torch.no_grad():
             lr = self.lr * (self.lr_lambda(self.step_count) if self.lr_lambda is not None else 1.0)
             self.step_count += 1
