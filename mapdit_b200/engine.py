@@ -175,8 +175,22 @@ class Engine:
         self._ws[key] = ws
         return ws
 
+    _COND_KEYS = ("mods", "smu", "ssg", "rotcs")
+
+    def cond_slot(self, ws, slot):
+        """the conditioning outputs (modulation vectors, rotation tables, MPScale factors) of `ws`, slot 0 = the workspace's own
+        buffers, slot 1 = a second set (allocated on first use): the graphed sampling loop computes step k+1's conditioning into
+        one slot on a side branch while step k's blocks read the other"""
+        if slot == 0:
+            return {k: ws[k] for k in self._COND_KEYS if k in ws}
+        if "cond1" not in ws:
+            ws["cond1"] = {k: torch.empty_like(ws[k]) for k in self._COND_KEYS if k in ws}
+        return ws["cond1"]
+
     # ------------------------------------------------------------------ forward
-    def forward(self, x, t, y, train=False, drop_mask=None):
+    def forward(self, x, t, y, train=False, drop_mask=None, cond_ready=None):
+        """`cond_ready` (eval only): conditioning slot that already holds the outputs of `conditioning(t, y)` — the chain at the head
+        of the forward is skipped and the blocks read that slot"""
         m = self.m
         if not x.is_cuda:
             raise RuntimeError("mapdit_b200.DiT runs on CUDA only (hand-written sm_100a kernels, no CPU fallback)")
@@ -185,30 +199,36 @@ class Engine:
             from .autograd import dit_forward_autograd
             return dit_forward_autograd(self, x, t, y, drop_mask)
         with torch.cuda.device(x.device):  # kernels launch on the current device's stream: make it the tensors' device
-            return self._forward_impl(x, t, y, train, drop_mask, mode, save=None)
+            return self._forward_impl(x, t, y, train, drop_mask, mode, save=None, cond_ready=cond_ready)
 
-    def _forward_impl(self, x, t, y, train, drop_mask, mode, save):
+    def _forward_impl(self, x, t, y, train, drop_mask, mode, save, cond_ready=None):
         prev = ops.set_variant(self.m.variant)
         try:
-            return self._forward_body(x, t, y, train, drop_mask, mode, save)
+            return self._forward_body(x, t, y, train, drop_mask, mode, save, cond_ready)
         finally:
             ops.set_variant(prev)
 
-    def _forward_body(self, x, t, y, train, drop_mask, mode, save):
+    def conditioning(self, t, y, slot=0, train=False, drop_mask=None):
+        """the part of the forward that depends on (t, y) only (src/dit.py:86-88 + every block's modulation linear,
+        src/blocks/dit_block.py:33, + MPScale of the final layer) into conditioning slot `slot`"""
         m = self.m
-        N = x.shape[0]
-        dev = x.device
-        D, L, T = m.hidden_size, m.depth, (m.input_size // m.patch_size) ** 2
-        H, hd = m.num_heads, m.hidden_size // m.num_heads
-        x = x.contiguous().float()
-        t = t.contiguous().to(torch.int64)
-        y = y.contiguous().to(torch.int64)
-        W = self.weights(mode, train)
-        ws = self.workspace(N, mode, dev)
-        ld = ws["mods"].shape[1]
-        bf = mode == "bf16"
+        mode = m.compute_dtype
+        prev = ops.set_variant(m.variant)
+        try:
+            with torch.cuda.device(t.device):
+                W = self.weights(mode, train)
+                ws = self.workspace(t.shape[0], mode, t.device)
+                self._conditioning(ws, W, t.contiguous().to(torch.int64), y.contiguous().to(torch.int64), train, drop_mask, mode,
+                                   self.cond_slot(ws, slot))
+        finally:
+            ops.set_variant(prev)
 
-        # ---- conditioning (fp32; src/dit.py:86-88, timestep_embedder.py:18-43, label_embedder.py:29-34)
+    def _conditioning(self, ws, W, t, y, train, drop_mask, mode, cb):
+        m = self.m
+        N, dev = t.shape[0], t.device
+        D, L = m.hidden_size, m.depth
+        bf = mode == "bf16"
+        ld = cb["mods"].shape[1]
         fl = m.flags
         if fl["use_mp_embedding"]:
             ops.fourier(t, m.t_embedder.embedding.scale, m.t_embedder.embedding.shift, ws["e"])
@@ -225,14 +245,44 @@ class Engine:
         ops.embed_rows(y, mask, m.num_classes, m.y_embedder.embedding.weight.data, ws["yemb"])
         ops.cond_combine(ws["temb"], ws["yemb"], ws["c"], ws["cs"], ws["cs16"])
         if bf:
-            ops.gemm_bf16(ws["cs16"], W.wmod, ws["mods"])
+            ops.gemm_bf16(ws["cs16"], W.wmod, cb["mods"])
         else:
-            ops.gemm_f32(ws["cs"], W.wmod, out=ws["mods"])
+            ops.gemm_f32(ws["cs"], W.wmod, out=cb["mods"])
         f = m.final_layer
-        ops.mp_scale(ws["c"], W.wmu, f.mean_scale.reference.data, ws["smu"])
-        ops.mp_scale(ws["c"], W.wsg, f.sigma_scale.reference.data, ws["ssg"])
+        ops.mp_scale(ws["c"], W.wmu, f.mean_scale.reference.data, cb["smu"])
+        ops.mp_scale(ws["c"], W.wsg, f.sigma_scale.reference.data, cb["ssg"])
+        if "rotcs" in cb and self._fused_rot(mode):
+            lay, mods, rcs, blk = self.layout, cb["mods"], cb["rotcs"], m.blocks
+            for i in range(L):
+                ops.rot_table(mods[:, i * lay["width"] + lay["rot_a"]:], blk[i].gain_msa.data, rcs[:, (2 * i) * D:], ld, D,
+                              mods[:, i * lay["width"] + lay["rot_m"]:], blk[i].gain_mlp.data, rcs[:, (2 * i + 1) * D:])
 
-        mods = ws["mods"]
+    def _fused_rot(self, mode):
+        fl = self.m.flags
+        return mode == "bf16" and self.m.modulation != "adaln" and fl["use_no_layernorm"] and fl["use_cosine_attention"]
+
+    def _forward_body(self, x, t, y, train, drop_mask, mode, save, cond_ready=None):
+        m = self.m
+        N = x.shape[0]
+        dev = x.device
+        D, L, T = m.hidden_size, m.depth, (m.input_size // m.patch_size) ** 2
+        H, hd = m.num_heads, m.hidden_size // m.num_heads
+        x = x.contiguous().float()
+        W = self.weights(mode, train)
+        ws = self.workspace(N, mode, dev)
+        bf = mode == "bf16"
+        fl = m.flags
+        # ---- conditioning (fp32; src/dit.py:86-88, timestep_embedder.py:18-43, label_embedder.py:29-34)
+        cb = self.cond_slot(ws, cond_ready or 0)
+        if cond_ready is None:
+            self._conditioning(ws, W, t.contiguous().to(torch.int64), y.contiguous().to(torch.int64), train, drop_mask, mode, cb)
+        ld = cb["mods"].shape[1]
+        f = m.final_layer
+        mods = cb["mods"]
+        return self._blocks(x, ws, W, cb, mods, ld, N, dev, D, L, T, H, hd, bf, fl, f, mode)
+
+    def _blocks(self, x, ws, W, cb, mods, ld, N, dev, D, L, T, H, hd, bf, fl, f, mode):
+        m = self.m
         lay = self.layout
         adaln = m.modulation == "adaln"
         ln = not fl["use_no_layernorm"]  # vanilla adaLN: LayerNorm then x(1+scale)+shift (UNPINNED)
@@ -277,10 +327,7 @@ class Engine:
         # the same for rotation(+scaling) modulation: BASELINE.json's headline configuration (UNPINNED)
         fused_rot = bf and not adaln and not ln and cosine
         if fused_rot:
-            rcs = ws["rotcs"]
-            for i in range(L):
-                ops.rot_table(mod(i, "rot_a"), blk[i].gain_msa.data, rcs[:, (2 * i) * D:], ld, D,
-                              mod(i, "rot_m"), blk[i].gain_mlp.data, rcs[:, (2 * i + 1) * D:])
+            rcs = cb["rotcs"]  # filled by _conditioning
             has_sc = "scale_a" in lay
         # ---- patch embed + first modulate (src/dit.py:81-84)
         X, Hb = ws["x"], ws["h"]
@@ -341,5 +388,5 @@ class Engine:
         else:
             ops.gemm_f32(Hb, W.wfl, out=ws["lin"])
         out = torch.empty(N, 2 * m.in_channels, m.input_size, m.input_size, device=dev, dtype=torch.float32)
-        ops.final_unpatchify(ws["lin"], ws["smu"], ws["ssg"], out, m.patch_size)
+        ops.final_unpatchify(ws["lin"], cb["smu"], cb["ssg"], out, m.patch_size)
         return out
