@@ -101,9 +101,11 @@ class ClockSampler:
 
 # --------------------------------------------------------------------------------------------- reference arm (CPU)
 def run_reference(args, workload=None, emit=True):
-    """The reference's own implementation of the path cannot travel to the GPU box (it is a Python repo mounted
-    read-only in the build container), so this arm times its pinned CPU restatement (oracle/, kind 'port') on all
-    host cores, on a bounded sample of the same workload."""
+    """The reference arm: the reference's own CPU implementation of the path on all host cores, on a bounded sample of the same
+    workload.  When `oracle/_ref` is there (the UNMODIFIED reference mirrored by oracle/vendor_reference.py: it travels to the GPU
+    box with the snapshot) that is the reference ITSELF through its public API — `DIT_MODELS[...]`, `create_diffusion`,
+    `training_losses` + `torch.optim.Adam` as in train.py:86-96, `p_sample` as in sample.py:52-61 — with its MP-AdaLN modulation (the
+    only one it has code for), `cpu_baseline.kind = "reference"`; otherwise the pinned restatement (oracle/, kind "port")."""
     import torch
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -116,47 +118,81 @@ def run_reference(args, workload=None, emit=True):
         line["sample50"] = {k: sl[k] for k in ("value", "unit", "ms_per_step", "cpu_baseline", "e2e")}
         emit_line(line)
         return line
-        return line
-    from oracle import mapdit_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cfg = O.config_for(MODEL, modulation=MODULATION)
-    sd = O.init_state_dict(cfg, seed=0)
-    B = 8
+    B, S = 8, args.input_size
     g = torch.Generator().manual_seed(1)
-    x = torch.randn(B, 4, 32, 32, generator=g)
+    x = torch.randn(B, 4, S, S, generator=g)
     y = torch.randint(0, 1000, (B,), generator=g)
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    use_ref = os.path.isfile(os.path.join(ref_dir, "src", "models.py")) and not args.flags_off
     times = []
-    if workload == "train":
-        p = O.make_params(sd)
-        T = O.make_tables("")
-        opt = torch.optim.Adam([v for v in p.values() if v.requires_grad], lr=1e-2, betas=(0.9, 0.99))
-        t = torch.randint(0, 1000, (B,), generator=g)
-        noise = torch.randn(B, 4, 32, 32, generator=g)
-        sample = f"{MODEL} training step (loss+backward+Adam) at batch {B} on the CPU oracle"
+    nsub = 2 if workload == "sample" else 1
+    if use_ref:
+        kind, who, modulation = "reference", "the unmodified reference (oracle/_ref) on the host cores", "adaln (the reference has no other)"
+        if ref_dir not in sys.path:
+            sys.path.insert(0, ref_dir)
+        from diffusion import create_diffusion as ref_create_diffusion  # the reference's packages
+        from src.models import DIT_MODELS as REF_MODELS
+        torch.manual_seed(0)
+        model = REF_MODELS[MODEL](in_channels=4, input_size=S, num_classes=1000)
+        if workload == "train":
+            diffusion = ref_create_diffusion(timestep_respacing="")
+            opt = torch.optim.Adam(model.parameters(), lr=1e-2, betas=(0.9, 0.99))
+            model.train()
 
-        def step():
-            opt.zero_grad()
-            O.train_step_grads(p, cfg, T, x, t, y, noise)
-            opt.step()
-        per_step_images = B
+            def step():  # train.py:86-96
+                t = torch.randint(0, diffusion.num_timesteps, (B,))
+                loss = diffusion.training_losses(model, x, t, dict(y=y))["loss"].mean()
+                opt.zero_grad()
+                loss.backward()
+                opt.step()
+        else:
+            diffusion = ref_create_diffusion(str(SAMPLING_STEPS))
+            model.eval()
+
+            def step():  # the first `nsub` iterations of p_sample_loop (sample.py:52-61 without CFG), or one eval forward
+                img = x
+                with torch.no_grad():
+                    for k in range(nsub):
+                        tt = torch.full((B,), diffusion.num_timesteps - 1 - k, dtype=torch.long)
+                        if workload == "sample":
+                            img = diffusion.p_sample(model.forward, img, tt, clip_denoised=True, model_kwargs=dict(y=y))["sample"]
+                        else:
+                            model(img, tt, y)
     else:
-        T = O.make_tables(str(SAMPLING_STEPS))
-        tm = torch.tensor(T.timestep_map)
-        nsub = 2 if workload == "sample" else 1
-        sample = (f"{MODEL} {nsub} of {SAMPLING_STEPS} sampling steps at batch {B} on the CPU oracle, scaled to {SAMPLING_STEPS} steps"
-                  if workload == "sample" else f"{MODEL} eval forward at batch {B} on the CPU oracle")
+        from oracle import mapdit_oracle as O
+        kind, who, modulation = "port", "the pinned CPU restatement (oracle/mapdit_oracle.py)", MODULATION
+        cfg = O.config_for(MODEL, modulation=MODULATION, input_size=S)
+        sd = O.init_state_dict(cfg, seed=0)
+        if workload == "train":
+            p = O.make_params(sd)
+            T = O.make_tables("")
+            opt = torch.optim.Adam([v for v in p.values() if v.requires_grad], lr=1e-2, betas=(0.9, 0.99))
+            t = torch.randint(0, 1000, (B,), generator=g)
+            noise = torch.randn(B, 4, S, S, generator=g)
 
-        def step():
-            img = x
-            with torch.no_grad():
-                for k in range(nsub):
-                    i = T.num_timesteps - 1 - k
-                    tt = torch.full((B,), i, dtype=torch.long)
-                    out = O.dit_forward(sd, cfg, img, tm[tt], y)
-                    if workload == "sample":
-                        img = O.p_sample_step(T, out, img, tt, torch.randn_like(img))["sample"]
-        per_step_images = B * nsub / SAMPLING_STEPS if workload == "sample" else B
+            def step():
+                opt.zero_grad()
+                O.train_step_grads(p, cfg, T, x, t, y, noise)
+                opt.step()
+        else:
+            T = O.make_tables(str(SAMPLING_STEPS))
+            tm = torch.tensor(T.timestep_map)
+
+            def step():
+                img = x
+                with torch.no_grad():
+                    for k in range(nsub):
+                        i = T.num_timesteps - 1 - k
+                        tt = torch.full((B,), i, dtype=torch.long)
+                        out = O.dit_forward(sd, cfg, img, tm[tt], y)
+                        if workload == "sample":
+                            img = O.p_sample_step(T, out, img, tt, torch.randn_like(img))["sample"]
+    sample = {"train": f"{MODEL} training step (training_losses + backward + Adam) at batch {B}",
+              "sample": f"{MODEL} {nsub} of {SAMPLING_STEPS} sampling steps at batch {B}, scaled to {SAMPLING_STEPS} steps",
+              "forward": f"{MODEL} eval forward at batch {B}"}[workload] + f": {who}"
+    per_step_images = B * nsub / SAMPLING_STEPS if workload == "sample" else B
     for i in range(args.warmup + args.steps):
         t0 = time.perf_counter()
         step()
@@ -168,8 +204,9 @@ def run_reference(args, workload=None, emit=True):
     line = {"impl": "reference", "metric": metric_name(workload), "value": value, "unit": unit, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(workload), "model": MODEL, "modulation": MODULATION, "batch_per_step": B},
-            "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
+            "config": {"workload": workload_name(workload), "model": MODEL, "modulation": modulation, "batch_per_step": B,
+                       "note": "bounded sample of the workload at batch 8 on the host cores; img/s is per image, so it compares with the GPU arm's"},
+            "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     if emit:
         emit_line(line)

@@ -203,3 +203,22 @@ def test_epilogue_and_variant_constants_match_header():
     for name in ("STORE", "QKNORM", "MPSILU", "RESID_MOD", "RESID", "SILU_BWD", "RESID_ROT", "STORE_DELTA"):
         assert defs[f"MAPDIT_EPI_{name}"] == getattr(_lib, f"EPI_{name}"), name
     assert len({defs[k] for k in defs if k.startswith("MAPDIT_EPI_")}) == 8  # no two selectors share a value
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """`bench.py --impl reference`: the reference's own CPU implementation (oracle/_ref, the unmodified reference mirrored by
+    oracle/vendor_reference.py) when present, else the pinned restatement; one JSON line with the contract's keys"""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--model", "DiT-XS/8", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    have_ref = os.path.isfile(os.path.join(ROOT, "oracle", "_ref", "src", "models.py"))
+    assert d["impl"] == "reference" and d["unit"] == "img/s" and d["value"] > 0 and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == ("reference" if have_ref else "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["sample50"]["value"] > 0 and d["sample50"]["cpu_baseline"]["kind"] == d["cpu_baseline"]["kind"]
