@@ -31,7 +31,6 @@ using namespace tc;
 constexpr int HD = 64, RT = 128, CB = 64;     // row tile (TMEM lanes), column block
 constexpr int ROW_BYTES = RT * HD * 2;        // 16 KB  [128 x 64] bf16
 constexpr int BLK_BYTES = CB * HD * 2;        // 8 KB   [64 x 64] bf16
-constexpr int NTHREADS = 192;
 constexpr uint32_t TMEM_COLS = 256;
 constexpr float LOG2E = 1.4426950408889634f;
 
@@ -126,19 +125,18 @@ struct BCfg {
   static constexpr int NACC = HDV == 64 ? 64 : 80;       // accumulator columns of dQ / dK / dV
   static constexpr int PROW = RT * 128, PBLK = CB * 128;  // one panel of a 128-row tile / a 64-row block
   static constexpr int ROWB = PROW * PANELS, BLKB = PBLK * PANELS;
-  // column-block stages (K_j | V_j, or Q_j | dO_j).  Two CTAs per SM hide the TMA latency behind each other at head_dim 64; the
-  // single CTA of head_dim 72 has the shared memory for a deeper ring instead (with two stages a block's tiles were requested only
-  // one block ahead: ncu showed 37 % of the samples in the softmax warps' wait for S)
-  static constexpr int DQ_ST = HDV == 64 ? 2 : 4, DKV_ST = HDV == 64 ? 2 : 3;
-  static constexpr int DQ_SMEM = 2 * ROWB + DQ_ST * 2 * BLKB + ROW_BYTES + 1024 + 256;
-  static constexpr int DKV_SMEM = 2 * ROWB + DKV_ST * 2 * BLKB + 2 * ROW_BYTES + 2 * 2 * CB * 4 + 1024 + 256;
-  static constexpr int CTAS = HDV == 64 ? 2 : 1;               // per SM (shared memory)
-  // S / dP accumulator buffers.  Two CTAs per SM (head_dim 64) overlap one CTA's softmax with the other's MMAs; the single CTA of
-  // head_dim 72 gets the same overlap from a second S / dP buffer in its otherwise unused TMEM columns: scores(j+1) runs while
-  // the softmax warps still work on block j
-  static constexpr int SB = HDV == 64 ? 1 : 2;
-  static constexpr uint32_t DQ_TMEM = HDV == 64 ? 256 : 512;   // SB x (S 64 + dP 64) + dQ NACC
-  static constexpr uint32_t DKV_TMEM = HDV == 64 ? 256 : 512;  // SB x (S^T 64 + dP^T 64) + dK NACC + dV NACC
+  // One CTA per SM.  Ring of column-block stages (K_j | V_j, or Q_j | dO_j): with two stages a block's tiles were requested only one
+  // block ahead and ncu showed 37 % of the samples in the softmax warps' wait for S
+  static constexpr int NST = 4;
+  // softmax warps: one per TMEM lane quarter, each thread a whole 64-column row of the logit block
+  static constexpr int NSW = 4;
+  static constexpr int NTHR = 64 + NSW * 32;
+  static constexpr int DQ_SMEM = 2 * ROWB + NST * 2 * BLKB + 1024 + 256;
+  static constexpr int DKV_SMEM = 2 * ROWB + NST * 2 * BLKB + 2 * 2 * CB * 4 + 1024 + 256;
+  // TMEM: two (S [0, 64) | dP [64, 128)) buffers, then the accumulators (dQ, or dK and dV).  scores(j+1) runs on the tensor core while
+  // the softmax warps still work on block j.
+  static constexpr uint32_t T_ACC = 256;
+  static constexpr uint32_t TMEM = 512;
 };
 __host__ __device__ constexpr float att_scale_of(int hdv) { return hdv == 64 ? 0.125f : 0.11785113019775793f; }  // 1/sqrt(hd)
 __host__ __device__ constexpr float sqrt_hd_of(int hdv) { return hdv == 64 ? 8.0f : 8.48528137423857f; }
@@ -213,34 +211,41 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
 }
 
 // ------------------------------------------------------------------------------------------------ dQ
+// dS never touches shared memory: the softmax thread that owns a query row reads its S and dP values from TMEM, and writes the 64 bf16
+// dS values back IN PLACE over the S columns it has just read (packed pairs, 16 columns per 32 keys at column 0 and 32 of the buffer);
+// the dQ += dS K_j MMAs take that tile as their A operand straight from TMEM.  With the [128 x 64] logit blocks of this kernel an MMA is
+// only 32-40 tensor-core cycles long but fetches 6 KB of operands, so shared-memory bandwidth (MMA operand reads + the staging tile's
+// stores and re-reads + TMA writes: 134 KB per block, 128 B/clk) was the bound of the first version, and every other shared-memory
+// access (mbarrier polls, fences) queued behind it (tools/attn_bwd_xl_timeline.py).  The tensor core executes one thread's MMAs in issue
+// order, which is all the protection the in-place tile needs: S(j+2) is issued after dQ(j) and cannot overtake it.
 template <int HDV>
-__global__ void __launch_bounds__(NTHREADS, BCfg<HDV>::CTAS)
+__global__ void __launch_bounds__(BCfg<HDV>::NTHR, 1)
 attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_constant__ CUtensorMap tm_qkv_blk,
                const __grid_constant__ CUtensorMap tm_do_row, const bf16* __restrict__ o, const bf16* __restrict__ dout,
                const float* __restrict__ lse, float* __restrict__ delta, bf16* __restrict__ dqkv, int tokens, int heads,
-               const bf16* __restrict__ qkv, const float* __restrict__ sc, float eps) {
+               const bf16* __restrict__ qkv, const float* __restrict__ sc, float eps, long long* __restrict__ dbg) {
   using B = BCfg<HDV>;
-  constexpr int ROWB = B::ROWB, BLKB = B::BLKB, PROW = B::PROW, PBLK = B::PBLK;
+  // optional timeline of CTA (0,0,0) (tools/attn_bwd_xl_timeline.py): dbg[role*256 + 4*j + e] = clock64 at event e of key block j
+#define DQ_STAMP(role, j, e)                                                                                          \
+  do {                                                                                                                \
+    if (dbg && (blockIdx.x | blockIdx.y | blockIdx.z) == 0 && (j) < 64 && lane == 0) dbg[(role) * 256 + 4 * (j) + (e)] = clock64(); \
+  } while (0)
+  constexpr int ROWB = B::ROWB, BLKB = B::BLKB, PROW = B::PROW, PBLK = B::PBLK, NST = B::NST, NSW = B::NSW;
+  constexpr uint32_t T_DQ = B::T_ACC;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   uint8_t* sQ = smem;
   uint8_t* sdO = sQ + ROWB;
-  uint8_t* sKV = sdO + ROWB;          // stage s: K_j at sKV + s*2*BLKB, V_j after it
-  constexpr int NST = B::DQ_ST;
-  uint8_t* sdS = sKV + NST * 2 * BLKB;  // [128 x 64] bf16 K-major
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + ROW_BYTES);
+  uint8_t* sKV = sdO + ROWB;  // stage s: K_j at sKV + s*2*BLKB, V_j after it
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + NST * 2 * BLKB);
   uint64_t* bar_q = bars;
-  uint64_t* kv_full = bars + 1;   // [NST <= 4]
-  uint64_t* kv_empty = bars + 5;  // [NST <= 4]
-  uint64_t* s_full = bars + 9;    // [SB]
-  uint64_t* s_empty = bars + 11;  // [SB]
-  uint64_t* ds_full = bars + 13;
-  uint64_t* ds_empty = bars + 14;
-  uint64_t* o_full = bars + 15;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
-  constexpr int SB = B::SB;
-  constexpr uint32_t T_DQ = SB * 128;  // dQ accumulator behind the SB x (S [0, 64) | dP [64, 128)) buffers
+  uint64_t* kv_full = bars + 1;   // [NST]
+  uint64_t* kv_empty = bars + 5;  // [NST]
+  uint64_t* s_full = bars + 9;    // [2]  S / dP of a block are in TMEM
+  uint64_t* ds_full = bars + 11;  // [2]  dS of a block is in TMEM
+  uint64_t* o_full = bars + 13;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
@@ -257,14 +262,12 @@ attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_cons
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], 4);
+      mbar_init(&ds_full[i], NSW);
     }
-    mbar_init(ds_full, 4);
-    mbar_init(ds_empty, 1);
     mbar_init(o_full, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<B::DQ_TMEM>(tmem_slot);
+  if (warp == 1) tmem_alloc<B::TMEM>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -277,6 +280,7 @@ attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_cons
     for (int j = 0; j < nkb; ++j) {
       const int s = j % NST;
       mbar_wait(&kv_empty[s], ((j / NST) & 1) ^ 1);
+      DQ_STAMP(2, j, 0);
       uint8_t* dst = sKV + s * 2 * BLKB;
       mbar_arrive_expect_tx(&kv_full[s], 2 * BLKB);
       load_tile<HDV>(dst, &tm_qkv_blk, &kv_full[s], 1, h, heads, row_base + j * CB, PBLK);
@@ -285,38 +289,42 @@ attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_cons
   } else if (warp == 1) {
     const bool leader = elect_one();  // whole warp runs the loop, one lane issues (see tc_common.cuh)
     constexpr uint32_t idesc_s = make_idesc_bf16(RT, CB, 0, 0);       // S / dP: both operands K-major
-    constexpr uint32_t idesc_q = make_idesc_bf16(RT, B::NACC, 0, 1);  // dQ += dS K_j: K_j MN-major (d contiguous)
-    const uint32_t q_addr = smem_u32(sQ), do_addr = smem_u32(sdO), ds_addr = smem_u32(sdS);
+    constexpr uint32_t idesc_q = make_idesc_bf16(RT, B::NACC, 0, 1);  // dQ += dS K_j: dS from TMEM, K_j MN-major (d contiguous)
+    // descriptors of the resident tiles and of ring slot 0; every MMA operand is one of these moved by a compile-time or per-block offset
+    const uint64_t d_q = make_smem_desc(smem_u32(sQ), 16, 1024), d_do = make_smem_desc(smem_u32(sdO), 16, 1024);
+    const uint64_t d_kv = make_smem_desc(smem_u32(sKV), 16, 1024);     // K-major view of a K / V block (S, dP)
+    const uint64_t d_kmn = make_smem_desc(smem_u32(sKV), PBLK, 1024);  // MN-major view of a K block (dQ): LBO = panel stride
     auto scores = [&](int j) {
-      const int s = j % NST, b = j % SB;
+      const int s = j % NST, b = j & 1;
       mbar_wait(&kv_full[s], (j / NST) & 1);
-      mbar_wait(&s_empty[b], ((j / SB) & 1) ^ 1);
       tc_fence_after();
-      const uint32_t k_addr = smem_u32(sKV + s * 2 * BLKB), v_addr = k_addr + BLKB;
+      const uint64_t d_k = desc_advance(d_kv, s * 2 * BLKB), d_v = desc_advance(d_k, BLKB);
       const uint32_t t_s = tmem_base + b * 128;
       // the S and dP chains accumulate into different TMEM tiles: issued alternately so consecutive MMAs are independent
 #pragma unroll
       for (int k = 0; k < B::KST; ++k) {
         const uint32_t ro = (k >> 2) * PROW + (k & 3) * 32, bo = (k >> 2) * PBLK + (k & 3) * 32;  // panel + 16-channel step
-        if (leader) umma_ss(t_s, make_smem_desc(q_addr + ro, 16, 1024), make_smem_desc(k_addr + bo, 16, 1024), idesc_s, k != 0);
-        if (leader) umma_ss(t_s + 64, make_smem_desc(do_addr + ro, 16, 1024), make_smem_desc(v_addr + bo, 16, 1024), idesc_s, k != 0);
+        if (leader) umma_ss(t_s, desc_advance(d_q, ro), desc_advance(d_k, bo), idesc_s, k != 0);
+        if (leader) umma_ss(t_s + 64, desc_advance(d_do, ro), desc_advance(d_v, bo), idesc_s, k != 0);
       }
       if (leader) umma_commit(&s_full[b]);
     };
     mbar_wait(bar_q, 0);
     scores(0);
     for (int j = 0; j < nkb; ++j) {
-      const int s = j % NST;
-      if (j + 1 < nkb) scores(j + 1);
-      mbar_wait(ds_full, j & 1);
+      const int s = j % NST, b = j & 1;
+      if (j + 1 < nkb) scores(j + 1);  // into the other buffer: its dS tile was read by dQ(j-1), issued before this
+      DQ_STAMP(0, j, 0);
+      mbar_wait(&ds_full[b], (j >> 1) & 1);
       tc_fence_after();
-      const uint32_t k_addr = smem_u32(sKV + s * 2 * BLKB);
+      DQ_STAMP(0, j, 1);
+      const uint64_t d_b = desc_advance(d_kmn, s * 2 * BLKB);
+      const uint32_t t_ds = tmem_base + b * 128;
 #pragma unroll
-      for (int k = 0; k < CB / 16; ++k)
-        if (leader) umma_ss(tmem_base + T_DQ, make_smem_desc(ds_addr + k * 32, 16, 1024), make_smem_desc(k_addr + k * 2048, PBLK, 1024), idesc_q,
-                (j | k) != 0);
+      for (int k = 0; k < CB / 16; ++k)  // 16 keys = 8 packed columns; keys 32.. start at column 32
+        if (leader) umma_ts(tmem_base + T_DQ, t_ds + (k >> 1) * 32 + (k & 1) * 8, desc_advance(d_b, k * 2048), idesc_q, (j | k) != 0);
       if (leader) umma_commit(&kv_empty[s]);
-      if (leader) umma_commit(ds_empty);
+      DQ_STAMP(0, j, 2);
     }
     if (leader) umma_commit(o_full);
   } else if (warp >= 2) {
@@ -346,13 +354,14 @@ attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_cons
     }
     const float c1 = att_scale_of(HDV) * LOG2E, c2 = L * LOG2E;
     for (int j = 0; j < nkb; ++j) {
-      const int b = j % SB;
-      mbar_wait(&s_full[b], (j / SB) & 1);
+      const int b = j & 1;
+      if (warp == 2) DQ_STAMP(1, j, 0);
+      mbar_wait(&s_full[b], (j >> 1) & 1);
       tc_fence_after();
-      uint32_t pk[32];
+      if (warp == 2) DQ_STAMP(1, j, 1);
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
-        uint32_t sv[32], dp[32];
+        uint32_t sv[32], dp[32], pk[16];
         tmem_ld32(t_lane + b * 128 + half * 32, sv);
         tmem_ld32(t_lane + b * 128 + 64 + half * 32, dp);
         tmem_ld_wait();
@@ -360,17 +369,16 @@ attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_cons
         for (int i = 0; i < 16; ++i) {
           float p0 = ex2(fmaf(__uint_as_float(sv[2 * i]), c1, -c2)), p1 = ex2(fmaf(__uint_as_float(sv[2 * i + 1]), c1, -c2));
           float d0 = p0 * (__uint_as_float(dp[2 * i]) - dl), d1 = p1 * (__uint_as_float(dp[2 * i + 1]) - dl);
-          pk[half * 16 + i] = pack_bf16(d0, d1);
+          pk[i] = pack_bf16(d0, d1);
         }
+        tmem_st16(t_lane + b * 128 + half * 32, pk);  // over S columns this thread has read
       }
+      if (warp == 2) DQ_STAMP(1, j, 2);
+      tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[b]);
-      mbar_wait(ds_empty, (j & 1) ^ 1);
-      store_row_sw128(sdS, r, pk);
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(ds_full);
+      if (lane == 0) mbar_arrive(&ds_full[b]);
+      if (warp == 2) DQ_STAMP(1, j, 3);
     }
     mbar_wait(o_full, 0);
     tc_fence_after();
@@ -392,40 +400,37 @@ attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_cons
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<B::DQ_TMEM>(tmem_base);
+  if (warp == 1) tmem_dealloc<B::TMEM>(tmem_base);
+#undef DQ_STAMP
 }
 
 // ------------------------------------------------------------------------------------------------ dK, dV
+// Rows (TMEM lanes) are keys.  P^T and dS^T go back into TMEM in place, over the S^T and dP^T columns they were computed from, and are
+// the A operands of dV += P^T dO_j and dK += dS^T Q_j (see attn_bwd_dq_tc).
 template <int HDV>
-__global__ void __launch_bounds__(NTHREADS, BCfg<HDV>::CTAS)
+__global__ void __launch_bounds__(BCfg<HDV>::NTHR, 1)
 attn_bwd_dkv_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_constant__ CUtensorMap tm_qkv_blk,
                 const __grid_constant__ CUtensorMap tm_do_blk, const float* __restrict__ lse, const float* __restrict__ delta,
                 bf16* __restrict__ dqkv, int tokens, int heads, const bf16* __restrict__ qkv, const float* __restrict__ sc, float eps) {
   using B = BCfg<HDV>;
-  constexpr int ROWB = B::ROWB, BLKB = B::BLKB, PROW = B::PROW, PBLK = B::PBLK;
-  constexpr int SB = B::SB;
-  constexpr uint32_t T_DK = SB * 128, T_DV = SB * 128 + B::NACC;  // accumulators behind the SB x (S^T [0, 64) | dP^T [64, 128)) buffers
+  constexpr int ROWB = B::ROWB, BLKB = B::BLKB, PROW = B::PROW, PBLK = B::PBLK, NST = B::NST, NSW = B::NSW;
+  constexpr uint32_t T_DK = B::T_ACC, T_DV = B::T_ACC + B::NACC;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   uint8_t* sK = smem;
   uint8_t* sV = sK + ROWB;
-  uint8_t* sQdO = sV + ROWB;             // stage s: Q_j at sQdO + s*2*BLKB, dO_j after it
-  constexpr int NST = B::DKV_ST;
-  uint8_t* sPt = sQdO + NST * 2 * BLKB;  // [128 keys x 64 queries] bf16 K-major
-  uint8_t* sdSt = sPt + ROW_BYTES;
-  float* sL = reinterpret_cast<float*>(sdSt + ROW_BYTES);  // [2][64]
-  float* sD = sL + 2 * CB;                                  // [2][64]
+  uint8_t* sQdO = sV + ROWB;  // stage s: Q_j at sQdO + s*2*BLKB, dO_j after it
+  float* sL = reinterpret_cast<float*>(sQdO + NST * 2 * BLKB);  // [2][64]
+  float* sD = sL + 2 * CB;                                       // [2][64]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sD + 2 * CB);
   uint64_t* bar_kv = bars;
-  uint64_t* qd_full = bars + 1;   // [NST <= 4]
-  uint64_t* qd_empty = bars + 5;  // [NST <= 4]
-  uint64_t* s_full = bars + 9;    // [SB]
-  uint64_t* s_empty = bars + 11;  // [SB]
-  uint64_t* p_full = bars + 13;
-  uint64_t* p_empty = bars + 14;
-  uint64_t* o_full = bars + 15;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* qd_full = bars + 1;   // [NST]
+  uint64_t* qd_empty = bars + 5;  // [NST]
+  uint64_t* s_full = bars + 9;    // [2]
+  uint64_t* p_full = bars + 11;   // [2]
+  uint64_t* o_full = bars + 13;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kt = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
@@ -442,14 +447,12 @@ attn_bwd_dkv_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_con
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], 4);
+      mbar_init(&p_full[i], NSW);
     }
-    mbar_init(p_full, 4);
-    mbar_init(p_empty, 1);
     mbar_init(o_full, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<B::DKV_TMEM>(tmem_slot);
+  if (warp == 1) tmem_alloc<B::TMEM>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -470,45 +473,45 @@ attn_bwd_dkv_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_con
   } else if (warp == 1) {
     const bool leader = elect_one();  // whole warp runs the loop, one lane issues (see tc_common.cuh)
     constexpr uint32_t idesc_s = make_idesc_bf16(RT, CB, 0, 0);       // S^T = K Q_j^T, dP^T = V dO_j^T
-    constexpr uint32_t idesc_a = make_idesc_bf16(RT, B::NACC, 0, 1);  // dV += P^T dO_j, dK += dS^T Q_j : B MN-major
-    const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), pt_addr = smem_u32(sPt), dst_addr = smem_u32(sdSt);
+    constexpr uint32_t idesc_a = make_idesc_bf16(RT, B::NACC, 0, 1);  // dV += P^T dO_j, dK += dS^T Q_j : A from TMEM, B MN-major
+    const uint64_t d_k = make_smem_desc(smem_u32(sK), 16, 1024), d_v = make_smem_desc(smem_u32(sV), 16, 1024);
+    const uint64_t d_qd = make_smem_desc(smem_u32(sQdO), 16, 1024);      // K-major view of a Q / dO block (S^T, dP^T)
+    const uint64_t d_qdmn = make_smem_desc(smem_u32(sQdO), PBLK, 1024);  // MN-major view (dK, dV): LBO = panel stride
     auto scores = [&](int j) {
-      const int s = j % NST, b = j % SB;
+      const int s = j % NST, b = j & 1;
       mbar_wait(&qd_full[s], (j / NST) & 1);
-      mbar_wait(&s_empty[b], ((j / SB) & 1) ^ 1);
       tc_fence_after();
-      const uint32_t q_addr = smem_u32(sQdO + s * 2 * BLKB), do_addr = q_addr + BLKB;
+      const uint64_t d_q = desc_advance(d_qd, s * 2 * BLKB), d_do = desc_advance(d_q, BLKB);
       const uint32_t t_s = tmem_base + b * 128;
 #pragma unroll
       for (int k = 0; k < B::KST; ++k) {  // S^T and dP^T chains interleaved (independent accumulators)
         const uint32_t ro = (k >> 2) * PROW + (k & 3) * 32, bo = (k >> 2) * PBLK + (k & 3) * 32;
-        if (leader) umma_ss(t_s, make_smem_desc(k_addr + ro, 16, 1024), make_smem_desc(q_addr + bo, 16, 1024), idesc_s, k != 0);
-        if (leader) umma_ss(t_s + 64, make_smem_desc(v_addr + ro, 16, 1024), make_smem_desc(do_addr + bo, 16, 1024), idesc_s, k != 0);
+        if (leader) umma_ss(t_s, desc_advance(d_k, ro), desc_advance(d_q, bo), idesc_s, k != 0);
+        if (leader) umma_ss(t_s + 64, desc_advance(d_v, ro), desc_advance(d_do, bo), idesc_s, k != 0);
       }
       if (leader) umma_commit(&s_full[b]);
     };
     mbar_wait(bar_kv, 0);
     scores(0);
     for (int j = 0; j < nqb; ++j) {
-      const int s = j % NST;
+      const int s = j % NST, b = j & 1;
       if (j + 1 < nqb) scores(j + 1);
-      mbar_wait(p_full, j & 1);
+      mbar_wait(&p_full[b], (j >> 1) & 1);
       tc_fence_after();
-      const uint32_t q_addr = smem_u32(sQdO + s * 2 * BLKB), do_addr = q_addr + BLKB;
+      const uint64_t d_q = desc_advance(d_qdmn, s * 2 * BLKB), d_do = desc_advance(d_q, BLKB);
+      const uint32_t t_p = tmem_base + b * 128;  // P^T over the S^T columns, dS^T over the dP^T columns
 #pragma unroll
       for (int k = 0; k < CB / 16; ++k) {  // dV and dK chains interleaved
-        if (leader) umma_ss(tmem_base + T_DV, make_smem_desc(pt_addr + k * 32, 16, 1024), make_smem_desc(do_addr + k * 2048, PBLK, 1024), idesc_a,
-                (j | k) != 0);
-        if (leader) umma_ss(tmem_base + T_DK, make_smem_desc(dst_addr + k * 32, 16, 1024), make_smem_desc(q_addr + k * 2048, PBLK, 1024), idesc_a,
-                (j | k) != 0);
+        const uint32_t ko = (k >> 1) * 32 + (k & 1) * 8;
+        if (leader) umma_ts(tmem_base + T_DV, t_p + ko, desc_advance(d_do, k * 2048), idesc_a, (j | k) != 0);
+        if (leader) umma_ts(tmem_base + T_DK, t_p + 64 + ko, desc_advance(d_q, k * 2048), idesc_a, (j | k) != 0);
       }
       if (leader) umma_commit(&qd_empty[s]);
-      if (leader) umma_commit(p_empty);
     }
     if (leader) umma_commit(o_full);
   } else if (warp >= 2) {
     const int qq = warp & 3;
-    const int r = qq * 32 + lane;  // key row of the tile
+    const int r = qq * 32 + lane;      // key row of the tile
     const int tid = threadIdx.x - 64;  // 0..127 among the softmax warps
     const uint32_t t_lane = tmem_base + ((uint32_t)(qq * 32) << 16);
     const float c1 = att_scale_of(HDV) * LOG2E;
@@ -526,13 +529,12 @@ attn_bwd_dkv_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_con
       else sD[s * CB + (tid - 64)] = ld_val;
       if (j + 1 < nqb) ld_val = fetch(j + 1);
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      const int b = j % SB;
-      mbar_wait(&s_full[b], (j / SB) & 1);
+      const int b = j & 1;
+      mbar_wait(&s_full[b], (j >> 1) & 1);
       tc_fence_after();
-      uint32_t pp[32], pd[32];
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
-        uint32_t sv[32], dp[32];
+        uint32_t sv[32], dp[32], pp[16], pd[16];
         tmem_ld32(t_lane + b * 128 + half * 32, sv);
         tmem_ld32(t_lane + b * 128 + 64 + half * 32, dp);
         tmem_ld_wait();
@@ -542,19 +544,16 @@ attn_bwd_dkv_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_con
           float p0 = ex2(fmaf(__uint_as_float(sv[2 * i]), c1, -sL[s * CB + c]));
           float p1 = ex2(fmaf(__uint_as_float(sv[2 * i + 1]), c1, -sL[s * CB + c + 1]));
           float d0 = p0 * (__uint_as_float(dp[2 * i]) - sD[s * CB + c]), d1 = p1 * (__uint_as_float(dp[2 * i + 1]) - sD[s * CB + c + 1]);
-          pp[half * 16 + i] = pack_bf16(p0, p1);
-          pd[half * 16 + i] = pack_bf16(d0, d1);
+          pp[i] = pack_bf16(p0, p1);
+          pd[i] = pack_bf16(d0, d1);
         }
+        tmem_st16(t_lane + b * 128 + half * 32, pp);
+        tmem_st16(t_lane + b * 128 + 64 + half * 32, pd);
       }
+      tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[b]);
-      mbar_wait(p_empty, (j & 1) ^ 1);
-      store_row_sw128(sPt, r, pp);
-      store_row_sw128(sdSt, r, pd);
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(p_full);
+      if (lane == 0) mbar_arrive(&p_full[b]);
     }
     mbar_wait(o_full, 0);
     tc_fence_after();
@@ -583,7 +582,7 @@ attn_bwd_dkv_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_con
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<B::DKV_TMEM>(tmem_base);
+  if (warp == 1) tmem_dealloc<B::TMEM>(tmem_base);
 }
 
 // ------------------------------------------------------------------------------------------------ fused dQ, dK, dV (tokens == 256)
@@ -1606,10 +1605,10 @@ static int attn_bwd_pair72(const void* qkv, const void* o, const void* dout, con
   }
   cudaStream_t s = (cudaStream_t)stream;
   dim3 grid((tokens + RT - 1) / RT, heads, n_samples);
-  attn_bwd_dq_tc<72><<<grid, NTHREADS, BCfg<72>::DQ_SMEM, s>>>(t_qkv_row, t_qkv_blk, t_do_row, (const bf16*)o, (const bf16*)dout, lse, delta,
-                                                             (bf16*)dqkv, tokens, heads, (const bf16*)qkv, sc, eps);
+  attn_bwd_dq_tc<72><<<grid, BCfg<72>::NTHR, BCfg<72>::DQ_SMEM, s>>>(t_qkv_row, t_qkv_blk, t_do_row, (const bf16*)o, (const bf16*)dout, lse, delta,
+                                                             (bf16*)dqkv, tokens, heads, (const bf16*)qkv, sc, eps, g_attn_dbg);
   MAPDIT_LAUNCH_CHECK("cos_attn_bwd(dq, hd 72)");
-  attn_bwd_dkv_tc<72><<<grid, NTHREADS, BCfg<72>::DKV_SMEM, s>>>(t_qkv_row, t_qkv_blk, t_do_blk, lse, delta, (bf16*)dqkv, tokens, heads,
+  attn_bwd_dkv_tc<72><<<grid, BCfg<72>::NTHR, BCfg<72>::DKV_SMEM, s>>>(t_qkv_row, t_qkv_blk, t_do_blk, lse, delta, (bf16*)dqkv, tokens, heads,
                                                                (const bf16*)qkv, sc, eps);
   MAPDIT_LAUNCH_CHECK("cos_attn_bwd(dkv, hd 72)");
   return MAPDIT_OK;
@@ -1696,10 +1695,10 @@ static int attn_bwd_impl(const void* qkv, const void* o, const void* dout, const
     return MAPDIT_OK;
   }
   dim3 grid((tokens + RT - 1) / RT, heads, n_samples);
-  attn_bwd_dq_tc<64><<<grid, NTHREADS, BCfg<64>::DQ_SMEM, s>>>(t_qkv_row, t_qkv_blk, t_do_row, (const bf16*)o, (const bf16*)dout, lse, delta,
-                                                 (bf16*)dqkv, tokens, heads, (const bf16*)qkv, sc, eps);
+  attn_bwd_dq_tc<64><<<grid, BCfg<64>::NTHR, BCfg<64>::DQ_SMEM, s>>>(t_qkv_row, t_qkv_blk, t_do_row, (const bf16*)o, (const bf16*)dout, lse, delta,
+                                                 (bf16*)dqkv, tokens, heads, (const bf16*)qkv, sc, eps, g_attn_dbg);
   MAPDIT_LAUNCH_CHECK("cos_attn_bwd(dq)");
-  attn_bwd_dkv_tc<64><<<grid, NTHREADS, BCfg<64>::DKV_SMEM, s>>>(t_qkv_row, t_qkv_blk, t_do_blk, lse, delta, (bf16*)dqkv, tokens, heads,
+  attn_bwd_dkv_tc<64><<<grid, BCfg<64>::NTHR, BCfg<64>::DKV_SMEM, s>>>(t_qkv_row, t_qkv_blk, t_do_blk, lse, delta, (bf16*)dqkv, tokens, heads,
                                                    (const bf16*)qkv, sc, eps);
   MAPDIT_LAUNCH_CHECK("cos_attn_bwd(dkv)");
   return MAPDIT_OK;
