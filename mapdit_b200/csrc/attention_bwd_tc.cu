@@ -127,15 +127,20 @@ struct BCfg {
   static constexpr int ROWB = PROW * PANELS, BLKB = PBLK * PANELS;
   // One CTA per SM.  Ring of column-block stages (K_j | V_j, or Q_j | dO_j): with two stages a block's tiles were requested only one
   // block ahead and ncu showed 37 % of the samples in the softmax warps' wait for S
-  static constexpr int NST = 4;
-  // softmax warps: one per TMEM lane quarter, each thread a whole 64-column row of the logit block
-  static constexpr int NSW = 4;
+  // (the dq kernel holds K_j until dQ(j), which is issued behind S / dP of block j+2: three live blocks + two requested ahead)
+  static constexpr int DQ_NST = 5, DKV_NST = 4;
+  // softmax warps: two per TMEM lane quarter (= per SM sub-partition, so that one hides the tcgen05.ld / MUFU latency of the other), each
+  // thread 32 of the 64 columns of its row of the logit block
+  static constexpr int NSW = 8;
   static constexpr int NTHR = 64 + NSW * 32;
-  static constexpr int DQ_SMEM = 2 * ROWB + NST * 2 * BLKB + 1024 + 256;
-  static constexpr int DKV_SMEM = 2 * ROWB + NST * 2 * BLKB + 2 * 2 * CB * 4 + 1024 + 256;
+  static constexpr int DQ_SMEM = 2 * ROWB + DQ_NST * 2 * BLKB + 1024 + 256;
+  static constexpr int DKV_SMEM = 2 * ROWB + DKV_NST * 2 * BLKB + 2 * 2 * CB * 4 + 1024 + 256;
   // TMEM: two (S [0, 64) | dP [64, 128)) buffers, then the accumulators (dQ, or dK and dV).  scores(j+1) runs on the tensor core while
   // the softmax warps still work on block j.
   static constexpr uint32_t T_ACC = 256;
+  // behind the accumulators: the CTA's two resident [128 x head_dim] tiles (Q and dO, or K and V) as TMEM A operands, KST x 8 columns
+  // of packed bf16 pairs each (see tile_to_tmem)
+  static constexpr uint32_t A_COLS = KST * 8;
   static constexpr uint32_t TMEM = 512;
 };
 __host__ __device__ constexpr float att_scale_of(int hdv) { return hdv == 64 ? 0.125f : 0.11785113019775793f; }  // 1/sqrt(hd)
@@ -210,28 +215,54 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
                : "memory");
 }
 
+// Row r of a resident [128 x head_dim] tile (TMA-written SWIZZLE_128B panels) -> TMEM lane r, columns [0, KST*8): packed bf16 pairs in
+// channel order, which is the A-operand layout of tcgen05.mma (k-step kk = columns kk*8 .. kk*8+7).  The tile is the A operand of every
+// S / dP MMA of the CTA: read from TMEM it costs no shared-memory bandwidth, which is what bounds these kernels (an MMA over a
+// [128 x 64] logit block is 32 tensor-core cycles but fetched 4 KB of A and 2 KB of B).  Channels 72..79 are the TMA unit's zero fill.
+template <int HDV>
+__device__ __forceinline__ void tile_to_tmem(uint32_t taddr, const uint8_t* tile, int r) {
+  using B = BCfg<HDV>;
+#pragma unroll
+  for (int kk = 0; kk < B::KST; ++kk) {
+    const uint8_t* prow = tile + (kk >> 2) * B::PROW + (r >> 3) * 1024 + (r & 7) * 128;
+    const int c = (kk & 3) * 2;
+    const uint4 u0 = *reinterpret_cast<const uint4*>(prow + ((c ^ (r & 7)) << 4));
+    const uint4 u1 = *reinterpret_cast<const uint4*>(prow + (((c + 1) ^ (r & 7)) << 4));
+    const uint32_t w[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+    tmem_st8(taddr + kk * 8, w);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ dQ
-// dS never touches shared memory: the softmax thread that owns a query row reads its S and dP values from TMEM, and writes the 64 bf16
-// dS values back IN PLACE over the S columns it has just read (packed pairs, 16 columns per 32 keys at column 0 and 32 of the buffer);
-// the dQ += dS K_j MMAs take that tile as their A operand straight from TMEM.  With the [128 x 64] logit blocks of this kernel an MMA is
+// dS never touches shared memory: the softmax threads that own a query row read its S and dP values from TMEM and write the 64 bf16
+// dS values (packed pairs, 32 columns) into one of two small TMEM tiles; the dQ += dS K_j MMAs take that tile as their A operand
+// straight from TMEM.  With the [128 x 64] logit blocks of this kernel an MMA is
 // only 32-40 tensor-core cycles long but fetches 6 KB of operands, so shared-memory bandwidth (MMA operand reads + the staging tile's
 // stores and re-reads + TMA writes: 134 KB per block, 128 B/clk) was the bound of the first version, and every other shared-memory
-// access (mbarrier polls, fences) queued behind it (tools/attn_bwd_xl_timeline.py).  The tensor core executes one thread's MMAs in issue
-// order, which is all the protection the in-place tile needs: S(j+2) is issued after dQ(j) and cannot overtake it.
+// access (mbarrier polls, fences) queued behind it (tools/attn_bwd_xl_timeline.py, tools/probes/mma_rate_probe.cu: 48 cycles per
+// [128 x 64 x 16] MMA with both operands in shared memory, 32 with A in TMEM).
+// Issue order per block j, once the softmax warps have published dS(j) (which also says they are done reading S / dP(j)):
+// S / dP(j+2) into the buffer of block j FIRST, then dQ(j) -- the softmax warps wait for S(j+2) while nothing waits for dQ(j).  (One
+// commit behind both, so that seeing S(j+2) implies the dS tile may be overwritten, saves a barrier but shows S(j+2) 160 cycles later:
+// measured slower.)
 template <int HDV>
 __global__ void __launch_bounds__(BCfg<HDV>::NTHR, 1)
 attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_constant__ CUtensorMap tm_qkv_blk,
-               const __grid_constant__ CUtensorMap tm_do_row, const bf16* __restrict__ o, const bf16* __restrict__ dout,
-               const float* __restrict__ lse, float* __restrict__ delta, bf16* __restrict__ dqkv, int tokens, int heads,
+               const __grid_constant__ CUtensorMap tm_do_row, const float* __restrict__ lse, const float* __restrict__ delta,
+               bf16* __restrict__ dqkv, int tokens, int heads,
                const bf16* __restrict__ qkv, const float* __restrict__ sc, float eps, long long* __restrict__ dbg) {
   using B = BCfg<HDV>;
-  // optional timeline of CTA (0,0,0) (tools/attn_bwd_xl_timeline.py): dbg[role*256 + 4*j + e] = clock64 at event e of key block j
+  // optional timeline of one CTA of a middle wave (tools/attn_bwd_xl_timeline.py): dbg[role*256 + 4*j + e] = clock64 at event e of key
+  // block j; role 3: CTA-level events
 #define DQ_STAMP(role, j, e)                                                                                          \
   do {                                                                                                                \
-    if (dbg && (blockIdx.x | blockIdx.y | blockIdx.z) == 0 && (j) < 64 && lane == 0) dbg[(role) * 256 + 4 * (j) + (e)] = clock64(); \
+    if (dbg && (blockIdx.x | blockIdx.y) == 0 && blockIdx.z == gridDim.z / 2 && (j) < 64 && (threadIdx.x & 31) == 0) \
+      dbg[(role) * 256 + 4 * (j) + (e)] = clock64();                                                                \
   } while (0)
-  constexpr int ROWB = B::ROWB, BLKB = B::BLKB, PROW = B::PROW, PBLK = B::PBLK, NST = B::NST, NSW = B::NSW;
-  constexpr uint32_t T_DQ = B::T_ACC;
+  if (threadIdx.x == 0) DQ_STAMP(3, 0, 0);
+  constexpr int ROWB = B::ROWB, BLKB = B::BLKB, PROW = B::PROW, PBLK = B::PBLK, NST = B::DQ_NST, NSW = B::NSW;
+  constexpr uint32_t T_DQ = B::T_ACC, T_QA = T_DQ + B::NACC, T_DOA = T_QA + B::A_COLS, T_DS = T_DOA + B::A_COLS;  // dQ | Q, dO (A operands) | 2 x dS
+  static_assert(T_DS + 2 * 32 <= B::TMEM, "TMEM columns");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -240,12 +271,14 @@ attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_cons
   uint8_t* sKV = sdO + ROWB;  // stage s: K_j at sKV + s*2*BLKB, V_j after it
   uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + NST * 2 * BLKB);
   uint64_t* bar_q = bars;
-  uint64_t* kv_full = bars + 1;   // [NST]
-  uint64_t* kv_empty = bars + 5;  // [NST]
-  uint64_t* s_full = bars + 9;    // [2]  S / dP of a block are in TMEM
-  uint64_t* ds_full = bars + 11;  // [2]  dS of a block is in TMEM
-  uint64_t* o_full = bars + 13;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* kv_full = bars + 1;           // [NST]
+  uint64_t* kv_empty = kv_full + NST;     // [NST]
+  uint64_t* s_full = kv_empty + NST;      // [2]  S / dP of a block are in TMEM
+  uint64_t* ds_full = s_full + 2;         // [2]  dS of a block is in TMEM (and its S / dP have been read)
+  uint64_t* ds_empty = ds_full + 2;       // [2]  dQ(j) has read the dS tile
+  uint64_t* o_full = ds_empty + 2;
+  uint64_t* a_full = o_full + 1;          // Q and dO are in TMEM
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
@@ -263,8 +296,10 @@ attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_cons
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
       mbar_init(&ds_full[i], NSW);
+      mbar_init(&ds_empty[i], 1);
     }
     mbar_init(o_full, 1);
+    mbar_init(a_full, NSW);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<B::TMEM>(tmem_slot);
@@ -272,6 +307,7 @@ attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  if (threadIdx.x == 0) DQ_STAMP(3, 0, 1);
 
   if (warp == 0 && lane == 0) {
     mbar_arrive_expect_tx(bar_q, 2 * ROWB);
@@ -288,106 +324,114 @@ attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_cons
     }
   } else if (warp == 1) {
     const bool leader = elect_one();  // whole warp runs the loop, one lane issues (see tc_common.cuh)
-    constexpr uint32_t idesc_s = make_idesc_bf16(RT, CB, 0, 0);       // S / dP: both operands K-major
+    constexpr uint32_t idesc_s = make_idesc_bf16(RT, CB, 0, 0);       // S / dP: A (Q, dO) from TMEM, B K-major
     constexpr uint32_t idesc_q = make_idesc_bf16(RT, B::NACC, 0, 1);  // dQ += dS K_j: dS from TMEM, K_j MN-major (d contiguous)
     // descriptors of the resident tiles and of ring slot 0; every MMA operand is one of these moved by a compile-time or per-block offset
-    const uint64_t d_q = make_smem_desc(smem_u32(sQ), 16, 1024), d_do = make_smem_desc(smem_u32(sdO), 16, 1024);
     const uint64_t d_kv = make_smem_desc(smem_u32(sKV), 16, 1024);     // K-major view of a K / V block (S, dP)
     const uint64_t d_kmn = make_smem_desc(smem_u32(sKV), PBLK, 1024);  // MN-major view of a K block (dQ): LBO = panel stride
-    auto scores = [&](int j) {
+    auto scores = [&](int j) {  // kv_full of the block's ring slot has been waited for
       const int s = j % NST, b = j & 1;
-      mbar_wait(&kv_full[s], (j / NST) & 1);
-      tc_fence_after();
       const uint64_t d_k = desc_advance(d_kv, s * 2 * BLKB), d_v = desc_advance(d_k, BLKB);
       const uint32_t t_s = tmem_base + b * 128;
       // the S and dP chains accumulate into different TMEM tiles: issued alternately so consecutive MMAs are independent
 #pragma unroll
       for (int k = 0; k < B::KST; ++k) {
-        const uint32_t ro = (k >> 2) * PROW + (k & 3) * 32, bo = (k >> 2) * PBLK + (k & 3) * 32;  // panel + 16-channel step
-        if (leader) umma_ss(t_s, desc_advance(d_q, ro), desc_advance(d_k, bo), idesc_s, k != 0);
-        if (leader) umma_ss(t_s + 64, desc_advance(d_do, ro), desc_advance(d_v, bo), idesc_s, k != 0);
+        const uint32_t bo = (k >> 2) * PBLK + (k & 3) * 32;  // panel + 16-channel step
+        if (leader) umma_ts(t_s, tmem_base + T_QA + k * 8, desc_advance(d_k, bo), idesc_s, k != 0);
+        if (leader) umma_ts(t_s + 64, tmem_base + T_DOA + k * 8, desc_advance(d_v, bo), idesc_s, k != 0);
       }
       if (leader) umma_commit(&s_full[b]);
     };
-    mbar_wait(bar_q, 0);
+    mbar_wait(a_full, 0);
+    tc_fence_after();
+    mbar_wait(&kv_full[0], 0);
     scores(0);
+    if (nkb > 1) {
+      mbar_wait(&kv_full[1 % NST], (1 / NST) & 1);
+      scores(1);
+    }
     for (int j = 0; j < nkb; ++j) {
       const int s = j % NST, b = j & 1;
-      if (j + 1 < nkb) scores(j + 1);  // into the other buffer: its dS tile was read by dQ(j-1), issued before this
+      // the ring wait of block j+2 in the shadow of the softmax warps' work on block j, not behind it (every mbarrier wait of this warp,
+      // even on a completed phase, is 100+ cycles)
+      if (j + 2 < nkb) mbar_wait(&kv_full[(j + 2) % NST], ((j + 2) / NST) & 1);
       DQ_STAMP(0, j, 0);
-      mbar_wait(&ds_full[b], (j >> 1) & 1);
+      mbar_wait_spin(&ds_full[b], (j >> 1) & 1);
       tc_fence_after();
       DQ_STAMP(0, j, 1);
+      if (j + 2 < nkb) scores(j + 2);
       const uint64_t d_b = desc_advance(d_kmn, s * 2 * BLKB);
-      const uint32_t t_ds = tmem_base + b * 128;
 #pragma unroll
-      for (int k = 0; k < CB / 16; ++k)  // 16 keys = 8 packed columns; keys 32.. start at column 32
-        if (leader) umma_ts(tmem_base + T_DQ, t_ds + (k >> 1) * 32 + (k & 1) * 8, desc_advance(d_b, k * 2048), idesc_q, (j | k) != 0);
+      for (int k = 0; k < CB / 16; ++k)  // 16 keys = 8 packed columns
+        if (leader) umma_ts(tmem_base + T_DQ, tmem_base + T_DS + b * 32 + k * 8, desc_advance(d_b, k * 2048), idesc_q, (j | k) != 0);
       if (leader) umma_commit(&kv_empty[s]);
+      if (leader) umma_commit(&ds_empty[b]);
       DQ_STAMP(0, j, 2);
     }
     if (leader) umma_commit(o_full);
   } else if (warp >= 2) {
     const int qq = warp & 3;
+    const int h0 = (warp - 2) >> 2;  // which 32 of the 64 columns of a logit block this warp owns
     const int r = qq * 32 + lane;
     const uint32_t t_lane = tmem_base + ((uint32_t)(qq * 32) << 16);
     const bool row_ok = q0 + r < tokens;
     const size_t grow = (size_t)row_base + q0 + r;
-    // delta_i = dO_i . O_i (the head's rows straight from global) and L_i
+    // delta_i = dO_i . O_i (attn_delta_kernel) and L_i
     float dl = 0.f, L = 0.f;
     if (row_ok) {
-      const uint4* po = reinterpret_cast<const uint4*>(o + grow * D + h * HDV);
-      const uint4* pg = reinterpret_cast<const uint4*>(dout + grow * D + h * HDV);
-#pragma unroll
-      for (int c = 0; c < HDV / 8; ++c) {
-        uint4 a = po[c], b = pg[c];
-        const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&a);
-        const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&b);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          float2 x = __bfloat1622float2(ha[e]), y = __bfloat1622float2(hb[e]);
-          dl = fmaf(x.x, y.x, fmaf(x.y, y.y, dl));
-        }
-      }
       L = lse[grow * heads + h];
-      delta[grow * heads + h] = dl;
+      dl = delta[grow * heads + h];
     }
     const float c1 = att_scale_of(HDV) * LOG2E, c2 = L * LOG2E;
+    // the row of Q (first four warps) or of dO (the other four): TMA tile -> TMEM A operand
+    if (warp == 2) DQ_STAMP(3, 0, 2);
+    mbar_wait(bar_q, 0);
+    if (warp == 2) DQ_STAMP(3, 0, 3);
+    if (h0 == 0) tile_to_tmem<HDV>(t_lane + T_QA, sQ, r);
+    else tile_to_tmem<HDV>(t_lane + T_DOA, sdO, r);
+    tmem_st_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(a_full);
+    if (warp == 2) DQ_STAMP(3, 1, 0);
     for (int j = 0; j < nkb; ++j) {
       const int b = j & 1;
       if (warp == 2) DQ_STAMP(1, j, 0);
       mbar_wait(&s_full[b], (j >> 1) & 1);
       tc_fence_after();
       if (warp == 2) DQ_STAMP(1, j, 1);
+      uint32_t sv[32], dp[32], pk[16];
+      tmem_ld32(t_lane + b * 128 + h0 * 32, sv);
+      tmem_ld32(t_lane + b * 128 + 64 + h0 * 32, dp);
+      tmem_ld_wait();
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        uint32_t sv[32], dp[32], pk[16];
-        tmem_ld32(t_lane + b * 128 + half * 32, sv);
-        tmem_ld32(t_lane + b * 128 + 64 + half * 32, dp);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float p0 = ex2(fmaf(__uint_as_float(sv[2 * i]), c1, -c2)), p1 = ex2(fmaf(__uint_as_float(sv[2 * i + 1]), c1, -c2));
-          float d0 = p0 * (__uint_as_float(dp[2 * i]) - dl), d1 = p1 * (__uint_as_float(dp[2 * i + 1]) - dl);
-          pk[i] = pack_bf16(d0, d1);
-        }
-        tmem_st16(t_lane + b * 128 + half * 32, pk);  // over S columns this thread has read
+      for (int i = 0; i < 16; ++i) {
+        float p0 = ex2(fmaf(__uint_as_float(sv[2 * i]), c1, -c2)), p1 = ex2(fmaf(__uint_as_float(sv[2 * i + 1]), c1, -c2));
+        float d0 = p0 * (__uint_as_float(dp[2 * i]) - dl), d1 = p1 * (__uint_as_float(dp[2 * i + 1]) - dl);
+        pk[i] = pack_bf16(d0, d1);
       }
       if (warp == 2) DQ_STAMP(1, j, 2);
+      mbar_wait(&ds_empty[b], ((j >> 1) & 1) ^ 1);  // dQ(j-2) has read the tile (long ago)
+      tc_fence_after();
+      tmem_st16(t_lane + T_DS + b * 32 + h0 * 16, pk);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&ds_full[b]);
       if (warp == 2) DQ_STAMP(1, j, 3);
     }
-    mbar_wait(o_full, 0);
-    tc_fence_after();
+    // epilogue by the first four warps: a whole gradient row per thread (the q-norm backward needs its dot product with q^)
     uint32_t a0[32], a1[32], tl[8];
-    tmem_ld32(t_lane + T_DQ, a0);
-    tmem_ld32(t_lane + T_DQ + 32, a1);
-    if constexpr (HDV != 64) tmem_ld8(t_lane + T_DQ + 64, tl);
-    tmem_ld_wait();
-    if (row_ok) {
+    if (h0 == 0) {
+      mbar_wait(o_full, 0);
+      tc_fence_after();
+      if (warp == 2) DQ_STAMP(3, 1, 1);
+      tmem_ld32(t_lane + T_DQ, a0);
+      tmem_ld32(t_lane + T_DQ + 32, a1);
+      if constexpr (HDV != 64) tmem_ld8(t_lane + T_DQ + 64, tl);
+      tmem_ld_wait();
+    }
+    if (row_ok && h0 == 0) {
       bf16* dst = dqkv + grow * 3 * D + h * HDV;
       if constexpr (HDV == 64) {
         if (sc) store_out_row_qknorm(dst, qkv + grow * 3 * D + h * HDV, a0, a1, 0.125f, sc[grow * 2 * heads + h], eps);
@@ -398,9 +442,11 @@ attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_cons
       }
     }
   }
+  if (warp == 2) DQ_STAMP(3, 1, 2);
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<B::TMEM>(tmem_base);
+  if (threadIdx.x == 32) DQ_STAMP(3, 1, 3);
 #undef DQ_STAMP
 }
 
@@ -411,10 +457,18 @@ template <int HDV>
 __global__ void __launch_bounds__(BCfg<HDV>::NTHR, 1)
 attn_bwd_dkv_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_constant__ CUtensorMap tm_qkv_blk,
                 const __grid_constant__ CUtensorMap tm_do_blk, const float* __restrict__ lse, const float* __restrict__ delta,
-                bf16* __restrict__ dqkv, int tokens, int heads, const bf16* __restrict__ qkv, const float* __restrict__ sc, float eps) {
+                bf16* __restrict__ dqkv, int tokens, int heads, const bf16* __restrict__ qkv, const float* __restrict__ sc, float eps, long long* __restrict__ dbg) {
   using B = BCfg<HDV>;
-  constexpr int ROWB = B::ROWB, BLKB = B::BLKB, PROW = B::PROW, PBLK = B::PBLK, NST = B::NST, NSW = B::NSW;
-  constexpr uint32_t T_DK = B::T_ACC, T_DV = B::T_ACC + B::NACC;
+  // optional timeline of one CTA of a middle wave, roles 4..7 of the buffer (see attn_bwd_dq_tc)
+#define DKV_STAMP(role, j, e)                                                                                         \
+  do {                                                                                                                \
+    if (dbg && (blockIdx.x | blockIdx.y) == 0 && blockIdx.z == gridDim.z / 2 && (j) < 64 && (threadIdx.x & 31) == 0) \
+      dbg[(4 + (role)) * 256 + 4 * (j) + (e)] = clock64();                                                          \
+  } while (0)
+  if (threadIdx.x == 0) DKV_STAMP(3, 0, 0);
+  constexpr int ROWB = B::ROWB, BLKB = B::BLKB, PROW = B::PROW, PBLK = B::PBLK, NST = B::DKV_NST, NSW = B::NSW;
+  constexpr uint32_t T_DK = B::T_ACC, T_DV = T_DK + B::NACC, T_KA = T_DV + B::NACC, T_VA = T_KA + B::A_COLS;  // dK | dV | K, V as A operands
+  static_assert(T_VA + B::A_COLS <= B::TMEM, "TMEM columns");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -425,12 +479,13 @@ attn_bwd_dkv_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_con
   float* sD = sL + 2 * CB;                                       // [2][64]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sD + 2 * CB);
   uint64_t* bar_kv = bars;
-  uint64_t* qd_full = bars + 1;   // [NST]
-  uint64_t* qd_empty = bars + 5;  // [NST]
-  uint64_t* s_full = bars + 9;    // [2]
-  uint64_t* p_full = bars + 11;   // [2]
-  uint64_t* o_full = bars + 13;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* qd_full = bars + 1;          // [NST]
+  uint64_t* qd_empty = qd_full + NST;    // [NST]
+  uint64_t* s_full = qd_empty + NST;     // [2]
+  uint64_t* p_full = s_full + 2;         // [2]
+  uint64_t* o_full = p_full + 2;
+  uint64_t* a_full = o_full + 1;         // K and V are in TMEM
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kt = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
@@ -450,6 +505,7 @@ attn_bwd_dkv_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_con
       mbar_init(&p_full[i], NSW);
     }
     mbar_init(o_full, 1);
+    mbar_init(a_full, NSW);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<B::TMEM>(tmem_slot);
@@ -457,6 +513,7 @@ attn_bwd_dkv_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  if (threadIdx.x == 0) DKV_STAMP(3, 0, 1);
 
   if (warp == 0 && lane == 0) {
     mbar_arrive_expect_tx(bar_kv, 2 * ROWB);
@@ -465,6 +522,7 @@ attn_bwd_dkv_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_con
     for (int j = 0; j < nqb; ++j) {
       const int s = j % NST;
       mbar_wait(&qd_empty[s], ((j / NST) & 1) ^ 1);
+      DKV_STAMP(2, j, 0);
       uint8_t* dst = sQdO + s * 2 * BLKB;
       mbar_arrive_expect_tx(&qd_full[s], 2 * BLKB);
       load_tile<HDV>(dst, &tm_qkv_blk, &qd_full[s], 0, h, heads, row_base + j * CB, PBLK);
@@ -474,30 +532,35 @@ attn_bwd_dkv_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_con
     const bool leader = elect_one();  // whole warp runs the loop, one lane issues (see tc_common.cuh)
     constexpr uint32_t idesc_s = make_idesc_bf16(RT, CB, 0, 0);       // S^T = K Q_j^T, dP^T = V dO_j^T
     constexpr uint32_t idesc_a = make_idesc_bf16(RT, B::NACC, 0, 1);  // dV += P^T dO_j, dK += dS^T Q_j : A from TMEM, B MN-major
-    const uint64_t d_k = make_smem_desc(smem_u32(sK), 16, 1024), d_v = make_smem_desc(smem_u32(sV), 16, 1024);
     const uint64_t d_qd = make_smem_desc(smem_u32(sQdO), 16, 1024);      // K-major view of a Q / dO block (S^T, dP^T)
     const uint64_t d_qdmn = make_smem_desc(smem_u32(sQdO), PBLK, 1024);  // MN-major view (dK, dV): LBO = panel stride
-    auto scores = [&](int j) {
+    auto scores = [&](int j) {  // qd_full of the block's ring slot has been waited for
       const int s = j % NST, b = j & 1;
-      mbar_wait(&qd_full[s], (j / NST) & 1);
-      tc_fence_after();
       const uint64_t d_q = desc_advance(d_qd, s * 2 * BLKB), d_do = desc_advance(d_q, BLKB);
       const uint32_t t_s = tmem_base + b * 128;
 #pragma unroll
       for (int k = 0; k < B::KST; ++k) {  // S^T and dP^T chains interleaved (independent accumulators)
-        const uint32_t ro = (k >> 2) * PROW + (k & 3) * 32, bo = (k >> 2) * PBLK + (k & 3) * 32;
-        if (leader) umma_ss(t_s, desc_advance(d_k, ro), desc_advance(d_q, bo), idesc_s, k != 0);
-        if (leader) umma_ss(t_s + 64, desc_advance(d_v, ro), desc_advance(d_do, bo), idesc_s, k != 0);
+        const uint32_t bo = (k >> 2) * PBLK + (k & 3) * 32;
+        if (leader) umma_ts(t_s, tmem_base + T_KA + k * 8, desc_advance(d_q, bo), idesc_s, k != 0);
+        if (leader) umma_ts(t_s + 64, tmem_base + T_VA + k * 8, desc_advance(d_do, bo), idesc_s, k != 0);
       }
       if (leader) umma_commit(&s_full[b]);
     };
-    mbar_wait(bar_kv, 0);
+    mbar_wait(a_full, 0);
+    tc_fence_after();
+    mbar_wait(&qd_full[0], 0);
     scores(0);
+    if (nqb > 1) mbar_wait(&qd_full[1 % NST], (1 / NST) & 1);
     for (int j = 0; j < nqb; ++j) {
       const int s = j % NST, b = j & 1;
+      DKV_STAMP(0, j, 3);
       if (j + 1 < nqb) scores(j + 1);
-      mbar_wait(&p_full[b], (j >> 1) & 1);
+      // the ring wait of block j+2 in the shadow of the softmax warps' work on block j (see attn_bwd_dq_tc)
+      if (j + 2 < nqb) mbar_wait(&qd_full[(j + 2) % NST], ((j + 2) / NST) & 1);
+      DKV_STAMP(0, j, 0);
+      mbar_wait_spin(&p_full[b], (j >> 1) & 1);
       tc_fence_after();
+      DKV_STAMP(0, j, 1);
       const uint64_t d_q = desc_advance(d_qdmn, s * 2 * BLKB), d_do = desc_advance(d_q, BLKB);
       const uint32_t t_p = tmem_base + b * 128;  // P^T over the S^T columns, dS^T over the dP^T columns
 #pragma unroll
@@ -507,64 +570,86 @@ attn_bwd_dkv_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_con
         if (leader) umma_ts(tmem_base + T_DK, t_p + 64 + ko, desc_advance(d_q, k * 2048), idesc_a, (j | k) != 0);
       }
       if (leader) umma_commit(&qd_empty[s]);
+      DKV_STAMP(0, j, 2);
     }
     if (leader) umma_commit(o_full);
   } else if (warp >= 2) {
     const int qq = warp & 3;
+    const int h0 = (warp - 2) >> 2;    // which 32 of the 64 query columns of a block this warp owns
     const int r = qq * 32 + lane;      // key row of the tile
-    const int tid = threadIdx.x - 64;  // 0..127 among the softmax warps
+    const int tid = threadIdx.x - 64;  // 0..255 among the softmax warps
     const uint32_t t_lane = tmem_base + ((uint32_t)(qq * 32) << 16);
     const float c1 = att_scale_of(HDV) * LOG2E;
     // per-query L (threads 0-63) and delta (64-127) of a block: 64 different lines of global memory each.  The values of block j+1
     // are requested while block j is processed (ncu: 11 % of this kernel's stall samples sat on these loads and the barrier behind them)
+    // (nothing may depend on the loaded value before the next block's store: the first version multiplied by log2 e right behind the load
+    // and the warp sat out the load latency, 1 100 cycles per block, on that multiply)
     auto fetch = [&](int j) {
       const size_t qrow = (size_t)row_base + j * CB + (tid & 63);
-      return tid < 64 ? lse[qrow * heads + h] * LOG2E : delta[qrow * heads + h];
+      return tid < 64 ? lse[qrow * heads + h] : delta[qrow * heads + h];
     };
-    float ld_val = fetch(0);
+    float ld_val = tid < 128 ? fetch(0) : 0.f;
+    // the row of K (first four warps) or of V (the other four): TMA tile -> TMEM A operand
+    if (warp == 2) DKV_STAMP(3, 0, 2);
+    mbar_wait(bar_kv, 0);
+    if (warp == 2) DKV_STAMP(3, 0, 3);
+    if (h0 == 0) tile_to_tmem<HDV>(t_lane + T_KA, sK, r);
+    else tile_to_tmem<HDV>(t_lane + T_VA, sV, r);
+    tmem_st_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(a_full);
+    if (warp == 2) DKV_STAMP(3, 1, 0);
     for (int j = 0; j < nqb; ++j) {
       const int s = j & 1;
-      // -> smem (double-buffered), visible to the 128 softmax threads
-      if (tid < 64) sL[s * CB + tid] = ld_val;
-      else sD[s * CB + (tid - 64)] = ld_val;
-      if (j + 1 < nqb) ld_val = fetch(j + 1);
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      // -> smem (double-buffered), visible to the softmax threads
+      if (tid < 64) sL[s * CB + tid] = ld_val * LOG2E;
+      else if (tid < 128) sD[s * CB + (tid - 64)] = ld_val;
+      if (j + 1 < nqb && tid < 128) ld_val = fetch(j + 1);
+      asm volatile("bar.sync 1, %0;" ::"n"(NSW * 32) : "memory");
       const int b = j & 1;
+      if (warp == 2) DKV_STAMP(1, j, 0);
       mbar_wait(&s_full[b], (j >> 1) & 1);
       tc_fence_after();
+      if (warp == 2) DKV_STAMP(1, j, 1);
+      uint32_t sv[32], dp[32], pp[16], pd[16];
+      tmem_ld32(t_lane + b * 128 + h0 * 32, sv);
+      tmem_ld32(t_lane + b * 128 + 64 + h0 * 32, dp);
+      tmem_ld_wait();
+      const float4* pL = reinterpret_cast<const float4*>(sL + s * CB + h0 * 32);
+      const float4* pD = reinterpret_cast<const float4*>(sD + s * CB + h0 * 32);
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        uint32_t sv[32], dp[32], pp[16], pd[16];
-        tmem_ld32(t_lane + b * 128 + half * 32, sv);
-        tmem_ld32(t_lane + b * 128 + 64 + half * 32, dp);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int c = half * 32 + 2 * i;
-          float p0 = ex2(fmaf(__uint_as_float(sv[2 * i]), c1, -sL[s * CB + c]));
-          float p1 = ex2(fmaf(__uint_as_float(sv[2 * i + 1]), c1, -sL[s * CB + c + 1]));
-          float d0 = p0 * (__uint_as_float(dp[2 * i]) - sD[s * CB + c]), d1 = p1 * (__uint_as_float(dp[2 * i + 1]) - sD[s * CB + c + 1]);
-          pp[i] = pack_bf16(p0, p1);
-          pd[i] = pack_bf16(d0, d1);
-        }
-        tmem_st16(t_lane + b * 128 + half * 32, pp);
-        tmem_st16(t_lane + b * 128 + 64 + half * 32, pd);
+      for (int i = 0; i < 8; ++i) {  // four query columns per trip: L and delta as one 16-byte broadcast read each
+        const float4 l4 = pL[i], d4 = pD[i];
+        float p0 = ex2(fmaf(__uint_as_float(sv[4 * i]), c1, -l4.x)), p1 = ex2(fmaf(__uint_as_float(sv[4 * i + 1]), c1, -l4.y));
+        float p2 = ex2(fmaf(__uint_as_float(sv[4 * i + 2]), c1, -l4.z)), p3 = ex2(fmaf(__uint_as_float(sv[4 * i + 3]), c1, -l4.w));
+        pp[2 * i] = pack_bf16(p0, p1);
+        pp[2 * i + 1] = pack_bf16(p2, p3);
+        pd[2 * i] = pack_bf16(p0 * (__uint_as_float(dp[4 * i]) - d4.x), p1 * (__uint_as_float(dp[4 * i + 1]) - d4.y));
+        pd[2 * i + 1] = pack_bf16(p2 * (__uint_as_float(dp[4 * i + 2]) - d4.z), p3 * (__uint_as_float(dp[4 * i + 3]) - d4.w));
       }
+      // in place, over columns only this thread reads: 32 queries = 16 packed columns at the start of the warp's 32-column group
+      if (warp == 2) DKV_STAMP(1, j, 2);
+      tmem_st16(t_lane + b * 128 + h0 * 32, pp);
+      tmem_st16(t_lane + b * 128 + 64 + h0 * 32, pd);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[b]);
+      if (warp == 2) DKV_STAMP(1, j, 3);
     }
     mbar_wait(o_full, 0);
     tc_fence_after();
+    if (warp == 2) DKV_STAMP(3, 1, 1);
     uint32_t a0[32], a1[32], tl[8];
     const bool row_ok = k0 + r < tokens;
     const size_t grow = (size_t)row_base + k0 + r;
-    tmem_ld32(t_lane + T_DK, a0);
-    tmem_ld32(t_lane + T_DK + 32, a1);
-    if constexpr (HDV != 64) tmem_ld8(t_lane + T_DK + 64, tl);
+    // the first four warps write dK, the other four dV
+    tmem_ld32(t_lane + (h0 == 0 ? T_DK : T_DV), a0);
+    tmem_ld32(t_lane + (h0 == 0 ? T_DK : T_DV) + 32, a1);
+    if constexpr (HDV != 64) tmem_ld8(t_lane + (h0 == 0 ? T_DK : T_DV) + 64, tl);
     tmem_ld_wait();
-    if (row_ok) {
+    if (row_ok && h0 == 0) {
       bf16* dst = dqkv + grow * 3 * D + D + h * HDV;
       if constexpr (HDV == 64) {
         if (sc) store_out_row_qknorm(dst, qkv + grow * 3 * D + D + h * HDV, a0, a1, 0.125f, sc[grow * 2 * heads + heads + h], eps);
@@ -574,15 +659,14 @@ attn_bwd_dkv_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_con
         else store_acc_row<HDV>(dst, a0, a1, tl, att_scale_of(HDV));
       }
     }
-    tmem_ld32(t_lane + T_DV, a0);
-    tmem_ld32(t_lane + T_DV + 32, a1);
-    if constexpr (HDV != 64) tmem_ld8(t_lane + T_DV + 64, tl);
-    tmem_ld_wait();
-    if (row_ok) store_acc_row<HDV>(dqkv + grow * 3 * D + 2 * D + h * HDV, a0, a1, tl, 1.0f);
+    if (row_ok && h0 == 1) store_acc_row<HDV>(dqkv + grow * 3 * D + 2 * D + h * HDV, a0, a1, tl, 1.0f);
   }
+  if (warp == 2) DKV_STAMP(3, 1, 2);
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<B::TMEM>(tmem_base);
+  if (threadIdx.x == 32) DKV_STAMP(3, 1, 3);
+#undef DKV_STAMP
 }
 
 // ------------------------------------------------------------------------------------------------ fused dQ, dK, dV (tokens == 256)
@@ -1529,23 +1613,26 @@ attn_bwd_fused2_tc(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
+template <int HDV>
 __global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ dout, float* __restrict__ delta,
-                                                         long long m_heads, int heads) {
-  // delta[row, head] = dO_row,head . O_row,head over 64 channels (128 contiguous bytes of each tensor).  Eight lanes share one
-  // (row, head): lane l reads the 16-byte chunk l % 8, so every load instruction of a warp covers 512 contiguous bytes
-  // (a thread-per-row layout touches 32 different lines per instruction and ran at 60 % of the HBM peak); a warp handles
-  // 32 (row, head) pairs per trip, all 16 loads issued before the first use.
-  const int lane = threadIdx.x & 31, sub = lane >> 3, ch = lane & 7;
+                                                         long long m_heads) {
+  // delta[row, head] = dO_row,head . O_row,head over HDV channels (128 or 144 contiguous bytes of each tensor; the [rows, heads * HDV]
+  // tensors are one contiguous run of (row, head) segments).  LPP lanes share one (row, head): lane l reads the 16-byte chunk l % LPP
+  // (nine of sixteen lanes at HDV 72), so a load instruction of a warp covers whole contiguous segments (a thread-per-row layout touches
+  // 32 different lines per instruction and ran at 60 % of the HBM peak; inside the dq kernel it cost 12 000 cycles per CTA); all 16 loads
+  // of a thread are issued before the first use.
+  constexpr int LPP = HDV == 64 ? 8 : 16, NCH = HDV / 8, PPI = 32 / LPP;  // lanes per pair, chunks per pair, pairs per load instruction
+  const int lane = threadIdx.x & 31, sub = lane / LPP, ch = lane % LPP;
   const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const long long base = warp_id * 32;
+  const long long base = warp_id * (8 * PPI);
   if (base >= m_heads) return;
   uint4 a[8], b[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    const long long i = base + k * 4 + sub;
-    const bool ok = i < m_heads;
-    a[k] = ok ? reinterpret_cast<const uint4*>(o + i * HD)[ch] : make_uint4(0, 0, 0, 0);
-    b[k] = ok ? reinterpret_cast<const uint4*>(dout + i * HD)[ch] : make_uint4(0, 0, 0, 0);
+    const long long i = base + k * PPI + sub;
+    const bool ok = i < m_heads && ch < NCH;
+    a[k] = ok ? reinterpret_cast<const uint4*>(o + i * HDV)[ch] : make_uint4(0, 0, 0, 0);
+    b[k] = ok ? reinterpret_cast<const uint4*>(dout + i * HDV)[ch] : make_uint4(0, 0, 0, 0);
   }
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
@@ -1557,12 +1644,16 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict_
       const float2 x = __bfloat1622float2(ha[e]), y = __bfloat1622float2(hb[e]);
       dl = fmaf(x.x, y.x, fmaf(x.y, y.y, dl));
     }
-    dl += __shfl_xor_sync(0xffffffffu, dl, 1);
-    dl += __shfl_xor_sync(0xffffffffu, dl, 2);
-    dl += __shfl_xor_sync(0xffffffffu, dl, 4);
-    const long long i = base + k * 4 + sub;
+#pragma unroll
+    for (int m = 1; m < LPP; m <<= 1) dl += __shfl_xor_sync(0xffffffffu, dl, m);
+    const long long i = base + k * PPI + sub;
     if (ch == 0 && i < m_heads) delta[i] = dl;
   }
+}
+template <int HDV>
+static void launch_delta(const void* o, const void* dout, float* delta, long long m_heads, cudaStream_t s) {
+  constexpr int PAIRS_PER_BLOCK = 8 * (HDV == 64 ? 4 : 2) * 8;  // 8 warps x 8 loads x pairs per load instruction
+  attn_delta_kernel<HDV><<<(unsigned)((m_heads + PAIRS_PER_BLOCK - 1) / PAIRS_PER_BLOCK), 256, 0, s>>>((const bf16*)o, (const bf16*)dout, delta, m_heads);
 }
 
 int encode2d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint64_t ld_elems, uint32_t box_rows) {
@@ -1605,11 +1696,13 @@ static int attn_bwd_pair72(const void* qkv, const void* o, const void* dout, con
   }
   cudaStream_t s = (cudaStream_t)stream;
   dim3 grid((tokens + RT - 1) / RT, heads, n_samples);
-  attn_bwd_dq_tc<72><<<grid, BCfg<72>::NTHR, BCfg<72>::DQ_SMEM, s>>>(t_qkv_row, t_qkv_blk, t_do_row, (const bf16*)o, (const bf16*)dout, lse, delta,
+  launch_delta<72>(o, dout, delta, (long long)rows * heads, s);
+  MAPDIT_LAUNCH_CHECK("cos_attn_bwd(delta, hd 72)");
+  attn_bwd_dq_tc<72><<<grid, BCfg<72>::NTHR, BCfg<72>::DQ_SMEM, s>>>(t_qkv_row, t_qkv_blk, t_do_row, lse, delta,
                                                              (bf16*)dqkv, tokens, heads, (const bf16*)qkv, sc, eps, g_attn_dbg);
   MAPDIT_LAUNCH_CHECK("cos_attn_bwd(dq, hd 72)");
   attn_bwd_dkv_tc<72><<<grid, BCfg<72>::NTHR, BCfg<72>::DKV_SMEM, s>>>(t_qkv_row, t_qkv_blk, t_do_blk, lse, delta, (bf16*)dqkv, tokens, heads,
-                                                               (const bf16*)qkv, sc, eps);
+                                                               (const bf16*)qkv, sc, eps, g_attn_dbg);
   MAPDIT_LAUNCH_CHECK("cos_attn_bwd(dkv, hd 72)");
   return MAPDIT_OK;
 }
@@ -1663,7 +1756,7 @@ static int attn_bwd_impl(const void* qkv, const void* o, const void* dout, const
     }
     if (o) {
       const long long mh = (long long)rows * heads;
-      attn_delta_kernel<<<(unsigned)((mh + 255) / 256), 256, 0, s>>>((const bf16*)o, (const bf16*)dout, delta, mh, heads);
+      launch_delta<64>(o, dout, delta, mh, s);
       MAPDIT_LAUNCH_CHECK("cos_attn_bwd(delta)");
     }
     const int items = n_samples * heads;
@@ -1695,11 +1788,13 @@ static int attn_bwd_impl(const void* qkv, const void* o, const void* dout, const
     return MAPDIT_OK;
   }
   dim3 grid((tokens + RT - 1) / RT, heads, n_samples);
-  attn_bwd_dq_tc<64><<<grid, BCfg<64>::NTHR, BCfg<64>::DQ_SMEM, s>>>(t_qkv_row, t_qkv_blk, t_do_row, (const bf16*)o, (const bf16*)dout, lse, delta,
+  launch_delta<64>(o, dout, delta, (long long)rows * heads, s);
+  MAPDIT_LAUNCH_CHECK("cos_attn_bwd(delta)");
+  attn_bwd_dq_tc<64><<<grid, BCfg<64>::NTHR, BCfg<64>::DQ_SMEM, s>>>(t_qkv_row, t_qkv_blk, t_do_row, lse, delta,
                                                  (bf16*)dqkv, tokens, heads, (const bf16*)qkv, sc, eps, g_attn_dbg);
   MAPDIT_LAUNCH_CHECK("cos_attn_bwd(dq)");
   attn_bwd_dkv_tc<64><<<grid, BCfg<64>::NTHR, BCfg<64>::DKV_SMEM, s>>>(t_qkv_row, t_qkv_blk, t_do_blk, lse, delta, (bf16*)dqkv, tokens, heads,
-                                                   (const bf16*)qkv, sc, eps);
+                                                   (const bf16*)qkv, sc, eps, g_attn_dbg);
   MAPDIT_LAUNCH_CHECK("cos_attn_bwd(dkv)");
   return MAPDIT_OK;
 }

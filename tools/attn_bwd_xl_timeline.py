@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Timeline of CTA (0,0,0) of attn_bwd_dq_tc<72> (DiT-XL/2 @ 64x64 shapes; clock64 stamps, developer tool): per key block j, when the MMA
+"""Timeline of one CTA (middle wave) of attn_bwd_dq_tc<72> (DiT-XL/2 @ 64x64 shapes; clock64 stamps, developer tool): per key block j, when the MMA
 warp had issued S/dP of j+1, saw dS of j and had issued the dQ MMAs; when softmax warp 2 started waiting for S, saw it, finished
 the exp pass and published dS; when the TMA producer saw the ring slot of block j free."""
 import ctypes as C
@@ -21,21 +21,26 @@ ops.cos_attn(qkv, o, B, T, H, HD, lse=lse)
 dqkv, delta = torch.empty_like(qkv), torch.empty(M, H, device="cuda")
 for _ in range(2):
     ops.cos_attn_bwd(qkv, o, do, lse, dqkv, delta, B, T, H, HD)
-dbg = torch.zeros(1024, dtype=torch.int64, device="cuda")
+dbg = torch.zeros(2048, dtype=torch.int64, device="cuda")
 L = _lib.lib()
 L.mapdit_attn_debug_buffer.argtypes = [C.c_void_p]
 L.mapdit_attn_debug_buffer(C.c_void_p(dbg.data_ptr()))
 ops.cos_attn_bwd(qkv, o, do, lse, dqkv, delta, B, T, H, HD)
 torch.cuda.synchronize()
 L.mapdit_attn_debug_buffer(None)
-d = dbg.cpu()[:768].view(3, 64, 4)
-t0 = int(d[d > 0].min())
-rel = lambda v: int(v) - t0 if int(v) else -1
-print("  j | MMA: S(j+1) issued, dS(j) seen, dQ(j) issued | softmax w2: wait S, S seen, exp done, dS published | TMA: slot free")
-for j in range(T // 64):
-    m, s, t = d[0, j], d[1, j], d[2, j]
-    print(f"{j:3d} | {rel(m[0]):7d} {rel(m[1]):7d} {rel(m[2]):7d} | {rel(s[0]):7d} {rel(s[1]):7d} {rel(s[2]):7d} {rel(s[3]):7d} | {rel(t[0]):7d}")
-fine = dbg.cpu()[768:768 + 256].view(16, 16)
-print("MMA warp inside scores(j): enter, K/V seen, S buffer free, after each k-step pair ..., committed")
-for j in range(16):
-    print(f"{j:3d} | " + " ".join(f"{rel(v):7d}" for v in fine[j][:9]))
+def show(d, name):
+    t0 = int(d[d > 0].min())
+    rel = lambda v: int(v) - t0 if int(v) else -1
+    print(f"---- {name}")
+    print("  j | MMA: loop top, ring slot j+2 seen, tile(j) seen, MMAs issued | softmax w2: wait S, S seen, exp done, published | TMA: slot free")
+    for j in range(T // 64):
+        m, s, t = d[0, j], d[1, j], d[2, j]
+        print(f"{j:3d} | {rel(m[3]):7d} {rel(m[0]):7d} {rel(m[1]):7d} {rel(m[2]):7d} | {rel(s[0]):7d} {rel(s[1]):7d} {rel(s[2]):7d} {rel(s[3]):7d} | {rel(t[0]):7d}")
+    c = d[3]
+    print("CTA: entry, init done | softmax w2: prologue loads done, resident tiles seen, A operands in TMEM | accumulators complete, epilogue stored, exit")
+    print(f"   {rel(c[0][0])} {rel(c[0][1])} | {rel(c[0][2])} {rel(c[0][3])} {rel(c[1][0])} | {rel(c[1][1])} {rel(c[1][2])} {rel(c[1][3])}")
+
+
+allr = dbg.cpu().view(8, 64, 4)
+show(allr[:4], "attn_bwd_dq_tc<72>")
+show(allr[4:], "attn_bwd_dkv_tc<72>")
