@@ -20,8 +20,9 @@ int mapdit_attn_mma_bwd(const void* qkv, const void* o, const void* dout, const 
                         int heads, int hd, void* stream);
 bool mapdit_attn_mma_supported(int tokens, int hd);
 
-int g_mapdit_attn_bwd_fused = 2;  // mapdit_set_option("attn_bwd_fused", 0/1/2): tokens == 256: 0 = dq + dkv kernel pair, 1 = fused kernel,
-                                  // 2 = fused kernel with a dedicated read-out warpgroup
+int g_mapdit_attn_bwd_fused = 3;  // mapdit_set_option("attn_bwd_fused", 0..3): tokens == 256: 0 = dq + dkv kernel pair, 1 = fused kernel,
+                                  // 2 = fused kernel with a dedicated read-out warpgroup, 3 = that with 64-query half-iterations and
+                                  // P^T / dS^T in TMEM
 
 extern long long* g_attn_dbg;  // developer timeline hook (mapdit_attn_debug_buffer)
 
@@ -1613,6 +1614,392 @@ attn_bwd_fused2_tc(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
+// ------------------------------------------------------------------------------------------------ fused backward, third cut
+// The producer and the read-out warps of attn_bwd_fused2_tc, a different inner loop.  fused2 handed the whole [128 keys x 128 queries]
+// P^T and dS^T tiles through shared memory: 64 KB of stores, a proxy fence, 24 MMAs with both operands in shared memory (48 cycles
+// each, shared-memory bound) and no second S^T / dP^T buffer, so softmax and tensor core strictly alternated (4.6 k cycles per
+// iteration, tools/attn_bwd_timeline.py).  Here an iteration is split into two HALF-iterations of 64 queries: S^T / dP^T are 64 TMEM
+// columns each, which leaves room for two buffers; P^T and dS^T go back into TMEM in place and are the A operands of the dV / dK MMAs
+// (as in attn_bwd_dkv_tc); only dS^T is also staged in shared memory, for the transposed read of the dQ MMA (issued every second
+// half-iteration over both panels), in one of two staging tiles.
+__global__ void __launch_bounds__(F2_NTHREADS, 1)
+attn_bwd_fused3_tc(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
+                   const __grid_constant__ CUtensorMap tm_out, const float* __restrict__ lse, const float* __restrict__ delta, int heads,
+                   int total_items, const float* __restrict__ sc, float eps, long long* __restrict__ dbg) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* sTile = smem;                      // 8 input tiles + the dQ staging tile, index = T* enum
+  uint8_t* sStg = sTile + 9 * F_TILE;  // 2 x dS^T staging tile ([128 keys x 128 queries] as two 64-query panels), for the dQ MMAs only
+  float* sL = reinterpret_cast<float*>(sStg + 2 * F_STG);  // [2][256] log2-domain log-sum-exp of the item's queries
+  float* sDl = sL + 2 * F_T;                            // [2][256] delta
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDl + 2 * F_T);
+  uint64_t* full = bars;            // [8] input tile landed
+  uint64_t* empty = bars + 8;       // [8] input tile may be refilled
+  uint64_t* s_full = bars + 16;     // [2] S^T / dP^T of half-iteration u complete in TMEM buffer u & 1
+  uint64_t* p_full = bars + 18;     // [2] P^T / dS^T of half-iteration u written (TMEM in place; dS^T also into its staging panel), 8 warps
+  uint64_t* stg_empty = bars + 20;  // [2] the dQ MMAs of iteration g have read staging tile g & 1
+  uint64_t* acc_free = bars + 22;   // dV / dK read out (4 epilogue warps), twice per item
+  uint64_t* dqs_free = bars + 23;   // dQ of the item's second query block read out
+  uint64_t* dqf_free = bars + 24;   // dQ of the item's first query block read out
+  uint64_t* kv0_ready = bars + 25;  // MMA -> epilogue: dV_0 / dK_0 complete (after iteration 1)
+  uint64_t* dqs_ready = bars + 26;  // dQ (second block) complete (after iteration 2)
+  uint64_t* fin_ready = bars + 27;  // dV_1 / dK_1 / dQ (first block) complete (after iteration 3)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int D = heads * HD;
+  const int my_items = blockIdx.x < total_items ? (total_items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int G = my_items * 8;  // half-iterations u = 8 * it + w: w >> 1 = the (key tile, query block) step of the item, w & 1 = which 64 queries of the block
+  auto qb_of = [](int g) { return (((g & 3) == 1 || (g & 3) == 2) ? 1 : 0) ^ ((g >> 2) & 1); };
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tm_qkv);
+    prefetch_tmap(&tm_do);
+    prefetch_tmap(&tm_out);
+    for (int i = 0; i < 8; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], i < TD0 ? 5 : 1);  // K / V / Q tiles: the MMA warp + four epilogue warps
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 8);
+      mbar_init(&stg_empty[i], 1);
+    }
+    mbar_init(acc_free, 4);
+    mbar_init(dqs_free, 4);
+    mbar_init(dqf_free, 4);
+    mbar_init(kv0_ready, 1);
+    mbar_init(dqs_ready, 1);
+    mbar_init(fin_ready, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  // two (S^T [0, 64) | dP^T [64, 128)) buffers for alternate half-iterations, then the accumulators
+  constexpr uint32_t C_DV = 256, C_DK = 320, C_DQ = 384;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < my_items; ++it) {
+        const int item = blockIdx.x + it * gridDim.x;
+        const int n = item / heads, h = item - n * heads;
+        const uint32_t ph = it & 1;
+        const int f = it & 1;
+        if (it + 1 < my_items) {  // next item's 128 KB into L2, one whole item ahead (see attn_bwd_fused_tc)
+          const int nitem = item + gridDim.x;
+          const int nn = nitem / heads, nh = nitem - nn * heads;
+#pragma unroll
+          for (int rb = 0; rb < 2; ++rb) {
+            const int row = nn * F_T + rb * RT;
+            tma_prefetch_l2_2d(&tm_qkv, nh * HD, row);
+            tma_prefetch_l2_2d(&tm_qkv, D + nh * HD, row);
+            tma_prefetch_l2_2d(&tm_qkv, 2 * D + nh * HD, row);
+            tma_prefetch_l2_2d(&tm_do, nh * HD, row);
+          }
+        }
+        const int order[8] = {TK0, TV0, TQ0 + f, TD0 + f, TQ0 + (f ^ 1), TD0 + (f ^ 1), TK1, TV1};
+        for (int k = 0; k < 8; ++k) {
+          const int t = order[k];
+          mbar_wait(&empty[t], ph ^ 1);
+          mbar_arrive_expect_tx(&full[t], F_TILE);
+          const int row = n * F_T + (t & 1) * RT;
+          if (t >= TD0) tma_load_2d(sTile + t * F_TILE, &tm_do, &full[t], h * HD, row);
+          else tma_load_2d(sTile + t * F_TILE, &tm_qkv, &full[t], (t >= TQ0 ? 0 : (t >= TV0 ? 2 * D : D)) + h * HD, row);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    const bool leader = elect_one();
+    constexpr uint32_t idesc_s = make_idesc_bf16(RT, 64, 0, 0);   // S^T = K Q^T, dP^T = V dO^T over 64 queries
+    constexpr uint32_t idesc_a = make_idesc_bf16(RT, HD, 0, 1);   // dV += P^T dO, dK += dS^T Q: A from TMEM, B MN-major
+    constexpr uint32_t idesc_q = make_idesc_bf16(RT, HD, 1, 1);   // dQ += dS K: A = the dS^T staging tile read MN-major, B MN-major
+    const uint64_t d_tile = make_smem_desc(smem_u32(sTile), 16, 1024);      // K-major view of input tile 0
+    const uint64_t d_tmn = make_smem_desc(smem_u32(sTile), 1024, 1024);     // MN-major view of input tile 0 (B of dV / dK / dQ)
+    const uint64_t d_stg = make_smem_desc(smem_u32(sStg), F_TILE, 1024);    // MN-major view of staging tile 0 (A of dQ): LBO = panel stride
+    auto scores = [&](int u) {
+      const int w = u & 7, pos = w >> 1, sub = w & 1, kt = pos >> 1, qb = qb_of(u >> 1), b = u & 1;
+      const uint32_t ph = (u >> 3) & 1;
+      if ((w & 3) == 0) {
+        mbar_wait(&full[TK0 + kt], ph);
+        mbar_wait(&full[TV0 + kt], ph);
+      }
+      if (kt == 0 && sub == 0) {
+        mbar_wait(&full[TQ0 + qb], ph);
+        mbar_wait(&full[TD0 + qb], ph);
+      }
+      const uint64_t d_k = desc_advance(d_tile, (TK0 + kt) * F_TILE), d_v = desc_advance(d_tile, (TV0 + kt) * F_TILE);
+      const uint64_t d_q = desc_advance(d_tile, (TQ0 + qb) * F_TILE + sub * (F_TILE / 2));
+      const uint64_t d_do = desc_advance(d_tile, (TD0 + qb) * F_TILE + sub * (F_TILE / 2));
+      const uint32_t t_s = tmem_base + b * 128;
+#pragma unroll
+      for (int k = 0; k < HD / 16; ++k) {
+        if (leader) umma_ss(t_s, desc_advance(d_k, k * 32), desc_advance(d_q, k * 32), idesc_s, k != 0);
+        if (leader) umma_ss(t_s + 64, desc_advance(d_v, k * 32), desc_advance(d_do, k * 32), idesc_s, k != 0);
+      }
+      if (leader) umma_commit(&s_full[b]);
+    };
+    if (G > 0) scores(0);
+    if (G > 1) scores(1);
+    for (int u = 0; u < G; ++u) {
+      const int w = u & 7, pos = w >> 1, sub = w & 1, kt = pos >> 1, g = u >> 1, qb = qb_of(g), it = u >> 3, b = u & 1;
+      // accumulators this half-iteration starts from zero must have been read out
+      if (w == 4) mbar_wait(acc_free, 0);                                   // dV_0 / dK_0
+      if (w == 0 && it > 0) mbar_wait(acc_free, 1);                          // previous item: dV_1 / dK_1
+      if (w == 1 && it > 0) mbar_wait(dqs_free, (it - 1) & 1);               // ... the dQ these columns held (its second block)
+      if (w == 3 && it > 0) mbar_wait(dqf_free, (it - 1) & 1);               // ... and its first block
+      mbar_wait_spin(&p_full[b], (u >> 1) & 1);
+      FSTAMP(0, u, 1);
+      tc_fence_after();
+      const uint64_t d_do = desc_advance(d_tmn, (TD0 + qb) * F_TILE + sub * (F_TILE / 2));
+      const uint64_t d_q = desc_advance(d_tmn, (TQ0 + qb) * F_TILE + sub * (F_TILE / 2));
+      const uint32_t t_p = tmem_base + b * 128;  // P^T over the S^T columns, dS^T over the dP^T columns (see the softmax warps)
+#pragma unroll
+      for (int k = 0; k < 64 / 16; ++k) {  // 16 queries per k-step
+        const uint32_t ko = (k >> 1) * 32 + (k & 1) * 8;
+        if (leader) umma_ts(tmem_base + C_DV, t_p + ko, desc_advance(d_do, k * 2048), idesc_a, ((w & 3) | k) != 0);
+        if (leader) umma_ts(tmem_base + C_DK, t_p + 64 + ko, desc_advance(d_q, k * 2048), idesc_a, ((w & 3) | k) != 0);
+      }
+      if (sub == 1) {  // both 64-query panels of the block's dS^T are staged: dQ_qb += dS K_kt over the 128 keys
+        const uint64_t d_a = desc_advance(d_stg, (g & 1) * F_STG), d_kk = desc_advance(d_tmn, (TK0 + kt) * F_TILE);
+#pragma unroll
+        for (int k = 0; k < 128 / 16; ++k)
+          if (leader) umma_ss(tmem_base + C_DQ + qb * HD, desc_advance(d_a, k * 2048), desc_advance(d_kk, k * 2048), idesc_q, (kt | k) != 0);
+        if (leader) umma_commit(&stg_empty[g & 1]);
+      }
+      // (kv0_ready only behind the dQ MMAs of w == 3, the last readers of the K_0 tile: the read-out warps overwrite that tile with dK_0.
+      // Committing it ahead of them passed the tests three times and then corrupted 4 % of the gradient when the timing shifted.)
+      if (w == 3 && leader) umma_commit(kv0_ready);
+      FSTAMP(0, u, 2);
+      if (w == 3) {
+        if (leader) umma_commit(&empty[TK0]);
+        if (leader) umma_commit(&empty[TV0]);
+      } else if (w == 5) {
+        if (leader) umma_commit(dqs_ready);
+        if (leader) umma_commit(&empty[TQ0 + qb]);
+        if (leader) umma_commit(&empty[TD0 + qb]);
+      } else if (w == 7) {
+        if (leader) umma_commit(fin_ready);
+        if (leader) umma_commit(&empty[TQ0 + qb]);
+        if (leader) umma_commit(&empty[TD0 + qb]);
+        if (leader) umma_commit(&empty[TK1]);
+        if (leader) umma_commit(&empty[TV1]);
+      }
+      // S^T / dP^T two half-iterations ahead, into the buffer whose P^T / dS^T the TS MMAs above read: the tensor core runs one thread's
+      // MMAs in issue order.  (Ahead of the dQ MMAs instead of behind them: measured slower.)
+      if (u + 2 < G) scores(u + 2);
+    }
+  } else if (warp < 10) {
+    // ------------------------------------------------------------------ softmax warps: S^T, dP^T -> P^T, dS^T staging tiles
+    const int wq = warp & 3;
+    const int h0 = (warp - 2) >> 2;  // which 32 of the 64 queries of a half-iteration
+    const int r = wq * 32 + lane;    // key row
+    const int tid = threadIdx.x - 64;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(wq * 32) << 16);
+    const float c1 = 0.125f * LOG2E;
+    // per-query L and delta of an item go global -> shared with cp.async: no register holds them across the exp pass
+    auto fetch_ld = [&](int item, int buf) {
+      const int n = item / heads, h = item - n * heads;
+      const size_t qrow = (size_t)n * F_T + tid;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(sL + buf + tid)), "l"(lse + qrow * heads + h) : "memory");
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(sDl + buf + tid)), "l"(delta + qrow * heads + h) : "memory");
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto land_ld = [&](int buf) {  // own element arrived: natural log -> log2 domain, then the 256-thread barrier publishes it
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      sL[buf + tid] *= LOG2E;
+    };
+    if (G > 0) fetch_ld(blockIdx.x, 0);
+    for (int u = 0; u < G; ++u) {
+      const int w = u & 7, sub = w & 1, g = u >> 1, qb = qb_of(g), it = u >> 3, b = u & 1;
+      const int item = blockIdx.x + it * gridDim.x;
+      const int buf = (it & 1) * F_T;
+      if (w == 0) {
+        land_ld(buf);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
+      if (w == 4 && it + 1 < my_items) fetch_ld(item + gridDim.x, buf ^ F_T);
+      if (warp == 2) FSTAMP(1, u, 0);
+      mbar_wait(&s_full[b], (u >> 1) & 1);
+      if (warp == 2) FSTAMP(1, u, 1);
+      tc_fence_after();
+      const float4* pL = reinterpret_cast<const float4*>(sL + buf + qb * RT + sub * 64 + h0 * 32);
+      const float4* pD = reinterpret_cast<const float4*>(sDl + buf + qb * RT + sub * 64 + h0 * 32);
+      uint32_t sv[32], dp[32], pp[16], pd[16];
+      tmem_ld32(t_lane + b * 128 + h0 * 32, sv);
+      tmem_ld32(t_lane + b * 128 + 64 + h0 * 32, dp);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 l4 = pL[j], d4 = pD[j];
+        const float p0 = ex2(fmaf(__uint_as_float(sv[4 * j]), c1, -l4.x));
+        const float p1 = ex2(fmaf(__uint_as_float(sv[4 * j + 1]), c1, -l4.y));
+        const float p2 = ex2(fmaf(__uint_as_float(sv[4 * j + 2]), c1, -l4.z));
+        const float p3 = ex2(fmaf(__uint_as_float(sv[4 * j + 3]), c1, -l4.w));
+        pp[2 * j] = pack_bf16(p0, p1);
+        pp[2 * j + 1] = pack_bf16(p2, p3);
+        pd[2 * j] = pack_bf16(p0 * (__uint_as_float(dp[4 * j]) - d4.x), p1 * (__uint_as_float(dp[4 * j + 1]) - d4.y));
+        pd[2 * j + 1] = pack_bf16(p2 * (__uint_as_float(dp[4 * j + 2]) - d4.z), p3 * (__uint_as_float(dp[4 * j + 3]) - d4.w));
+      }
+      if (warp == 2) FSTAMP(1, u, 2);
+      // in place, over columns only this thread reads: 32 queries = 16 packed columns at the start of the warp's 32-column group; these
+      // are the A operands of the dV / dK MMAs
+      tmem_st16(t_lane + b * 128 + h0 * 32, pp);
+      tmem_st16(t_lane + b * 128 + 64 + h0 * 32, pd);
+      // dS^T once more into panel `sub` of the block's staging tile: the dQ MMAs read it transposed (MN-major), which TMEM cannot serve
+      if (sub == 0 && g >= 2) mbar_wait(&stg_empty[g & 1], ((g >> 1) & 1) ^ 1);  // the dQ MMAs of iteration g - 2 have read the tile
+      store_half_row_sw128(sStg + (g & 1) * F_STG + sub * F_TILE, r, h0, pd);
+      tmem_st_wait();
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[b]);
+      if (warp == 2) FSTAMP(1, u, 3);
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps 10-13: accumulator read-outs, q^ stashes
+    const int wq = warp & 3;
+    const int r = wq * 32 + lane;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(wq * 32) << 16);
+    auto signal_free = [&](uint64_t* bar) {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar);
+    };
+    auto slab_store = [&](uint8_t* stile, size_t grow0, int gcol) {  // rows of this warp written: 32-row slab -> dqkv by TMA
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) tma_store_2d(&tm_out, stile + wq * 32 * 128, gcol, (int)(grow0 + wq * 32));
+    };
+    auto release = [&](int t0, int t1) {  // the stores issued so far have read their smem: hand input tiles back
+      if (lane == 0) {
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        mbar_arrive(&empty[t0]);
+        if (t1 >= 0) mbar_arrive(&empty[t1]);
+      }
+      __syncwarp();
+    };
+    // dV: plain copy of a finished accumulator into (dead) tile `stile`
+    auto readout_plain = [&](uint32_t col, uint8_t* stile, float scale) {
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        uint32_t a[32], out[16];
+        tmem_ld32(t_lane + col + 32 * hf, a);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 16; ++c) out[c] = pack_bf16(__uint_as_float(a[2 * c]) * scale, __uint_as_float(a[2 * c + 1]) * scale);
+        store_half_row_sw128(stile, r, hf, out);
+      }
+    };
+    // dQ / dK: q/k-normalisation backward against the normalised row in `stile` (see store_out_row_qknorm), written over it.  The whole
+    // accumulator row goes into registers first and `done` is signalled right behind that one TMEM round trip: the MMA warp waits for
+    // it before the next key tile / item may accumulate into these columns (the two-pass read-out of fused2 signalled ~1.5 k cycles later).
+    auto readout_qk = [&](uint32_t col, uint8_t* stile, float s, uint64_t* done) {
+      uint32_t a0[32], a1[32];
+      tmem_ld32(t_lane + col, a0);
+      tmem_ld32(t_lane + col + 32, a1);
+      tmem_ld_wait();
+      if (done) signal_free(done);
+      float dot = 0.f;
+      if (sc) {
+        float y[32];
+        load_half_row_sw128(stile, r, 0, y);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) dot = fmaf(y[c], __uint_as_float(a0[c]), dot);
+        load_half_row_sw128(stile, r, 1, y);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) dot = fmaf(y[c], __uint_as_float(a1[c]), dot);
+      }
+      dot *= 0.125f;
+      const float rpe = 8.0f / s;
+      const float rr = fmaxf(rpe - eps, 1e-30f);
+      const float sco = sc ? -s * (dot * rpe / (64.0f * rr)) : 0.f;
+      const float ga = (sc ? s : 1.0f) * 0.125f;
+      {
+        uint32_t out[16];
+        float y[32];
+        load_half_row_sw128(stile, r, 0, y);
+#pragma unroll
+        for (int c = 0; c < 16; ++c)
+          out[c] = pack_bf16(fmaf(ga, __uint_as_float(a0[2 * c]), sco * y[2 * c]), fmaf(ga, __uint_as_float(a0[2 * c + 1]), sco * y[2 * c + 1]));
+        store_half_row_sw128(stile, r, 0, out);
+        load_half_row_sw128(stile, r, 1, y);
+#pragma unroll
+        for (int c = 0; c < 16; ++c)
+          out[c] = pack_bf16(fmaf(ga, __uint_as_float(a1[2 * c]), sco * y[2 * c]), fmaf(ga, __uint_as_float(a1[2 * c + 1]), sco * y[2 * c + 1]));
+        store_half_row_sw128(stile, r, 1, out);
+      }
+    };
+    auto stash_q = [&](int qb) {  // this thread's q^ row of query block qb -> the dQ staging tile; then the Q tile may be refilled
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      __syncwarp();
+      const uint32_t off = (r >> 3) * 1024 + (r & 7) * 128;
+      const uint4* src = reinterpret_cast<const uint4*>(sTile + (TQ0 + qb) * F_TILE + off);
+      uint4* dst = reinterpret_cast<uint4*>(sTile + TOUT * F_TILE + off);
+      uint4 v[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) v[c] = src[c ^ (r & 7)];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) dst[c ^ (r & 7)] = v[c];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[TQ0 + qb]);
+    };
+    for (int it = 0; it < my_items; ++it) {
+      const int item = blockIdx.x + it * gridDim.x;
+      const int n = item / heads, h = item - n * heads;
+      const uint32_t ph = it & 1;
+      const int qf = it & 1, qs = qf ^ 1;  // first / second query block of this item
+      const size_t row0 = (size_t)n * F_T;
+      float s_q = 1.f, s_k = 1.f;
+      // ---- second query block resident from iteration 1 on: stash its q^ rows (dQ staging tile is free: its last store was read)
+      mbar_wait(&full[TQ0 + qs], ph);
+      stash_q(qs);
+      // ---- key tile 0 complete after iteration 1
+      if (sc) s_k = sc[(row0 + r) * 2 * heads + heads + h];
+      mbar_wait(kv0_ready, ph);
+      tc_fence_after();
+      readout_plain(C_DV, sTile + TV0 * F_TILE, 1.0f);
+      readout_qk(C_DK, sTile + TK0 * F_TILE, s_k, acc_free);
+      slab_store(sTile + TV0 * F_TILE, row0, 2 * D + h * HD);
+      slab_store(sTile + TK0 * F_TILE, row0, D + h * HD);
+      release(TK0, TV0);  // the next item needs these two first: hand them back before anything else
+      if (warp == 10) FSTAMP(2, 8 * it, 0);
+      // ---- dQ of the second block complete after iteration 2
+      if (sc) s_q = sc[(row0 + qs * RT + r) * 2 * heads + h];
+      mbar_wait(dqs_ready, ph);
+      tc_fence_after();
+      readout_qk(C_DQ + qs * HD, sTile + TOUT * F_TILE, s_q, dqs_free);
+      slab_store(sTile + TOUT * F_TILE, row0 + qs * RT, h * HD);
+      if (warp == 10) FSTAMP(2, 8 * it, 1);
+      // ---- first query block: stash (its tile is still resident: this warp's arrival is part of its release)
+      stash_q(qf);
+      // ---- key tile 1 and the first block's dQ complete after iteration 3
+      if (sc) {
+        s_k = sc[(row0 + RT + r) * 2 * heads + heads + h];
+        s_q = sc[(row0 + qf * RT + r) * 2 * heads + h];
+      }
+      mbar_wait(fin_ready, ph);
+      tc_fence_after();
+      readout_plain(C_DV, sTile + TV1 * F_TILE, 1.0f);
+      readout_qk(C_DK, sTile + TK1 * F_TILE, s_k, acc_free);
+      slab_store(sTile + TV1 * F_TILE, row0 + RT, 2 * D + h * HD);
+      slab_store(sTile + TK1 * F_TILE, row0 + RT, D + h * HD);
+      readout_qk(C_DQ + qf * HD, sTile + TOUT * F_TILE, s_q, dqf_free);
+      slab_store(sTile + TOUT * F_TILE, row0 + qf * RT, h * HD);
+      release(TK1, TV1);
+      if (warp == 10) FSTAMP(2, 8 * it, 2);
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete before the CTA exits
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
 template <int HDV>
 __global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ dout, float* __restrict__ delta,
                                                          long long m_heads) {
@@ -1767,6 +2154,20 @@ static int attn_bwd_impl(const void* qkv, const void* o, const void* dout, const
     if (encode2d(&t_out, dqkv, 3 * D, rows, 3 * D, 32) != 0) {
       mapdit_set_error("cos_attn_bwd(fused): cuTensorMapEncodeTiled failed");
       return MAPDIT_ERR_CUDA;
+    }
+    if (g_mapdit_attn_bwd_fused >= 3) {
+      static bool f3attr = false;
+      if (!f3attr) {
+        if (cudaFuncSetAttribute(attn_bwd_fused3_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM) != cudaSuccess) {
+          mapdit_set_error("cos_attn_bwd(fused3): cudaFuncSetAttribute failed");
+          return MAPDIT_ERR_CUDA;
+        }
+        f3attr = true;
+      }
+      attn_bwd_fused3_tc<<<items < sms ? items : sms, F2_NTHREADS, F_SMEM, s>>>(t_qkv_row, t_do_row, t_out, lse, delta, heads, items, sc, eps,
+                                                                              g_attn_dbg);
+      MAPDIT_LAUNCH_CHECK("cos_attn_bwd(fused3)");
+      return MAPDIT_OK;
     }
     if (g_mapdit_attn_bwd_fused >= 2) {
       static bool f2attr = false;
