@@ -62,23 +62,6 @@ __device__ __forceinline__ float ex2f(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// D[tmem] (+)= A[tmem] * B[smem]
-__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
-      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
-      "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld1(uint32_t taddr, uint32_t& v) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
 }
@@ -201,18 +184,23 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       // second N panel of the PV B operand: the constant ones panel (64 channels: column 64 = row sum) or V's own second panel (72)
       const uint32_t v_lbo = HD == 64 ? 0u : (uint32_t)PANEL_K;
       const uint32_t ones_addr = smem_u32(sOnes);
+      // descriptors of Q buffer 0 (this issuer's tile) and of ring stage 0; every MMA operand is one of these moved by a byte offset
+      // (desc_advance: one add).  Rebuilding the descriptors per MMA made the issue loop twice as long as the MMAs it issues
+      // (tools/attn_timeline.py: 1.3-1.5 k cycles for 12 MMAs worth 580 tensor-core cycles).
+      const uint64_t d_q0 = make_smem_desc(smem_u32(sQ + x * A::TILE_Q), 16, 1024);
+      const uint64_t d_k0 = make_smem_desc(smem_u32(sKV), 16, 1024);
+      const uint64_t d_v0 = make_smem_desc(smem_u32(sKV + K_BYTES), HD == 64 ? ones_addr - smem_u32(sKV + K_BYTES) : v_lbo, 1024);
       auto issue_s = [&](uint32_t g) {  // S_x(g) = Q_x K_g^T into buffer g & 1, then signal tile x's softmax warps
         const uint32_t it = g / nkb, b = g % SBUF;
         if (g - it * nkb == 0) mbar_wait(&q_full[it % QBUF], (it / QBUF) & 1);
         mbar_wait(&kv_full[g % NS], (g / NS) & 1);
         tc_fence_after();
-        const uint32_t q_addr = smem_u32(sQ + (it % QBUF) * Q_BYTES + x * A::TILE_Q);
-        const uint32_t k_addr = smem_u32(sKV + (g % NS) * KV_BYTES);
+        const uint64_t d_q = desc_advance(d_q0, (it % QBUF) * Q_BYTES), d_k = desc_advance(d_k0, (g % NS) * KV_BYTES);
 #pragma unroll
         for (int k = 0; k < A::KSTEPS; ++k)  // 16 channels per MMA; step 4 (head_dim 72) is the first 16 channels of the second panel
           if (leader)
-            umma_ss(tmem_base + col_s(x, b), make_smem_desc(q_addr + (k >> 2) * PANEL_Q + (k & 3) * 32, 16, 1024),
-                    make_smem_desc(k_addr + (k >> 2) * PANEL_K + (k & 3) * 32, 16, 1024), idesc_s, k != 0);
+            umma_ss(tmem_base + col_s(x, b), desc_advance(d_q, (k >> 2) * PANEL_Q + (k & 3) * 32),
+                    desc_advance(d_k, (k >> 2) * PANEL_K + (k & 3) * 32), idesc_s, k != 0);
         if (leader) umma_commit(&s_full[2 * x + b]);
         // the query tiles of an item are free once S_B of its last key block has been issued
         if (leader && g - it * nkb + 1 == (uint32_t)nkb) umma_commit(&q_empty[it % QBUF]);
@@ -221,7 +209,9 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       for (uint32_t g = 0; g < total_steps; ++g) {
         const uint32_t it = g / nkb, j = g - it * nkb, b = g % SBUF;
         const bool last_j = (j + 1 == (uint32_t)nkb);
-        const uint32_t v_addr = smem_u32(sKV + (g % NS) * KV_BYTES + K_BYTES);
+        // head_dim 64: the second N panel is the fixed ones panel, so the leading-dimension offset shrinks as the stage address grows
+        const uint32_t v_off = (g % NS) * KV_BYTES;
+        const uint64_t d_v = desc_advance(d_v0, v_off) - (HD == 64 ? (uint64_t)(v_off >> 4) << 16 : 0ull);
         {
           if (j == 0) mbar_wait(&o_empty[x], (it & 1) ^ 1);  // the epilogue has read the previous item's O_x
           mbar_wait(&p_full[2 * x + b], (g / SBUF) & 1);
@@ -230,8 +220,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #pragma unroll
           for (int k = 0; k < KB / 16; ++k)  // 16 keys per MMA: P advances 8 TMEM columns, V two 8-row groups
             if (leader)
-              umma_ts(tmem_base + col_o(x), tmem_base + col_s(x, b) + k * 8,
-                      make_smem_desc(v_addr + k * 2048, HD == 64 ? ones_addr - v_addr : v_lbo, 1024), idesc_o, (j | k) != 0);
+              umma_ts(tmem_base + col_o(x), tmem_base + col_s(x, b) + k * 8, desc_advance(d_v, k * 2048), idesc_o, (j | k) != 0);
           if (leader && last_j) umma_commit(&o_full[x]);
           if (leader) umma_commit(&kv_empty[g % NS]);  // V_g is done with (K_g since S_x(g), two steps ago)
           if (g + SBUF < total_steps) issue_s(g + SBUF);  // reuses buffer b right behind the PV that read P from it
