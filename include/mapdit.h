@@ -126,10 +126,12 @@ int mapdit_sizeof_gemm_args(void); /* lets a binding check its struct mirror */
  * for large-M GEMMs; "gemm_2cta_bn" (0 = auto, 128 / 192 / 256 = force that pair-tile width where it applies); "gemm_fused_resid" (0 = first-generation
  * residual epilogues, 1 = second generation where the main loop is short (default), 2 = always); "attn_v2" (0/1) selects the one-CTA-per-SM
  * ping-pong attention forward for tokens % 256 == 0; "attn_bwd_fused" (tokens == 256: 0 = dq + dkv kernel pair, 1 = single fused
- * kernel, 2 = fused kernel with a dedicated read-out warpgroup, the default) */
+ * kernel, 2 = fused kernel with a dedicated read-out warpgroup, 3 = that kernel with 64-query half-iterations and P^T / dS^T kept in
+ * TMEM as MMA operands, the default) */
 int mapdit_set_option(const char* name, int value);
-/* developer hook: device buffer of >= 1024 int64 that CTA 0 of the attn_v2 / attn_bwd_fused / 2-CTA GEMM kernels fills with
- * clock64 stamps (null = off); read by tools/attn_timeline.py, tools/attn_bwd_timeline.py, tools/gemm_timeline.py */
+/* developer hook: device buffer of >= 2048 int64 that one CTA of the attn_v2 / attn_bwd_fused / attention backward pair / 2-CTA GEMM
+ * kernels fills with clock64 stamps (null = off); read by tools/attn_timeline.py, tools/attn_bwd_timeline.py,
+ * tools/attn_bwd_xl_timeline.py, tools/gemm_timeline.py */
 int mapdit_attn_debug_buffer(void* buf);
 /* weight gradient C[N_out, K_in] (fp32) = dY[M, N_out]^T · X[M, K_in] on tcgen05, operands read MN-major in place
  * (autograd of F.linear, src/basic/mp_linear.py:46,75); split-K with fp32 vector reductions when N_out*K_in is small */

@@ -1,16 +1,18 @@
-// Backward of cosine attention on tcgen05 (head_dim 64, tokens a multiple of 64, bf16 operands, fp32 accumulation).
+// Backward of cosine attention on tcgen05 (head_dim 64 or 72, tokens a multiple of 64, bf16 operands, fp32 accumulation).
 //
 //   logits = q·k/8,  P = exp(logits - L) (L = saved log-sum-exp),  delta_i = dO_i·O_i
 //   dV = P^T dO,  dP = dO V^T,  dS = P (dP - delta),  dQ = dS K / 8,  dK = dS^T Q / 8
 //
-// Two kernels, each shaped like the forward kernel (TMA producer warp, single-thread MMA issuer, four
-// softmax warps that own one TMEM lane = one row each):
+// General path: a coalesced delta kernel, then two kernels shaped like the forward kernel (TMA producer warp, MMA issuer warp,
+// eight softmax warps: two per TMEM lane quarter, a thread owns 32 columns of one row):
 //   * dq kernel  : CTA = (sample, head, 128 queries); rows = queries.  S = Q K_j^T and dP = dO V_j^T per 64-key block,
-//                  dS (bf16) goes to shared memory as a K-major A operand, dQ += dS K_j with K_j re-read MN-major from
-//                  the same TMA tile.  Also produces delta for the second kernel.
+//                  dS (bf16) goes back into TMEM as the A operand of dQ += dS K_j, K_j re-read MN-major from its TMA tile.
 //   * dkv kernel : CTA = (sample, head, 128 keys); rows = keys.  S^T = K Q_j^T and dP^T = V dO_j^T per 64-query block, so
-//                  P^T and dS^T are produced directly in the K-major layout the dV += P^T dO_j and dK += dS^T Q_j MMAs
-//                  need; dO_j and Q_j are re-read MN-major from their TMA tiles.  No transposes, no atomics.
+//                  P^T and dS^T are produced directly in the row = key layout the dV += P^T dO_j and dK += dS^T Q_j MMAs
+//                  need (written in place over S^T / dP^T in TMEM); dO_j and Q_j are re-read MN-major from their TMA tiles.
+//                  No transposes, no atomics.
+//   Every A operand lives in TMEM (the resident Q, dO / K, V tiles are copied there once per CTA): see attn_bwd_dq_tc.
+// tokens == 256 at head_dim 64: one fused persistent kernel (attn_bwd_fused_tc and its successors) further down.
 #include "tc_common.cuh"
 
 int mapdit_attn_bwd_simt(const void* qkv, const void* o, const void* dout, const float* lse, void* dqkv, float* delta, int n_samples,

@@ -316,17 +316,19 @@ def test_attention_backward_with_fused_qk_norm(N, T, H, dtype):
     print(f"fused attention + qk-norm backward {dtype}: rel-L2 vs autograd {e:.2e}")
     assert e < (3e-5 if dtype == torch.float32 else 2.5e-2)
     if T == 256 and dtype == torch.bfloat16:
-        # tokens == 256 runs the single fused kernel (attn_bwd_fused_tc); the dq + dkv kernel pair must agree with it
+        # tokens == 256 runs the fused kernel (attn_bwd_fused3_tc by default); the dq + dkv kernel pair (0) and the two earlier
+        # fused kernels (1, 2) must agree with it
         from mapdit_b200 import _lib
-        _lib.set_option("attn_bwd_fused", 0)
-        try:
-            d2 = torch.full_like(qkv, float("nan"))
-            ops.cos_attn_bwd_qknorm(qkv, o, dout, lse, sc, d2, delta, N, T, H, hd)
-            torch.cuda.synchronize()
-        finally:
-            _lib.set_option("attn_bwd_fused", 1)
-        assert rel_l2(d2.float(), r.grad) < 2.5e-2
-        assert rel_l2(d2.float(), dqkv.float()) < 1e-2
+        for variant in (0, 1, 2):
+            _lib.set_option("attn_bwd_fused", variant)
+            try:
+                d2 = torch.full_like(qkv, float("nan"))
+                ops.cos_attn_bwd_qknorm(qkv, o, dout, lse, sc, d2, delta, N, T, H, hd)
+                torch.cuda.synchronize()
+            finally:
+                _lib.set_option("attn_bwd_fused", 3)
+            assert rel_l2(d2.float(), r.grad) < 2.5e-2, variant
+            assert rel_l2(d2.float(), dqkv.float()) < 1e-2, variant
         for third in range(3):  # per-tensor (dq, dk, dv) so a wrong small tensor cannot hide in the norm of the others
             sl = slice(third * D, (third + 1) * D)
             assert rel_l2(dqkv[:, sl].float(), r.grad[:, sl]) < 2.5e-2, third
