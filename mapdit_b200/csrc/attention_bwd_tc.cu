@@ -248,44 +248,58 @@ __device__ __forceinline__ void tile_to_tmem(uint32_t taddr, const uint8_t* tile
 // S / dP(j+2) into the buffer of block j FIRST, then dQ(j) -- the softmax warps wait for S(j+2) while nothing waits for dQ(j).  (One
 // commit behind both, so that seeing S(j+2) implies the dS tile may be overwritten, saves a barrier but shows S(j+2) 160 cycles later:
 // measured slower.)
+// Persistent: one CTA per SM walks (query tile, head, sample) items.  With a CTA per item a third of its 25 k cycles were prologue
+// (TMA of Q / dO, cold K/V ring), epilogue and the gap to the next CTA, none of it overlapped (225 KB of shared memory and 480 TMEM
+// columns: one CTA per SM).  Here the K/V ring keeps running across items (all block counters are global), the next item's Q / dO land
+// in the staging tiles while the current item computes, and they are copied into the TMEM A tiles as soon as the current item's last
+// S / dP MMAs have completed -- before its dQ is read out.
 template <int HDV>
 __global__ void __launch_bounds__(BCfg<HDV>::NTHR, 1)
 attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_constant__ CUtensorMap tm_qkv_blk,
                const __grid_constant__ CUtensorMap tm_do_row, const float* __restrict__ lse, const float* __restrict__ delta,
-               bf16* __restrict__ dqkv, int tokens, int heads,
+               bf16* __restrict__ dqkv, int tokens, int heads, int n_samples,
                const bf16* __restrict__ qkv, const float* __restrict__ sc, float eps, long long* __restrict__ dbg) {
   using B = BCfg<HDV>;
-  // optional timeline of one CTA of a middle wave (tools/attn_bwd_xl_timeline.py): dbg[role*256 + 4*j + e] = clock64 at event e of key
-  // block j; role 3: CTA-level events
-#define DQ_STAMP(role, j, e)                                                                                          \
+  // optional timeline of CTA 0 (tools/attn_bwd_xl_timeline.py): dbg[role*256 + 4*g + e] = clock64 at event e of the CTA's g-th key
+  // block (counted across its items); role 3: item-level events of the first items
+#define DQ_STAMP(role, g, e)                                                                                          \
   do {                                                                                                                \
-    if (dbg && (blockIdx.x | blockIdx.y) == 0 && blockIdx.z == gridDim.z / 2 && (j) < 64 && (threadIdx.x & 31) == 0) \
-      dbg[(role) * 256 + 4 * (j) + (e)] = clock64();                                                                \
+    if (dbg && blockIdx.x == 0 && (g) < 64 && (threadIdx.x & 31) == 0) dbg[(role) * 256 + 4 * (g) + (e)] = clock64(); \
   } while (0)
-  if (threadIdx.x == 0) DQ_STAMP(3, 0, 0);
   constexpr int ROWB = B::ROWB, BLKB = B::BLKB, PROW = B::PROW, PBLK = B::PBLK, NST = B::DQ_NST, NSW = B::NSW;
   constexpr uint32_t T_DQ = B::T_ACC, T_QA = T_DQ + B::NACC, T_DOA = T_QA + B::A_COLS, T_DS = T_DOA + B::A_COLS;  // dQ | Q, dO (A operands) | 2 x dS
   static_assert(T_DS + 2 * 32 <= B::TMEM, "TMEM columns");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-  uint8_t* sQ = smem;
+  uint8_t* sQ = smem;         // staging of the next item's Q / dO tiles (TMA -> here -> TMEM)
   uint8_t* sdO = sQ + ROWB;
   uint8_t* sKV = sdO + ROWB;  // stage s: K_j at sKV + s*2*BLKB, V_j after it
   uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + NST * 2 * BLKB);
-  uint64_t* bar_q = bars;
+  uint64_t* bar_q = bars;                 // an item's Q / dO tiles have landed in the staging tiles
   uint64_t* kv_full = bars + 1;           // [NST]
   uint64_t* kv_empty = kv_full + NST;     // [NST]
   uint64_t* s_full = kv_empty + NST;      // [2]  S / dP of a block are in TMEM
   uint64_t* ds_full = s_full + 2;         // [2]  dS of a block is in TMEM (and its S / dP have been read)
   uint64_t* ds_empty = ds_full + 2;       // [2]  dQ(j) has read the dS tile
-  uint64_t* o_full = ds_empty + 2;
-  uint64_t* a_full = o_full + 1;          // Q and dO are in TMEM
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + 1);
+  uint64_t* o_full = ds_empty + 2;        // an item's dQ is complete
+  uint64_t* a_full = o_full + 1;          // an item's Q and dO are in TMEM
+  uint64_t* stage_free = a_full + 1;      // ... and the staging tiles may take the next item's
+  uint64_t* acc_free = stage_free + 1;    // an item's dQ has been read out
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_free + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qt = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
-  const int D = heads * HDV, q0 = qt * RT, nkb = tokens / CB, row_base = n * tokens;
+  const int D = heads * HDV, nkb = tokens / CB, nqt = (tokens + RT - 1) / RT;
+  const int total_items = nqt * heads * n_samples;
+  const int my_items = (int)blockIdx.x < total_items ? (total_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  // item -> query tile (fastest: the CTAs that run together share K / V in L2), head, sample
+  auto decode = [&](int it, int& q0, int& h, int& row_base) {
+    const int item = blockIdx.x + it * gridDim.x;
+    const int qt = item % nqt, rest = item / nqt;
+    h = rest % heads;
+    row_base = (rest / heads) * tokens;
+    q0 = qt * RT;
+  };
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tm_qkv_row);
@@ -303,6 +317,8 @@ attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_cons
     }
     mbar_init(o_full, 1);
     mbar_init(a_full, NSW);
+    mbar_init(stage_free, NSW);
+    mbar_init(acc_free, NSW / 2);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<B::TMEM>(tmem_slot);
@@ -310,30 +326,47 @@ attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
-  if (threadIdx.x == 0) DQ_STAMP(3, 0, 1);
 
-  if (warp == 0 && lane == 0) {
-    mbar_arrive_expect_tx(bar_q, 2 * ROWB);
-    load_tile<HDV>(sQ, &tm_qkv_row, bar_q, 0, h, heads, row_base + q0, PROW);
-    load_tile<HDV>(sdO, &tm_do_row, bar_q, 0, h, heads, row_base + q0, PROW);
-    for (int j = 0; j < nkb; ++j) {
-      const int s = j % NST;
-      mbar_wait(&kv_empty[s], ((j / NST) & 1) ^ 1);
-      DQ_STAMP(2, j, 0);
-      uint8_t* dst = sKV + s * 2 * BLKB;
-      mbar_arrive_expect_tx(&kv_full[s], 2 * BLKB);
-      load_tile<HDV>(dst, &tm_qkv_blk, &kv_full[s], 1, h, heads, row_base + j * CB, PBLK);
-      load_tile<HDV>(dst + BLKB, &tm_qkv_blk, &kv_full[s], 2, h, heads, row_base + j * CB, PBLK);
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------------------------------------------------------- TMA producer
+      auto load_rows = [&](int it) {
+        int q0, h, row_base;
+        decode(it, q0, h, row_base);
+        mbar_arrive_expect_tx(bar_q, 2 * ROWB);
+        load_tile<HDV>(sQ, &tm_qkv_row, bar_q, 0, h, heads, row_base + q0, PROW);
+        load_tile<HDV>(sdO, &tm_do_row, bar_q, 0, h, heads, row_base + q0, PROW);
+      };
+      if (my_items > 0) load_rows(0);
+      uint32_t g = 0;
+      for (int it = 0; it < my_items; ++it) {
+        int q0, h, row_base;
+        decode(it, q0, h, row_base);
+        for (int j = 0; j < nkb; ++j, ++g) {
+          const int s = g % NST;
+          mbar_wait(&kv_empty[s], ((g / NST) & 1) ^ 1);
+          DQ_STAMP(2, g, 0);
+          uint8_t* dst = sKV + s * 2 * BLKB;
+          mbar_arrive_expect_tx(&kv_full[s], 2 * BLKB);
+          load_tile<HDV>(dst, &tm_qkv_blk, &kv_full[s], 1, h, heads, row_base + j * CB, PBLK);
+          load_tile<HDV>(dst + BLKB, &tm_qkv_blk, &kv_full[s], 2, h, heads, row_base + j * CB, PBLK);
+        }
+        if (it + 1 < my_items) {  // the ring throttles this loop: we get here a few blocks before the item ends
+          mbar_wait(stage_free, it & 1);
+          load_rows(it + 1);
+        }
+      }
     }
   } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
     const bool leader = elect_one();  // whole warp runs the loop, one lane issues (see tc_common.cuh)
     constexpr uint32_t idesc_s = make_idesc_bf16(RT, CB, 0, 0);       // S / dP: A (Q, dO) from TMEM, B K-major
     constexpr uint32_t idesc_q = make_idesc_bf16(RT, B::NACC, 0, 1);  // dQ += dS K_j: dS from TMEM, K_j MN-major (d contiguous)
-    // descriptors of the resident tiles and of ring slot 0; every MMA operand is one of these moved by a compile-time or per-block offset
+    // descriptors of ring slot 0; every MMA operand is one of these moved by a compile-time or per-block offset
     const uint64_t d_kv = make_smem_desc(smem_u32(sKV), 16, 1024);     // K-major view of a K / V block (S, dP)
     const uint64_t d_kmn = make_smem_desc(smem_u32(sKV), PBLK, 1024);  // MN-major view of a K block (dQ): LBO = panel stride
-    auto scores = [&](int j) {  // kv_full of the block's ring slot has been waited for
-      const int s = j % NST, b = j & 1;
+    auto scores = [&](uint32_t g) {  // kv_full of the block's ring slot has been waited for
+      const uint32_t s = g % NST, b = g & 1;
       const uint64_t d_k = desc_advance(d_kv, s * 2 * BLKB), d_v = desc_advance(d_k, BLKB);
       const uint32_t t_s = tmem_base + b * 128;
       // the S and dP chains accumulate into different TMEM tiles: issued alternately so consecutive MMAs are independent
@@ -345,154 +378,197 @@ attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_cons
       }
       if (leader) umma_commit(&s_full[b]);
     };
-    mbar_wait(a_full, 0);
-    tc_fence_after();
-    mbar_wait(&kv_full[0], 0);
-    scores(0);
-    if (nkb > 1) {
-      mbar_wait(&kv_full[1 % NST], (1 / NST) & 1);
-      scores(1);
-    }
-    for (int j = 0; j < nkb; ++j) {
-      const int s = j % NST, b = j & 1;
-      // the ring wait of block j+2 in the shadow of the softmax warps' work on block j, not behind it (every mbarrier wait of this warp,
-      // even on a completed phase, is 100+ cycles)
-      if (j + 2 < nkb) mbar_wait(&kv_full[(j + 2) % NST], ((j + 2) / NST) & 1);
-      DQ_STAMP(0, j, 0);
-      mbar_wait_spin(&ds_full[b], (j >> 1) & 1);
+    uint32_t g0 = 0;
+    for (int it = 0; it < my_items; ++it, g0 += nkb) {
+      mbar_wait(a_full, it & 1);
       tc_fence_after();
-      DQ_STAMP(0, j, 1);
-      if (j + 2 < nkb) scores(j + 2);
-      const uint64_t d_b = desc_advance(d_kmn, s * 2 * BLKB);
+      mbar_wait(&kv_full[g0 % NST], (g0 / NST) & 1);
+      scores(g0);
+      if (nkb > 1) {
+        mbar_wait(&kv_full[(g0 + 1) % NST], ((g0 + 1) / NST) & 1);
+        scores(g0 + 1);
+      }
+      for (int j = 0; j < nkb; ++j) {
+        const uint32_t g = g0 + j, s = g % NST, b = g & 1;
+        // the ring wait of block j+2 in the shadow of the softmax warps' work on block j, not behind it (every mbarrier wait of this warp,
+        // even on a completed phase, is 100+ cycles)
+        if (j + 2 < nkb) mbar_wait(&kv_full[(g + 2) % NST], ((g + 2) / NST) & 1);
+        DQ_STAMP(0, g, 0);
+        mbar_wait_spin(&ds_full[b], (g >> 1) & 1);
+        tc_fence_after();
+        DQ_STAMP(0, g, 1);
+        if (j + 2 < nkb) scores(g + 2);
+        if (j == 0 && it > 0) {  // the previous item's dQ has been read out of the accumulator
+          mbar_wait(acc_free, (it - 1) & 1);
+          tc_fence_after();
+        }
+        const uint64_t d_b = desc_advance(d_kmn, s * 2 * BLKB);
 #pragma unroll
-      for (int k = 0; k < CB / 16; ++k)  // 16 keys = 8 packed columns
-        if (leader) umma_ts(tmem_base + T_DQ, tmem_base + T_DS + b * 32 + k * 8, desc_advance(d_b, k * 2048), idesc_q, (j | k) != 0);
-      if (leader) umma_commit(&kv_empty[s]);
-      if (leader) umma_commit(&ds_empty[b]);
-      DQ_STAMP(0, j, 2);
+        for (int k = 0; k < CB / 16; ++k)  // 16 keys = 8 packed columns
+          if (leader) umma_ts(tmem_base + T_DQ, tmem_base + T_DS + b * 32 + k * 8, desc_advance(d_b, k * 2048), idesc_q, (j | k) != 0);
+        if (leader) umma_commit(&kv_empty[s]);
+        if (leader) umma_commit(&ds_empty[b]);
+        DQ_STAMP(0, g, 2);
+      }
+      if (leader) umma_commit(o_full);
     }
-    if (leader) umma_commit(o_full);
-  } else if (warp >= 2) {
+  } else {
+    // ------------------------------------------------------------------ softmax warps / epilogue
     const int qq = warp & 3;
     const int h0 = (warp - 2) >> 2;  // which 32 of the 64 columns of a logit block this warp owns
     const int r = qq * 32 + lane;
     const uint32_t t_lane = tmem_base + ((uint32_t)(qq * 32) << 16);
-    const bool row_ok = q0 + r < tokens;
-    const size_t grow = (size_t)row_base + q0 + r;
-    // delta_i = dO_i . O_i (attn_delta_kernel) and L_i
-    float dl = 0.f, L = 0.f;
-    if (row_ok) {
-      L = lse[grow * heads + h];
-      dl = delta[grow * heads + h];
-    }
-    const float c1 = att_scale_of(HDV) * LOG2E, c2 = L * LOG2E;
-    // the row of Q (first four warps) or of dO (the other four): TMA tile -> TMEM A operand
-    if (warp == 2) DQ_STAMP(3, 0, 2);
-    mbar_wait(bar_q, 0);
-    if (warp == 2) DQ_STAMP(3, 0, 3);
-    if (h0 == 0) tile_to_tmem<HDV>(t_lane + T_QA, sQ, r);
-    else tile_to_tmem<HDV>(t_lane + T_DOA, sdO, r);
-    tmem_st_wait();
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(a_full);
-    if (warp == 2) DQ_STAMP(3, 1, 0);
-    for (int j = 0; j < nkb; ++j) {
-      const int b = j & 1;
-      if (warp == 2) DQ_STAMP(1, j, 0);
-      mbar_wait(&s_full[b], (j >> 1) & 1);
-      tc_fence_after();
-      if (warp == 2) DQ_STAMP(1, j, 1);
-      uint32_t sv[32], dp[32], pk[16];
-      tmem_ld32(t_lane + b * 128 + h0 * 32, sv);
-      tmem_ld32(t_lane + b * 128 + 64 + h0 * 32, dp);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        float p0 = ex2(fmaf(__uint_as_float(sv[2 * i]), c1, -c2)), p1 = ex2(fmaf(__uint_as_float(sv[2 * i + 1]), c1, -c2));
-        float d0 = p0 * (__uint_as_float(dp[2 * i]) - dl), d1 = p1 * (__uint_as_float(dp[2 * i + 1]) - dl);
-        pk[i] = pack_bf16(d0, d1);
-      }
-      if (warp == 2) DQ_STAMP(1, j, 2);
-      mbar_wait(&ds_empty[b], ((j >> 1) & 1) ^ 1);  // dQ(j-2) has read the tile (long ago)
-      tc_fence_after();
-      tmem_st16(t_lane + T_DS + b * 32 + h0 * 16, pk);
+    const float c1 = att_scale_of(HDV) * LOG2E;
+    // the row of Q (first four warps) or of dO (the other four) of item `it`: staging tile -> TMEM A operand.  Only once the S / dP
+    // MMAs of the previous item have completed (its last s_full has been seen by this thread).
+    auto rows_to_tmem = [&](int it) {
+      mbar_wait(bar_q, it & 1);
+      if (h0 == 0) tile_to_tmem<HDV>(t_lane + T_QA, sQ, r);
+      else tile_to_tmem<HDV>(t_lane + T_DOA, sdO, r);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&ds_full[b]);
-      if (warp == 2) DQ_STAMP(1, j, 3);
+      if (lane == 0) {
+        mbar_arrive(a_full);
+        mbar_arrive(stage_free);
+      }
+    };
+    // delta_i = dO_i . O_i (attn_delta_kernel) and L_i of this thread's row, requested one item ahead
+    auto row_stats = [&](int it, float& L, float& dl) {
+      int q0, h, row_base;
+      decode(it, q0, h, row_base);
+      L = 0.f, dl = 0.f;
+      if (q0 + r < tokens) {
+        const size_t grow = (size_t)row_base + q0 + r;
+        L = lse[grow * heads + h];
+        dl = delta[grow * heads + h];
+      }
+    };
+    float L_nxt = 0.f, dl_nxt = 0.f;
+    if (my_items > 0) {
+      row_stats(0, L_nxt, dl_nxt);
+      rows_to_tmem(0);
     }
-    // epilogue by the first four warps: a whole gradient row per thread (the q-norm backward needs its dot product with q^)
-    uint32_t a0[32], a1[32], tl[8];
-    if (h0 == 0) {
-      mbar_wait(o_full, 0);
-      tc_fence_after();
-      if (warp == 2) DQ_STAMP(3, 1, 1);
-      tmem_ld32(t_lane + T_DQ, a0);
-      tmem_ld32(t_lane + T_DQ + 32, a1);
-      if constexpr (HDV != 64) tmem_ld8(t_lane + T_DQ + 64, tl);
-      tmem_ld_wait();
-    }
-    if (row_ok && h0 == 0) {
-      bf16* dst = dqkv + grow * 3 * D + h * HDV;
-      if constexpr (HDV == 64) {
-        if (sc) store_out_row_qknorm(dst, qkv + grow * 3 * D + h * HDV, a0, a1, 0.125f, sc[grow * 2 * heads + h], eps);
-        else store_out_row(dst, a0, a1, 0.125f);
-      } else {
-        if (sc) store_acc_row_qknorm72(dst, qkv + grow * 3 * D + h * HDV, a0, a1, tl, att_scale_of(HDV), sc[grow * 2 * heads + h], eps);
-        else store_acc_row<HDV>(dst, a0, a1, tl, att_scale_of(HDV));
+    uint32_t g0 = 0;
+    for (int it = 0; it < my_items; ++it, g0 += nkb) {
+      int q0, h, row_base;
+      decode(it, q0, h, row_base);
+      const bool row_ok = q0 + r < tokens;
+      const size_t grow = (size_t)row_base + q0 + r;
+      const float dl = dl_nxt, c2 = L_nxt * LOG2E;
+      if (it + 1 < my_items) row_stats(it + 1, L_nxt, dl_nxt);
+      for (int j = 0; j < nkb; ++j) {
+        const uint32_t g = g0 + j, b = g & 1;
+        if (warp == 2) DQ_STAMP(1, g, 0);
+        mbar_wait(&s_full[b], (g >> 1) & 1);
+        tc_fence_after();
+        if (warp == 2) DQ_STAMP(1, g, 1);
+        uint32_t sv[32], dp[32], pk[16];
+        tmem_ld32(t_lane + b * 128 + h0 * 32, sv);
+        tmem_ld32(t_lane + b * 128 + 64 + h0 * 32, dp);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float p0 = ex2(fmaf(__uint_as_float(sv[2 * i]), c1, -c2)), p1 = ex2(fmaf(__uint_as_float(sv[2 * i + 1]), c1, -c2));
+          float d0 = p0 * (__uint_as_float(dp[2 * i]) - dl), d1 = p1 * (__uint_as_float(dp[2 * i + 1]) - dl);
+          pk[i] = pack_bf16(d0, d1);
+        }
+        if (warp == 2) DQ_STAMP(1, g, 2);
+        mbar_wait(&ds_empty[b], ((g >> 1) & 1) ^ 1);  // dQ of two blocks ago has read the tile (long ago)
+        tc_fence_after();
+        tmem_st16(t_lane + T_DS + b * 32 + h0 * 16, pk);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ds_full[b]);
+        if (warp == 2) DQ_STAMP(1, g, 3);
+      }
+      // the item's last S / dP MMAs have completed (we saw its last s_full): the A tiles may take the next item's rows.  Ahead of
+      // the read-out below, so that the tensor core has S / dP of the next item's first blocks to do meanwhile.
+      if (it + 1 < my_items) rows_to_tmem(it + 1);
+      if (warp == 2 && it < 16) DQ_STAMP(3, it, 0);
+      // read-out by the first four warps: a whole gradient row per thread (the q-norm backward needs its dot product with q^)
+      if (h0 == 0) {
+        uint32_t a0[32], a1[32], tl[8];
+        mbar_wait(o_full, it & 1);
+        tc_fence_after();
+        tmem_ld32(t_lane + T_DQ, a0);
+        tmem_ld32(t_lane + T_DQ + 32, a1);
+        if constexpr (HDV != 64) tmem_ld8(t_lane + T_DQ + 64, tl);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_free);
+        if (warp == 2 && it < 16) DQ_STAMP(3, it, 1);
+        if (row_ok) {
+          bf16* dst = dqkv + grow * 3 * D + h * HDV;
+          if constexpr (HDV == 64) {
+            if (sc) store_out_row_qknorm(dst, qkv + grow * 3 * D + h * HDV, a0, a1, 0.125f, sc[grow * 2 * heads + h], eps);
+            else store_out_row(dst, a0, a1, 0.125f);
+          } else {
+            if (sc) store_acc_row_qknorm72(dst, qkv + grow * 3 * D + h * HDV, a0, a1, tl, att_scale_of(HDV), sc[grow * 2 * heads + h], eps);
+            else store_acc_row<HDV>(dst, a0, a1, tl, att_scale_of(HDV));
+          }
+        }
+        if (warp == 2 && it < 16) DQ_STAMP(3, it, 2);
       }
     }
   }
-  if (warp == 2) DQ_STAMP(3, 1, 2);
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<B::TMEM>(tmem_base);
-  if (threadIdx.x == 32) DQ_STAMP(3, 1, 3);
 #undef DQ_STAMP
 }
 
 // ------------------------------------------------------------------------------------------------ dK, dV
 // Rows (TMEM lanes) are keys.  P^T and dS^T go back into TMEM in place, over the S^T and dP^T columns they were computed from, and are
-// the A operands of dV += P^T dO_j and dK += dS^T Q_j (see attn_bwd_dq_tc).
+// the A operands of dV += P^T dO_j and dK += dS^T Q_j.  Persistent over (key tile, head, sample) items like attn_bwd_dq_tc.
 template <int HDV>
 __global__ void __launch_bounds__(BCfg<HDV>::NTHR, 1)
 attn_bwd_dkv_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_constant__ CUtensorMap tm_qkv_blk,
                 const __grid_constant__ CUtensorMap tm_do_blk, const float* __restrict__ lse, const float* __restrict__ delta,
-                bf16* __restrict__ dqkv, int tokens, int heads, const bf16* __restrict__ qkv, const float* __restrict__ sc, float eps, long long* __restrict__ dbg) {
+                bf16* __restrict__ dqkv, int tokens, int heads, int n_samples, const bf16* __restrict__ qkv, const float* __restrict__ sc,
+                float eps, long long* __restrict__ dbg) {
   using B = BCfg<HDV>;
-  // optional timeline of one CTA of a middle wave, roles 4..7 of the buffer (see attn_bwd_dq_tc)
-#define DKV_STAMP(role, j, e)                                                                                         \
-  do {                                                                                                                \
-    if (dbg && (blockIdx.x | blockIdx.y) == 0 && blockIdx.z == gridDim.z / 2 && (j) < 64 && (threadIdx.x & 31) == 0) \
-      dbg[(4 + (role)) * 256 + 4 * (j) + (e)] = clock64();                                                          \
+  // optional timeline of CTA 0, roles 4..7 of the buffer (see attn_bwd_dq_tc)
+#define DKV_STAMP(role, g, e)                                                                                             \
+  do {                                                                                                                    \
+    if (dbg && blockIdx.x == 0 && (g) < 64 && (threadIdx.x & 31) == 0) dbg[(4 + (role)) * 256 + 4 * (g) + (e)] = clock64(); \
   } while (0)
-  if (threadIdx.x == 0) DKV_STAMP(3, 0, 0);
   constexpr int ROWB = B::ROWB, BLKB = B::BLKB, PROW = B::PROW, PBLK = B::PBLK, NST = B::DKV_NST, NSW = B::NSW;
   constexpr uint32_t T_DK = B::T_ACC, T_DV = T_DK + B::NACC, T_KA = T_DV + B::NACC, T_VA = T_KA + B::A_COLS;  // dK | dV | K, V as A operands
   static_assert(T_VA + B::A_COLS <= B::TMEM, "TMEM columns");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-  uint8_t* sK = smem;
+  uint8_t* sK = smem;         // staging of the next item's K / V tiles (TMA -> here -> TMEM)
   uint8_t* sV = sK + ROWB;
   uint8_t* sQdO = sV + ROWB;  // stage s: Q_j at sQdO + s*2*BLKB, dO_j after it
   float* sL = reinterpret_cast<float*>(sQdO + NST * 2 * BLKB);  // [2][64]
   float* sD = sL + 2 * CB;                                       // [2][64]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sD + 2 * CB);
-  uint64_t* bar_kv = bars;
+  uint64_t* bar_kv = bars;               // an item's K / V tiles have landed in the staging tiles
   uint64_t* qd_full = bars + 1;          // [NST]
   uint64_t* qd_empty = qd_full + NST;    // [NST]
   uint64_t* s_full = qd_empty + NST;     // [2]
   uint64_t* p_full = s_full + 2;         // [2]
-  uint64_t* o_full = p_full + 2;
-  uint64_t* a_full = o_full + 1;         // K and V are in TMEM
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + 1);
+  uint64_t* o_full = p_full + 2;         // an item's dK and dV are complete
+  uint64_t* a_full = o_full + 1;         // an item's K and V are in TMEM
+  uint64_t* stage_free = a_full + 1;     // ... and the staging tiles may take the next item's
+  uint64_t* acc_free = stage_free + 1;   // an item's dK and dV have been read out
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_free + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kt = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
-  const int D = heads * HDV, k0 = kt * RT, nqb = tokens / CB, row_base = n * tokens;
+  const int D = heads * HDV, nqb = tokens / CB, nkt = (tokens + RT - 1) / RT;
+  const int total_items = nkt * heads * n_samples;
+  const int my_items = (int)blockIdx.x < total_items ? (total_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  auto decode = [&](int it, int& k0, int& h, int& row_base) {
+    const int item = blockIdx.x + it * gridDim.x;
+    const int kt = item % nkt, rest = item / nkt;
+    h = rest % heads;
+    row_base = (rest / heads) * tokens;
+    k0 = kt * RT;
+  };
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tm_qkv_row);
@@ -509,6 +585,8 @@ attn_bwd_dkv_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_con
     }
     mbar_init(o_full, 1);
     mbar_init(a_full, NSW);
+    mbar_init(stage_free, NSW);
+    mbar_init(acc_free, NSW);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<B::TMEM>(tmem_slot);
@@ -516,29 +594,46 @@ attn_bwd_dkv_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
-  if (threadIdx.x == 0) DKV_STAMP(3, 0, 1);
 
-  if (warp == 0 && lane == 0) {
-    mbar_arrive_expect_tx(bar_kv, 2 * ROWB);
-    load_tile<HDV>(sK, &tm_qkv_row, bar_kv, 1, h, heads, row_base + k0, PROW);
-    load_tile<HDV>(sV, &tm_qkv_row, bar_kv, 2, h, heads, row_base + k0, PROW);
-    for (int j = 0; j < nqb; ++j) {
-      const int s = j % NST;
-      mbar_wait(&qd_empty[s], ((j / NST) & 1) ^ 1);
-      DKV_STAMP(2, j, 0);
-      uint8_t* dst = sQdO + s * 2 * BLKB;
-      mbar_arrive_expect_tx(&qd_full[s], 2 * BLKB);
-      load_tile<HDV>(dst, &tm_qkv_blk, &qd_full[s], 0, h, heads, row_base + j * CB, PBLK);
-      load_tile<HDV>(dst + BLKB, &tm_do_blk, &qd_full[s], 0, h, heads, row_base + j * CB, PBLK);
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------------------------------------------------------- TMA producer
+      auto load_rows = [&](int it) {
+        int k0, h, row_base;
+        decode(it, k0, h, row_base);
+        mbar_arrive_expect_tx(bar_kv, 2 * ROWB);
+        load_tile<HDV>(sK, &tm_qkv_row, bar_kv, 1, h, heads, row_base + k0, PROW);
+        load_tile<HDV>(sV, &tm_qkv_row, bar_kv, 2, h, heads, row_base + k0, PROW);
+      };
+      if (my_items > 0) load_rows(0);
+      uint32_t g = 0;
+      for (int it = 0; it < my_items; ++it) {
+        int k0, h, row_base;
+        decode(it, k0, h, row_base);
+        for (int j = 0; j < nqb; ++j, ++g) {
+          const int s = g % NST;
+          mbar_wait(&qd_empty[s], ((g / NST) & 1) ^ 1);
+          DKV_STAMP(2, g, 0);
+          uint8_t* dst = sQdO + s * 2 * BLKB;
+          mbar_arrive_expect_tx(&qd_full[s], 2 * BLKB);
+          load_tile<HDV>(dst, &tm_qkv_blk, &qd_full[s], 0, h, heads, row_base + j * CB, PBLK);
+          load_tile<HDV>(dst + BLKB, &tm_do_blk, &qd_full[s], 0, h, heads, row_base + j * CB, PBLK);
+        }
+        if (it + 1 < my_items) {
+          mbar_wait(stage_free, it & 1);
+          load_rows(it + 1);
+        }
+      }
     }
   } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
     const bool leader = elect_one();  // whole warp runs the loop, one lane issues (see tc_common.cuh)
     constexpr uint32_t idesc_s = make_idesc_bf16(RT, CB, 0, 0);       // S^T = K Q_j^T, dP^T = V dO_j^T
     constexpr uint32_t idesc_a = make_idesc_bf16(RT, B::NACC, 0, 1);  // dV += P^T dO_j, dK += dS^T Q_j : A from TMEM, B MN-major
     const uint64_t d_qd = make_smem_desc(smem_u32(sQdO), 16, 1024);      // K-major view of a Q / dO block (S^T, dP^T)
     const uint64_t d_qdmn = make_smem_desc(smem_u32(sQdO), PBLK, 1024);  // MN-major view (dK, dV): LBO = panel stride
-    auto scores = [&](int j) {  // qd_full of the block's ring slot has been waited for
-      const int s = j % NST, b = j & 1;
+    auto scores = [&](uint32_t g) {  // qd_full of the block's ring slot has been waited for
+      const uint32_t s = g % NST, b = g & 1;
       const uint64_t d_q = desc_advance(d_qd, s * 2 * BLKB), d_do = desc_advance(d_q, BLKB);
       const uint32_t t_s = tmem_base + b * 128;
 #pragma unroll
@@ -549,126 +644,156 @@ attn_bwd_dkv_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_con
       }
       if (leader) umma_commit(&s_full[b]);
     };
-    mbar_wait(a_full, 0);
-    tc_fence_after();
-    mbar_wait(&qd_full[0], 0);
-    scores(0);
-    if (nqb > 1) mbar_wait(&qd_full[1 % NST], (1 / NST) & 1);
-    for (int j = 0; j < nqb; ++j) {
-      const int s = j % NST, b = j & 1;
-      DKV_STAMP(0, j, 3);
-      if (j + 1 < nqb) scores(j + 1);
-      // the ring wait of block j+2 in the shadow of the softmax warps' work on block j (see attn_bwd_dq_tc)
-      if (j + 2 < nqb) mbar_wait(&qd_full[(j + 2) % NST], ((j + 2) / NST) & 1);
-      DKV_STAMP(0, j, 0);
-      mbar_wait_spin(&p_full[b], (j >> 1) & 1);
+    uint32_t g0 = 0;
+    for (int it = 0; it < my_items; ++it, g0 += nqb) {
+      mbar_wait(a_full, it & 1);
       tc_fence_after();
-      DKV_STAMP(0, j, 1);
-      const uint64_t d_q = desc_advance(d_qdmn, s * 2 * BLKB), d_do = desc_advance(d_q, BLKB);
-      const uint32_t t_p = tmem_base + b * 128;  // P^T over the S^T columns, dS^T over the dP^T columns
+      mbar_wait(&qd_full[g0 % NST], (g0 / NST) & 1);
+      scores(g0);
+      if (nqb > 1) mbar_wait(&qd_full[(g0 + 1) % NST], ((g0 + 1) / NST) & 1);
+      for (int j = 0; j < nqb; ++j) {
+        const uint32_t g = g0 + j, s = g % NST, b = g & 1;
+        DKV_STAMP(0, g, 3);
+        if (j + 1 < nqb) scores(g + 1);  // into the other buffer: its P^T / dS^T were read by the MMAs of block j-1, issued before this
+        // the ring wait of block j+2 in the shadow of the softmax warps' work on block j (see attn_bwd_dq_tc)
+        if (j + 2 < nqb) mbar_wait(&qd_full[(g + 2) % NST], ((g + 2) / NST) & 1);
+        DKV_STAMP(0, g, 0);
+        mbar_wait_spin(&p_full[b], (g >> 1) & 1);
+        tc_fence_after();
+        DKV_STAMP(0, g, 1);
+        if (j == 0 && it > 0) {  // the previous item's dK / dV have been read out of the accumulators
+          mbar_wait(acc_free, (it - 1) & 1);
+          tc_fence_after();
+        }
+        const uint64_t d_q = desc_advance(d_qdmn, s * 2 * BLKB), d_do = desc_advance(d_q, BLKB);
+        const uint32_t t_p = tmem_base + b * 128;  // P^T over the S^T columns, dS^T over the dP^T columns
 #pragma unroll
-      for (int k = 0; k < CB / 16; ++k) {  // dV and dK chains interleaved
-        const uint32_t ko = (k >> 1) * 32 + (k & 1) * 8;
-        if (leader) umma_ts(tmem_base + T_DV, t_p + ko, desc_advance(d_do, k * 2048), idesc_a, (j | k) != 0);
-        if (leader) umma_ts(tmem_base + T_DK, t_p + 64 + ko, desc_advance(d_q, k * 2048), idesc_a, (j | k) != 0);
+        for (int k = 0; k < CB / 16; ++k) {  // dV and dK chains interleaved
+          const uint32_t ko = (k >> 1) * 32 + (k & 1) * 8;
+          if (leader) umma_ts(tmem_base + T_DV, t_p + ko, desc_advance(d_do, k * 2048), idesc_a, (j | k) != 0);
+          if (leader) umma_ts(tmem_base + T_DK, t_p + 64 + ko, desc_advance(d_q, k * 2048), idesc_a, (j | k) != 0);
+        }
+        if (leader) umma_commit(&qd_empty[s]);
+        DKV_STAMP(0, g, 2);
       }
-      if (leader) umma_commit(&qd_empty[s]);
-      DKV_STAMP(0, j, 2);
+      if (leader) umma_commit(o_full);
     }
-    if (leader) umma_commit(o_full);
-  } else if (warp >= 2) {
+  } else {
+    // ------------------------------------------------------------------ softmax warps / epilogue
     const int qq = warp & 3;
     const int h0 = (warp - 2) >> 2;    // which 32 of the 64 query columns of a block this warp owns
     const int r = qq * 32 + lane;      // key row of the tile
     const int tid = threadIdx.x - 64;  // 0..255 among the softmax warps
     const uint32_t t_lane = tmem_base + ((uint32_t)(qq * 32) << 16);
     const float c1 = att_scale_of(HDV) * LOG2E;
-    // per-query L (threads 0-63) and delta (64-127) of a block: 64 different lines of global memory each.  The values of block j+1
-    // are requested while block j is processed (ncu: 11 % of this kernel's stall samples sat on these loads and the barrier behind them)
-    // (nothing may depend on the loaded value before the next block's store: the first version multiplied by log2 e right behind the load
-    // and the warp sat out the load latency, 1 100 cycles per block, on that multiply)
-    auto fetch = [&](int j) {
-      const size_t qrow = (size_t)row_base + j * CB + (tid & 63);
-      return tid < 64 ? lse[qrow * heads + h] : delta[qrow * heads + h];
-    };
-    float ld_val = tid < 128 ? fetch(0) : 0.f;
-    // the row of K (first four warps) or of V (the other four): TMA tile -> TMEM A operand
-    if (warp == 2) DKV_STAMP(3, 0, 2);
-    mbar_wait(bar_kv, 0);
-    if (warp == 2) DKV_STAMP(3, 0, 3);
-    if (h0 == 0) tile_to_tmem<HDV>(t_lane + T_KA, sK, r);
-    else tile_to_tmem<HDV>(t_lane + T_VA, sV, r);
-    tmem_st_wait();
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(a_full);
-    if (warp == 2) DKV_STAMP(3, 1, 0);
-    for (int j = 0; j < nqb; ++j) {
-      const int s = j & 1;
-      // -> smem (double-buffered), visible to the softmax threads
-      if (tid < 64) sL[s * CB + tid] = ld_val * LOG2E;
-      else if (tid < 128) sD[s * CB + (tid - 64)] = ld_val;
-      if (j + 1 < nqb && tid < 128) ld_val = fetch(j + 1);
-      asm volatile("bar.sync 1, %0;" ::"n"(NSW * 32) : "memory");
-      const int b = j & 1;
-      if (warp == 2) DKV_STAMP(1, j, 0);
-      mbar_wait(&s_full[b], (j >> 1) & 1);
-      tc_fence_after();
-      if (warp == 2) DKV_STAMP(1, j, 1);
-      uint32_t sv[32], dp[32], pp[16], pd[16];
-      tmem_ld32(t_lane + b * 128 + h0 * 32, sv);
-      tmem_ld32(t_lane + b * 128 + 64 + h0 * 32, dp);
-      tmem_ld_wait();
-      const float4* pL = reinterpret_cast<const float4*>(sL + s * CB + h0 * 32);
-      const float4* pD = reinterpret_cast<const float4*>(sD + s * CB + h0 * 32);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {  // four query columns per trip: L and delta as one 16-byte broadcast read each
-        const float4 l4 = pL[i], d4 = pD[i];
-        float p0 = ex2(fmaf(__uint_as_float(sv[4 * i]), c1, -l4.x)), p1 = ex2(fmaf(__uint_as_float(sv[4 * i + 1]), c1, -l4.y));
-        float p2 = ex2(fmaf(__uint_as_float(sv[4 * i + 2]), c1, -l4.z)), p3 = ex2(fmaf(__uint_as_float(sv[4 * i + 3]), c1, -l4.w));
-        pp[2 * i] = pack_bf16(p0, p1);
-        pp[2 * i + 1] = pack_bf16(p2, p3);
-        pd[2 * i] = pack_bf16(p0 * (__uint_as_float(dp[4 * i]) - d4.x), p1 * (__uint_as_float(dp[4 * i + 1]) - d4.y));
-        pd[2 * i + 1] = pack_bf16(p2 * (__uint_as_float(dp[4 * i + 2]) - d4.z), p3 * (__uint_as_float(dp[4 * i + 3]) - d4.w));
-      }
-      // in place, over columns only this thread reads: 32 queries = 16 packed columns at the start of the warp's 32-column group
-      if (warp == 2) DKV_STAMP(1, j, 2);
-      tmem_st16(t_lane + b * 128 + h0 * 32, pp);
-      tmem_st16(t_lane + b * 128 + 64 + h0 * 32, pd);
+    // the row of K (first four warps) or of V (the other four) of item `it`: staging tile -> TMEM A operand, once the S^T / dP^T MMAs
+    // of the previous item have completed (its last s_full has been seen by this thread)
+    auto rows_to_tmem = [&](int it) {
+      mbar_wait(bar_kv, it & 1);
+      if (h0 == 0) tile_to_tmem<HDV>(t_lane + T_KA, sK, r);
+      else tile_to_tmem<HDV>(t_lane + T_VA, sV, r);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[b]);
-      if (warp == 2) DKV_STAMP(1, j, 3);
-    }
-    mbar_wait(o_full, 0);
-    tc_fence_after();
-    if (warp == 2) DKV_STAMP(3, 1, 1);
-    uint32_t a0[32], a1[32], tl[8];
-    const bool row_ok = k0 + r < tokens;
-    const size_t grow = (size_t)row_base + k0 + r;
-    // the first four warps write dK, the other four dV
-    tmem_ld32(t_lane + (h0 == 0 ? T_DK : T_DV), a0);
-    tmem_ld32(t_lane + (h0 == 0 ? T_DK : T_DV) + 32, a1);
-    if constexpr (HDV != 64) tmem_ld8(t_lane + (h0 == 0 ? T_DK : T_DV) + 64, tl);
-    tmem_ld_wait();
-    if (row_ok && h0 == 0) {
-      bf16* dst = dqkv + grow * 3 * D + D + h * HDV;
-      if constexpr (HDV == 64) {
-        if (sc) store_out_row_qknorm(dst, qkv + grow * 3 * D + D + h * HDV, a0, a1, 0.125f, sc[grow * 2 * heads + heads + h], eps);
-        else store_out_row(dst, a0, a1, 0.125f);
-      } else {
-        if (sc) store_acc_row_qknorm72(dst, qkv + grow * 3 * D + D + h * HDV, a0, a1, tl, att_scale_of(HDV), sc[grow * 2 * heads + heads + h], eps);
-        else store_acc_row<HDV>(dst, a0, a1, tl, att_scale_of(HDV));
+      if (lane == 0) {
+        mbar_arrive(a_full);
+        mbar_arrive(stage_free);
       }
+    };
+    // per-query L (threads 0-63) and delta (64-127) of a block: 64 different lines of global memory each.  The values of the CTA's next
+    // block (of the next item behind an item's last) are requested while the current one is processed.  (Nothing may depend on the
+    // loaded value before the next block's store: the first version multiplied by log2 e right behind the load and the warp sat out the
+    // load latency, 1 100 cycles per block, on that multiply.)
+    auto fetch = [&](int it, int j) {
+      int k0, h, row_base;
+      decode(it, k0, h, row_base);
+      const size_t qrow = (size_t)row_base + j * CB + (tid & 63);
+      return tid < 64 ? lse[qrow * heads + h] : delta[qrow * heads + h];
+    };
+    float ld_val = 0.f;
+    if (my_items > 0) {
+      if (tid < 128) ld_val = fetch(0, 0);
+      rows_to_tmem(0);
     }
-    if (row_ok && h0 == 1) store_acc_row<HDV>(dqkv + grow * 3 * D + 2 * D + h * HDV, a0, a1, tl, 1.0f);
+    uint32_t g0 = 0;
+    for (int it = 0; it < my_items; ++it, g0 += nqb) {
+      int k0, h, row_base;
+      decode(it, k0, h, row_base);
+      for (int j = 0; j < nqb; ++j) {
+        const uint32_t g = g0 + j;
+        const int s = g & 1, b = g & 1;
+        // -> smem (double-buffered), visible to the softmax threads
+        if (tid < 64) sL[s * CB + tid] = ld_val * LOG2E;
+        else if (tid < 128) sD[s * CB + (tid - 64)] = ld_val;
+        if (tid < 128) {
+          if (j + 1 < nqb) ld_val = fetch(it, j + 1);
+          else if (it + 1 < my_items) ld_val = fetch(it + 1, 0);
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(NSW * 32) : "memory");
+        if (warp == 2) DKV_STAMP(1, g, 0);
+        mbar_wait(&s_full[b], (g >> 1) & 1);
+        tc_fence_after();
+        if (warp == 2) DKV_STAMP(1, g, 1);
+        uint32_t sv[32], dp[32], pp[16], pd[16];
+        tmem_ld32(t_lane + b * 128 + h0 * 32, sv);
+        tmem_ld32(t_lane + b * 128 + 64 + h0 * 32, dp);
+        tmem_ld_wait();
+        const float4* pL = reinterpret_cast<const float4*>(sL + s * CB + h0 * 32);
+        const float4* pD = reinterpret_cast<const float4*>(sD + s * CB + h0 * 32);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {  // four query columns per trip: L and delta as one 16-byte broadcast read each
+          const float4 l4 = pL[i], d4 = pD[i];
+          float p0 = ex2(fmaf(__uint_as_float(sv[4 * i]), c1, -l4.x)), p1 = ex2(fmaf(__uint_as_float(sv[4 * i + 1]), c1, -l4.y));
+          float p2 = ex2(fmaf(__uint_as_float(sv[4 * i + 2]), c1, -l4.z)), p3 = ex2(fmaf(__uint_as_float(sv[4 * i + 3]), c1, -l4.w));
+          pp[2 * i] = pack_bf16(p0, p1);
+          pp[2 * i + 1] = pack_bf16(p2, p3);
+          pd[2 * i] = pack_bf16(p0 * (__uint_as_float(dp[4 * i]) - d4.x), p1 * (__uint_as_float(dp[4 * i + 1]) - d4.y));
+          pd[2 * i + 1] = pack_bf16(p2 * (__uint_as_float(dp[4 * i + 2]) - d4.z), p3 * (__uint_as_float(dp[4 * i + 3]) - d4.w));
+        }
+        // in place, over columns only this thread reads: 32 queries = 16 packed columns at the start of the warp's 32-column group
+        if (warp == 2) DKV_STAMP(1, g, 2);
+        tmem_st16(t_lane + b * 128 + h0 * 32, pp);
+        tmem_st16(t_lane + b * 128 + 64 + h0 * 32, pd);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[b]);
+        if (warp == 2) DKV_STAMP(1, g, 3);
+      }
+      // the item's last S^T / dP^T MMAs have completed: the A tiles may take the next item's rows, ahead of the read-out below
+      if (it + 1 < my_items) rows_to_tmem(it + 1);
+      if (warp == 2 && it < 16) DKV_STAMP(3, it, 0);
+      mbar_wait(o_full, it & 1);
+      tc_fence_after();
+      uint32_t a0[32], a1[32], tl[8];
+      const bool row_ok = k0 + r < tokens;
+      const size_t grow = (size_t)row_base + k0 + r;
+      // the first four warps write dK, the other four dV
+      tmem_ld32(t_lane + (h0 == 0 ? T_DK : T_DV), a0);
+      tmem_ld32(t_lane + (h0 == 0 ? T_DK : T_DV) + 32, a1);
+      if constexpr (HDV != 64) tmem_ld8(t_lane + (h0 == 0 ? T_DK : T_DV) + 64, tl);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_free);
+      if (warp == 2 && it < 16) DKV_STAMP(3, it, 1);
+      if (row_ok && h0 == 0) {
+        bf16* dst = dqkv + grow * 3 * D + D + h * HDV;
+        if constexpr (HDV == 64) {
+          if (sc) store_out_row_qknorm(dst, qkv + grow * 3 * D + D + h * HDV, a0, a1, 0.125f, sc[grow * 2 * heads + heads + h], eps);
+          else store_out_row(dst, a0, a1, 0.125f);
+        } else {
+          if (sc) store_acc_row_qknorm72(dst, qkv + grow * 3 * D + D + h * HDV, a0, a1, tl, att_scale_of(HDV), sc[grow * 2 * heads + heads + h], eps);
+          else store_acc_row<HDV>(dst, a0, a1, tl, att_scale_of(HDV));
+        }
+      }
+      if (row_ok && h0 == 1) store_acc_row<HDV>(dqkv + grow * 3 * D + 2 * D + h * HDV, a0, a1, tl, 1.0f);
+      if (warp == 2 && it < 16) DKV_STAMP(3, it, 2);
+    }
   }
-  if (warp == 2) DKV_STAMP(3, 1, 2);
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<B::TMEM>(tmem_base);
-  if (threadIdx.x == 32) DKV_STAMP(3, 1, 3);
 #undef DKV_STAMP
 }
 
@@ -2057,6 +2182,15 @@ extern "C" int mapdit_qk_norm_bwd(void* dqkv, const void* qkv, const float* sc, 
                                   void* stream);
 
 // head_dim 72 (DiT-XL): the dq + dkv kernel pair on two-panel operand tiles, 3-D tensor maps {72 channels, heads, rows}
+// grid of the persistent dq / dkv kernels: one CTA per SM (or per item if there are fewer)
+static int pair_grid(int tokens, int heads, int n_samples) {
+  int sms = 148, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long items = (long long)((tokens + RT - 1) / RT) * heads * n_samples;
+  return (int)(items < sms ? items : sms);
+}
+
 static int attn_bwd_pair72(const void* qkv, const void* o, const void* dout, const float* lse, const float* sc, float eps, void* dqkv,
                            float* delta, int n_samples, int tokens, int heads, void* stream) {
   MAPDIT_REQUIRE(o != nullptr, "cos_attn_bwd: o is required for head_dim 72");
@@ -2084,14 +2218,14 @@ static int attn_bwd_pair72(const void* qkv, const void* o, const void* dout, con
     attr_set = true;
   }
   cudaStream_t s = (cudaStream_t)stream;
-  dim3 grid((tokens + RT - 1) / RT, heads, n_samples);
+  const int grid = pair_grid(tokens, heads, n_samples);  // persistent: one CTA per SM over (row tile, head, sample) items
   launch_delta<72>(o, dout, delta, (long long)rows * heads, s);
   MAPDIT_LAUNCH_CHECK("cos_attn_bwd(delta, hd 72)");
-  attn_bwd_dq_tc<72><<<grid, BCfg<72>::NTHR, BCfg<72>::DQ_SMEM, s>>>(t_qkv_row, t_qkv_blk, t_do_row, lse, delta,
-                                                             (bf16*)dqkv, tokens, heads, (const bf16*)qkv, sc, eps, g_attn_dbg);
+  attn_bwd_dq_tc<72><<<grid, BCfg<72>::NTHR, BCfg<72>::DQ_SMEM, s>>>(t_qkv_row, t_qkv_blk, t_do_row, lse, delta, (bf16*)dqkv, tokens, heads,
+                                                                   n_samples, (const bf16*)qkv, sc, eps, g_attn_dbg);
   MAPDIT_LAUNCH_CHECK("cos_attn_bwd(dq, hd 72)");
   attn_bwd_dkv_tc<72><<<grid, BCfg<72>::NTHR, BCfg<72>::DKV_SMEM, s>>>(t_qkv_row, t_qkv_blk, t_do_blk, lse, delta, (bf16*)dqkv, tokens, heads,
-                                                               (const bf16*)qkv, sc, eps, g_attn_dbg);
+                                                                     n_samples, (const bf16*)qkv, sc, eps, g_attn_dbg);
   MAPDIT_LAUNCH_CHECK("cos_attn_bwd(dkv, hd 72)");
   return MAPDIT_OK;
 }
@@ -2190,14 +2324,14 @@ static int attn_bwd_impl(const void* qkv, const void* o, const void* dout, const
     MAPDIT_LAUNCH_CHECK("cos_attn_bwd(fused)");
     return MAPDIT_OK;
   }
-  dim3 grid((tokens + RT - 1) / RT, heads, n_samples);
+  const int grid = pair_grid(tokens, heads, n_samples);
   launch_delta<64>(o, dout, delta, (long long)rows * heads, s);
   MAPDIT_LAUNCH_CHECK("cos_attn_bwd(delta)");
-  attn_bwd_dq_tc<64><<<grid, BCfg<64>::NTHR, BCfg<64>::DQ_SMEM, s>>>(t_qkv_row, t_qkv_blk, t_do_row, lse, delta,
-                                                 (bf16*)dqkv, tokens, heads, (const bf16*)qkv, sc, eps, g_attn_dbg);
+  attn_bwd_dq_tc<64><<<grid, BCfg<64>::NTHR, BCfg<64>::DQ_SMEM, s>>>(t_qkv_row, t_qkv_blk, t_do_row, lse, delta, (bf16*)dqkv, tokens, heads,
+                                                                   n_samples, (const bf16*)qkv, sc, eps, g_attn_dbg);
   MAPDIT_LAUNCH_CHECK("cos_attn_bwd(dq)");
   attn_bwd_dkv_tc<64><<<grid, BCfg<64>::NTHR, BCfg<64>::DKV_SMEM, s>>>(t_qkv_row, t_qkv_blk, t_do_blk, lse, delta, (bf16*)dqkv, tokens, heads,
-                                                   (const bf16*)qkv, sc, eps, g_attn_dbg);
+                                                                     n_samples, (const bf16*)qkv, sc, eps, g_attn_dbg);
   MAPDIT_LAUNCH_CHECK("cos_attn_bwd(dkv)");
   return MAPDIT_OK;
 }

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Timeline of one CTA (middle wave) of attn_bwd_dq_tc<72> (DiT-XL/2 @ 64x64 shapes; clock64 stamps, developer tool): per key block j, when the MMA
+"""Timeline of CTA 0 of the persistent attn_bwd_dq_tc<72> / attn_bwd_dkv_tc<72> (DiT-XL/2 @ 64x64 shapes; clock64 stamps, developer tool): per key block j, when the MMA
 warp had issued S/dP of j+1, saw dS of j and had issued the dQ MMAs; when softmax warp 2 started waiting for S, saw it, finished
 the exp pass and published dS; when the TMA producer saw the ring slot of block j free."""
 import ctypes as C
@@ -31,14 +31,15 @@ L.mapdit_attn_debug_buffer(None)
 def show(d, name):
     t0 = int(d[d > 0].min())
     rel = lambda v: int(v) - t0 if int(v) else -1
-    print(f"---- {name}")
-    print("  j | MMA: loop top, ring slot j+2 seen, tile(j) seen, MMAs issued | softmax w2: wait S, S seen, exp done, published | TMA: slot free")
-    for j in range(T // 64):
-        m, s, t = d[0, j], d[1, j], d[2, j]
-        print(f"{j:3d} | {rel(m[3]):7d} {rel(m[0]):7d} {rel(m[1]):7d} {rel(m[2]):7d} | {rel(s[0]):7d} {rel(s[1]):7d} {rel(s[2]):7d} {rel(s[3]):7d} | {rel(t[0]):7d}")
-    c = d[3]
-    print("CTA: entry, init done | softmax w2: prologue loads done, resident tiles seen, A operands in TMEM | accumulators complete, epilogue stored, exit")
-    print(f"   {rel(c[0][0])} {rel(c[0][1])} | {rel(c[0][2])} {rel(c[0][3])} {rel(c[1][0])} | {rel(c[1][1])} {rel(c[1][2])} {rel(c[1][3])}")
+    print(f"---- {name}: CTA 0, blocks counted across its items ({T // 64} per item)")
+    print("  g | MMA: loop top, ring slot g+2 seen, tile(g) seen, MMAs issued | softmax w2: wait S, S seen, exp done, published | TMA: slot free")
+    for g in range(2 * T // 64 + 4):
+        m, s, t = d[0, g], d[1, g], d[2, g]
+        print(f"{g:3d} | {rel(m[3]):7d} {rel(m[0]):7d} {rel(m[1]):7d} {rel(m[2]):7d} | {rel(s[0]):7d} {rel(s[1]):7d} {rel(s[2]):7d} {rel(s[3]):7d} | {rel(t[0]):7d}")
+    print("item | softmax w2: next item's rows in TMEM, accumulators in registers, stored")
+    for it in range(4):
+        c = d[3, it]
+        print(f"{it:4d} | {rel(c[0]):7d} {rel(c[1]):7d} {rel(c[2]):7d}")
 
 
 allr = dbg.cpu().view(8, 64, 4)
