@@ -34,7 +34,7 @@ def test_gemm_bf16_tn(m, n, k):
 
 @pytest.mark.parametrize("N,T,H,hd,dtype", [(2, 64, 3, 64, torch.float32), (1, 256, 2, 64, torch.float32), (1, 80, 2, 72, torch.float32),
                                              (2, 128, 2, 64, torch.bfloat16), (1, 256, 2, 64, torch.bfloat16),
-                                             (30, 256, 6, 64, torch.bfloat16)])
+                                             (30, 256, 6, 64, torch.bfloat16), (40, 192, 4, 64, torch.bfloat16)])
 def test_attention_backward(N, T, H, hd, dtype):
     from mapdit_b200 import ops
     D = H * hd
@@ -562,7 +562,10 @@ def test_two_rank_data_parallel_matches_single_process():
     assert res["replicas_bit_identical"] and res["train_param_rel_l2_worst"] < 2e-3 and res["sample_rel_l2"] < 1e-5
 
 
-@pytest.mark.parametrize("N,T,H", [(2, 128, 3), (1, 1024, 2), (3, 256, 16), (2, 192, 4)])
+# the last three: more (row tile, head, sample) items than SMs, so the persistent CTAs walk several items each -- with an odd number of
+# 64-row blocks per item (T = 192, 64: the S / dP buffer parity and the ring slot of an item's first block change from item to item),
+# partial row tiles (T % 128 != 0) and single-block items (T = 64)
+@pytest.mark.parametrize("N,T,H", [(2, 128, 3), (1, 1024, 2), (3, 256, 16), (2, 192, 4), (5, 512, 16), (11, 192, 8), (9, 64, 17)])
 def test_attention_backward_head_dim_72_tcgen05(N, T, H):
     """DiT-XL's head_dim 72: dq + dkv tcgen05 kernel pair on two-panel operand tiles (3-D TMA maps zero-fill channels 72..127),
     80-column accumulators, q/k-normalisation backward fused into the dq / dk read-out; vs fp64 autograd through
