@@ -48,7 +48,13 @@ struct ACfg {
   static constexpr int QBUF = HDV == 64 ? 2 : 1;                // query buffers (the two-panel tiles leave room for one)
   static constexpr int NS = HDV == 64 ? (KB == 64 ? 4 : 3) : 2;  // K/V stages
   static constexpr int RS_BYTES = HDV == 64 ? 0 : 2 * 2 * QT * 4;  // row sums [item parity][tile][row] (no ones panel at 72)
-  static constexpr int SMEM_BYTES = QBUF * Q_BYTES + NS * KV_BYTES + ONES_BYTES + RS_BYTES + 1024 + 512;
+  // output staging: a finished O row is normalised in registers, written into a SWIZZLE_128B tile and leaves through per-warp TMA
+  // stores of 32-row slabs (row-per-thread 16-byte global stores are 32 line transactions per instruction; they cost the kernel 7 %,
+  // mostly by slowing the softmax warps' shared-memory traffic while an item's O was written).  64 channels: one tile per query
+  // tile; 72: one tile + a dense [128 x 8] tail (channels 64..71) shared by both query tiles.
+  static constexpr int OUT_TILE = QT * 128;
+  static constexpr int OUT_BYTES = HDV == 64 ? 2 * OUT_TILE : OUT_TILE + QT * 16;
+  static constexpr int SMEM_BYTES = QBUF * Q_BYTES + NS * KV_BYTES + OUT_BYTES + ONES_BYTES + RS_BYTES + 1024 + 512;
 };
 constexpr int NTHREADS = 15 * 32;
 constexpr int W_EPI = 8, W_TMA = 12, W_MMA = 13;  // warps 13 and 14 issue the MMAs of tile A and tile B
@@ -68,8 +74,9 @@ __device__ __forceinline__ void tmem_ld1(uint32_t taddr, uint32_t& v) {
 
 template <int HD>
 __global__ void __launch_bounds__(NTHREADS, 1)
-attn_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, bf16* __restrict__ o,
-                float* __restrict__ lse, int tokens, int heads, int n_samples, long long* __restrict__ dbg) {
+attn_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
+                const __grid_constant__ CUtensorMap tm_o, const __grid_constant__ CUtensorMap tm_o_tail, float* __restrict__ lse, int tokens,
+                int heads, int n_samples, long long* __restrict__ dbg) {
   using A = ACfg<HD>;
   constexpr int Q_BYTES = A::Q_BYTES, K_BYTES = A::K_BYTES, KV_BYTES = A::KV_BYTES, ONES_BYTES = A::ONES_BYTES, NS = A::NS, QBUF = A::QBUF;
   constexpr int PANEL_Q = QT * 128, PANEL_K = KB * 128;  // bytes of one 64-channel panel of a query tile / a key block
@@ -83,7 +90,8 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   uint8_t* sQ = smem;                       // [QBUF buffers][tile A | tile B], a tile = PANELS x [128 x 64]
   uint8_t* sKV = sQ + QBUF * Q_BYTES;       // stage s: K at sKV + s*KV_BYTES, V right after
-  uint8_t* sOnes = sKV + NS * KV_BYTES;
+  uint8_t* sOut = sKV + NS * KV_BYTES;      // output staging tile(s), then (head_dim 72) the tail
+  uint8_t* sOnes = sOut + A::OUT_BYTES;
   float* sRS = reinterpret_cast<float*>(sOnes + ONES_BYTES);  // head_dim 72 only
   uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + ONES_BYTES + A::RS_BYTES);
   uint64_t* q_full = bars;              // [2]
@@ -110,6 +118,8 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   if (warp == W_TMA && lane == 0) {
     prefetch_tmap(&tm_q);
     prefetch_tmap(&tm_kv);
+    prefetch_tmap(&tm_o);
+    if constexpr (HD != 64) prefetch_tmap(&tm_o_tail);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&q_full[i], 1);
       mbar_init(&q_empty[i], 2);
@@ -304,7 +314,16 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         else total = sRS[((it & 1) * 2 + x) * QT + qq * 32 + lane];  // written before the last P was published (ordered by the barriers)
         const float inv = 1.0f / total;
         if (lse) lse[grow * heads + h] = sqrt_hd + logf(total);
-        bf16* dst = o + grow * D + h * HD;
+        // this warp's 32-row slab of the staging tile: the store that last read it has to be through with it (64 channels: the
+        // previous item's tile x, one store group back; 72: the other query tile, the last group)
+        uint8_t* stile = sOut + (HD == 64 ? x * A::OUT_TILE : 0);
+        if (lane == 0) {
+          if constexpr (HD == 64) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+        __syncwarp();
+        const int r = qq * 32 + lane;
+        uint8_t* prow = stile + (r >> 3) * 1024 + (r & 7) * 128;
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           uint32_t tail[8];
@@ -327,7 +346,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             u.y = pack_bf16(__uint_as_float(ov[8 * c + 2]) * inv, __uint_as_float(ov[8 * c + 3]) * inv);
             u.z = pack_bf16(__uint_as_float(ov[8 * c + 4]) * inv, __uint_as_float(ov[8 * c + 5]) * inv);
             u.w = pack_bf16(__uint_as_float(ov[8 * c + 6]) * inv, __uint_as_float(ov[8 * c + 7]) * inv);
-            *reinterpret_cast<uint4*>(dst + half * 32 + 8 * c) = u;
+            *reinterpret_cast<uint4*>(prow + (((half * 4 + c) ^ (r & 7)) << 4)) = u;
           }
           if constexpr (HD != 64) {
             if (half == 1) {  // channels 64..71
@@ -336,12 +355,32 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
               u.y = pack_bf16(__uint_as_float(tail[2]) * inv, __uint_as_float(tail[3]) * inv);
               u.z = pack_bf16(__uint_as_float(tail[4]) * inv, __uint_as_float(tail[5]) * inv);
               u.w = pack_bf16(__uint_as_float(tail[6]) * inv, __uint_as_float(tail[7]) * inv);
-              *reinterpret_cast<uint4*>(dst + 64) = u;
+              *reinterpret_cast<uint4*>(sOut + A::OUT_TILE + r * 16) = u;
             }
           }
         }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          const int grow0 = n * tokens + pr * 2 * QT + x * QT + qq * 32;
+          if constexpr (HD == 64) {
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"((uint64_t)&tm_o),
+                         "r"(smem_u32(stile + qq * 4096)), "r"(h * HD), "r"(grow0)
+                         : "memory");
+          } else {
+            asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"((uint64_t)&tm_o),
+                         "r"(smem_u32(stile + qq * 4096)), "r"(0), "r"(h), "r"(grow0)
+                         : "memory");
+            asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"((uint64_t)&tm_o_tail),
+                         "r"(smem_u32(sOut + A::OUT_TILE + qq * 512)), "r"(64), "r"(h), "r"(grow0)
+                         : "memory");
+          }
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
       }
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // the stores complete before the CTA exits
+    __syncwarp();
   }
   tc_fence_before();
   __syncthreads();
@@ -359,7 +398,8 @@ extern "C" int mapdit_attn_debug_buffer(void* p) {  // developer hook: timeline 
 
 namespace {
 template <int HDV>
-int launch_attn_tc2(const CUtensorMap& tq, const CUtensorMap& tkv, void* o, float* lse, int n, int tokens, int heads, void* stream) {
+int launch_attn_tc2(const CUtensorMap& tq, const CUtensorMap& tkv, const CUtensorMap& to, const CUtensorMap& to_tail, float* lse, int n,
+                    int tokens, int heads, void* stream) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(attn_tc2_kernel<HDV>, cudaFuncAttributeMaxDynamicSharedMemorySize, ACfg<HDV>::SMEM_BYTES);
@@ -373,21 +413,27 @@ int launch_attn_tc2(const CUtensorMap& tq, const CUtensorMap& tkv, void* o, floa
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
   const int grid = items < sms ? items : sms;  // persistent, one CTA per SM (512 TMEM columns)
-  attn_tc2_kernel<HDV><<<grid, NTHREADS, ACfg<HDV>::SMEM_BYTES, (cudaStream_t)stream>>>(tq, tkv, (bf16*)o, lse, tokens, heads, n, g_attn_dbg);
+  attn_tc2_kernel<HDV><<<grid, NTHREADS, ACfg<HDV>::SMEM_BYTES, (cudaStream_t)stream>>>(tq, tkv, to, to_tail, lse, tokens, heads, n, g_attn_dbg);
   return MAPDIT_OK;
 }
 }  // namespace
 
 int mapdit_attn_tc2_fwd(const void* qkv, void* o, float* lse, int n, int tokens, int heads, int hd, void* stream) {
   const int D = heads * hd;
-  CUtensorMap tq, tkv;
-  CUresult r1, r2;
+  CUtensorMap tq, tkv, to, to_tail;  // to / to_tail: the output through per-warp TMA stores of 32-row slabs
+  CUresult r1, r2, r3, r4;
   if (hd == 64) {
     const uint64_t dims[2] = {(uint64_t)3 * D, (uint64_t)n * tokens};
     const uint64_t strides[1] = {(uint64_t)3 * D * 2};
     const uint32_t box_q[2] = {64, 2 * QT}, box_kv[2] = {64, KB};
     r1 = mapdit_encode_tmap(&tq, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, qkv, dims, strides, box_q, CU_TENSOR_MAP_SWIZZLE_128B);
     r2 = mapdit_encode_tmap(&tkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, qkv, dims, strides, box_kv, CU_TENSOR_MAP_SWIZZLE_128B);
+    const uint64_t odims[2] = {(uint64_t)D, (uint64_t)n * tokens};
+    const uint64_t ostrides[1] = {(uint64_t)D * 2};
+    const uint32_t box_o[2] = {64, 32};
+    r3 = mapdit_encode_tmap(&to, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, o, odims, ostrides, box_o, CU_TENSOR_MAP_SWIZZLE_128B);
+    r4 = r3;
+    to_tail = to;
   } else {
     // {channel within head, head of q|k|v, row}: a 64-channel box at channel 64 runs past the head's 72 channels and is zero-filled there
     const uint64_t dims[3] = {(uint64_t)hd, (uint64_t)3 * heads, (uint64_t)n * tokens};
@@ -395,12 +441,19 @@ int mapdit_attn_tc2_fwd(const void* qkv, void* o, float* lse, int n, int tokens,
     const uint32_t box_q[3] = {64, 1, QT}, box_kv[3] = {64, 1, KB};
     r1 = mapdit_encode_tmap(&tq, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, qkv, dims, strides, box_q, CU_TENSOR_MAP_SWIZZLE_128B);
     r2 = mapdit_encode_tmap(&tkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, qkv, dims, strides, box_kv, CU_TENSOR_MAP_SWIZZLE_128B);
+    // output {channel within head, head, row}: the 64-channel box of a 72-channel head is clipped by the store, the tail box adds 64..71
+    const uint64_t odims[3] = {(uint64_t)hd, (uint64_t)heads, (uint64_t)n * tokens};
+    const uint64_t ostrides[2] = {(uint64_t)hd * 2, (uint64_t)D * 2};
+    const uint32_t box_o[3] = {64, 1, 32}, box_t[3] = {8, 1, 32};
+    r3 = mapdit_encode_tmap(&to, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, o, odims, ostrides, box_o, CU_TENSOR_MAP_SWIZZLE_128B);
+    r4 = mapdit_encode_tmap(&to_tail, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, o, odims, ostrides, box_t, CU_TENSOR_MAP_SWIZZLE_NONE);
   }
-  if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) {
-    mapdit_set_error("attn_tc2_fwd: cuTensorMapEncodeTiled failed (%d, %d)", (int)r1, (int)r2);
+  if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS || r3 != CUDA_SUCCESS || r4 != CUDA_SUCCESS) {
+    mapdit_set_error("attn_tc2_fwd: cuTensorMapEncodeTiled failed (%d, %d, %d, %d)", (int)r1, (int)r2, (int)r3, (int)r4);
     return MAPDIT_ERR_CUDA;
   }
-  const int rc = hd == 64 ? launch_attn_tc2<64>(tq, tkv, o, lse, n, tokens, heads, stream) : launch_attn_tc2<72>(tq, tkv, o, lse, n, tokens, heads, stream);
+  const int rc = hd == 64 ? launch_attn_tc2<64>(tq, tkv, to, to_tail, lse, n, tokens, heads, stream)
+                           : launch_attn_tc2<72>(tq, tkv, to, to_tail, lse, n, tokens, heads, stream);
   if (rc != MAPDIT_OK) return rc;
   MAPDIT_LAUNCH_CHECK("attn_tc2_fwd");
   return MAPDIT_OK;
