@@ -49,7 +49,16 @@ __device__ __forceinline__ void store_row_sw128(uint8_t* tile, int r, const uint
   for (int c = 0; c < 8; ++c)
     *reinterpret_cast<uint4*>(prow + ((c ^ (r & 7)) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
 }
-__device__ __forceinline__ void store_out_row(bf16* dst, const uint32_t (&a)[32], const uint32_t (&b)[32], float sc) {
+// Where a finished gradient row of the dq / dkv kernels goes: row r of a shared-memory tile laid out like the TMA operand tiles (64-channel
+// SWIZZLE_128B panels; chunk = 8 channels = 16 bytes), from which each warp's 32-row slab leaves by TMA store.  (Row-per-thread 16-byte
+// global stores are 32 line transactions per instruction: the read-out was bound by them.)
+struct RowOut {
+  uint8_t* p0;  // row r of panel 0
+  uint8_t* p1;  // row r of panel 1 (head_dim 72: channels 64..71)
+  int sw;       // r & 7
+  __device__ __forceinline__ uint4* chunk(int c) const { return reinterpret_cast<uint4*>((c < 8 ? p0 : p1) + (((c & 7) ^ sw) << 4)); }
+};
+__device__ __forceinline__ void store_out_row(const RowOut& dst, const uint32_t (&a)[32], const uint32_t (&b)[32], float sc) {
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     uint4 u;
@@ -57,7 +66,7 @@ __device__ __forceinline__ void store_out_row(bf16* dst, const uint32_t (&a)[32]
     u.y = pack_bf16(__uint_as_float(a[8 * c + 2]) * sc, __uint_as_float(a[8 * c + 3]) * sc);
     u.z = pack_bf16(__uint_as_float(a[8 * c + 4]) * sc, __uint_as_float(a[8 * c + 5]) * sc);
     u.w = pack_bf16(__uint_as_float(a[8 * c + 6]) * sc, __uint_as_float(a[8 * c + 7]) * sc);
-    *reinterpret_cast<uint4*>(dst + 8 * c) = u;
+    *dst.chunk(c) = u;
   }
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
@@ -66,14 +75,14 @@ __device__ __forceinline__ void store_out_row(bf16* dst, const uint32_t (&a)[32]
     u.y = pack_bf16(__uint_as_float(b[8 * c + 2]) * sc, __uint_as_float(b[8 * c + 3]) * sc);
     u.z = pack_bf16(__uint_as_float(b[8 * c + 4]) * sc, __uint_as_float(b[8 * c + 5]) * sc);
     u.w = pack_bf16(__uint_as_float(b[8 * c + 6]) * sc, __uint_as_float(b[8 * c + 7]) * sc);
-    *reinterpret_cast<uint4*>(dst + 32 + 8 * c) = u;
+    *dst.chunk(4 + c) = u;
   }
 }
 
 // dq / dk epilogue with the backward of the q/k L2 normalisation fused in (src/layers/attention.py:43-45; closed form in
 // backward.cu qk_norm_bwd): the thread owns the whole 64-channel gradient row G = acc * att_scale of the NORMALISED head
 // y = sqrt(hd) v / (r + eps); with s = sqrt(hd)/(r+eps) saved by the forward, dv = s (G - y (y.G)(r+eps)/(hd r)).
-__device__ __forceinline__ void store_out_row_qknorm(bf16* dst, const bf16* __restrict__ yrow, const uint32_t (&a)[32],
+__device__ __forceinline__ void store_out_row_qknorm(const RowOut& dst, const bf16* __restrict__ yrow, const uint32_t (&a)[32],
                                                      const uint32_t (&b)[32], float att_scale, float s, float eps) {
   float y[64];
 #pragma unroll
@@ -102,7 +111,7 @@ __device__ __forceinline__ void store_out_row_qknorm(bf16* dst, const bf16* __re
     u.y = pack_bf16(fmaf(ga, __uint_as_float(a[8 * c + 2]), -s * coef * y[8 * c + 2]), fmaf(ga, __uint_as_float(a[8 * c + 3]), -s * coef * y[8 * c + 3]));
     u.z = pack_bf16(fmaf(ga, __uint_as_float(a[8 * c + 4]), -s * coef * y[8 * c + 4]), fmaf(ga, __uint_as_float(a[8 * c + 5]), -s * coef * y[8 * c + 5]));
     u.w = pack_bf16(fmaf(ga, __uint_as_float(a[8 * c + 6]), -s * coef * y[8 * c + 6]), fmaf(ga, __uint_as_float(a[8 * c + 7]), -s * coef * y[8 * c + 7]));
-    *reinterpret_cast<uint4*>(dst + 8 * c) = u;
+    *dst.chunk(c) = u;
   }
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
@@ -111,7 +120,7 @@ __device__ __forceinline__ void store_out_row_qknorm(bf16* dst, const bf16* __re
     u.y = pack_bf16(fmaf(ga, __uint_as_float(b[8 * c + 2]), -s * coef * y[32 + 8 * c + 2]), fmaf(ga, __uint_as_float(b[8 * c + 3]), -s * coef * y[32 + 8 * c + 3]));
     u.z = pack_bf16(fmaf(ga, __uint_as_float(b[8 * c + 4]), -s * coef * y[32 + 8 * c + 4]), fmaf(ga, __uint_as_float(b[8 * c + 5]), -s * coef * y[32 + 8 * c + 5]));
     u.w = pack_bf16(fmaf(ga, __uint_as_float(b[8 * c + 6]), -s * coef * y[32 + 8 * c + 6]), fmaf(ga, __uint_as_float(b[8 * c + 7]), -s * coef * y[32 + 8 * c + 7]));
-    *reinterpret_cast<uint4*>(dst + 32 + 8 * c) = u;
+    *dst.chunk(4 + c) = u;
   }
 }
 
@@ -160,9 +169,26 @@ __device__ __forceinline__ void load_tile(uint8_t* dst, const CUtensorMap* m, ui
     for (int p = 0; p < 2; ++p) tma_load_3d(dst + p * panel_bytes, m, bar, 64 * p, part * heads + h, row);
   }
 }
+// one warp's 32-row slab (rows 32 qq ..) of a staging tile -> global by TMA store, one bulk group.  The map's box is {64 channels, (1
+// head,) 32 rows}; at head_dim 72 the second panel's box starts at channel 64 and the store clips it at the head's 72 channels.
+template <int HDV>
+__device__ __forceinline__ void store_slab(const CUtensorMap* m, const uint8_t* tile, int qq, int part, int h, int heads, int row, int panel_bytes) {
+  if constexpr (HDV == 64) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"((uint64_t)m),
+                 "r"(smem_u32(tile + qq * 4096)), "r"(part * heads * 64 + h * 64), "r"(row)
+                 : "memory");
+  } else {
+#pragma unroll
+    for (int p = 0; p < 2; ++p)
+      asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"((uint64_t)m),
+                   "r"(smem_u32(tile + p * panel_bytes + qq * 4096)), "r"(64 * p), "r"(part * heads + h), "r"(row)
+                   : "memory");
+  }
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
 // accumulator row (a | b | tail: NACC fp32) of thread = row -> HDV bf16, scaled
 template <int HDV>
-__device__ __forceinline__ void store_acc_row(bf16* dst, const uint32_t (&a)[32], const uint32_t (&b)[32], const uint32_t (&t)[8], float sc) {
+__device__ __forceinline__ void store_acc_row(const RowOut& dst, const uint32_t (&a)[32], const uint32_t (&b)[32], const uint32_t (&t)[8], float sc) {
   store_out_row(dst, a, b, sc);
   if constexpr (HDV != 64) {
     uint4 u;
@@ -170,11 +196,11 @@ __device__ __forceinline__ void store_acc_row(bf16* dst, const uint32_t (&a)[32]
     u.y = pack_bf16(__uint_as_float(t[2]) * sc, __uint_as_float(t[3]) * sc);
     u.z = pack_bf16(__uint_as_float(t[4]) * sc, __uint_as_float(t[5]) * sc);
     u.w = pack_bf16(__uint_as_float(t[6]) * sc, __uint_as_float(t[7]) * sc);
-    *reinterpret_cast<uint4*>(dst + 64) = u;
+    *dst.chunk(8) = u;
   }
 }
 // the same with the backward of the q/k L2 normalisation (see store_out_row_qknorm) for a 72-channel head
-__device__ __forceinline__ void store_acc_row_qknorm72(bf16* dst, const bf16* __restrict__ yrow, const uint32_t (&a)[32], const uint32_t (&b)[32],
+__device__ __forceinline__ void store_acc_row_qknorm72(const RowOut& dst, const bf16* __restrict__ yrow, const uint32_t (&a)[32], const uint32_t (&b)[32],
                                                        const uint32_t (&t)[8], float att_scale, float s, float eps) {
   float dot = 0.f;
 #pragma unroll
@@ -208,7 +234,7 @@ __device__ __forceinline__ void store_acc_row_qknorm72(bf16* dst, const bf16* __
       const float g1 = __uint_as_float(i + 1 < 32 ? a[(i + 1) & 31] : (i + 1 < 64 ? b[(i + 1) & 31] : t[(i + 1) & 7]));
       w[e] = pack_bf16(fmaf(ga, g0, sc_y * y2.x), fmaf(ga, g1, sc_y * y2.y));
     }
-    *reinterpret_cast<uint4*>(dst + 8 * c) = make_uint4(w[0], w[1], w[2], w[3]);
+    *dst.chunk(c) = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
@@ -256,8 +282,8 @@ __device__ __forceinline__ void tile_to_tmem(uint32_t taddr, const uint8_t* tile
 template <int HDV>
 __global__ void __launch_bounds__(BCfg<HDV>::NTHR, 1)
 attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_constant__ CUtensorMap tm_qkv_blk,
-               const __grid_constant__ CUtensorMap tm_do_row, const float* __restrict__ lse, const float* __restrict__ delta,
-               bf16* __restrict__ dqkv, int tokens, int heads, int n_samples,
+               const __grid_constant__ CUtensorMap tm_do_row, const __grid_constant__ CUtensorMap tm_out, const float* __restrict__ lse,
+               const float* __restrict__ delta, int tokens, int heads, int n_samples,
                const bf16* __restrict__ qkv, const float* __restrict__ sc, float eps, long long* __restrict__ dbg) {
   using B = BCfg<HDV>;
   // optional timeline of CTA 0 (tools/attn_bwd_xl_timeline.py): dbg[role*256 + 4*g + e] = clock64 at event e of the CTA's g-th key
@@ -305,6 +331,7 @@ attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_cons
     prefetch_tmap(&tm_qkv_row);
     prefetch_tmap(&tm_qkv_blk);
     prefetch_tmap(&tm_do_row);
+    prefetch_tmap(&tm_out);
     mbar_init(bar_q, 1);
     for (int i = 0; i < NST; ++i) {
       mbar_init(&kv_full[i], 1);
@@ -430,7 +457,17 @@ attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_cons
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(a_full);
+        // the staging tiles are free for the producer again -- except that the first four warps put the current item's dQ into the
+        // Q tile next and release it when their TMA store has read it (`release_out`)
+        if (h0 == 1 || it == 0) mbar_arrive(stage_free);
+      }
+    };
+    bool out_pending = false;  // lane 0 of the first four warps: a dQ slab store of this thread may still be reading the staging tile
+    auto release_out = [&]() {
+      if (out_pending) {
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         mbar_arrive(stage_free);
+        out_pending = false;
       }
     };
     // delta_i = dO_i . O_i (attn_delta_kernel) and L_i of this thread's row, requested one item ahead
@@ -482,6 +519,7 @@ attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_cons
         __syncwarp();
         if (lane == 0) mbar_arrive(&ds_full[b]);
         if (warp == 2) DQ_STAMP(1, g, 3);
+        if (j == 0) release_out();  // the previous item's dQ store has long read its slab by now
       }
       // the item's last S / dP MMAs have completed (we saw its last s_full): the A tiles may take the next item's rows.  Ahead of
       // the read-out below, so that the tensor core has S / dP of the next item's first blocks to do meanwhile.
@@ -500,8 +538,11 @@ attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_cons
         __syncwarp();
         if (lane == 0) mbar_arrive(acc_free);
         if (warp == 2 && it < 16) DQ_STAMP(3, it, 1);
+        // the row goes into the (free again) Q staging tile, the warp's 32-row slab from there to dqkv by TMA.  row_ok is uniform over
+        // a warp (tokens % 64 == 0): slabs past the sample's end are not stored.
         if (row_ok) {
-          bf16* dst = dqkv + grow * 3 * D + h * HDV;
+          uint8_t* prow = sQ + (r >> 3) * 1024 + (r & 7) * 128;
+          const RowOut dst{prow, prow + PROW, r & 7};
           if constexpr (HDV == 64) {
             if (sc) store_out_row_qknorm(dst, qkv + grow * 3 * D + h * HDV, a0, a1, 0.125f, sc[grow * 2 * heads + h], eps);
             else store_out_row(dst, a0, a1, 0.125f);
@@ -510,10 +551,20 @@ attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_cons
             else store_acc_row<HDV>(dst, a0, a1, tl, att_scale_of(HDV));
           }
         }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          if (row_ok) {
+            store_slab<HDV>(&tm_out, sQ, qq, 0, h, heads, row_base + q0 + qq * 32, PROW);
+            out_pending = true;
+          }
+          if (!row_ok && it + 1 < my_items) mbar_arrive(stage_free);
+        }
         if (warp == 2 && it < 16) DQ_STAMP(3, it, 2);
       }
     }
   }
+  if (warp >= 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // the stores complete before the CTA exits
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<B::TMEM>(tmem_base);
@@ -526,9 +577,9 @@ attn_bwd_dq_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_cons
 template <int HDV>
 __global__ void __launch_bounds__(BCfg<HDV>::NTHR, 1)
 attn_bwd_dkv_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_constant__ CUtensorMap tm_qkv_blk,
-                const __grid_constant__ CUtensorMap tm_do_blk, const float* __restrict__ lse, const float* __restrict__ delta,
-                bf16* __restrict__ dqkv, int tokens, int heads, int n_samples, const bf16* __restrict__ qkv, const float* __restrict__ sc,
-                float eps, long long* __restrict__ dbg) {
+                const __grid_constant__ CUtensorMap tm_do_blk, const __grid_constant__ CUtensorMap tm_out, const float* __restrict__ lse,
+                const float* __restrict__ delta, int tokens, int heads, int n_samples, const bf16* __restrict__ qkv,
+                const float* __restrict__ sc, float eps, long long* __restrict__ dbg) {
   using B = BCfg<HDV>;
   // optional timeline of CTA 0, roles 4..7 of the buffer (see attn_bwd_dq_tc)
 #define DKV_STAMP(role, g, e)                                                                                             \
@@ -574,6 +625,7 @@ attn_bwd_dkv_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_con
     prefetch_tmap(&tm_qkv_row);
     prefetch_tmap(&tm_qkv_blk);
     prefetch_tmap(&tm_do_blk);
+    prefetch_tmap(&tm_out);
     mbar_init(bar_kv, 1);
     for (int i = 0; i < NST; ++i) {
       mbar_init(&qd_full[i], 1);
@@ -697,7 +749,17 @@ attn_bwd_dkv_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_con
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(a_full);
+        // the staging tiles take the current item's dK (K tile) and dV (V tile) next: released to the producer when the TMA stores
+        // have read them (`release_out`)
+        if (it == 0) mbar_arrive(stage_free);
+      }
+    };
+    bool out_pending = false;  // lane 0: a slab store of this thread may still be reading the staging tile
+    auto release_out = [&]() {
+      if (out_pending) {
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         mbar_arrive(stage_free);
+        out_pending = false;
       }
     };
     // per-query L (threads 0-63) and delta (64-127) of a block: 64 different lines of global memory each.  The values of the CTA's next
@@ -759,6 +821,7 @@ attn_bwd_dkv_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_con
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[b]);
         if (warp == 2) DKV_STAMP(1, g, 3);
+        if (j == 0) release_out();  // the previous item's dK / dV store has long read its slab by now
       }
       // the item's last S^T / dP^T MMAs have completed: the A tiles may take the next item's rows, ahead of the read-out below
       if (it + 1 < my_items) rows_to_tmem(it + 1);
@@ -777,20 +840,38 @@ attn_bwd_dkv_tc(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_con
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_free);
       if (warp == 2 && it < 16) DKV_STAMP(3, it, 1);
-      if (row_ok && h0 == 0) {
-        bf16* dst = dqkv + grow * 3 * D + D + h * HDV;
-        if constexpr (HDV == 64) {
-          if (sc) store_out_row_qknorm(dst, qkv + grow * 3 * D + D + h * HDV, a0, a1, 0.125f, sc[grow * 2 * heads + heads + h], eps);
-          else store_out_row(dst, a0, a1, 0.125f);
+      // rows go into the (free again) staging tiles -- dK over the K tile, dV over the V tile -- and each warp's 32-row slab from there to
+      // dqkv by TMA.  row_ok is uniform over a warp (tokens % 64 == 0): slabs past the sample's end are not stored.
+      uint8_t* stile = h0 == 0 ? sK : sV;
+      if (row_ok) {
+        uint8_t* prow = stile + (r >> 3) * 1024 + (r & 7) * 128;
+        const RowOut dst{prow, prow + PROW, r & 7};
+        if (h0 == 0) {
+          if constexpr (HDV == 64) {
+            if (sc) store_out_row_qknorm(dst, qkv + grow * 3 * D + D + h * HDV, a0, a1, 0.125f, sc[grow * 2 * heads + heads + h], eps);
+            else store_out_row(dst, a0, a1, 0.125f);
+          } else {
+            if (sc) store_acc_row_qknorm72(dst, qkv + grow * 3 * D + D + h * HDV, a0, a1, tl, att_scale_of(HDV), sc[grow * 2 * heads + heads + h], eps);
+            else store_acc_row<HDV>(dst, a0, a1, tl, att_scale_of(HDV));
+          }
         } else {
-          if (sc) store_acc_row_qknorm72(dst, qkv + grow * 3 * D + D + h * HDV, a0, a1, tl, att_scale_of(HDV), sc[grow * 2 * heads + heads + h], eps);
-          else store_acc_row<HDV>(dst, a0, a1, tl, att_scale_of(HDV));
+          store_acc_row<HDV>(dst, a0, a1, tl, 1.0f);
         }
       }
-      if (row_ok && h0 == 1) store_acc_row<HDV>(dqkv + grow * 3 * D + 2 * D + h * HDV, a0, a1, tl, 1.0f);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        if (row_ok) {
+          store_slab<HDV>(&tm_out, stile, qq, h0 == 0 ? 1 : 2, h, heads, row_base + k0 + qq * 32, PROW);
+          out_pending = true;
+        } else if (it + 1 < my_items) {
+          mbar_arrive(stage_free);
+        }
+      }
       if (warp == 2 && it < 16) DKV_STAMP(3, it, 2);
     }
   }
+  if (warp >= 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // the stores complete before the CTA exits
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<B::TMEM>(tmem_base);
@@ -2202,8 +2283,9 @@ static int attn_bwd_pair72(const void* qkv, const void* o, const void* dout, con
     const uint32_t box[3] = {64, 1, box_rows};
     return (int)mapdit_encode_tmap(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
   };
-  CUtensorMap t_qkv_row, t_qkv_blk, t_do_row, t_do_blk;
-  if (enc(&t_qkv_row, qkv, 3 * heads, RT) | enc(&t_qkv_blk, qkv, 3 * heads, CB) | enc(&t_do_row, dout, heads, RT) | enc(&t_do_blk, dout, heads, CB)) {
+  CUtensorMap t_qkv_row, t_qkv_blk, t_do_row, t_do_blk, t_out;  // t_out: dqkv in 32-row slabs (per-warp TMA stores of the read-out)
+  if (enc(&t_qkv_row, qkv, 3 * heads, RT) | enc(&t_qkv_blk, qkv, 3 * heads, CB) | enc(&t_do_row, dout, heads, RT) | enc(&t_do_blk, dout, heads, CB) |
+      enc(&t_out, dqkv, 3 * heads, 32)) {
     mapdit_set_error("cos_attn_bwd(hd 72): cuTensorMapEncodeTiled failed");
     return MAPDIT_ERR_CUDA;
   }
@@ -2221,10 +2303,10 @@ static int attn_bwd_pair72(const void* qkv, const void* o, const void* dout, con
   const int grid = pair_grid(tokens, heads, n_samples);  // persistent: one CTA per SM over (row tile, head, sample) items
   launch_delta<72>(o, dout, delta, (long long)rows * heads, s);
   MAPDIT_LAUNCH_CHECK("cos_attn_bwd(delta, hd 72)");
-  attn_bwd_dq_tc<72><<<grid, BCfg<72>::NTHR, BCfg<72>::DQ_SMEM, s>>>(t_qkv_row, t_qkv_blk, t_do_row, lse, delta, (bf16*)dqkv, tokens, heads,
+  attn_bwd_dq_tc<72><<<grid, BCfg<72>::NTHR, BCfg<72>::DQ_SMEM, s>>>(t_qkv_row, t_qkv_blk, t_do_row, t_out, lse, delta, tokens, heads,
                                                                    n_samples, (const bf16*)qkv, sc, eps, g_attn_dbg);
   MAPDIT_LAUNCH_CHECK("cos_attn_bwd(dq, hd 72)");
-  attn_bwd_dkv_tc<72><<<grid, BCfg<72>::NTHR, BCfg<72>::DKV_SMEM, s>>>(t_qkv_row, t_qkv_blk, t_do_blk, lse, delta, (bf16*)dqkv, tokens, heads,
+  attn_bwd_dkv_tc<72><<<grid, BCfg<72>::NTHR, BCfg<72>::DKV_SMEM, s>>>(t_qkv_row, t_qkv_blk, t_do_blk, t_out, lse, delta, tokens, heads,
                                                                      n_samples, (const bf16*)qkv, sc, eps, g_attn_dbg);
   MAPDIT_LAUNCH_CHECK("cos_attn_bwd(dkv, hd 72)");
   return MAPDIT_OK;
@@ -2327,10 +2409,15 @@ static int attn_bwd_impl(const void* qkv, const void* o, const void* dout, const
   const int grid = pair_grid(tokens, heads, n_samples);
   launch_delta<64>(o, dout, delta, (long long)rows * heads, s);
   MAPDIT_LAUNCH_CHECK("cos_attn_bwd(delta)");
-  attn_bwd_dq_tc<64><<<grid, BCfg<64>::NTHR, BCfg<64>::DQ_SMEM, s>>>(t_qkv_row, t_qkv_blk, t_do_row, lse, delta, (bf16*)dqkv, tokens, heads,
+  CUtensorMap t_slab;  // dqkv in 32-row slabs (per-warp TMA stores of the read-out)
+  if (encode2d(&t_slab, dqkv, 3 * D, rows, 3 * D, 32) != 0) {
+    mapdit_set_error("cos_attn_bwd: cuTensorMapEncodeTiled failed");
+    return MAPDIT_ERR_CUDA;
+  }
+  attn_bwd_dq_tc<64><<<grid, BCfg<64>::NTHR, BCfg<64>::DQ_SMEM, s>>>(t_qkv_row, t_qkv_blk, t_do_row, t_slab, lse, delta, tokens, heads,
                                                                    n_samples, (const bf16*)qkv, sc, eps, g_attn_dbg);
   MAPDIT_LAUNCH_CHECK("cos_attn_bwd(dq)");
-  attn_bwd_dkv_tc<64><<<grid, BCfg<64>::NTHR, BCfg<64>::DKV_SMEM, s>>>(t_qkv_row, t_qkv_blk, t_do_blk, lse, delta, (bf16*)dqkv, tokens, heads,
+  attn_bwd_dkv_tc<64><<<grid, BCfg<64>::NTHR, BCfg<64>::DKV_SMEM, s>>>(t_qkv_row, t_qkv_blk, t_do_blk, t_slab, lse, delta, tokens, heads,
                                                                      n_samples, (const bf16*)qkv, sc, eps, g_attn_dbg);
   MAPDIT_LAUNCH_CHECK("cos_attn_bwd(dkv)");
   return MAPDIT_OK;
