@@ -347,9 +347,15 @@ def kernel_roofline(model, B, pk):
                                  ldmod=6 * D, ldrot=D, tokens=T)
         return ops.gemm_bf16(a, w, x, epilogue=_lib.EPI_RESID_MOD, out2=h, resid=x, gate=mods, shift=mods[:, D:], scale=mods[:, 2 * D:],
                              gain=gain, ldmod=6 * D, tokens=T)
+    # attention backward (delta pre-kernel + the fused kernel of the 256-token models, or the dq / dkv kernel pair): 5 GEMMs of algorithmic work
+    dO, dqkv = mk(M, D), torch.empty(M, 3 * D, device=dev, dtype=torch.bfloat16)
+    lse, delta = torch.empty(M, H, device=dev), torch.empty(M, H, device=dev)
+    ops.cos_attn(qkv, o, B, T, H, D // H, lse=lse)
+    o_saved = o.clone()
     cases = {
         "qkv_gemm_qknorm": (lambda: ops.gemm_bf16(h, wqkv, qkv, epilogue=_lib.EPI_QKNORM, tokens=T, head_dim=D // H, qk_cols=2 * D), 2 * M * D * 3 * D),
         "attn": (lambda: ops.cos_attn(qkv, o, B, T, H, D // H), 4 * M * T * D),
+        "attn_bwd": (lambda: ops.cos_attn_bwd(qkv, o_saved, dO, lse, dqkv, delta, B, T, H, D // H), 10 * M * T * D),
         "out_gemm_resid_mod": (lambda: resid_mod(o, wo), 2 * M * D * D),
         "fc1_gemm_mpsilu": (lambda: ops.gemm_bf16(h, w1, u4, epilogue=_lib.EPI_MPSILU), 2 * M * D * 4 * D),
         "fc2_gemm_resid_mod": (lambda: resid_mod(u4, w2), 2 * M * 4 * D * D),
