@@ -109,7 +109,8 @@ def lib():
         L.mapdit_rotmod_bwd_partials.restype = _i
         _lib = L
         for env, opt in (("MAPDIT_GEMM_2CTA", b"gemm_2cta"), ("MAPDIT_GEMM_2CTA_BN", b"gemm_2cta_bn"),
-                         ("MAPDIT_GEMM_FUSED_RESID", b"gemm_fused_resid")):  # developer A/B switches
+                         ("MAPDIT_GEMM_FUSED_RESID", b"gemm_fused_resid"), ("MAPDIT_ATTN_BWD_FUSED", b"attn_bwd_fused"),
+                         ("MAPDIT_ATTN_V2", b"attn_v2")):  # developer A/B switches
             if os.environ.get(env) is not None:
                 L.mapdit_set_option(opt, int(os.environ[env]))
     return _lib
