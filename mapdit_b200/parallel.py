@@ -46,10 +46,10 @@ class GradReducer:
         self.flat, self.slices, self.group = flat, list(slices), group
         self.compressed, self.compress = compressed, compress
         assert compressed is None or (compressed.numel() == flat.numel() and compress is not None)
-        self._works, self._done = [], set()
+        self._works, self._done, self._work_of = [], set(), {}
 
     def start_step(self):
-        self._works, self._done = [], set()
+        self._works, self._done, self._work_of = [], set(), {}
 
     def ready(self, i: int):
         _, w = world()
@@ -62,11 +62,23 @@ class GradReducer:
                 self.compress(buf, self.compressed[lo:hi])
                 buf = self.compressed[lo:hi]
             self._works.append(dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            self._work_of[i] = self._works[-1]
         self._done.add(i)
 
-    def finish(self):
+    def finish(self, wait: bool = True):
+        """launch whatever is left; `wait=False` leaves the waiting to `wait_bucket` (the optimiser then updates bucket i while
+        bucket i+1 is still being reduced)"""
         for i in range(len(self.slices)):
             self.ready(i)
-        for wk in self._works:
+        if wait:
+            for wk in self._works:
+                wk.wait()
+            self._works, self._work_of = [], {}
+
+    def wait_bucket(self, i: int):
+        """the current stream waits for bucket i's all-reduce (no-op for one rank or an already awaited bucket)"""
+        wk = self._work_of.pop(i, None)
+        if wk is not None:
             wk.wait()
-        self._works = []
+        if not self._work_of:
+            self._works = []

@@ -94,7 +94,7 @@ class TrainStep:
             if gi < len(self.slices) - 1 and gi == self._last_group_of_bucket[b]:
                 self.reducer.ready(b)
 
-    def compute_grads(self, x, t, y, noise=None, drop_mask=None, loss_divisor=None, reduce=True):
+    def compute_grads(self, x, t, y, noise=None, drop_mask=None, loss_divisor=None, reduce=True, _defer_wait=False):
         """q_sample -> forward -> loss -> backward (-> all-reduce) of the local batch into the flat gradient span `flat_g`
         (train.py:86-95); returns the per-sample losses [N].  `loss_divisor` (default: the local batch size, i.e. loss.mean())
         is what the per-sample losses are divided by before the backward — shard gradients taken with the GLOBAL batch size
@@ -125,7 +125,7 @@ class TrainStep:
                     ops.loss_fwd_bwd(out, x0, x_t, noise, tl, tab, loss, None, None, dout, gs, gs)
                     tr.backward(saved, dout)
                     if reduce:
-                        self.reducer.finish()
+                        self.reducer.finish(wait=not _defer_wait)  # step(): apply_grads waits bucket by bucket
                     self._reduced = bool(reduce)
             finally:
                 tr.grad_buffers = None
@@ -140,18 +140,26 @@ class TrainStep:
         with torch.cuda.device(self.flat_p.device), torch.no_grad():
             lr = self.lr * (self.lr_lambda(self.step_count) if self.lr_lambda is not None else 1.0)
             self.step_count += 1
-            if self.flat_g16 is not None:
-                ops.adam_step_g16(self.flat_p, self.flat_g16, self.flat_m, self.flat_v, lr, self.betas[0], self.betas[1], self.eps,
-                                  self.step_count, grad_scale=1.0 / self.world)
-            else:
-                ops.adam_step(self.flat_p, self.flat_g, self.flat_m, self.flat_v, lr, self.betas[0], self.betas[1], self.eps,
-                              self.step_count, grad_scale=1.0 / self.world)
+            # one launch per reduce bucket, each behind its own all-reduce: the update of the first bucket (reduced long ago) runs while
+            # the last bucket is still on the wire.  One rank / buckets already awaited: the waits are no-ops.
+            spans = self.reducer.slices if self.world > 1 else [(0, self.flat_p.numel())]
+            for bi, (lo, hi) in enumerate(spans):
+                if hi <= lo:
+                    continue
+                if self.world > 1:
+                    self.reducer.wait_bucket(bi)
+                if self.flat_g16 is not None:
+                    ops.adam_step_g16(self.flat_p[lo:hi], self.flat_g16[lo:hi], self.flat_m[lo:hi], self.flat_v[lo:hi], lr, self.betas[0],
+                                      self.betas[1], self.eps, self.step_count, grad_scale=1.0 / self.world)
+                else:
+                    ops.adam_step(self.flat_p[lo:hi], self.flat_g[lo:hi], self.flat_m[lo:hi], self.flat_v[lo:hi], lr, self.betas[0],
+                                  self.betas[1], self.eps, self.step_count, grad_scale=1.0 / self.world)
             self.model.engine.invalidate()  # parameters moved through raw pointers: cached effective weights are stale
             if self.ema is not None:
                 self.ema.update(self.step_count, self.model)
 
     def step(self, x, t, y, noise=None, drop_mask=None):
         """one optimisation step on the local batch; returns the mean loss (device scalar)"""
-        loss = self.compute_grads(x, t, y, noise, drop_mask)
+        loss = self.compute_grads(x, t, y, noise, drop_mask, _defer_wait=True)
         self.apply_grads()
         return loss.mean()

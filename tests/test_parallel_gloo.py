@@ -50,6 +50,17 @@ def _worker(rank, world, port, out):
     red3.finish()
     ok &= bool(torch.equal(c16.float(), torch.arange(64, dtype=torch.float32) * sum(r + 1 for r in range(world))))
     ok &= bool(torch.equal(loc, torch.arange(64, dtype=torch.float32) * (rank + 1)))
+    # deferred waits (TrainStep.step: the optimiser updates bucket i behind its own all-reduce while bucket i+1 is on the wire)
+    f4 = torch.arange(40, dtype=torch.float32) * (rank + 1)
+    red4 = GradReducer(f4, [(0, 16), (16, 40)])
+    red4.start_step()
+    red4.ready(0)
+    red4.finish(wait=False)
+    red4.wait_bucket(0)
+    ok &= bool(torch.equal(f4[:16], torch.arange(16, dtype=torch.float32) * sum(r + 1 for r in range(world))))
+    red4.wait_bucket(1)
+    red4.wait_bucket(1)  # idempotent
+    ok &= bool(torch.equal(f4, torch.arange(40, dtype=torch.float32) * sum(r + 1 for r in range(world))))
     # final gather is rank-major
     s = gather_samples(torch.full((2, 3), float(rank)))
     ok &= s.shape == (2 * world, 3) and bool((s[:2] == 0).all()) and bool((s[2:4] == 1).all())

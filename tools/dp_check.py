@@ -62,7 +62,7 @@ def main():
         ts = TrainStep(m, M.create_diffusion(""), world_size=w)
         if w == 1:
             ts.reducer.ready = lambda i: None   # single-process replay on a multi-rank job: no collective
-            ts.reducer.finish = lambda: None
+            ts.reducer.finish = lambda wait=True: None
         losses = []
         for k in range(2):
             losses.append(ts.step(x[sl].to(dev), t[sl].to(dev), y[sl].to(dev), noise[k, sl].to(dev), drop_mask=drop[sl].to(dev)))
