@@ -31,6 +31,21 @@ def gather_samples(local: torch.Tensor, group=None) -> torch.Tensor:
     return torch.cat(outs, dim=0)
 
 
+def bucket_plan(n_groups: int, blocks_per_bucket: int):
+    """Which reduce bucket each gradient group goes into.  Groups 0 .. n_groups-2 are the blocks in backward order, the last group
+    holds the embedders / final layer.  `blocks_per_bucket` consecutive blocks share a bucket and the last group joins the last
+    bucket; 1 keeps the last group in a bucket of its own (one bucket per block); <= 0 puts everything into one bucket.
+    Returns (bucket_of_group, last_group_of_bucket): a bucket is complete when its last group has reported."""
+    if n_groups <= 1 or blocks_per_bucket <= 0:
+        bog = [0] * n_groups
+    else:
+        bog = [min(gi, n_groups - 2) // blocks_per_bucket for gi in range(n_groups)]
+        if blocks_per_bucket == 1:
+            bog[n_groups - 1] = bog[n_groups - 2] + 1
+    nb = (max(bog) + 1) if bog else 0
+    return bog, [max(gi for gi in range(n_groups) if bog[gi] == b) for b in range(nb)]
+
+
 class GradReducer:
     """Bucketed, overlapped gradient all-reduce over a flat buffer.
 

@@ -10,7 +10,7 @@ the backward finishes them (last block first), so each block's gradient slice is
 import torch
 
 from . import ops
-from .parallel import GradReducer
+from .parallel import GradReducer, bucket_plan
 
 
 class TrainStep:
@@ -71,16 +71,11 @@ class TrainStep:
         # every NCCL kernel that starts mid-backward takes SMs from the persistent GEMM it lands on (whose CTAs then run as a second
         # wave), so few large buckets beat many small ones: N = 4 on one box 43.5-43.7 ms against 43.9 with a bucket per block
         # and 43.8 with a single bucket at the end (N = 1: 42.6 ms); N = 2 on another box 43.3 against 43.5-44.4 (N = 1: 42.5).
-        bpb = int(os.environ.get("MAPDIT_DP_BLOCKS_PER_BUCKET", str(max(1, (len(self.slices) - 1 + 1) // 2))))
+        n_blocks = len(self.slices) - 1
+        bpb = int(os.environ.get("MAPDIT_DP_BLOCKS_PER_BUCKET", str(max(1, (n_blocks + 1) // 2))))
         ng = len(self.slices)
-        if bpb <= 0:
-            self._bucket_of_group = [0] * ng
-        else:
-            self._bucket_of_group = [min(gi, ng - 2) // bpb for gi in range(ng)] if ng > 1 else [0]
-            if bpb == 1:
-                self._bucket_of_group[ng - 1] = self._bucket_of_group[ng - 2] + 1 if ng > 1 else 0  # (the historical layout: own bucket)
-        nb = max(self._bucket_of_group) + 1
-        self._last_group_of_bucket = [max(gi for gi in range(ng) if self._bucket_of_group[gi] == b) for b in range(nb)]
+        self._bucket_of_group, self._last_group_of_bucket = bucket_plan(ng, bpb)
+        nb = len(self._last_group_of_bucket)
         bucket_slices = [(min(self.slices[gi][0] for gi in range(ng) if self._bucket_of_group[gi] == b),
                           max(self.slices[gi][1] for gi in range(ng) if self._bucket_of_group[gi] == b)) for b in range(nb)]
         self.reducer = GradReducer(self.flat_g, bucket_slices, compressed=self.flat_g16,

@@ -222,3 +222,21 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d["cpu_baseline"]["kind"] == ("reference" if have_ref else "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["sample50"]["value"] > 0 and d["sample50"]["cpu_baseline"]["kind"] == d["cpu_baseline"]["kind"]
+
+
+def test_gradient_bucket_plan():
+    """TrainStep's reduce buckets: every group in exactly one bucket, buckets are runs of consecutive groups in backward order, a
+    bucket's last group is the one whose completion launches its all-reduce"""
+    from mapdit_b200.parallel import bucket_plan
+    for ng in (1, 2, 3, 13, 29):
+        for bpb in (0, 1, 2, 3, 6, 7, 12, 100):
+            bog, last = bucket_plan(ng, bpb)
+            assert len(bog) == ng and bog[0] == 0 and all(0 <= bog[i + 1] - bog[i] <= 1 for i in range(ng - 1)), (ng, bpb, bog)
+            assert last == [max(i for i in range(ng) if bog[i] == b) for b in range(max(bog) + 1)] and last[-1] == ng - 1
+            if bpb <= 0 or ng == 1:
+                assert max(bog) == 0
+            elif bpb == 1:
+                assert bog == list(range(ng))  # the historical layout: a bucket per block, the embedders / final layer on their own
+            else:
+                assert all(bog.count(b) <= bpb + 1 for b in set(bog)) and bog[-1] == bog[-2]  # the last group joins the last bucket
+    assert bucket_plan(13, 6) == ([0] * 6 + [1] * 7, [5, 12])
